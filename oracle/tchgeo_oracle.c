@@ -1,0 +1,803 @@
+/*
+ * tchgeo_oracle.c -- CPU restatement of tch-geometric's mini-batch sampling hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under tch-geometric_b200/ may include, link or call this
+ * file.  It is used by tests/, by __graft_entry__.smoke() (as the checker) and by bench.py's
+ * cpu_baseline / --impl reference legs (as the timed CPU arm).  The product path is the CUDA
+ * library behind include/tchgeo_cuda.h and fails loudly when that library is missing.
+ *
+ * Every function cites the reference file:line (relative to the reference repo root) that it
+ * restates.  The reference is single-threaded CPU Rust; it cannot be built in this image (no
+ * cargo/rustc, and its `tch` dependency is an un-fetchable git fork, Cargo.toml:16), so this
+ * restatement is the oracle.
+ *
+ * Pinning status
+ *   - ind2ptr / to_csc / to_csr: PINNED against the reference's known-answer tests
+ *     (src/data/storage.rs:153-163 and :166-184) and the karate fixture; see tests/test_oracle.py.
+ *   - sampling / walks: the reference has NO golden sampled values (its tests are invariant-only,
+ *     src/algo/neighbor_sampling.rs:370-401, src/algo/random_walk.rs:322-330) and its Python entry
+ *     points seed from entropy (src/utils/random.rs:10).  The deterministic regime (fanout >=
+ *     degree) is pinned exactly; the stochastic regime is "parity unpinned" at the RNG-stream
+ *     level: rand 0.8.5 (SmallRng = xoshiro256++) is an un-vendored dependency (Cargo.lock:619),
+ *     restated here from its published algorithm (ORC_RNG_XOSHIRO) without a way to cross-check the
+ *     stream.  Distributional parity (the reference's *biased* reservoirs, quirks Q1/Q2) is what
+ *     the tests assert.
+ *
+ * Two RNG modes
+ *   ORC_RNG_XOSHIRO : sequential xoshiro256++ consumed in exactly the reference's order
+ *                     (faithful restatement; used for the CPU baseline timing and as the
+ *                     distributional reference).
+ *   ORC_RNG_COUNTER : the same serial algorithms, but every draw comes from Philox4x32-10 keyed by
+ *                     (seed) and indexed by (frontier position, draw index, batch, relation/tag),
+ *                     i.e. the counter layout documented in DESIGN.md "RNG contract".  The CUDA
+ *                     kernels use the identical layout, so GPU output must equal this mode
+ *                     BIT-EXACTLY even in the stochastic regime.  XOSHIRO-vs-COUNTER equivalence is
+ *                     tested statistically on the CPU.
+ */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <math.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_OK 0
+#define ORC_ERR_ARG 1
+#define ORC_ERR_CAPACITY 2
+#define ORC_ERR_PANIC 3 /* the reference would panic here (gen_range(0..0), OOB index, ...) */
+
+#define ORC_RNG_XOSHIRO 0
+#define ORC_RNG_COUNTER 1
+
+#define ORC_SAMPLER_UNIFORM 0          /* UnweightedSampler<false>, neighbor_sampling.rs:124-127 */
+#define ORC_SAMPLER_UNIFORM_REPLACE 1  /* UnweightedSampler<true>,  neighbor_sampling.rs:111-123 */
+#define ORC_SAMPLER_WEIGHTED 2         /* WeightedSampler,          neighbor_sampling.rs:141-158 */
+
+#define ORC_TAG_RESERVOIR 1u
+#define ORC_TAG_REPLACE 2u
+#define ORC_TAG_WEIGHTED 3u
+#define ORC_TAG_WALK 4u
+
+#define ORC_FILTER_NONE (-1)  /* IdentityFilter, neighbor_sampling.rs:22-30 */
+#define ORC_TEMPORAL_STATIC 0 /* neighbor_sampling.rs:32-34 */
+#define ORC_TEMPORAL_RELATIVE 1
+#define ORC_TEMPORAL_DYNAMIC 2
+
+/* ------------------------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al., SC'11; Random123).  Public algorithm; KATs in tests.         */
+/* ------------------------------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
+  uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+  uint32_t k0 = key[0], k1 = key[1];
+  for (int r = 0; r < 10; ++r) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* rand 0.8.5 restatement (un-vendored dependency; parity unpinned, see header)               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int mode;
+  uint64_t s[4];   /* xoshiro256++ state (ORC_RNG_XOSHIRO) */
+  uint32_t key[2]; /* philox key          (ORC_RNG_COUNTER) */
+} orc_rng;
+
+static inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+/* Xoshiro256PlusPlus::seed_from_u64: SplitMix64 expansion. */
+static void xoshiro_seed_from_u64(orc_rng* r, uint64_t state) {
+  for (int i = 0; i < 4; ++i) {
+    state += 0x9e3779b97f4a7c15ULL;
+    uint64_t z = state;
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+    r->s[i] = z ^ (z >> 31);
+  }
+}
+
+static inline uint64_t xoshiro_next_u64(orc_rng* r) {
+  uint64_t* s = r->s;
+  uint64_t result = rotl64(s[0] + s[3], 23) + s[0];
+  uint64_t t = s[1] << 17;
+  s[2] ^= s[0];
+  s[3] ^= s[1];
+  s[1] ^= s[2];
+  s[0] ^= s[3];
+  s[2] ^= t;
+  s[3] = rotl64(s[3], 45);
+  return result;
+}
+static inline uint32_t xoshiro_next_u32(orc_rng* r) { return (uint32_t)(xoshiro_next_u64(r) >> 32); }
+
+void orc_rng_init(orc_rng* r, int mode, uint64_t seed) {
+  r->mode = mode;
+  r->key[0] = (uint32_t)seed;
+  r->key[1] = (uint32_t)(seed >> 32);
+  xoshiro_seed_from_u64(r, seed); /* SmallRng::from_seed([0;32]) == seed_from_u64(0) */
+}
+
+/* UniformInt<u64>::sample_single: gen_range(0..range), widening multiply + rejection zone. */
+static inline uint64_t xoshiro_gen_range_u64(orc_rng* r, uint64_t range) {
+  int lz = __builtin_clzll(range);
+  uint64_t zone = (range << lz) - 1;
+  for (;;) {
+    uint64_t v = xoshiro_next_u64(r);
+    __uint128_t m = (__uint128_t)v * range;
+    uint64_t lo = (uint64_t)m;
+    if (lo <= zone) return (uint64_t)(m >> 64);
+  }
+}
+/* UniformFloat<f32>::sample_single for 0.0..1.0 */
+static inline float xoshiro_gen_f32(orc_rng* r) {
+  for (;;) {
+    uint32_t bits = (xoshiro_next_u32(r) >> 9) | 0x3F800000u;
+    float v12;
+    memcpy(&v12, &bits, 4);
+    float res = (v12 - 1.0f) * 1.0f + 0.0f;
+    if (res < 1.0f) return res;
+  }
+}
+/* UniformFloat<f64>::sample_single for 0.0..high */
+static inline double xoshiro_gen_f64(orc_rng* r, double high) {
+  for (;;) {
+    uint64_t bits = (xoshiro_next_u64(r) >> 12) | 0x3FF0000000000000ULL;
+    double v12;
+    memcpy(&v12, &bits, 8);
+    double res = (v12 - 1.0) * high + 0.0;
+    if (res < high) return res;
+  }
+}
+
+/* Draw context for ORC_RNG_COUNTER: identifies the frontier node the draws belong to. */
+typedef struct {
+  uint32_t pos;   /* index of the frontier node in its (dst-type) samples vector */
+  uint32_t batch; /* batch index */
+  uint32_t rel;   /* relation index (0 for homogeneous) */
+} orc_ctx;
+
+static inline uint32_t mulhi32(uint32_t a, uint32_t b) { return (uint32_t)(((uint64_t)a * b) >> 32); }
+
+static inline void counter_draw(const orc_rng* r, const orc_ctx* c, uint32_t block, uint32_t tag, uint32_t out[4]) {
+  uint32_t ctr[4] = {c->pos, block, c->batch, tag | (c->rel << 8)};
+  orc_philox4x32_10(ctr, r->key, out);
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A2: ind2ptr, src/data/storage.rs:67-101                                                    */
+/* ------------------------------------------------------------------------------------------ */
+int orc_ind2ptr(const int64_t* ind, int64_t numel, int64_t m, int64_t* out) {
+  if (numel == 0) { /* storage.rs:78-80 */
+    for (int64_t i = 0; i <= m; ++i) out[i] = 0;
+    return ORC_OK;
+  }
+  for (int64_t i = 0; i <= ind[0]; ++i) out[i] = 0; /* :82-84 */
+  int64_t idx = ind[0];
+  for (int64_t i = 0; i < numel - 1; ++i) { /* :87-94 */
+    int64_t next_idx = ind[i + 1];
+    for (int64_t j = idx; j < next_idx; ++j) out[j + 1] = i + 1;
+    idx = next_idx;
+  }
+  for (int64_t i = ind[numel - 1] + 1; i < m + 1; ++i) out[i] = numel; /* :96-98 */
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A1: COO -> CSC/CSR, src/data/storage.rs:103-127.                                           */
+/*   perm = argsort(col*size0 + row) (CSC) or argsort(row*size1 + col) (CSR); torch's argsort  */
+/*   is not stable, so among duplicate (row,col) pairs perm is unspecified (quirk Q9); this    */
+/*   restatement uses a stable LSD radix sort, one valid answer.                               */
+/* ------------------------------------------------------------------------------------------ */
+static void radix_argsort_u64(const uint64_t* keys, int64_t n, int64_t* perm, uint64_t max_key) {
+  int bits = 0;
+  while (bits < 64 && (max_key >> bits) != 0) ++bits;
+  if (bits == 0) bits = 1;
+  const int RB = 11, NB = 1 << RB;
+  int64_t* tmp = (int64_t*)malloc(sizeof(int64_t) * (size_t)(n > 0 ? n : 1));
+  int64_t* src = perm;
+  int64_t* dst = tmp;
+  for (int64_t i = 0; i < n; ++i) src[i] = i;
+  int64_t* cnt = (int64_t*)malloc(sizeof(int64_t) * NB);
+  for (int shift = 0; shift < bits; shift += RB) {
+    memset(cnt, 0, sizeof(int64_t) * NB);
+    for (int64_t i = 0; i < n; ++i) cnt[(keys[src[i]] >> shift) & (NB - 1)]++;
+    int64_t acc = 0;
+    for (int b = 0; b < NB; ++b) { int64_t c = cnt[b]; cnt[b] = acc; acc += c; }
+    for (int64_t i = 0; i < n; ++i) { int64_t p = src[i]; dst[cnt[(keys[p] >> shift) & (NB - 1)]++] = p; }
+    int64_t* t = src; src = dst; dst = t;
+  }
+  if (src != perm) memcpy(perm, src, sizeof(int64_t) * (size_t)n);
+  free(cnt);
+  free(tmp);
+}
+
+int orc_to_csx(const int64_t* row, const int64_t* col, int64_t E, int64_t size0, int64_t size1, int csc,
+               int64_t* ptrs, int64_t* indices, int64_t* perm) {
+  uint64_t* keys = (uint64_t*)malloc(sizeof(uint64_t) * (size_t)(E > 0 ? E : 1));
+  int64_t* sorted_major = (int64_t*)malloc(sizeof(int64_t) * (size_t)(E > 0 ? E : 1));
+  uint64_t max_key = 0;
+  for (int64_t e = 0; e < E; ++e) {
+    /* storage.rs:119 (CSC) / :112 (CSR) */
+    uint64_t k = csc ? (uint64_t)(col[e] * size0 + row[e]) : (uint64_t)(row[e] * size1 + col[e]);
+    keys[e] = k;
+    if (k > max_key) max_key = k;
+  }
+  radix_argsort_u64(keys, E, perm, max_key);
+  const int64_t* major = csc ? col : row;
+  const int64_t* minor = csc ? row : col;
+  for (int64_t e = 0; e < E; ++e) { /* col.i(&perm) / row.i(&perm), :120-121 */
+    sorted_major[e] = major[perm[e]];
+    indices[e] = minor[perm[e]];
+  }
+  orc_ind2ptr(sorted_major, E, csc ? size1 : size0, ptrs);
+  free(keys);
+  free(sorted_major);
+  return ORC_OK;
+}
+
+/* F2 (next row): csc_edge_cumsum, src/data/transform.rs:36-60 (f64 instantiation) */
+int orc_csc_edge_cumsum_f64(const int64_t* col_ptrs, int64_t n_cols, double* row_data) {
+  for (int64_t c = 0; c < n_cols; ++c) {
+    int64_t s = col_ptrs[c], e = col_ptrs[c + 1];
+    if (e - s <= 1) continue; /* transform.rs:46-48 */
+    double acc = 0.0;
+    for (int64_t p = s; p < e; ++p) { acc = acc + row_data[p]; row_data[p] = acc; }
+  }
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A3: graph view accessors, src/data/graph.rs:65-88                                          */
+/* ------------------------------------------------------------------------------------------ */
+static inline int has_edge(const int64_t* ptrs, const int64_t* indices, int64_t x, int64_t y) {
+  int64_t lo = ptrs[x], hi = ptrs[x + 1]; /* neighbors_slice(x).binary_search(&y), graph.rs:80-83 */
+  while (lo < hi) {
+    int64_t mid = lo + ((hi - lo) >> 1);
+    int64_t v = indices[mid];
+    if (v == y) return 1;
+    if (v < y) lo = mid + 1; else hi = mid;
+  }
+  return 0;
+}
+int orc_has_edge(const int64_t* ptrs, const int64_t* indices, int64_t x, int64_t y) { return has_edge(ptrs, indices, x, y); }
+
+/* ------------------------------------------------------------------------------------------ */
+/* A9: filters, src/algo/neighbor_sampling.rs:14-77                                           */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  int mode;    /* ORC_FILTER_NONE or ORC_TEMPORAL_* */
+  int forward; /* FORWARD const generic */
+  int64_t win_lo, win_hi; /* RangeInclusive window */
+  const int64_t* timestamps;
+} orc_filter;
+
+static inline int filter_pass(const orc_filter* f, int64_t state, int64_t edge_ptr) {
+  if (f->mode == ORC_FILTER_NONE) return 1;
+  int64_t t = f->timestamps[edge_ptr];
+  if (f->mode == ORC_TEMPORAL_STATIC) return f->win_lo <= t && t <= f->win_hi; /* :59 */
+  int64_t d = t - state;                                                        /* :60-65 */
+  if (!f->forward) d = -d;
+  return f->win_lo <= d && d <= f->win_hi;
+}
+static inline int64_t filter_mutate(const orc_filter* f, int64_t state, int64_t edge_ptr) {
+  if (f->mode == ORC_TEMPORAL_DYNAMIC) return f->timestamps[edge_ptr]; /* :73 */
+  return state;                                                        /* :71-72 */
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A4/A5/A6: sampling primitives, src/utils/sampling.rs:6-69, driven through the Sampler impls */
+/* at src/algo/neighbor_sampling.rs:93-158.  `dst` receives edge pointers (CSC positions).     */
+/* Returns the number of samples, or -1 where the reference panics.                            */
+/* ------------------------------------------------------------------------------------------ */
+static int64_t sample_reservoir(orc_rng* rng, const orc_ctx* ctx, const orc_filter* f, int64_t state,
+                                int64_t begin, int64_t end, int64_t k, int64_t* dst) {
+  /* reservoir_sampling, sampling.rs:6-26 */
+  int64_t n = 0, p = begin;
+  for (; p < end && n < k; ++p) { /* :12-15: zip(dst, src) fills the first k passing items */
+    if (!filter_pass(f, state, p)) continue;
+    dst[n++] = p;
+  }
+  int64_t i = n; /* :17 */
+  uint32_t buf[4];
+  for (; p < end; ++p) { /* :18-24 */
+    if (!filter_pass(f, state, p)) continue;
+    if (i == 0) return -1; /* gen_range(0..0) panics (k == 0) */
+    int64_t j;
+    if (rng->mode == ORC_RNG_XOSHIRO) {
+      j = (int64_t)xoshiro_gen_range_u64(rng, (uint64_t)i);
+    } else {
+      /* step i >= k uses word (i-k)&3 of block (i-k)>>2 */
+      uint32_t d = (uint32_t)(i - k);
+      if ((d & 3u) == 0u) counter_draw(rng, ctx, d >> 2, ORC_TAG_RESERVOIR, buf);
+      j = (int64_t)mulhi32(buf[d & 3u], (uint32_t)i);
+    }
+    if (j < k) dst[j] = p;
+    i += 1;
+  }
+  return n;
+}
+
+static int64_t sample_replace(orc_rng* rng, const orc_ctx* ctx, const orc_filter* f, int64_t state,
+                              int64_t begin, int64_t end, int64_t k, int64_t* dst, int64_t* scratch) {
+  /* UnweightedSampler<true>::sample, neighbor_sampling.rs:111-123: collect, then replacement_sampling
+   * (sampling.rs:57-69): exactly k iid picks, even when n < k (quirk Q3). */
+  int64_t n = 0;
+  for (int64_t p = begin; p < end; ++p)
+    if (filter_pass(f, state, p)) scratch[n++] = p;
+  if (n == 0) return 0;
+  uint32_t buf[4];
+  for (int64_t s = 0; s < k; ++s) {
+    int64_t j;
+    if (rng->mode == ORC_RNG_XOSHIRO) {
+      j = (int64_t)xoshiro_gen_range_u64(rng, (uint64_t)n);
+    } else {
+      if ((s & 3) == 0) counter_draw(rng, ctx, (uint32_t)(s >> 2), ORC_TAG_REPLACE, buf);
+      j = (int64_t)mulhi32(buf[s & 3], (uint32_t)n);
+    }
+    dst[s] = scratch[j];
+  }
+  return k;
+}
+
+static int64_t sample_weighted(orc_rng* rng, const orc_ctx* ctx, const orc_filter* f, int64_t state,
+                               const double* weights, int64_t begin, int64_t end, int64_t k, int64_t* dst) {
+  /* reservoir_sampling_weighted, sampling.rs:28-55 (quirk Q2: acceptance w/w_sum, uniform slot) */
+  int64_t n = 0, p = begin;
+  double w_sum = 0.0;
+  for (; p < end && n < k; ++p) { /* :37-45 */
+    if (!filter_pass(f, state, p)) continue;
+    dst[n++] = p;
+    w_sum = w_sum + weights[p];
+  }
+  int64_t item = n;
+  uint32_t buf[4];
+  for (; p < end; ++p) { /* :47-53 */
+    if (!filter_pass(f, state, p)) continue;
+    double w = weights[p];
+    w_sum = w_sum + w;
+    if (rng->mode == ORC_RNG_XOSHIRO) {
+      if (!(0.0 < w_sum)) return -1; /* gen_range on an empty range panics */
+      double j = xoshiro_gen_f64(rng, w_sum);
+      if (j < w) {
+        if (k == 0) return -1;
+        dst[xoshiro_gen_range_u64(rng, (uint64_t)k)] = p;
+      }
+    } else {
+      if (!(0.0 < w_sum) || k == 0) return -1;
+      counter_draw(rng, ctx, (uint32_t)item, ORC_TAG_WEIGHTED, buf);
+      uint64_t u53 = ((uint64_t)buf[0] << 21) | (uint64_t)(buf[1] >> 11);
+      double u = (double)u53 * (1.0 / 9007199254740992.0);
+      double j = u * w_sum;
+      if (j < w) dst[mulhi32(buf[2], (uint32_t)k)] = p;
+    }
+    item += 1;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* growable i64 vector mirroring Vec<i64>::push                                               */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int64_t* d; int64_t len, cap; int fixed; } vec64;
+static inline int vec_push(vec64* v, int64_t x) {
+  if (v->len == v->cap) {
+    if (v->fixed) return 0;
+    int64_t nc = v->cap ? v->cap * 2 : 4;
+    v->d = (int64_t*)realloc(v->d, sizeof(int64_t) * (size_t)nc);
+    v->cap = nc;
+  }
+  v->d[v->len++] = x;
+  return 1;
+}
+
+typedef struct {
+  int kind;
+  const double* weights;
+} orc_sampler;
+
+/* one frontier node: the per-node body shared by neighbor_sampling.rs:195-219 and :317-341 */
+static int sample_node(orc_rng* rng, const orc_ctx* ctx, const orc_sampler* smp, const orc_filter* flt,
+                       const int64_t* ptrs, const int64_t* indices, int64_t num_cols, int64_t w, int64_t w_state,
+                       int64_t k, int64_t* slots, int64_t** scratch, int64_t* scratch_cap, int64_t* n_out) {
+  if (w < 0 || w >= num_cols) return ORC_ERR_PANIC; /* slice index out of bounds (quirk Q10) */
+  int64_t begin = ptrs[w], end = ptrs[w + 1];
+  *n_out = 0;
+  if (begin >= end) return ORC_OK; /* :199-202, tested before filtering (quirk Q4) */
+  int64_t n;
+  switch (smp->kind) {
+    case ORC_SAMPLER_UNIFORM: n = sample_reservoir(rng, ctx, flt, w_state, begin, end, k, slots); break;
+    case ORC_SAMPLER_UNIFORM_REPLACE:
+      if (end - begin > *scratch_cap) {
+        *scratch_cap = (end - begin) * 2;
+        *scratch = (int64_t*)realloc(*scratch, sizeof(int64_t) * (size_t)*scratch_cap);
+      }
+      n = sample_replace(rng, ctx, flt, w_state, begin, end, k, slots, *scratch);
+      break;
+    case ORC_SAMPLER_WEIGHTED: n = sample_weighted(rng, ctx, flt, w_state, smp->weights, begin, end, k, slots); break;
+    default: return ORC_ERR_ARG;
+  }
+  if (n < 0) return ORC_ERR_PANIC;
+  *n_out = n;
+  return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A7: neighbor_sampling_homogenous, src/algo/neighbor_sampling.rs:162-230                    */
+/*   Outputs follow src/python.rs:259-270: samples, rows, cols, edge_index, layer_offsets.     */
+/*   Buffers are caller-provided with capacities; lengths are returned.                        */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct {
+  vec64 samples, states, rows, cols, eidx;
+} ns_out;
+
+static int ns_homogenous_core(orc_rng* rng, uint32_t batch, const int64_t* ptrs, const int64_t* indices,
+                              int64_t num_cols, const int64_t* inputs, int64_t num_inputs,
+                              const int64_t* num_neighbors, int num_hops, const orc_sampler* smp,
+                              const orc_filter* flt, const int64_t* inputs_state, ns_out* o,
+                              int64_t* layer_offsets /* [num_hops*3] */) {
+  int track_state = flt->mode != ORC_FILTER_NONE;
+  for (int64_t i = 0; i < num_inputs; ++i) { /* :184-185 */
+    if (!vec_push(&o->samples, inputs[i])) return ORC_ERR_CAPACITY;
+    if (track_state) vec_push(&o->states, inputs_state[i]);
+  }
+  int64_t begin = 0, end = o->samples.len; /* :187 */
+  int64_t* scratch = NULL;
+  int64_t scratch_cap = 0;
+  int64_t* slots = NULL;
+  int rc = ORC_OK;
+  for (int h = 0; h < num_hops && rc == ORC_OK; ++h) {
+    int64_t k = num_neighbors[h];
+    slots = (int64_t*)realloc(slots, sizeof(int64_t) * (size_t)(k > 0 ? k : 1)); /* sampler.init(k), :190 */
+    layer_offsets[3 * h + 0] = o->samples.len; /* :193 */
+    layer_offsets[3 * h + 1] = o->cols.len;
+    layer_offsets[3 * h + 2] = o->samples.len;
+    for (int64_t i = begin; i < end; ++i) { /* :195 */
+      int64_t w = o->samples.d[i];
+      int64_t w_state = track_state ? o->states.d[i] : 0;
+      orc_ctx ctx = {(uint32_t)i, batch, 0u};
+      int64_t n;
+      rc = sample_node(rng, &ctx, smp, flt, ptrs, indices, num_cols, w, w_state, k, slots, &scratch, &scratch_cap, &n);
+      if (rc != ORC_OK) break;
+      for (int64_t s = 0; s < n; ++s) { /* :210-218 */
+        int64_t edge_ptr = slots[s];
+        int64_t v = indices[edge_ptr];
+        int64_t j = o->samples.len;
+        if (!vec_push(&o->samples, v)) { rc = ORC_ERR_CAPACITY; break; }
+        if (track_state) vec_push(&o->states, filter_mutate(flt, w_state, edge_ptr));
+        if (!vec_push(&o->rows, j) || !vec_push(&o->cols, i) || !vec_push(&o->eidx, edge_ptr)) { rc = ORC_ERR_CAPACITY; break; }
+      }
+      if (rc != ORC_OK) break;
+    }
+    begin = end; /* :221-222 */
+    end = o->samples.len;
+  }
+  free(scratch);
+  free(slots);
+  return rc;
+}
+
+int orc_neighbor_sampling_homogenous(
+    const int64_t* col_ptrs, int64_t num_cols, const int64_t* row_indices,
+    const int64_t* inputs, int64_t num_inputs, const int64_t* num_neighbors, int num_hops,
+    int sampler_kind, const double* weights,
+    int filter_mode, int filter_forward, int64_t win_lo, int64_t win_hi, const int64_t* timestamps,
+    const int64_t* inputs_state,
+    int rng_mode, uint64_t seed, uint32_t batch,
+    int64_t* samples, int64_t samples_cap, int64_t* rows, int64_t* cols, int64_t* edge_index, int64_t edges_cap,
+    int64_t* out_lens /* [2]: n_samples, n_edges */, int64_t* layer_offsets /* [num_hops*3] */) {
+  orc_rng rng;
+  orc_rng_init(&rng, rng_mode, seed);
+  orc_sampler smp = {sampler_kind, weights};
+  orc_filter flt = {filter_mode, filter_forward, win_lo, win_hi, timestamps};
+  ns_out o;
+  memset(&o, 0, sizeof(o));
+  o.samples.d = samples; o.samples.cap = samples_cap; o.samples.fixed = 1;
+  o.rows.d = rows; o.rows.cap = edges_cap; o.rows.fixed = 1;
+  o.cols.d = cols; o.cols.cap = edges_cap; o.cols.fixed = 1;
+  o.eidx.d = edge_index; o.eidx.cap = edges_cap; o.eidx.fixed = 1;
+  int rc = ns_homogenous_core(&rng, batch, col_ptrs, row_indices, num_cols, inputs, num_inputs, num_neighbors,
+                              num_hops, &smp, &flt, inputs_state, &o, layer_offsets);
+  out_lens[0] = o.samples.len;
+  out_lens[1] = o.cols.len;
+  free(o.states.d);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* CPU baseline driver: B independent seed batches over a shared read-only CSC, T threads      */
+/* (how a DataLoader(num_workers=T) drives the reference).  Each batch mirrors the reference's */
+/* allocation behaviour: growing Vecs (neighbor_sampling.rs:176-182, graph.rs:123-146) followed */
+/* by 4 Vec->Tensor copies (python.rs:259-262).  Returns totals only.                          */
+/* ------------------------------------------------------------------------------------------ */
+int orc_neighbor_sampling_homogenous_batches(
+    const int64_t* col_ptrs, int64_t num_cols, const int64_t* row_indices,
+    const int64_t* inputs /* [B*S] */, int64_t num_batches, int64_t seeds_per_batch,
+    const int64_t* num_neighbors, int num_hops, int sampler_kind, const double* weights,
+    int rng_mode, uint64_t seed, int num_threads,
+    int64_t* total_samples, int64_t* total_edges) {
+  int64_t tot_s = 0, tot_e = 0;
+  int err = 0;
+#ifdef _OPENMP
+  if (num_threads > 0) omp_set_num_threads(num_threads);
+#endif
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : tot_s, tot_e) reduction(| : err)
+  for (int64_t b = 0; b < num_batches; ++b) {
+    orc_rng rng;
+    orc_rng_init(&rng, rng_mode, rng_mode == ORC_RNG_XOSHIRO ? seed + (uint64_t)b : seed);
+    orc_sampler smp = {sampler_kind, weights};
+    orc_filter flt = {ORC_FILTER_NONE, 0, 0, 0, NULL};
+    ns_out o;
+    memset(&o, 0, sizeof(o));
+    int64_t lo[3 * 64];
+    int rc = ns_homogenous_core(&rng, (uint32_t)b, col_ptrs, row_indices, num_cols, inputs + b * seeds_per_batch,
+                                seeds_per_batch, num_neighbors, num_hops > 64 ? 64 : num_hops, &smp, &flt, NULL, &o, lo);
+    /* python.rs:259-262: four Vec<i64> -> Tensor copies */
+    int64_t* t0 = (int64_t*)malloc(sizeof(int64_t) * (size_t)(o.samples.len + 1));
+    int64_t* t1 = (int64_t*)malloc(sizeof(int64_t) * (size_t)(o.rows.len + 1));
+    int64_t* t2 = (int64_t*)malloc(sizeof(int64_t) * (size_t)(o.cols.len + 1));
+    int64_t* t3 = (int64_t*)malloc(sizeof(int64_t) * (size_t)(o.eidx.len + 1));
+    memcpy(t0, o.samples.d, sizeof(int64_t) * (size_t)o.samples.len);
+    memcpy(t1, o.rows.d, sizeof(int64_t) * (size_t)o.rows.len);
+    memcpy(t2, o.cols.d, sizeof(int64_t) * (size_t)o.cols.len);
+    memcpy(t3, o.eidx.d, sizeof(int64_t) * (size_t)o.eidx.len);
+    tot_s += o.samples.len;
+    tot_e += o.cols.len;
+    /* keep the copies observable so the compiler cannot drop them */
+    if (o.samples.len > 0 && t0[o.samples.len - 1] != o.samples.d[o.samples.len - 1]) err |= 1;
+    if (o.cols.len > 0 && (t1[o.rows.len - 1] ^ t2[o.cols.len - 1] ^ t3[o.eidx.len - 1]) == INT64_MIN) err |= 2;
+    if (rc != ORC_OK) err |= 4;
+    free(t0); free(t1); free(t2); free(t3);
+    free(o.samples.d); free(o.states.d); free(o.rows.d); free(o.cols.d); free(o.eidx.d);
+  }
+  *total_samples = tot_s;
+  *total_edges = tot_e;
+  return err ? ORC_ERR_PANIC : ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A8: neighbor_sampling_heterogenous, src/algo/neighbor_sampling.rs:233-356                  */
+/*   Node types and relations are passed as indices.  Relations are visited in the order       */
+/*   given (canonicalisation of quirk Q6: the reference iterates a std HashMap).               */
+/*   rel_fanouts[r*num_hops + l]; rel_active[r] == 0 <=> relation absent from num_neighbors.   */
+/* ------------------------------------------------------------------------------------------ */
+int orc_neighbor_sampling_heterogenous(
+    int num_node_types, int num_rels, const int32_t* rel_src, const int32_t* rel_dst,
+    const int64_t* const* col_ptrs, const int64_t* num_cols, const int64_t* const* row_indices,
+    const int64_t* const* inputs, const int64_t* num_inputs,
+    const int64_t* rel_fanouts, const uint8_t* rel_active, int num_hops,
+    int sampler_kind, const double* const* weights,
+    int filter_mode, int filter_forward, int64_t win_lo, int64_t win_hi, const int64_t* const* timestamps,
+    const int64_t* const* inputs_state,
+    int rng_mode, uint64_t seed, uint32_t batch,
+    int64_t* const* samples, const int64_t* samples_cap, int64_t* samples_len,
+    int64_t* const* rows, int64_t* const* cols, int64_t* const* edge_index, const int64_t* edges_cap, int64_t* edges_len,
+    int64_t* layer_offsets /* [num_rels*num_hops*3] */, int64_t* layer_offsets_len /* [num_rels] */) {
+  orc_rng rng;
+  orc_rng_init(&rng, rng_mode, seed);
+  int track_state = filter_mode != ORC_FILTER_NONE;
+  vec64* vs = (vec64*)calloc((size_t)num_node_types, sizeof(vec64));
+  vec64* vst = (vec64*)calloc((size_t)num_node_types, sizeof(vec64));
+  vec64* vr = (vec64*)calloc((size_t)num_rels, sizeof(vec64));
+  vec64* vc = (vec64*)calloc((size_t)num_rels, sizeof(vec64));
+  vec64* ve = (vec64*)calloc((size_t)num_rels, sizeof(vec64));
+  int64_t* sl_begin = (int64_t*)calloc((size_t)num_node_types, sizeof(int64_t));
+  int64_t* sl_end = (int64_t*)calloc((size_t)num_node_types, sizeof(int64_t));
+  int rc = ORC_OK;
+  for (int t = 0; t < num_node_types; ++t) { /* :264-278 */
+    vs[t].d = samples[t]; vs[t].cap = samples_cap[t]; vs[t].fixed = 1;
+    for (int64_t i = 0; i < num_inputs[t]; ++i) {
+      if (!vec_push(&vs[t], inputs[t][i])) rc = ORC_ERR_CAPACITY;
+      if (track_state && inputs_state && inputs_state[t]) vec_push(&vst[t], inputs_state[t][i]);
+    }
+    sl_begin[t] = 0; /* :288-290 */
+    sl_end[t] = vs[t].len;
+  }
+  for (int r = 0; r < num_rels; ++r) {
+    vr[r].d = rows[r]; vr[r].cap = edges_cap[r]; vr[r].fixed = 1;
+    vc[r].d = cols[r]; vc[r].cap = edges_cap[r]; vc[r].fixed = 1;
+    ve[r].d = edge_index[r]; ve[r].cap = edges_cap[r]; ve[r].fixed = 1;
+    layer_offsets_len[r] = 0;
+  }
+  int64_t* scratch = NULL;
+  int64_t scratch_cap = 0;
+  int64_t* slots = NULL;
+  for (int ell = 0; ell < num_hops && rc == ORC_OK; ++ell) { /* :292 */
+    for (int r = 0; r < num_rels && rc == ORC_OK; ++r) { /* :294, canonical order */
+      if (!rel_active[r]) continue;
+      int64_t k = rel_fanouts[(int64_t)r * num_hops + ell];
+      int src_t = rel_src[r], dst_t = rel_dst[r];
+      orc_sampler smp = {sampler_kind, weights ? weights[r] : NULL};
+      orc_filter flt = {filter_mode, filter_forward, win_lo, win_hi, timestamps ? timestamps[r] : NULL};
+      slots = (int64_t*)realloc(slots, sizeof(int64_t) * (size_t)(k > 0 ? k : 1));
+      int64_t* lo = layer_offsets + ((int64_t)r * num_hops + layer_offsets_len[r]) * 3; /* :314-315 */
+      lo[0] = vs[src_t].len; lo[1] = vc[r].len; lo[2] = vs[dst_t].len;
+      layer_offsets_len[r] += 1;
+      int64_t begin = sl_begin[dst_t], end = sl_end[dst_t]; /* :317 */
+      for (int64_t i = begin; i < end; ++i) {
+        int64_t w = vs[dst_t].d[i];
+        int64_t w_state = track_state ? vst[dst_t].d[i] : 0;
+        orc_ctx ctx = {(uint32_t)i, batch, (uint32_t)r};
+        int64_t n;
+        rc = sample_node(&rng, &ctx, &smp, &flt, col_ptrs[r], row_indices[r], num_cols[r], w, w_state, k, slots,
+                         &scratch, &scratch_cap, &n);
+        if (rc != ORC_OK) break;
+        for (int64_t s = 0; s < n; ++s) { /* :333-341 */
+          int64_t edge_ptr = slots[s];
+          int64_t v = row_indices[r][edge_ptr];
+          int64_t j = vs[src_t].len;
+          if (!vec_push(&vs[src_t], v)) { rc = ORC_ERR_CAPACITY; break; }
+          if (track_state) vec_push(&vst[src_t], filter_mutate(&flt, w_state, edge_ptr));
+          if (!vec_push(&vr[r], j) || !vec_push(&vc[r], i) || !vec_push(&ve[r], edge_ptr)) { rc = ORC_ERR_CAPACITY; break; }
+        }
+        if (rc != ORC_OK) break;
+      }
+    }
+    for (int t = 0; t < num_node_types; ++t) { /* :345-348 */
+      sl_begin[t] = sl_end[t];
+      sl_end[t] = vs[t].len;
+    }
+  }
+  for (int t = 0; t < num_node_types; ++t) { samples_len[t] = vs[t].len; free(vst[t].d); }
+  for (int r = 0; r < num_rels; ++r) edges_len[r] = vc[r].len;
+  free(scratch); free(slots);
+  free(vs); free(vst); free(vr); free(vc); free(ve); free(sl_begin); free(sl_end);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A10: random_walk, src/algo/random_walk.rs:10-75                                            */
+/* ------------------------------------------------------------------------------------------ */
+static void walk_probs(float p, float q, float* prob0, float* prob1, float* prob2) {
+  /* :29-36, f32 arithmetic */
+  float a = 1.0f / p, b = 1.0f, c = 1.0f / q;
+  float max_prob = a;
+  if (b >= max_prob) max_prob = b; /* Iterator::max_by returns the last maximum */
+  if (c >= max_prob) max_prob = c;
+  *prob0 = 1.0f / p / max_prob;
+  *prob1 = 1.0f / max_prob;
+  *prob2 = 1.0f / q / max_prob;
+}
+
+int orc_random_walk(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,
+                    const int64_t* start, int64_t num_walks, int64_t walk_length, float p, float q,
+                    int rng_mode, uint64_t seed, int64_t walker_base,
+                    int64_t* walks /* [num_walks, walk_length+1] */, int64_t* total_attempts) {
+  orc_rng rng;
+  orc_rng_init(&rng, rng_mode, seed);
+  int64_t L = walk_length + 1;
+  for (int64_t i = 0; i < num_walks * L; ++i) walks[i] = -1; /* Tensor::full(-1), :18-23 */
+  float prob0, prob1, prob2;
+  walk_probs(p, q, &prob0, &prob1, &prob2);
+  int64_t attempts = 0;
+  for (int64_t i = 0; i < num_walks; ++i) { /* :38 */
+    int64_t prev = -1, cur = start[i];
+    walks[i * L] = cur;
+    uint64_t walker = (uint64_t)(walker_base + i);
+    for (int64_t l = 0; l < walk_length; ++l) {
+      if (cur < 0 || cur >= num_rows) return ORC_ERR_PANIC;
+      int64_t nb = row_ptrs[cur], ne = row_ptrs[cur + 1];
+      if (nb >= ne) break; /* :45-47 */
+      int64_t next;
+      uint32_t buf[4];
+      for (uint32_t a = 0;; ++a) { /* :52-66 */
+        float r;
+        if (rng.mode == ORC_RNG_XOSHIRO) {
+          next = col_indices[nb + (int64_t)xoshiro_gen_range_u64(&rng, (uint64_t)(ne - nb))];
+          r = xoshiro_gen_f32(&rng);
+        } else {
+          if ((a & 1u) == 0u) {
+            uint32_t ctr[4] = {(uint32_t)walker, (uint32_t)(walker >> 32), (uint32_t)l, ORC_TAG_WALK | ((a >> 1) << 8)};
+            orc_philox4x32_10(ctr, rng.key, buf);
+          }
+          uint32_t ri = buf[(a & 1u) * 2u], rf = buf[(a & 1u) * 2u + 1u];
+          next = col_indices[nb + (int64_t)mulhi32(ri, (uint32_t)(ne - nb))];
+          r = (float)(rf >> 8) * (1.0f / 16777216.0f);
+        }
+        ++attempts;
+        if (next == prev) {
+          if (r < prob0) break;
+        } else {
+          if (next < 0 || next >= num_rows) return ORC_ERR_PANIC; /* ptrs[next + 1] out of bounds */
+          /* prev == -1 on the first step: binary search for -1 never succeeds (quirk Q8) */
+          if (has_edge(row_ptrs, col_indices, next, prev)) {
+            if (r < prob1) break;
+          } else if (r < prob2) {
+            break;
+          }
+        }
+      }
+      prev = cur; /* :68-70 */
+      cur = next;
+      walks[i * L + l + 1] = cur;
+    }
+  }
+  if (total_attempts) *total_attempts = attempts;
+  return ORC_OK;
+}
+
+/* multi-threaded CPU baseline for walks: walkers split statically across threads */
+int orc_random_walk_mt(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,
+                       const int64_t* start, int64_t num_walks, int64_t walk_length, float p, float q,
+                       int rng_mode, uint64_t seed, int num_threads, int64_t* walks, int64_t* total_attempts) {
+  int64_t L = walk_length + 1;
+  int64_t att = 0;
+  int err = 0;
+#ifdef _OPENMP
+  if (num_threads > 0) omp_set_num_threads(num_threads);
+#endif
+  int64_t chunk = 4096;
+  int64_t nchunks = (num_walks + chunk - 1) / chunk;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : att) reduction(| : err)
+  for (int64_t c = 0; c < nchunks; ++c) {
+    int64_t b = c * chunk, e = b + chunk < num_walks ? b + chunk : num_walks;
+    int64_t a = 0;
+    int rc = orc_random_walk(row_ptrs, num_rows, col_indices, start + b, e - b, walk_length, p, q, rng_mode,
+                             rng_mode == ORC_RNG_XOSHIRO ? seed + (uint64_t)c : seed, b, walks + b * L, &a);
+    att += a;
+    if (rc != ORC_OK) err |= 1;
+  }
+  if (total_attempts) *total_attempts = att;
+  return err ? ORC_ERR_PANIC : ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------ */
+/* A7 (dedup stage): insertion-order relabel map, semantic of                                  */
+/* src/algo/negative_sampling.rs:20-47 (samples_mapping) applied to a sampled tree:            */
+/*   nodes      = seeds (all of them, duplicates kept) ++ every non-seed id at first appearance */
+/*   map[seed]  = index of its LAST occurrence among the seeds (HashMap::extend overwrites, :26) */
+/*   map[other] = len(nodes) at first appearance (:36-39)                                      */
+/*   local[i]   = map[samples[i]] for every position of the tree's samples vector              */
+/* ------------------------------------------------------------------------------------------ */
+typedef struct { int64_t key, val; } hslot;
+int orc_unique_relabel(const int64_t* samples, int64_t n, int64_t num_seeds,
+                       int64_t* nodes /* cap n */, int64_t* num_nodes, int64_t* local /* [n] */) {
+  int64_t cap = 16;
+  while (cap < 2 * n + 2) cap <<= 1;
+  hslot* tab = (hslot*)malloc(sizeof(hslot) * (size_t)cap);
+  for (int64_t i = 0; i < cap; ++i) tab[i].val = -1;
+  int64_t len = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t key = samples[i];
+    uint64_t h = (uint64_t)key * 0x9E3779B97F4A7C15ULL;
+    int64_t s = (int64_t)(h >> 20) & (cap - 1);
+    while (tab[s].val != -1 && tab[s].key != key) s = (s + 1) & (cap - 1);
+    if (i < num_seeds) {
+      nodes[len] = key;          /* samples.extend_from_slice(inputs), :25 */
+      tab[s].key = key;
+      tab[s].val = len;          /* later duplicates overwrite, :26 */
+      len++;
+    } else if (tab[s].val == -1) {
+      tab[s].key = key;          /* or_insert_with, :36-39 */
+      tab[s].val = len;
+      nodes[len++] = key;
+    }
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t key = samples[i];
+    uint64_t h = (uint64_t)key * 0x9E3779B97F4A7C15ULL;
+    int64_t s = (int64_t)(h >> 20) & (cap - 1);
+    while (tab[s].key != key || tab[s].val == -1) s = (s + 1) & (cap - 1);
+    local[i] = tab[s].val;
+  }
+  *num_nodes = len;
+  free(tab);
+  return ORC_OK;
+}
+
+int orc_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
