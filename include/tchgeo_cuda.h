@@ -1,0 +1,196 @@
+/*
+ * tchgeo_cuda.h -- C ABI of the B200-native (sm_100a) sampling hot path for tch-geometric.
+ *
+ * This is the drop-in boundary: the entry points below are what the reference's Rust host
+ * (src/python.rs) binds through `extern "C"` in place of its CPU algorithms.  Every pointer marked
+ * DEVICE is a CUDA device pointer taken straight from `tch::Tensor::data_ptr()` (or
+ * `torch.Tensor.data_ptr()`); every pointer marked HOST is ordinary host memory.  No torch types,
+ * no C++ types, no exceptions: every entry returns a tchgeo_status (0 = ok).  The library never
+ * allocates user-visible memory: outputs and workspaces are allocated by the caller (sizes come
+ * from the *_workspace_bytes / *_capacity queries) and narrowed to the returned lengths.
+ * There is no CPU fallback behind this ABI.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   tchgeo_ind2ptr                      src/data/storage.rs:67-101   (ind2ptr)
+ *   tchgeo_coo_to_csx                   src/data/storage.rs:103-127  (TryFrom<&CooGraphStorage>),
+ *                                       called from src/python.rs:27-39 (to_csc) and :41-53 (to_csr)
+ *   tchgeo_neighbor_sampling_*          src/algo/neighbor_sampling.rs:162-230 (homogenous) and
+ *                                       :233-356 (heterogenous), called from src/python.rs:251,363;
+ *                                       samplers src/utils/sampling.rs:6-69
+ *   tchgeo_random_walk                  src/algo/random_walk.rs:10-75, called from src/python.rs:598
+ *   tchgeo_unique_relabel               insertion-order relabel map, semantic of
+ *                                       src/algo/negative_sampling.rs:20-47 (the dedup stage
+ *                                       north_star asks for; additive, never alters drop-in outputs)
+ *
+ * Threading: all entry points are re-entrant and keep no global mutable state except the
+ * thread-local last-error string.  Work is issued on the caller's stream.
+ *
+ * RNG contract: Philox4x32-10, key = (seed_lo, seed_hi); counters are documented in DESIGN.md
+ * ("RNG contract") and are independent of launch geometry, so results depend only on
+ * (seed, batch index, relation index, position of the frontier node in its samples vector).
+ */
+#ifndef TCHGEO_CUDA_H_
+#define TCHGEO_CUDA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TCHGEO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define TCHGEO_API __attribute__((visibility("default")))
+#else
+#define TCHGEO_API
+#endif
+
+typedef int32_t tchgeo_status;
+enum {
+  TCHGEO_OK = 0,
+  TCHGEO_ERR_BAD_ARG = 1,       /* null pointer, negative size, unsupported fanout ...            */
+  TCHGEO_ERR_CUDA = 2,          /* a CUDA runtime call failed; see tchgeo_last_error()            */
+  TCHGEO_ERR_CAPACITY = 3,      /* an output buffer or the workspace is too small                 */
+  TCHGEO_ERR_INDEX = 4,         /* node id / edge endpoint out of range (reference: Rust panic)   */
+  TCHGEO_ERR_REFERENCE_PANIC = 5, /* input on which the reference panics (fanout 0 with deg > 0,
+                                     non-positive weight sum, src/utils/sampling.rs:19,49,51)      */
+  TCHGEO_ERR_INTERNAL = 6       /* look-back watchdog tripped (should never happen)               */
+};
+
+/* sampler kinds: src/python.rs:210-216 dispatch */
+enum {
+  TCHGEO_SAMPLER_UNIFORM = 0,         /* UnweightedSampler<false> (default), reservoir, quirk Q1 */
+  TCHGEO_SAMPLER_UNIFORM_REPLACE = 1, /* UnweightedSampler<true>, exactly k iid picks, quirk Q3   */
+  TCHGEO_SAMPLER_WEIGHTED = 2         /* WeightedSampler<f64>, quirk Q2                           */
+};
+
+/* cudaStream_t passed as void* so that C callers need no CUDA headers. */
+typedef void* tchgeo_stream;
+
+TCHGEO_API int32_t tchgeo_abi_version(void);
+/* Human-readable description of the last non-OK status on this thread (never NULL). */
+TCHGEO_API const char* tchgeo_last_error(void);
+
+/* -------------------------------------------------------------------------------------------- */
+/* ind2ptr: out[i] = #{e : ind[e] < i}, i in [0, m]; `ind` sorted ascending.                      */
+/* replaces src/data/storage.rs:67-101                                                           */
+/* -------------------------------------------------------------------------------------------- */
+TCHGEO_API tchgeo_status tchgeo_ind2ptr(const int64_t* ind /*DEVICE [numel]*/, int64_t numel, int64_t m,
+                             int64_t* out /*DEVICE [m+1]*/, tchgeo_stream stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* COO -> CSC (csc != 0) or CSR (csc == 0).  perm = argsort(major*size_minor + minor) (stable),   */
+/* ptrs = ind2ptr(major[perm]), indices = minor[perm].  n_rows = size.0, n_cols = size.1.          */
+/* replaces src/data/storage.rs:103-127                                                          */
+/* -------------------------------------------------------------------------------------------- */
+TCHGEO_API size_t tchgeo_coo_to_csx_workspace_bytes(int64_t num_edges, int64_t n_rows, int64_t n_cols);
+TCHGEO_API tchgeo_status tchgeo_coo_to_csx(const int64_t* row /*DEVICE [E]*/, const int64_t* col /*DEVICE [E]*/,
+                                int64_t num_edges, int64_t n_rows, int64_t n_cols, int32_t csc,
+                                int64_t* ptrs /*DEVICE [n_major+1]*/, int64_t* indices /*DEVICE [E]*/,
+                                int64_t* perm /*DEVICE [E]*/, void* workspace /*DEVICE*/, size_t workspace_bytes,
+                                tchgeo_stream stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* Multi-hop neighbor sampling.  One call samples `num_batches` independent seed batches (the     */
+/* reference call is num_batches == 1); batch b's outputs are exactly what the reference returns   */
+/* for inputs[b] and live at offset b*stride of each output buffer.                                */
+/* -------------------------------------------------------------------------------------------- */
+typedef struct tchgeo_sampling_args {
+  /* ---- graph: node types, relations (canonical relation order = array order, quirk Q6) ---- */
+  int32_t num_node_types;           /* T (1 for homogeneous)                                      */
+  int32_t num_rels;                 /* R (1 for homogeneous)                                      */
+  int32_t num_hops;                 /* H                                                          */
+  int32_t sampler_kind;             /* TCHGEO_SAMPLER_*                                           */
+  const int32_t* rel_src;           /* HOST [R] node-type index of the relation's source          */
+  const int32_t* rel_dst;           /* HOST [R] node-type index of the relation's destination     */
+  const int64_t* const* col_ptrs;   /* HOST [R] of DEVICE [num_cols[r]+1]                          */
+  const int64_t* num_cols;          /* HOST [R] number of dst nodes of the relation                */
+  const int64_t* const* row_indices;/* HOST [R] of DEVICE [nnz_r]                                  */
+  const double* const* weights;     /* HOST [R] of DEVICE [nnz_r] (f64) or NULL unless WEIGHTED    */
+  const int64_t* fanouts;           /* HOST [R*H] num_neighbors[r][hop]                            */
+  const uint8_t* rel_active;        /* HOST [R] 0 = relation absent from num_neighbors, or NULL    */
+  /* ---- seeds ---- */
+  int64_t num_batches;              /* B                                                          */
+  const int64_t* const* inputs;     /* HOST [T] of DEVICE [B, seeds_per_batch[t]] (may be NULL if 0) */
+  const int64_t* seeds_per_batch;   /* HOST [T]                                                    */
+  /* ---- rng ---- */
+  uint64_t seed;
+  uint32_t batch_base;              /* batch b draws with batch index batch_base + b               */
+  uint32_t reserved0;
+  /* ---- outputs (caller allocated) ---- */
+  int64_t* const* samples;          /* HOST [T] of DEVICE [B, samples_stride[t]]                   */
+  const int64_t* samples_stride;    /* HOST [T] per-batch capacity                                 */
+  int64_t* const* rows;             /* HOST [R] of DEVICE [B, edges_stride[r]]                     */
+  int64_t* const* cols;             /* HOST [R]                                                    */
+  int64_t* const* edge_index;       /* HOST [R]                                                    */
+  const int64_t* edges_stride;      /* HOST [R] per-batch capacity                                 */
+  /* ---- host results, filled after one stream synchronisation (all may be NULL to skip) ---- */
+  int64_t* samples_len;             /* HOST [B*T]                                                  */
+  int64_t* edges_len;               /* HOST [B*R]                                                  */
+  int64_t* layer_offsets;           /* HOST [B*R*H*3] LayerOffset = (len(samples[src]),
+                                       len(edges[rel]), len(samples[dst])) at relation start,
+                                       src/algo/neighbor_sampling.rs:193,:314-315                  */
+  /* ---- workspace ---- */
+  void* workspace;                  /* DEVICE                                                      */
+  size_t workspace_bytes;
+  tchgeo_stream stream;
+} tchgeo_sampling_args;
+
+/* Worst-case per-batch capacities (elements) for samples[t] and edges[r]:
+ * the reference recurrence with every neighbourhood at full fanout. HOST outputs [T], [R]. */
+TCHGEO_API tchgeo_status tchgeo_neighbor_sampling_capacity(const tchgeo_sampling_args* args, int64_t* samples_cap,
+                                                int64_t* edges_cap);
+TCHGEO_API size_t tchgeo_neighbor_sampling_workspace_bytes(const tchgeo_sampling_args* args);
+
+/* replaces src/algo/neighbor_sampling.rs:233-356 (and :162-230 with T = R = 1).
+ * If samples_len/edges_len/layer_offsets are all NULL the call is asynchronous: it returns after
+ * enqueueing and device-side errors surface through tchgeo_neighbor_sampling_collect. */
+TCHGEO_API tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* args);
+
+/* Synchronise args->stream, fetch lengths / layer offsets / device error flag of the last
+ * tchgeo_neighbor_sampling call that used args->workspace. */
+TCHGEO_API tchgeo_status tchgeo_neighbor_sampling_collect(const tchgeo_sampling_args* args);
+
+/* Flat-argument convenience wrapper for the homogeneous case (T = R = 1):
+ * replaces src/algo/neighbor_sampling.rs:162-230 as called from src/python.rs:251.
+ * layer_offsets: HOST [B*H*3]; out_lens: HOST [B*2] = (len(samples), len(edges)). */
+TCHGEO_API tchgeo_status tchgeo_neighbor_sampling_homogenous(
+    const int64_t* col_ptrs /*DEVICE [num_cols+1]*/, int64_t num_cols, const int64_t* row_indices /*DEVICE*/,
+    const int64_t* inputs /*DEVICE [B,S]*/, int64_t num_batches, int64_t seeds_per_batch,
+    const int64_t* num_neighbors /*HOST [H]*/, int32_t num_hops, int32_t sampler_kind,
+    const double* weights /*DEVICE or NULL*/, uint64_t seed, uint32_t batch_base,
+    int64_t* samples /*DEVICE [B,samples_stride]*/, int64_t samples_stride,
+    int64_t* rows /*DEVICE [B,edges_stride]*/, int64_t* cols, int64_t* edge_index, int64_t edges_stride,
+    int64_t* out_lens /*HOST or NULL*/, int64_t* layer_offsets /*HOST or NULL*/,
+    void* workspace /*DEVICE*/, size_t workspace_bytes, tchgeo_stream stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* node2vec random walk over CSR.  walks: [num_walks, walk_length+1] row-major, -1 padded.        */
+/* Walker i draws with walker index walker_base + i (so sharded launches reproduce one big one).   */
+/* replaces src/algo/random_walk.rs:10-75                                                        */
+/* -------------------------------------------------------------------------------------------- */
+TCHGEO_API tchgeo_status tchgeo_random_walk(const int64_t* row_ptrs /*DEVICE [num_rows+1]*/, int64_t num_rows,
+                                 const int64_t* col_indices /*DEVICE*/, const int64_t* start /*DEVICE [num_walks]*/,
+                                 int64_t num_walks, int64_t walk_length, float p, float q, uint64_t seed,
+                                 int64_t walker_base, int64_t* walks /*DEVICE*/,
+                                 int64_t* stats /*DEVICE [2] scratch: rejection-loop attempts, error flags*/,
+                                 int64_t* attempts_out /*HOST [1] or NULL*/, tchgeo_stream stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* Dedup + insertion-order relabel of one sampled tree (additive stage).                          */
+/*   nodes      = seeds (duplicates kept) ++ every other id at first appearance                    */
+/*   local[i]   = index into `nodes` of samples[i] (a duplicated seed maps to its LAST seed slot)  */
+/* semantic of src/algo/negative_sampling.rs:20-47                                               */
+/* -------------------------------------------------------------------------------------------- */
+TCHGEO_API size_t tchgeo_unique_relabel_workspace_bytes(int64_t n);
+TCHGEO_API tchgeo_status tchgeo_unique_relabel(const int64_t* samples /*DEVICE [n]*/, int64_t n, int64_t num_seeds,
+                                    int64_t* nodes /*DEVICE [n]*/, int64_t* local /*DEVICE [n]*/,
+                                    int64_t* num_nodes /*HOST [1]*/, void* workspace /*DEVICE*/,
+                                    size_t workspace_bytes, tchgeo_stream stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TCHGEO_CUDA_H_ */

@@ -1,0 +1,650 @@
+// Multi-hop fixed-fanout neighbor sampling for sm_100a (B200).
+//
+// Replaces src/algo/neighbor_sampling.rs:162-230 (homogenous) and :233-356 (heterogenous) of the
+// reference, together with the samplers of src/utils/sampling.rs:6-69, behind the C ABI declared in
+// include/tchgeo_cuda.h.  Output layout is the reference's computation tree (no dedup): every
+// sampled edge appends one node, rows[e] = index of that node in samples[src], cols[e] = index of the
+// frontier node in samples[dst], edge_index[e] = CSC position (neighbor_sampling.rs:210-218).
+//
+// One kernel launch per (hop, relation) processes that hop's frontier of *all* batches:
+//   tile = up to 256 frontier nodes of one batch, handled by one 256-thread CTA
+//   A. coalesced load of frontier ids, gather of the (ptrs[w], ptrs[w+1]) pair, per-node count
+//      cnt = min(deg, k) (or k*[deg>0] with replacement), block scan
+//   B. the tile's exclusive output offset inside its batch comes from a decoupled look-back over the
+//      batch's earlier tiles (single pass, no separate count/scan kernels, no host sync)
+//   C. sampling decisions in shared memory
+//        UNIFORM : the serial reservoir of sampling.rs:6-26 is replayed exactly in parallel:
+//                  slot s ends up holding the item of the LAST step i>=k whose draw j_i == s, else
+//                  item s.  Steps are independent given i, so the tile's (node, 4-step block) pairs
+//                  are flattened over all 256 threads; each draws Philox(seed; pos, block, batch)
+//                  and does atomicMax(slot, step) in shared memory for the hits.
+//        REPLACE : k iid draws per non-empty neighbourhood (sampling.rs:57-69).
+//        WEIGHTED: warp per node; inclusive warp scan of the f64 weights gives w_sum at every step;
+//                  step i fires iff u*w_sum_i < w_i and then overwrites a uniform slot
+//                  (sampling.rs:28-55); last firing writer per slot wins via atomicMax.
+//   D. thread-per-output-edge epilogue: one random 8-byte gather from row_indices and four fully
+//      coalesced 8-byte streaming stores (samples, rows, cols, edge_index).
+// HBM-bound integer work: no tensor cores.  See DESIGN.md for the byte model and RNG contract.
+#include <cub/block/block_scan.cuh>
+
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace tchgeo {
+namespace {
+
+constexpr int HOP_THREADS = 256;
+constexpr int MAX_TILE_EDGES = 8192;   // shared-memory slots per tile when fanout <= 8192
+constexpr int MAX_FANOUT = 32768;      // one node per tile above 8192; bounded by shared memory
+constexpr uint64_t ST_FLAG_AGG = 1ull << 62;
+constexpr uint64_t ST_FLAG_INCL = 2ull << 62;
+constexpr uint64_t ST_VAL_MASK = (1ull << 62) - 1;
+constexpr int CNT_BITS = 20;           // packed scan: low 20 bits = output count, high 44 = draw blocks
+
+struct HopParams {
+  const int64_t* ptrs;
+  const int64_t* indices;
+  const double* weights;
+  int64_t num_cols;
+  const int64_t* dst_samples;  // frontier ids live here (may alias src_samples)
+  int64_t dst_stride;
+  int64_t* src_samples;        // sampled nodes are appended here
+  int64_t src_stride;
+  int64_t* rows;
+  int64_t* cols;
+  int64_t* eidx;
+  int64_t e_stride;
+  const int64_t* fr_begin;     // [B] frontier window in dst_samples
+  const int64_t* fr_end;       // [B]
+  const int64_t* src_len_in;   // [B] len(samples[src]) before this launch
+  int64_t* src_len_out;        // [B] ... after
+  const int64_t* e_len_in;     // [B] len(edges[rel]) before this launch
+  int64_t* e_len_out;          // [B] ... after
+  uint64_t* status;            // [B * tiles_per_batch] look-back words, zero-initialised
+  uint32_t* ticket;            // zero-initialised tile dispenser
+  uint32_t* err;
+  int32_t tiles_per_batch;
+  int32_t tile_nodes;
+  int32_t tile_edges;          // tile_nodes * fanout
+  int32_t fanout;
+  uint32_t key0, key1;
+  uint32_t rel;
+  uint32_t batch_base;
+};
+
+__global__ void fill_i64_kernel(int64_t* p, int64_t v, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) {
+  using BlockScan = cub::BlockScan<unsigned long long, HOP_THREADS>;
+  __shared__ typename BlockScan::TempStorage scan_tmp;
+  __shared__ int64_t s_start[HOP_THREADS];
+  __shared__ int64_t s_choff[HOP_THREADS + 1];
+  __shared__ uint32_t s_deg[HOP_THREADS];
+  __shared__ int s_off[HOP_THREADS + 1];
+  __shared__ uint32_t s_ticket;
+  __shared__ int64_t s_excl;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  uint32_t* s_slot = reinterpret_cast<uint32_t*>(dyn_smem);
+  uint8_t* s_owner = reinterpret_cast<uint8_t*>(s_slot + p.tile_edges);
+
+  const int tid = threadIdx.x;
+  const int lane = tid & 31;
+  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+  __syncthreads();
+  // Tiles are handed out in start order, so every tile this one waits on is already running.
+  const uint32_t ticket = s_ticket;
+  const int b = (int)(ticket / (uint32_t)p.tiles_per_batch);
+  const int t = (int)(ticket - (uint32_t)b * (uint32_t)p.tiles_per_batch);
+  const int TN = p.tile_nodes;
+  const int k = p.fanout;
+
+  const int64_t fb = p.fr_begin[b];
+  int64_t fe = p.fr_end[b];
+  if (fe > p.dst_stride) fe = p.dst_stride;  // only after a capacity error upstream
+  const int64_t F = fe > fb ? fe - fb : 0;
+  const int64_t node0 = (int64_t)t * TN;
+  const int nn = (int)max((int64_t)0, min((int64_t)TN, F - node0));
+  const bool is_last = (nn > 0 && node0 + nn == F) || (F == 0 && t == 0);
+  if (nn == 0 && !is_last) return;
+
+  // ---- A: frontier ids, degree, count -----------------------------------------------------------
+  int cnt = 0;
+  uint32_t deg = 0;
+  int64_t nblocks = 0;
+  if (tid < nn) {
+    const int64_t w = p.dst_samples[(int64_t)b * p.dst_stride + fb + node0 + tid];
+    int64_t s = 0;
+    if (w < 0 || w >= p.num_cols) {
+      atomicOr(p.err, DEV_ERR_INDEX);  // reference: slice index panic (quirk Q10)
+    } else {
+      s = __ldg(p.ptrs + w);
+      const int64_t d = __ldg(p.ptrs + w + 1) - s;
+      if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
+      else deg = (uint32_t)d;
+    }
+    s_start[tid] = s;
+    s_deg[tid] = deg;
+    if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
+      cnt = deg > 0 ? k : 0;  // exactly k picks, even when deg < k (quirk Q3)
+    } else {
+      cnt = deg < (uint32_t)k ? (int)deg : k;
+      if (k == 0 && deg > 0) atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0..0), sampling.rs:19
+      if (KIND == TCHGEO_SAMPLER_UNIFORM && deg > (uint32_t)k) nblocks = ((int64_t)deg - k + 3) >> 2;
+    }
+  }
+  unsigned long long packed = (unsigned long long)cnt | ((unsigned long long)nblocks << CNT_BITS);
+  unsigned long long pexcl, ptotal;
+  BlockScan(scan_tmp).ExclusiveSum(packed, pexcl, ptotal);
+  const int off = (int)(pexcl & ((1u << CNT_BITS) - 1));
+  const int total = (int)(ptotal & ((1u << CNT_BITS) - 1));
+  const int64_t Q = (int64_t)(ptotal >> CNT_BITS);
+  s_off[tid] = off;
+  s_choff[tid] = (int64_t)(pexcl >> CNT_BITS);
+  if (tid == 0) {
+    s_off[HOP_THREADS] = total;
+    s_choff[HOP_THREADS] = Q;
+  }
+
+  // ---- B: decoupled look-back over this batch's earlier tiles -----------------------------------
+  uint64_t* my_status = p.status + (size_t)b * p.tiles_per_batch;
+  if (tid < 32) {
+    int64_t excl = 0;
+    if (t == 0) {
+      if (lane == 0) st_relaxed_u64(my_status, ST_FLAG_INCL | (uint64_t)total);
+    } else {
+      if (lane == 0) st_relaxed_u64(my_status + t, ST_FLAG_AGG | (uint64_t)total);
+      int j = t - 1;
+      uint32_t spins = 0;
+      while (true) {
+        const int idx = j - lane;
+        const uint64_t v = idx >= 0 ? ld_relaxed_u64(my_status + idx) : ST_FLAG_INCL;
+        const uint32_t flag = (uint32_t)(v >> 62);
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+        const uint32_t inval_mask = __ballot_sync(0xffffffffu, flag == 0u);
+        const int first_incl = incl_mask ? __ffs(incl_mask) - 1 : 32;
+        const int first_inval = inval_mask ? __ffs(inval_mask) - 1 : 32;
+        if (first_inval < first_incl) {  // a predecessor we need has not published yet
+          if (++spins > (1u << 24)) {
+            if (lane == 0) atomicOr(p.err, DEV_ERR_WATCHDOG);
+            break;
+          }
+          __nanosleep(64);
+          continue;
+        }
+        int64_t val = lane <= first_incl ? (int64_t)(v & ST_VAL_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (first_incl < 32) break;
+        j -= 32;
+      }
+      if (lane == 0) st_relaxed_u64(my_status + t, ST_FLAG_INCL | (uint64_t)(excl + total));
+    }
+    if (lane == 0) s_excl = excl;
+  }
+  __syncthreads();
+
+  const int64_t excl = s_excl;
+  const int64_t e_base = p.e_len_in[b] + excl;
+  const int64_t s_base = p.src_len_in[b] + excl;
+  if (is_last && tid == 0) {
+    p.e_len_out[b] = e_base + total;
+    p.src_len_out[b] = s_base + total;
+  }
+  if (e_base + total > p.e_stride || s_base + total > p.src_stride) {
+    if (tid == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
+    return;
+  }
+  if (total == 0) return;
+
+  // ---- C: sampling decisions in shared memory ---------------------------------------------------
+  if (tid < nn) {
+    for (int s = 0; s < cnt; ++s) {
+      s_owner[off + s] = (uint8_t)tid;
+      if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE) s_slot[off + s] = 0u;
+    }
+  }
+  __syncthreads();
+
+  const uint32_t pos0 = (uint32_t)(fb + node0);
+  const uint32_t batch = p.batch_base + (uint32_t)b;
+
+  if (KIND == TCHGEO_SAMPLER_UNIFORM) {
+    // flattened (node, 4-step block) work items; block c of node n covers steps k+4c .. k+4c+3
+    for (int64_t q = tid; q < Q; q += HOP_THREADS) {
+      int lo = 0, hi = nn;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_choff[mid] <= q) lo = mid + 1; else hi = mid;
+      }
+      const int n = lo - 1;
+      const uint32_t c = (uint32_t)(q - s_choff[n]);
+      const uint32_t dn = s_deg[n];
+      const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1);
+      const uint32_t step0 = (uint32_t)k + 4u * c;
+      uint32_t* slots = s_slot + s_off[n];
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u) {
+        const uint32_t step = step0 + u;
+        if (step < dn) {
+          const uint32_t j = __umulhi(pick4(r, u), step);  // uniform in [0, step), sampling.rs:19
+          if (j < (uint32_t)k) atomicMax(slots + j, step);  // last writer of slot j wins, :20-22
+        }
+      }
+    }
+    __syncthreads();
+  } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
+    const int warp = tid >> 5;
+    for (int n = warp; n < nn; n += HOP_THREADS / 32) {
+      const uint32_t dn = s_deg[n];
+      if (dn <= (uint32_t)k) continue;
+      const double* wp = p.weights + s_start[n];
+      uint32_t* slots = s_slot + s_off[n];
+      double carry = 0.0;
+      for (uint32_t base = 0; base < dn; base += 32) {
+        const uint32_t item = base + lane;
+        const double w = item < dn ? __ldg(wp + item) : 0.0;
+        double incl = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const double w_sum = carry + incl;  // sampling.rs:48
+        if (item >= (uint32_t)k && item < dn) {
+          if (!(w_sum > 0.0)) {
+            atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
+          } else {
+            const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, item, batch, TAG_WEIGHTED | (p.rel << 8), p.key0, p.key1);
+            const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
+            const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
+            if (__dmul_rn(u, w_sum) < w) atomicMax(slots + __umulhi(r.z, (uint32_t)k), item);  // :49-52
+          }
+        }
+        carry = __shfl_sync(0xffffffffu, w_sum, 31);
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- D: one thread per output edge ------------------------------------------------------------
+  int64_t* o_s = p.src_samples + (int64_t)b * p.src_stride + s_base;
+  int64_t* o_r = p.rows + (int64_t)b * p.e_stride + e_base;
+  int64_t* o_c = p.cols + (int64_t)b * p.e_stride + e_base;
+  int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
+  const int64_t col0 = fb + node0;
+  constexpr int U = 4;
+  for (int e0 = tid; e0 < total; e0 += HOP_THREADS * U) {
+    int64_t ptr[U];
+    int64_t val[U];
+    int own[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * HOP_THREADS;
+      ptr[u] = 0;
+      own[u] = 0;
+      if (e < total) {
+        const int n = s_owner[e];
+        const int s = e - s_off[n];
+        own[u] = n;
+        int64_t rel_ptr;
+        if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
+          const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, (uint32_t)s >> 2, batch, TAG_REPLACE | (p.rel << 8), p.key0, p.key1);
+          rel_ptr = __umulhi(pick4(r, (uint32_t)s & 3u), s_deg[n]);  // sampling.rs:64
+        } else {
+          const uint32_t st = s_slot[e];
+          rel_ptr = st ? st : (uint32_t)s;
+        }
+        ptr[u] = s_start[n] + rel_ptr;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * HOP_THREADS;
+      val[u] = e < total ? ld_nc_na_i64(p.indices + ptr[u]) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * HOP_THREADS;
+      if (e < total) {
+        st_cs_i64(o_e + e, ptr[u]);
+        st_cs_i64(o_c + e, col0 + own[u]);
+        st_cs_i64(o_r + e, s_base + e);
+        o_s[e] = val[u];  // re-read as the next hop's frontier: keep in L2
+      }
+    }
+  }
+}
+
+// ---- host-side plan: which launches, which version rows of the length table ------------------
+struct Launch {
+  int rel, hop;
+  int fr_begin_row, fr_end_row;
+  int src_in_row, src_out_row;
+  int e_in_row, e_out_row;
+  int dst_len_row;
+  int64_t fanout;
+  int tile_nodes, tile_edges, tiles_per_batch;
+  size_t status_off;  // in uint64 words
+};
+
+struct Plan {
+  int T, R, H;
+  int64_t B;
+  std::vector<Launch> launches;
+  std::vector<int> n_row0;              // [T] initial length rows
+  std::vector<int> n_row_final;         // [T]
+  std::vector<int> e_row_final;         // [R]
+  std::vector<int> lo_rows;             // [R*H*3] rows for layer offsets, -1 = relation inactive
+  std::vector<int64_t> samples_cap, edges_cap;  // worst case per batch
+  int num_rows;                         // V
+  size_t status_words;
+  // workspace layout (bytes)
+  size_t off_ctrl, off_state, off_status, total_bytes;
+};
+
+constexpr size_t CTRL_WORDS = 64;  // uint32: [0] = err, [1..] = one ticket per launch (grown if needed)
+
+tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
+  TCHGEO_REQUIRE(a != nullptr, "args is NULL");
+  TCHGEO_REQUIRE(a->num_node_types > 0 && a->num_rels > 0 && a->num_hops >= 0, "bad T/R/H");
+  TCHGEO_REQUIRE(a->num_batches > 0 && a->num_batches < (1ll << 24), "num_batches out of range");
+  TCHGEO_REQUIRE(a->rel_src && a->rel_dst && (a->fanouts || a->num_hops == 0) && a->seeds_per_batch, "NULL host array");
+  TCHGEO_REQUIRE(a->sampler_kind >= 0 && a->sampler_kind <= 2, "unknown sampler kind");
+  pl.T = a->num_node_types; pl.R = a->num_rels; pl.H = a->num_hops; pl.B = a->num_batches;
+  const int T = pl.T, R = pl.R, H = pl.H;
+  for (int r = 0; r < R; ++r) {
+    TCHGEO_REQUIRE(a->rel_src[r] >= 0 && a->rel_src[r] < T && a->rel_dst[r] >= 0 && a->rel_dst[r] < T,
+                   "relation %d: node type index out of range", r);
+    for (int h = 0; h < H; ++h) {
+      const int64_t k = a->fanouts[(size_t)r * H + h];
+      TCHGEO_REQUIRE(k >= 0 && k <= MAX_FANOUT, "relation %d hop %d: fanout %lld unsupported (max %d)", r, h,
+                     (long long)k, MAX_FANOUT);
+    }
+  }
+  int rows = 1;  // row 0 = zeros
+  pl.n_row0.assign(T, 0);
+  std::vector<int> cur_n(T), sl_begin(T), sl_end(T), cur_e(R, 0);
+  std::vector<int64_t> wc_len(T), wc_front(T);
+  pl.samples_cap.assign(T, 0);
+  pl.edges_cap.assign(R, 0);
+  for (int t = 0; t < T; ++t) {
+    TCHGEO_REQUIRE(a->seeds_per_batch[t] >= 0, "negative seed count");
+    pl.n_row0[t] = rows++;
+    cur_n[t] = pl.n_row0[t];
+    sl_begin[t] = 0;
+    sl_end[t] = cur_n[t];
+    wc_len[t] = wc_front[t] = a->seeds_per_batch[t];
+  }
+  pl.lo_rows.assign((size_t)R * std::max(H, 1) * 3, -1);
+  pl.launches.clear();
+  size_t status_words = 0;
+  const int64_t LIM = (int64_t)1 << 40;
+  for (int h = 0; h < H; ++h) {
+    std::vector<int64_t> add(T, 0);
+    for (int r = 0; r < R; ++r) {
+      if (a->rel_active && !a->rel_active[r]) continue;
+      const int st = a->rel_src[r], dt = a->rel_dst[r];
+      const int64_t k = a->fanouts[(size_t)r * H + h];
+      int* lo = &pl.lo_rows[((size_t)r * H + h) * 3];
+      lo[0] = cur_n[st]; lo[1] = cur_e[r]; lo[2] = cur_n[dt];
+      const int64_t fcap = wc_front[dt];
+      if (fcap == 0 || k == 0) {
+        // nothing can be appended: lengths keep their current version rows.
+        // (k == 0 with a non-empty neighbourhood panics in the reference unless sampling with
+        //  replacement; that case is detected by a launch below only when k > 0, so flag it here.)
+        if (k == 0 && fcap > 0 && a->sampler_kind != TCHGEO_SAMPLER_UNIFORM_REPLACE) {
+          // keep the launch so the kernel can raise DEV_ERR_PANIC for deg > 0
+        } else {
+          continue;
+        }
+      }
+      Launch L;
+      L.rel = r; L.hop = h; L.fanout = k;
+      L.fr_begin_row = sl_begin[dt]; L.fr_end_row = sl_end[dt];
+      L.src_in_row = cur_n[st]; L.src_out_row = rows++;
+      L.e_in_row = cur_e[r]; L.e_out_row = rows++;
+      L.dst_len_row = cur_n[dt];
+      const int64_t kk = std::max<int64_t>(k, 1);
+      int tn = (int)std::min<int64_t>(HOP_THREADS, std::max<int64_t>(1, MAX_TILE_EDGES / kk));
+      L.tile_nodes = tn;
+      L.tile_edges = (int)(tn * kk);
+      const int64_t tpb = (fcap + tn - 1) / tn;
+      TCHGEO_REQUIRE(tpb * pl.B < ((int64_t)1 << 31), "grid too large: %lld tiles x %lld batches", (long long)tpb,
+                     (long long)pl.B);
+      L.tiles_per_batch = (int)tpb;
+      L.status_off = status_words;
+      status_words += (size_t)tpb * (size_t)pl.B;
+      pl.launches.push_back(L);
+      cur_n[st] = L.src_out_row;
+      cur_e[r] = L.e_out_row;
+      const int64_t n_new = fcap * k;
+      TCHGEO_REQUIRE(n_new < LIM && wc_len[st] + n_new < LIM, "worst-case output too large");
+      pl.edges_cap[r] += n_new;
+      add[st] += n_new;
+      wc_len[st] += n_new;
+    }
+    for (int t = 0; t < T; ++t) {  // neighbor_sampling.rs:345-348
+      sl_begin[t] = sl_end[t];
+      sl_end[t] = cur_n[t];
+      wc_front[t] = add[t];
+    }
+  }
+  for (int t = 0; t < T; ++t) pl.samples_cap[t] = wc_len[t];
+  pl.n_row_final = cur_n;
+  pl.e_row_final = cur_e;
+  pl.num_rows = rows;
+  pl.status_words = status_words;
+  const size_t ctrl_words = std::max(CTRL_WORDS, pl.launches.size() + 2);
+  pl.off_ctrl = 0;
+  pl.off_state = ((ctrl_words * 4 + 255) / 256) * 256;
+  pl.off_status = pl.off_state + (((size_t)rows * pl.B * 8 + 255) / 256) * 256;
+  pl.total_bytes = pl.off_status + status_words * 8 + 256;
+  return TCHGEO_OK;
+}
+
+template <int KIND>
+cudaError_t launch_hop(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+  static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    e = cudaFuncSetAttribute(hop_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  hop_kernel<KIND><<<(unsigned)grid, HOP_THREADS, smem, stream>>>(hp);
+  return cudaGetLastError();
+}
+
+}  // namespace
+}  // namespace tchgeo
+
+using namespace tchgeo;
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling_capacity(const tchgeo_sampling_args* args, int64_t* samples_cap,
+                                                           int64_t* edges_cap) {
+  Plan pl;
+  tchgeo_status st = build_plan(args, pl);
+  if (st != TCHGEO_OK) return st;
+  if (samples_cap) for (int t = 0; t < pl.T; ++t) samples_cap[t] = pl.samples_cap[t];
+  if (edges_cap) for (int r = 0; r < pl.R; ++r) edges_cap[r] = pl.edges_cap[r];
+  return TCHGEO_OK;
+}
+
+extern "C" size_t tchgeo_neighbor_sampling_workspace_bytes(const tchgeo_sampling_args* args) {
+  Plan pl;
+  if (build_plan(args, pl) != TCHGEO_OK) return 0;
+  return pl.total_bytes;
+}
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling_collect(const tchgeo_sampling_args* a) {
+  Plan pl;
+  tchgeo_status st = build_plan(a, pl);
+  if (st != TCHGEO_OK) return st;
+  TCHGEO_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= pl.total_bytes, "workspace too small");
+  cudaStream_t stream = (cudaStream_t)a->stream;
+  char* ws = (char*)a->workspace;
+  const size_t n_state = (size_t)pl.num_rows * pl.B;
+  std::vector<int64_t> state(n_state);
+  uint32_t err = 0;
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(state.data(), ws + pl.off_state, n_state * 8, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&err, ws + pl.off_ctrl, 4, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  const int T = pl.T, R = pl.R, H = pl.H;
+  const int64_t B = pl.B;
+  for (int64_t b = 0; b < B; ++b) {
+    if (a->samples_len)
+      for (int t = 0; t < T; ++t) a->samples_len[b * T + t] = state[(size_t)pl.n_row_final[t] * B + b];
+    if (a->edges_len)
+      for (int r = 0; r < R; ++r) a->edges_len[b * R + r] = state[(size_t)pl.e_row_final[r] * B + b];
+    if (a->layer_offsets)
+      for (int r = 0; r < R; ++r)
+        for (int h = 0; h < H; ++h)
+          for (int c = 0; c < 3; ++c) {
+            const int row = pl.lo_rows[((size_t)r * H + h) * 3 + c];
+            a->layer_offsets[(((size_t)b * R + r) * H + h) * 3 + c] = row < 0 ? -1 : state[(size_t)row * B + b];
+          }
+  }
+  return status_from_dev_err(err);
+}
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a) {
+  Plan pl;
+  tchgeo_status st = build_plan(a, pl);
+  if (st != TCHGEO_OK) return st;
+  const int T = pl.T, R = pl.R;
+  const int64_t B = pl.B;
+  TCHGEO_REQUIRE(a->col_ptrs && a->row_indices && a->num_cols && a->inputs && a->samples && a->samples_stride &&
+                     a->rows && a->cols && a->edge_index && a->edges_stride,
+                 "NULL pointer table");
+  TCHGEO_REQUIRE(a->workspace != nullptr, "workspace is NULL");
+  if (a->workspace_bytes < pl.total_bytes) {
+    set_last_error("workspace too small: need %zu bytes, got %zu", pl.total_bytes, a->workspace_bytes);
+    return TCHGEO_ERR_CAPACITY;
+  }
+  for (int t = 0; t < T; ++t) {
+    if (a->seeds_per_batch[t] > 0) TCHGEO_REQUIRE(a->inputs[t] != nullptr, "inputs[%d] is NULL", t);
+    if (a->samples_stride[t] < a->seeds_per_batch[t]) {
+      set_last_error("samples_stride[%d] smaller than the seed count", t);
+      return TCHGEO_ERR_CAPACITY;
+    }
+    if (a->samples_stride[t] > 0) TCHGEO_REQUIRE(a->samples[t] != nullptr, "samples[%d] is NULL", t);
+    TCHGEO_REQUIRE(a->samples_stride[t] < ((int64_t)1 << 32), "samples_stride[%d] must be < 2^32", t);
+  }
+  for (const Launch& L : pl.launches) {
+    const int r = L.rel;
+    TCHGEO_REQUIRE(a->col_ptrs[r] && a->num_cols[r] >= 0, "relation %d: col_ptrs is NULL", r);
+    TCHGEO_REQUIRE(a->row_indices[r] != nullptr, "relation %d: row_indices is NULL", r);
+    if (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED)
+      TCHGEO_REQUIRE(a->weights && a->weights[r], "relation %d: weighted sampler without weights", r);
+    if (a->edges_stride[r] > 0)
+      TCHGEO_REQUIRE(a->rows[r] && a->cols[r] && a->edge_index[r], "relation %d: NULL edge output", r);
+  }
+  cudaStream_t stream = (cudaStream_t)a->stream;
+  char* ws = (char*)a->workspace;
+  uint32_t* ctrl = (uint32_t*)(ws + pl.off_ctrl);
+  int64_t* state = (int64_t*)(ws + pl.off_state);
+  uint64_t* status = (uint64_t*)(ws + pl.off_status);
+
+  // control words, length table and look-back status all start at zero
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(ws, 0, pl.total_bytes, stream));
+  for (int t = 0; t < T; ++t) {
+    const int64_t S = a->seeds_per_batch[t];
+    if (S == 0) continue;
+    // samples[t][b, 0:S] = inputs[t][b, :]   (neighbor_sampling.rs:184 / :264-271)
+    TCHGEO_CUDA_CHECK(cudaMemcpy2DAsync(a->samples[t], (size_t)a->samples_stride[t] * 8, a->inputs[t], (size_t)S * 8,
+                                        (size_t)S * 8, (size_t)B, cudaMemcpyDeviceToDevice, stream));
+    fill_i64_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(state + (size_t)pl.n_row0[t] * B, S, B);
+    TCHGEO_CUDA_CHECK(cudaGetLastError());
+  }
+  int li = 0;
+  for (const Launch& L : pl.launches) {
+    const int r = L.rel, stt = a->rel_src[r], dtt = a->rel_dst[r];
+    HopParams hp;
+    hp.ptrs = a->col_ptrs[r];
+    hp.indices = a->row_indices[r];
+    hp.weights = (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED) ? a->weights[r] : nullptr;
+    hp.num_cols = a->num_cols[r];
+    hp.dst_samples = a->samples[dtt];
+    hp.dst_stride = a->samples_stride[dtt];
+    hp.src_samples = a->samples[stt];
+    hp.src_stride = a->samples_stride[stt];
+    hp.rows = a->rows[r];
+    hp.cols = a->cols[r];
+    hp.eidx = a->edge_index[r];
+    hp.e_stride = a->edges_stride[r];
+    hp.fr_begin = state + (size_t)L.fr_begin_row * B;
+    hp.fr_end = state + (size_t)L.fr_end_row * B;
+    hp.src_len_in = state + (size_t)L.src_in_row * B;
+    hp.src_len_out = state + (size_t)L.src_out_row * B;
+    hp.e_len_in = state + (size_t)L.e_in_row * B;
+    hp.e_len_out = state + (size_t)L.e_out_row * B;
+    hp.status = status + L.status_off;
+    hp.ticket = ctrl + 1 + li;
+    hp.err = ctrl;
+    hp.tiles_per_batch = L.tiles_per_batch;
+    hp.tile_nodes = L.tile_nodes;
+    hp.tile_edges = L.tile_edges;
+    hp.fanout = (int32_t)L.fanout;
+    hp.key0 = (uint32_t)a->seed;
+    hp.key1 = (uint32_t)(a->seed >> 32);
+    hp.rel = (uint32_t)r;
+    hp.batch_base = a->batch_base;
+    const int64_t grid = (int64_t)L.tiles_per_batch * B;
+    const size_t smem = (size_t)L.tile_edges * 5 + 16;
+    cudaError_t e;
+    switch (a->sampler_kind) {
+      case TCHGEO_SAMPLER_UNIFORM: e = launch_hop<TCHGEO_SAMPLER_UNIFORM>(hp, grid, smem, stream); break;
+      case TCHGEO_SAMPLER_UNIFORM_REPLACE: e = launch_hop<TCHGEO_SAMPLER_UNIFORM_REPLACE>(hp, grid, smem, stream); break;
+      default: e = launch_hop<TCHGEO_SAMPLER_WEIGHTED>(hp, grid, smem, stream); break;
+    }
+    TCHGEO_CUDA_CHECK(e);
+    ++li;
+  }
+  if (a->samples_len || a->edges_len || a->layer_offsets) return tchgeo_neighbor_sampling_collect(a);
+  return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling_homogenous(
+    const int64_t* col_ptrs, int64_t num_cols, const int64_t* row_indices, const int64_t* inputs, int64_t num_batches,
+    int64_t seeds_per_batch, const int64_t* num_neighbors, int32_t num_hops, int32_t sampler_kind,
+    const double* weights, uint64_t seed, uint32_t batch_base, int64_t* samples, int64_t samples_stride, int64_t* rows,
+    int64_t* cols, int64_t* edge_index, int64_t edges_stride, int64_t* out_lens, int64_t* layer_offsets,
+    void* workspace, size_t workspace_bytes, tchgeo_stream stream) {
+  const int32_t zero = 0;
+  tchgeo_sampling_args a;
+  memset(&a, 0, sizeof(a));
+  a.num_node_types = 1; a.num_rels = 1; a.num_hops = num_hops; a.sampler_kind = sampler_kind;
+  a.rel_src = &zero; a.rel_dst = &zero;
+  a.col_ptrs = &col_ptrs; a.num_cols = &num_cols; a.row_indices = &row_indices; a.weights = &weights;
+  a.fanouts = num_neighbors; a.rel_active = nullptr;
+  a.num_batches = num_batches; a.inputs = &inputs; a.seeds_per_batch = &seeds_per_batch;
+  a.seed = seed; a.batch_base = batch_base;
+  a.samples = &samples; a.samples_stride = &samples_stride;
+  a.rows = &rows; a.cols = &cols; a.edge_index = &edge_index; a.edges_stride = &edges_stride;
+  std::vector<int64_t> slen, elen;
+  if (out_lens) {
+    slen.resize((size_t)std::max<int64_t>(num_batches, 1));
+    elen.resize((size_t)std::max<int64_t>(num_batches, 1));
+    a.samples_len = slen.data();
+    a.edges_len = elen.data();
+  }
+  a.layer_offsets = layer_offsets;
+  a.workspace = workspace; a.workspace_bytes = workspace_bytes; a.stream = stream;
+  tchgeo_status st = tchgeo_neighbor_sampling(&a);
+  if (out_lens && (st == TCHGEO_OK || st >= TCHGEO_ERR_CAPACITY))
+    for (int64_t b = 0; b < num_batches; ++b) {
+      out_lens[2 * b] = slen[(size_t)b];
+      out_lens[2 * b + 1] = elen[(size_t)b];
+    }
+  return st;
+}

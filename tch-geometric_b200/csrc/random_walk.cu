@@ -1,0 +1,183 @@
+// node2vec p/q-biased random walk over CSR for sm_100a.
+//
+// Replaces src/algo/random_walk.rs:10-75 of the reference (rejection sampling, :52-66, with
+// has_edge = binary search in the candidate's sorted adjacency, src/data/graph.rs:80-83).
+//
+// One thread per walker.  Every attempt draws (neighbour index, f32 uniform) from
+// Philox(seed; walker, step, attempt/2), so a walk does not depend on launch geometry or sharding.
+// Exact shortcuts that do not change any outcome:
+//   * the binary search is skipped when the uniform already decides the attempt
+//     (r < min(prob1, prob2) accepts, r >= max(prob1, prob2) rejects, whatever has_edge says);
+//   * prev == -1 on the first step never matches (quirk Q8), no search;
+//   * the accepted candidate's (row_ptrs[next], row_ptrs[next+1]) pair is carried into the next step.
+// Output rows are [walk_length+1] i64 (648 B for length 80): each warp stages 32 walkers x 16 steps
+// in shared memory and writes 128-byte runs instead of 8-byte strided stores; dead walkers and the
+// -1 padding are written by the same path, so no separate fill(-1) pass over the output is needed.
+#include "common.cuh"
+
+namespace tchgeo {
+namespace {
+
+constexpr int WALK_THREADS = 256;
+constexpr int WALK_CHUNK = 16;
+constexpr uint32_t WALK_MAX_ATTEMPTS = 1u << 25;
+
+struct WalkParams {
+  const int64_t* row_ptrs;
+  const int64_t* col_indices;
+  const int64_t* start;
+  int64_t* walks;
+  unsigned long long* attempts;
+  uint32_t* err;
+  int64_t num_rows;
+  int64_t num_walks;
+  int64_t walk_length;
+  int64_t walker_base;
+  float prob0, prob1, prob2;
+  uint32_t key0, key1;
+};
+
+__device__ __forceinline__ bool has_edge_dev(const int64_t* __restrict__ col, int64_t lo, int64_t hi, int64_t y) {
+  while (lo < hi) {  // graph.rs:80-83
+    const int64_t mid = lo + ((hi - lo) >> 1);
+    const int64_t v = __ldg(col + mid);
+    if (v == y) return true;
+    if (v < y) lo = mid + 1; else hi = mid;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) {
+  __shared__ int64_t tile[WALK_THREADS / 32][32][WALK_CHUNK + 1];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * WALK_THREADS + threadIdx.x;
+  const int64_t warp_first = i - lane;
+  const int64_t L = p.walk_length + 1;
+  const bool active = i < p.num_walks;
+  const uint64_t walker = (uint64_t)(p.walker_base + i);
+  const float pmin = fminf(p.prob1, p.prob2), pmax = fmaxf(p.prob1, p.prob2);
+
+  int64_t cur = active ? p.start[i] : -1;
+  int64_t prev = -1;
+  int64_t nb = 0, ne = 0, pnb = 0, pne = 0;
+  bool alive = active;
+  if (alive) {
+    if (cur < 0 || cur >= p.num_rows) {
+      atomicOr(p.err, DEV_ERR_INDEX);
+      alive = false;
+    } else {
+      nb = __ldg(p.row_ptrs + cur);
+      ne = __ldg(p.row_ptrs + cur + 1);
+    }
+  }
+  unsigned long long my_attempts = 0;
+
+  for (int64_t c0 = 0; c0 < L; c0 += WALK_CHUNK) {
+    const int nc = (int)min((int64_t)WALK_CHUNK, L - c0);
+    for (int cc = 0; cc < nc; ++cc) {
+      const int64_t colidx = c0 + cc;
+      int64_t out;
+      if (colidx == 0) {
+        out = cur;  // walks[i, 0] = start, random_walk.rs:41
+      } else {
+        if (alive) {
+          const int64_t d = ne - nb;
+          if (d <= 0) {
+            alive = false;  // random_walk.rs:45-47: the rest of the row stays -1
+          } else {
+            const uint32_t l = (uint32_t)(colidx - 1);
+            int64_t next = -1, nnb = 0, nne = 0;
+            Philox4 r4 = {0, 0, 0, 0};
+            bool accepted = false;
+            for (uint32_t a = 0; a < WALK_MAX_ATTEMPTS; ++a) {
+              if ((a & 1u) == 0u)
+                r4 = philox4x32_10((uint32_t)walker, (uint32_t)(walker >> 32), l, TAG_WALK | ((a >> 1) << 8), p.key0, p.key1);
+              const uint32_t ri = (a & 1u) ? r4.z : r4.x;
+              const uint32_t rf = (a & 1u) ? r4.w : r4.y;
+              next = __ldg(p.col_indices + nb + (int64_t)__umulhi(ri, (uint32_t)d));  // :53
+              const float r = (float)(rf >> 8) * (1.0f / 16777216.0f);               // :54
+              ++my_attempts;
+              if (next == prev) {  // :56-58
+                if (r < p.prob0) { nnb = pnb; nne = pne; accepted = true; break; }
+                continue;
+              }
+              if (r >= pmax) continue;  // rejected whatever has_edge says
+              if (next < 0 || next >= p.num_rows) { atomicOr(p.err, DEV_ERR_INDEX); break; }
+              nnb = __ldg(p.row_ptrs + next);
+              nne = __ldg(p.row_ptrs + next + 1);
+              if (r < pmin) { accepted = true; break; }  // accepted whatever has_edge says
+              const bool he = prev >= 0 && has_edge_dev(p.col_indices, nnb, nne, prev);  // :59
+              if (he ? (r < p.prob1) : (r < p.prob2)) { accepted = true; break; }        // :60-65
+            }
+            if (accepted) {
+              prev = cur; pnb = nb; pne = ne;  // :68-69
+              cur = next; nb = nnb; ne = nne;
+            } else {
+              if (next >= 0 && next < p.num_rows) atomicOr(p.err, DEV_ERR_WATCHDOG);
+              alive = false;
+            }
+          }
+        }
+        out = alive ? cur : -1;
+      }
+      tile[warp][lane][cc] = out;
+    }
+    __syncwarp();
+    // cooperative write-out: 32 rows x nc columns, runs of nc contiguous i64 per row
+    for (int idx = lane; idx < 32 * nc; idx += 32) {
+      const int r = idx / nc, cc = idx - r * nc;
+      const int64_t wi = warp_first + r;
+      if (wi < p.num_walks) st_cs_i64(p.walks + wi * L + c0 + cc, tile[warp][r][cc]);
+    }
+    __syncwarp();
+  }
+  if (p.attempts) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_attempts += __shfl_xor_sync(0xffffffffu, my_attempts, o);
+    if (lane == 0 && my_attempts) atomicAdd(p.attempts, my_attempts);
+  }
+}
+
+}  // namespace
+}  // namespace tchgeo
+
+using namespace tchgeo;
+
+extern "C" tchgeo_status tchgeo_random_walk(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,
+                                            const int64_t* start, int64_t num_walks, int64_t walk_length, float p,
+                                            float q, uint64_t seed, int64_t walker_base, int64_t* walks,
+                                            int64_t* stats, int64_t* attempts_out, tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(num_walks >= 0 && walk_length >= 0 && num_rows >= 0, "negative size");
+  TCHGEO_REQUIRE(row_ptrs && stats && (num_walks == 0 || (start && walks)), "NULL pointer");
+  TCHGEO_REQUIRE(walk_length < ((int64_t)1 << 31), "walk_length too large");
+  // "p or q may not be 0 or nan", random_walk.rs:30
+  TCHGEO_REQUIRE(p == p && q == q && p != 0.0f && q != 0.0f, "p or q may not be 0 or nan");
+  if (attempts_out) *attempts_out = 0;
+  if (num_walks == 0) return TCHGEO_OK;
+  // random_walk.rs:29-36, f32 arithmetic; max_by keeps the last maximum
+  const float a = 1.0f / p, b = 1.0f, c = 1.0f / q;
+  float max_prob = a;
+  if (b >= max_prob) max_prob = b;
+  if (c >= max_prob) max_prob = c;
+  WalkParams wp;
+  wp.row_ptrs = row_ptrs; wp.col_indices = col_indices; wp.start = start; wp.walks = walks;
+  wp.attempts = (unsigned long long*)stats;
+  wp.err = (uint32_t*)(stats + 1);
+  wp.num_rows = num_rows; wp.num_walks = num_walks; wp.walk_length = walk_length; wp.walker_base = walker_base;
+  wp.prob0 = 1.0f / p / max_prob;
+  wp.prob1 = 1.0f / max_prob;
+  wp.prob2 = 1.0f / q / max_prob;
+  wp.key0 = (uint32_t)seed; wp.key1 = (uint32_t)(seed >> 32);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(stats, 0, 16, stream));
+  const int64_t grid = (num_walks + WALK_THREADS - 1) / WALK_THREADS;
+  TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many walkers for one launch");
+  walk_kernel<<<(unsigned)grid, WALK_THREADS, 0, stream>>>(wp);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  int64_t h[2] = {0, 0};
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(h, stats, 16, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (attempts_out) *attempts_out = h[0];
+  return status_from_dev_err((uint32_t)h[1]);
+}

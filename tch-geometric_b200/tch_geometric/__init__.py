@@ -1,0 +1,34 @@
+"""tch_geometric -- B200-native (sm_100a) drop-in for the reference module's sampling hot path.
+
+Mirrors `tch_geometric/__init__.py:1-2` + `tch_geometric.pyi` of the reference for the functions on
+the path (to_csc, to_csr, neighbor_sampling_homogenous, neighbor_sampling_heterogenous, random_walk);
+everything else in the reference (hgt/budget sampling, temporal walks, negative sampling) stays on the
+reference's CPU implementation and is not provided here.  Importing this package loads
+libtchgeo_cuda.so and fails if it has not been built: there is no CPU fallback.
+"""
+from . import _native  # noqa: F401  (loads the CUDA library, raises if missing)
+from .ops import (  # noqa: F401
+    HomogenousSampler,
+    SampledBatches,
+    ind2ptr,
+    neighbor_sampling_heterogenous,
+    neighbor_sampling_homogenous,
+    neighbor_sampling_homogenous_batched,
+    random_walk,
+    rel_key,
+    rng_reseed,
+    to_csc,
+    to_csr,
+    unique_relabel,
+)
+from .utils import (  # noqa: F401
+    TEMPORAL_SAMPLE_DYNAMIC,
+    TEMPORAL_SAMPLE_RELATIVE,
+    TEMPORAL_SAMPLE_STATIC,
+    EdgeFilter,
+    EdgeSampler,
+    TemporalEdgeFilter,
+    UniformEdgeSampler,
+    WeightedEdgeSampler,
+)
+from ._native import ReferencePanic  # noqa: F401

@@ -1,0 +1,106 @@
+"""ctypes binding of libtchgeo_cuda.so (the C ABI in include/tchgeo_cuda.h).
+
+This is the Python counterpart of the `extern "C"` block the reference's Rust host (src/python.rs)
+would carry: raw device pointers from `Tensor.data_ptr()` are passed straight through.  There is no
+fallback: if the CUDA library is missing, importing this module raises.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtchgeo_cuda.so")
+
+OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_INDEX, ERR_REFERENCE_PANIC, ERR_INTERNAL = range(7)
+SAMPLER_UNIFORM, SAMPLER_UNIFORM_REPLACE, SAMPLER_WEIGHTED = 0, 1, 2
+ABI_VERSION = 1
+
+c_i64, c_i32, c_u64, c_u32, c_vp, c_sz = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32,
+                                          ctypes.c_void_p, ctypes.c_size_t)
+
+
+class SamplingArgs(ctypes.Structure):
+    """struct tchgeo_sampling_args (field order must match include/tchgeo_cuda.h)."""
+    _fields_ = [
+        ("num_node_types", c_i32), ("num_rels", c_i32), ("num_hops", c_i32), ("sampler_kind", c_i32),
+        ("rel_src", c_vp), ("rel_dst", c_vp),
+        ("col_ptrs", c_vp), ("num_cols", c_vp), ("row_indices", c_vp), ("weights", c_vp),
+        ("fanouts", c_vp), ("rel_active", c_vp),
+        ("num_batches", c_i64), ("inputs", c_vp), ("seeds_per_batch", c_vp),
+        ("seed", c_u64), ("batch_base", c_u32), ("reserved0", c_u32),
+        ("samples", c_vp), ("samples_stride", c_vp),
+        ("rows", c_vp), ("cols", c_vp), ("edge_index", c_vp), ("edges_stride", c_vp),
+        ("samples_len", c_vp), ("edges_len", c_vp), ("layer_offsets", c_vp),
+        ("workspace", c_vp), ("workspace_bytes", c_sz), ("stream", c_vp),
+    ]
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python tch-geometric_b200/build.py` "
+            "(nvcc, sm_100a). tch_geometric (B200) has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    lib.tchgeo_abi_version.restype = c_i32
+    lib.tchgeo_last_error.restype = ctypes.c_char_p
+    lib.tchgeo_ind2ptr.restype = c_i32
+    lib.tchgeo_ind2ptr.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp]
+    lib.tchgeo_coo_to_csx_workspace_bytes.restype = c_sz
+    lib.tchgeo_coo_to_csx_workspace_bytes.argtypes = [c_i64, c_i64, c_i64]
+    lib.tchgeo_coo_to_csx.restype = c_i32
+    lib.tchgeo_coo_to_csx.argtypes = [c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
+    P = ctypes.POINTER(SamplingArgs)
+    lib.tchgeo_neighbor_sampling_capacity.restype = c_i32
+    lib.tchgeo_neighbor_sampling_capacity.argtypes = [P, c_vp, c_vp]
+    lib.tchgeo_neighbor_sampling_workspace_bytes.restype = c_sz
+    lib.tchgeo_neighbor_sampling_workspace_bytes.argtypes = [P]
+    lib.tchgeo_neighbor_sampling.restype = c_i32
+    lib.tchgeo_neighbor_sampling.argtypes = [P]
+    lib.tchgeo_neighbor_sampling_collect.restype = c_i32
+    lib.tchgeo_neighbor_sampling_collect.argtypes = [P]
+    lib.tchgeo_neighbor_sampling_homogenous.restype = c_i32
+    lib.tchgeo_neighbor_sampling_homogenous.argtypes = [
+        c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_vp, c_i32, c_i32, c_vp, c_u64, c_u32,
+        c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.tchgeo_random_walk.restype = c_i32
+    lib.tchgeo_random_walk.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_u64,
+                                       c_i64, c_vp, c_vp, c_vp, c_vp]
+    lib.tchgeo_unique_relabel_workspace_bytes.restype = c_sz
+    lib.tchgeo_unique_relabel_workspace_bytes.argtypes = [c_i64]
+    lib.tchgeo_unique_relabel.restype = c_i32
+    lib.tchgeo_unique_relabel.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
+    if lib.tchgeo_abi_version() != ABI_VERSION:
+        raise ImportError("libtchgeo_cuda.so ABI version mismatch")
+    return lib
+
+
+lib = _load()
+
+EXPORTS = [
+    "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
+    "tchgeo_coo_to_csx", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
+    "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
+    "tchgeo_random_walk", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
+]
+
+
+def last_error():
+    return lib.tchgeo_last_error().decode("utf-8", "replace")
+
+
+class ReferencePanic(RuntimeError):
+    """Input on which the reference panics (pyo3 PanicException there)."""
+
+
+def check(status):
+    """Map a tchgeo_status to the reference's error behaviour: TensorConversionError -> ValueError
+    (src/utils/tensor.rs:22-27); inputs the reference panics on -> ReferencePanic."""
+    if status == OK:
+        return
+    msg = last_error()
+    if status in (ERR_INDEX, ERR_REFERENCE_PANIC):
+        raise ReferencePanic(msg)
+    if status == ERR_CAPACITY:
+        raise MemoryError(msg)
+    if status in (ERR_CUDA, ERR_INTERNAL):
+        raise RuntimeError(msg)
+    raise ValueError(msg)

@@ -1,0 +1,451 @@
+"""Host side of the B200 sampling path: the Python mirror of the reference's binding layer
+(src/python.rs) for to_csc / to_csr / neighbor_sampling_homogenous / neighbor_sampling_heterogenous /
+random_walk.  Same names, argument meaning, return layouts and error behaviour as
+tch_geometric/tch_geometric.pyi; tensors live on a CUDA device instead of the CPU
+(src/utils/tensor.rs:50-52 becomes a CUDA-device check on this path).
+
+torch is used only for device memory and streams; all compute happens behind the C ABI of
+libtchgeo_cuda.so (include/tchgeo_cuda.h).  There is no CPU fallback.
+"""
+import ctypes
+import os
+import threading
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+from torch import Tensor
+
+from . import _native as N
+
+LayerOffset = Tuple[int, int, int]
+
+# ---------------------------------------------------------------------------------------------
+# process-global RNG, mirroring src/utils/random.rs:8-23: entropy-seeded, every API call forks a
+# child stream (here: a fresh 64-bit Philox key).  rng_reseed exists in the reference but has no
+# Python binding (python.rs:785-796); it is exported here because tests need reproducibility.
+# ---------------------------------------------------------------------------------------------
+_rng_lock = threading.Lock()
+_rng_state = int.from_bytes(os.urandom(8), "little")
+_MASK64 = (1 << 64) - 1
+
+
+def rng_reseed(seed: int) -> None:
+    global _rng_state
+    with _rng_lock:
+        _rng_state = int(seed) & _MASK64
+
+
+def splitmix64(state: int) -> Tuple[int, int]:
+    """One splitmix64 step: (state) -> (new_state, output)."""
+    state = (state + 0x9E3779B97F4A7C15) & _MASK64
+    z = state
+    z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & _MASK64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _MASK64
+    return state, z ^ (z >> 31)
+
+
+def _rng_get() -> int:
+    """One child seed per API call (random.rs:19-23)."""
+    global _rng_state
+    with _rng_lock:
+        _rng_state, out = splitmix64(_rng_state)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor plumbing (src/utils/tensor.rs:10-70)
+# ---------------------------------------------------------------------------------------------
+def _check(t, dtype, name, device=None):
+    if not isinstance(t, Tensor):
+        raise ValueError(f"{name} must be a torch.Tensor")
+    if not t.is_cuda:
+        raise ValueError(f"Tensor must be on Cuda device ({name} is on {t.device})")  # InvalidDevice
+    if device is not None and t.device != device:
+        raise ValueError(f"Tensor must be on {device} device ({name} is on {t.device})")
+    if t.dtype != dtype:
+        raise ValueError(f"Tensor must be a is of invalid type. Expected {dtype} but got {t.dtype} ({name})")
+    if not t.is_contiguous():
+        # the reference silently reads garbage here (quirk Q10); refuse instead
+        raise ValueError(f"{name} must be contiguous")
+    return t
+
+
+def _stream(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr() if t is not None else 0)
+
+
+def _size_tuple(size) -> Tuple[int, int]:
+    """GraphSize, python.rs:12-25"""
+    if isinstance(size, (tuple, list)):
+        if len(size) != 2:
+            raise ValueError("size must be an int or a pair of ints")
+        return int(size[0]), int(size[1])
+    return int(size), int(size)
+
+
+# ---------------------------------------------------------------------------------------------
+# to_csc / to_csr (python.rs:27-53 -> storage.rs:103-127)
+# ---------------------------------------------------------------------------------------------
+def _to_csx(row_col: Tensor, size, csc: bool):
+    _check(row_col, torch.int64, "row_col")
+    if row_col.dim() != 2 or row_col.shape[0] != 2:
+        raise ValueError("Tensor must be of rank [2, E]")
+    n_rows, n_cols = _size_tuple(size)
+    dev = row_col.device
+    E = row_col.shape[1]
+    n_major = n_cols if csc else n_rows
+    with torch.cuda.device(dev):
+        ptrs = torch.empty(n_major + 1, dtype=torch.int64, device=dev)
+        indices = torch.empty(E, dtype=torch.int64, device=dev)
+        perm = torch.empty(E, dtype=torch.int64, device=dev)
+        ws_bytes = N.lib.tchgeo_coo_to_csx_workspace_bytes(E, n_rows, n_cols)
+        ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+        st = N.lib.tchgeo_coo_to_csx(_ptr(row_col[0]), _ptr(row_col[1]), E, n_rows, n_cols, 1 if csc else 0,
+                                     _ptr(ptrs), _ptr(indices), _ptr(perm), _ptr(ws), ws_bytes, _stream(dev))
+    N.check(st)
+    return ptrs, indices, perm
+
+
+def to_csc(row_col: Tensor, size: Union[int, Tuple[int, int]]) -> Tuple[Tensor, Tensor, Tensor]:
+    return _to_csx(row_col, size, True)
+
+
+def to_csr(row_col: Tensor, size: Union[int, Tuple[int, int]]) -> Tuple[Tensor, Tensor, Tensor]:
+    return _to_csx(row_col, size, False)
+
+
+def ind2ptr(ind: Tensor, m: int) -> Tensor:
+    """storage.rs:67-101 (not exported by the reference's Python module; exposed for its KAT)."""
+    _check(ind, torch.int64, "ind")
+    out = torch.empty(m + 1, dtype=torch.int64, device=ind.device)
+    with torch.cuda.device(ind.device):
+        N.check(N.lib.tchgeo_ind2ptr(_ptr(ind), ind.numel(), m, _ptr(out), _stream(ind.device)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# sampler / filter argument extraction (python.rs:107-168)
+# ---------------------------------------------------------------------------------------------
+def _extract_sampler(sampler, hetero: bool):
+    """SamplerType is tried in declaration order: Uniform(with_replacement) then Weighted(weights)."""
+    if sampler is None:
+        return N.SAMPLER_UNIFORM, None
+    wr = getattr(sampler, "with_replacement", None)
+    if isinstance(wr, bool):
+        return (N.SAMPLER_UNIFORM_REPLACE if wr else N.SAMPLER_UNIFORM), None
+    w = getattr(sampler, "weights", None)
+    if w is not None:
+        if hetero != isinstance(w, dict):
+            raise ValueError("Unknown error: data must be %s" % ("heterogenous" if hetero else "homogenous"))
+        return N.SAMPLER_WEIGHTED, w
+    # pyo3 fails the Option<SamplerType> extraction with a TypeError
+    raise TypeError("sampler must have a `with_replacement: bool` or a `weights` attribute")
+
+
+def _reject_filter(filter):
+    if filter is not None:
+        raise NotImplementedError(
+            "TemporalFilter (python.rs:137-168) is not on the B200 path yet (SURVEY.md §8 row F1)")
+
+
+# ---------------------------------------------------------------------------------------------
+# generic driver over tchgeo_neighbor_sampling
+# ---------------------------------------------------------------------------------------------
+class _Call:
+    """Owns the host arrays, output tensors and workspace of one tchgeo_neighbor_sampling call."""
+
+    def __init__(self, device, rel_src, rel_dst, col_ptrs, row_indices, weights, fanouts, rel_active, inputs, seeds,
+                 num_batches, num_hops, sampler_kind, seed, batch_base=0):
+        T, R, H, B = len(seeds), len(rel_src), num_hops, num_batches
+        self.T, self.R, self.H, self.B, self.device = T, R, H, B, device
+        a = N.SamplingArgs()
+        self.args = a
+        k = self._keep = []
+
+        def host(arr, dtype):
+            x = np.ascontiguousarray(np.asarray(arr, dtype=dtype))
+            k.append(x)
+            return x
+
+        def ptr_table(tensors):
+            x = np.array([(t.data_ptr() if t is not None else 0) for t in tensors], dtype=np.uint64)
+            k.append(x)
+            k.append(list(tensors))
+            return x
+
+        a.num_node_types, a.num_rels, a.num_hops, a.sampler_kind = T, R, H, sampler_kind
+        a.rel_src = host(rel_src, np.int32).ctypes.data
+        a.rel_dst = host(rel_dst, np.int32).ctypes.data
+        a.col_ptrs = ptr_table(col_ptrs).ctypes.data
+        a.num_cols = host([(t.numel() - 1 if t is not None else 0) for t in col_ptrs], np.int64).ctypes.data
+        a.row_indices = ptr_table(row_indices).ctypes.data
+        a.weights = ptr_table(weights).ctypes.data if weights is not None else None
+        a.fanouts = host(fanouts, np.int64).ctypes.data
+        a.rel_active = host(rel_active, np.uint8).ctypes.data
+        a.num_batches = B
+        a.inputs = ptr_table(inputs).ctypes.data
+        a.seeds_per_batch = host(seeds, np.int64).ctypes.data
+        a.seed = seed
+        a.batch_base = batch_base
+        cap_n = np.zeros(T, dtype=np.int64)
+        cap_e = np.zeros(R, dtype=np.int64)
+        N.check(N.lib.tchgeo_neighbor_sampling_capacity(ctypes.byref(a), cap_n.ctypes.data, cap_e.ctypes.data))
+        self.cap_n, self.cap_e = cap_n, cap_e
+        k += [cap_n, cap_e]
+        i64 = dict(dtype=torch.int64, device=device)
+        self.samples = [torch.empty((B, int(c)), **i64) for c in cap_n]
+        self.rows = [torch.empty((B, int(c)), **i64) for c in cap_e]
+        self.cols = [torch.empty((B, int(c)), **i64) for c in cap_e]
+        self.eidx = [torch.empty((B, int(c)), **i64) for c in cap_e]
+        a.samples = ptr_table(self.samples).ctypes.data
+        a.samples_stride = cap_n.ctypes.data
+        a.rows = ptr_table(self.rows).ctypes.data
+        a.cols = ptr_table(self.cols).ctypes.data
+        a.edge_index = ptr_table(self.eidx).ctypes.data
+        a.edges_stride = cap_e.ctypes.data
+        self.samples_len = np.zeros((B, T), dtype=np.int64)
+        self.edges_len = np.zeros((B, R), dtype=np.int64)
+        self.layer_offsets = np.zeros((B, R, max(H, 1), 3), dtype=np.int64)
+        a.samples_len = self.samples_len.ctypes.data
+        a.edges_len = self.edges_len.ctypes.data
+        a.layer_offsets = self.layer_offsets.ctypes.data
+        ws_bytes = N.lib.tchgeo_neighbor_sampling_workspace_bytes(ctypes.byref(a))
+        self.workspace = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=device)
+        a.workspace = self.workspace.data_ptr()
+        a.workspace_bytes = ws_bytes
+
+    def run(self, seed=None, batch_base=None):
+        a = self.args
+        if seed is not None:
+            a.seed = seed
+        if batch_base is not None:
+            a.batch_base = batch_base
+        with torch.cuda.device(self.device):
+            a.stream = torch.cuda.current_stream(self.device).cuda_stream
+            N.check(N.lib.tchgeo_neighbor_sampling(ctypes.byref(a)))
+        return self
+
+
+def _as_seed_matrix(inputs: Tensor, device, name="inputs") -> Tensor:
+    if not isinstance(inputs, Tensor):
+        raise ValueError(f"{name} must be a torch.Tensor")
+    if inputs.dtype != torch.int64:
+        raise ValueError(f"Tensor must be a is of invalid type. Expected torch.int64 but got {inputs.dtype} ({name})")
+    if inputs.device != device:
+        # seeds usually come from a host-side loader: one small H2D copy (async if pinned)
+        inputs = inputs.to(device, non_blocking=True)
+    return inputs.contiguous()
+
+
+def neighbor_sampling_homogenous(
+        col_ptrs: Tensor,
+        row_indices: Tensor,
+        inputs: Tensor,
+        num_neighbors: List[int],
+        sampler=None,
+        filter=None,
+) -> Tuple[Tensor, Tensor, Tensor, Tensor, List[LayerOffset]]:
+    """python.rs:187-271.  Returns (samples, rows, cols, edge_index, layer_offsets)."""
+    call = _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, filter, batched=False)
+    call.run(seed=_rng_get())
+    ns, ne = int(call.samples_len[0, 0]), int(call.edges_len[0, 0])
+    lo = [tuple(int(x) for x in call.layer_offsets[0, 0, h]) for h in range(call.H)]
+    return call.samples[0][0, :ns], call.rows[0][0, :ne], call.cols[0][0, :ne], call.eidx[0][0, :ne], lo
+
+
+def _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, filter, batched):
+    _reject_filter(filter)
+    _check(col_ptrs, torch.int64, "col_ptrs")
+    dev = col_ptrs.device
+    _check(row_indices, torch.int64, "row_indices", dev)
+    kind, w = _extract_sampler(sampler, hetero=False)
+    if w is not None:
+        _check(w, torch.float64, "weights", dev)
+    inputs = _as_seed_matrix(inputs, dev)
+    if batched:
+        if inputs.dim() != 2:
+            raise ValueError("batched inputs must have shape [B, S]")
+        B, S = inputs.shape
+    else:
+        B, S = 1, inputs.numel()
+    fan = [int(k) for k in num_neighbors]
+    if any(k < 0 for k in fan):
+        raise OverflowError("can't convert negative int to unsigned")  # Vec<usize> extraction
+    return _Call(dev, [0], [0], [col_ptrs], [row_indices], [w] if w is not None else None, fan, [1], [inputs], [S],
+                 max(B, 1), len(fan), kind, 0)
+
+
+class SampledBatches:
+    """Result of neighbor_sampling_homogenous_batched: B independent reference-layout results that
+    share padded [B, capacity] buffers.  `batch(b)` is exactly what the reference returns for inputs[b]."""
+
+    def __init__(self, call):
+        self._call = call
+        self.samples, self.rows, self.cols, self.edge_index = call.samples[0], call.rows[0], call.cols[0], call.eidx[0]
+        self.samples_len = call.samples_len[:, 0]
+        self.edges_len = call.edges_len[:, 0]
+        self.layer_offsets = call.layer_offsets[:, 0]
+
+    def __len__(self):
+        return self._call.B
+
+    def batch(self, b):
+        ns, ne = int(self.samples_len[b]), int(self.edges_len[b])
+        lo = [tuple(int(x) for x in self.layer_offsets[b, h]) for h in range(self._call.H)]
+        return self.samples[b, :ns], self.rows[b, :ne], self.cols[b, :ne], self.edge_index[b, :ne], lo
+
+
+class HomogenousSampler:
+    """Reusable plan for repeated batched sampling over one graph (extension; not in the reference).
+    Output buffers and workspace are allocated once; `sample(inputs)` enqueues B batches in H launches."""
+
+    def __init__(self, col_ptrs, row_indices, num_batches, seeds_per_batch, num_neighbors, sampler=None):
+        dev = col_ptrs.device
+        self._inputs = torch.zeros((num_batches, seeds_per_batch), dtype=torch.int64, device=dev)
+        self._call = _homogenous_call(col_ptrs, row_indices, self._inputs, num_neighbors, sampler, None, batched=True)
+
+    def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> SampledBatches:
+        src = _as_seed_matrix(inputs, self._inputs.device)
+        if src.shape != self._inputs.shape:
+            raise ValueError(f"inputs must have shape {tuple(self._inputs.shape)}")
+        self._inputs.copy_(src, non_blocking=True)
+        self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base)
+        return SampledBatches(self._call)
+
+
+def neighbor_sampling_homogenous_batched(col_ptrs, row_indices, inputs, num_neighbors, sampler=None,
+                                         seed: Optional[int] = None, batch_base: int = 0) -> SampledBatches:
+    """Extension: inputs [B, S] -> B independent neighbor_sampling_homogenous results in one call."""
+    call = _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, None, batched=True)
+    call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base)
+    return SampledBatches(call)
+
+
+def rel_key(edge_type) -> str:
+    """neighbor_sampling.rs:255-258"""
+    return "{}__{}__{}".format(*edge_type)
+
+
+def neighbor_sampling_heterogenous(
+        node_types: List[str],
+        edge_types: List[Tuple[str, str, str]],
+        col_ptrs: Dict[str, Tensor],
+        row_indices: Dict[str, Tensor],
+        inputs: Dict[str, Tensor],
+        num_neighbors: Dict[str, List[int]],
+        num_hops: int,
+        sampler=None,
+        filter=None,
+):
+    """python.rs:273-395.  Returns (samples{node_type}, rows{rel}, cols{rel}, edge_index{rel},
+    layer_offsets{rel}).  Relations are visited in `edge_types` order (the reference iterates a
+    HashMap, quirk Q6)."""
+    _reject_filter(filter)
+    node_types = list(node_types)
+    edge_types = [tuple(e) for e in edge_types]
+    tix = {t: i for i, t in enumerate(node_types)}
+    rels = [rel_key(e) for e in edge_types]
+    # graphs are built from col_ptrs.keys() (python.rs:293-300): every key needs row_indices and an edge type
+    for r in col_ptrs:
+        if r not in row_indices:
+            raise KeyError(r)
+    for r in num_neighbors:
+        if r not in rels:
+            raise KeyError(r)  # to_edge_types[rel_type] panics, neighbor_sampling.rs:296
+        if r not in col_ptrs:
+            raise KeyError(r)  # graphs[rel_type] panics, :310
+    dev = None
+    for t in list(col_ptrs.values()):
+        dev = t.device
+        break
+    if dev is None:
+        raise ValueError("col_ptrs is empty")
+    kind, wdict = _extract_sampler(sampler, hetero=True)
+    cp, ri, ws = [], [], []
+    for r in rels:
+        if r in col_ptrs:
+            cp.append(_check(col_ptrs[r], torch.int64, f"col_ptrs[{r}]", dev))
+            ri.append(_check(row_indices[r], torch.int64, f"row_indices[{r}]", dev))
+        else:
+            cp.append(None)
+            ri.append(None)
+        if kind == N.SAMPLER_WEIGHTED:
+            ws.append(_check(wdict[r], torch.float64, f"weights[{r}]", dev) if r in wdict else None)
+    active = [1 if r in num_neighbors else 0 for r in rels]
+    fan = np.zeros((len(rels), max(num_hops, 1)), dtype=np.int64)
+    for i, r in enumerate(rels):
+        if r in num_neighbors:
+            ks = [int(k) for k in num_neighbors[r]]
+            if len(ks) < num_hops:
+                raise IndexError("num_neighbors[%s] has fewer than num_hops entries" % r)  # :295 index panic
+            fan[i, :num_hops] = ks[:num_hops]
+    inp, seeds = [], []
+    for t in node_types:
+        if t in inputs:
+            x = _as_seed_matrix(inputs[t], dev, f"inputs[{t}]").reshape(1, -1)
+            inp.append(x)
+            seeds.append(x.shape[1])
+        else:
+            inp.append(None)
+            seeds.append(0)
+    call = _Call(dev, [tix[e[0]] for e in edge_types], [tix[e[2]] for e in edge_types], cp, ri,
+                 ws if kind == N.SAMPLER_WEIGHTED else None, fan[:, :num_hops].reshape(-1) if num_hops > 0 else [],
+                 active, inp, seeds, 1, num_hops, kind, 0)
+    call.run(seed=_rng_get())
+    out_s = {t: call.samples[i][0, :int(call.samples_len[0, i])] for i, t in enumerate(node_types)}
+    out_r, out_c, out_e, out_lo = {}, {}, {}, {}
+    for i, r in enumerate(rels):
+        if r not in col_ptrs:
+            continue  # outputs are keyed by graphs.keys(), neighbor_sampling.rs:280-285
+        ne = int(call.edges_len[0, i])
+        out_r[r], out_c[r], out_e[r] = call.rows[i][0, :ne], call.cols[i][0, :ne], call.eidx[i][0, :ne]
+        out_lo[r] = ([tuple(int(x) for x in call.layer_offsets[0, i, h]) for h in range(num_hops)]
+                     if active[i] else [])
+    return out_s, out_r, out_c, out_e, out_lo
+
+
+# ---------------------------------------------------------------------------------------------
+# random_walk (python.rs:583-608 -> random_walk.rs:10-75)
+# ---------------------------------------------------------------------------------------------
+def random_walk(row_ptrs: Tensor, col_indices: Tensor, start: Tensor, walk_length: int, p: float, q: float,
+                *, seed: Optional[int] = None, walker_base: int = 0, return_attempts: bool = False):
+    _check(row_ptrs, torch.int64, "row_ptrs")
+    dev = row_ptrs.device
+    _check(col_indices, torch.int64, "col_indices", dev)
+    start = _as_seed_matrix(start, dev, "start").reshape(-1)
+    S = start.numel()
+    walks = torch.empty((S, walk_length + 1), dtype=torch.int64, device=dev)
+    stats = torch.empty(2, dtype=torch.int64, device=dev)
+    attempts = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        st = N.lib.tchgeo_random_walk(_ptr(row_ptrs), row_ptrs.numel() - 1, _ptr(col_indices), _ptr(start), S,
+                                      int(walk_length), float(p), float(q), _rng_get() if seed is None else seed,
+                                      int(walker_base), _ptr(walks), _ptr(stats), ctypes.addressof(attempts),
+                                      _stream(dev))
+    N.check(st)
+    return (walks, attempts.value) if return_attempts else walks
+
+
+# ---------------------------------------------------------------------------------------------
+# dedup + relabel stage (additive; semantic of negative_sampling.rs:20-47)
+# ---------------------------------------------------------------------------------------------
+def unique_relabel(samples: Tensor, num_seeds: int) -> Tuple[Tensor, Tensor]:
+    """-> (nodes, local): nodes = seeds ++ other ids in first-appearance order; local[i] indexes nodes."""
+    _check(samples, torch.int64, "samples")
+    dev = samples.device
+    n = samples.numel()
+    nodes = torch.empty(n, dtype=torch.int64, device=dev)
+    local = torch.empty(n, dtype=torch.int64, device=dev)
+    ws_bytes = N.lib.tchgeo_unique_relabel_workspace_bytes(n)
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
+    num = ctypes.c_int64(0)
+    with torch.cuda.device(dev):
+        st = N.lib.tchgeo_unique_relabel(_ptr(samples), n, int(num_seeds), _ptr(nodes), _ptr(local),
+                                         ctypes.addressof(num), _ptr(ws), ws_bytes, _stream(dev))
+    N.check(st)
+    return nodes[:num.value], local

@@ -1,0 +1,123 @@
+"""CPU-only: host-side logic of the Python mirror (argument extraction, error behaviour, RNG forking,
+capacity planning, sharding).  Mirrors src/python.rs:107-168 and src/utils/tensor.rs:10-70."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import tch_geometric as thg
+from tch_geometric import _native as N
+from tch_geometric import ops
+from tch_geometric.sharding import shard_range
+from oracle import oracle as O
+
+
+def test_reference_surface_is_present():
+    for name in ("to_csc", "to_csr", "neighbor_sampling_homogenous", "neighbor_sampling_heterogenous", "random_walk",
+                 "UniformEdgeSampler", "WeightedEdgeSampler", "TemporalEdgeFilter", "TEMPORAL_SAMPLE_STATIC"):
+        assert hasattr(thg, name)
+    assert thg.UniformEdgeSampler().with_replacement is False
+    assert (thg.TEMPORAL_SAMPLE_STATIC, thg.TEMPORAL_SAMPLE_RELATIVE, thg.TEMPORAL_SAMPLE_DYNAMIC) == (0, 1, 2)
+
+
+def test_cpu_tensors_are_rejected_not_silently_computed():
+    """No CPU fallback: the reference's InvalidDevice error becomes 'must be on Cuda device'."""
+    p = torch.zeros(3, dtype=torch.int64)
+    with pytest.raises(ValueError, match="Cuda"):
+        thg.neighbor_sampling_homogenous(p, p, p, [2])
+    with pytest.raises(ValueError, match="Cuda"):
+        thg.to_csc(torch.zeros((2, 3), dtype=torch.int64), 3)
+    with pytest.raises(ValueError, match="Cuda"):
+        thg.random_walk(p, p, p, 3, 1.0, 1.0)
+    with pytest.raises(ValueError, match="Cuda"):
+        thg.unique_relabel(p, 1)
+
+
+def test_sampler_extraction_order():
+    """derive(FromPyObject) tries Uniform{with_replacement: bool} first, then Weighted{weights}."""
+    assert ops._extract_sampler(None, False) == (N.SAMPLER_UNIFORM, None)
+    assert ops._extract_sampler(thg.UniformEdgeSampler(True), False)[0] == N.SAMPLER_UNIFORM_REPLACE
+    assert ops._extract_sampler(thg.UniformEdgeSampler(False), True)[0] == N.SAMPLER_UNIFORM
+    w = torch.ones(3, dtype=torch.float64)
+    assert ops._extract_sampler(thg.WeightedEdgeSampler(w), False) == (N.SAMPLER_WEIGHTED, w)
+    with pytest.raises(ValueError, match="homogenous"):
+        ops._extract_sampler(thg.WeightedEdgeSampler({"a": w}), False)
+    with pytest.raises(ValueError, match="heterogenous"):
+        ops._extract_sampler(thg.WeightedEdgeSampler(w), True)
+    with pytest.raises(TypeError):
+        ops._extract_sampler(object(), False)
+
+    class Both:  # an object with both attributes is a uniform sampler, as in the reference
+        with_replacement = True
+        weights = w
+    assert ops._extract_sampler(Both(), False)[0] == N.SAMPLER_UNIFORM_REPLACE
+
+
+def test_graph_size_extraction():
+    assert ops._size_tuple(5) == (5, 5) and ops._size_tuple((3, 4)) == (3, 4)
+    with pytest.raises(ValueError):
+        ops._size_tuple((1, 2, 3))
+
+
+def test_rng_forks_a_child_per_call_and_reseeds():
+    thg.rng_reseed(42)
+    a = [ops._rng_get() for _ in range(3)]
+    thg.rng_reseed(42)
+    b = [ops._rng_get() for _ in range(3)]
+    assert a == b and len(set(a)) == 3
+    assert a[0] == ops.splitmix64(42)[1]
+    # splitmix64 known answer (seed 0 -> first output), the same expansion rand uses for seed_from_u64
+    assert ops.splitmix64(0)[1] == 0xE220A8397B1DCDAF
+
+
+def _capacity(T, R, H, rel_src, rel_dst, fan, seeds, active=None, kind=0, B=1):
+    a = N.SamplingArgs()
+    keep = [np.asarray(rel_src, dtype=np.int32), np.asarray(rel_dst, dtype=np.int32), np.asarray(fan, dtype=np.int64),
+            np.asarray(seeds, dtype=np.int64), np.asarray(active if active is not None else [1] * R, dtype=np.uint8)]
+    a.num_node_types, a.num_rels, a.num_hops, a.sampler_kind, a.num_batches = T, R, H, kind, B
+    a.rel_src, a.rel_dst, a.fanouts, a.seeds_per_batch, a.rel_active = (k.ctypes.data for k in keep)
+    cn, ce = np.zeros(T, dtype=np.int64), np.zeros(R, dtype=np.int64)
+    N.check(N.lib.tchgeo_neighbor_sampling_capacity(ctypes.byref(a), cn.ctypes.data, ce.ctypes.data))
+    return cn.tolist(), ce.tolist()
+
+
+def test_capacity_planner_matches_reference_recurrence():
+    assert _capacity(1, 1, 2, [0], [0], [5, 5], [34]) == ([34 + 170 + 850], [170 + 850])
+    assert _capacity(1, 1, 0, [0], [0], [], [7]) == ([7], [0])
+    # hetero: types a,b ; rels r0: a->b (src a, dst b), r1: b->b ; seeds only on b
+    cn, ce = _capacity(2, 2, 2, [0, 1], [1, 1], [2, 3, 4, 5], [0, 10])
+    # hop0: r0 adds 20 to a, r1 adds 40 to b ; hop1: frontier a=20 (no relation has dst a), b=40: r0 adds 120 to a, r1 adds 200 to b
+    assert (cn, ce) == ([140, 250], [140, 240])
+    # inactive relation contributes nothing
+    cn, ce = _capacity(2, 2, 2, [0, 1], [1, 1], [2, 3, 4, 5], [0, 10], active=[1, 0])
+    assert (cn, ce) == ([20, 10], [20, 0])
+
+
+def test_capacity_bounds_the_oracle(karate):
+    ei, n = karate
+    ptrs, idx, _ = O.to_csc(ei, n)
+    for fan in ([5, 5], [17, 17], [3, 2, 4]):
+        for sampler in (None, ("uniform", True)):
+            s, r, c, e, lo = O.neighbor_sampling_homogenous(ptrs, idx, np.arange(34), fan, sampler=sampler)
+            cn, ce = _capacity(1, 1, len(fan), [0], [0], fan, [34], kind=1 if sampler else 0)
+            assert len(s) <= cn[0] and len(r) <= ce[0]
+
+
+def test_filter_argument_is_refused_loudly():
+    p = torch.zeros(3, dtype=torch.int64)
+    f = (thg.TemporalEdgeFilter((0, 2), p), p)
+    with pytest.raises(NotImplementedError):
+        thg.neighbor_sampling_homogenous(p, p, p, [2], None, f)
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 256, 1000):
+        for world in (1, 2, 3, 8):
+            parts = [shard_range(n, r, world) for r in range(world)]
+            assert parts[0][0] == 0 and parts[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+            sizes = [b - a for a, b in parts]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(5, 2, 2)
