@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the sampling hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): synthetic ogbn-products-shaped graph (2 449 029 nodes,
+61 859 140 CSC entries), homogeneous neighbor sampling, fanouts [15,10,5], 1024 seeds per batch,
+default sampler (uniform without replacement).  One *step* = one pass of the hot path over
+`--batches` (default 256) seed batches, i.e. the "many batches in flight" regime of SURVEY §8(d).
+
+Prints ONE JSON line:
+  value      sampled edges/s, whole job, seeds already resident in HBM when the timed region starts
+             (CUDA events on the launching stream, max over ranks).
+  e2e        the same metric through the public plan API with HOST buffers: seeds start in pinned host
+             memory, every step's four output tensors + layer offsets are copied back to pinned host
+             memory inside the timed region.
+  roofline   hop-3 kernel (the dominant launch): algorithmic bytes 24*F + 40*E over its CUDA-event
+             duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the CPU oracle (C restatement of the reference algorithm) on this box's host cores,
+             on a bounded sample of the same workload.
+
+--impl reference times the reference's CPU algorithm (the oracle port: the reference is Rust and
+cannot be built in this image) with all host threads on bounded samples of the same workload.
+Multi-GPU (torchrun, one rank per GPU): CSC replicated, seed batches sharded, no data-path
+collective; weak scaling (each rank samples `--batches` batches per step).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tch-geometric_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from tools import synth  # noqa: E402
+
+FANOUTS = [15, 10, 5]
+SEEDS_PER_BATCH = 1024
+METRIC = "sampled_edges_per_sec_3hop_15_10_5"
+UNIT = "edges/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, STREAM-style copy)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+def build_graph(device, scale):
+    t0 = time.time()
+    ei, n = synth.products_like(device, scale=scale)
+    if device.type == "cuda":
+        torch.cuda.synchronize(device)
+    log(f"[bench] graph generated: N={n} E={ei.shape[1]} in {time.time() - t0:.1f}s")
+    return ei, n
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference algorithm
+# ---------------------------------------------------------------------------------------------
+def cpu_sampling_rate(ptrs, idx, n, num_batches, threads, first_batch):
+    from oracle import oracle as O
+    seeds = synth.seed_batches(n, num_batches, SEEDS_PER_BATCH, first_batch=first_batch)
+    t0 = time.perf_counter()
+    ts, te = O.neighbor_sampling_homogenous_batches(ptrs, idx, seeds, FANOUTS, rng_mode=O.RNG_XOSHIRO, seed=first_batch,
+                                                    num_threads=threads)
+    dt = time.perf_counter() - t0
+    return te / dt, te, dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation (oracle port) on the host cores."""
+    rank, world, local = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    cores = os.cpu_count() or 1
+    use_cuda = torch.cuda.is_available()
+    device = torch.device("cuda", local) if use_cuda else torch.device("cpu")
+    ei, n = build_graph(device, args.scale)
+    ei = ei.cpu().numpy()
+    t0 = time.time()
+    ptrs, idx, _ = O.to_csc(ei, n)  # the reference's own path restated (storage.rs:103-127)
+    log(f"[bench] reference arm: CSC built on the CPU in {time.time() - t0:.1f}s; {cores} host threads")
+    del ei
+    per_step = max(cores * 8, 32) if args.ref_batches <= 0 else args.ref_batches
+    for w in range(args.warmup):
+        cpu_sampling_rate(ptrs, idx, n, per_step, cores, first_batch=w * per_step)
+    tot_e, tot_t = 0, 0.0
+    for k in range(args.steps):
+        _, te, dt = cpu_sampling_rate(ptrs, idx, n, per_step, cores, first_batch=(args.warmup + k) * per_step)
+        tot_e += te
+        tot_t += dt
+    value = tot_e / tot_t
+    sample = f"{per_step} batches x {SEEDS_PER_BATCH} seeds per step, {args.steps} steps, {cores} threads"
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": workload_config(n, int(idx.size), per_step, args.scale),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out), flush=True)
+
+
+def workload_config(n, e, batches, scale):
+    return {
+        "workload": f"products-shaped synthetic graph (N={n}, E={e}{'' if scale == 1.0 else f', scale={scale}'}), "
+                    f"neighbor_sampling_homogenous fanouts {FANOUTS}, {SEEDS_PER_BATCH} seeds/batch, "
+                    f"{batches} batches/step, uniform without replacement",
+        "fanouts": FANOUTS, "seeds_per_batch": SEEDS_PER_BATCH, "batches_per_step": batches,
+        "l2_policy": "inputs larger than L2: row_indices is 495 MB and each step streams GBs of outputs through the "
+                     "126 MB L2; seeds differ every step",
+        "parallelism": "seed batches sharded over ranks, CSC replicated, no data-path collective",
+    }
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_ours(args):
+    import tch_geometric as thg
+    import torch.distributed as dist
+
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
+    l2_fetch = None
+    if args.l2_fetch:
+        l2_fetch = thg.set_l2_fetch_granularity(args.l2_fetch, device)
+        log(f"[bench] L2 fetch granularity set to {args.l2_fetch}, driver reports {l2_fetch}")
+
+    # ---- setup (untimed): graph, CSC through the new to_csc -----------------------------------
+    ei, n = build_graph(device, args.scale)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    to_csc_ms = []
+    for _ in range(3):  # first call pays module load + workspace cudaMalloc; report the steady state too
+        ptrs = idx = perm = None
+        ev0.record()
+        ptrs, idx, perm = thg.to_csc(ei, n)
+        ev1.record()
+        torch.cuda.synchronize()
+        to_csc_ms.append(ev0.elapsed_time(ev1))
+    to_csc_first_ms, to_csc_ms = to_csc_ms[0], min(to_csc_ms[1:])
+    E = int(idx.numel())
+    del ei, perm
+    torch.cuda.empty_cache()
+    log(f"[bench] rank {rank}: to_csc {to_csc_ms:.2f} ms (first call {to_csc_first_ms:.2f} ms) for E={E}")
+
+    # every rank samples its own global batch indices: step s, rank r -> batches [(s*world + r)*B, +B)
+    steps_total = W + K
+    host_seeds = torch.empty((steps_total, B, S), dtype=torch.int64).pin_memory()
+    for s in range(steps_total):
+        host_seeds[s] = torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B))
+    dev_seeds = host_seeds.to(device)
+    plan = thg.HomogenousSampler(ptrs, idx, B, S, FANOUTS)
+    cap_n, cap_e = int(plan._call.cap_n[0]), int(plan._call.cap_e[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing (value) + per-launch roofline ---------------------------------
+    for s in range(W):
+        plan.sample(dev_seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edges = 0
+    hop_ms = np.zeros(len(FANOUTS))
+    hop_F = np.zeros(len(FANOUTS))
+    hop_E = np.zeros(len(FANOUTS))
+    start.record()
+    for s in range(W, W + K):
+        res = plan.sample(dev_seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
+        edges += int(res.edges_len.sum())
+        lo = res.layer_offsets  # [B, H, 3]
+        n_end = np.concatenate([lo[:, 1:, 0], res.samples_len[:, None]], axis=1)  # len(samples) after each hop
+        e_end = np.concatenate([lo[:, 1:, 1], res.edges_len[:, None]], axis=1)
+        hop_E += (e_end - lo[:, :, 1]).sum(axis=0)
+        f_begin = np.concatenate([np.zeros((B, 1), dtype=np.int64), lo[:, :-1, 0]], axis=1)
+        hop_F += (lo[:, :, 0] - f_begin).sum(axis=0)
+        hop_ms += res.launch_ms
+    stop.record()
+    barrier()
+    clk = clocks.stop()
+    elapsed_ms = start.elapsed_time(stop)
+    from tch_geometric.sharding import reduce_job
+    elapsed_ms, edges_all = reduce_job(elapsed_ms, float(edges), device)
+    value = edges_all / (elapsed_ms * 1e-3)
+    seeds_per_s = world * B * S * K / (elapsed_ms * 1e-3)
+
+    peak, peak_src = measured_peak_gbs()
+    dom = int(np.argmax(hop_ms))
+    alg_bytes = 24.0 * hop_F + 40.0 * hop_E  # per launch, summed over the K timed launches
+    achieved = alg_bytes[dom] / (hop_ms[dom] * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": f"hop_kernel<UNIFORM> hop {dom + 1} (fanout {FANOUTS[dom]})",
+        "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": alg_bytes[dom] / K, "launch_ms": hop_ms[dom] / K,
+        "per_hop": [{"hop": h + 1, "ms": hop_ms[h] / K, "frontier_nodes": hop_F[h] / K, "edges": hop_E[h] / K,
+                     "GB/s": (alg_bytes[h] / (hop_ms[h] * 1e-3) / 1e9) if hop_ms[h] > 0 else None}
+                    for h in range(len(FANOUTS))],
+        "all_hops_GBps": alg_bytes.sum() / (hop_ms.sum() * 1e-3) / 1e9,
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "hop3_dram_bytes_per_launch.json")
+    if os.path.exists(traffic_file):
+        try:
+            roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+
+    # ---- end-to-end with host buffers (e2e) ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(thg, plan, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier)
+
+    # ---- CPU baseline on rank 0, N = 1 only -----------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_baseline(ptrs, idx, n, args)
+
+    if world > 1:
+        dist.barrier()
+    if rank == 0:
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int64", "data": "synthetic", "config": workload_config(n, E, B, args.scale),
+            "seeds_per_sec": seeds_per_s, "edges_per_step_per_gpu": edges / K,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": K * (len(FANOUTS) + 1),
+            "clocks": clk, "l2_fetch_granularity": l2_fetch, "to_csc_ms": to_csc_ms, "to_csc_first_call_ms": to_csc_first_ms,
+        }
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(thg, plan, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier):
+    """Public plan API with HOST buffers: pinned seeds -> H2D -> sample -> D2H of the four outputs."""
+    from tch_geometric.sharding import reduce_job
+    try:
+        h_samples = torch.empty((B, cap_n), dtype=torch.int64).pin_memory()
+        h_edges = [torch.empty((B, cap_e), dtype=torch.int64).pin_memory() for _ in range(3)]
+    except RuntimeError as e:
+        log(f"[bench] could not pin host output buffers: {e}")
+        return None
+
+    def step(s):
+        res = plan.sample(host_seeds[s], seed=2000 + s, batch_base=(s * world + rank) * B)  # H2D inside
+        ns, ne = res.samples_len, res.edges_len
+        d2h = 0
+        for b in range(B):
+            nb, eb = int(ns[b]), int(ne[b])
+            h_samples[b, :nb].copy_(res.samples[b, :nb], non_blocking=True)
+            h_edges[0][b, :eb].copy_(res.rows[b, :eb], non_blocking=True)
+            h_edges[1][b, :eb].copy_(res.cols[b, :eb], non_blocking=True)
+            h_edges[2][b, :eb].copy_(res.edge_index[b, :eb], non_blocking=True)
+            d2h += 8 * (nb + 3 * eb)
+        d2h += res.layer_offsets.nbytes + ns.nbytes + ne.nbytes  # already on the host (read back by the call)
+        return int(ne.sum()), d2h
+
+    for s in range(min(W, 2)):
+        step(s)
+    barrier()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    start.record()
+    edges, d2h = 0, 0
+    for s in range(W, W + K):
+        e, d = step(s)
+        edges += e
+        d2h += d
+    stop.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    ms = max(start.elapsed_time(stop), wall_ms)
+    ms, edges_all = reduce_job(ms, float(edges), device)
+    return {"value": edges_all / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
+            "d2h_bytes_per_step": d2h // K, "ms_per_step": ms / K,
+            "path": "HomogenousSampler.sample(pinned host seeds) + D2H of samples/rows/cols/edge_index prefixes "
+                    "and layer offsets into pinned host buffers"}
+
+
+def run_cpu_baseline(ptrs, idx, n, args):
+    cores = os.cpu_count() or 1
+    hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
+    r1, e1, t1 = cpu_sampling_rate(hp, hi, n, 8, 1, first_batch=10_000_000)
+    nb = int(min(max(cores * 4, 16), max(16, 20.0 * cores / (t1 / 8))))  # ~20 s of CPU work in total
+    rT, eT, tT = cpu_sampling_rate(hp, hi, n, nb, cores, first_batch=10_000_100)
+    log(f"[bench] cpu baseline: 1 thread {r1 / 1e6:.2f} M edges/s, {cores} threads {rT / 1e6:.2f} M edges/s")
+    return {"value": rT, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{nb} batches x {SEEDS_PER_BATCH} seeds on {cores} threads ({tT:.1f} s); "
+                      f"1 thread: {r1:.0f} edges/s on 8 batches ({t1:.1f} s)",
+            "value_1_thread": r1}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
+    ap.add_argument("--ref-batches", type=int, default=0, help="batches per step of the reference arm (0 = 8 x cores)")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (0 = leave)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,12 @@ TCHGEO_API int32_t tchgeo_abi_version(void);
 /* Human-readable description of the last non-OK status on this thread (never NULL). */
 TCHGEO_API const char* tchgeo_last_error(void);
 
+/* Device tuning hint (optional, process-wide for the current device): L2 -> DRAM fetch granularity in
+ * bytes (32, 64 or 128; cudaLimitMaxL2FetchGranularity).  The sampling path reads one 32-byte sector per
+ * random 8-byte gather, so 32 avoids fetching neighbour sectors that are never used.  `actual` (HOST,
+ * may be NULL) receives the value the driver reports afterwards. */
+TCHGEO_API tchgeo_status tchgeo_device_set_l2_fetch_granularity(int32_t bytes, int32_t* actual);
+
 /* -------------------------------------------------------------------------------------------- */
 /* ind2ptr: out[i] = #{e : ind[e] < i}, i in [0, m]; `ind` sorted ascending.                      */
 /* replaces src/data/storage.rs:67-101                                                           */
@@ -148,6 +154,13 @@ TCHGEO_API size_t tchgeo_neighbor_sampling_workspace_bytes(const tchgeo_sampling
  * If samples_len/edges_len/layer_offsets are all NULL the call is asynchronous: it returns after
  * enqueueing and device-side errors surface through tchgeo_neighbor_sampling_collect. */
 TCHGEO_API tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* args);
+
+/* Same as tchgeo_neighbor_sampling, but brackets every (hop, relation) kernel launch with CUDA events
+ * on args->stream and returns the per-launch device durations (launch order = hop-major, relation
+ * order within a hop; launches that cannot produce output are skipped).  Always synchronises.
+ * launch_ms: HOST [launch_ms_cap]; num_launches: HOST [1]. Used by bench.py for the roofline figure. */
+TCHGEO_API tchgeo_status tchgeo_neighbor_sampling_timed(const tchgeo_sampling_args* args, float* launch_ms,
+                                                        int32_t launch_ms_cap, int32_t* num_launches);
 
 /* Synchronise args->stream, fetch lengths / layer offsets / device error flag of the last
  * tchgeo_neighbor_sampling call that used args->workspace. */

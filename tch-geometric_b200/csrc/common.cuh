@@ -99,6 +99,34 @@ __device__ __forceinline__ void st_relaxed_u64(uint64_t* p, uint64_t v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// L2 cache policies (createpolicy): the colptr array is small and re-read all the time -> evict_last;
+// random single-use gathers must not push it out -> evict_first.
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ int64_t ld_nc_l2hint_i64(const int64_t* p, uint64_t pol) {
+  int64_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int64_t ld_nc_na_l2hint_i64(const int64_t* p, uint64_t pol) {
+  int64_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ int32_t ld_nc_na_l2hint_i32(const int32_t* p, uint64_t pol) {
+  int32_t v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.s32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // streaming (evict-first) 8-byte store for write-once outputs
 __device__ __forceinline__ void st_cs_i64(int64_t* p, int64_t v) {
   asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

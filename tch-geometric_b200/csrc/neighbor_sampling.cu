@@ -28,6 +28,7 @@
 #include <cub/block/block_scan.cuh>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -37,12 +38,13 @@ namespace tchgeo {
 namespace {
 
 constexpr int HOP_THREADS = 256;
+constexpr int HOP_DEFAULT_MIN_BLOCKS = 6;  // resident CTAs per SM the register budget is compiled for
 constexpr int MAX_TILE_EDGES = 8192;   // shared-memory slots per tile when fanout <= 8192
 constexpr int MAX_FANOUT = 32768;      // one node per tile above 8192; bounded by shared memory
 constexpr uint64_t ST_FLAG_AGG = 1ull << 62;
 constexpr uint64_t ST_FLAG_INCL = 2ull << 62;
 constexpr uint64_t ST_VAL_MASK = (1ull << 62) - 1;
-constexpr int CNT_BITS = 20;           // packed scan: low 20 bits = output count, high 44 = draw blocks
+constexpr int LIGHT_BLOCKS_MAX = 32;   // nodes needing more 4-step draw blocks are processed CTA-wide
 
 struct HopParams {
   const int64_t* ptrs;
@@ -66,6 +68,7 @@ struct HopParams {
   uint64_t* status;            // [B * tiles_per_batch] look-back words, zero-initialised
   uint32_t* ticket;            // zero-initialised tile dispenser
   uint32_t* err;
+  int32_t num_batches;
   int32_t tiles_per_batch;
   int32_t tile_nodes;
   int32_t tile_edges;          // tile_nodes * fanout
@@ -80,15 +83,19 @@ __global__ void fill_i64_kernel(int64_t* p, int64_t v, int64_t n) {
   if (i < n) p[i] = v;
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) {
-  using BlockScan = cub::BlockScan<unsigned long long, HOP_THREADS>;
+template <int KIND, int MINB>
+__global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams p) {
+  using BlockScan = cub::BlockScan<uint32_t, HOP_THREADS>;
   __shared__ typename BlockScan::TempStorage scan_tmp;
   __shared__ int64_t s_start[HOP_THREADS];
-  __shared__ int64_t s_choff[HOP_THREADS + 1];
   __shared__ uint32_t s_deg[HOP_THREADS];
-  __shared__ int s_off[HOP_THREADS + 1];
+  __shared__ uint16_t s_off[HOP_THREADS + 1];    // exclusive output offsets inside the tile
+  __shared__ uint16_t s_choff[HOP_THREADS + 1];  // exclusive draw-block offsets of the light nodes
+  __shared__ uint8_t s_chown[LIGHT_BLOCKS_MAX * HOP_THREADS];  // draw block -> owning node
+  __shared__ uint8_t s_heavy[HOP_THREADS];
   __shared__ uint32_t s_ticket;
+  __shared__ uint32_t s_work;     // dynamic work counter of the draw phase
+  __shared__ uint32_t s_nheavy;
   __shared__ int64_t s_excl;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   uint32_t* s_slot = reinterpret_cast<uint32_t*>(dyn_smem);
@@ -96,12 +103,19 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
-  if (tid == 0) s_ticket = atomicAdd(p.ticket, 1u);
+  if (tid == 0) {
+    s_ticket = atomicAdd(p.ticket, 1u);
+    s_work = 0u;
+    s_nheavy = 0u;
+  }
   __syncthreads();
-  // Tiles are handed out in start order, so every tile this one waits on is already running.
+  // Tiles are handed out in start order and TILE-MAJOR (ticket -> tile t of batch b = ticket % B):
+  // the tiles in flight at any moment belong to different batches, so the per-batch look-back chains
+  // advance independently, and every tile this one waits on (same batch, smaller t) holds a smaller
+  // ticket, i.e. is already running or done.
   const uint32_t ticket = s_ticket;
-  const int b = (int)(ticket / (uint32_t)p.tiles_per_batch);
-  const int t = (int)(ticket - (uint32_t)b * (uint32_t)p.tiles_per_batch);
+  const int t = (int)(ticket / (uint32_t)p.num_batches);
+  const int b = (int)(ticket - (uint32_t)t * (uint32_t)p.num_batches);
   const int TN = p.tile_nodes;
   const int k = p.fanout;
 
@@ -117,15 +131,17 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
   // ---- A: frontier ids, degree, count -----------------------------------------------------------
   int cnt = 0;
   uint32_t deg = 0;
-  int64_t nblocks = 0;
+  uint32_t nblocks = 0;  // 4-step Philox blocks this node needs (UNIFORM only)
+  bool heavy = false;
   if (tid < nn) {
     const int64_t w = p.dst_samples[(int64_t)b * p.dst_stride + fb + node0 + tid];
     int64_t s = 0;
     if (w < 0 || w >= p.num_cols) {
       atomicOr(p.err, DEV_ERR_INDEX);  // reference: slice index panic (quirk Q10)
     } else {
-      s = __ldg(p.ptrs + w);
-      const int64_t d = __ldg(p.ptrs + w + 1) - s;
+      const uint64_t keep = l2_policy_evict_last();  // colptr (8 B/node) should live in the 126 MB L2
+      s = ld_nc_l2hint_i64(p.ptrs + w, keep);
+      const int64_t d = ld_nc_l2hint_i64(p.ptrs + w + 1, keep) - s;
       if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
       else deg = (uint32_t)d;
     }
@@ -136,30 +152,45 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
     } else {
       cnt = deg < (uint32_t)k ? (int)deg : k;
       if (k == 0 && deg > 0) atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0..0), sampling.rs:19
-      if (KIND == TCHGEO_SAMPLER_UNIFORM && deg > (uint32_t)k) nblocks = ((int64_t)deg - k + 3) >> 2;
+      if (KIND == TCHGEO_SAMPLER_UNIFORM && deg > (uint32_t)k) {
+        nblocks = (deg - (uint32_t)k + 3u) >> 2;
+        heavy = nblocks > (uint32_t)LIGHT_BLOCKS_MAX;
+      }
     }
   }
-  unsigned long long packed = (unsigned long long)cnt | ((unsigned long long)nblocks << CNT_BITS);
-  unsigned long long pexcl, ptotal;
-  BlockScan(scan_tmp).ExclusiveSum(packed, pexcl, ptotal);
-  const int off = (int)(pexcl & ((1u << CNT_BITS) - 1));
-  const int total = (int)(ptotal & ((1u << CNT_BITS) - 1));
-  const int64_t Q = (int64_t)(ptotal >> CNT_BITS);
-  s_off[tid] = off;
-  s_choff[tid] = (int64_t)(pexcl >> CNT_BITS);
-  if (tid == 0) {
-    s_off[HOP_THREADS] = total;
-    s_choff[HOP_THREADS] = Q;
-  }
+  // one 32-bit scan carries both prefix sums: low 16 bits = outputs (<= 32768 per tile),
+  // high 16 bits = draw blocks of the light nodes (<= 32 * 256)
+  const uint32_t light_blocks = heavy ? 0u : nblocks;
+  uint32_t pexcl, ptotal;
+  BlockScan(scan_tmp).ExclusiveSum((uint32_t)cnt | (light_blocks << 16), pexcl, ptotal);
+  const int off = (int)(pexcl & 0xffffu);
+  const int total = (int)(ptotal & 0xffffu);
+  const int choff = (int)(pexcl >> 16);
+  const int Q = (int)(ptotal >> 16);
+  s_off[tid] = (uint16_t)off;
+  s_choff[tid] = (uint16_t)choff;
 
-  // ---- B: decoupled look-back over this batch's earlier tiles -----------------------------------
+  // publish this tile's aggregate as early as possible
   uint64_t* my_status = p.status + (size_t)b * p.tiles_per_batch;
+  if (tid == 0) st_relaxed_u64(my_status + t, (t == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | (uint64_t)total);
+
+  // ---- C1: per-node set-up of the shared tables (own node only: needs no barrier) ---------------
+  if (tid < nn) {
+    for (int s = 0; s < cnt; ++s) {
+      s_owner[off + s] = (uint8_t)tid;
+      if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE) s_slot[off + s] = 0u;
+    }
+    if (KIND == TCHGEO_SAMPLER_UNIFORM) {
+      for (uint32_t c = 0; c < light_blocks; ++c) s_chown[choff + c] = (uint8_t)tid;
+      if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint8_t)tid;
+    }
+  }
+  __syncthreads();
+
+  // ---- B: decoupled look-back over this batch's earlier tiles (warp 0), overlapped with C2 ------
   if (tid < 32) {
     int64_t excl = 0;
-    if (t == 0) {
-      if (lane == 0) st_relaxed_u64(my_status, ST_FLAG_INCL | (uint64_t)total);
-    } else {
-      if (lane == 0) st_relaxed_u64(my_status + t, ST_FLAG_AGG | (uint64_t)total);
+    if (t > 0) {
       int j = t - 1;
       uint32_t spins = 0;
       while (true) {
@@ -175,7 +206,7 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
             if (lane == 0) atomicOr(p.err, DEV_ERR_WATCHDOG);
             break;
           }
-          __nanosleep(64);
+          __nanosleep(32);
           continue;
         }
         int64_t val = lane <= first_incl ? (int64_t)(v & ST_VAL_MASK) : 0;
@@ -189,57 +220,57 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
     }
     if (lane == 0) s_excl = excl;
   }
-  __syncthreads();
 
-  const int64_t excl = s_excl;
-  const int64_t e_base = p.e_len_in[b] + excl;
-  const int64_t s_base = p.src_len_in[b] + excl;
-  if (is_last && tid == 0) {
-    p.e_len_out[b] = e_base + total;
-    p.src_len_out[b] = s_base + total;
-  }
-  if (e_base + total > p.e_stride || s_base + total > p.src_stride) {
-    if (tid == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
-    return;
-  }
-  if (total == 0) return;
-
-  // ---- C: sampling decisions in shared memory ---------------------------------------------------
-  if (tid < nn) {
-    for (int s = 0; s < cnt; ++s) {
-      s_owner[off + s] = (uint8_t)tid;
-      if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE) s_slot[off + s] = 0u;
-    }
-  }
-  __syncthreads();
-
+  // ---- C2: sampling decisions in shared memory --------------------------------------------------
   const uint32_t pos0 = (uint32_t)(fb + node0);
   const uint32_t batch = p.batch_base + (uint32_t)b;
 
   if (KIND == TCHGEO_SAMPLER_UNIFORM) {
-    // flattened (node, 4-step block) work items; block c of node n covers steps k+4c .. k+4c+3
-    for (int64_t q = tid; q < Q; q += HOP_THREADS) {
-      int lo = 0, hi = nn;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_choff[mid] <= q) lo = mid + 1; else hi = mid;
-      }
-      const int n = lo - 1;
-      const uint32_t c = (uint32_t)(q - s_choff[n]);
-      const uint32_t dn = s_deg[n];
-      const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1);
-      const uint32_t step0 = (uint32_t)k + 4u * c;
-      uint32_t* slots = s_slot + s_off[n];
+    // Light nodes: (node, 4-step block) work items, grabbed 32 at a time so that warp 0 joins in
+    // after its look-back.  Block c of node n covers steps k+4c .. k+4c+3 of the serial reservoir.
+    while (true) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(&s_work, 32u);
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (base >= (uint32_t)Q) break;
+      const uint32_t q = base + lane;
+      if (q < (uint32_t)Q) {
+        const int n = s_chown[q];
+        const uint32_t c = q - s_choff[n];
+        const uint32_t dn = s_deg[n];
+        const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1);
+        const uint32_t step0 = (uint32_t)k + 4u * c;
+        uint32_t* slots = s_slot + s_off[n];
 #pragma unroll
-      for (uint32_t u = 0; u < 4; ++u) {
-        const uint32_t step = step0 + u;
-        if (step < dn) {
-          const uint32_t j = __umulhi(pick4(r, u), step);  // uniform in [0, step), sampling.rs:19
-          if (j < (uint32_t)k) atomicMax(slots + j, step);  // last writer of slot j wins, :20-22
+        for (uint32_t u = 0; u < 4; ++u) {
+          const uint32_t step = step0 + u;
+          if (step < dn) {
+            const uint32_t j = __umulhi(pick4(r, u), step);  // uniform in [0, step), sampling.rs:19
+            if (j < (uint32_t)k) atomicMax(slots + j, step);  // last writer of slot j wins, :20-22
+          }
         }
       }
     }
-    __syncthreads();
+    // Heavy nodes (deg > k + 4*LIGHT_BLOCKS_MAX): the whole CTA strides over one node's blocks.
+    const int nheavy = (int)s_nheavy;
+    for (int h = 0; h < nheavy; ++h) {
+      const int n = s_heavy[h];
+      const uint32_t dn = s_deg[n];
+      const uint32_t nb = (dn - (uint32_t)k + 3u) >> 2;
+      uint32_t* slots = s_slot + s_off[n];
+      for (uint32_t c = tid; c < nb; c += HOP_THREADS) {
+        const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1);
+        const uint32_t step0 = (uint32_t)k + 4u * c;
+#pragma unroll
+        for (uint32_t u = 0; u < 4; ++u) {
+          const uint32_t step = step0 + u;
+          if (step < dn) {
+            const uint32_t j = __umulhi(pick4(r, u), step);
+            if (j < (uint32_t)k) atomicMax(slots + j, step);
+          }
+        }
+      }
+    }
   } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
     const int warp = tid >> 5;
     for (int n = warp; n < nn; n += HOP_THREADS / 32) {
@@ -271,8 +302,21 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
         carry = __shfl_sync(0xffffffffu, w_sum, 31);
       }
     }
-    __syncthreads();
   }
+  __syncthreads();
+
+  const int64_t excl = s_excl;
+  const int64_t e_base = p.e_len_in[b] + excl;
+  const int64_t s_base = p.src_len_in[b] + excl;
+  if (is_last && tid == 0) {
+    p.e_len_out[b] = e_base + total;
+    p.src_len_out[b] = s_base + total;
+  }
+  if (e_base + total > p.e_stride || s_base + total > p.src_stride) {
+    if (tid == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
+    return;
+  }
+  if (total == 0) return;
 
   // ---- D: one thread per output edge ------------------------------------------------------------
   int64_t* o_s = p.src_samples + (int64_t)b * p.src_stride + s_base;
@@ -281,6 +325,7 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
   int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
   const int64_t col0 = fb + node0;
   constexpr int U = 4;
+  const uint64_t stream_pol = l2_policy_evict_first();  // single-use random sectors
   for (int e0 = tid; e0 < total; e0 += HOP_THREADS * U) {
     int64_t ptr[U];
     int64_t val[U];
@@ -308,7 +353,7 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int e = e0 + u * HOP_THREADS;
-      val[u] = e < total ? ld_nc_na_i64(p.indices + ptr[u]) : 0;
+      val[u] = e < total ? ld_nc_na_l2hint_i64(p.indices + ptr[u], stream_pol) : 0;
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -317,7 +362,7 @@ __global__ void __launch_bounds__(HOP_THREADS, 4) hop_kernel(const HopParams p) 
         st_cs_i64(o_e + e, ptr[u]);
         st_cs_i64(o_c + e, col0 + own[u]);
         st_cs_i64(o_r + e, s_base + e);
-        o_s[e] = val[u];  // re-read as the next hop's frontier: keep in L2
+        st_cs_i64(o_s + e, val[u]);  // the next hop reads it only after GBs of other traffic
       }
     }
   }
@@ -450,19 +495,39 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   return TCHGEO_OK;
 }
 
-template <int KIND>
-cudaError_t launch_hop(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+template <int KIND, int MINB>
+cudaError_t launch_hop_v(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
   static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(hop_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(hop_kernel<KIND, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  hop_kernel<KIND><<<(unsigned)grid, HOP_THREADS, smem, stream>>>(hp);
+  hop_kernel<KIND, MINB><<<(unsigned)grid, HOP_THREADS, smem, stream>>>(hp);
   return cudaGetLastError();
+}
+
+// TCHGEO_HOP_MIN_BLOCKS (4, 6 or 8) selects the register budget variant; tuning knob, default 6.
+inline int hop_min_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("TCHGEO_HOP_MIN_BLOCKS");
+    int x = e ? atoi(e) : HOP_DEFAULT_MIN_BLOCKS;
+    v = (x == 4 || x == 6 || x == 8) ? x : HOP_DEFAULT_MIN_BLOCKS;
+  }
+  return v;
+}
+
+template <int KIND>
+cudaError_t launch_hop(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+  switch (hop_min_blocks()) {
+    case 4: return launch_hop_v<KIND, 4>(hp, grid, smem, stream);
+    case 8: return launch_hop_v<KIND, 8>(hp, grid, smem, stream);
+    default: return launch_hop_v<KIND, 6>(hp, grid, smem, stream);
+  }
 }
 
 }  // namespace
@@ -517,7 +582,8 @@ extern "C" tchgeo_status tchgeo_neighbor_sampling_collect(const tchgeo_sampling_
   return status_from_dev_err(err);
 }
 
-extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a) {
+static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_ms, int32_t launch_ms_cap,
+                                  int32_t* num_launches) {
   Plan pl;
   tchgeo_status st = build_plan(a, pl);
   if (st != TCHGEO_OK) return st;
@@ -543,7 +609,7 @@ extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a)
   for (const Launch& L : pl.launches) {
     const int r = L.rel;
     TCHGEO_REQUIRE(a->col_ptrs[r] && a->num_cols[r] >= 0, "relation %d: col_ptrs is NULL", r);
-    TCHGEO_REQUIRE(a->row_indices[r] != nullptr, "relation %d: row_indices is NULL", r);
+    // row_indices[r] may be NULL for a relation without edges: it is only dereferenced when deg > 0
     if (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED)
       TCHGEO_REQUIRE(a->weights && a->weights[r], "relation %d: weighted sampler without weights", r);
     if (a->edges_stride[r] > 0)
@@ -567,6 +633,15 @@ extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a)
     TCHGEO_CUDA_CHECK(cudaGetLastError());
   }
   int li = 0;
+  const int n_launch = (int)pl.launches.size();
+  if (num_launches) *num_launches = n_launch;
+  std::vector<cudaEvent_t> ev;
+  if (launch_ms) {
+    TCHGEO_REQUIRE(launch_ms_cap >= n_launch, "launch_ms too small: %d launches", n_launch);
+    ev.resize((size_t)n_launch + 1);
+    for (auto& e : ev) TCHGEO_CUDA_CHECK(cudaEventCreate(&e));
+    TCHGEO_CUDA_CHECK(cudaEventRecord(ev[0], stream));
+  }
   for (const Launch& L : pl.launches) {
     const int r = L.rel, stt = a->rel_src[r], dtt = a->rel_dst[r];
     HopParams hp;
@@ -591,6 +666,7 @@ extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a)
     hp.status = status + L.status_off;
     hp.ticket = ctrl + 1 + li;
     hp.err = ctrl;
+    hp.num_batches = (int32_t)B;
     hp.tiles_per_batch = L.tiles_per_batch;
     hp.tile_nodes = L.tile_nodes;
     hp.tile_edges = L.tile_edges;
@@ -609,9 +685,29 @@ extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a)
     }
     TCHGEO_CUDA_CHECK(e);
     ++li;
+    if (launch_ms) TCHGEO_CUDA_CHECK(cudaEventRecord(ev[(size_t)li], stream));
   }
-  if (a->samples_len || a->edges_len || a->layer_offsets) return tchgeo_neighbor_sampling_collect(a);
-  return TCHGEO_OK;
+  tchgeo_status rc = TCHGEO_OK;
+  if (launch_ms || a->samples_len || a->edges_len || a->layer_offsets) rc = tchgeo_neighbor_sampling_collect(a);
+  if (launch_ms) {
+    for (int i = 0; i < n_launch; ++i) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, ev[(size_t)i], ev[(size_t)i + 1]) != cudaSuccess) ms = -1.f;
+      launch_ms[i] = ms;
+    }
+    for (auto& e : ev) cudaEventDestroy(e);
+  }
+  return rc;
+}
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a) {
+  return run_sampling(a, nullptr, 0, nullptr);
+}
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling_timed(const tchgeo_sampling_args* a, float* launch_ms,
+                                                        int32_t launch_ms_cap, int32_t* num_launches) {
+  TCHGEO_REQUIRE(launch_ms != nullptr, "launch_ms is NULL");
+  return run_sampling(a, launch_ms, launch_ms_cap, num_launches);
 }
 
 extern "C" tchgeo_status tchgeo_neighbor_sampling_homogenous(

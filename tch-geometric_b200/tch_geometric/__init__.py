@@ -17,6 +17,7 @@ from .ops import (  # noqa: F401
     random_walk,
     rel_key,
     rng_reseed,
+    set_l2_fetch_granularity,
     to_csc,
     to_csr,
     unique_relabel,

@@ -42,6 +42,8 @@ def _load():
     lib = ctypes.CDLL(LIB_PATH)
     lib.tchgeo_abi_version.restype = c_i32
     lib.tchgeo_last_error.restype = ctypes.c_char_p
+    lib.tchgeo_device_set_l2_fetch_granularity.restype = c_i32
+    lib.tchgeo_device_set_l2_fetch_granularity.argtypes = [c_i32, c_vp]
     lib.tchgeo_ind2ptr.restype = c_i32
     lib.tchgeo_ind2ptr.argtypes = [c_vp, c_i64, c_i64, c_vp, c_vp]
     lib.tchgeo_coo_to_csx_workspace_bytes.restype = c_sz
@@ -55,6 +57,8 @@ def _load():
     lib.tchgeo_neighbor_sampling_workspace_bytes.argtypes = [P]
     lib.tchgeo_neighbor_sampling.restype = c_i32
     lib.tchgeo_neighbor_sampling.argtypes = [P]
+    lib.tchgeo_neighbor_sampling_timed.restype = c_i32
+    lib.tchgeo_neighbor_sampling_timed.argtypes = [P, c_vp, c_i32, c_vp]
     lib.tchgeo_neighbor_sampling_collect.restype = c_i32
     lib.tchgeo_neighbor_sampling_collect.argtypes = [P]
     lib.tchgeo_neighbor_sampling_homogenous.restype = c_i32
@@ -76,9 +80,9 @@ def _load():
 lib = _load()
 
 EXPORTS = [
-    "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
+    "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_device_set_l2_fetch_granularity", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
     "tchgeo_coo_to_csx", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
-    "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
+    "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_timed", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
     "tchgeo_random_walk", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
 ]
 

@@ -88,6 +88,15 @@ def _size_tuple(size) -> Tuple[int, int]:
     return int(size), int(size)
 
 
+def set_l2_fetch_granularity(nbytes: int = 32, device=None) -> int:
+    """Optional device hint (extension): L2->DRAM fetch granularity for the gather-bound sampling path.
+    Returns the value the driver reports afterwards."""
+    actual = ctypes.c_int32(0)
+    with torch.cuda.device(device if device is not None else torch.cuda.current_device()):
+        N.check(N.lib.tchgeo_device_set_l2_fetch_granularity(int(nbytes), ctypes.addressof(actual)))
+    return actual.value
+
+
 # ---------------------------------------------------------------------------------------------
 # to_csc / to_csr (python.rs:27-53 -> storage.rs:103-127)
 # ---------------------------------------------------------------------------------------------
@@ -219,7 +228,7 @@ class _Call:
         a.workspace = self.workspace.data_ptr()
         a.workspace_bytes = ws_bytes
 
-    def run(self, seed=None, batch_base=None):
+    def run(self, seed=None, batch_base=None, timed=False):
         a = self.args
         if seed is not None:
             a.seed = seed
@@ -227,7 +236,13 @@ class _Call:
             a.batch_base = batch_base
         with torch.cuda.device(self.device):
             a.stream = torch.cuda.current_stream(self.device).cuda_stream
-            N.check(N.lib.tchgeo_neighbor_sampling(ctypes.byref(a)))
+            if timed:
+                ms = np.zeros(max(self.R * max(self.H, 1), 1), dtype=np.float32)
+                n = ctypes.c_int32(0)
+                N.check(N.lib.tchgeo_neighbor_sampling_timed(ctypes.byref(a), ms.ctypes.data, ms.size, ctypes.addressof(n)))
+                self.launch_ms = ms[:n.value].copy()
+            else:
+                N.check(N.lib.tchgeo_neighbor_sampling(ctypes.byref(a)))
         return self
 
 
@@ -309,13 +324,19 @@ class HomogenousSampler:
         self._inputs = torch.zeros((num_batches, seeds_per_batch), dtype=torch.int64, device=dev)
         self._call = _homogenous_call(col_ptrs, row_indices, self._inputs, num_neighbors, sampler, None, batched=True)
 
-    def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> SampledBatches:
-        src = _as_seed_matrix(inputs, self._inputs.device)
-        if src.shape != self._inputs.shape:
+    def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0,
+               timed: bool = False) -> SampledBatches:
+        """inputs: [B, S] i64 on the device or in (pinned) host memory.  With timed=True the result
+        carries `launch_ms`, the device duration of each hop kernel (CUDA events on the current stream)."""
+        if not isinstance(inputs, Tensor) or inputs.dtype != torch.int64:
+            raise ValueError("inputs must be an int64 tensor")
+        if tuple(inputs.shape) != tuple(self._inputs.shape):
             raise ValueError(f"inputs must have shape {tuple(self._inputs.shape)}")
-        self._inputs.copy_(src, non_blocking=True)
-        self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base)
-        return SampledBatches(self._call)
+        self._inputs.copy_(inputs, non_blocking=True)
+        self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base, timed=timed)
+        res = SampledBatches(self._call)
+        res.launch_ms = getattr(self._call, "launch_ms", None) if timed else None
+        return res
 
 
 def neighbor_sampling_homogenous_batched(col_ptrs, row_indices, inputs, num_neighbors, sampler=None,
