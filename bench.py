@@ -250,8 +250,8 @@ def run_ours(args):
     for s in range(W):
         plan.sample(dev_seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
     clocks = ClockSampler(local)
+    clocks.start()  # sampled over both timed regions (device-resident loop and e2e loop)
     barrier()
-    clocks.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     edges = 0
     hop_ms = np.zeros(len(FANOUTS))
@@ -270,7 +270,6 @@ def run_ours(args):
         hop_ms += res.launch_ms
     stop.record()
     barrier()
-    clk = clocks.stop()
     elapsed_ms = start.elapsed_time(stop)
     from tch_geometric.sharding import reduce_job
     elapsed_ms, edges_all = reduce_job(elapsed_ms, float(edges), device)
@@ -302,6 +301,8 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(thg, plan, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier)
+
+    clk = clocks.stop()
 
     # ---- CPU baseline on rank 0, N = 1 only -----------------------------------------------------
     cpu = None
@@ -375,7 +376,7 @@ def run_cpu_baseline(ptrs, idx, n, args):
     cores = os.cpu_count() or 1
     hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
     r1, e1, t1 = cpu_sampling_rate(hp, hi, n, 8, 1, first_batch=10_000_000)
-    nb = int(min(max(cores * 4, 16), max(16, 20.0 * cores / (t1 / 8))))  # ~20 s of CPU work in total
+    nb = int(max(cores * 4, min(4096, 5.0 * cores / (t1 / 8))))  # ~5 s of wall time on all cores
     rT, eT, tT = cpu_sampling_rate(hp, hi, n, nb, cores, first_batch=10_000_100)
     log(f"[bench] cpu baseline: 1 thread {r1 / 1e6:.2f} M edges/s, {cores} threads {rT / 1e6:.2f} M edges/s")
     return {"value": rT, "unit": UNIT, "cores": cores, "kind": "port",
@@ -387,7 +388,7 @@ def run_cpu_baseline(ptrs, idx, n, args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")

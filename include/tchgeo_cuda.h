@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TCHGEO_ABI_VERSION 1
+#define TCHGEO_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define TCHGEO_API __attribute__((visibility("default")))
@@ -115,6 +115,11 @@ typedef struct tchgeo_sampling_args {
   const int64_t* num_cols;          /* HOST [R] number of dst nodes of the relation                */
   const int64_t* const* row_indices;/* HOST [R] of DEVICE [nnz_r]                                  */
   const double* const* weights;     /* HOST [R] of DEVICE [nnz_r] (f64) or NULL unless WEIGHTED    */
+  const int32_t* const* row_indices32; /* optional (table or entries may be NULL): HOST [R] of DEVICE
+                                       [nnz_r] int32 copies of row_indices made by
+                                       tchgeo_compress_indices.  HBM layout optimisation only: the
+                                       random gathers then touch half as many DRAM lines; outputs are
+                                       unchanged (i64).                                            */
   const int64_t* fanouts;           /* HOST [R*H] num_neighbors[r][hop]                            */
   const uint8_t* rel_active;        /* HOST [R] 0 = relation absent from num_neighbors, or NULL    */
   /* ---- seeds ---- */
@@ -143,6 +148,12 @@ typedef struct tchgeo_sampling_args {
   size_t workspace_bytes;
   tchgeo_stream stream;
 } tchgeo_sampling_args;
+
+/* dst[i] = (int32) src[i]; TCHGEO_ERR_INDEX if a value is outside [0, 2^31).  Builds the optional
+ * row_indices32 replica. */
+TCHGEO_API tchgeo_status tchgeo_compress_indices(const int64_t* src /*DEVICE [n]*/, int64_t n,
+                                                 int32_t* dst /*DEVICE [n]*/, int32_t* scratch /*DEVICE [1]*/,
+                                                 tchgeo_stream stream);
 
 /* Worst-case per-batch capacities (elements) for samples[t] and edges[r]:
  * the reference recurrence with every neighbourhood at full fanout. HOST outputs [T], [R]. */

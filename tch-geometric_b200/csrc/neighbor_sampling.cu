@@ -49,6 +49,7 @@ constexpr int LIGHT_BLOCKS_MAX = 32;   // nodes needing more 4-step draw blocks 
 struct HopParams {
   const int64_t* ptrs;
   const int64_t* indices;
+  const int32_t* indices32;  // optional compressed replica of `indices`
   const double* weights;
   int64_t num_cols;
   const int64_t* dst_samples;  // frontier ids live here (may alias src_samples)
@@ -78,9 +79,53 @@ struct HopParams {
   uint32_t batch_base;
 };
 
+__global__ void __launch_bounds__(256) compress_kernel(const int64_t* __restrict__ src, int64_t n,
+                                                       int32_t* __restrict__ dst, uint32_t* err) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  bool bad = false;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t v = src[i];
+    bad |= (v < 0 || v > 0x7fffffffll);
+    dst[i] = (int32_t)v;
+  }
+  if (bad) atomicOr(err, DEV_ERR_INDEX);
+}
+
 __global__ void fill_i64_kernel(int64_t* p, int64_t v, int64_t n) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+
+// per-node record kept in shared memory (one 8-byte load in the hot loops)
+struct __align__(8) NodeRec {
+  uint32_t deg;    // neighbourhood size
+  uint16_t off;    // exclusive output offset inside the tile
+  uint16_t choff;  // exclusive draw-block offset (light nodes)
+};
+
+struct TileHdr {  // written by thread 0, read by everyone after the first barrier
+  int64_t fb, F, e_in, s_in;
+  int b, t;
+};
+
+__device__ __forceinline__ uint32_t smem_atom_add(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.shared.add.u32 %0, [%1], %2;"
+               : "=r"(old) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+  return old;
+}
+
+// steps step0 .. step0+3 of the serial reservoir (sampling.rs:17-23) for one node: draw j uniform in
+// [0, step); a hit (j < k) overwrites slot j; the LAST hit of a slot wins -> atomicMax on the step index.
+__device__ __forceinline__ void reservoir_block(const Philox4& r, uint32_t step0, uint32_t deg, uint32_t k,
+                                                uint32_t* slots) {
+#pragma unroll
+  for (uint32_t u = 0; u < 4; ++u) {
+    const uint32_t step = step0 + u;
+    const uint32_t j = __umulhi(pick4(r, u), step);
+    const bool hit = (step < deg) & (j < k);
+    if (hit) atomicMax(slots + j, step);
+  }
 }
 
 template <int KIND, int MINB>
@@ -88,12 +133,10 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
   using BlockScan = cub::BlockScan<uint32_t, HOP_THREADS>;
   __shared__ typename BlockScan::TempStorage scan_tmp;
   __shared__ int64_t s_start[HOP_THREADS];
-  __shared__ uint32_t s_deg[HOP_THREADS];
-  __shared__ uint16_t s_off[HOP_THREADS + 1];    // exclusive output offsets inside the tile
-  __shared__ uint16_t s_choff[HOP_THREADS + 1];  // exclusive draw-block offsets of the light nodes
+  __shared__ NodeRec s_rec[HOP_THREADS];
   __shared__ uint8_t s_chown[LIGHT_BLOCKS_MAX * HOP_THREADS];  // draw block -> owning node
   __shared__ uint8_t s_heavy[HOP_THREADS];
-  __shared__ uint32_t s_ticket;
+  __shared__ TileHdr s_hdr;
   __shared__ uint32_t s_work;     // dynamic work counter of the draw phase
   __shared__ uint32_t s_nheavy;
   __shared__ int64_t s_excl;
@@ -103,80 +146,83 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int TN = p.tile_nodes;
   if (tid == 0) {
-    s_ticket = atomicAdd(p.ticket, 1u);
+    // Tiles are handed out in start order and TILE-MAJOR (ticket -> tile t of batch b = ticket % B):
+    // the tiles in flight at any moment belong to different batches, so the per-batch look-back
+    // chains advance independently, and every tile this one waits on (same batch, smaller t) holds a
+    // smaller ticket, i.e. is already running or done.
+    const uint32_t ticket = atomicAdd(p.ticket, 1u);
+    const int t = (int)(ticket / (uint32_t)p.num_batches);
+    const int b = (int)(ticket - (uint32_t)t * (uint32_t)p.num_batches);
+    const int64_t fb = p.fr_begin[b];
+    int64_t fe = p.fr_end[b];
+    if (fe > p.dst_stride) fe = p.dst_stride;  // only after a capacity error upstream
+    s_hdr.fb = fb;
+    s_hdr.F = fe > fb ? fe - fb : 0;
+    s_hdr.e_in = p.e_len_in[b];
+    s_hdr.s_in = p.src_len_in[b];
+    s_hdr.b = b;
+    s_hdr.t = t;
     s_work = 0u;
     s_nheavy = 0u;
   }
   __syncthreads();
-  // Tiles are handed out in start order and TILE-MAJOR (ticket -> tile t of batch b = ticket % B):
-  // the tiles in flight at any moment belong to different batches, so the per-batch look-back chains
-  // advance independently, and every tile this one waits on (same batch, smaller t) holds a smaller
-  // ticket, i.e. is already running or done.
-  const uint32_t ticket = s_ticket;
-  const int t = (int)(ticket / (uint32_t)p.num_batches);
-  const int b = (int)(ticket - (uint32_t)t * (uint32_t)p.num_batches);
-  const int TN = p.tile_nodes;
-  const int k = p.fanout;
-
-  const int64_t fb = p.fr_begin[b];
-  int64_t fe = p.fr_end[b];
-  if (fe > p.dst_stride) fe = p.dst_stride;  // only after a capacity error upstream
-  const int64_t F = fe > fb ? fe - fb : 0;
+  const int b = s_hdr.b, t = s_hdr.t;
+  const int64_t fb = s_hdr.fb, F = s_hdr.F;
+  const uint32_t k = (uint32_t)p.fanout;
   const int64_t node0 = (int64_t)t * TN;
   const int nn = (int)max((int64_t)0, min((int64_t)TN, F - node0));
   const bool is_last = (nn > 0 && node0 + nn == F) || (F == 0 && t == 0);
   if (nn == 0 && !is_last) return;
 
   // ---- A: frontier ids, degree, count -----------------------------------------------------------
-  int cnt = 0;
+  uint32_t cnt = 0;
   uint32_t deg = 0;
   uint32_t nblocks = 0;  // 4-step Philox blocks this node needs (UNIFORM only)
   bool heavy = false;
+  int64_t start = 0;
   if (tid < nn) {
     const int64_t w = p.dst_samples[(int64_t)b * p.dst_stride + fb + node0 + tid];
-    int64_t s = 0;
     if (w < 0 || w >= p.num_cols) {
       atomicOr(p.err, DEV_ERR_INDEX);  // reference: slice index panic (quirk Q10)
     } else {
       const uint64_t keep = l2_policy_evict_last();  // colptr (8 B/node) should live in the 126 MB L2
-      s = ld_nc_l2hint_i64(p.ptrs + w, keep);
-      const int64_t d = ld_nc_l2hint_i64(p.ptrs + w + 1, keep) - s;
+      start = ld_nc_l2hint_i64(p.ptrs + w, keep);
+      const int64_t d = ld_nc_l2hint_i64(p.ptrs + w + 1, keep) - start;
       if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
       else deg = (uint32_t)d;
     }
-    s_start[tid] = s;
-    s_deg[tid] = deg;
     if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
       cnt = deg > 0 ? k : 0;  // exactly k picks, even when deg < k (quirk Q3)
     } else {
-      cnt = deg < (uint32_t)k ? (int)deg : k;
+      cnt = deg < k ? deg : k;
       if (k == 0 && deg > 0) atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0..0), sampling.rs:19
-      if (KIND == TCHGEO_SAMPLER_UNIFORM && deg > (uint32_t)k) {
-        nblocks = (deg - (uint32_t)k + 3u) >> 2;
+      if (KIND == TCHGEO_SAMPLER_UNIFORM && deg > k) {
+        nblocks = (deg - k + 3u) >> 2;
         heavy = nblocks > (uint32_t)LIGHT_BLOCKS_MAX;
       }
     }
   }
   // one 32-bit scan carries both prefix sums: low 16 bits = outputs (<= 32768 per tile),
-  // high 16 bits = draw blocks of the light nodes (<= 32 * 256)
+  // high 16 bits = draw blocks of the light nodes (<= LIGHT_BLOCKS_MAX * 256)
   const uint32_t light_blocks = heavy ? 0u : nblocks;
   uint32_t pexcl, ptotal;
-  BlockScan(scan_tmp).ExclusiveSum((uint32_t)cnt | (light_blocks << 16), pexcl, ptotal);
-  const int off = (int)(pexcl & 0xffffu);
-  const int total = (int)(ptotal & 0xffffu);
-  const int choff = (int)(pexcl >> 16);
-  const int Q = (int)(ptotal >> 16);
-  s_off[tid] = (uint16_t)off;
-  s_choff[tid] = (uint16_t)choff;
+  BlockScan(scan_tmp).ExclusiveSum(cnt | (light_blocks << 16), pexcl, ptotal);
+  const uint32_t off = pexcl & 0xffffu;
+  const uint32_t total = ptotal & 0xffffu;
+  const uint32_t choff = pexcl >> 16;
+  const uint32_t Q = ptotal >> 16;
 
   // publish this tile's aggregate as early as possible
   uint64_t* my_status = p.status + (size_t)b * p.tiles_per_batch;
   if (tid == 0) st_relaxed_u64(my_status + t, (t == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | (uint64_t)total);
 
   // ---- C1: per-node set-up of the shared tables (own node only: needs no barrier) ---------------
+  s_start[tid] = start;
+  s_rec[tid] = NodeRec{deg, (uint16_t)off, (uint16_t)choff};
   if (tid < nn) {
-    for (int s = 0; s < cnt; ++s) {
+    for (uint32_t s = 0; s < cnt; ++s) {
       s_owner[off + s] = (uint8_t)tid;
       if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE) s_slot[off + s] = 0u;
     }
@@ -226,58 +272,43 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
   const uint32_t batch = p.batch_base + (uint32_t)b;
 
   if (KIND == TCHGEO_SAMPLER_UNIFORM) {
-    // Light nodes: (node, 4-step block) work items, grabbed 32 at a time so that warp 0 joins in
+    const uint32_t tag = TAG_RESERVOIR | (p.rel << 8);
+    const uint32_t key0 = p.key0, key1 = p.key1;
+    // Light nodes: (node, 4-step block) work items, grabbed 128 at a time so that warp 0 joins in
     // after its look-back.  Block c of node n covers steps k+4c .. k+4c+3 of the serial reservoir.
     while (true) {
       uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(&s_work, 32u);
+      if (lane == 0) base = smem_atom_add(&s_work, 128u);
       base = __shfl_sync(0xffffffffu, base, 0);
-      if (base >= (uint32_t)Q) break;
-      const uint32_t q = base + lane;
-      if (q < (uint32_t)Q) {
-        const int n = s_chown[q];
-        const uint32_t c = q - s_choff[n];
-        const uint32_t dn = s_deg[n];
-        const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1);
-        const uint32_t step0 = (uint32_t)k + 4u * c;
-        uint32_t* slots = s_slot + s_off[n];
-#pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
-          const uint32_t step = step0 + u;
-          if (step < dn) {
-            const uint32_t j = __umulhi(pick4(r, u), step);  // uniform in [0, step), sampling.rs:19
-            if (j < (uint32_t)k) atomicMax(slots + j, step);  // last writer of slot j wins, :20-22
-          }
-        }
+      if (base >= Q) break;
+#pragma unroll 1
+      for (uint32_t q = base + lane; q < min(base + 128u, Q); q += 32) {
+        const uint32_t n = s_chown[q];
+        const NodeRec rec = s_rec[n];
+        const uint32_t c = q - rec.choff;
+        const Philox4 r = philox4x32_10(pos0 + n, c, batch, tag, key0, key1);
+        reservoir_block(r, k + 4u * c, rec.deg, k, s_slot + rec.off);
       }
     }
-    // Heavy nodes (deg > k + 4*LIGHT_BLOCKS_MAX): the whole CTA strides over one node's blocks.
-    const int nheavy = (int)s_nheavy;
-    for (int h = 0; h < nheavy; ++h) {
-      const int n = s_heavy[h];
-      const uint32_t dn = s_deg[n];
-      const uint32_t nb = (dn - (uint32_t)k + 3u) >> 2;
-      uint32_t* slots = s_slot + s_off[n];
-      for (uint32_t c = tid; c < nb; c += HOP_THREADS) {
-        const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1);
-        const uint32_t step0 = (uint32_t)k + 4u * c;
-#pragma unroll
-        for (uint32_t u = 0; u < 4; ++u) {
-          const uint32_t step = step0 + u;
-          if (step < dn) {
-            const uint32_t j = __umulhi(pick4(r, u), step);
-            if (j < (uint32_t)k) atomicMax(slots + j, step);
-          }
-        }
+    // Heavy nodes (deg > k + 4*LIGHT_BLOCKS_MAX): one warp strides over one node's blocks.
+    const uint32_t nheavy = s_nheavy;
+    for (uint32_t h = (uint32_t)(tid >> 5); h < nheavy; h += HOP_THREADS / 32) {
+      const uint32_t n = s_heavy[h];
+      const NodeRec rec = s_rec[n];
+      const uint32_t nb = (rec.deg - k + 3u) >> 2;
+      for (uint32_t c = lane; c < nb; c += 32) {
+        const Philox4 r = philox4x32_10(pos0 + n, c, batch, tag, key0, key1);
+        reservoir_block(r, k + 4u * c, rec.deg, k, s_slot + rec.off);
       }
     }
   } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
     const int warp = tid >> 5;
     for (int n = warp; n < nn; n += HOP_THREADS / 32) {
-      const uint32_t dn = s_deg[n];
-      if (dn <= (uint32_t)k) continue;
+      const NodeRec rec = s_rec[n];
+      const uint32_t dn = rec.deg;
+      if (dn <= k) continue;
       const double* wp = p.weights + s_start[n];
-      uint32_t* slots = s_slot + s_off[n];
+      uint32_t* slots = s_slot + rec.off;
       double carry = 0.0;
       for (uint32_t base = 0; base < dn; base += 32) {
         const uint32_t item = base + lane;
@@ -289,14 +320,14 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
           if (lane >= o) incl += up;
         }
         const double w_sum = carry + incl;  // sampling.rs:48
-        if (item >= (uint32_t)k && item < dn) {
+        if (item >= k && item < dn) {
           if (!(w_sum > 0.0)) {
             atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
           } else {
             const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, item, batch, TAG_WEIGHTED | (p.rel << 8), p.key0, p.key1);
             const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
             const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
-            if (__dmul_rn(u, w_sum) < w) atomicMax(slots + __umulhi(r.z, (uint32_t)k), item);  // :49-52
+            if (__dmul_rn(u, w_sum) < w) atomicMax(slots + __umulhi(r.z, k), item);  // :49-52
           }
         }
         carry = __shfl_sync(0xffffffffu, w_sum, 31);
@@ -306,8 +337,8 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
   __syncthreads();
 
   const int64_t excl = s_excl;
-  const int64_t e_base = p.e_len_in[b] + excl;
-  const int64_t s_base = p.src_len_in[b] + excl;
+  const int64_t e_base = s_hdr.e_in + excl;
+  const int64_t s_base = s_hdr.s_in + excl;
   if (is_last && tid == 0) {
     p.e_len_out[b] = e_base + total;
     p.src_len_out[b] = s_base + total;
@@ -324,40 +355,42 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
   int64_t* o_c = p.cols + (int64_t)b * p.e_stride + e_base;
   int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
   const int64_t col0 = fb + node0;
-  constexpr int U = 4;
   const uint64_t stream_pol = l2_policy_evict_first();  // single-use random sectors
-  for (int e0 = tid; e0 < total; e0 += HOP_THREADS * U) {
+  const uint32_t rtag = TAG_REPLACE | (p.rel << 8);
+  constexpr uint32_t U = 4;
+  for (uint32_t e0 = tid; e0 < total; e0 += HOP_THREADS * U) {
     int64_t ptr[U];
     int64_t val[U];
-    int own[U];
+    uint32_t own[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * HOP_THREADS;
-      ptr[u] = 0;
-      own[u] = 0;
-      if (e < total) {
-        const int n = s_owner[e];
-        const int s = e - s_off[n];
-        own[u] = n;
-        int64_t rel_ptr;
-        if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
-          const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, (uint32_t)s >> 2, batch, TAG_REPLACE | (p.rel << 8), p.key0, p.key1);
-          rel_ptr = __umulhi(pick4(r, (uint32_t)s & 3u), s_deg[n]);  // sampling.rs:64
-        } else {
-          const uint32_t st = s_slot[e];
-          rel_ptr = st ? st : (uint32_t)s;
-        }
-        ptr[u] = s_start[n] + rel_ptr;
+    for (uint32_t u = 0; u < U; ++u) {
+      const uint32_t e = min(e0 + u * HOP_THREADS, total - 1);  // clamped: tail lanes redo the last edge
+      const uint32_t n = s_owner[e];
+      const NodeRec rec = s_rec[n];
+      const uint32_t s = e - rec.off;
+      own[u] = n;
+      uint32_t rel_ptr;
+      if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
+        const Philox4 r = philox4x32_10(pos0 + n, s >> 2, batch, rtag, p.key0, p.key1);
+        rel_ptr = __umulhi(pick4(r, s & 3u), rec.deg);  // sampling.rs:64
+      } else {
+        const uint32_t st = s_slot[e];
+        rel_ptr = st ? st : s;
       }
+      ptr[u] = s_start[n] + rel_ptr;
+    }
+    if (p.indices32) {
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u)
+        val[u] = (e0 + u * HOP_THREADS < total) ? (int64_t)ld_nc_na_l2hint_i32(p.indices32 + ptr[u], stream_pol) : 0;
+    } else {
+#pragma unroll
+      for (uint32_t u = 0; u < U; ++u)
+        val[u] = (e0 + u * HOP_THREADS < total) ? ld_nc_na_l2hint_i64(p.indices + ptr[u], stream_pol) : 0;
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * HOP_THREADS;
-      val[u] = e < total ? ld_nc_na_l2hint_i64(p.indices + ptr[u], stream_pol) : 0;
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int e = e0 + u * HOP_THREADS;
+    for (uint32_t u = 0; u < U; ++u) {
+      const uint32_t e = e0 + u * HOP_THREADS;
       if (e < total) {
         st_cs_i64(o_e + e, ptr[u]);
         st_cs_i64(o_c + e, col0 + own[u]);
@@ -647,6 +680,7 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     HopParams hp;
     hp.ptrs = a->col_ptrs[r];
     hp.indices = a->row_indices[r];
+    hp.indices32 = a->row_indices32 ? a->row_indices32[r] : nullptr;
     hp.weights = (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED) ? a->weights[r] : nullptr;
     hp.num_cols = a->num_cols[r];
     hp.dst_samples = a->samples[dtt];
@@ -743,4 +777,20 @@ extern "C" tchgeo_status tchgeo_neighbor_sampling_homogenous(
       out_lens[2 * b + 1] = elen[(size_t)b];
     }
   return st;
+}
+
+extern "C" tchgeo_status tchgeo_compress_indices(const int64_t* src, int64_t n, int32_t* dst, int32_t* scratch,
+                                                 tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(n >= 0 && scratch != nullptr && (n == 0 || (src && dst)), "bad compress argument");
+  if (n == 0) return TCHGEO_OK;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4, stream));
+  int64_t grid = (n + 255) / 256;
+  if (grid > 148 * 16) grid = 148 * 16;
+  compress_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, n, dst, (uint32_t*)scratch);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  uint32_t herr = 0;
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&herr, scratch, 4, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return status_from_dev_err(herr);
 }

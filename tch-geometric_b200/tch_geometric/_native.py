@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libtchgeo_cuda.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_INDEX, ERR_REFERENCE_PANIC, ERR_INTERNAL = range(7)
 SAMPLER_UNIFORM, SAMPLER_UNIFORM_REPLACE, SAMPLER_WEIGHTED = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 c_i64, c_i32, c_u64, c_u32, c_vp, c_sz = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32,
                                           ctypes.c_void_p, ctypes.c_size_t)
@@ -23,7 +23,7 @@ class SamplingArgs(ctypes.Structure):
     _fields_ = [
         ("num_node_types", c_i32), ("num_rels", c_i32), ("num_hops", c_i32), ("sampler_kind", c_i32),
         ("rel_src", c_vp), ("rel_dst", c_vp),
-        ("col_ptrs", c_vp), ("num_cols", c_vp), ("row_indices", c_vp), ("weights", c_vp),
+        ("col_ptrs", c_vp), ("num_cols", c_vp), ("row_indices", c_vp), ("weights", c_vp), ("row_indices32", c_vp),
         ("fanouts", c_vp), ("rel_active", c_vp),
         ("num_batches", c_i64), ("inputs", c_vp), ("seeds_per_batch", c_vp),
         ("seed", c_u64), ("batch_base", c_u32), ("reserved0", c_u32),
@@ -57,6 +57,8 @@ def _load():
     lib.tchgeo_neighbor_sampling_workspace_bytes.argtypes = [P]
     lib.tchgeo_neighbor_sampling.restype = c_i32
     lib.tchgeo_neighbor_sampling.argtypes = [P]
+    lib.tchgeo_compress_indices.restype = c_i32
+    lib.tchgeo_compress_indices.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp]
     lib.tchgeo_neighbor_sampling_timed.restype = c_i32
     lib.tchgeo_neighbor_sampling_timed.argtypes = [P, c_vp, c_i32, c_vp]
     lib.tchgeo_neighbor_sampling_collect.restype = c_i32
@@ -81,7 +83,7 @@ lib = _load()
 
 EXPORTS = [
     "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_device_set_l2_fetch_granularity", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
-    "tchgeo_coo_to_csx", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
+    "tchgeo_coo_to_csx", "tchgeo_compress_indices", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
     "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_timed", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
     "tchgeo_random_walk", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
 ]

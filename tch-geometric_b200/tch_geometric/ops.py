@@ -163,6 +163,37 @@ def _reject_filter(filter):
 
 
 # ---------------------------------------------------------------------------------------------
+# compressed row_indices replica (HBM layout optimisation, outputs unchanged): the sampling kernel's
+# random gathers read int32 entries, so a neighbourhood spans half as many DRAM lines.  The reference
+# API is stateless (tensors are passed on every call), so replicas are cached per tensor and
+# invalidated by the tensor's version counter.  Measured on B200 (products-shaped graph, hop 3):
+# DRAM reads 6.28 GB -> 4.86 GB per launch, 2.24 ms -> 1.88 ms.  TCHGEO_INDEX_REPLICA=0 disables it.
+# ---------------------------------------------------------------------------------------------
+_replica_cache = {}
+_REPLICA_CACHE_MAX = 16
+
+
+def _compressed_indices(t: Optional[Tensor]) -> Optional[Tensor]:
+    if t is None or t.numel() == 0 or os.environ.get("TCHGEO_INDEX_REPLICA", "1") == "0":
+        return None
+    key = (t.data_ptr(), t.numel(), t.device.index)
+    hit = _replica_cache.get(key)
+    if hit is not None and hit[0] == t._version:
+        return hit[1]
+    out = torch.empty(t.numel(), dtype=torch.int32, device=t.device)
+    scratch = torch.empty(1, dtype=torch.int32, device=t.device)
+    with torch.cuda.device(t.device):
+        st = N.lib.tchgeo_compress_indices(_ptr(t), t.numel(), _ptr(out), _ptr(scratch), _stream(t.device))
+    if st == N.ERR_INDEX:
+        return None  # ids beyond int32 (or negative): sample from the i64 array; the kernel reports bad ids
+    N.check(st)
+    if len(_replica_cache) >= _REPLICA_CACHE_MAX:
+        _replica_cache.pop(next(iter(_replica_cache)))
+    _replica_cache[key] = (t._version, out)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # generic driver over tchgeo_neighbor_sampling
 # ---------------------------------------------------------------------------------------------
 class _Call:
@@ -194,6 +225,7 @@ class _Call:
         a.num_cols = host([(t.numel() - 1 if t is not None else 0) for t in col_ptrs], np.int64).ctypes.data
         a.row_indices = ptr_table(row_indices).ctypes.data
         a.weights = ptr_table(weights).ctypes.data if weights is not None else None
+        a.row_indices32 = ptr_table([_compressed_indices(t) for t in row_indices]).ctypes.data
         a.fanouts = host(fanouts, np.int64).ctypes.data
         a.rel_active = host(rel_active, np.uint8).ctypes.data
         a.num_batches = B

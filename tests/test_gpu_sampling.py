@@ -309,3 +309,26 @@ def test_heterogenous_weighted_and_partial(thg, fakehetero):
     _cmp_hetero(got, want)
     for k in got[4]:
         assert (len(got[4][k]) == 2) == (k in nn)
+
+
+def test_index_replica_does_not_change_results(thg, fakedataset, monkeypatch):
+    """the int32 row_indices replica is a memory-layout optimisation only; in-place edits invalidate it."""
+    ei, n = fakedataset
+    ptrs, idx, _ = graph(thg, ei, n)
+    inputs = dev(np.random.default_rng(3).integers(0, n, 300))
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("TCHGEO_INDEX_REPLICA", flag)
+        thg.rng_reseed(8)
+        outs.append(thg.neighbor_sampling_homogenous(ptrs, idx, inputs, [15, 10, 5]))
+    for a, b in zip(outs[0][:4], outs[1][:4]):
+        assert torch.equal(a, b)
+    # mutate the graph in place: the cached replica must not be used any more
+    monkeypatch.setenv("TCHGEO_INDEX_REPLICA", "1")
+    idx2 = idx.clone()
+    thg.rng_reseed(8)
+    a = thg.neighbor_sampling_homogenous(ptrs, idx2, inputs, [4])
+    idx2.add_(0).copy_(torch.flip(idx, [0]))
+    thg.rng_reseed(8)
+    b = thg.neighbor_sampling_homogenous(ptrs, idx2, inputs, [4])
+    assert torch.equal(a[3], b[3]) and torch.equal(b[0][300:], idx2[b[3]])
