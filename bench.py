@@ -49,6 +49,17 @@ METRIC = "sampled_edges_per_sec_3hop_15_10_5"
 UNIT = "edges/s"
 
 
+# Only the final JSON line may reach stdout: libraries (e.g. NCCL's version banner) print there too, so
+# fd 1 is pointed at stderr for the whole run and the JSON goes to the saved descriptor.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(obj):
+    _JSON_OUT.write(json.dumps(obj) + "\n")
+    _JSON_OUT.flush()
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
@@ -178,7 +189,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(n, e, batches, scale):
@@ -321,7 +332,7 @@ def run_ours(args):
             "gpu_launches": K * (len(FANOUTS) + 1),
             "clocks": clk, "l2_fetch_granularity": l2_fetch, "to_csc_ms": to_csc_ms, "to_csc_first_call_ms": to_csc_first_ms,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -385,12 +396,175 @@ def run_cpu_baseline(ptrs, idx, n, args):
             "value_1_thread": r1}
 
 
+# ---------------------------------------------------------------------------------------------
+# secondary workloads (BASELINE.json configs[2] and configs[3]); same JSON shape, own metric names
+# ---------------------------------------------------------------------------------------------
+def run_walk(args):
+    """configs[2]: node2vec random_walk, walk_length 80, p=1, q=0.5, 10 walks per node, walkers sharded."""
+    import tch_geometric as thg
+    import torch.distributed as dist
+    from tch_geometric.sharding import reduce_job, shard_range
+    rank, world, local = dist_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    ei, n = build_graph(device, args.scale)
+    rp, ci, _ = thg.to_csr(ei, n)
+    del ei
+    torch.cuda.empty_cache()
+    L, P, Q = 80, 1.0, 0.5
+    total_walkers = n * 10
+    w0, w1 = shard_range(total_walkers, rank, world)          # strong scaling: the job is fixed
+    start = (torch.arange(w0, w1, device=device, dtype=torch.int64) // 10)  # arange(N).repeat_interleave(10)
+    K, W = args.steps, args.warmup
+    for s in range(W):
+        thg.random_walk(rp, ci, start, L, P, Q, seed=s, walker_base=w0)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps_taken, attempts = 0, 0
+    e0.record()
+    for s in range(K):
+        walks, att = thg.random_walk(rp, ci, start, L, P, Q, seed=100 + s, walker_base=w0, return_attempts=True)
+        attempts += att
+        if s == K - 1:
+            e1.record()
+            steps_taken = int((walks[:, 1:] >= 0).sum().item())
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    ms, steps_all = reduce_job(ms, float(steps_taken) * K, device)
+    _, att_all = reduce_job(0.0, float(attempts), device)
+    value = steps_all / (ms * 1e-3)
+    peak, peak_src = measured_peak_gbs()
+    deg_mean = ci.numel() / n
+    bytes_per_attempt = 24 + 8 * int(np.ceil(np.log2(max(deg_mean, 2))))
+    alg = (att_all * bytes_per_attempt + steps_all * 8) / world  # per-GPU bytes over the timed region
+    achieved = alg / (ms * 1e-3) / 1e9
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        sub = 1_000_000 if args.scale == 1.0 else min(100_000, total_walkers)
+        hrp, hci = rp.cpu().numpy(), ci.cpu().numpy()
+        st = start[:sub].cpu().numpy()
+        t0 = time.perf_counter()
+        wk, _ = O.random_walk_mt(hrp, hci, st, L, P, Q, rng_mode=O.RNG_XOSHIRO, seed=1, num_threads=cores)
+        dt = time.perf_counter() - t0
+        cpu = {"value": float((wk[:, 1:] >= 0).sum()) / dt, "unit": "steps/s", "cores": cores, "kind": "port",
+               "sample": f"{sub} walkers x {L} steps on {cores} threads ({dt:.1f} s)"}
+    if rank == 0:
+        emit({"metric": "node2vec_walk_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K,
+              "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "int64", "data": "synthetic",
+              "config": {"workload": f"products-shaped synthetic graph (N={n}, E={ci.numel()}), random_walk "
+                                     f"walk_length={L}, p={P}, q={Q}, {total_walkers} walkers (10 per node)",
+                         "l2_policy": "inputs larger than L2 (col_indices 495 MB, walks 15.9 GB)",
+                         "parallelism": "walkers sharded over ranks, CSR replicated, no collective"},
+              "attempts_per_step": att_all / max(steps_all, 1.0),
+              "roofline": {"bound": "hbm", "kernel": "walk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                           "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_attempt": bytes_per_attempt},
+              "cpu_baseline": cpu, "e2e": None, "gpu_launches": K, "clocks": clk})
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_hetero(args):
+    """configs[3]: ogbn-mag-shaped heterogeneous sampling, fanouts [10,10] per relation, 1024 paper seeds."""
+    import tch_geometric as thg
+    import torch.distributed as dist
+    from tch_geometric.sharding import reduce_job
+    rank, world, local = dist_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    counts, edges = synth.mag_like(device, scale=args.scale)
+    node_types = list(counts)
+    edge_types = list(edges)
+    cp, ri = {}, {}
+    for et, ei in edges.items():
+        p_, i_, _ = thg.to_csc(ei, (counts[et[0]], counts[et[2]]))
+        cp[thg.rel_key(et)], ri[thg.rel_key(et)] = p_, i_
+    B, S, K, W, H = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup, 2
+    nn = {thg.rel_key(et): [10, 10] for et in edge_types}
+    plan = thg.HeterogenousSampler(node_types, edge_types, cp, ri, B, {"paper": S}, nn, H)
+
+    def seeds(step):
+        out = np.empty((B, S), dtype=np.int64)
+        for b in range(B):
+            out[b] = np.random.default_rng(1234 + (step * world + rank) * B + b).choice(counts["paper"], S, replace=False)
+        return torch.from_numpy(out).to(device)
+
+    all_seeds = [seeds(s) for s in range(W + K)]
+    for s in range(W):
+        plan.sample({"paper": all_seeds[s]}, seed=1000 + s, batch_base=(s * world + rank) * B)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edges_n = 0
+    launch_ms = None
+    e0.record()
+    for s in range(W, W + K):
+        plan.sample({"paper": all_seeds[s]}, seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
+        edges_n += int(plan.edges_len.sum())
+        launch_ms = plan.launch_ms if launch_ms is None else launch_ms + plan.launch_ms
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    ms, edges_all = reduce_job(ms, float(edges_n), device)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        from concurrent.futures import ThreadPoolExecutor
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        hcp = {k: v.cpu().numpy() for k, v in cp.items()}
+        hri = {k: v.cpu().numpy() for k, v in ri.items()}
+        hs = all_seeds[0].cpu().numpy()
+        nb = min(B, cores * 16)
+
+        def one(b):
+            out = O.neighbor_sampling_heterogenous(node_types, edge_types, hcp, hri, {"paper": hs[b]}, nn, H,
+                                                   rng_mode=O.RNG_XOSHIRO, seed=b)
+            return sum(len(v) for v in out[1].values())
+        t0 = time.perf_counter()
+        with ThreadPoolExecutor(cores) as ex:
+            tot = sum(ex.map(one, range(nb)))
+        dt = time.perf_counter() - t0
+        cpu = {"value": tot / dt, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{nb} batches x {S} paper seeds on {cores} threads ({dt:.1f} s)"}
+    if rank == 0:
+        emit({"metric": "sampled_edges_per_sec_hetero_mag_10_10", "value": edges_all / (ms * 1e-3), "unit": UNIT,
+              "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+              "config": {"workload": f"ogbn-mag-shaped synthetic hetero graph {counts}, 4 relations, "
+                                     f"neighbor_sampling_heterogenous fanouts [10,10] per relation, {S} paper seeds/batch, "
+                                     f"{B} batches/step", "parallelism": "seed batches sharded, CSCs replicated"},
+              "launch_ms": [float(x) / K for x in launch_ms], "edges_per_step_per_gpu": edges_n / K,
+              "cpu_baseline": cpu, "e2e": None, "gpu_launches": K * (len(launch_ms) + 1), "clocks": clk})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero"],
+                    help="sampling = headline (configs[1]); walk = configs[2]; hetero = configs[3]")
     ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
     ap.add_argument("--ref-batches", type=int, default=0, help="batches per step of the reference arm (0 = 8 x cores)")
@@ -400,6 +574,10 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
+    elif args.workload == "walk":
+        run_walk(args)
+    elif args.workload == "hetero":
+        run_hetero(args)
     else:
         run_ours(args)
 

@@ -8,6 +8,7 @@ libtchgeo_cuda.so and fails if it has not been built: there is no CPU fallback.
 """
 from . import _native  # noqa: F401  (loads the CUDA library, raises if missing)
 from .ops import (  # noqa: F401
+    HeterogenousSampler,
     HomogenousSampler,
     SampledBatches,
     ind2ptr,

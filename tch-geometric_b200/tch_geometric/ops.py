@@ -384,20 +384,10 @@ def rel_key(edge_type) -> str:
     return "{}__{}__{}".format(*edge_type)
 
 
-def neighbor_sampling_heterogenous(
-        node_types: List[str],
-        edge_types: List[Tuple[str, str, str]],
-        col_ptrs: Dict[str, Tensor],
-        row_indices: Dict[str, Tensor],
-        inputs: Dict[str, Tensor],
-        num_neighbors: Dict[str, List[int]],
-        num_hops: int,
-        sampler=None,
-        filter=None,
-):
-    """python.rs:273-395.  Returns (samples{node_type}, rows{rel}, cols{rel}, edge_index{rel},
-    layer_offsets{rel}).  Relations are visited in `edge_types` order (the reference iterates a
-    HashMap, quirk Q6)."""
+def _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, inputs, num_neighbors, num_hops, sampler,
+                       filter, num_batches=None):
+    """Argument checking + plan for the heterogeneous sampler.  inputs[t]: [S_t] (single call) or
+    [B, S_t] when num_batches is given."""
     _reject_filter(filter)
     node_types = list(node_types)
     edge_types = [tuple(e) for e in edge_types]
@@ -437,10 +427,11 @@ def neighbor_sampling_heterogenous(
             if len(ks) < num_hops:
                 raise IndexError("num_neighbors[%s] has fewer than num_hops entries" % r)  # :295 index panic
             fan[i, :num_hops] = ks[:num_hops]
+    B = 1 if num_batches is None else int(num_batches)
     inp, seeds = [], []
     for t in node_types:
         if t in inputs:
-            x = _as_seed_matrix(inputs[t], dev, f"inputs[{t}]").reshape(1, -1)
+            x = _as_seed_matrix(inputs[t], dev, f"inputs[{t}]").reshape(B, -1)
             inp.append(x)
             seeds.append(x.shape[1])
         else:
@@ -448,18 +439,81 @@ def neighbor_sampling_heterogenous(
             seeds.append(0)
     call = _Call(dev, [tix[e[0]] for e in edge_types], [tix[e[2]] for e in edge_types], cp, ri,
                  ws if kind == N.SAMPLER_WEIGHTED else None, fan[:, :num_hops].reshape(-1) if num_hops > 0 else [],
-                 active, inp, seeds, 1, num_hops, kind, 0)
-    call.run(seed=_rng_get())
-    out_s = {t: call.samples[i][0, :int(call.samples_len[0, i])] for i, t in enumerate(node_types)}
+                 active, inp, seeds, B, num_hops, kind, 0)
+    call.meta = (node_types, rels, [r in col_ptrs for r in rels], active, num_hops)
+    call.seed_inputs = inp
+    return call
+
+
+def _hetero_batch(call, b):
+    node_types, rels, present, active, num_hops = call.meta
+    out_s = {t: call.samples[i][b, :int(call.samples_len[b, i])] for i, t in enumerate(node_types)}
     out_r, out_c, out_e, out_lo = {}, {}, {}, {}
     for i, r in enumerate(rels):
-        if r not in col_ptrs:
+        if not present[i]:
             continue  # outputs are keyed by graphs.keys(), neighbor_sampling.rs:280-285
-        ne = int(call.edges_len[0, i])
-        out_r[r], out_c[r], out_e[r] = call.rows[i][0, :ne], call.cols[i][0, :ne], call.eidx[i][0, :ne]
-        out_lo[r] = ([tuple(int(x) for x in call.layer_offsets[0, i, h]) for h in range(num_hops)]
+        ne = int(call.edges_len[b, i])
+        out_r[r], out_c[r], out_e[r] = call.rows[i][b, :ne], call.cols[i][b, :ne], call.eidx[i][b, :ne]
+        out_lo[r] = ([tuple(int(x) for x in call.layer_offsets[b, i, h]) for h in range(num_hops)]
                      if active[i] else [])
     return out_s, out_r, out_c, out_e, out_lo
+
+
+def neighbor_sampling_heterogenous(
+        node_types: List[str],
+        edge_types: List[Tuple[str, str, str]],
+        col_ptrs: Dict[str, Tensor],
+        row_indices: Dict[str, Tensor],
+        inputs: Dict[str, Tensor],
+        num_neighbors: Dict[str, List[int]],
+        num_hops: int,
+        sampler=None,
+        filter=None,
+):
+    """python.rs:273-395.  Returns (samples{node_type}, rows{rel}, cols{rel}, edge_index{rel},
+    layer_offsets{rel}).  Relations are visited in `edge_types` order (the reference iterates a
+    HashMap, quirk Q6)."""
+    call = _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, inputs, num_neighbors, num_hops, sampler,
+                              filter)
+    call.run(seed=_rng_get())
+    return _hetero_batch(call, 0)
+
+
+class HeterogenousSampler:
+    """Reusable plan for batched heterogeneous sampling (extension): `sample({type: [B, S_t]})` runs B
+    independent neighbor_sampling_heterogenous calls with one launch per (hop, relation)."""
+
+    def __init__(self, node_types, edge_types, col_ptrs, row_indices, num_batches, seeds_per_batch: Dict[str, int],
+                 num_neighbors, num_hops, sampler=None):
+        dev = next(iter(col_ptrs.values())).device
+        proto = {t: torch.zeros((num_batches, int(s)), dtype=torch.int64, device=dev) for t, s in seeds_per_batch.items()}
+        self._call = _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, proto, num_neighbors, num_hops,
+                                        sampler, None, num_batches=num_batches)
+        self._proto = proto
+        self.num_batches = num_batches
+
+    def sample(self, inputs: Dict[str, Tensor], seed: Optional[int] = None, batch_base: int = 0, timed: bool = False):
+        for t, buf in self._proto.items():
+            if tuple(inputs[t].shape) != tuple(buf.shape):
+                raise ValueError(f"inputs[{t}] must have shape {tuple(buf.shape)}")
+            buf.copy_(inputs[t], non_blocking=True)
+        self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base, timed=timed)
+        return self
+
+    @property
+    def launch_ms(self):
+        return getattr(self._call, "launch_ms", None)
+
+    @property
+    def edges_len(self):
+        return self._call.edges_len  # [B, R]
+
+    @property
+    def samples_len(self):
+        return self._call.samples_len  # [B, T]
+
+    def batch(self, b):
+        return _hetero_batch(self._call, b)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -332,3 +332,17 @@ def test_index_replica_does_not_change_results(thg, fakedataset, monkeypatch):
     thg.rng_reseed(8)
     b = thg.neighbor_sampling_homogenous(ptrs, idx2, inputs, [4])
     assert torch.equal(a[3], b[3]) and torch.equal(b[0][300:], idx2[b[3]])
+
+
+def test_heterogenous_batched_plan(thg, fakehetero):
+    node_types, edge_types, cp, ri, hcp, hri = _hetero_graph(thg, fakehetero)
+    B = 5
+    rng = np.random.default_rng(12)
+    inputs = {node_types[0]: rng.integers(0, 800, (B, 6)), node_types[2]: rng.integers(0, 800, (B, 3))}
+    nn = {thg.rel_key(et): [3, 2] for et in edge_types}
+    plan = thg.HeterogenousSampler(node_types, edge_types, cp, ri, B, {t: v.shape[1] for t, v in inputs.items()}, nn, 2)
+    plan.sample({t: dev(v) for t, v in inputs.items()}, seed=77, batch_base=3)
+    for b in range(B):
+        want = O.neighbor_sampling_heterogenous(node_types, edge_types, hcp, hri, {t: v[b] for t, v in inputs.items()},
+                                                nn, 2, seed=77, batch=3 + b)
+        _cmp_hetero(plan.batch(b), want)
