@@ -191,6 +191,22 @@ TCHGEO_API tchgeo_status tchgeo_neighbor_sampling_homogenous(
     void* workspace /*DEVICE*/, size_t workspace_bytes, tchgeo_stream stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* Range-partitioned CSC (graph split over ranks by column range; BASELINE config 5): owner side. */
+/* Answers n requests for columns [col_begin, col_begin + ncols_local): request i = node id        */
+/* req_ids[i], req_meta[i] = (batch << 32) | position of that node in its batch's samples vector.   */
+/* out_ids / out_ptrs: [n, fanout], slot s of request i = sampled neighbour id and GLOBAL csc        */
+/* position (edge_base + local position), -1 for unused slots.  Draws use the counters of the       */
+/* replicated path, so a requester that lays the answers out in frontier order reproduces           */
+/* tchgeo_neighbor_sampling bit for bit.  Synchronises the stream (error flag read-back).           */
+/* -------------------------------------------------------------------------------------------- */
+TCHGEO_API tchgeo_status tchgeo_serve_requests(
+    const int64_t* ptrs_local /*DEVICE [ncols_local+1], rebased to indices_local*/,
+    const int64_t* indices_local /*DEVICE*/, const double* weights_local /*DEVICE or NULL*/, int64_t col_begin,
+    int64_t ncols_local, int64_t edge_base, const int64_t* req_ids /*DEVICE [n]*/, const int64_t* req_meta /*DEVICE [n]*/,
+    int64_t n, int64_t fanout, int32_t sampler_kind, uint64_t seed, uint32_t rel, int64_t* out_ids /*DEVICE [n*fanout]*/,
+    int64_t* out_ptrs /*DEVICE [n*fanout]*/, int32_t* err_scratch /*DEVICE [1]*/, tchgeo_stream stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* node2vec random walk over CSR.  walks: [num_walks, walk_length+1] row-major, -1 padded.        */
 /* Walker i draws with walker index walker_base + i (so sharded launches reproduce one big one).   */
 /* replaces src/algo/random_walk.rs:10-75                                                        */

@@ -330,3 +330,19 @@ def unique_relabel(samples, num_seeds):
 
 def num_threads():
     return int(lib().orc_num_threads())
+
+
+def serve_requests(ptrs_local, indices_local, col_begin, edge_base, req_ids, req_meta, fanout, sampler=None, seed=0, rel=0):
+    """checker for tchgeo_serve_requests -> (out_ids [n, fanout], out_ptrs [n, fanout])"""
+    ptrs_local, indices_local = _i64(ptrs_local), _i64(indices_local)
+    req_ids, req_meta = _i64(req_ids), _i64(req_meta)
+    kind, w = _sampler_args(sampler)
+    w = None if w is None else np.ascontiguousarray(np.asarray(w, dtype=np.float64))
+    n = req_ids.size
+    out_ids = np.empty((n, fanout), dtype=np.int64)
+    out_ptrs = np.empty((n, fanout), dtype=np.int64)
+    _check(lib().orc_serve_requests(_p(ptrs_local), _p(indices_local), _p(w, ctypes.c_double), ctypes.c_int64(col_begin),
+                                    ctypes.c_int64(ptrs_local.size - 1), ctypes.c_int64(edge_base), _p(req_ids),
+                                    _p(req_meta), ctypes.c_int64(n), ctypes.c_int64(fanout), ctypes.c_int(kind),
+                                    ctypes.c_uint64(seed), ctypes.c_uint32(rel), _p(out_ids), _p(out_ptrs)))
+    return out_ids, out_ptrs

@@ -794,6 +794,38 @@ int orc_unique_relabel(const int64_t* samples, int64_t n, int64_t num_seeds,
   return ORC_OK;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Owner side of the range-partitioned CSC path (no reference counterpart: the reference is      */
+/* single-process).  Checker for tchgeo_serve_requests: answers each request with the per-node   */
+/* body of neighbor_sampling.rs:199-218 in counter mode.                                         */
+/* ------------------------------------------------------------------------------------------ */
+int orc_serve_requests(const int64_t* ptrs_local, const int64_t* indices_local, const double* weights_local,
+                       int64_t col_begin, int64_t ncols_local, int64_t edge_base, const int64_t* req_ids,
+                       const int64_t* req_meta, int64_t n, int64_t fanout, int sampler_kind, uint64_t seed,
+                       uint32_t rel, int64_t* out_ids, int64_t* out_ptrs) {
+  orc_rng rng;
+  orc_rng_init(&rng, ORC_RNG_COUNTER, seed);
+  orc_sampler smp = {sampler_kind, weights_local};
+  orc_filter flt = {ORC_FILTER_NONE, 0, 0, 0, NULL};
+  int64_t* slots = (int64_t*)malloc(sizeof(int64_t) * (size_t)(fanout > 0 ? fanout : 1));
+  int64_t* scratch = NULL;
+  int64_t scratch_cap = 0;
+  int rc = ORC_OK;
+  for (int64_t i = 0; i < n && rc == ORC_OK; ++i) {
+    orc_ctx ctx = {(uint32_t)req_meta[i], (uint32_t)((uint64_t)req_meta[i] >> 32), rel};
+    int64_t cnt = 0;
+    rc = sample_node(&rng, &ctx, &smp, &flt, ptrs_local, indices_local, ncols_local, req_ids[i] - col_begin, 0, fanout,
+                     slots, &scratch, &scratch_cap, &cnt);
+    for (int64_t s = 0; s < fanout; ++s) {
+      out_ids[i * fanout + s] = s < cnt ? indices_local[slots[s]] : -1;
+      out_ptrs[i * fanout + s] = s < cnt ? edge_base + slots[s] : -1;
+    }
+  }
+  free(slots);
+  free(scratch);
+  return rc;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -127,6 +127,26 @@ __device__ __forceinline__ int32_t ld_nc_na_l2hint_i32(const int32_t* p, uint64_
   return v;
 }
 
+// Random gathers with a 64-byte L2 fetch.  Measured on B200 (tools/micro/gather_modes.cu): a plain
+// ld.global / ld.global.nc miss fetches ~111 B from DRAM per random 8-byte gather (the L2 promotes the miss
+// to the whole 128-byte line), L1::no_allocate / .cs / evict_first variants fetch 124 B and are 13 % slower,
+// while the .L2::64B qualifier brings it down to 62 B.  cudaLimitMaxL2FetchGranularity has no effect.
+__device__ __forceinline__ int64_t ld_gather64_i64(const int64_t* p) {
+  int64_t v;
+  asm volatile("ld.global.nc.L2::64B.s64 %0, [%1];" : "=l"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int32_t ld_gather64_i32(const int32_t* p) {
+  int32_t v;
+  asm volatile("ld.global.nc.L2::64B.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int64_t ld_gather64_keep_i64(const int64_t* p, uint64_t pol) {
+  int64_t v;
+  asm volatile("ld.global.nc.L2::cache_hint.L2::64B.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(pol));
+  return v;
+}
+
 // streaming (evict-first) 8-byte store for write-once outputs
 __device__ __forceinline__ void st_cs_i64(int64_t* p, int64_t v) {
   asm volatile("st.global.cs.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");

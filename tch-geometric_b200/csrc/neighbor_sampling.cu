@@ -37,8 +37,8 @@
 namespace tchgeo {
 namespace {
 
-constexpr int HOP_THREADS = 256;
-constexpr int HOP_DEFAULT_MIN_BLOCKS = 6;  // resident CTAs per SM the register budget is compiled for
+constexpr int HOP_THREADS = 128;          // default threads (= max frontier nodes) per tile
+constexpr int HOP_DEFAULT_MIN_BLOCKS = 5;  // register budget: 5 x 256 (or 10 x 128) threads per SM, 48 regs, no spills
 constexpr int MAX_TILE_EDGES = 8192;   // shared-memory slots per tile when fanout <= 8192
 constexpr int MAX_FANOUT = 32768;      // one node per tile above 8192; bounded by shared memory
 constexpr uint64_t ST_FLAG_AGG = 1ull << 62;
@@ -128,14 +128,14 @@ __device__ __forceinline__ void reservoir_block(const Philox4& r, uint32_t step0
   }
 }
 
-template <int KIND, int MINB>
-__global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams p) {
-  using BlockScan = cub::BlockScan<uint32_t, HOP_THREADS>;
+template <int KIND, int MINB, int NT>
+__global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
+  using BlockScan = cub::BlockScan<uint32_t, NT>;
   __shared__ typename BlockScan::TempStorage scan_tmp;
-  __shared__ int64_t s_start[HOP_THREADS];
-  __shared__ NodeRec s_rec[HOP_THREADS];
-  __shared__ uint8_t s_chown[LIGHT_BLOCKS_MAX * HOP_THREADS];  // draw block -> owning node
-  __shared__ uint8_t s_heavy[HOP_THREADS];
+  __shared__ int64_t s_start[NT];
+  __shared__ NodeRec s_rec[NT];
+  __shared__ uint8_t s_chown[LIGHT_BLOCKS_MAX * NT];  // draw block -> owning node
+  __shared__ uint8_t s_heavy[NT];
   __shared__ TileHdr s_hdr;
   __shared__ uint32_t s_work;     // dynamic work counter of the draw phase
   __shared__ uint32_t s_nheavy;
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
       atomicOr(p.err, DEV_ERR_INDEX);  // reference: slice index panic (quirk Q10)
     } else {
       const uint64_t keep = l2_policy_evict_last();  // colptr (8 B/node) should live in the 126 MB L2
-      start = ld_nc_l2hint_i64(p.ptrs + w, keep);
-      const int64_t d = ld_nc_l2hint_i64(p.ptrs + w + 1, keep) - start;
+      start = ld_gather64_keep_i64(p.ptrs + w, keep);
+      const int64_t d = ld_gather64_keep_i64(p.ptrs + w + 1, keep) - start;
       if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
       else deg = (uint32_t)d;
     }
@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
     }
     // Heavy nodes (deg > k + 4*LIGHT_BLOCKS_MAX): one warp strides over one node's blocks.
     const uint32_t nheavy = s_nheavy;
-    for (uint32_t h = (uint32_t)(tid >> 5); h < nheavy; h += HOP_THREADS / 32) {
+    for (uint32_t h = (uint32_t)(tid >> 5); h < nheavy; h += NT / 32) {
       const uint32_t n = s_heavy[h];
       const NodeRec rec = s_rec[n];
       const uint32_t nb = (rec.deg - k + 3u) >> 2;
@@ -303,7 +303,7 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
     }
   } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
     const int warp = tid >> 5;
-    for (int n = warp; n < nn; n += HOP_THREADS / 32) {
+    for (int n = warp; n < nn; n += NT / 32) {
       const NodeRec rec = s_rec[n];
       const uint32_t dn = rec.deg;
       if (dn <= k) continue;
@@ -355,16 +355,15 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
   int64_t* o_c = p.cols + (int64_t)b * p.e_stride + e_base;
   int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
   const int64_t col0 = fb + node0;
-  const uint64_t stream_pol = l2_policy_evict_first();  // single-use random sectors
   const uint32_t rtag = TAG_REPLACE | (p.rel << 8);
   constexpr uint32_t U = 4;
-  for (uint32_t e0 = tid; e0 < total; e0 += HOP_THREADS * U) {
+  for (uint32_t e0 = tid; e0 < total; e0 += NT * U) {
     int64_t ptr[U];
     int64_t val[U];
     uint32_t own[U];
 #pragma unroll
     for (uint32_t u = 0; u < U; ++u) {
-      const uint32_t e = min(e0 + u * HOP_THREADS, total - 1);  // clamped: tail lanes redo the last edge
+      const uint32_t e = min(e0 + u * NT, total - 1);  // clamped: tail lanes redo the last edge
       const uint32_t n = s_owner[e];
       const NodeRec rec = s_rec[n];
       const uint32_t s = e - rec.off;
@@ -382,15 +381,15 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
     if (p.indices32) {
 #pragma unroll
       for (uint32_t u = 0; u < U; ++u)
-        val[u] = (e0 + u * HOP_THREADS < total) ? (int64_t)ld_nc_na_l2hint_i32(p.indices32 + ptr[u], stream_pol) : 0;
+        val[u] = (e0 + u * NT < total) ? (int64_t)ld_gather64_i32(p.indices32 + ptr[u]) : 0;
     } else {
 #pragma unroll
       for (uint32_t u = 0; u < U; ++u)
-        val[u] = (e0 + u * HOP_THREADS < total) ? ld_nc_na_l2hint_i64(p.indices + ptr[u], stream_pol) : 0;
+        val[u] = (e0 + u * NT < total) ? ld_gather64_i64(p.indices + ptr[u]) : 0;
     }
 #pragma unroll
     for (uint32_t u = 0; u < U; ++u) {
-      const uint32_t e = e0 + u * HOP_THREADS;
+      const uint32_t e = e0 + u * NT;
       if (e < total) {
         st_cs_i64(o_e + e, ptr[u]);
         st_cs_i64(o_c + e, col0 + own[u]);
@@ -399,6 +398,29 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
       }
     }
   }
+}
+
+// Tuning knobs (defaults are what bench.py measures): TCHGEO_HOP_THREADS = 128 | 256 threads per tile,
+// TCHGEO_HOP_MIN_BLOCKS = 4 | 6 | 8 register-budget variant of the 256-thread kernel.
+inline int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+inline int hop_threads() {
+  static int v = -1;
+  if (v < 0) {
+    const int x = env_int("TCHGEO_HOP_THREADS", HOP_THREADS);
+    v = (x == 128 || x == 256) ? x : HOP_THREADS;
+  }
+  return v;
+}
+inline int hop_min_blocks() {
+  static int v = -1;
+  if (v < 0) {
+    const int x = env_int("TCHGEO_HOP_MIN_BLOCKS", HOP_DEFAULT_MIN_BLOCKS);
+    v = (x >= 4 && x <= 8) ? x : HOP_DEFAULT_MIN_BLOCKS;
+  }
+  return v;
 }
 
 // ---- host-side plan: which launches, which version rows of the length table ------------------
@@ -491,7 +513,7 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
       L.e_in_row = cur_e[r]; L.e_out_row = rows++;
       L.dst_len_row = cur_n[dt];
       const int64_t kk = std::max<int64_t>(k, 1);
-      int tn = (int)std::min<int64_t>(HOP_THREADS, std::max<int64_t>(1, MAX_TILE_EDGES / kk));
+      int tn = (int)std::min<int64_t>(hop_threads(), std::max<int64_t>(1, MAX_TILE_EDGES / kk));
       L.tile_nodes = tn;
       L.tile_edges = (int)(tn * kk);
       const int64_t tpb = (fcap + tn - 1) / tn;
@@ -528,38 +550,36 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   return TCHGEO_OK;
 }
 
-template <int KIND, int MINB>
+template <int KIND, int MINB, int NT>
 cudaError_t launch_hop_v(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
   static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(hop_kernel<KIND, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(hop_kernel<KIND, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  hop_kernel<KIND, MINB><<<(unsigned)grid, HOP_THREADS, smem, stream>>>(hp);
+  hop_kernel<KIND, MINB, NT><<<(unsigned)grid, NT, smem, stream>>>(hp);
   return cudaGetLastError();
-}
-
-// TCHGEO_HOP_MIN_BLOCKS (4, 6 or 8) selects the register budget variant; tuning knob, default 6.
-inline int hop_min_blocks() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("TCHGEO_HOP_MIN_BLOCKS");
-    int x = e ? atoi(e) : HOP_DEFAULT_MIN_BLOCKS;
-    v = (x == 4 || x == 6 || x == 8) ? x : HOP_DEFAULT_MIN_BLOCKS;
-  }
-  return v;
 }
 
 template <int KIND>
 cudaError_t launch_hop(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+  if (hop_threads() == 128) {
+    switch (hop_min_blocks()) {
+      case 5: return launch_hop_v<KIND, 10, 128>(hp, grid, smem, stream);
+      case 7: return launch_hop_v<KIND, 14, 128>(hp, grid, smem, stream);
+      default: return launch_hop_v<KIND, 12, 128>(hp, grid, smem, stream);
+    }
+  }
   switch (hop_min_blocks()) {
-    case 4: return launch_hop_v<KIND, 4>(hp, grid, smem, stream);
-    case 8: return launch_hop_v<KIND, 8>(hp, grid, smem, stream);
-    default: return launch_hop_v<KIND, 6>(hp, grid, smem, stream);
+    case 4: return launch_hop_v<KIND, 4, 256>(hp, grid, smem, stream);
+    case 5: return launch_hop_v<KIND, 5, 256>(hp, grid, smem, stream);
+    case 7: return launch_hop_v<KIND, 7, 256>(hp, grid, smem, stream);
+    case 8: return launch_hop_v<KIND, 8, 256>(hp, grid, smem, stream);
+    default: return launch_hop_v<KIND, 6, 256>(hp, grid, smem, stream);
   }
 }
 

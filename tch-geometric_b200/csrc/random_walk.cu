@@ -40,7 +40,7 @@ struct WalkParams {
 __device__ __forceinline__ bool has_edge_dev(const int64_t* __restrict__ col, int64_t lo, int64_t hi, int64_t y) {
   while (lo < hi) {  // graph.rs:80-83
     const int64_t mid = lo + ((hi - lo) >> 1);
-    const int64_t v = __ldg(col + mid);
+    const int64_t v = ld_gather64_i64(col + mid);
     if (v == y) return true;
     if (v < y) lo = mid + 1; else hi = mid;
   }
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) 
                 r4 = philox4x32_10((uint32_t)walker, (uint32_t)(walker >> 32), l, TAG_WALK | ((a >> 1) << 8), p.key0, p.key1);
               const uint32_t ri = (a & 1u) ? r4.z : r4.x;
               const uint32_t rf = (a & 1u) ? r4.w : r4.y;
-              next = __ldg(p.col_indices + nb + (int64_t)__umulhi(ri, (uint32_t)d));  // :53
+              next = ld_gather64_i64(p.col_indices + nb + (int64_t)__umulhi(ri, (uint32_t)d));  // :53
               const float r = (float)(rf >> 8) * (1.0f / 16777216.0f);               // :54
               ++my_attempts;
               if (next == prev) {  // :56-58
@@ -104,8 +104,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) 
               }
               if (r >= pmax) continue;  // rejected whatever has_edge says
               if (next < 0 || next >= p.num_rows) { atomicOr(p.err, DEV_ERR_INDEX); break; }
-              nnb = __ldg(p.row_ptrs + next);
-              nne = __ldg(p.row_ptrs + next + 1);
+              nnb = ld_gather64_i64(p.row_ptrs + next);
+              nne = ld_gather64_i64(p.row_ptrs + next + 1);
               if (r < pmin) { accepted = true; break; }  // accepted whatever has_edge says
               const bool he = prev >= 0 && has_edge_dev(p.col_indices, nnb, nne, prev);  // :59
               if (he ? (r < p.prob1) : (r < p.prob2)) { accepted = true; break; }        // :60-65

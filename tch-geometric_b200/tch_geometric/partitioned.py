@@ -1,0 +1,180 @@
+"""Range-partitioned CSC sampling (BASELINE config 5): the graph's columns are split over ranks and the
+hop frontiers are exchanged with an all-to-all (NCCL over NVLink on the GPUs).
+
+Every rank samples its OWN seed batches; per hop it
+  1. buckets its frontier by owning rank (owner(w) = w // cols_per_rank),
+  2. all-to-all's the requests (node id, global batch index, position in the batch's samples vector),
+  3. answers the requests it received with `tchgeo_serve_requests` (the CUDA kernel; draws use the same
+     Philox counters as the replicated path),
+  4. all-to-all's the answers back and lays them out in frontier order.
+Because the counters depend only on (seed, batch, position, degree), the result equals the single-GPU
+`neighbor_sampling_homogenous` result bit for bit, whatever the partitioning.
+
+The reference has no counterpart (it is single-process); the tree layout produced here is the one of
+src/algo/neighbor_sampling.rs:162-230.  Host orchestration uses torch ops for the bucketing and the
+compaction (plumbing); the sampling itself runs in the serve kernel.
+"""
+import ctypes
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+from torch import Tensor
+
+from . import _native as N
+from .ops import _check, _extract_sampler, _ptr, _rng_get, _stream
+
+
+def cols_per_rank(num_nodes: int, world: int) -> int:
+    return max((num_nodes + world - 1) // world, 1)
+
+
+def partition_bounds(num_nodes: int, rank: int, world: int) -> Tuple[int, int]:
+    c = cols_per_rank(num_nodes, world)
+    return min(rank * c, num_nodes), min((rank + 1) * c, num_nodes)
+
+
+class ColumnPartition:
+    """This rank's share of a CSC: columns [col_begin, col_end) with a colptr rebased to the local
+    row_indices slice; edge_base = number of CSC entries owned by lower ranks."""
+
+    def __init__(self, col_ptrs_local: Tensor, row_indices_local: Tensor, num_nodes: int, rank: int, world: int,
+                 edge_base: int, weights_local: Optional[Tensor] = None):
+        self.col_begin, self.col_end = partition_bounds(num_nodes, rank, world)
+        if col_ptrs_local.numel() != self.col_end - self.col_begin + 1:
+            raise ValueError("col_ptrs_local must have one entry per owned column plus one")
+        self.ptrs, self.indices, self.weights = col_ptrs_local, row_indices_local, weights_local
+        self.num_nodes, self.rank, self.world, self.edge_base = int(num_nodes), rank, world, int(edge_base)
+        self.cols_per_rank = cols_per_rank(num_nodes, world)
+
+    @staticmethod
+    def from_full(col_ptrs: Tensor, row_indices: Tensor, rank: int, world: int, weights: Optional[Tensor] = None):
+        """Slice a replicated CSC (tests and small graphs)."""
+        n = col_ptrs.numel() - 1
+        b, e = partition_bounds(n, rank, world)
+        lo, hi = int(col_ptrs[b].item()), int(col_ptrs[e].item())
+        return ColumnPartition((col_ptrs[b:e + 1] - lo).contiguous(), row_indices[lo:hi].contiguous(), n, rank, world, lo,
+                               None if weights is None else weights[lo:hi].contiguous())
+
+
+class SingleComm:
+    rank, world = 0, 1
+
+    def exchange(self, send_counts: Tensor, *tensors):
+        return (send_counts,) + tuple(tensors)
+
+
+class DistComm:
+    """all-to-all(v) over a torch.distributed group (NCCL on GPUs, gloo in the CPU tests)."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+
+    def exchange(self, send_counts: Tensor, *tensors):
+        recv_counts = torch.empty_like(send_counts)
+        dist.all_to_all_single(recv_counts, send_counts, group=self.group)
+        sc, rc = send_counts.tolist(), recv_counts.tolist()
+        outs = []
+        for t in tensors:
+            out = torch.empty((sum(rc),) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_to_all_single(out, t.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+            outs.append(out)
+        return (recv_counts,) + tuple(outs)
+
+
+def cuda_serve(part: ColumnPartition, req_ids: Tensor, req_meta: Tensor, fanout: int, kind: int, seed: int, rel: int = 0):
+    """Answer requests with the CUDA kernel behind tchgeo_serve_requests -> (ids [n,k], ptrs [n,k])."""
+    dev = part.ptrs.device
+    _check(part.ptrs, torch.int64, "col_ptrs_local")
+    _check(part.indices, torch.int64, "row_indices_local", dev)
+    n = req_ids.numel()
+    out_ids = torch.empty((n, fanout), dtype=torch.int64, device=dev)
+    out_ptrs = torch.empty((n, fanout), dtype=torch.int64, device=dev)
+    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        st = N.lib.tchgeo_serve_requests(_ptr(part.ptrs), _ptr(part.indices), _ptr(part.weights), part.col_begin,
+                                         part.col_end - part.col_begin, part.edge_base, _ptr(req_ids.contiguous()),
+                                         _ptr(req_meta.contiguous()), n, int(fanout), kind, seed, rel, _ptr(out_ids),
+                                         _ptr(out_ptrs), _ptr(scratch), _stream(dev))
+    N.check(st)
+    return out_ids, out_ptrs
+
+
+class PartitionedSampler:
+    """neighbor_sampling_homogenous over a column-partitioned CSC.  `sample` is collective: every rank of
+    the communicator must call it (with its own seed batches) the same number of times."""
+
+    def __init__(self, part: ColumnPartition, num_neighbors: Sequence[int], sampler=None, comm=None, serve=None):
+        self.part = part
+        self.fanouts = [int(k) for k in num_neighbors]
+        self.kind, w = _extract_sampler(sampler, hetero=False)
+        if self.kind == N.SAMPLER_WEIGHTED and part.weights is None:
+            raise ValueError("weighted sampling needs ColumnPartition.weights_local")
+        self.comm = comm if comm is not None else (DistComm() if dist.is_available() and dist.is_initialized() else SingleComm())
+        self.serve = serve if serve is not None else cuda_serve
+        self.stats = {"requests_sent": 0, "request_bytes": 0, "answer_bytes": 0}
+
+    def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0):
+        """inputs [B, S] (this rank's batches) -> list of B tuples (samples, rows, cols, edge_index, layer_offsets)."""
+        if inputs.dim() != 2 or inputs.dtype != torch.int64:
+            raise ValueError("inputs must be an int64 tensor of shape [B, S]")
+        seed = _rng_get() if seed is None else seed
+        dev, (B, S), world = inputs.device, inputs.shape, self.comm.world
+        C = self.part.cols_per_rank
+        ar = lambda n: torch.arange(n, dtype=torch.int64, device=dev)
+        ids = inputs.reshape(-1)
+        bidx = ar(B).repeat_interleave(S)
+        pos = ar(S).repeat(B)
+        node_len = torch.full((B,), S, dtype=torch.int64, device=dev)
+        edge_len = torch.zeros(B, dtype=torch.int64, device=dev)
+        hop_ids, hop_cols, hop_eidx, hop_bidx, hop_lo = [], [], [], [], []
+        for k in self.fanouts:
+            hop_lo.append(torch.stack([node_len, edge_len, node_len], dim=1).clone())
+            F = ids.numel()
+            owner = torch.clamp(torch.div(ids, C, rounding_mode="floor"), 0, world - 1)
+            order = torch.argsort(owner, stable=True)
+            send_counts = torch.bincount(owner, minlength=world)
+            req_ids = ids[order]
+            req_meta = ((bidx[order] + batch_base) << 32) | pos[order]
+            recv_counts, r_ids, r_meta = self.comm.exchange(send_counts, req_ids, req_meta)
+            o_ids, o_ptrs = self.serve(self.part, r_ids, r_meta, k, self.kind, seed, 0)
+            _, a_ids, a_ptrs = self.comm.exchange(recv_counts, o_ids, o_ptrs)
+            self.stats["requests_sent"] += F
+            self.stats["request_bytes"] += 16 * F
+            self.stats["answer_bytes"] += 16 * k * F
+            inv = torch.empty_like(order)
+            inv[order] = ar(F)
+            a_ids, a_ptrs = a_ids[inv], a_ptrs[inv]                 # answers back in frontier order
+            mask = a_ptrs >= 0
+            cnt = mask.sum(dim=1)
+            new_ids, new_eidx = a_ids[mask], a_ptrs[mask]           # row-major: frontier order, then slot order
+            new_cols, new_bidx = pos.repeat_interleave(cnt), bidx.repeat_interleave(cnt)
+            per_batch = torch.zeros(B, dtype=torch.int64, device=dev).index_add_(0, bidx, cnt)
+            first = torch.cumsum(per_batch, 0) - per_batch
+            new_pos = ar(new_ids.numel()) - first[new_bidx] + node_len[new_bidx]
+            hop_ids.append(new_ids); hop_cols.append(new_cols); hop_eidx.append(new_eidx); hop_bidx.append(new_bidx)
+            node_len = node_len + per_batch
+            edge_len = edge_len + per_batch
+            ids, bidx, pos = new_ids, new_bidx, new_pos
+        # regroup hop-major arrays into per-batch contiguous results
+        all_b = torch.cat([ar(B).repeat_interleave(S)] + hop_bidx)
+        all_ids = torch.cat([inputs.reshape(-1)] + hop_ids)
+        o = torch.argsort(all_b, stable=True)
+        samples_flat = all_ids[o]
+        if hop_bidx:
+            eb = torch.cat(hop_bidx)
+            oe = torch.argsort(eb, stable=True)
+            cols_flat, eidx_flat = torch.cat(hop_cols)[oe], torch.cat(hop_eidx)[oe]
+        else:
+            cols_flat = eidx_flat = torch.zeros(0, dtype=torch.int64, device=dev)
+        nl, el = node_len.tolist(), edge_len.tolist()
+        lo_host = [x.tolist() for x in hop_lo]
+        out, n0, e0 = [], 0, 0
+        for b in range(B):
+            rows = torch.arange(S, S + el[b], dtype=torch.int64, device=dev)
+            lo = [tuple(int(v) for v in lo_host[h][b]) for h in range(len(self.fanouts))]
+            out.append((samples_flat[n0:n0 + nl[b]], rows, cols_flat[e0:e0 + el[b]], eidx_flat[e0:e0 + el[b]], lo))
+            n0 += nl[b]
+            e0 += el[b]
+        return out
