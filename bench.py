@@ -557,13 +557,81 @@ def run_hetero(args):
         dist.destroy_process_group()
 
 
+def run_partitioned(args):
+    """configs[4]: papers100M-shaped graph, CSC range-partitioned over the ranks, 3-hop [15,10,5] sampling with an
+    NCCL all-to-all frontier exchange per hop.  Weak scaling: every rank owns 13 882 495 columns / ~202 M edges, so
+    8 ranks hold exactly the 111 059 956-node, 1 615 685 872-edge shape."""
+    import tch_geometric as thg
+    import torch.distributed as dist
+    from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedSampler, SingleComm, partition_bounds
+    from tch_geometric.sharding import reduce_job
+    rank, world, local = dist_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    cols_full, edges_full = 111_059_956 // 8 + 1, 1_615_685_872 // 8
+    cols_rank = max(int(cols_full * args.scale), 64)
+    n = cols_rank * world
+    b, e = partition_bounds(n, rank, world)
+    deg = synth.lognormal_degrees(e - b, max(int(edges_full * args.scale), e - b), dmax=17_481, seed=42 + rank)
+    ei = synth.edges_from_degrees(deg, n, device, seed=42 + rank)            # rows over all N nodes, cols local
+    ptrs, idx, _ = thg.to_csc(ei, (n, e - b))
+    del ei
+    torch.cuda.empty_cache()
+    e_local = torch.tensor([idx.numel()], dtype=torch.int64, device=device)
+    if world > 1:
+        allc = [torch.zeros_like(e_local) for _ in range(world)]
+        dist.all_gather(allc, e_local)
+        edge_base = int(sum(int(x.item()) for x in allc[:rank]))
+        e_total = int(sum(int(x.item()) for x in allc))
+    else:
+        edge_base, e_total = 0, int(e_local.item())
+    part = ColumnPartition(ptrs, idx, n, rank, world, edge_base)
+    B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
+    ps = PartitionedSampler(part, FANOUTS, comm=DistComm() if world > 1 else SingleComm())
+    seeds = [torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B)).to(device)
+             for s in range(W + K)]
+    for s in range(W):
+        ps.sample(seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edges_n = 0
+    e0.record()
+    for s in range(W, W + K):
+        out = ps.sample(seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
+        edges_n += sum(int(o[1].numel()) for o in out)
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms, edges_all = reduce_job(e0.elapsed_time(e1), float(edges_n), device)
+    if rank == 0:
+        emit({"metric": "sampled_edges_per_sec_3hop_15_10_5_partitioned_csc", "value": edges_all / (ms * 1e-3),
+              "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+              "config": {"workload": f"papers100M-shaped synthetic graph (N={n}, E={e_total}; {cols_rank} columns per rank), "
+                                     f"CSC range-partitioned over {world} rank(s), fanouts {FANOUTS}, {S} seeds/batch, "
+                                     f"{B} batches/step/rank, NCCL all-to-all frontier exchange per hop",
+                         "parallelism": "column-range partition + all-to-all(v) of requests and answers"},
+              "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + K),
+                                                   "answers": ps.stats["answer_bytes"] // (W + K)},
+              "cpu_baseline": None, "e2e": None, "gpu_launches": K * len(FANOUTS), "clocks": clk})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero"],
+    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned"],
                     help="sampling = headline (configs[1]); walk = configs[2]; hetero = configs[3]")
     ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
@@ -578,6 +646,8 @@ def main():
         run_walk(args)
     elif args.workload == "hetero":
         run_hetero(args)
+    elif args.workload == "partitioned":
+        run_partitioned(args)
     else:
         run_ours(args)
 

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TCHGEO_ABI_VERSION 2
+#define TCHGEO_ABI_VERSION 3
 
 #if defined(__GNUC__)
 #define TCHGEO_API __attribute__((visibility("default")))
@@ -143,6 +143,15 @@ typedef struct tchgeo_sampling_args {
   int64_t* layer_offsets;           /* HOST [B*R*H*3] LayerOffset = (len(samples[src]),
                                        len(edges[rel]), len(samples[dst])) at relation start,
                                        src/algo/neighbor_sampling.rs:193,:314-315                  */
+  /* ---- temporal filter (src/algo/neighbor_sampling.rs:36-77, src/python.rs:137-168); 0 = IdentityFilter ---- */
+  int32_t filter_mode;              /* 0 none, 1 TEMPORAL_SAMPLE_STATIC, 2 _RELATIVE, 3 _DYNAMIC (reference mode + 1) */
+  int32_t filter_forward;           /* FORWARD const generic (ignored for STATIC)                  */
+  int64_t filter_window_lo;         /* inclusive window, RangeInclusive<i64>                       */
+  int64_t filter_window_hi;
+  const int64_t* const* timestamps; /* HOST [R] of DEVICE [nnz_r] i64 per CSC position             */
+  const int64_t* const* inputs_state; /* HOST [T] of DEVICE [B, seeds_per_batch[t]] i64            */
+  int64_t* const* states;           /* HOST [T] of DEVICE [B, samples_stride[t]] i64: per-sample
+                                       filter state (scratch/output, caller allocated)             */
   /* ---- workspace ---- */
   void* workspace;                  /* DEVICE                                                      */
   size_t workspace_bytes;

@@ -77,6 +77,13 @@ struct HopParams {
   uint32_t key0, key1;
   uint32_t rel;
   uint32_t batch_base;
+  // temporal filter (src/algo/neighbor_sampling.rs:36-77); filter_mode 0 = none
+  int32_t filter_mode;          // 1 static, 2 relative, 3 dynamic
+  int32_t filter_forward;
+  int64_t win_lo, win_hi;
+  const int64_t* timestamps;    // [nnz] per CSC position
+  const int64_t* dst_states;    // [B, dst_stride] state of every sample of the dst type
+  int64_t* src_states;          // [B, src_stride] states of appended samples are written here
 };
 
 __global__ void __launch_bounds__(256) compress_kernel(const int64_t* __restrict__ src, int64_t n,
@@ -400,6 +407,230 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Temporal-filter variant (src/algo/neighbor_sampling.rs:36-77 + :204-217).
+// The samplers see only the edges that pass the filter, in CSC order, so every position below is a
+// position AMONG THE PASSING EDGES.  One warp per frontier node: pass 1 counts the passing edges,
+// the tile then takes its output offset from the same look-back protocol as hop_kernel, pass 2 makes the
+// sampling decisions (same Philox counters, steps indexed by passing position) and a final sweep over
+// the neighbourhood emits the chosen edges and the new per-sample states.
+// ---------------------------------------------------------------------------------------------
+constexpr int FT_THREADS = 128;
+
+__device__ __forceinline__ bool filter_pass(const HopParams& p, int64_t t, int64_t state) {
+  if (p.filter_mode == 1) return p.win_lo <= t && t <= p.win_hi;  // STATIC, :59
+  int64_t d = t - state;                                            // RELATIVE / DYNAMIC, :60-65
+  if (!p.filter_forward) d = -d;
+  return p.win_lo <= d && d <= p.win_hi;
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParams p) {
+  using BlockScan = cub::BlockScan<uint32_t, FT_THREADS>;
+  __shared__ typename BlockScan::TempStorage scan_tmp;
+  __shared__ int64_t s_start[FT_THREADS], s_state[FT_THREADS];
+  __shared__ uint32_t s_deg[FT_THREADS], s_pass[FT_THREADS], s_off[FT_THREADS];
+  __shared__ TileHdr s_hdr;
+  __shared__ int64_t s_excl;
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  uint32_t* s_slot = reinterpret_cast<uint32_t*>(dyn_smem);  // [tile_edges]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NWARP = FT_THREADS / 32;
+  const int TN = p.tile_nodes;
+  if (tid == 0) {
+    const uint32_t ticket = atomicAdd(p.ticket, 1u);
+    const int t = (int)(ticket / (uint32_t)p.num_batches);
+    const int b = (int)(ticket - (uint32_t)t * (uint32_t)p.num_batches);
+    const int64_t fb = p.fr_begin[b];
+    int64_t fe = p.fr_end[b];
+    if (fe > p.dst_stride) fe = p.dst_stride;
+    s_hdr.fb = fb; s_hdr.F = fe > fb ? fe - fb : 0;
+    s_hdr.e_in = p.e_len_in[b]; s_hdr.s_in = p.src_len_in[b];
+    s_hdr.b = b; s_hdr.t = t;
+  }
+  __syncthreads();
+  const int b = s_hdr.b, t = s_hdr.t;
+  const int64_t fb = s_hdr.fb, F = s_hdr.F;
+  const uint32_t k = (uint32_t)p.fanout;
+  const int64_t node0 = (int64_t)t * TN;
+  const int nn = (int)max((int64_t)0, min((int64_t)TN, F - node0));
+  const bool is_last = (nn > 0 && node0 + nn == F) || (F == 0 && t == 0);
+  if (nn == 0 && !is_last) return;
+
+  // ---- pass 1: number of passing edges per node ------------------------------------------------
+  for (int n = warp; n < nn; n += NWARP) {
+    const int64_t gi = (int64_t)b * p.dst_stride + fb + node0 + n;
+    const int64_t w = p.dst_samples[gi];
+    const int64_t state = p.dst_states[gi];
+    int64_t start = 0;
+    uint32_t deg = 0, npass = 0;
+    if (w < 0 || w >= p.num_cols) {
+      if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX);
+    } else {
+      start = __ldg(p.ptrs + w);
+      const int64_t d = __ldg(p.ptrs + w + 1) - start;
+      if (d < 0 || d > 0x7fffffffll) { if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX); }
+      else deg = (uint32_t)d;
+    }
+    for (uint32_t base = 0; base < deg; base += 32) {
+      const uint32_t item = base + lane;
+      const bool ok = item < deg && filter_pass(p, __ldg(p.timestamps + start + item), state);
+      npass += __popc(__ballot_sync(0xffffffffu, ok));
+    }
+    if (lane == 0) { s_start[n] = start; s_state[n] = state; s_deg[n] = deg; s_pass[n] = npass; }
+  }
+  __syncthreads();
+  uint32_t cnt = 0;
+  if (tid < nn) {
+    const uint32_t np = s_pass[tid];
+    if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) cnt = np > 0 ? k : 0;
+    else {
+      cnt = np < k ? np : k;
+      if (k == 0 && np > 0) atomicOr(p.err, DEV_ERR_PANIC);
+    }
+  }
+  uint32_t off, total;
+  BlockScan(scan_tmp).ExclusiveSum(cnt, off, total);
+  s_off[tid] = off;
+
+  // ---- look-back (same protocol as hop_kernel) --------------------------------------------------
+  uint64_t* my_status = p.status + (size_t)b * p.tiles_per_batch;
+  if (tid < 32) {
+    int64_t excl = 0;
+    if (t == 0) {
+      if (lane == 0) st_relaxed_u64(my_status, ST_FLAG_INCL | (uint64_t)total);
+    } else {
+      if (lane == 0) st_relaxed_u64(my_status + t, ST_FLAG_AGG | (uint64_t)total);
+      int j = t - 1;
+      uint32_t spins = 0;
+      while (true) {
+        const int idx = j - lane;
+        const uint64_t v = idx >= 0 ? ld_relaxed_u64(my_status + idx) : ST_FLAG_INCL;
+        const uint32_t flag = (uint32_t)(v >> 62);
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+        const uint32_t inval_mask = __ballot_sync(0xffffffffu, flag == 0u);
+        const int first_incl = incl_mask ? __ffs(incl_mask) - 1 : 32;
+        const int first_inval = inval_mask ? __ffs(inval_mask) - 1 : 32;
+        if (first_inval < first_incl) {
+          if (++spins > (1u << 24)) { if (lane == 0) atomicOr(p.err, DEV_ERR_WATCHDOG); break; }
+          __nanosleep(32);
+          continue;
+        }
+        int64_t val = lane <= first_incl ? (int64_t)(v & ST_VAL_MASK) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        excl += val;
+        if (first_incl < 32) break;
+        j -= 32;
+      }
+      if (lane == 0) st_relaxed_u64(my_status + t, ST_FLAG_INCL | (uint64_t)(excl + total));
+    }
+    if (lane == 0) s_excl = excl;
+  }
+  __syncthreads();
+  const int64_t excl = s_excl;
+  const int64_t e_base = s_hdr.e_in + excl;
+  const int64_t s_base = s_hdr.s_in + excl;
+  if (is_last && tid == 0) {
+    p.e_len_out[b] = e_base + total;
+    p.src_len_out[b] = s_base + total;
+  }
+  if (e_base + total > p.e_stride || s_base + total > p.src_stride) {
+    if (tid == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
+    return;
+  }
+  if (total == 0) return;
+
+  // ---- pass 2: decisions + emission, one warp per node ------------------------------------------
+  const uint32_t pos0 = (uint32_t)(fb + node0);
+  const uint32_t batch = p.batch_base + (uint32_t)b;
+  int64_t* o_s = p.src_samples + (int64_t)b * p.src_stride + s_base;
+  int64_t* o_st = p.src_states + (int64_t)b * p.src_stride + s_base;
+  int64_t* o_r = p.rows + (int64_t)b * p.e_stride + e_base;
+  int64_t* o_c = p.cols + (int64_t)b * p.e_stride + e_base;
+  int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
+  for (int n = warp; n < nn; n += NWARP) {
+    const uint32_t np = s_pass[n], deg = s_deg[n], o = s_off[n];
+    const uint32_t c_n = KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE ? (np > 0 ? k : 0u) : min(np, k);
+    if (c_n == 0) continue;
+    const int64_t start = s_start[n], state = s_state[n];
+    uint32_t* q = s_slot + o;  // q[s] = passing position chosen for slot s
+    for (uint32_t s = lane; s < c_n; s += 32) q[s] = 0u;
+    __syncwarp();
+    if (KIND == TCHGEO_SAMPLER_UNIFORM && np > k) {
+      const uint32_t nb = (np - k + 3u) >> 2;
+      for (uint32_t c = lane; c < nb; c += 32)
+        reservoir_block(philox4x32_10(pos0 + n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1), k + 4u * c, np, k, q);
+    } else if (KIND == TCHGEO_SAMPLER_WEIGHTED && np > k) {
+      double carry = 0.0;
+      uint32_t rank0 = 0;
+      for (uint32_t base = 0; base < deg; base += 32) {
+        const uint32_t item = base + lane;
+        const bool ok = item < deg && filter_pass(p, __ldg(p.timestamps + start + item), state);
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        const uint32_t rank = rank0 + __popc(m & ((1u << lane) - 1u));
+        const double w = ok ? __ldg(p.weights + start + item) : 0.0;
+        double incl = w;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+          const double up = __shfl_up_sync(0xffffffffu, incl, sft);
+          if (lane >= sft) incl += up;
+        }
+        const double w_sum = carry + incl;
+        if (ok && rank >= k) {
+          if (!(w_sum > 0.0)) atomicOr(p.err, DEV_ERR_PANIC);
+          else {
+            const Philox4 r = philox4x32_10(pos0 + n, rank, batch, TAG_WEIGHTED | (p.rel << 8), p.key0, p.key1);
+            const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
+            const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
+            if (__dmul_rn(u, w_sum) < w) atomicMax(q + __umulhi(r.z, k), rank);
+          }
+        }
+        carry = __shfl_sync(0xffffffffu, w_sum, 31);
+        rank0 += __popc(m);
+      }
+    }
+    __syncwarp();
+    for (uint32_t s = lane; s < c_n; s += 32) {
+      if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
+        const Philox4 r = philox4x32_10(pos0 + n, s >> 2, batch, TAG_REPLACE | (p.rel << 8), p.key0, p.key1);
+        q[s] = __umulhi(pick4(r, s & 3u), np);
+      } else {
+        const uint32_t st = q[s];
+        q[s] = st ? st : s;
+      }
+    }
+    __syncwarp();
+    // sweep: the passing edge with position `rank` feeds every slot that chose it
+    uint32_t rank0 = 0;
+    for (uint32_t base = 0; base < deg; base += 32) {
+      const uint32_t item = base + lane;
+      const int64_t ptr = start + item;
+      const int64_t ts = item < deg ? __ldg(p.timestamps + ptr) : 0;
+      const bool ok = item < deg && filter_pass(p, ts, state);
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (ok) {
+        const uint32_t rank = rank0 + __popc(m & ((1u << lane) - 1u));
+        int64_t v = 0;
+        bool loaded = false;
+        for (uint32_t s = 0; s < c_n; ++s) {
+          if (q[s] == rank) {
+            if (!loaded) { v = __ldg(p.indices + ptr); loaded = true; }
+            const uint32_t e = o + s;
+            o_s[e] = v;
+            o_st[e] = p.filter_mode == 3 ? ts : state;  // mutate(), :69-76
+            o_r[e] = s_base + e;
+            o_c[e] = fb + node0 + n;
+            o_e[e] = ptr;
+          }
+        }
+      }
+      rank0 += __popc(m);
+    }
+  }
+}
+
 // Tuning knobs (defaults are what bench.py measures): TCHGEO_HOP_THREADS = 128 | 256 threads per tile,
 // TCHGEO_HOP_MIN_BLOCKS = 4 | 6 | 8 register-budget variant of the 256-thread kernel.
 inline int env_int(const char* name, int dflt) {
@@ -513,7 +744,8 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
       L.e_in_row = cur_e[r]; L.e_out_row = rows++;
       L.dst_len_row = cur_n[dt];
       const int64_t kk = std::max<int64_t>(k, 1);
-      int tn = (int)std::min<int64_t>(hop_threads(), std::max<int64_t>(1, MAX_TILE_EDGES / kk));
+      const int tile_threads = a->filter_mode ? FT_THREADS : hop_threads();
+      int tn = (int)std::min<int64_t>(tile_threads, std::max<int64_t>(1, MAX_TILE_EDGES / kk));
       L.tile_nodes = tn;
       L.tile_edges = (int)(tn * kk);
       const int64_t tpb = (fcap + tn - 1) / tn;
@@ -668,6 +900,14 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     if (a->edges_stride[r] > 0)
       TCHGEO_REQUIRE(a->rows[r] && a->cols[r] && a->edge_index[r], "relation %d: NULL edge output", r);
   }
+  if (a->filter_mode) {
+    TCHGEO_REQUIRE(a->filter_mode >= 1 && a->filter_mode <= 3, "unknown filter mode");
+    TCHGEO_REQUIRE(a->timestamps && a->states && a->inputs_state, "temporal filter needs timestamps, states, inputs_state");
+    for (int t = 0; t < T; ++t) {
+      if (a->samples_stride[t] > 0) TCHGEO_REQUIRE(a->states[t] != nullptr, "states[%d] is NULL", t);
+      if (a->seeds_per_batch[t] > 0) TCHGEO_REQUIRE(a->inputs_state[t] != nullptr, "inputs_state[%d] is NULL", t);
+    }
+  }
   cudaStream_t stream = (cudaStream_t)a->stream;
   char* ws = (char*)a->workspace;
   uint32_t* ctrl = (uint32_t*)(ws + pl.off_ctrl);
@@ -684,6 +924,9 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
                                         (size_t)S * 8, (size_t)B, cudaMemcpyDeviceToDevice, stream));
     fill_i64_kernel<<<(unsigned)((B + 255) / 256), 256, 0, stream>>>(state + (size_t)pl.n_row0[t] * B, S, B);
     TCHGEO_CUDA_CHECK(cudaGetLastError());
+    if (a->filter_mode)  // states.extend_from_slice(inputs_state), neighbor_sampling.rs:185 / :273-277
+      TCHGEO_CUDA_CHECK(cudaMemcpy2DAsync(a->states[t], (size_t)a->samples_stride[t] * 8, a->inputs_state[t],
+                                          (size_t)S * 8, (size_t)S * 8, (size_t)B, cudaMemcpyDeviceToDevice, stream));
   }
   int li = 0;
   const int n_launch = (int)pl.launches.size();
@@ -731,11 +974,28 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.batch_base = a->batch_base;
     const int64_t grid = (int64_t)L.tiles_per_batch * B;
     const size_t smem = (size_t)L.tile_edges * 5 + 16;
+    hp.filter_mode = a->filter_mode;
+    hp.filter_forward = a->filter_forward;
+    hp.win_lo = a->filter_window_lo;
+    hp.win_hi = a->filter_window_hi;
+    hp.timestamps = a->filter_mode ? a->timestamps[r] : nullptr;
+    hp.dst_states = a->filter_mode ? a->states[dtt] : nullptr;
+    hp.src_states = a->filter_mode ? a->states[stt] : nullptr;
     cudaError_t e;
-    switch (a->sampler_kind) {
-      case TCHGEO_SAMPLER_UNIFORM: e = launch_hop<TCHGEO_SAMPLER_UNIFORM>(hp, grid, smem, stream); break;
-      case TCHGEO_SAMPLER_UNIFORM_REPLACE: e = launch_hop<TCHGEO_SAMPLER_UNIFORM_REPLACE>(hp, grid, smem, stream); break;
-      default: e = launch_hop<TCHGEO_SAMPLER_WEIGHTED>(hp, grid, smem, stream); break;
+    if (a->filter_mode) {
+      const size_t fsmem = (size_t)L.tile_edges * 4 + 16;
+      switch (a->sampler_kind) {
+        case TCHGEO_SAMPLER_UNIFORM: hop_filtered_kernel<TCHGEO_SAMPLER_UNIFORM><<<(unsigned)grid, FT_THREADS, fsmem, stream>>>(hp); break;
+        case TCHGEO_SAMPLER_UNIFORM_REPLACE: hop_filtered_kernel<TCHGEO_SAMPLER_UNIFORM_REPLACE><<<(unsigned)grid, FT_THREADS, fsmem, stream>>>(hp); break;
+        default: hop_filtered_kernel<TCHGEO_SAMPLER_WEIGHTED><<<(unsigned)grid, FT_THREADS, fsmem, stream>>>(hp); break;
+      }
+      e = cudaGetLastError();
+    } else {
+      switch (a->sampler_kind) {
+        case TCHGEO_SAMPLER_UNIFORM: e = launch_hop<TCHGEO_SAMPLER_UNIFORM>(hp, grid, smem, stream); break;
+        case TCHGEO_SAMPLER_UNIFORM_REPLACE: e = launch_hop<TCHGEO_SAMPLER_UNIFORM_REPLACE>(hp, grid, smem, stream); break;
+        default: e = launch_hop<TCHGEO_SAMPLER_WEIGHTED>(hp, grid, smem, stream); break;
+      }
     }
     TCHGEO_CUDA_CHECK(e);
     ++li;

@@ -22,6 +22,8 @@ pub struct tchgeo_sampling_args {
     pub rows: *const *mut i64, pub cols: *const *mut i64, pub edge_index: *const *mut i64,
     pub edges_stride: *const i64,
     pub samples_len: *mut i64, pub edges_len: *mut i64, pub layer_offsets: *mut i64,
+    pub filter_mode: i32, pub filter_forward: i32, pub filter_window_lo: i64, pub filter_window_hi: i64,
+    pub timestamps: *const *const i64, pub inputs_state: *const *const i64, pub states: *const *mut i64,
     pub workspace: *mut c_void, pub workspace_bytes: usize, pub stream: *mut c_void,
 }
 

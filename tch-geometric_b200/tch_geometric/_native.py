@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libtchgeo_cuda.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_INDEX, ERR_REFERENCE_PANIC, ERR_INTERNAL = range(7)
 SAMPLER_UNIFORM, SAMPLER_UNIFORM_REPLACE, SAMPLER_WEIGHTED = 0, 1, 2
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_i64, c_i32, c_u64, c_u32, c_vp, c_sz = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32,
                                           ctypes.c_void_p, ctypes.c_size_t)
@@ -30,6 +30,8 @@ class SamplingArgs(ctypes.Structure):
         ("samples", c_vp), ("samples_stride", c_vp),
         ("rows", c_vp), ("cols", c_vp), ("edge_index", c_vp), ("edges_stride", c_vp),
         ("samples_len", c_vp), ("edges_len", c_vp), ("layer_offsets", c_vp),
+        ("filter_mode", c_i32), ("filter_forward", c_i32), ("filter_window_lo", c_i64), ("filter_window_hi", c_i64),
+        ("timestamps", c_vp), ("inputs_state", c_vp), ("states", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_sz), ("stream", c_vp),
     ]
 

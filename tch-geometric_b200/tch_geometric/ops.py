@@ -156,10 +156,25 @@ def _extract_sampler(sampler, hetero: bool):
     raise TypeError("sampler must have a `with_replacement: bool` or a `weights` attribute")
 
 
-def _reject_filter(filter):
-    if filter is not None:
-        raise NotImplementedError(
-            "TemporalFilter (python.rs:137-168) is not on the B200 path yet (SURVEY.md §8 row F1)")
+def _extract_filter(filter, hetero: bool):
+    """FilterType::TemporalFilter((TemporalFilter{window, timestamps, forward, mode}, inputs_state)), python.rs:137-168.
+    -> None | (abi_mode, forward, (lo, hi), timestamps, inputs_state).  As in python.rs:219-249 a mode outside
+    {STATIC, RELATIVE, DYNAMIC} falls through to the IdentityFilter arm."""
+    if filter is None:
+        return None
+    try:
+        ft, inputs_state = filter
+        window, timestamps = ft.window, ft.timestamps
+        forward, mode = bool(ft.forward), int(ft.mode)
+        lo, hi = int(window[0]), int(window[1])
+    except (TypeError, ValueError, AttributeError) as exc:
+        raise TypeError("filter must be a (TemporalEdgeFilter, inputs_state) pair") from exc
+    for name, v in (("timestamps", timestamps), ("inputs_state", inputs_state)):
+        if hetero != isinstance(v, dict):
+            raise ValueError("Unknown error: data must be %s" % ("heterogenous" if hetero else "homogenous"))
+    if mode not in (0, 1, 2):
+        return None
+    return mode + 1, forward, (lo, hi), timestamps, inputs_state
 
 
 # ---------------------------------------------------------------------------------------------
@@ -200,7 +215,8 @@ class _Call:
     """Owns the host arrays, output tensors and workspace of one tchgeo_neighbor_sampling call."""
 
     def __init__(self, device, rel_src, rel_dst, col_ptrs, row_indices, weights, fanouts, rel_active, inputs, seeds,
-                 num_batches, num_hops, sampler_kind, seed, batch_base=0):
+                 num_batches, num_hops, sampler_kind, seed, batch_base=0, filt=None):
+        """filt: None | (abi_mode, forward, (lo, hi), [timestamps per relation], [inputs_state per node type])"""
         T, R, H, B = len(seeds), len(rel_src), num_hops, num_batches
         self.T, self.R, self.H, self.B, self.device = T, R, H, B, device
         a = N.SamplingArgs()
@@ -249,6 +265,14 @@ class _Call:
         a.cols = ptr_table(self.cols).ctypes.data
         a.edge_index = ptr_table(self.eidx).ctypes.data
         a.edges_stride = cap_e.ctypes.data
+        self.states = None
+        if filt is not None:
+            a.filter_mode, a.filter_forward = int(filt[0]), int(filt[1])
+            a.filter_window_lo, a.filter_window_hi = filt[2]
+            a.timestamps = ptr_table(filt[3]).ctypes.data
+            a.inputs_state = ptr_table(filt[4]).ctypes.data
+            self.states = [torch.empty((B, int(c)), **i64) for c in cap_n]
+            a.states = ptr_table(self.states).ctypes.data
         self.samples_len = np.zeros((B, T), dtype=np.int64)
         self.edges_len = np.zeros((B, R), dtype=np.int64)
         self.layer_offsets = np.zeros((B, R, max(H, 1), 3), dtype=np.int64)
@@ -306,7 +330,7 @@ def neighbor_sampling_homogenous(
 
 
 def _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, filter, batched):
-    _reject_filter(filter)
+    flt = _extract_filter(filter, hetero=False)
     _check(col_ptrs, torch.int64, "col_ptrs")
     dev = col_ptrs.device
     _check(row_indices, torch.int64, "row_indices", dev)
@@ -323,8 +347,17 @@ def _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, filt
     fan = [int(k) for k in num_neighbors]
     if any(k < 0 for k in fan):
         raise OverflowError("can't convert negative int to unsigned")  # Vec<usize> extraction
+    filt = None
+    if flt is not None:
+        mode, forward, window, ts, st = flt
+        _check(ts, torch.int64, "timestamps", dev)
+        st = _as_seed_matrix(st, dev, "inputs_state")
+        if st.numel() != inputs.numel():
+            # the reference indexes states[i] for every frontier index and panics when it is short (quirk Q10)
+            raise N.ReferencePanic("inputs_state must have one entry per input")
+        filt = (mode, forward, window, [ts], [st])
     return _Call(dev, [0], [0], [col_ptrs], [row_indices], [w] if w is not None else None, fan, [1], [inputs], [S],
-                 max(B, 1), len(fan), kind, 0)
+                 max(B, 1), len(fan), kind, 0, filt=filt)
 
 
 class SampledBatches:
@@ -388,7 +421,7 @@ def _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, inputs, nu
                        filter, num_batches=None):
     """Argument checking + plan for the heterogeneous sampler.  inputs[t]: [S_t] (single call) or
     [B, S_t] when num_batches is given."""
-    _reject_filter(filter)
+    flt = _extract_filter(filter, hetero=True)
     node_types = list(node_types)
     edge_types = [tuple(e) for e in edge_types]
     tix = {t: i for i, t in enumerate(node_types)}
@@ -437,9 +470,25 @@ def _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, inputs, nu
         else:
             inp.append(None)
             seeds.append(0)
+    filt = None
+    if flt is not None:
+        mode, forward, window, tsd, std = flt
+        ts = [(_check(tsd[r], torch.int64, f"timestamps[{r}]", dev) if r in tsd else None) for r in rels]
+        st = []
+        for t, x in zip(node_types, inp):
+            if x is None:
+                st.append(None)
+                continue
+            if t not in std:
+                raise N.ReferencePanic(f"inputs_state[{t}] is missing")  # states[node_type] stays empty -> index panic
+            y = _as_seed_matrix(std[t], dev, f"inputs_state[{t}]").reshape(B, -1)
+            if y.shape != x.shape:
+                raise N.ReferencePanic(f"inputs_state[{t}] must have one entry per input")
+            st.append(y)
+        filt = (mode, forward, window, ts, st)
     call = _Call(dev, [tix[e[0]] for e in edge_types], [tix[e[2]] for e in edge_types], cp, ri,
                  ws if kind == N.SAMPLER_WEIGHTED else None, fan[:, :num_hops].reshape(-1) if num_hops > 0 else [],
-                 active, inp, seeds, B, num_hops, kind, 0)
+                 active, inp, seeds, B, num_hops, kind, 0, filt=filt)
     call.meta = (node_types, rels, [r in col_ptrs for r in rels], active, num_hops)
     call.seed_inputs = inp
     return call

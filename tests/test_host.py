@@ -104,11 +104,21 @@ def test_capacity_bounds_the_oracle(karate):
             assert len(s) <= cn[0] and len(r) <= ce[0]
 
 
-def test_filter_argument_is_refused_loudly():
+def test_filter_extraction():
+    """python.rs:137-168 + the dispatch at :219-249 (unknown modes fall through to IdentityFilter)."""
     p = torch.zeros(3, dtype=torch.int64)
-    f = (thg.TemporalEdgeFilter((0, 2), p), p)
-    with pytest.raises(NotImplementedError):
-        thg.neighbor_sampling_homogenous(p, p, p, [2], None, f)
+    assert ops._extract_filter(None, False) is None
+    f = ops._extract_filter((thg.TemporalEdgeFilter((0, 2), p), p), False)
+    assert f[0] == 1 and f[1] is False and f[2] == (0, 2)
+    f = ops._extract_filter((thg.TemporalEdgeFilter((-1, 5), p, forward=True, mode=thg.TEMPORAL_SAMPLE_DYNAMIC), p), False)
+    assert f[0] == 3 and f[1] is True and f[2] == (-1, 5)
+    assert ops._extract_filter((thg.TemporalEdgeFilter((0, 2), p, mode=7), p), False) is None
+    with pytest.raises(ValueError, match="homogenous"):
+        ops._extract_filter((thg.TemporalEdgeFilter((0, 2), {"a": p}), p), False)
+    with pytest.raises(ValueError, match="heterogenous"):
+        ops._extract_filter((thg.TemporalEdgeFilter((0, 2), {"a": p}), p), True)
+    with pytest.raises(TypeError):
+        ops._extract_filter(thg.TemporalEdgeFilter((0, 2), p), False)
 
 
 def test_shard_range_partitions_exactly():

@@ -332,3 +332,57 @@ def test_cpu_baseline_driver_matches_single_calls(karate_csc):
         ns += len(s)
         ne += len(r)
     assert (ts, te) == (ns, ne)
+
+
+# ---------------------------------------------------------------------------------------------
+# temporal filter (neighbor_sampling.rs:36-77), the reference's test :498-570
+# ---------------------------------------------------------------------------------------------
+def _paths(rows, cols, num_inputs):
+    """root index and edge list of every sampled node (tree layout: cols[e] is the parent of rows[e])."""
+    parent = {int(j): (int(i), e) for e, (j, i) in enumerate(zip(rows, cols))}
+    out = {}
+    for j in parent:
+        edges, cur = [], j
+        while cur >= num_inputs:
+            cur, e = parent[cur]
+            edges.append(e)
+        out[j] = (cur, edges)
+    return out
+
+
+@pytest.mark.parametrize("mode", [O.RNG_XOSHIRO, O.RNG_COUNTER])
+def test_temporal_filter_windows(karate_csc, mode):
+    ptrs, idx, _ = karate_csc
+    ts = np.random.default_rng(0).integers(0, 4, idx.size)          # edge timestamps in [0, 4), :504
+    inputs, t0, fan = np.array([0, 1, 4, 5]), np.array([0, 1, 2, 3]), [4, 3]
+    # static window 0..=2 (:512-536): every edge on every path has a timestamp inside the window
+    flt = dict(mode=O.TEMPORAL_STATIC, forward=False, window=(0, 2), timestamps=ts, inputs_state=t0)
+    s, r, c, e, lo = O.neighbor_sampling_homogenous(ptrs, idx, inputs, fan, filter=flt, rng_mode=mode, seed=1)
+    validate_neighbor_samples(ptrs, idx, r, c, s, s, lo, fan)
+    assert len(e) > 0 and ((ts[e] >= 0) & (ts[e] <= 2)).all()
+    # relative backward window (:538-569): start_t - 2 <= t <= start_t along the whole path
+    flt = dict(mode=O.TEMPORAL_RELATIVE, forward=False, window=(0, 2), timestamps=ts, inputs_state=t0)
+    s, r, c, e, lo = O.neighbor_sampling_homogenous(ptrs, idx, inputs, fan, filter=flt, rng_mode=mode, seed=2)
+    validate_neighbor_samples(ptrs, idx, r, c, s, s, lo, fan)
+    for j, (root, edges) in _paths(r, c, len(inputs)).items():
+        for ed in edges:
+            assert t0[root] - 2 <= ts[e[ed]] <= t0[root]
+    # dynamic forward: each hop is relative to the timestamp of the edge that reached the node
+    flt = dict(mode=O.TEMPORAL_DYNAMIC, forward=True, window=(0, 1), timestamps=ts, inputs_state=t0)
+    s, r, c, e, lo = O.neighbor_sampling_homogenous(ptrs, idx, inputs, fan, filter=flt, rng_mode=mode, seed=3)
+    hop1 = lo[1][1]
+    for ed in range(len(e)):
+        prev_t = t0[c[ed]] if ed < hop1 else ts[e[c[ed] - len(inputs)]]
+        assert 0 <= ts[e[ed]] - prev_t <= 1
+
+
+def test_temporal_filter_counts_only_passing_edges(karate_csc):
+    """fully filtered neighbourhoods yield nothing (quirk Q4); with replacement picks only passing edges."""
+    ptrs, idx, _ = karate_csc
+    ts = np.arange(idx.size) % 5
+    flt = dict(mode=O.TEMPORAL_STATIC, forward=False, window=(9, 9), timestamps=ts, inputs_state=np.zeros(3, dtype=np.int64))
+    s, r, c, e, lo = O.neighbor_sampling_homogenous(ptrs, idx, [0, 1, 2], [3, 3], filter=flt)
+    assert len(r) == 0 and lo == [(3, 0, 3), (3, 0, 3)]
+    flt["window"] = (2, 2)
+    s, r, c, e, lo = O.neighbor_sampling_homogenous(ptrs, idx, [0, 1, 2], [6], sampler=("uniform", True), filter=flt)
+    assert len(e) == 18 and (ts[e] == 2).all()
