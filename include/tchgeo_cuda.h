@@ -227,6 +227,14 @@ TCHGEO_API tchgeo_status tchgeo_random_walk(const int64_t* row_ptrs /*DEVICE [nu
                                  int64_t* stats /*DEVICE [2] scratch: rejection-loop attempts, error flags*/,
                                  int64_t* attempts_out /*HOST [1] or NULL*/, tchgeo_stream stream);
 
+/* Same, with an optional int32 replica of col_indices (tchgeo_compress_indices): the neighbour gathers
+ * and the has_edge binary searches then read it instead (half the DRAM lines per adjacency). */
+TCHGEO_API tchgeo_status tchgeo_random_walk_ex(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,
+                                               const int32_t* col_indices32 /*DEVICE or NULL*/, const int64_t* start,
+                                               int64_t num_walks, int64_t walk_length, float p, float q, uint64_t seed,
+                                               int64_t walker_base, int64_t* walks, int64_t* stats,
+                                               int64_t* attempts_out, tchgeo_stream stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* Dedup + insertion-order relabel of one sampled tree (additive stage).                          */
 /*   nodes      = seeds (duplicates kept) ++ every other id at first appearance                    */

@@ -77,6 +77,7 @@ struct HopParams {
   uint32_t key0, key1;
   uint32_t rel;
   uint32_t batch_base;
+  int32_t static_order;         // EXPERIMENT ONLY (TCHGEO_EXPERIMENT_STATIC_ORDER=1): tile = blockIdx, no ticket
   // temporal filter (src/algo/neighbor_sampling.rs:36-77); filter_mode 0 = none
   int32_t filter_mode;          // 1 static, 2 relative, 3 dynamic
   int32_t filter_forward;
@@ -135,6 +136,22 @@ __device__ __forceinline__ void reservoir_block(const Philox4& r, uint32_t step0
   }
 }
 
+// Same as reservoir_block, but straight-line: `slots_sa` is a 32-bit shared-state-space address and the
+// update is a predicated red.shared.max (no branch, no generic->shared address conversion per hit).
+__device__ __forceinline__ void reservoir_block_sa(const Philox4& r, uint32_t step0, uint32_t deg, uint32_t k,
+                                                   uint32_t slots_sa) {
+#pragma unroll
+  for (uint32_t u = 0; u < 4; ++u) {
+    const uint32_t step = step0 + u;
+    const uint32_t j = __umulhi(pick4(r, u), step);
+    const uint32_t hit = (uint32_t)((step < deg) & (j < k));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.max.u32 [%0], %1;\n\t}"
+        ::"r"(slots_sa + 4u * j), "r"(step), "r"(hit)
+        : "memory");
+  }
+}
+
 template <int KIND, int MINB, int NT>
 __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   using BlockScan = cub::BlockScan<uint32_t, NT>;
@@ -159,7 +176,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
     // the tiles in flight at any moment belong to different batches, so the per-batch look-back
     // chains advance independently, and every tile this one waits on (same batch, smaller t) holds a
     // smaller ticket, i.e. is already running or done.
-    const uint32_t ticket = atomicAdd(p.ticket, 1u);
+    const uint32_t ticket = p.static_order ? blockIdx.x : atomicAdd(p.ticket, 1u);
     const int t = (int)(ticket / (uint32_t)p.num_batches);
     const int b = (int)(ticket - (uint32_t)t * (uint32_t)p.num_batches);
     const int64_t fb = p.fr_begin[b];
@@ -281,6 +298,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   if (KIND == TCHGEO_SAMPLER_UNIFORM) {
     const uint32_t tag = TAG_RESERVOIR | (p.rel << 8);
     const uint32_t key0 = p.key0, key1 = p.key1;
+    const uint32_t slot_sa = (uint32_t)__cvta_generic_to_shared(s_slot);
     // Light nodes: (node, 4-step block) work items, grabbed 128 at a time so that warp 0 joins in
     // after its look-back.  Block c of node n covers steps k+4c .. k+4c+3 of the serial reservoir.
     while (true) {
@@ -294,7 +312,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
         const NodeRec rec = s_rec[n];
         const uint32_t c = q - rec.choff;
         const Philox4 r = philox4x32_10(pos0 + n, c, batch, tag, key0, key1);
-        reservoir_block(r, k + 4u * c, rec.deg, k, s_slot + rec.off);
+        reservoir_block_sa(r, k + 4u * c, rec.deg, k, slot_sa + 4u * rec.off);
       }
     }
     // Heavy nodes (deg > k + 4*LIGHT_BLOCKS_MAX): one warp strides over one node's blocks.
@@ -305,7 +323,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
       const uint32_t nb = (rec.deg - k + 3u) >> 2;
       for (uint32_t c = lane; c < nb; c += 32) {
         const Philox4 r = philox4x32_10(pos0 + n, c, batch, tag, key0, key1);
-        reservoir_block(r, k + 4u * c, rec.deg, k, s_slot + rec.off);
+        reservoir_block_sa(r, k + 4u * c, rec.deg, k, slot_sa + 4u * rec.off);
       }
     }
   } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
@@ -974,6 +992,7 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.batch_base = a->batch_base;
     const int64_t grid = (int64_t)L.tiles_per_batch * B;
     const size_t smem = (size_t)L.tile_edges * 5 + 16;
+    hp.static_order = env_int("TCHGEO_EXPERIMENT_STATIC_ORDER", 0);
     hp.filter_mode = a->filter_mode;
     hp.filter_forward = a->filter_forward;
     hp.win_lo = a->filter_window_lo;

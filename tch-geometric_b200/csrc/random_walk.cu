@@ -10,21 +10,28 @@
 //     (r < min(prob1, prob2) accepts, r >= max(prob1, prob2) rejects, whatever has_edge says);
 //   * prev == -1 on the first step never matches (quirk Q8), no search;
 //   * the accepted candidate's (row_ptrs[next], row_ptrs[next+1]) pair is carried into the next step.
-// Output rows are [walk_length+1] i64 (648 B for length 80): each warp stages 32 walkers x 16 steps
-// in shared memory and writes 128-byte runs instead of 8-byte strided stores; dead walkers and the
+// Output rows are [walk_length+1] i64 (648 B for length 80): each warp stages 32 walkers x 8 steps
+// in shared memory and writes 64-byte runs instead of 8-byte strided stores; dead walkers and the
 // -1 padding are written by the same path, so no separate fill(-1) pass over the output is needed.
+// Memory behaviour (measured, products-shaped graph): the kernel lives on L1/L2 reuse of a walker's
+// current adjacency (the has_edge probes and the next step's gather hit the same lines), so MORE
+// resident walkers or a smaller L1 (bigger staging tile) make it slower: 4-5 CTAs/SM and an 8-step
+// staging tile are the measured optimum; row_ptrs is kept in L2 (evict_last) and the adjacency reads use
+// the optional int32 replica (100 ms -> 63 ms for 24.5 M walkers x 80 steps).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace tchgeo {
 namespace {
 
 constexpr int WALK_THREADS = 256;
-constexpr int WALK_CHUNK = 16;
 constexpr uint32_t WALK_MAX_ATTEMPTS = 1u << 25;
 
 struct WalkParams {
   const int64_t* row_ptrs;
   const int64_t* col_indices;
+  const int32_t* col_indices32;  // optional int32 replica (half the DRAM lines per adjacency)
   const int64_t* start;
   int64_t* walks;
   unsigned long long* attempts;
@@ -37,18 +44,25 @@ struct WalkParams {
   uint32_t key0, key1;
 };
 
-__device__ __forceinline__ bool has_edge_dev(const int64_t* __restrict__ col, int64_t lo, int64_t hi, int64_t y) {
+template <bool I32>
+__device__ __forceinline__ int64_t load_col(const WalkParams& p, int64_t pos) {
+  return I32 ? (int64_t)ld_gather64_i32(p.col_indices32 + pos) : ld_gather64_i64(p.col_indices + pos);
+}
+
+template <bool I32>
+__device__ __forceinline__ bool has_edge_dev(const WalkParams& p, int64_t lo, int64_t hi, int64_t y) {
   while (lo < hi) {  // graph.rs:80-83
     const int64_t mid = lo + ((hi - lo) >> 1);
-    const int64_t v = ld_gather64_i64(col + mid);
+    const int64_t v = load_col<I32>(p, mid);
     if (v == y) return true;
     if (v < y) lo = mid + 1; else hi = mid;
   }
   return false;
 }
 
-__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) {
-  __shared__ int64_t tile[WALK_THREADS / 32][32][WALK_CHUNK + 1];
+template <bool I32, int MINB, int CH>
+__global__ void __launch_bounds__(WALK_THREADS, MINB) walk_kernel(const WalkParams p) {
+  __shared__ int64_t tile[WALK_THREADS / 32][32][CH + 1];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int64_t i = (int64_t)blockIdx.x * WALK_THREADS + threadIdx.x;
@@ -57,6 +71,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) 
   const bool active = i < p.num_walks;
   const uint64_t walker = (uint64_t)(p.walker_base + i);
   const float pmin = fminf(p.prob1, p.prob2), pmax = fmaxf(p.prob1, p.prob2);
+  const uint64_t keep = l2_policy_evict_last();  // row_ptrs (8 B/node) should stay in the 126 MB L2
 
   int64_t cur = active ? p.start[i] : -1;
   int64_t prev = -1;
@@ -67,14 +82,14 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) 
       atomicOr(p.err, DEV_ERR_INDEX);
       alive = false;
     } else {
-      nb = __ldg(p.row_ptrs + cur);
-      ne = __ldg(p.row_ptrs + cur + 1);
+      nb = ld_gather64_keep_i64(p.row_ptrs + cur, keep);
+      ne = ld_gather64_keep_i64(p.row_ptrs + cur + 1, keep);
     }
   }
   unsigned long long my_attempts = 0;
 
-  for (int64_t c0 = 0; c0 < L; c0 += WALK_CHUNK) {
-    const int nc = (int)min((int64_t)WALK_CHUNK, L - c0);
+  for (int64_t c0 = 0; c0 < L; c0 += CH) {
+    const int nc = (int)min((int64_t)CH, L - c0);
     for (int cc = 0; cc < nc; ++cc) {
       const int64_t colidx = c0 + cc;
       int64_t out;
@@ -95,7 +110,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) 
                 r4 = philox4x32_10((uint32_t)walker, (uint32_t)(walker >> 32), l, TAG_WALK | ((a >> 1) << 8), p.key0, p.key1);
               const uint32_t ri = (a & 1u) ? r4.z : r4.x;
               const uint32_t rf = (a & 1u) ? r4.w : r4.y;
-              next = ld_gather64_i64(p.col_indices + nb + (int64_t)__umulhi(ri, (uint32_t)d));  // :53
+              next = load_col<I32>(p, nb + (int64_t)__umulhi(ri, (uint32_t)d));  // :53
               const float r = (float)(rf >> 8) * (1.0f / 16777216.0f);               // :54
               ++my_attempts;
               if (next == prev) {  // :56-58
@@ -104,10 +119,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(const WalkParams p) 
               }
               if (r >= pmax) continue;  // rejected whatever has_edge says
               if (next < 0 || next >= p.num_rows) { atomicOr(p.err, DEV_ERR_INDEX); break; }
-              nnb = ld_gather64_i64(p.row_ptrs + next);
-              nne = ld_gather64_i64(p.row_ptrs + next + 1);
+              nnb = ld_gather64_keep_i64(p.row_ptrs + next, keep);
+              nne = ld_gather64_keep_i64(p.row_ptrs + next + 1, keep);
               if (r < pmin) { accepted = true; break; }  // accepted whatever has_edge says
-              const bool he = prev >= 0 && has_edge_dev(p.col_indices, nnb, nne, prev);  // :59
+              const bool he = prev >= 0 && has_edge_dev<I32>(p, nnb, nne, prev);  // :59
               if (he ? (r < p.prob1) : (r < p.prob2)) { accepted = true; break; }        // :60-65
             }
             if (accepted) {
@@ -148,6 +163,15 @@ extern "C" tchgeo_status tchgeo_random_walk(const int64_t* row_ptrs, int64_t num
                                             const int64_t* start, int64_t num_walks, int64_t walk_length, float p,
                                             float q, uint64_t seed, int64_t walker_base, int64_t* walks,
                                             int64_t* stats, int64_t* attempts_out, tchgeo_stream stream_) {
+  return tchgeo_random_walk_ex(row_ptrs, num_rows, col_indices, nullptr, start, num_walks, walk_length, p, q, seed,
+                               walker_base, walks, stats, attempts_out, stream_);
+}
+
+extern "C" tchgeo_status tchgeo_random_walk_ex(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,
+                                               const int32_t* col_indices32, const int64_t* start, int64_t num_walks,
+                                               int64_t walk_length, float p, float q, uint64_t seed,
+                                               int64_t walker_base, int64_t* walks, int64_t* stats,
+                                               int64_t* attempts_out, tchgeo_stream stream_) {
   TCHGEO_REQUIRE(num_walks >= 0 && walk_length >= 0 && num_rows >= 0, "negative size");
   TCHGEO_REQUIRE(row_ptrs && stats && (num_walks == 0 || (start && walks)), "NULL pointer");
   TCHGEO_REQUIRE(walk_length < ((int64_t)1 << 31), "walk_length too large");
@@ -161,7 +185,8 @@ extern "C" tchgeo_status tchgeo_random_walk(const int64_t* row_ptrs, int64_t num
   if (b >= max_prob) max_prob = b;
   if (c >= max_prob) max_prob = c;
   WalkParams wp;
-  wp.row_ptrs = row_ptrs; wp.col_indices = col_indices; wp.start = start; wp.walks = walks;
+  wp.row_ptrs = row_ptrs; wp.col_indices = col_indices; wp.col_indices32 = col_indices32; wp.start = start;
+  wp.walks = walks;
   wp.attempts = (unsigned long long*)stats;
   wp.err = (uint32_t*)(stats + 1);
   wp.num_rows = num_rows; wp.num_walks = num_walks; wp.walk_length = walk_length; wp.walker_base = walker_base;
@@ -173,7 +198,30 @@ extern "C" tchgeo_status tchgeo_random_walk(const int64_t* row_ptrs, int64_t num
   TCHGEO_CUDA_CHECK(cudaMemsetAsync(stats, 0, 16, stream));
   const int64_t grid = (num_walks + WALK_THREADS - 1) / WALK_THREADS;
   TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many walkers for one launch");
-  walk_kernel<<<(unsigned)grid, WALK_THREADS, 0, stream>>>(wp);
+  static int minb = -1;  // tuning knob TCHGEO_WALK_MIN_BLOCKS = 4 | 5 | 6 (register budget 56 / 48 / 40)
+  if (minb < 0) {
+    const char* e = getenv("TCHGEO_WALK_MIN_BLOCKS");
+    const int x = e ? atoi(e) : 5;
+    minb = (x >= 4 && x <= 6) ? x : 5;
+  }
+  static int chunk = -1;  // tuning knob TCHGEO_WALK_CHUNK = 4 | 8 | 16 staged steps (shared memory vs L1 size)
+  if (chunk < 0) {
+    const char* e = getenv("TCHGEO_WALK_CHUNK");
+    const int x = e ? atoi(e) : 8;
+    chunk = (x == 4 || x == 8 || x == 16) ? x : 8;
+  }
+#define TCHGEO_LAUNCH_WALK(I32, MB)                                                                  \
+  do {                                                                                               \
+    if (chunk == 4) walk_kernel<I32, MB, 4><<<(unsigned)grid, WALK_THREADS, 0, stream>>>(wp);        \
+    else if (chunk == 16) walk_kernel<I32, MB, 16><<<(unsigned)grid, WALK_THREADS, 0, stream>>>(wp); \
+    else walk_kernel<I32, MB, 8><<<(unsigned)grid, WALK_THREADS, 0, stream>>>(wp);                   \
+  } while (0)
+  if (col_indices32) {
+    if (minb == 4) TCHGEO_LAUNCH_WALK(true, 4); else if (minb == 6) TCHGEO_LAUNCH_WALK(true, 6); else TCHGEO_LAUNCH_WALK(true, 5);
+  } else {
+    if (minb == 4) TCHGEO_LAUNCH_WALK(false, 4); else if (minb == 6) TCHGEO_LAUNCH_WALK(false, 6); else TCHGEO_LAUNCH_WALK(false, 5);
+  }
+#undef TCHGEO_LAUNCH_WALK
   TCHGEO_CUDA_CHECK(cudaGetLastError());
   int64_t h[2] = {0, 0};
   TCHGEO_CUDA_CHECK(cudaMemcpyAsync(h, stats, 16, cudaMemcpyDeviceToHost, stream));

@@ -75,6 +75,9 @@ def _load():
     lib.tchgeo_random_walk.restype = c_i32
     lib.tchgeo_random_walk.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_u64,
                                        c_i64, c_vp, c_vp, c_vp, c_vp]
+    lib.tchgeo_random_walk_ex.restype = c_i32
+    lib.tchgeo_random_walk_ex.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_float, ctypes.c_float,
+                                          c_u64, c_i64, c_vp, c_vp, c_vp, c_vp]
     lib.tchgeo_unique_relabel_workspace_bytes.restype = c_sz
     lib.tchgeo_unique_relabel_workspace_bytes.argtypes = [c_i64]
     lib.tchgeo_unique_relabel.restype = c_i32
@@ -90,7 +93,7 @@ EXPORTS = [
     "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_device_set_l2_fetch_granularity", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
     "tchgeo_coo_to_csx", "tchgeo_compress_indices", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
     "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_timed", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
-    "tchgeo_serve_requests", "tchgeo_random_walk", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
+    "tchgeo_serve_requests", "tchgeo_random_walk", "tchgeo_random_walk_ex", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
 ]
 
 

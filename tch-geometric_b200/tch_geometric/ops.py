@@ -579,10 +579,10 @@ def random_walk(row_ptrs: Tensor, col_indices: Tensor, start: Tensor, walk_lengt
     stats = torch.empty(2, dtype=torch.int64, device=dev)
     attempts = ctypes.c_int64(0)
     with torch.cuda.device(dev):
-        st = N.lib.tchgeo_random_walk(_ptr(row_ptrs), row_ptrs.numel() - 1, _ptr(col_indices), _ptr(start), S,
-                                      int(walk_length), float(p), float(q), _rng_get() if seed is None else seed,
-                                      int(walker_base), _ptr(walks), _ptr(stats), ctypes.addressof(attempts),
-                                      _stream(dev))
+        st = N.lib.tchgeo_random_walk_ex(_ptr(row_ptrs), row_ptrs.numel() - 1, _ptr(col_indices),
+                                         _ptr(_compressed_indices(col_indices)), _ptr(start), S, int(walk_length),
+                                         float(p), float(q), _rng_get() if seed is None else seed, int(walker_base),
+                                         _ptr(walks), _ptr(stats), ctypes.addressof(attempts), _stream(dev))
     N.check(st)
     return (walks, attempts.value) if return_attempts else walks
 
