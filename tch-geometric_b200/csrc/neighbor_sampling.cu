@@ -38,6 +38,7 @@ namespace tchgeo {
 namespace {
 
 constexpr int HOP_THREADS = 128;          // default threads (= max frontier nodes) per tile
+constexpr int HOP_DEFAULT_TPC = 2;          // tiles per CTA
 constexpr int HOP_DEFAULT_MIN_BLOCKS = 5;  // register budget: 5 x 256 (or 10 x 128) threads per SM, 48 regs, no spills
 constexpr int MAX_TILE_EDGES = 8192;   // shared-memory slots per tile when fanout <= 8192
 constexpr int MAX_FANOUT = 32768;      // one node per tile above 8192; bounded by shared memory
@@ -77,6 +78,7 @@ struct HopParams {
   uint32_t key0, key1;
   uint32_t rel;
   uint32_t batch_base;
+  uint32_t total_tiles;         // num_batches * tiles_per_batch
   int32_t static_order;         // EXPERIMENT ONLY (TCHGEO_EXPERIMENT_STATIC_ORDER=1): tile = blockIdx, no ticket
   // temporal filter (src/algo/neighbor_sampling.rs:36-77); filter_mode 0 = none
   int32_t filter_mode;          // 1 static, 2 relative, 3 dynamic
@@ -152,7 +154,7 @@ __device__ __forceinline__ void reservoir_block_sa(const Philox4& r, uint32_t st
   }
 }
 
-template <int KIND, int MINB, int NT>
+template <int KIND, int MINB, int NT, int TPC>
 __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   using BlockScan = cub::BlockScan<uint32_t, NT>;
   __shared__ typename BlockScan::TempStorage scan_tmp;
@@ -160,7 +162,9 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   __shared__ NodeRec s_rec[NT];
   __shared__ uint8_t s_chown[LIGHT_BLOCKS_MAX * NT];  // draw block -> owning node
   __shared__ uint8_t s_heavy[NT];
-  __shared__ TileHdr s_hdr;
+  __shared__ TileHdr s_hdr[TPC];
+  __shared__ int64_t s_pre_start[TPC][NT];  // prefetched colptr data of the CTA's TPC tiles
+  __shared__ uint32_t s_pre_deg[TPC][NT];
   __shared__ uint32_t s_work;     // dynamic work counter of the draw phase
   __shared__ uint32_t s_nheavy;
   __shared__ int64_t s_excl;
@@ -171,52 +175,86 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   const int TN = p.tile_nodes;
+  const uint32_t k = (uint32_t)p.fanout;
   if (tid == 0) {
     // Tiles are handed out in start order and TILE-MAJOR (ticket -> tile t of batch b = ticket % B):
     // the tiles in flight at any moment belong to different batches, so the per-batch look-back
     // chains advance independently, and every tile this one waits on (same batch, smaller t) holds a
-    // smaller ticket, i.e. is already running or done.
-    const uint32_t ticket = p.static_order ? blockIdx.x : atomicAdd(p.ticket, 1u);
-    const int t = (int)(ticket / (uint32_t)p.num_batches);
-    const int b = (int)(ticket - (uint32_t)t * (uint32_t)p.num_batches);
-    const int64_t fb = p.fr_begin[b];
-    int64_t fe = p.fr_end[b];
-    if (fe > p.dst_stride) fe = p.dst_stride;  // only after a capacity error upstream
-    s_hdr.fb = fb;
-    s_hdr.F = fe > fb ? fe - fb : 0;
-    s_hdr.e_in = p.e_len_in[b];
-    s_hdr.s_in = p.src_len_in[b];
-    s_hdr.b = b;
-    s_hdr.t = t;
+    // smaller ticket, i.e. belongs to a CTA that is already running (or to this CTA, earlier in its loop).
+    const uint32_t base = p.static_order ? blockIdx.x * TPC : atomicAdd(p.ticket, (uint32_t)TPC);
+#pragma unroll
+    for (int i = 0; i < TPC; ++i) {
+      const uint32_t ticket = base + i;
+      TileHdr h;
+      h.fb = 0; h.F = 0; h.e_in = 0; h.s_in = 0; h.b = 0; h.t = 1;  // t=1, F=0: an empty tile that is not "last"
+      if (ticket < p.total_tiles) {
+        h.t = (int)(ticket / (uint32_t)p.num_batches);
+        h.b = (int)(ticket - (uint32_t)h.t * (uint32_t)p.num_batches);
+        h.fb = p.fr_begin[h.b];
+        int64_t fe = p.fr_end[h.b];
+        if (fe > p.dst_stride) fe = p.dst_stride;  // only after a capacity error upstream
+        h.F = fe > h.fb ? fe - h.fb : 0;
+        h.e_in = p.e_len_in[h.b];
+        h.s_in = p.src_len_in[h.b];
+      }
+      s_hdr[i] = h;
+    }
     s_work = 0u;
     s_nheavy = 0u;
   }
   __syncthreads();
-  const int b = s_hdr.b, t = s_hdr.t;
-  const int64_t fb = s_hdr.fb, F = s_hdr.F;
-  const uint32_t k = (uint32_t)p.fanout;
+
+  // ---- A: frontier ids and colptr pairs of ALL the CTA's tiles are requested up front, so the two
+  //         dependent gathers of tile i+1 overlap the processing of tile i --------------------------
+  {
+    int64_t w[TPC], st[TPC], en[TPC];
+#pragma unroll
+    for (int i = 0; i < TPC; ++i) {
+      const TileHdr h = s_hdr[i];
+      const int64_t node0 = (int64_t)h.t * TN;
+      w[i] = -2;
+      if (node0 + tid < h.F && tid < TN) w[i] = p.dst_samples[(int64_t)h.b * p.dst_stride + h.fb + node0 + tid];
+    }
+    const uint64_t keep = l2_policy_evict_last();  // colptr (8 B/node) should live in the 126 MB L2
+#pragma unroll
+    for (int i = 0; i < TPC; ++i) {
+      st[i] = 0; en[i] = 0;
+      if (w[i] >= 0 && w[i] < p.num_cols) {
+        st[i] = ld_gather64_keep_i64(p.ptrs + w[i], keep);
+        en[i] = ld_gather64_keep_i64(p.ptrs + w[i] + 1, keep);
+      } else if (w[i] != -2) {
+        atomicOr(p.err, DEV_ERR_INDEX);  // reference: slice index panic (quirk Q10)
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < TPC; ++i) {
+      const int64_t d = en[i] - st[i];
+      uint32_t deg = 0;
+      if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
+      else deg = (uint32_t)d;
+      s_pre_start[i][tid] = st[i];
+      s_pre_deg[i][tid] = deg;
+    }
+  }
+
+#pragma unroll 1
+  for (int ti = 0; ti < TPC; ++ti) {
+  if (ti) __syncthreads();  // the shared tables of the previous tile are free again
+  const int b = s_hdr[ti].b, t = s_hdr[ti].t;
+  const int64_t fb = s_hdr[ti].fb, F = s_hdr[ti].F;
   const int64_t node0 = (int64_t)t * TN;
   const int nn = (int)max((int64_t)0, min((int64_t)TN, F - node0));
   const bool is_last = (nn > 0 && node0 + nn == F) || (F == 0 && t == 0);
-  if (nn == 0 && !is_last) return;
+  if (nn == 0 && !is_last) continue;
 
-  // ---- A: frontier ids, degree, count -----------------------------------------------------------
   uint32_t cnt = 0;
   uint32_t deg = 0;
   uint32_t nblocks = 0;  // 4-step Philox blocks this node needs (UNIFORM only)
   bool heavy = false;
   int64_t start = 0;
   if (tid < nn) {
-    const int64_t w = p.dst_samples[(int64_t)b * p.dst_stride + fb + node0 + tid];
-    if (w < 0 || w >= p.num_cols) {
-      atomicOr(p.err, DEV_ERR_INDEX);  // reference: slice index panic (quirk Q10)
-    } else {
-      const uint64_t keep = l2_policy_evict_last();  // colptr (8 B/node) should live in the 126 MB L2
-      start = ld_gather64_keep_i64(p.ptrs + w, keep);
-      const int64_t d = ld_gather64_keep_i64(p.ptrs + w + 1, keep) - start;
-      if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
-      else deg = (uint32_t)d;
-    }
+    start = s_pre_start[ti][tid];
+    deg = s_pre_deg[ti][tid];
     if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
       cnt = deg > 0 ? k : 0;  // exactly k picks, even when deg < k (quirk Q3)
     } else {
@@ -362,17 +400,21 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   __syncthreads();
 
   const int64_t excl = s_excl;
-  const int64_t e_base = s_hdr.e_in + excl;
-  const int64_t s_base = s_hdr.s_in + excl;
+  const int64_t e_base = s_hdr[ti].e_in + excl;
+  const int64_t s_base = s_hdr[ti].s_in + excl;
+  if (tid == 0) {  // reset for the CTA's next tile (ordered by the barrier at the top of the loop)
+    s_work = 0u;
+    s_nheavy = 0u;
+  }
   if (is_last && tid == 0) {
     p.e_len_out[b] = e_base + total;
     p.src_len_out[b] = s_base + total;
   }
   if (e_base + total > p.e_stride || s_base + total > p.src_stride) {
     if (tid == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
-    return;
+    continue;
   }
-  if (total == 0) return;
+  if (total == 0) continue;
 
   // ---- D: one thread per output edge ------------------------------------------------------------
   int64_t* o_s = p.src_samples + (int64_t)b * p.src_stride + s_base;
@@ -423,6 +465,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
       }
     }
   }
+  }  // tiles of this CTA
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -667,7 +710,7 @@ inline int hop_min_blocks() {
   static int v = -1;
   if (v < 0) {
     const int x = env_int("TCHGEO_HOP_MIN_BLOCKS", HOP_DEFAULT_MIN_BLOCKS);
-    v = (x >= 4 && x <= 8) ? x : HOP_DEFAULT_MIN_BLOCKS;
+    v = (x >= 4 && x <= 6) ? x : HOP_DEFAULT_MIN_BLOCKS;
   }
   return v;
 }
@@ -800,36 +843,54 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   return TCHGEO_OK;
 }
 
-template <int KIND, int MINB, int NT>
-cudaError_t launch_hop_v(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+template <int KIND, int MINB, int NT, int TPC>
+cudaError_t launch_hop_v(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
   static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(hop_kernel<KIND, MINB, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(hop_kernel<KIND, MINB, NT, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  hop_kernel<KIND, MINB, NT><<<(unsigned)grid, NT, smem, stream>>>(hp);
+  const int64_t grid = (tiles + TPC - 1) / TPC;
+  hop_kernel<KIND, MINB, NT, TPC><<<(unsigned)grid, NT, smem, stream>>>(hp);
   return cudaGetLastError();
 }
 
-template <int KIND>
-cudaError_t launch_hop(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+template <int KIND, int TPC>
+cudaError_t launch_hop_t(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
   if (hop_threads() == 128) {
     switch (hop_min_blocks()) {
-      case 5: return launch_hop_v<KIND, 10, 128>(hp, grid, smem, stream);
-      case 7: return launch_hop_v<KIND, 14, 128>(hp, grid, smem, stream);
-      default: return launch_hop_v<KIND, 12, 128>(hp, grid, smem, stream);
+      case 4: return launch_hop_v<KIND, 8, 128, TPC>(hp, tiles, smem, stream);
+      case 6: return launch_hop_v<KIND, 12, 128, TPC>(hp, tiles, smem, stream);
+      default: return launch_hop_v<KIND, 10, 128, TPC>(hp, tiles, smem, stream);
     }
   }
   switch (hop_min_blocks()) {
-    case 4: return launch_hop_v<KIND, 4, 256>(hp, grid, smem, stream);
-    case 5: return launch_hop_v<KIND, 5, 256>(hp, grid, smem, stream);
-    case 7: return launch_hop_v<KIND, 7, 256>(hp, grid, smem, stream);
-    case 8: return launch_hop_v<KIND, 8, 256>(hp, grid, smem, stream);
-    default: return launch_hop_v<KIND, 6, 256>(hp, grid, smem, stream);
+    case 4: return launch_hop_v<KIND, 4, 256, TPC>(hp, tiles, smem, stream);
+    case 6: return launch_hop_v<KIND, 6, 256, TPC>(hp, tiles, smem, stream);
+    default: return launch_hop_v<KIND, 5, 256, TPC>(hp, tiles, smem, stream);
+  }
+}
+
+// tiles per CTA (TCHGEO_HOP_TPC = 1 | 2 | 4): the colptr gathers of all of a CTA's tiles are issued up front
+inline int hop_tpc() {
+  static int v = -1;
+  if (v < 0) {
+    const int x = env_int("TCHGEO_HOP_TPC", HOP_DEFAULT_TPC);
+    v = (x == 1 || x == 2 || x == 4) ? x : HOP_DEFAULT_TPC;
+  }
+  return v;
+}
+
+template <int KIND>
+cudaError_t launch_hop(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
+  switch (hop_tpc()) {
+    case 1: return launch_hop_t<KIND, 1>(hp, tiles, smem, stream);
+    case 4: return launch_hop_t<KIND, 4>(hp, tiles, smem, stream);
+    default: return launch_hop_t<KIND, 2>(hp, tiles, smem, stream);
   }
 }
 
@@ -992,6 +1053,7 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.batch_base = a->batch_base;
     const int64_t grid = (int64_t)L.tiles_per_batch * B;
     const size_t smem = (size_t)L.tile_edges * 5 + 16;
+    hp.total_tiles = (uint32_t)((int64_t)L.tiles_per_batch * B);
     hp.static_order = env_int("TCHGEO_EXPERIMENT_STATIC_ORDER", 0);
     hp.filter_mode = a->filter_mode;
     hp.filter_forward = a->filter_forward;
