@@ -422,7 +422,7 @@ def run_walk(args):
     del ei
     torch.cuda.empty_cache()
     L, P, Q = 80, 1.0, 0.5
-    total_walkers = n * 10
+    total_walkers = n * 10 if not args.walkers else int(args.walkers)  # --walkers: profiling runs only
     w0, w1 = shard_range(total_walkers, rank, world)          # strong scaling: the job is fixed
     start = (torch.arange(w0, w1, device=device, dtype=torch.int64) // 10)  # arange(N).repeat_interleave(10)
     K, W = args.steps, args.warmup
@@ -474,9 +474,13 @@ def run_walk(args):
                          "l2_policy": "inputs larger than L2 (col_indices 495 MB, walks 15.9 GB)",
                          "parallelism": "walkers sharded over ranks, CSR replicated, no collective"},
               "attempts_per_step": att_all / max(steps_all, 1.0),
-              "roofline": {"bound": "hbm", "kernel": "walk_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+              "roofline": {"bound": "hbm", "kernel": "walk_kernel",
+                           "achieved": achieved, "peak": peak, "unit": "GB/s",
                            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                           "algorithmic_bytes_per_attempt": bytes_per_attempt},
+                           "algorithmic_bytes_per_attempt": bytes_per_attempt,
+                           "note": "algorithmic bytes follow SURVEY 8(d) (reference algorithm: neighbour gather + row_ptrs "
+                                   "pair + binary search per attempt); the kernel skips the searches the uniform already decides "
+                                   "(about half of them at p=1, q=0.5)"},
               "cpu_baseline": cpu, "e2e": None, "gpu_launches": K, "clocks": clk})
     if world > 1:
         dist.destroy_process_group()
@@ -644,6 +648,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
     ap.add_argument("--ref-batches", type=int, default=0, help="batches per step of the reference arm (0 = 8 x cores)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (0 = leave)")
+    ap.add_argument("--walkers", type=int, default=0, help="walk workload: number of walkers (0 = 10 per node)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
