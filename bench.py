@@ -47,6 +47,19 @@ FANOUTS = [15, 10, 5]
 SEEDS_PER_BATCH = 1024
 METRIC = "sampled_edges_per_sec_3hop_15_10_5"
 UNIT = "edges/s"
+SAMPLER_LABEL = {"uniform": "uniform without replacement", "replace": "uniform with replacement",
+                 "weighted": "weighted (f64 weights ~ U(0.2, 5.0) per CSC entry)"}
+
+
+def metric_name(sampler):
+    return METRIC if sampler == "uniform" else f"{METRIC}_{sampler}"
+
+
+def edge_weights(num_edges, device):
+    """w ~ U(0.2, 5.0) f64 per CSC position, mirroring the reference's own weighted test (neighbor_sampling.rs:475)."""
+    g = torch.Generator(device=device)
+    g.manual_seed(4242)
+    return torch.rand(num_edges, generator=g, dtype=torch.float64, device=device) * 4.8 + 0.2
 
 
 # Only the final JSON line may reach stdout: libraries (e.g. NCCL's version banner) print there too, so
@@ -145,12 +158,13 @@ def build_graph(device, scale):
 # ---------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm
 # ---------------------------------------------------------------------------------------------
-def cpu_sampling_rate(ptrs, idx, n, num_batches, threads, first_batch):
+def cpu_sampling_rate(ptrs, idx, n, num_batches, threads, first_batch, sampler=None):
+    """sampler: None | ("uniform", True) | ("weighted", weights) in the oracle's notation"""
     from oracle import oracle as O
     seeds = synth.seed_batches(n, num_batches, SEEDS_PER_BATCH, first_batch=first_batch)
     t0 = time.perf_counter()
-    ts, te = O.neighbor_sampling_homogenous_batches(ptrs, idx, seeds, FANOUTS, rng_mode=O.RNG_XOSHIRO, seed=first_batch,
-                                                    num_threads=threads)
+    ts, te = O.neighbor_sampling_homogenous_batches(ptrs, idx, seeds, FANOUTS, sampler=sampler, rng_mode=O.RNG_XOSHIRO,
+                                                    seed=first_batch, num_threads=threads)
     dt = time.perf_counter() - t0
     return te / dt, te, dt
 
@@ -170,21 +184,23 @@ def run_reference_arm(args):
     ptrs, idx, _ = O.to_csc(ei, n)  # the reference's own path restated (storage.rs:103-127)
     log(f"[bench] reference arm: CSC built on the CPU in {time.time() - t0:.1f}s; {cores} host threads")
     del ei
+    osampler = oracle_sampler(args.sampler, idx.size, device)
     per_step = max(cores * 8, 32) if args.ref_batches <= 0 else args.ref_batches
     for w in range(args.warmup):
-        cpu_sampling_rate(ptrs, idx, n, per_step, cores, first_batch=w * per_step)
+        cpu_sampling_rate(ptrs, idx, n, per_step, cores, first_batch=w * per_step, sampler=osampler)
     tot_e, tot_t = 0, 0.0
     for k in range(args.steps):
-        _, te, dt = cpu_sampling_rate(ptrs, idx, n, per_step, cores, first_batch=(args.warmup + k) * per_step)
+        _, te, dt = cpu_sampling_rate(ptrs, idx, n, per_step, cores, first_batch=(args.warmup + k) * per_step,
+                                      sampler=osampler)
         tot_e += te
         tot_t += dt
     value = tot_e / tot_t
     sample = f"{per_step} batches x {SEEDS_PER_BATCH} seeds per step, {args.steps} steps, {cores} threads"
     out = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "impl": "reference", "metric": metric_name(args.sampler), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / max(args.steps, 1), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-        "config": workload_config(n, int(idx.size), per_step, args.scale),
+        "config": workload_config(n, int(idx.size), per_step, args.scale, args.sampler),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -192,11 +208,19 @@ def run_reference_arm(args):
     emit(out)
 
 
-def workload_config(n, e, batches, scale):
+def oracle_sampler(name, num_edges, device):
+    if name == "replace":
+        return ("uniform", True)
+    if name == "weighted":
+        return ("weighted", edge_weights(num_edges, device).cpu().numpy())
+    return None
+
+
+def workload_config(n, e, batches, scale, sampler="uniform"):
     return {
         "workload": f"products-shaped synthetic graph (N={n}, E={e}{'' if scale == 1.0 else f', scale={scale}'}), "
                     f"neighbor_sampling_homogenous fanouts {FANOUTS}, {SEEDS_PER_BATCH} seeds/batch, "
-                    f"{batches} batches/step, uniform without replacement",
+                    f"{batches} batches/step, {SAMPLER_LABEL[sampler]}",
         "fanouts": FANOUTS, "seeds_per_batch": SEEDS_PER_BATCH, "batches_per_step": batches,
         "l2_policy": "inputs larger than L2: row_indices is 495 MB and each step streams GBs of outputs through the "
                      "126 MB L2; seeds differ every step",
@@ -249,7 +273,13 @@ def run_ours(args):
     for s in range(steps_total):
         host_seeds[s] = torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B))
     dev_seeds = host_seeds.to(device)
-    plan = thg.HomogenousSampler(ptrs, idx, B, S, FANOUTS)
+    sampler, weights = None, None
+    if args.sampler == "replace":
+        sampler = thg.UniformEdgeSampler(with_replacement=True)
+    elif args.sampler == "weighted":
+        weights = edge_weights(E, device)
+        sampler = thg.WeightedEdgeSampler(weights)
+    plan = thg.HomogenousSampler(ptrs, idx, B, S, FANOUTS, sampler=sampler)
     cap_n, cap_e = int(plan._call.cap_n[0]), int(plan._call.cap_e[0])
 
     def barrier():
@@ -268,6 +298,7 @@ def run_ours(args):
     hop_ms = np.zeros(len(FANOUTS))
     hop_F = np.zeros(len(FANOUTS))
     hop_E = np.zeros(len(FANOUTS))
+    hop_deg = np.zeros(len(FANOUTS))   # sum of the frontier nodes' degrees (weighted: the weights that are scanned)
     start.record()
     for s in range(W, W + K):
         res = plan.sample(dev_seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
@@ -280,6 +311,14 @@ def run_ours(args):
         hop_F += (lo[:, :, 0] - f_begin).sum(axis=0)
         hop_ms += res.launch_ms
     stop.record()
+    if weights is not None:  # untimed: frontier degree sums of the last step, for the weighted byte model
+        pos = torch.arange(cap_n, device=device)[None, :]
+        f_b = torch.as_tensor(f_begin, device=device)
+        f_e = torch.as_tensor(lo[:, :, 0], device=device)
+        for h in range(len(FANOUTS)):
+            ids = res.samples[(pos >= f_b[:, h:h + 1]) & (pos < f_e[:, h:h + 1])]
+            hop_deg[h] = float((ptrs[ids + 1] - ptrs[ids]).sum().item()) * K
+        del pos, ids
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     from tch_geometric.sharding import reduce_job
@@ -289,10 +328,11 @@ def run_ours(args):
 
     peak, peak_src = measured_peak_gbs()
     dom = int(np.argmax(hop_ms))
-    alg_bytes = 24.0 * hop_F + 40.0 * hop_E  # per launch, summed over the K timed launches
+    # per launch, summed over the K timed launches; the weighted sampler adds 8 B per scanned weight
+    alg_bytes = 24.0 * hop_F + 40.0 * hop_E + 8.0 * hop_deg
     achieved = alg_bytes[dom] / (hop_ms[dom] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"hop_kernel<UNIFORM> hop {dom + 1} (fanout {FANOUTS[dom]})",
+        "bound": "hbm", "kernel": f"hop_kernel<{args.sampler.upper()}> hop {dom + 1} (fanout {FANOUTS[dom]})",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes[dom] / K, "launch_ms": hop_ms[dom] / K,
@@ -302,7 +342,7 @@ def run_ours(args):
         "all_hops_GBps": alg_bytes.sum() / (hop_ms.sum() * 1e-3) / 1e9,
     }
     traffic_file = os.path.join(ROOT, "profiles", "hop3_dram_bytes_per_launch.json")
-    if os.path.exists(traffic_file):
+    if args.sampler == "uniform" and os.path.exists(traffic_file):
         try:
             roofline["traffic"] = json.load(open(traffic_file))["dram_bytes_per_launch"]
         except Exception:
@@ -318,15 +358,15 @@ def run_ours(args):
     # ---- CPU baseline on rank 0, N = 1 only -----------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = run_cpu_baseline(ptrs, idx, n, args)
+        cpu = run_cpu_baseline(ptrs, idx, n, args, oracle_sampler(args.sampler, E, device))
 
     if world > 1:
         dist.barrier()
     if rank == 0:
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "metric": metric_name(args.sampler), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "int64", "data": "synthetic", "config": workload_config(n, E, B, args.scale),
+            "dtype": "int64", "data": "synthetic", "config": workload_config(n, E, B, args.scale, args.sampler),
             "seeds_per_sec": seeds_per_s, "edges_per_step_per_gpu": edges / K,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": K * (len(FANOUTS) + 1),
@@ -390,12 +430,12 @@ def run_e2e(thg, plan, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e
                     "prefixes and layer offsets into pinned host buffers"}
 
 
-def run_cpu_baseline(ptrs, idx, n, args):
+def run_cpu_baseline(ptrs, idx, n, args, osampler=None):
     cores = os.cpu_count() or 1
     hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
-    r1, e1, t1 = cpu_sampling_rate(hp, hi, n, 8, 1, first_batch=10_000_000)
+    r1, e1, t1 = cpu_sampling_rate(hp, hi, n, 8, 1, first_batch=10_000_000, sampler=osampler)
     nb = int(max(cores * 4, min(4096, 5.0 * cores / (t1 / 8))))  # ~5 s of wall time on all cores
-    rT, eT, tT = cpu_sampling_rate(hp, hi, n, nb, cores, first_batch=10_000_100)
+    rT, eT, tT = cpu_sampling_rate(hp, hi, n, nb, cores, first_batch=10_000_100, sampler=osampler)
     log(f"[bench] cpu baseline: 1 thread {r1 / 1e6:.2f} M edges/s, {cores} threads {rT / 1e6:.2f} M edges/s")
     return {"value": rT, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{nb} batches x {SEEDS_PER_BATCH} seeds on {cores} threads ({tT:.1f} s); "
@@ -648,6 +688,8 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
     ap.add_argument("--ref-batches", type=int, default=0, help="batches per step of the reference arm (0 = 8 x cores)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (0 = leave)")
+    ap.add_argument("--sampler", default="uniform", choices=["uniform", "replace", "weighted"],
+                    help="sampling workload: neighbour sampler (uniform = the headline configuration)")
     ap.add_argument("--walkers", type=int, default=0, help="walk workload: number of walkers (0 = 10 per node)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

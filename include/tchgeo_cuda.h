@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TCHGEO_ABI_VERSION 3
+#define TCHGEO_ABI_VERSION 4
 
 #if defined(__GNUC__)
 #define TCHGEO_API __attribute__((visibility("default")))
@@ -99,6 +99,25 @@ TCHGEO_API tchgeo_status tchgeo_coo_to_csx(const int64_t* row /*DEVICE [E]*/, co
                                 tchgeo_stream stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* Per-column transforms of CSC edge data.                                       */
+/* tchgeo_csc_edge_cumsum_f64: in-place inclusive prefix sum inside every column, summed serially in  */
+/* CSC order; columns with <= 1 element are skipped and a column end beyond numel is clamped, as      */
+/* Tensor::slice does.  replaces src/data/transform.rs:36-60 (f64).                                  */
+/* tchgeo_csc_sort_edges: new_perm = perm with every column's entries reordered by ascending (or      */
+/* descending) weight; stable (ties keep CSC order; the reference's torch argsort is unstable).       */
+/* replaces src/data/transform.rs:7-34.                                                              */
+/* -------------------------------------------------------------------------------------------- */
+TCHGEO_API tchgeo_status tchgeo_csc_edge_cumsum_f64(const int64_t* col_ptrs /*DEVICE [n_cols+1]*/, int64_t n_cols,
+                                                    double* row_data /*DEVICE [numel], in place*/, int64_t numel,
+                                                    int32_t* scratch /*DEVICE [1]*/, tchgeo_stream stream);
+TCHGEO_API size_t tchgeo_csc_sort_edges_workspace_bytes(int64_t numel, int64_t n_cols);
+TCHGEO_API tchgeo_status tchgeo_csc_sort_edges(const int64_t* col_ptrs /*DEVICE [n_cols+1]*/, int64_t n_cols,
+                                               const int64_t* perm /*DEVICE [numel]*/,
+                                               const double* row_weights /*DEVICE [numel]*/, int64_t numel,
+                                               int32_t descending, int64_t* new_perm /*DEVICE [numel]*/,
+                                               void* workspace /*DEVICE*/, size_t workspace_bytes, tchgeo_stream stream);
+
+/* -------------------------------------------------------------------------------------------- */
 /* Multi-hop neighbor sampling.  One call samples `num_batches` independent seed batches (the     */
 /* reference call is num_batches == 1); batch b's outputs are exactly what the reference returns   */
 /* for inputs[b] and live at offset b*stride of each output buffer.                                */
@@ -120,6 +139,11 @@ typedef struct tchgeo_sampling_args {
                                        tchgeo_compress_indices.  HBM layout optimisation only: the
                                        random gathers then touch half as many DRAM lines; outputs are
                                        unchanged (i64).                                            */
+  const double* const* weights_cumsum; /* optional (table or entries may be NULL): HOST [R] of DEVICE [nnz_r]
+                                       f64 = tchgeo_csc_edge_cumsum_f64 of weights[r] (serial per-column prefix
+                                       sums = the w_sum sequence of sampling.rs:37-48).  The weighted kernel then
+                                       reads w_sum instead of scanning the weights, which also makes weighted
+                                       output bit-exact for arbitrary weights.  Ignored with a temporal filter. */
   const int64_t* fanouts;           /* HOST [R*H] num_neighbors[r][hop]                            */
   const uint8_t* rel_active;        /* HOST [R] 0 = relation absent from num_neighbors, or NULL    */
   /* ---- seeds ---- */

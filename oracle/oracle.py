@@ -116,9 +116,26 @@ def to_csr(row_col, size):
 
 
 def csc_edge_cumsum(col_ptrs, row_data):
+    """transform.rs:36-60 (returns the result instead of mutating in place)"""
     col_ptrs = _i64(col_ptrs)
     out = np.ascontiguousarray(np.asarray(row_data, dtype=np.float64)).copy()
-    _check(lib().orc_csc_edge_cumsum_f64(_p(col_ptrs), ctypes.c_int64(col_ptrs.size - 1), _p(out, ctypes.c_double)))
+    _check(lib().orc_csc_edge_cumsum_f64(_p(col_ptrs), ctypes.c_int64(col_ptrs.size - 1), _p(out, ctypes.c_double),
+                                         ctypes.c_int64(out.size)))
+    return out
+
+
+def csc_sort_edges(col_ptrs, perm, row_weights, descending=False):
+    """transform.rs:7-34: per column, new_perm[col] = perm[col][argsort(weights[col], descending)].  torch's argsort
+    is unstable (ties unspecified); ties are resolved by CSC position here, as on the GPU."""
+    col_ptrs, perm = _i64(col_ptrs), _i64(perm)
+    w = np.asarray(row_weights, dtype=np.float64)
+    out = perm.copy()  # :15
+    for s, e in zip(col_ptrs[:-1], col_ptrs[1:]):
+        if e - s <= 1:  # :22-24
+            continue
+        e = min(int(e), perm.size)  # Tensor::slice clamps
+        keys = -w[s:e] if descending else w[s:e]
+        out[s:e] = perm[s:e][np.argsort(keys, kind="stable")]
     return out
 
 

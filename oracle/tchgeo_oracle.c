@@ -245,11 +245,14 @@ int orc_to_csx(const int64_t* row, const int64_t* col, int64_t E, int64_t size0,
   return ORC_OK;
 }
 
-/* F2 (next row): csc_edge_cumsum, src/data/transform.rs:36-60 (f64 instantiation) */
-int orc_csc_edge_cumsum_f64(const int64_t* col_ptrs, int64_t n_cols, double* row_data) {
+/* F2: csc_edge_cumsum, src/data/transform.rs:36-60 (f64 instantiation).  Tensor::slice clamps the column end to
+ * numel (the reference's own KAT, transform.rs:85-97, ends with a pointer past the data). */
+int orc_csc_edge_cumsum_f64(const int64_t* col_ptrs, int64_t n_cols, double* row_data, int64_t numel) {
   for (int64_t c = 0; c < n_cols; ++c) {
     int64_t s = col_ptrs[c], e = col_ptrs[c + 1];
     if (e - s <= 1) continue; /* transform.rs:46-48 */
+    if (s < 0) return ORC_ERR_PANIC;
+    if (e > numel) e = numel;
     double acc = 0.0;
     for (int64_t p = s; p < e; ++p) { acc = acc + row_data[p]; row_data[p] = acc; }
   }

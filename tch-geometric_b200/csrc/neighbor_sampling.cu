@@ -52,6 +52,7 @@ struct HopParams {
   const int64_t* indices;
   const int32_t* indices32;  // optional compressed replica of `indices`
   const double* weights;
+  const double* wcum;        // optional serial per-column prefix sums of `weights` (csc_edge_cumsum)
   int64_t num_cols;
   const int64_t* dst_samples;  // frontier ids live here (may alias src_samples)
   int64_t dst_stride;
@@ -366,6 +367,31 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
     }
   } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
     const int warp = tid >> 5;
+    const uint32_t wtag = TAG_WEIGHTED | (p.rel << 8);
+    if (p.wcum) {
+      // w_sum at every step comes from the precomputed serial prefix sums: no scan, and the comparison below
+      // sees exactly the reference's f64 values whatever the weights are (sampling.rs:47-52).
+      for (int n = warp; n < nn; n += NT / 32) {
+        const NodeRec rec = s_rec[n];
+        const uint32_t dn = rec.deg;
+        if (dn <= k) continue;
+        const double* wp = p.weights + s_start[n];
+        const double* cp = p.wcum + s_start[n];
+        uint32_t* slots = s_slot + rec.off;
+        for (uint32_t item = k + lane; item < dn; item += 32) {
+          const double w = __ldg(wp + item);
+          const double w_sum = dn > 1 ? __ldg(cp + item) : w;
+          if (!(w_sum > 0.0)) {
+            atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
+          } else {
+            const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, item, batch, wtag, p.key0, p.key1);
+            const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
+            const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
+            if (__dmul_rn(u, w_sum) < w) atomicMax(slots + __umulhi(r.z, k), item);  // :49-52
+          }
+        }
+      }
+    } else {
     for (int n = warp; n < nn; n += NT / 32) {
       const NodeRec rec = s_rec[n];
       const uint32_t dn = rec.deg;
@@ -387,7 +413,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
           if (!(w_sum > 0.0)) {
             atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
           } else {
-            const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, item, batch, TAG_WEIGHTED | (p.rel << 8), p.key0, p.key1);
+            const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, item, batch, wtag, p.key0, p.key1);
             const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
             const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
             if (__dmul_rn(u, w_sum) < w) atomicMax(slots + __umulhi(r.z, k), item);  // :49-52
@@ -395,6 +421,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
         }
         carry = __shfl_sync(0xffffffffu, w_sum, 31);
       }
+    }
     }
   }
   __syncthreads();
@@ -1024,6 +1051,7 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.indices = a->row_indices[r];
     hp.indices32 = a->row_indices32 ? a->row_indices32[r] : nullptr;
     hp.weights = (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED) ? a->weights[r] : nullptr;
+    hp.wcum = (hp.weights && a->weights_cumsum) ? a->weights_cumsum[r] : nullptr;
     hp.num_cols = a->num_cols[r];
     hp.dst_samples = a->samples[dtt];
     hp.dst_stride = a->samples_stride[dtt];

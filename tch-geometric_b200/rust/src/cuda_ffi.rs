@@ -15,6 +15,7 @@ pub struct tchgeo_sampling_args {
     pub rel_src: *const i32, pub rel_dst: *const i32,
     pub col_ptrs: *const *const i64, pub num_cols: *const i64, pub row_indices: *const *const i64,
     pub weights: *const *const f64, pub row_indices32: *const *const i32,
+    pub weights_cumsum: *const *const f64,
     pub fanouts: *const i64, pub rel_active: *const u8,
     pub num_batches: i64, pub inputs: *const *const i64, pub seeds_per_batch: *const i64,
     pub seed: u64, pub batch_base: u32, pub reserved0: u32,

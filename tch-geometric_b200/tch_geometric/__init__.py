@@ -11,6 +11,8 @@ from .ops import (  # noqa: F401
     HeterogenousSampler,
     HomogenousSampler,
     SampledBatches,
+    csc_edge_cumsum,
+    csc_sort_edges,
     ind2ptr,
     neighbor_sampling_heterogenous,
     neighbor_sampling_homogenous,

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libtchgeo_cuda.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_INDEX, ERR_REFERENCE_PANIC, ERR_INTERNAL = range(7)
 SAMPLER_UNIFORM, SAMPLER_UNIFORM_REPLACE, SAMPLER_WEIGHTED = 0, 1, 2
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_i64, c_i32, c_u64, c_u32, c_vp, c_sz = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32,
                                           ctypes.c_void_p, ctypes.c_size_t)
@@ -24,6 +24,7 @@ class SamplingArgs(ctypes.Structure):
         ("num_node_types", c_i32), ("num_rels", c_i32), ("num_hops", c_i32), ("sampler_kind", c_i32),
         ("rel_src", c_vp), ("rel_dst", c_vp),
         ("col_ptrs", c_vp), ("num_cols", c_vp), ("row_indices", c_vp), ("weights", c_vp), ("row_indices32", c_vp),
+        ("weights_cumsum", c_vp),
         ("fanouts", c_vp), ("rel_active", c_vp),
         ("num_batches", c_i64), ("inputs", c_vp), ("seeds_per_batch", c_vp),
         ("seed", c_u64), ("batch_base", c_u32), ("reserved0", c_u32),
@@ -52,6 +53,12 @@ def _load():
     lib.tchgeo_coo_to_csx_workspace_bytes.argtypes = [c_i64, c_i64, c_i64]
     lib.tchgeo_coo_to_csx.restype = c_i32
     lib.tchgeo_coo_to_csx.argtypes = [c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.tchgeo_csc_edge_cumsum_f64.restype = c_i32
+    lib.tchgeo_csc_edge_cumsum_f64.argtypes = [c_vp, c_i64, c_vp, c_i64, c_vp, c_vp]
+    lib.tchgeo_csc_sort_edges_workspace_bytes.restype = c_sz
+    lib.tchgeo_csc_sort_edges_workspace_bytes.argtypes = [c_i64, c_i64]
+    lib.tchgeo_csc_sort_edges.restype = c_i32
+    lib.tchgeo_csc_sort_edges.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]
     P = ctypes.POINTER(SamplingArgs)
     lib.tchgeo_neighbor_sampling_capacity.restype = c_i32
     lib.tchgeo_neighbor_sampling_capacity.argtypes = [P, c_vp, c_vp]
@@ -91,7 +98,7 @@ lib = _load()
 
 EXPORTS = [
     "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_device_set_l2_fetch_granularity", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
-    "tchgeo_coo_to_csx", "tchgeo_compress_indices", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
+    "tchgeo_coo_to_csx", "tchgeo_csc_edge_cumsum_f64", "tchgeo_csc_sort_edges_workspace_bytes", "tchgeo_csc_sort_edges", "tchgeo_compress_indices", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
     "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_timed", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
     "tchgeo_serve_requests", "tchgeo_random_walk", "tchgeo_random_walk_ex", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
 ]

@@ -209,6 +209,61 @@ def _compressed_indices(t: Optional[Tensor]) -> Optional[Tensor]:
 
 
 # ---------------------------------------------------------------------------------------------
+# per-column transforms of CSC edge data (src/data/transform.rs; not exported by the reference's Python module,
+# exposed here because the weighted sampler uses the prefix sums and the reference carries KATs for both)
+# ---------------------------------------------------------------------------------------------
+def csc_edge_cumsum(col_ptrs: Tensor, row_data: Tensor) -> None:
+    """transform.rs:36-60: in-place inclusive prefix sum of `row_data` (f64) inside every column, serial order."""
+    _check(col_ptrs, torch.int64, "col_ptrs")
+    dev = col_ptrs.device
+    _check(row_data, torch.float64, "row_data", dev)
+    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.tchgeo_csc_edge_cumsum_f64(_ptr(col_ptrs), max(col_ptrs.numel() - 1, 0), _ptr(row_data),
+                                                 row_data.numel(), _ptr(scratch), _stream(dev)))
+
+
+def csc_sort_edges(col_ptrs: Tensor, perm: Tensor, row_weights: Tensor, descending: bool = False) -> Tensor:
+    """transform.rs:7-34: new_perm = perm with every column's entries reordered by their weight (stable)."""
+    _check(col_ptrs, torch.int64, "col_ptrs")
+    dev = col_ptrs.device
+    _check(perm, torch.int64, "perm", dev)
+    _check(row_weights, torch.float64, "row_weights", dev)
+    if perm.numel() != row_weights.numel():
+        raise ValueError("perm and row_weights must have the same length")
+    n, ncols = perm.numel(), max(col_ptrs.numel() - 1, 0)
+    out = torch.empty_like(perm)
+    ws_bytes = N.lib.tchgeo_csc_sort_edges_workspace_bytes(n, ncols)
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.tchgeo_csc_sort_edges(_ptr(col_ptrs), ncols, _ptr(perm), _ptr(row_weights), n,
+                                            1 if descending else 0, _ptr(out), _ptr(ws), ws_bytes, _stream(dev)))
+    return out
+
+
+_cumsum_cache = {}
+
+
+def _weights_cumsum(col_ptrs: Tensor, weights: Optional[Tensor]) -> Optional[Tensor]:
+    """Serial per-column prefix sums of the sampler weights (= the reference's w_sum sequence), cached per
+    (col_ptrs, weights) pair like the int32 replica.  TCHGEO_WEIGHT_CUMSUM=0 disables it (the kernel then scans
+    the weights with warp shuffles, which rounds differently for weights that are not exactly summable)."""
+    if weights is None or weights.numel() == 0 or os.environ.get("TCHGEO_WEIGHT_CUMSUM", "1") == "0":
+        return None
+    key = (col_ptrs.data_ptr(), col_ptrs.numel(), weights.data_ptr(), weights.numel(), weights.device.index)
+    ver = (col_ptrs._version, weights._version)
+    hit = _cumsum_cache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    out = weights.clone()
+    csc_edge_cumsum(col_ptrs, out)
+    if len(_cumsum_cache) >= _REPLICA_CACHE_MAX:
+        _cumsum_cache.pop(next(iter(_cumsum_cache)))
+    _cumsum_cache[key] = (ver, out)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # generic driver over tchgeo_neighbor_sampling
 # ---------------------------------------------------------------------------------------------
 class _Call:
@@ -242,6 +297,8 @@ class _Call:
         a.row_indices = ptr_table(row_indices).ctypes.data
         a.weights = ptr_table(weights).ctypes.data if weights is not None else None
         a.row_indices32 = ptr_table([_compressed_indices(t) for t in row_indices]).ctypes.data
+        if weights is not None and filt is None:
+            a.weights_cumsum = ptr_table([_weights_cumsum(c, w) for c, w in zip(col_ptrs, weights)]).ctypes.data
         a.fanouts = host(fanouts, np.int64).ctypes.data
         a.rel_active = host(rel_active, np.uint8).ctypes.data
         a.num_batches = B

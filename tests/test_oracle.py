@@ -82,6 +82,15 @@ def test_csc_edge_cumsum_kat():
     assert got.tolist() == [9.0, 14.0, 22.0, 9.0, 19.0, 11.0, 12.0, 1.5]
 
 
+def test_csc_sort_edges_kat():
+    # src/data/transform.rs:69-82
+    got = O.csc_sort_edges([0, 0, 0, 0, 3, 5, 5, 5, 7, 9], [0, 1, 2, 3, 4, 5, 6, 7],
+                           [9.0, 5.0, 8.0, 9.0, 10.0, 11.0, 1.0, 1.5])
+    assert got.tolist() == [1, 2, 0, 3, 4, 6, 5, 7]
+    desc = O.csc_sort_edges([0, 3, 5], [10, 11, 12, 13, 14], [1.0, 3.0, 2.0, 5.0, 5.0], descending=True)
+    assert desc.tolist() == [11, 12, 10, 13, 14]  # ties keep CSC order
+
+
 # ---------------------------------------------------------------------------------------------
 # neighbor sampling: the reference's invariant tests (neighbor_sampling.rs:438-495, :573-648)
 # ---------------------------------------------------------------------------------------------
