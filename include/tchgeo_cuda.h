@@ -260,6 +260,49 @@ TCHGEO_API tchgeo_status tchgeo_random_walk_ex(const int64_t* row_ptrs, int64_t 
                                                int64_t* attempts_out, tchgeo_stream stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* Negative neighbour sampling over CSR.  For every input v of every node type    */
+/* and each of num_neg slots: pick one of the relations that start at v's type (uniformly, only     */
+/* when there are several), draw up to try_count candidates w uniform in [0, node_count[rel]) and   */
+/* keep the first with !has_edge(v, w) (inbound: !has_edge(w, v)) and v != w.  samples[t] = inputs[t]*/
+/* ++ accepted candidates of dst type t at first appearance (insertion-order HashMap semantic, a    */
+/* duplicated input maps to its last position); edges of relation r in generation order: rows = index*/
+/* of the input, cols = local id of the candidate.  Relations are visited in array order and node   */
+/* types in index order (the reference iterates HashMaps).                                          */
+/* replaces src/algo/negative_sampling.rs:6-47 and :49-131, called from src/python.rs:689-783        */
+/* -------------------------------------------------------------------------------------------- */
+typedef struct tchgeo_negative_args {
+  int32_t num_node_types;            /* T (1 for homogeneous)                                      */
+  int32_t num_rels;                  /* R (1 for homogeneous)                                      */
+  const int32_t* rel_src;            /* HOST [R]                                                   */
+  const int32_t* rel_dst;            /* HOST [R]                                                   */
+  const int64_t* const* row_ptrs;    /* HOST [R] of DEVICE [num_rows[r]+1] (CSR)                    */
+  const int64_t* const* col_indices; /* HOST [R] of DEVICE [nnz_r], ascending inside a row          */
+  const int64_t* num_rows;           /* HOST [R] rows of the CSR                                   */
+  const int64_t* node_count;         /* HOST [R] size.1: candidates come from [0, node_count[r])    */
+  const int64_t* const* inputs;      /* HOST [T] of DEVICE [num_inputs[t]]                          */
+  const int64_t* num_inputs;         /* HOST [T] (0 = type absent from inputs)                      */
+  int64_t num_neg;
+  int64_t try_count;
+  int32_t inbound;                   /* heterogenous only: test has_edge(w, v) instead of (v, w)    */
+  int32_t reserved0;
+  uint64_t seed;
+  int64_t* const* samples;           /* HOST [T] of DEVICE [samples_cap[t]]                         */
+  int64_t* const* rows;              /* HOST [R] of DEVICE [edges_cap[r]]                           */
+  int64_t* const* cols;              /* HOST [R]                                                   */
+  int64_t* samples_len;              /* HOST [T] out                                               */
+  int64_t* edges_len;                /* HOST [R] out                                               */
+  void* workspace;                   /* DEVICE                                                     */
+  size_t workspace_bytes;
+  tchgeo_stream stream;
+} tchgeo_negative_args;
+
+TCHGEO_API tchgeo_status tchgeo_negative_sampling_capacity(const tchgeo_negative_args* args, int64_t* samples_cap /*HOST [T]*/,
+                                                           int64_t* edges_cap /*HOST [R]*/);
+TCHGEO_API size_t tchgeo_negative_sampling_workspace_bytes(const tchgeo_negative_args* args);
+/* Synchronises args->stream (lengths are returned to the host). */
+TCHGEO_API tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* args);
+
+/* -------------------------------------------------------------------------------------------- */
 /* Dedup + insertion-order relabel of one sampled tree (additive stage).                          */
 /*   nodes      = seeds (duplicates kept) ++ every other id at first appearance                    */
 /*   local[i]   = index into `nodes` of samples[i] (a duplicated seed maps to its LAST seed slot)  */

@@ -334,6 +334,60 @@ def random_walk_mt(row_ptrs, col_indices, start, walk_length, p, q, rng_mode=RNG
     return walks, att.value
 
 
+def _negative(node_types, edge_types, row_ptrs, col_indices, sizes, inputs, num_neg, try_count, inbound, heterogenous,
+              rng_mode, seed):
+    T, R = len(node_types), len(edge_types)
+    tix = {t: i for i, t in enumerate(node_types)}
+    rels = [rel_key(e) for e in edge_types]
+    rel_src = np.array([tix[e[0]] for e in edge_types], dtype=np.int32)
+    rel_dst = np.array([tix[e[2]] for e in edge_types], dtype=np.int32)
+
+    def parr(arrs):
+        out = (ctypes.POINTER(ctypes.c_int64) * len(arrs))()
+        for i, a in enumerate(arrs):
+            out[i] = _p(a)
+        return out
+
+    rp = [_i64(row_ptrs[r]) for r in rels]
+    ci = [_i64(col_indices[r]) for r in rels]
+    nrows = np.array([a.size - 1 for a in rp], dtype=np.int64)
+    ncount = np.array([int(sizes[r][1]) for r in rels], dtype=np.int64)
+    inp = [_i64(inputs[t]) if t in inputs else np.zeros(0, dtype=np.int64) for t in node_types]
+    ninp = np.array([a.size for a in inp], dtype=np.int64)
+    total = int(ninp.sum()) * int(num_neg)
+    samples = [np.empty(max(int(ninp[t]) + total, 1), dtype=np.int64) for t in range(T)]
+    rows = [np.empty(max(int(ninp[rel_src[r]]) * int(num_neg), 1), dtype=np.int64) for r in range(R)]
+    cols = [np.empty_like(a) for a in rows]
+    slen, elen = np.zeros(T, dtype=np.int64), np.zeros(R, dtype=np.int64)
+    rc = lib().orc_negative_sampling(
+        ctypes.c_int(T), ctypes.c_int(R), _p(rel_src, ctypes.c_int32), _p(rel_dst, ctypes.c_int32), parr(rp), parr(ci),
+        _p(nrows), _p(ncount), parr(inp), _p(ninp), ctypes.c_int64(num_neg), ctypes.c_int64(try_count),
+        ctypes.c_int(1 if inbound else 0), ctypes.c_int(1 if heterogenous else 0), ctypes.c_int(rng_mode),
+        ctypes.c_uint64(seed), parr(samples), parr(rows), parr(cols), _p(slen), _p(elen))
+    _check(rc)
+    out_s = {t: samples[i][:slen[i]].copy() for i, t in enumerate(node_types)}
+    out_r = {r: rows[i][:elen[i]].copy() for i, r in enumerate(rels)}
+    out_c = {r: cols[i][:elen[i]].copy() for i, r in enumerate(rels)}
+    counts = {t: int(ninp[i]) for i, t in enumerate(node_types)}
+    return out_s, out_r, out_c, counts
+
+
+def negative_sample_neighbors_homogenous(row_ptrs, col_indices, graph_size, inputs, num_neg, try_count,
+                                         rng_mode=RNG_COUNTER, seed=0):
+    """python.rs:689-721 -> (samples, rows, cols, sample_count)"""
+    s, r, c, n = _negative(["n"], [("n", "e", "n")], {"n__e__n": row_ptrs}, {"n__e__n": col_indices},
+                           {"n__e__n": _size(graph_size)}, {"n": inputs}, num_neg, try_count, False, False, rng_mode, seed)
+    return s["n"], r["n__e__n"], c["n__e__n"], n["n"]
+
+
+def negative_sample_neighbors_heterogenous(node_types, edge_types, row_ptrs, col_indices, sizes, inputs, num_neg,
+                                           try_count, inbound, rng_mode=RNG_COUNTER, seed=0):
+    """python.rs:723-783 -> (samples{type}, rows{rel}, cols{rel}, sample_count{type}); node types are visited in
+    `node_types` order and relations in `edge_types` order (the reference iterates HashMaps)."""
+    return _negative(node_types, edge_types, row_ptrs, col_indices, sizes, inputs, num_neg, try_count, inbound, True,
+                     rng_mode, seed)
+
+
 def unique_relabel(samples, num_seeds):
     """dedup stage (negative_sampling.rs:20-47 semantic) -> (nodes, local)"""
     samples = _i64(samples)

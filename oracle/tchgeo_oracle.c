@@ -829,6 +829,115 @@ int orc_serve_requests(const int64_t* ptrs_local, const int64_t* indices_local, 
   return rc;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* F3: negative_sample_neighbors_homogenous / _heterogenous, src/algo/negative_sampling.rs:6-47 and  */
+/* :49-131.  One restatement covers both: T node types, R relations (CSR), relations visited in    */
+/* array order and node types in index order (the reference iterates HashMaps: nondeterministic     */
+/* order, canonicalised like quirk Q6).  `heterogenous` selects the reference function: the         */
+/* heterogeneous one draws the relation with gen_range(0..node_rels.len()) for every slot (:104),    */
+/* the homogeneous one draws nothing.  Counter mode: draws come from Philox(seed; input i, slot,     */
+/* attempt/4, TAG_NEGATIVE | type << 8), relation choice from block 0xFFFFFFFF (only when there is   */
+/* more than one candidate relation; with one candidate every draw yields it).                      */
+/* ------------------------------------------------------------------------------------------ */
+#define ORC_TAG_NEGATIVE 5u
+
+typedef struct { hslot* tab; int64_t cap; } hmap;
+static void hmap_init(hmap* m, int64_t n) {
+  m->cap = 16;
+  while (m->cap < 2 * n + 2) m->cap <<= 1;
+  m->tab = (hslot*)malloc(sizeof(hslot) * (size_t)m->cap);
+  for (int64_t i = 0; i < m->cap; ++i) m->tab[i].val = -1;
+}
+static hslot* hmap_slot(hmap* m, int64_t key) {
+  uint64_t h = (uint64_t)key * 0x9E3779B97F4A7C15ULL;
+  int64_t s = (int64_t)(h >> 20) & (m->cap - 1);
+  while (m->tab[s].val != -1 && m->tab[s].key != key) s = (s + 1) & (m->cap - 1);
+  return &m->tab[s];
+}
+
+int orc_negative_sampling(int T, int R, const int32_t* rel_src, const int32_t* rel_dst,
+                          const int64_t* const* row_ptrs, const int64_t* const* col_indices,
+                          const int64_t* num_rows, const int64_t* node_count,
+                          const int64_t* const* inputs, const int64_t* num_inputs,
+                          int64_t num_neg, int64_t try_count, int inbound, int heterogenous,
+                          int rng_mode, uint64_t seed,
+                          int64_t* const* samples /* [T] cap = capacity rule of the CUDA library */,
+                          int64_t* const* rows, int64_t* const* cols /* [R] cap = num_inputs[src] * num_neg */,
+                          int64_t* samples_len /* [T] */, int64_t* edges_len /* [R] */) {
+  orc_rng rng;
+  orc_rng_init(&rng, rng_mode, seed);
+  int64_t total = 0;
+  for (int t = 0; t < T; ++t) total += num_inputs[t] > 0 ? num_inputs[t] : 0;
+  int64_t max_new = total * num_neg;
+  hmap* maps = (hmap*)malloc(sizeof(hmap) * (size_t)T);
+  for (int t = 0; t < T; ++t) { /* :19-26 / :75-93 */
+    int64_t n = num_inputs[t] > 0 ? num_inputs[t] : 0;
+    hmap_init(&maps[t], n + max_new);
+    samples_len[t] = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      samples[t][samples_len[t]] = inputs[t][i];
+      hslot* sl = hmap_slot(&maps[t], inputs[t][i]);
+      sl->key = inputs[t][i];
+      sl->val = samples_len[t]; /* extend: later duplicates overwrite */
+      samples_len[t]++;
+    }
+  }
+  for (int r = 0; r < R; ++r) edges_len[r] = 0;
+  int rc = ORC_OK;
+  for (int s = 0; s < T && rc == ORC_OK; ++s) { /* for (node_type, inputs) in inputs, :97 */
+    int64_t n = num_inputs[s] > 0 ? num_inputs[s] : 0;
+    if (n == 0) continue;
+    int choices[64], nch = 0;
+    for (int r = 0; r < R && nch < 64; ++r) if (rel_src[r] == s) choices[nch++] = r; /* node_rels, :66-73 */
+    if (nch == 0) { rc = ORC_ERR_PANIC; break; } /* &node_rels[node_type], :98 */
+    for (int64_t i = 0; i < n && rc == ORC_OK; ++i) {
+      int64_t v = inputs[s][i];
+      for (int64_t k = 0; k < num_neg && rc == ORC_OK; ++k) {
+        int c = 0;
+        uint32_t buf[4];
+        if (rng_mode == ORC_RNG_XOSHIRO) {
+          if (heterogenous) c = (int)xoshiro_gen_range_u64(&rng, (uint64_t)nch); /* :104 */
+        } else if (nch > 1) {
+          uint32_t ctr[4] = {(uint32_t)i, (uint32_t)k, 0xFFFFFFFFu, ORC_TAG_NEGATIVE | ((uint32_t)s << 8)};
+          orc_philox4x32_10(ctr, rng.key, buf);
+          c = (int)mulhi32(buf[0], (uint32_t)nch);
+        }
+        int r = choices[c], d = rel_dst[r];
+        for (int64_t t = 0; t < try_count; ++t) { /* :33-43 / :110-126 */
+          int64_t w;
+          if (node_count[r] <= 0) { rc = ORC_ERR_PANIC; break; } /* gen_range(0..0) */
+          if (rng_mode == ORC_RNG_XOSHIRO) {
+            w = (int64_t)xoshiro_gen_range_u64(&rng, (uint64_t)node_count[r]);
+          } else {
+            if ((t & 3) == 0) {
+              uint32_t ctr[4] = {(uint32_t)i, (uint32_t)k, (uint32_t)(t >> 2), ORC_TAG_NEGATIVE | ((uint32_t)s << 8)};
+              orc_philox4x32_10(ctr, rng.key, buf);
+            }
+            w = (int64_t)mulhi32(buf[t & 3], (uint32_t)node_count[r]);
+          }
+          int64_t x = inbound ? w : v, y = inbound ? v : w;
+          if (x < 0 || x >= num_rows[r]) { rc = ORC_ERR_PANIC; break; } /* slice index panic */
+          if (!has_edge(row_ptrs[r], col_indices[r], x, y) && v != w) {
+            hslot* sl = hmap_slot(&maps[d], w);
+            if (sl->val == -1) { /* or_insert_with */
+              sl->key = w;
+              sl->val = samples_len[d];
+              samples[d][samples_len[d]++] = w;
+            }
+            rows[r][edges_len[r]] = i;
+            cols[r][edges_len[r]] = sl->val;
+            edges_len[r]++;
+            break;
+          }
+        }
+      }
+    }
+  }
+  for (int t = 0; t < T; ++t) free(maps[t].tab);
+  free(maps);
+  return rc;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

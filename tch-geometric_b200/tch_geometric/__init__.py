@@ -1,9 +1,10 @@
 """tch_geometric -- B200-native (sm_100a) drop-in for the reference module's sampling hot path.
 
 Mirrors `tch_geometric/__init__.py:1-2` + `tch_geometric.pyi` of the reference for the functions on
-the path (to_csc, to_csr, neighbor_sampling_homogenous, neighbor_sampling_heterogenous, random_walk);
-everything else in the reference (hgt/budget sampling, temporal walks, negative sampling) stays on the
-reference's CPU implementation and is not provided here.  Importing this package loads
+the path (to_csc, to_csr, neighbor_sampling_homogenous, neighbor_sampling_heterogenous, random_walk) and the
+"next" rows of SURVEY 8(f) built so far (negative_sample_neighbors_*, csc_edge_cumsum, csc_sort_edges);
+everything else in the reference (hgt/budget sampling, biased temporal walks) stays on the reference's CPU
+implementation and is not provided here.  Importing this package loads
 libtchgeo_cuda.so and fails if it has not been built: there is no CPU fallback.
 """
 from . import _native  # noqa: F401  (loads the CUDA library, raises if missing)
@@ -14,6 +15,8 @@ from .ops import (  # noqa: F401
     csc_edge_cumsum,
     csc_sort_edges,
     ind2ptr,
+    negative_sample_neighbors_heterogenous,
+    negative_sample_neighbors_homogenous,
     neighbor_sampling_heterogenous,
     neighbor_sampling_homogenous,
     neighbor_sampling_homogenous_batched,

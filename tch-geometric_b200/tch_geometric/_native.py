@@ -37,6 +37,18 @@ class SamplingArgs(ctypes.Structure):
     ]
 
 
+class NegativeArgs(ctypes.Structure):
+    """struct tchgeo_negative_args"""
+    _fields_ = [
+        ("num_node_types", c_i32), ("num_rels", c_i32), ("rel_src", c_vp), ("rel_dst", c_vp),
+        ("row_ptrs", c_vp), ("col_indices", c_vp), ("num_rows", c_vp), ("node_count", c_vp),
+        ("inputs", c_vp), ("num_inputs", c_vp), ("num_neg", c_i64), ("try_count", c_i64),
+        ("inbound", c_i32), ("reserved0", c_i32), ("seed", c_u64),
+        ("samples", c_vp), ("rows", c_vp), ("cols", c_vp), ("samples_len", c_vp), ("edges_len", c_vp),
+        ("workspace", c_vp), ("workspace_bytes", c_sz), ("stream", c_vp),
+    ]
+
+
 def _load():
     if not os.path.exists(LIB_PATH):
         raise ImportError(
@@ -85,6 +97,13 @@ def _load():
     lib.tchgeo_random_walk_ex.restype = c_i32
     lib.tchgeo_random_walk_ex.argtypes = [c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_i64, ctypes.c_float, ctypes.c_float,
                                           c_u64, c_i64, c_vp, c_vp, c_vp, c_vp]
+    PN = ctypes.POINTER(NegativeArgs)
+    lib.tchgeo_negative_sampling_capacity.restype = c_i32
+    lib.tchgeo_negative_sampling_capacity.argtypes = [PN, c_vp, c_vp]
+    lib.tchgeo_negative_sampling_workspace_bytes.restype = c_sz
+    lib.tchgeo_negative_sampling_workspace_bytes.argtypes = [PN]
+    lib.tchgeo_negative_sampling.restype = c_i32
+    lib.tchgeo_negative_sampling.argtypes = [PN]
     lib.tchgeo_unique_relabel_workspace_bytes.restype = c_sz
     lib.tchgeo_unique_relabel_workspace_bytes.argtypes = [c_i64]
     lib.tchgeo_unique_relabel.restype = c_i32
@@ -100,7 +119,7 @@ EXPORTS = [
     "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_device_set_l2_fetch_granularity", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
     "tchgeo_coo_to_csx", "tchgeo_csc_edge_cumsum_f64", "tchgeo_csc_sort_edges_workspace_bytes", "tchgeo_csc_sort_edges", "tchgeo_compress_indices", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
     "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_timed", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
-    "tchgeo_serve_requests", "tchgeo_random_walk", "tchgeo_random_walk_ex", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
+    "tchgeo_serve_requests", "tchgeo_negative_sampling_capacity", "tchgeo_negative_sampling_workspace_bytes", "tchgeo_negative_sampling", "tchgeo_random_walk", "tchgeo_random_walk_ex", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
 ]
 
 

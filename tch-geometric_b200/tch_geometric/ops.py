@@ -645,6 +645,99 @@ def random_walk(row_ptrs: Tensor, col_indices: Tensor, start: Tensor, walk_lengt
 
 
 # ---------------------------------------------------------------------------------------------
+# negative neighbour sampling (python.rs:689-783 -> negative_sampling.rs:6-131)
+# ---------------------------------------------------------------------------------------------
+def _negative(node_types, edge_types, row_ptrs, col_indices, sizes, inputs, num_neg, try_count, inbound, seed):
+    node_types = list(node_types)
+    edge_types = [tuple(e) for e in edge_types]
+    tix = {t: i for i, t in enumerate(node_types)}
+    rels = [rel_key(e) for e in edge_types]
+    T, R = len(node_types), len(rels)
+    for r in row_ptrs:  # graphs are built from row_ptrs.keys(), python.rs:748-753
+        if r not in col_indices or r not in sizes:
+            raise KeyError(r)
+    for t in inputs:
+        if t not in tix:
+            raise KeyError(t)
+    dev = next(iter(row_ptrs.values())).device
+    keep = []
+
+    def host(arr, dtype):
+        x = np.ascontiguousarray(np.asarray(arr, dtype=dtype))
+        keep.append(x)
+        return x
+
+    def ptr_table(tensors):
+        x = np.array([(t.data_ptr() if t is not None else 0) for t in tensors], dtype=np.uint64)
+        keep.append(x)
+        keep.append(list(tensors))
+        return x
+
+    rp, ci, nrows, ncount = [], [], [], []
+    for r in rels:
+        if r not in row_ptrs:
+            raise KeyError(r)  # &graphs[rel_type] panics when the relation is drawn, negative_sampling.rs:105
+        rp.append(_check(row_ptrs[r], torch.int64, f"row_ptrs[{r}]", dev))
+        ci.append(_check(col_indices[r], torch.int64, f"col_indices[{r}]", dev))
+        nrows.append(rp[-1].numel() - 1)
+        ncount.append(_size_tuple(sizes[r])[1])
+    inp = [(_as_seed_matrix(inputs[t], dev, f"inputs[{t}]").reshape(-1) if t in inputs else None) for t in node_types]
+    a = N.NegativeArgs()
+    a.num_node_types, a.num_rels = T, R
+    a.rel_src = host([tix[e[0]] for e in edge_types], np.int32).ctypes.data
+    a.rel_dst = host([tix[e[2]] for e in edge_types], np.int32).ctypes.data
+    a.row_ptrs, a.col_indices = ptr_table(rp).ctypes.data, ptr_table(ci).ctypes.data
+    a.num_rows, a.node_count = host(nrows, np.int64).ctypes.data, host(ncount, np.int64).ctypes.data
+    a.inputs = ptr_table(inp).ctypes.data
+    a.num_inputs = host([(x.numel() if x is not None else 0) for x in inp], np.int64).ctypes.data
+    a.num_neg, a.try_count, a.inbound, a.seed = int(num_neg), int(try_count), 1 if inbound else 0, seed
+    if a.num_neg < 0 or a.try_count < 0:
+        num_neg, try_count = max(a.num_neg, 0), max(a.try_count, 0)  # `for _ in 0..n` with n < 0 is an empty loop
+        a.num_neg, a.try_count = num_neg, try_count
+    cap_n, cap_e = np.zeros(T, dtype=np.int64), np.zeros(R, dtype=np.int64)
+    N.check(N.lib.tchgeo_negative_sampling_capacity(ctypes.byref(a), cap_n.ctypes.data, cap_e.ctypes.data))
+    i64 = dict(dtype=torch.int64, device=dev)
+    samples = [torch.empty(int(c), **i64) for c in cap_n]
+    rows = [torch.empty(int(c), **i64) for c in cap_e]
+    cols = [torch.empty(int(c), **i64) for c in cap_e]
+    a.samples, a.rows, a.cols = ptr_table(samples).ctypes.data, ptr_table(rows).ctypes.data, ptr_table(cols).ctypes.data
+    slen, elen = np.zeros(T, dtype=np.int64), np.zeros(R, dtype=np.int64)
+    a.samples_len, a.edges_len = slen.ctypes.data, elen.ctypes.data
+    ws_bytes = N.lib.tchgeo_negative_sampling_workspace_bytes(ctypes.byref(a))
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
+    a.workspace, a.workspace_bytes = ws.data_ptr(), ws_bytes
+    with torch.cuda.device(dev):
+        a.stream = torch.cuda.current_stream(dev).cuda_stream
+        N.check(N.lib.tchgeo_negative_sampling(ctypes.byref(a)))
+    out_s = {t: samples[i][:int(slen[i])] for i, t in enumerate(node_types)}
+    out_r = {r: rows[i][:int(elen[i])] for i, r in enumerate(rels)}
+    out_c = {r: cols[i][:int(elen[i])] for i, r in enumerate(rels)}
+    counts = {t: (inp[i].numel() if inp[i] is not None else 0) for i, t in enumerate(node_types)}
+    return out_s, out_r, out_c, counts
+
+
+def negative_sample_neighbors_homogenous(row_ptrs: Tensor, col_indices: Tensor, graph_size: Tuple[int, int],
+                                         inputs: Tensor, num_neg: int, try_count: int, *,
+                                         seed: Optional[int] = None) -> Tuple[Tensor, Tensor, Tensor, int]:
+    """python.rs:689-721.  Returns (samples, rows, cols, sample_count): samples = inputs ++ accepted negatives at first
+    appearance, (rows[e], cols[e]) index `samples`, sample_count = len(inputs)."""
+    s, r, c, n = _negative(["n"], [("n", "e", "n")], {"n__e__n": row_ptrs}, {"n__e__n": col_indices},
+                           {"n__e__n": graph_size}, {"n": inputs}, num_neg, try_count, False,
+                           _rng_get() if seed is None else seed)
+    return s["n"], r["n__e__n"], c["n__e__n"], n["n"]
+
+
+def negative_sample_neighbors_heterogenous(node_types: List[str], edge_types: List[Tuple[str, str, str]],
+                                           row_ptrs: Dict[str, Tensor], col_indices: Dict[str, Tensor],
+                                           sizes: Dict[str, Tuple[int, int]], inputs: Dict[str, Tensor], num_neg: int,
+                                           try_count: int, inbound: bool, *, seed: Optional[int] = None):
+    """python.rs:723-783.  Returns (samples{node_type}, rows{rel}, cols{rel}, sample_count{node_type}).  Node types
+    are visited in `node_types` order and relations in `edge_types` order (the reference iterates HashMaps)."""
+    return _negative(node_types, edge_types, row_ptrs, col_indices, sizes, inputs, num_neg, try_count, inbound,
+                     _rng_get() if seed is None else seed)
+
+
+# ---------------------------------------------------------------------------------------------
 # dedup + relabel stage (additive; semantic of negative_sampling.rs:20-47)
 # ---------------------------------------------------------------------------------------------
 def unique_relabel(samples: Tensor, num_seeds: int) -> Tuple[Tensor, Tensor]:

@@ -27,7 +27,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 21
+    assert len(syms) == 24
     for s in ("tchgeo_coo_to_csx", "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_homogenous",
               "tchgeo_random_walk", "tchgeo_unique_relabel", "tchgeo_ind2ptr", "tchgeo_last_error"):
         assert s in syms
@@ -48,20 +48,22 @@ def test_library_is_sm100a_native(native):
     assert "sm_100a" in out.stdout
 
 
-def test_struct_layout_matches_c(native):
-    fields = [f[0] for f in native.SamplingArgs._fields_]
-    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "tchgeo_cuda.h"\nint main(){printf("%zu", sizeof(tchgeo_sampling_args));\n'
+@pytest.mark.parametrize("cname,pyname", [("tchgeo_sampling_args", "SamplingArgs"), ("tchgeo_negative_args", "NegativeArgs")])
+def test_struct_layout_matches_c(native, cname, pyname):
+    cls = getattr(native, pyname)
+    fields = [f[0] for f in cls._fields_]
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "tchgeo_cuda.h"\nint main(){printf("%%zu", sizeof(%s));\n' % cname
     for f in fields:
-        prog += f'printf(" %zu", offsetof(tchgeo_sampling_args, {f}));\n'
+        prog += f'printf(" %zu", offsetof({cname}, {f}));\n'
     prog += "return 0;}\n"
     with tempfile.TemporaryDirectory() as d:
         c, exe = os.path.join(d, "t.c"), os.path.join(d, "t")
         open(c, "w").write(prog)
         subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe])
         vals = [int(x) for x in subprocess.check_output([exe]).split()]
-    assert vals[0] == ctypes.sizeof(native.SamplingArgs)
+    assert vals[0] == ctypes.sizeof(cls)
     for f, off in zip(fields, vals[1:]):
-        assert getattr(native.SamplingArgs, f).offset == off, f
+        assert getattr(cls, f).offset == off, f
 
 
 def test_host_only_entry_points_work_without_a_gpu(native):
@@ -86,3 +88,15 @@ def test_host_only_entry_points_work_without_a_gpu(native):
     assert native.lib.tchgeo_ind2ptr(None, 5, 3, None, None) == native.ERR_BAD_ARG
     assert native.lib.tchgeo_random_walk(None, 1, None, None, 1, 1, 1.0, 1.0, 0, 0, None, None, None, None) == native.ERR_BAD_ARG
     assert native.lib.tchgeo_coo_to_csx(None, None, -1, 1, 1, 1, None, None, None, None, 0, None) == native.ERR_BAD_ARG
+    # negative sampling: capacity planning is host code too
+    n = native.NegativeArgs()
+    src, dst = np.array([0, 0], dtype=np.int32), np.array([0, 1], dtype=np.int32)
+    dummy = np.zeros(2, dtype=np.uint64) + 8  # non-NULL placeholders (never dereferenced by the planner)
+    nrows, ncount, ninp = np.array([5, 5], dtype=np.int64), np.array([5, 9], dtype=np.int64), np.array([4, 2], dtype=np.int64)
+    n.num_node_types, n.num_rels, n.num_neg, n.try_count = 2, 2, 3, 5
+    n.rel_src, n.rel_dst = src.ctypes.data, dst.ctypes.data
+    n.row_ptrs = n.col_indices = n.inputs = dummy.ctypes.data
+    n.num_rows, n.node_count, n.num_inputs = nrows.ctypes.data, ncount.ctypes.data, ninp.ctypes.data
+    cn, ce = np.zeros(2, dtype=np.int64), np.zeros(2, dtype=np.int64)
+    assert native.lib.tchgeo_negative_sampling_capacity(ctypes.byref(n), cn.ctypes.data, ce.ctypes.data) == 0
+    assert cn.tolist() == [4 + 12, 2 + 12] and ce.tolist() == [12, 12]
