@@ -526,6 +526,62 @@ def run_walk(args):
         dist.destroy_process_group()
 
 
+def run_negative(args):
+    """negative_sample_neighbors_homogenous on the products-shaped CSR, 1 Mi inputs x 5 negatives."""
+    import tch_geometric as thg
+    rank, world, local = dist_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    ei, n = build_graph(device, args.scale)
+    rp, ci, _ = thg.to_csr(ei, n)
+    del ei
+    torch.cuda.empty_cache()
+    S, NEG, TRY = (1 << 20 if args.scale == 1.0 else 1 << 14), 5, 5
+    K, W = args.steps, args.warmup
+    g = torch.Generator(device=device)
+    g.manual_seed(99)
+    inputs = [torch.randint(0, n, (S,), generator=g, dtype=torch.int64, device=device) for _ in range(W + K)]
+    for s in range(W):
+        thg.negative_sample_neighbors_homogenous(rp, ci, (n, n), inputs[s], NEG, TRY, seed=s)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    edges = 0
+    e0.record()
+    for s in range(W, W + K):
+        out = thg.negative_sample_neighbors_homogenous(rp, ci, (n, n), inputs[s], NEG, TRY, seed=100 + s)
+        edges += out[1].numel()
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    value = edges / (ms * 1e-3)
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as O
+        hrp, hci = rp.cpu().numpy(), ci.cpu().numpy()
+        sub = inputs[W][: min(S, 200_000)].cpu().numpy()
+        t0 = time.perf_counter()
+        o = O.negative_sample_neighbors_homogenous(hrp, hci, (n, n), sub, NEG, TRY, rng_mode=O.RNG_XOSHIRO, seed=1)
+        dt = time.perf_counter() - t0
+        cpu = {"value": o[1].size / dt, "unit": "negatives/s", "cores": 1, "kind": "port",
+               "sample": f"{sub.size} inputs x {NEG} negatives, single thread like the reference ({dt:.1f} s)"}
+    deg_mean = ci.numel() / n
+    alg = edges * (16 + 8 * int(np.ceil(np.log2(max(deg_mean, 2)))) + 24)  # row_ptrs pair + search + (rows, cols, sample)
+    peak, peak_src = measured_peak_gbs()
+    emit({"metric": "negative_samples_per_sec", "value": value, "unit": "negatives/s", "n_gpus": 1, "steps": K, "warmup": W,
+          "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+          "data": "synthetic",
+          "config": {"workload": f"products-shaped synthetic graph (N={n}, E={ci.numel()}), negative_sample_neighbors_homogenous, "
+                                 f"{S} inputs, num_neg={NEG}, try_count={TRY}",
+                     "l2_policy": "inputs differ every step; col_indices is 495 MB"},
+          "roofline": {"bound": "hbm", "kernel": "whole call (draw + 2 compactions + relabel)", "achieved": alg / (ms * 1e-3) / 1e9,
+                       "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None,
+                       "peak_source": peak_src},
+          "cpu_baseline": cpu, "e2e": None, "gpu_launches": K * 12, "clocks": clk})
+
+
 def run_hetero(args):
     """configs[3]: ogbn-mag-shaped heterogeneous sampling, fanouts [10,10] per relation, 1024 paper seeds."""
     import tch_geometric as thg
@@ -614,7 +670,7 @@ def run_partitioned(args):
     8 ranks hold exactly the 111 059 956-node, 1 615 685 872-edge shape."""
     import tch_geometric as thg
     import torch.distributed as dist
-    from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedSampler, SingleComm, partition_bounds
+    from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedPlan, SingleComm, partition_bounds
     from tch_geometric.sharding import reduce_job
     rank, world, local = dist_env()
     device = torch.device("cuda", local)
@@ -641,7 +697,7 @@ def run_partitioned(args):
         edge_base, e_total = 0, int(e_local.item())
     part = ColumnPartition(ptrs, idx, n, rank, world, edge_base)
     B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
-    ps = PartitionedSampler(part, FANOUTS, comm=DistComm() if world > 1 else SingleComm())
+    ps = PartitionedPlan(part, B, S, FANOUTS, comm=DistComm() if world > 1 else SingleComm())
     seeds = [torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B)).to(device)
              for s in range(W + K)]
     for s in range(W):
@@ -656,7 +712,7 @@ def run_partitioned(args):
     e0.record()
     for s in range(W, W + K):
         out = ps.sample(seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
-        edges_n += sum(int(o[1].numel()) for o in out)
+        edges_n += int(out.edges_len.sum())
     e1.record()
     torch.cuda.synchronize()
     clk = clocks.stop()
@@ -671,7 +727,7 @@ def run_partitioned(args):
                          "parallelism": "column-range partition + all-to-all(v) of requests and answers"},
               "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + K),
                                                    "answers": ps.stats["answer_bytes"] // (W + K)},
-              "cpu_baseline": None, "e2e": None, "gpu_launches": K * len(FANOUTS), "clocks": clk})
+              "cpu_baseline": None, "e2e": None, "gpu_launches": K * len(FANOUTS) * 8, "clocks": clk})
     if world > 1:
         dist.destroy_process_group()
 
@@ -682,7 +738,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned"],
+    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned", "negative"],
                     help="sampling = headline (configs[1]); walk = configs[2]; hetero = configs[3]")
     ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
@@ -702,6 +758,8 @@ def main():
         run_hetero(args)
     elif args.workload == "partitioned":
         run_partitioned(args)
+    elif args.workload == "negative":
+        run_negative(args)
     else:
         run_ours(args)
 

@@ -239,6 +239,46 @@ TCHGEO_API tchgeo_status tchgeo_serve_requests(
     int64_t n, int64_t fanout, int32_t sampler_kind, uint64_t seed, uint32_t rel, int64_t* out_ids /*DEVICE [n*fanout]*/,
     int64_t* out_ptrs /*DEVICE [n*fanout]*/, int32_t* err_scratch /*DEVICE [1]*/, tchgeo_stream stream);
 
+/* Requester side of the partitioned path as a device pipeline.  A hop on every rank is
+ *   tchgeo_part_begin_hop   count the frontier per owning rank (owner(w) = min(w / cols_per_rank, world-1)) into
+ *                           counts[world] and scatter request rows (id, (batch_base+b) << 32 | pos) into `req`
+ *                           grouped by owner (order inside a group is arbitrary); asynchronous
+ *   -- exchange counts, then the request rows, with an all-to-all (NCCL; the host reads the counts once) --
+ *   tchgeo_serve_requests_rows  owner side on interleaved rows: req [n,2] -> ans [n, 2*fanout] = fanout ids then
+ *                           fanout global CSC positions per row, -1 padded; asynchronous
+ *   -- all-to-all of the answer rows back --
+ *   tchgeo_part_finish_hop  per-node answer counts, exclusive scan in frontier order, then the tree layout of
+ *                           src/algo/neighbor_sampling.rs:210-218 appended to the caller's [B, stride] buffers at
+ *                           node_len_in / edge_len_in; writes the new lengths; asynchronous
+ * The frontier of batch b is samples[b, fr_begin[b] .. fr_end[b]) (fr_begin NULL = 0); frontier_cap bounds its
+ * size.  Device-side errors are OR-ed into *err_word (DEVICE u32, caller zeroes it; decode with
+ * tchgeo_status_from_error_word). */
+TCHGEO_API tchgeo_status tchgeo_part_begin_hop(const int64_t* samples /*DEVICE [B, samples_stride]*/, int64_t samples_stride,
+                                               const int64_t* fr_begin /*DEVICE [B] or NULL*/,
+                                               const int64_t* fr_end /*DEVICE [B]*/, int64_t num_batches,
+                                               int64_t frontier_cap, int64_t cols_per_rank, int32_t world,
+                                               uint32_t batch_base, int64_t* counts /*DEVICE [world]*/,
+                                               int64_t* cursor /*DEVICE [world] scratch*/,
+                                               int64_t* req /*DEVICE [B*frontier_cap, 2]*/, int32_t* err_word,
+                                               tchgeo_stream stream);
+TCHGEO_API tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, const int64_t* indices_local,
+                                                    const double* weights_local, int64_t col_begin, int64_t ncols_local,
+                                                    int64_t edge_base, const int64_t* req /*DEVICE [n,2]*/, int64_t n,
+                                                    int64_t fanout, int32_t sampler_kind, uint64_t seed, uint32_t rel,
+                                                    int64_t* ans /*DEVICE [n, 2*fanout]*/, int32_t* err_word,
+                                                    tchgeo_stream stream);
+TCHGEO_API size_t tchgeo_part_finish_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap);
+TCHGEO_API tchgeo_status tchgeo_part_finish_hop(const int64_t* req /*DEVICE [F,2] as sent*/, const int64_t* ans /*DEVICE [F, 2*fanout]*/,
+                                                int64_t num_requests, int64_t fanout, uint32_t batch_base,
+                                                const int64_t* fr_begin, int64_t num_batches, int64_t frontier_cap,
+                                                const int64_t* node_len_in /*DEVICE [B]*/, const int64_t* edge_len_in,
+                                                int64_t* node_len_out, int64_t* edge_len_out, int64_t* samples,
+                                                int64_t samples_stride, int64_t* rows, int64_t* cols, int64_t* edge_index,
+                                                int64_t edges_stride, int32_t* err_word, void* workspace,
+                                                size_t workspace_bytes, tchgeo_stream stream);
+/* Map a device error word (as accumulated by the asynchronous entry points) to a status + last-error string. */
+TCHGEO_API tchgeo_status tchgeo_status_from_error_word(uint32_t word);
+
 /* -------------------------------------------------------------------------------------------- */
 /* node2vec random walk over CSR.  walks: [num_walks, walk_length+1] row-major, -1 padded.        */
 /* Walker i draws with walker index walker_base + i (so sharded launches reproduce one big one).   */

@@ -29,3 +29,5 @@ extern "C" tchgeo_status tchgeo_device_set_l2_fetch_granularity(int32_t bytes, i
   if (actual) *actual = (int32_t)v;
   return TCHGEO_OK;
 }
+
+extern "C" tchgeo_status tchgeo_status_from_error_word(uint32_t word) { return tchgeo::status_from_dev_err(word); }

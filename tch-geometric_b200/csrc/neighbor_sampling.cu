@@ -77,6 +77,7 @@ struct HopParams {
   int32_t tile_edges;          // tile_nodes * fanout
   int32_t fanout;
   uint32_t key0, key1;
+  uint32_t rk[20];              // Philox round keys (key0 + r*W0, key1 + r*W1): constant-bank operands, no registers
   uint32_t rel;
   uint32_t batch_base;
   uint32_t total_tiles;         // num_batches * tiles_per_batch
@@ -153,6 +154,20 @@ __device__ __forceinline__ void reservoir_block_sa(const Philox4& r, uint32_t st
         ::"r"(slots_sa + 4u * j), "r"(step), "r"(hit)
         : "memory");
   }
+}
+
+// Philox4x32-10 with the round keys taken from the kernel parameters (constant bank): same function as
+// philox4x32_10(..., p.key0, p.key1), but the 18 bumped keys do not occupy registers for the whole draw loop.
+__device__ __forceinline__ Philox4 philox_rk(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const HopParams& p) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const uint32_t n0 = hi1 ^ c1 ^ p.rk[2 * r];
+    const uint32_t n2 = hi0 ^ c3 ^ p.rk[2 * r + 1];
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+  }
+  return Philox4{c0, c1, c2, c3};
 }
 
 template <int KIND, int MINB, int NT, int TPC>
@@ -336,7 +351,6 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
 
   if (KIND == TCHGEO_SAMPLER_UNIFORM) {
     const uint32_t tag = TAG_RESERVOIR | (p.rel << 8);
-    const uint32_t key0 = p.key0, key1 = p.key1;
     const uint32_t slot_sa = (uint32_t)__cvta_generic_to_shared(s_slot);
     // Light nodes: (node, 4-step block) work items, grabbed 128 at a time so that warp 0 joins in
     // after its look-back.  Block c of node n covers steps k+4c .. k+4c+3 of the serial reservoir.
@@ -350,7 +364,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
         const uint32_t n = s_chown[q];
         const NodeRec rec = s_rec[n];
         const uint32_t c = q - rec.choff;
-        const Philox4 r = philox4x32_10(pos0 + n, c, batch, tag, key0, key1);
+        const Philox4 r = philox_rk(pos0 + n, c, batch, tag, p);
         reservoir_block_sa(r, k + 4u * c, rec.deg, k, slot_sa + 4u * rec.off);
       }
     }
@@ -361,7 +375,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
       const NodeRec rec = s_rec[n];
       const uint32_t nb = (rec.deg - k + 3u) >> 2;
       for (uint32_t c = lane; c < nb; c += 32) {
-        const Philox4 r = philox4x32_10(pos0 + n, c, batch, tag, key0, key1);
+        const Philox4 r = philox_rk(pos0 + n, c, batch, tag, p);
         reservoir_block_sa(r, k + 4u * c, rec.deg, k, slot_sa + 4u * rec.off);
       }
     }
@@ -464,7 +478,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
       own[u] = n;
       uint32_t rel_ptr;
       if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
-        const Philox4 r = philox4x32_10(pos0 + n, s >> 2, batch, rtag, p.key0, p.key1);
+        const Philox4 r = philox_rk(pos0 + n, s >> 2, batch, rtag, p);
         rel_ptr = __umulhi(pick4(r, s & 3u), rec.deg);  // sampling.rs:64
       } else {
         const uint32_t st = s_slot[e];
@@ -737,7 +751,7 @@ inline int hop_min_blocks() {
   static int v = -1;
   if (v < 0) {
     const int x = env_int("TCHGEO_HOP_MIN_BLOCKS", HOP_DEFAULT_MIN_BLOCKS);
-    v = (x >= 4 && x <= 6) ? x : HOP_DEFAULT_MIN_BLOCKS;
+    v = (x >= 4 && x <= 8) ? x : HOP_DEFAULT_MIN_BLOCKS;  // 7, 8: 128-thread tiles only (14 / 16 CTAs per SM)
   }
   return v;
 }
@@ -892,6 +906,8 @@ cudaError_t launch_hop_t(const HopParams& hp, int64_t tiles, size_t smem, cudaSt
     switch (hop_min_blocks()) {
       case 4: return launch_hop_v<KIND, 8, 128, TPC>(hp, tiles, smem, stream);
       case 6: return launch_hop_v<KIND, 12, 128, TPC>(hp, tiles, smem, stream);
+      case 7: return launch_hop_v<KIND, 14, 128, TPC>(hp, tiles, smem, stream);
+      case 8: return launch_hop_v<KIND, 16, 128, TPC>(hp, tiles, smem, stream);
       default: return launch_hop_v<KIND, 10, 128, TPC>(hp, tiles, smem, stream);
     }
   }
@@ -1077,6 +1093,10 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.fanout = (int32_t)L.fanout;
     hp.key0 = (uint32_t)a->seed;
     hp.key1 = (uint32_t)(a->seed >> 32);
+    for (uint32_t r = 0; r < 10; ++r) {
+      hp.rk[2 * r] = hp.key0 + r * 0x9E3779B9u;
+      hp.rk[2 * r + 1] = hp.key1 + r * 0xBB67AE85u;
+    }
     hp.rel = (uint32_t)r;
     hp.batch_base = a->batch_base;
     const int64_t grid = (int64_t)L.tiles_per_batch * B;

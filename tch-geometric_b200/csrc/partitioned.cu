@@ -9,6 +9,9 @@
 // for bit no matter how the graph is partitioned.  Nothing here depends on the reference beyond the
 // samplers of src/utils/sampling.rs:6-69 restated in neighbor_sampling.cu.
 #include <cub/block/block_scan.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <algorithm>
 
 #include "common.cuh"
 
@@ -25,8 +28,10 @@ struct ServeParams {
   const double* weights;    // local weights or NULL
   const int64_t* req_ids;
   const int64_t* req_meta;  // (batch << 32) | pos
+  int64_t req_stride;       // elements between consecutive requests (1: two arrays, 2: interleaved (id, meta) rows)
   int64_t* out_ids;
   int64_t* out_ptrs;
+  int64_t out_stride;       // elements between consecutive answer rows (fanout, or 2*fanout for [n][ids | ptrs] rows)
   uint32_t* err;
   int64_t col_begin, ncols, edge_base, n;
   int32_t fanout, tile_reqs;
@@ -64,8 +69,8 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
   int64_t start = 0;
   bool heavy = false;
   if (tid < nn) {
-    const int64_t w = p.req_ids[r0 + tid] - p.col_begin;
-    const int64_t meta = p.req_meta[r0 + tid];
+    const int64_t w = p.req_ids[(r0 + tid) * p.req_stride] - p.col_begin;
+    const int64_t meta = p.req_meta[(r0 + tid) * p.req_stride];
     s_pos[tid] = (uint32_t)meta;
     s_batch[tid] = (uint32_t)((uint64_t)meta >> 32);
     if (w < 0 || w >= p.ncols) {
@@ -161,8 +166,8 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
       id = ld_gather64_i64(p.indices + lp);
       gp = p.edge_base + lp;
     }
-    st_cs_i64(p.out_ids + r0 * k + e, id);
-    st_cs_i64(p.out_ptrs + r0 * k + e, gp);
+    st_cs_i64(p.out_ids + (r0 + n) * p.out_stride + s, id);
+    st_cs_i64(p.out_ptrs + (r0 + n) * p.out_stride + s, gp);
   }
 }
 
@@ -171,22 +176,21 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
 
 using namespace tchgeo;
 
-extern "C" tchgeo_status tchgeo_serve_requests(const int64_t* ptrs_local, const int64_t* indices_local,
-                                               const double* weights_local, int64_t col_begin, int64_t ncols_local,
-                                               int64_t edge_base, const int64_t* req_ids, const int64_t* req_meta,
-                                               int64_t n, int64_t fanout, int32_t sampler_kind, uint64_t seed,
-                                               uint32_t rel, int64_t* out_ids, int64_t* out_ptrs,
-                                               int32_t* err_scratch, tchgeo_stream stream_) {
+static tchgeo_status serve_launch(const int64_t* ptrs_local, const int64_t* indices_local, const double* weights_local,
+                                  int64_t col_begin, int64_t ncols_local, int64_t edge_base, const int64_t* req_ids,
+                                  const int64_t* req_meta, int64_t req_stride, int64_t n, int64_t fanout,
+                                  int32_t sampler_kind, uint64_t seed, uint32_t rel, int64_t* out_ids, int64_t* out_ptrs,
+                                  int64_t out_stride, uint32_t* err, cudaStream_t stream) {
   TCHGEO_REQUIRE(n >= 0 && fanout >= 0 && fanout <= SV_MAX_TILE_SLOTS && ncols_local >= 0, "bad serve argument");
-  TCHGEO_REQUIRE(sampler_kind >= 0 && sampler_kind <= 2 && err_scratch != nullptr, "bad serve argument");
+  TCHGEO_REQUIRE(sampler_kind >= 0 && sampler_kind <= 2 && err != nullptr, "bad serve argument");
   TCHGEO_REQUIRE(sampler_kind != TCHGEO_SAMPLER_WEIGHTED || weights_local != nullptr, "weighted serve without weights");
   if (n == 0 || fanout == 0) return TCHGEO_OK;
   TCHGEO_REQUIRE(ptrs_local && req_ids && req_meta && out_ids && out_ptrs, "NULL pointer");
-  cudaStream_t stream = (cudaStream_t)stream_;
   ServeParams sp;
   sp.ptrs = ptrs_local; sp.indices = indices_local; sp.weights = weights_local;
-  sp.req_ids = req_ids; sp.req_meta = req_meta; sp.out_ids = out_ids; sp.out_ptrs = out_ptrs;
-  sp.err = (uint32_t*)err_scratch;
+  sp.req_ids = req_ids; sp.req_meta = req_meta; sp.req_stride = req_stride;
+  sp.out_ids = out_ids; sp.out_ptrs = out_ptrs; sp.out_stride = out_stride;
+  sp.err = err;
   sp.col_begin = col_begin; sp.ncols = ncols_local; sp.edge_base = edge_base; sp.n = n;
   sp.fanout = (int32_t)fanout;
   sp.tile_reqs = (int32_t)std::min<int64_t>(SV_THREADS, std::max<int64_t>(1, SV_MAX_TILE_SLOTS / fanout));
@@ -194,15 +198,278 @@ extern "C" tchgeo_status tchgeo_serve_requests(const int64_t* ptrs_local, const 
   const int64_t grid = (n + sp.tile_reqs - 1) / sp.tile_reqs;
   TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many requests for one launch");
   const size_t smem = (size_t)sp.tile_reqs * fanout * 4 + 16;
-  TCHGEO_CUDA_CHECK(cudaMemsetAsync(err_scratch, 0, 4, stream));
   switch (sampler_kind) {
     case TCHGEO_SAMPLER_UNIFORM: serve_kernel<TCHGEO_SAMPLER_UNIFORM><<<(unsigned)grid, SV_THREADS, smem, stream>>>(sp); break;
     case TCHGEO_SAMPLER_UNIFORM_REPLACE: serve_kernel<TCHGEO_SAMPLER_UNIFORM_REPLACE><<<(unsigned)grid, SV_THREADS, smem, stream>>>(sp); break;
     default: serve_kernel<TCHGEO_SAMPLER_WEIGHTED><<<(unsigned)grid, SV_THREADS, smem, stream>>>(sp); break;
   }
   TCHGEO_CUDA_CHECK(cudaGetLastError());
+  return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_serve_requests(const int64_t* ptrs_local, const int64_t* indices_local,
+                                               const double* weights_local, int64_t col_begin, int64_t ncols_local,
+                                               int64_t edge_base, const int64_t* req_ids, const int64_t* req_meta,
+                                               int64_t n, int64_t fanout, int32_t sampler_kind, uint64_t seed,
+                                               uint32_t rel, int64_t* out_ids, int64_t* out_ptrs,
+                                               int32_t* err_scratch, tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(err_scratch != nullptr, "bad serve argument");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(err_scratch, 0, 4, stream));
+  const tchgeo_status st = serve_launch(ptrs_local, indices_local, weights_local, col_begin, ncols_local, edge_base,
+                                        req_ids, req_meta, 1, n, fanout, sampler_kind, seed, rel, out_ids, out_ptrs,
+                                        fanout, (uint32_t*)err_scratch, stream);
+  if (st != TCHGEO_OK) return st;
   uint32_t herr = 0;
   TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&herr, err_scratch, 4, cudaMemcpyDeviceToHost, stream));
   TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
   return status_from_dev_err(herr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Requester side of the partitioned path as a device pipeline (no host round trip inside a hop except the
+// exchange of the per-owner request counts that sizes the all-to-all):
+//   tchgeo_part_begin_hop : count the frontier per owning rank, then scatter (id, meta) request rows into the
+//                           send buffer grouped by owner (order inside a group is arbitrary: answers come back in
+//                           request order and are placed by the (batch, position) they carry)
+//   tchgeo_serve_requests_rows : owner side on interleaved rows, asynchronous
+//   tchgeo_part_finish_hop: per-node answer counts -> exclusive scan in frontier order -> the tree layout of
+//                           neighbor_sampling.rs:210-218 in the caller's [B, capacity] buffers, new lengths
+// ---------------------------------------------------------------------------------------------
+namespace tchgeo {
+namespace {
+
+constexpr int PT_THREADS = 256;
+constexpr int PT_MAX_WORLD = 64;
+
+struct PartFrontier {
+  const int64_t* samples;     // [B, samples_stride]
+  int64_t samples_stride;
+  const int64_t* fr_begin;    // [B] or NULL (= 0)
+  const int64_t* fr_end;      // [B]
+  int64_t B, capF;            // capF: upper bound of the per-batch frontier size (launch geometry)
+  int64_t cols_per_rank;
+  int32_t world;
+  uint32_t batch_base;
+};
+
+__device__ __forceinline__ bool pt_node(const PartFrontier& f, int64_t t, int64_t& b, int64_t& pos, int64_t& id) {
+  b = t / f.capF;
+  const int64_t j = t - b * f.capF;
+  if (b >= f.B) return false;
+  const int64_t fb = f.fr_begin ? f.fr_begin[b] : 0;
+  int64_t fe = f.fr_end[b];
+  if (fe > f.samples_stride) fe = f.samples_stride;
+  if (j >= fe - fb) return false;
+  pos = fb + j;
+  id = f.samples[b * f.samples_stride + pos];
+  return true;
+}
+
+__device__ __forceinline__ int pt_owner(const PartFrontier& f, int64_t id) {
+  int64_t o = id / f.cols_per_rank;  // out-of-range ids go to the edge ranks, whose serve kernel reports them
+  if (id < 0) o = 0;
+  if (o >= f.world) o = f.world - 1;
+  return (int)o;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) part_count_kernel(const PartFrontier f, unsigned long long* counts,
+                                                               uint32_t* err) {
+  __shared__ unsigned int hist[PT_MAX_WORLD];
+  if (threadIdx.x < PT_MAX_WORLD) hist[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  int64_t b, pos, id;
+  if (t < f.B * f.capF && t % f.capF == 0) {  // first slot of a batch: the frontier must fit the launch geometry
+    const int64_t bb = t / f.capF;
+    if (f.fr_end[bb] - (f.fr_begin ? f.fr_begin[bb] : 0) > f.capF) atomicOr(err, DEV_ERR_CAPACITY);
+  }
+  if (pt_node(f, t, b, pos, id)) atomicAdd(&hist[pt_owner(f, id)], 1u);
+  __syncthreads();
+  if (threadIdx.x < f.world && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
+}
+
+__global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFrontier f, const unsigned long long* counts,
+                                                                 unsigned long long* cursor, int64_t* req) {
+  __shared__ unsigned int hist[PT_MAX_WORLD];
+  __shared__ unsigned long long base[PT_MAX_WORLD];
+  if (threadIdx.x < PT_MAX_WORLD) hist[threadIdx.x] = 0u;
+  __syncthreads();
+  const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  int64_t b = 0, pos = 0, id = 0;
+  const bool ok = pt_node(f, t, b, pos, id);
+  int o = 0;
+  unsigned int rank = 0;
+  if (ok) {
+    o = pt_owner(f, id);
+    rank = atomicAdd(&hist[o], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < f.world) {
+    unsigned long long off = 0;  // exclusive offset of this owner's group in the send buffer
+    for (int r = 0; r < threadIdx.x; ++r) off += counts[r];
+    const unsigned int h = hist[threadIdx.x];
+    base[threadIdx.x] = off + (h ? atomicAdd(cursor + threadIdx.x, (unsigned long long)h) : 0ull);
+  }
+  __syncthreads();
+  if (ok) {
+    const unsigned long long q = base[o] + rank;
+    const uint64_t meta = ((uint64_t)(f.batch_base + (uint32_t)b) << 32) | (uint64_t)(uint32_t)pos;
+    req[2 * q] = id;
+    req[2 * q + 1] = (int64_t)meta;
+  }
+}
+
+struct PartFinish {
+  const int64_t* req;      // [F, 2] the requests this rank sent (same order as the answers)
+  const int64_t* ans;      // [F, 2k] rows: k ids then k global csc positions, -1 padded
+  int64_t F;
+  int32_t k;
+  uint32_t batch_base;
+  const int64_t* fr_begin; // [B] or NULL
+  int64_t B, capF;
+  int32_t* fcnt;           // [B * capF + 1] answers per frontier node (padding = 0), then its exclusive scan in place
+  const int64_t* node_len_in;  // [B]
+  const int64_t* edge_len_in;  // [B]
+  int64_t* node_len_out;
+  int64_t* edge_len_out;
+  int64_t* samples; int64_t samples_stride;
+  int64_t* rows; int64_t* cols; int64_t* eidx; int64_t edges_stride;
+  uint32_t* err;
+};
+
+__global__ void __launch_bounds__(PT_THREADS) part_cnt_kernel(const PartFinish p) {
+  const int64_t q = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  if (q >= p.F) return;
+  const uint64_t meta = (uint64_t)p.req[2 * q + 1];
+  const int64_t b = (int64_t)(uint32_t)(meta >> 32) - (int64_t)p.batch_base;
+  const int64_t pos = (int64_t)(uint32_t)meta;
+  const int64_t j = pos - (p.fr_begin ? p.fr_begin[b] : 0);
+  const int64_t* a = p.ans + q * 2 * p.k + p.k;
+  int c = 0;
+  for (int s = 0; s < p.k; ++s) c += a[s] >= 0 ? 1 : 0;  // valid slots form a prefix
+  p.fcnt[b * p.capF + j] = c;
+}
+
+__global__ void __launch_bounds__(PT_THREADS) part_len_kernel(const PartFinish p) {
+  const int64_t b = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  if (b >= p.B) return;
+  const int64_t total = (int64_t)p.fcnt[(b + 1) * p.capF] - (int64_t)p.fcnt[b * p.capF];
+  const int64_t n = p.node_len_in[b] + total, e = p.edge_len_in[b] + total;
+  p.node_len_out[b] = n;
+  p.edge_len_out[b] = e;
+  if (n > p.samples_stride || e > p.edges_stride) atomicOr(p.err, DEV_ERR_CAPACITY);
+}
+
+__global__ void __launch_bounds__(PT_THREADS) part_emit_kernel(const PartFinish p) {
+  const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  if (t >= p.F * p.k) return;
+  const int64_t q = t / p.k;
+  const int s = (int)(t - q * p.k);
+  const int64_t gp = p.ans[q * 2 * p.k + p.k + s];
+  if (gp < 0) return;
+  const uint64_t meta = (uint64_t)p.req[2 * q + 1];
+  const int64_t b = (int64_t)(uint32_t)(meta >> 32) - (int64_t)p.batch_base;
+  const int64_t pos = (int64_t)(uint32_t)meta;
+  const int64_t j = pos - (p.fr_begin ? p.fr_begin[b] : 0);
+  const int64_t off = (int64_t)p.fcnt[b * p.capF + j] - (int64_t)p.fcnt[b * p.capF] + s;
+  const int64_t ni = p.node_len_in[b] + off, ei = p.edge_len_in[b] + off;
+  if (ni >= p.samples_stride || ei >= p.edges_stride) return;  // flagged by part_len_kernel
+  p.samples[b * p.samples_stride + ni] = p.ans[q * 2 * p.k + s];
+  p.rows[b * p.edges_stride + ei] = ni;     // index of the appended node, neighbor_sampling.rs:213-216
+  p.cols[b * p.edges_stride + ei] = pos;    // index of the frontier node
+  p.eidx[b * p.edges_stride + ei] = gp;     // global CSC position
+}
+
+}  // namespace
+}  // namespace tchgeo
+
+extern "C" tchgeo_status tchgeo_part_begin_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
+                                               const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
+                                               int64_t cols_per_rank, int32_t world, uint32_t batch_base,
+                                               int64_t* counts, int64_t* cursor, int64_t* req, int32_t* err_word,
+                                               tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(world >= 1 && world <= PT_MAX_WORLD, "world size must be in [1, 64]");
+  TCHGEO_REQUIRE(err_word != nullptr, "NULL pointer");
+  TCHGEO_REQUIRE(num_batches >= 0 && frontier_cap >= 0 && cols_per_rank >= 1 && samples_stride >= 0, "bad argument");
+  TCHGEO_REQUIRE(counts && cursor, "NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)world * 8, stream));
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)world * 8, stream));
+  const int64_t total = num_batches * frontier_cap;
+  if (total == 0) return TCHGEO_OK;
+  TCHGEO_REQUIRE(samples && fr_end && req, "NULL pointer");
+  const int64_t grid = (total + PT_THREADS - 1) / PT_THREADS;
+  TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "frontier too large for one launch");
+  PartFrontier f;
+  f.samples = samples; f.samples_stride = samples_stride; f.fr_begin = fr_begin; f.fr_end = fr_end;
+  f.B = num_batches; f.capF = frontier_cap; f.cols_per_rank = cols_per_rank; f.world = world; f.batch_base = batch_base;
+  part_count_kernel<<<(unsigned)grid, PT_THREADS, 0, stream>>>(f, (unsigned long long*)counts, (uint32_t*)err_word);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  part_scatter_kernel<<<(unsigned)grid, PT_THREADS, 0, stream>>>(f, (const unsigned long long*)counts,
+                                                                (unsigned long long*)cursor, req);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, const int64_t* indices_local,
+                                                    const double* weights_local, int64_t col_begin, int64_t ncols_local,
+                                                    int64_t edge_base, const int64_t* req, int64_t n, int64_t fanout,
+                                                    int32_t sampler_kind, uint64_t seed, uint32_t rel, int64_t* ans,
+                                                    int32_t* err_word, tchgeo_stream stream_) {
+  return serve_launch(ptrs_local, indices_local, weights_local, col_begin, ncols_local, edge_base, req, req ? req + 1 : req,
+                      2, n, fanout, sampler_kind, seed, rel, ans, ans ? ans + fanout : ans, 2 * fanout,
+                      (uint32_t*)err_word, (cudaStream_t)stream_);
+}
+
+extern "C" size_t tchgeo_part_finish_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap) {
+  const int64_t n = num_batches * frontier_cap + 1;
+  if (n <= 0 || n >= ((int64_t)1 << 31)) return 0;
+  size_t cub_bytes = 0;
+  if (cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, n) != cudaSuccess) return 0;
+  return 256 + ((size_t)n * 4 + 255) / 256 * 256 + (cub_bytes + 255) / 256 * 256;
+}
+
+extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int64_t* ans, int64_t num_requests,
+                                                int64_t fanout, uint32_t batch_base, const int64_t* fr_begin,
+                                                int64_t num_batches, int64_t frontier_cap, const int64_t* node_len_in,
+                                                const int64_t* edge_len_in, int64_t* node_len_out, int64_t* edge_len_out,
+                                                int64_t* samples, int64_t samples_stride, int64_t* rows, int64_t* cols,
+                                                int64_t* edge_index, int64_t edges_stride, int32_t* err_word,
+                                                void* workspace, size_t workspace_bytes, tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(num_requests >= 0 && fanout >= 0 && fanout < (1 << 20) && num_batches >= 0 && frontier_cap >= 0,
+                 "bad argument");
+  TCHGEO_REQUIRE(node_len_in && edge_len_in && node_len_out && edge_len_out && err_word, "NULL pointer");
+  const size_t need = tchgeo_part_finish_hop_workspace_bytes(num_batches, frontier_cap);
+  TCHGEO_REQUIRE(need != 0, "frontier too large for one call");
+  TCHGEO_REQUIRE(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes", need);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const int64_t n = num_batches * frontier_cap + 1;
+  int32_t* fcnt = (int32_t*)((char*)workspace + 256);
+  void* cub_tmp = (char*)fcnt + ((size_t)n * 4 + 255) / 256 * 256;
+  size_t cub_bytes = need - 256 - ((size_t)n * 4 + 255) / 256 * 256;
+  PartFinish p;
+  p.req = req; p.ans = ans; p.F = num_requests; p.k = (int32_t)fanout; p.batch_base = batch_base; p.fr_begin = fr_begin;
+  p.B = num_batches; p.capF = frontier_cap; p.fcnt = fcnt;
+  p.node_len_in = node_len_in; p.edge_len_in = edge_len_in; p.node_len_out = node_len_out; p.edge_len_out = edge_len_out;
+  p.samples = samples; p.samples_stride = samples_stride; p.rows = rows; p.cols = cols; p.eidx = edge_index;
+  p.edges_stride = edges_stride; p.err = (uint32_t*)err_word;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(fcnt, 0, (size_t)n * 4, stream));
+  if (num_requests > 0 && fanout > 0) {
+    TCHGEO_REQUIRE(req && ans && samples && rows && cols && edge_index, "NULL pointer");
+    part_cnt_kernel<<<(unsigned)((num_requests + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, stream>>>(p);
+    TCHGEO_CUDA_CHECK(cudaGetLastError());
+  }
+  TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, (const int32_t*)fcnt, fcnt, n, stream));
+  if (num_batches > 0) {
+    part_len_kernel<<<(unsigned)((num_batches + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, stream>>>(p);
+    TCHGEO_CUDA_CHECK(cudaGetLastError());
+  }
+  if (num_requests > 0 && fanout > 0) {
+    const int64_t total = num_requests * fanout;
+    TCHGEO_REQUIRE((total + PT_THREADS - 1) / PT_THREADS < ((int64_t)1 << 31), "too many answers for one launch");
+    part_emit_kernel<<<(unsigned)((total + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, stream>>>(p);
+    TCHGEO_CUDA_CHECK(cudaGetLastError());
+  }
+  return TCHGEO_OK;
 }

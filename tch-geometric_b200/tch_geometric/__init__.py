@@ -12,6 +12,7 @@ from .ops import (  # noqa: F401
     HeterogenousSampler,
     HomogenousSampler,
     SampledBatches,
+    clear_caches,
     csc_edge_cumsum,
     csc_sort_edges,
     ind2ptr,

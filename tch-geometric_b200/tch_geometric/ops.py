@@ -184,27 +184,67 @@ def _extract_filter(filter, hetero: bool):
 # invalidated by the tensor's version counter.  Measured on B200 (products-shaped graph, hop 3):
 # DRAM reads 6.28 GB -> 4.86 GB per launch, 2.24 ms -> 1.88 ms.  TCHGEO_INDEX_REPLICA=0 disables it.
 # ---------------------------------------------------------------------------------------------
-_replica_cache = {}
 _REPLICA_CACHE_MAX = 16
+
+
+class _DerivedCache:
+    """Derived device arrays (int32 replica, weight prefix sums) keyed by their source tensors' storage.  An entry
+    keeps a reference to its source tensors: the memory cannot be freed and handed to a different tensor at the same
+    address while the entry lives, so a hit can never be stale (in-place edits bump `_version` and miss).  LRU,
+    at most _REPLICA_CACHE_MAX entries; `clear_caches()` drops everything (and releases the sources)."""
+
+    def __init__(self):
+        self._d = {}
+
+    @staticmethod
+    def _key(srcs):
+        return tuple((t.data_ptr(), t.numel(), t.dtype, t.device.index) for t in srcs)
+
+    def get(self, srcs):
+        k = self._key(srcs)
+        hit = self._d.get(k)
+        if hit is not None and hit[0] == tuple(t._version for t in srcs):
+            self._d[k] = self._d.pop(k)  # most recently used last
+            return hit[2]
+        return None
+
+    def put(self, srcs, value):
+        k = self._key(srcs)
+        self._d.pop(k, None)
+        while len(self._d) >= _REPLICA_CACHE_MAX:
+            self._d.pop(next(iter(self._d)))
+        self._d[k] = (tuple(t._version for t in srcs), tuple(srcs), value)
+
+    def clear(self):
+        self._d.clear()
+
+
+_MISSING = object()
+_replica_cache = _DerivedCache()
+_cumsum_cache = _DerivedCache()
+
+
+def clear_caches() -> None:
+    """Drop the cached int32 index replicas and weight prefix sums (they keep their source tensors alive)."""
+    _replica_cache.clear()
+    _cumsum_cache.clear()
 
 
 def _compressed_indices(t: Optional[Tensor]) -> Optional[Tensor]:
     if t is None or t.numel() == 0 or os.environ.get("TCHGEO_INDEX_REPLICA", "1") == "0":
         return None
-    key = (t.data_ptr(), t.numel(), t.device.index)
-    hit = _replica_cache.get(key)
-    if hit is not None and hit[0] == t._version:
-        return hit[1]
+    hit = _replica_cache.get((t,))
+    if hit is not None:
+        return None if hit is _MISSING else hit
     out = torch.empty(t.numel(), dtype=torch.int32, device=t.device)
     scratch = torch.empty(1, dtype=torch.int32, device=t.device)
     with torch.cuda.device(t.device):
         st = N.lib.tchgeo_compress_indices(_ptr(t), t.numel(), _ptr(out), _ptr(scratch), _stream(t.device))
     if st == N.ERR_INDEX:
+        _replica_cache.put((t,), _MISSING)
         return None  # ids beyond int32 (or negative): sample from the i64 array; the kernel reports bad ids
     N.check(st)
-    if len(_replica_cache) >= _REPLICA_CACHE_MAX:
-        _replica_cache.pop(next(iter(_replica_cache)))
-    _replica_cache[key] = (t._version, out)
+    _replica_cache.put((t,), out)
     return out
 
 
@@ -241,25 +281,18 @@ def csc_sort_edges(col_ptrs: Tensor, perm: Tensor, row_weights: Tensor, descendi
     return out
 
 
-_cumsum_cache = {}
-
-
 def _weights_cumsum(col_ptrs: Tensor, weights: Optional[Tensor]) -> Optional[Tensor]:
     """Serial per-column prefix sums of the sampler weights (= the reference's w_sum sequence), cached per
     (col_ptrs, weights) pair like the int32 replica.  TCHGEO_WEIGHT_CUMSUM=0 disables it (the kernel then scans
     the weights with warp shuffles, which rounds differently for weights that are not exactly summable)."""
     if weights is None or weights.numel() == 0 or os.environ.get("TCHGEO_WEIGHT_CUMSUM", "1") == "0":
         return None
-    key = (col_ptrs.data_ptr(), col_ptrs.numel(), weights.data_ptr(), weights.numel(), weights.device.index)
-    ver = (col_ptrs._version, weights._version)
-    hit = _cumsum_cache.get(key)
-    if hit is not None and hit[0] == ver:
-        return hit[1]
+    hit = _cumsum_cache.get((col_ptrs, weights))
+    if hit is not None:
+        return hit
     out = weights.clone()
     csc_edge_cumsum(col_ptrs, out)
-    if len(_cumsum_cache) >= _REPLICA_CACHE_MAX:
-        _cumsum_cache.pop(next(iter(_cumsum_cache)))
-    _cumsum_cache[key] = (ver, out)
+    _cumsum_cache.put((col_ptrs, weights), out)
     return out
 
 

@@ -11,12 +11,20 @@ Because the counters depend only on (seed, batch, position, degree), the result 
 `neighbor_sampling_homogenous` result bit for bit, whatever the partitioning.
 
 The reference has no counterpart (it is single-process); the tree layout produced here is the one of
-src/algo/neighbor_sampling.rs:162-230.  Host orchestration uses torch ops for the bucketing and the
-compaction (plumbing); the sampling itself runs in the serve kernel.
+src/algo/neighbor_sampling.rs:162-230.
+
+Two drivers share the partition, the communicator and the serve kernel:
+  * PartitionedPlan    -- the product path: bucketing, owner side and the tree layout all run in CUDA kernels
+                          (tchgeo_part_begin_hop / tchgeo_serve_requests_rows / tchgeo_part_finish_hop); per hop the
+                          host only reads the per-owner request counts that size the all-to-all.  Outputs live in the
+                          same padded [B, capacity] buffers as the replicated sampler (SampledBatches).
+  * PartitionedSampler -- the same protocol written with torch ops; device-agnostic, so the 2-rank gloo tests run
+                          it on the CPU with the oracle as the owner, and the GPU tests use it as a cross-check.
 """
 import ctypes
 from typing import List, Optional, Sequence, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 from torch import Tensor
@@ -63,6 +71,14 @@ class SingleComm:
     def exchange(self, send_counts: Tensor, *tensors):
         return (send_counts,) + tuple(tensors)
 
+    def exchange_rows(self, send_counts: Tensor, rows: Tensor):
+        """-> (recv_counts list, send_counts list, received rows); reads the counts on the host (one sync)"""
+        sc = send_counts.tolist()
+        return sc, sc, rows
+
+    def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts):
+        return rows
+
 
 class DistComm:
     """all-to-all(v) over a torch.distributed group (NCCL on GPUs, gloo in the CPU tests)."""
@@ -81,6 +97,23 @@ class DistComm:
             dist.all_to_all_single(out, t.contiguous(), output_split_sizes=rc, input_split_sizes=sc, group=self.group)
             outs.append(out)
         return (recv_counts,) + tuple(outs)
+
+    def exchange_rows(self, send_counts: Tensor, rows: Tensor):
+        """Requests: all-to-all of the per-owner counts, one host read of both count vectors, all-to-all(v) of the rows."""
+        both = torch.empty((2, self.world), dtype=send_counts.dtype, device=send_counts.device)
+        both[0].copy_(send_counts)
+        dist.all_to_all_single(both[1], both[0], group=self.group)
+        sc, rc = both.tolist()
+        out = torch.empty((max(sum(rc), 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        dist.all_to_all_single(out[:sum(rc)], rows[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+        return rc, sc, out
+
+    def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts):
+        """Answers travel the reverse way: what was received is sent back, split sizes swapped."""
+        out = torch.empty((max(n_back, 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        dist.all_to_all_single(out[:n_back], rows[:n_rows], output_split_sizes=list(send_counts),
+                               input_split_sizes=list(recv_counts), group=self.group)
+        return out
 
 
 def cuda_serve(part: ColumnPartition, req_ids: Tensor, req_meta: Tensor, fanout: int, kind: int, seed: int, rel: int = 0):
@@ -192,3 +225,122 @@ class PartitionedSampler:
             out.append((torch.cat(parts_s), rows_all[:e_b], torch.cat(parts_c) if parts_c else empty,
                         torch.cat(parts_e) if parts_e else empty, lo))
         return out
+
+
+def serve_rows(part: ColumnPartition, req: Tensor, n: int, fanout: int, kind: int, seed: int, ans: Tensor, err: Tensor,
+               rel: int = 0):
+    """Owner side on interleaved rows (asynchronous): req [n,2] -> ans [n, 2*fanout]; errors are OR-ed into `err`."""
+    dev = part.ptrs.device
+    with torch.cuda.device(dev):
+        N.check(N.lib.tchgeo_serve_requests_rows(_ptr(part.ptrs), _ptr(part.indices), _ptr(part.weights), part.col_begin,
+                                                 part.col_end - part.col_begin, part.edge_base, _ptr(req), int(n),
+                                                 int(fanout), kind, seed, rel, _ptr(ans), _ptr(err), _stream(dev)))
+
+
+class PartitionedBatches:
+    """Result of PartitionedPlan.sample: B reference-layout results in padded [B, capacity] buffers (same access
+    pattern as ops.SampledBatches)."""
+
+    def __init__(self, plan, node_len, edge_len):
+        self.samples, self.rows, self.cols, self.edge_index = plan.samples, plan.rows, plan.cols, plan.eidx
+        self._H = len(plan.fanouts)
+        self._node_len, self._edge_len = node_len, edge_len         # host [H+1, B]
+        self.samples_len, self.edges_len = node_len[-1], edge_len[-1]
+
+    def __len__(self):
+        return self.samples.shape[0]
+
+    @property
+    def layer_offsets(self):
+        """[B, H, 3]: LayerOffset(len(samples), len(edges), len(samples)) at the start of every hop"""
+        nl, el = self._node_len[:-1].T, self._edge_len[:-1].T
+        return np.stack([nl, el, nl], axis=2)
+
+    def batch(self, b):
+        ns, ne = int(self.samples_len[b]), int(self.edges_len[b])
+        lo = [(int(self._node_len[h, b]), int(self._edge_len[h, b]), int(self._node_len[h, b])) for h in range(self._H)]
+        return self.samples[b, :ns], self.rows[b, :ne], self.cols[b, :ne], self.edge_index[b, :ne], lo
+
+
+class PartitionedPlan:
+    """neighbor_sampling_homogenous over a column-partitioned CSC, device pipeline.  `sample` is collective."""
+
+    def __init__(self, part: ColumnPartition, num_batches: int, seeds_per_batch: int, num_neighbors: Sequence[int],
+                 sampler=None, comm=None, serve_rows=None):
+        """serve_rows(r_req [n,2], recv_counts, fanout, seed, ans [n,2k]) overrides the owner side (tests simulate
+        several owners on one GPU with it); default: tchgeo_serve_requests_rows over `part`."""
+        self.part = part
+        self.serve_rows = serve_rows
+        self.fanouts = [int(k) for k in num_neighbors]
+        self.kind, _ = _extract_sampler(sampler, hetero=False)
+        if self.kind == N.SAMPLER_WEIGHTED and part.weights is None:
+            raise ValueError("weighted sampling needs ColumnPartition.weights_local")
+        self.comm = comm if comm is not None else (DistComm() if dist.is_available() and dist.is_initialized() else SingleComm())
+        _check(part.ptrs, torch.int64, "col_ptrs_local")
+        dev = part.ptrs.device
+        _check(part.indices, torch.int64, "row_indices_local", dev)
+        self.device, self.B, self.S = dev, int(num_batches), int(seeds_per_batch)
+        B, S, H = self.B, self.S, len(self.fanouts)
+        # worst-case frontier / output sizes per batch (the recurrence of tchgeo_neighbor_sampling_capacity)
+        self.capF, cap_e, f = [], 0, S
+        for k in self.fanouts:
+            self.capF.append(f)
+            f *= k
+            cap_e += f
+        self.cap_n, self.cap_e = S + cap_e, max(cap_e, 1)
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.samples = torch.empty((B, self.cap_n), **i64)
+        self.rows = torch.empty((B, self.cap_e), **i64)
+        self.cols = torch.empty((B, self.cap_e), **i64)
+        self.eidx = torch.empty((B, self.cap_e), **i64)
+        self.lens = torch.zeros((2, H + 1, B), **i64)               # [0] node_len, [1] edge_len after h hops
+        self.counts = torch.zeros((2, max(self.comm.world, 1)), **i64)  # [0] per-owner request counts, [1] cursor
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        fmax = max(self.capF) if self.capF else 0
+        self.req = torch.empty((max(B * fmax, 1), 2), **i64)
+        ws = max((N.lib.tchgeo_part_finish_hop_workspace_bytes(B, c) for c in self.capF), default=0)
+        if self.capF and ws == 0:
+            raise ValueError("frontier too large for one call: use fewer batches per call")
+        self.ws = torch.empty(max(int(ws), 1), dtype=torch.uint8, device=dev)
+        self.stats = {"requests_sent": 0, "request_bytes": 0, "answer_bytes": 0}
+
+    def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> PartitionedBatches:
+        """inputs [B, S] i64 (this rank's batches; device or pinned host) -> PartitionedBatches"""
+        if inputs.dim() != 2 or inputs.dtype != torch.int64 or tuple(inputs.shape) != (self.B, self.S):
+            raise ValueError(f"inputs must be an int64 tensor of shape {(self.B, self.S)}")
+        seed = _rng_get() if seed is None else seed
+        dev, B, S, part, comm, lib = self.device, self.B, self.S, self.part, self.comm, N.lib
+        world = comm.world
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            self.samples[:, :S].copy_(inputs, non_blocking=True)
+            self.err.zero_()
+            self.lens.zero_()
+            self.lens[0, 0].fill_(S)
+            for h, k in enumerate(self.fanouts):
+                fr_begin = self.lens[0, h - 1] if h > 0 else None
+                N.check(lib.tchgeo_part_begin_hop(_ptr(self.samples), self.cap_n, _ptr(fr_begin), _ptr(self.lens[0, h]), B,
+                                                  self.capF[h], part.cols_per_rank, world, batch_base,
+                                                  _ptr(self.counts[0]), _ptr(self.counts[1]), _ptr(self.req),
+                                                  _ptr(self.err), stream))
+                recv_counts, send_counts, r_req = comm.exchange_rows(self.counts[0], self.req)
+                F, n_recv = sum(send_counts), sum(recv_counts)
+                ans = torch.empty((max(n_recv, 1), 2 * k), dtype=torch.int64, device=dev)
+                if self.serve_rows is not None:
+                    self.serve_rows(r_req, recv_counts, k, seed, ans)
+                else:
+                    serve_rows(part, r_req, n_recv, k, self.kind, seed, ans, self.err)
+                back = comm.return_rows(ans, n_recv, F, send_counts, recv_counts)
+                N.check(lib.tchgeo_part_finish_hop(_ptr(self.req), _ptr(back), F, k, batch_base, _ptr(fr_begin), B,
+                                                   self.capF[h], _ptr(self.lens[0, h]), _ptr(self.lens[1, h]),
+                                                   _ptr(self.lens[0, h + 1]), _ptr(self.lens[1, h + 1]),
+                                                   _ptr(self.samples), self.cap_n, _ptr(self.rows), _ptr(self.cols),
+                                                   _ptr(self.eidx), self.cap_e, _ptr(self.err), _ptr(self.ws),
+                                                   self.ws.numel(), stream))
+                self.stats["requests_sent"] += F
+                self.stats["request_bytes"] += 16 * F
+                self.stats["answer_bytes"] += 16 * k * F
+            host = torch.cat([self.lens.reshape(-1), self.err.to(torch.int64)]).cpu().numpy()   # the call's last sync
+        N.check(lib.tchgeo_status_from_error_word(int(host[-1]) & 0xFFFFFFFF))
+        lens = host[:-1].reshape(2, len(self.fanouts) + 1, B)
+        return PartitionedBatches(self, lens[0], lens[1])

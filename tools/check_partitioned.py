@@ -18,7 +18,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import tch_geometric as thg  # noqa: E402
-from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedSampler  # noqa: E402
+from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedPlan, PartitionedSampler  # noqa: E402
 from tools import synth  # noqa: E402
 
 
@@ -46,11 +46,24 @@ def main():
         ok &= all(torch.equal(g, x) for g, x in zip(got[b][:4], want.batch(b)[:4]))
         ok &= list(got[b][4]) == list(want.batch(b)[4])
     edges = sum(int(g[1].numel()) for g in got)
+    # the device pipeline (what bench.py --workload partitioned times)
+    plan = PartitionedPlan(part, B, S, fan, comm=DistComm())
+    res = plan.sample(seeds, seed=31, batch_base=rank * B)
+    ok_plan = bool((res.layer_offsets == want.layer_offsets).all())
+    for b in range(B):
+        ok_plan &= all(torch.equal(g, x) for g, x in zip(res.batch(b)[:4], want.batch(b)[:4]))
+    ok &= ok_plan
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for it in range(args.iters):
         ps.sample(seeds, seed=100 + it, batch_base=rank * B)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt_torch = (time.perf_counter() - t0) / args.iters
+    t0 = time.perf_counter()
+    for it in range(args.iters):
+        plan.sample(seeds, seed=100 + it, batch_base=rank * B)
     torch.cuda.synchronize()
     dist.barrier()
     dt = (time.perf_counter() - t0) / args.iters
@@ -60,6 +73,7 @@ def main():
         print(json.dumps({"check": "partitioned == replicated (bit-exact)", "ranks_ok": int(flag[0].item()), "world": world,
                           "graph": {"nodes": n, "edges": int(idx.numel())}, "batches_per_rank": B,
                           "edges_per_call_all_ranks": flag[1].item(), "sec_per_call": dt,
+                          "sec_per_call_torch_orchestration": dt_torch,
                           "edges_per_sec": flag[1].item() / dt, "request_bytes": ps.stats["request_bytes"],
                           "answer_bytes": ps.stats["answer_bytes"]}), flush=True)
     dist.destroy_process_group()
