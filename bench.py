@@ -582,6 +582,68 @@ def run_negative(args):
           "cpu_baseline": cpu, "e2e": None, "gpu_launches": K * 12, "clocks": clk})
 
 
+def run_gather(args):
+    """x[samples] for the samples of one sampling step (products-shaped graph, 100 f32 features)."""
+    import tch_geometric as thg
+    rank, world, local = dist_env()
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    ei, n = build_graph(device, args.scale)
+    ptrs, idx, _ = thg.to_csc(ei, n)
+    del ei
+    torch.cuda.empty_cache()
+    D, B, S, K, W = 100, min(args.batches, 32), SEEDS_PER_BATCH, args.steps, args.warmup
+    x = torch.randn(n, D, device=device)
+    plan = thg.HomogenousSampler(ptrs, idx, B, S, FANOUTS)
+    index = []
+    for s in range(W + K):  # every step gathers the samples of a different sampling step (inputs differ every step)
+        res = plan.sample(torch.from_numpy(synth.seed_batches(n, B, S, first_batch=s * B)).to(device), seed=s)
+        index.append(torch.cat([res.samples[b, :int(res.samples_len[b])] for b in range(B)]))
+    for s in range(W):
+        thg.gather_rows(x, index[s])
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    rows = 0
+    e0.record()
+    for s in range(W, W + K):
+        out = thg.gather_rows(x, index[s])
+        rows += out.shape[0]
+    e1.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    ms = e0.elapsed_time(e1)
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for s in range(W, W + K):
+        ref = x[index[s]]
+    t1.record()
+    torch.cuda.synchronize()
+    assert torch.equal(ref, out)
+    alg = rows * (8 + 2 * D * 4)
+    peak, peak_src = measured_peak_gbs()
+    cpu = None
+    if not args.no_cpu:
+        hx, hi = x.cpu().numpy(), index[W][:2_000_000].cpu().numpy()
+        t = time.perf_counter()
+        _ = hx[hi]
+        dt = time.perf_counter() - t
+        cpu = {"value": hi.size / dt, "unit": "rows/s", "cores": 1, "kind": "port",
+               "sample": f"numpy fancy indexing of {hi.size} rows x {D} f32 ({dt:.2f} s)"}
+    emit({"metric": "gathered_feature_rows_per_sec", "value": rows / (ms * 1e-3), "unit": "rows/s", "n_gpus": 1, "steps": K,
+          "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32 rows (byte copy)", "data": "synthetic",
+          "config": {"workload": f"x[samples]: x = [{n}, {D}] f32, index = samples of {B} batches of the 3-hop {FANOUTS} "
+                                 f"sampling step ({rows // K} rows per step)",
+                     "l2_policy": "x is 980 MB, output 2 x larger than L2; a different index every step"},
+          "roofline": {"bound": "hbm", "kernel": "gather_rows_kernel<uint4>", "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak,
+                       "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                       "algorithmic_bytes_per_row": 8 + 2 * D * 4},
+          "torch_index_ms_per_step": t0.elapsed_time(t1) / K,
+          "cpu_baseline": cpu, "e2e": None, "gpu_launches": K, "clocks": clk})
+
+
 def run_hetero(args):
     """configs[3]: ogbn-mag-shaped heterogeneous sampling, fanouts [10,10] per relation, 1024 paper seeds."""
     import tch_geometric as thg
@@ -716,6 +778,10 @@ def run_partitioned(args):
     e1.record()
     torch.cuda.synchronize()
     clk = clocks.stop()
+    ps.profile = {}   # untimed extra pass: device time per phase (CUDA events between the phases)
+    for s in range(W, W + K):
+        ps.sample(seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
+    phases = {k: v / ps.profile["calls"] for k, v in ps.profile.items() if k != "calls"}
     ms, edges_all = reduce_job(e0.elapsed_time(e1), float(edges_n), device)
     if rank == 0:
         emit({"metric": "sampled_edges_per_sec_3hop_15_10_5_partitioned_csc", "value": edges_all / (ms * 1e-3),
@@ -725,8 +791,9 @@ def run_partitioned(args):
                                      f"CSC range-partitioned over {world} rank(s), fanouts {FANOUTS}, {S} seeds/batch, "
                                      f"{B} batches/step/rank, NCCL all-to-all frontier exchange per hop",
                          "parallelism": "column-range partition + all-to-all(v) of requests and answers"},
-              "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + K),
-                                                   "answers": ps.stats["answer_bytes"] // (W + K)},
+              "phase_ms_per_step_rank0": phases,
+              "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + 2 * K),
+                                                   "answers": ps.stats["answer_bytes"] // (W + 2 * K)},
               "cpu_baseline": None, "e2e": None, "gpu_launches": K * len(FANOUTS) * 8, "clocks": clk})
     if world > 1:
         dist.destroy_process_group()
@@ -738,7 +805,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned", "negative"],
+    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned", "negative", "gather"],
                     help="sampling = headline (configs[1]); walk = configs[2]; hetero = configs[3]")
     ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
@@ -760,6 +827,8 @@ def main():
         run_partitioned(args)
     elif args.workload == "negative":
         run_negative(args)
+    elif args.workload == "gather":
+        run_gather(args)
     else:
         run_ours(args)
 

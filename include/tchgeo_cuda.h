@@ -244,8 +244,9 @@ TCHGEO_API tchgeo_status tchgeo_serve_requests(
  *                           counts[world] and scatter request rows (id, (batch_base+b) << 32 | pos) into `req`
  *                           grouped by owner (order inside a group is arbitrary); asynchronous
  *   -- exchange counts, then the request rows, with an all-to-all (NCCL; the host reads the counts once) --
- *   tchgeo_serve_requests_rows  owner side on interleaved rows: req [n,2] -> ans [n, 2*fanout] = fanout ids then
- *                           fanout global CSC positions per row, -1 padded; asynchronous
+ *   tchgeo_serve_requests_rows  owner side on interleaved rows: req [n,2] -> compact int32 ans [n, 2*fanout] = fanout
+ *                           neighbour ids then fanout LOCAL CSC positions per row, -1 padded (half the exchange
+ *                           bytes; needs node ids and a rank's CSC share below 2^31); asynchronous
  *   -- all-to-all of the answer rows back --
  *   tchgeo_part_finish_hop  per-node answer counts, exclusive scan in frontier order, then the tree layout of
  *                           src/algo/neighbor_sampling.rs:210-218 appended to the caller's [B, stride] buffers at
@@ -263,13 +264,15 @@ TCHGEO_API tchgeo_status tchgeo_part_begin_hop(const int64_t* samples /*DEVICE [
                                                tchgeo_stream stream);
 TCHGEO_API tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, const int64_t* indices_local,
                                                     const double* weights_local, int64_t col_begin, int64_t ncols_local,
-                                                    int64_t edge_base, const int64_t* req /*DEVICE [n,2]*/, int64_t n,
+                                                    int64_t nnz_local, const int64_t* req /*DEVICE [n,2]*/, int64_t n,
                                                     int64_t fanout, int32_t sampler_kind, uint64_t seed, uint32_t rel,
-                                                    int64_t* ans /*DEVICE [n, 2*fanout]*/, int32_t* err_word,
+                                                    int32_t* ans /*DEVICE [n, 2*fanout] int32*/, int32_t* err_word,
                                                     tchgeo_stream stream);
 TCHGEO_API size_t tchgeo_part_finish_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap);
-TCHGEO_API tchgeo_status tchgeo_part_finish_hop(const int64_t* req /*DEVICE [F,2] as sent*/, const int64_t* ans /*DEVICE [F, 2*fanout]*/,
-                                                int64_t num_requests, int64_t fanout, uint32_t batch_base,
+TCHGEO_API tchgeo_status tchgeo_part_finish_hop(const int64_t* req /*DEVICE [F,2] as sent*/, const int32_t* ans /*DEVICE [F, 2*fanout]*/,
+                                                int64_t num_requests, int64_t fanout,
+                                                const int64_t* owner_edge_base /*DEVICE [world]*/, int64_t cols_per_rank,
+                                                int32_t world, uint32_t batch_base,
                                                 const int64_t* fr_begin, int64_t num_batches, int64_t frontier_cap,
                                                 const int64_t* node_len_in /*DEVICE [B]*/, const int64_t* edge_len_in,
                                                 int64_t* node_len_out, int64_t* edge_len_out, int64_t* samples,
@@ -341,6 +344,16 @@ TCHGEO_API tchgeo_status tchgeo_negative_sampling_capacity(const tchgeo_negative
 TCHGEO_API size_t tchgeo_negative_sampling_workspace_bytes(const tchgeo_negative_args* args);
 /* Synchronises args->stream (lengths are returned to the host). */
 TCHGEO_API tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* args);
+
+/* -------------------------------------------------------------------------------------------- */
+/* Row gather: dst[i, :] = src[index[i], :] for rows of row_bytes bytes of any     */
+/* dtype.  The step after the sampler in every loader (x[samples], edge_attr[perm[edge_index]];      */
+/* examples/neighbor_sampling.py:21-24).  TCHGEO_ERR_INDEX for an index outside [0, num_rows).       */
+/* -------------------------------------------------------------------------------------------- */
+TCHGEO_API tchgeo_status tchgeo_gather_rows(const void* src /*DEVICE [num_rows, row_bytes]*/, int64_t num_rows,
+                                            int64_t row_bytes, const int64_t* index /*DEVICE [n]*/, int64_t n,
+                                            void* dst /*DEVICE [n, row_bytes]*/, int32_t* scratch /*DEVICE [1]*/,
+                                            tchgeo_stream stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* Dedup + insertion-order relabel of one sampled tree (additive stage).                          */

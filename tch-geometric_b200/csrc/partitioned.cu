@@ -32,6 +32,7 @@ struct ServeParams {
   int64_t* out_ids;
   int64_t* out_ptrs;
   int64_t out_stride;       // elements between consecutive answer rows (fanout, or 2*fanout for [n][ids | ptrs] rows)
+  int32_t* out32;           // compact rows instead: [n][fanout ids | fanout LOCAL csc positions] as int32, -1 padded
   uint32_t* err;
   int64_t col_begin, ncols, edge_base, n;
   int32_t fanout, tile_reqs;
@@ -166,8 +167,14 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
       id = ld_gather64_i64(p.indices + lp);
       gp = p.edge_base + lp;
     }
-    st_cs_i64(p.out_ids + (r0 + n) * p.out_stride + s, id);
-    st_cs_i64(p.out_ptrs + (r0 + n) * p.out_stride + s, gp);
+    if (p.out32) {
+      int32_t* row = p.out32 + (r0 + n) * 2 * (int64_t)k;
+      row[s] = (int32_t)id;
+      row[k + s] = gp < 0 ? -1 : (int32_t)(gp - p.edge_base);
+    } else {
+      st_cs_i64(p.out_ids + (r0 + n) * p.out_stride + s, id);
+      st_cs_i64(p.out_ptrs + (r0 + n) * p.out_stride + s, gp);
+    }
   }
 }
 
@@ -180,16 +187,16 @@ static tchgeo_status serve_launch(const int64_t* ptrs_local, const int64_t* indi
                                   int64_t col_begin, int64_t ncols_local, int64_t edge_base, const int64_t* req_ids,
                                   const int64_t* req_meta, int64_t req_stride, int64_t n, int64_t fanout,
                                   int32_t sampler_kind, uint64_t seed, uint32_t rel, int64_t* out_ids, int64_t* out_ptrs,
-                                  int64_t out_stride, uint32_t* err, cudaStream_t stream) {
+                                  int64_t out_stride, int32_t* out32, uint32_t* err, cudaStream_t stream) {
   TCHGEO_REQUIRE(n >= 0 && fanout >= 0 && fanout <= SV_MAX_TILE_SLOTS && ncols_local >= 0, "bad serve argument");
   TCHGEO_REQUIRE(sampler_kind >= 0 && sampler_kind <= 2 && err != nullptr, "bad serve argument");
   TCHGEO_REQUIRE(sampler_kind != TCHGEO_SAMPLER_WEIGHTED || weights_local != nullptr, "weighted serve without weights");
   if (n == 0 || fanout == 0) return TCHGEO_OK;
-  TCHGEO_REQUIRE(ptrs_local && req_ids && req_meta && out_ids && out_ptrs, "NULL pointer");
+  TCHGEO_REQUIRE(ptrs_local && req_ids && req_meta && (out32 || (out_ids && out_ptrs)), "NULL pointer");
   ServeParams sp;
   sp.ptrs = ptrs_local; sp.indices = indices_local; sp.weights = weights_local;
   sp.req_ids = req_ids; sp.req_meta = req_meta; sp.req_stride = req_stride;
-  sp.out_ids = out_ids; sp.out_ptrs = out_ptrs; sp.out_stride = out_stride;
+  sp.out_ids = out_ids; sp.out_ptrs = out_ptrs; sp.out_stride = out_stride; sp.out32 = out32;
   sp.err = err;
   sp.col_begin = col_begin; sp.ncols = ncols_local; sp.edge_base = edge_base; sp.n = n;
   sp.fanout = (int32_t)fanout;
@@ -218,7 +225,7 @@ extern "C" tchgeo_status tchgeo_serve_requests(const int64_t* ptrs_local, const 
   TCHGEO_CUDA_CHECK(cudaMemsetAsync(err_scratch, 0, 4, stream));
   const tchgeo_status st = serve_launch(ptrs_local, indices_local, weights_local, col_begin, ncols_local, edge_base,
                                         req_ids, req_meta, 1, n, fanout, sampler_kind, seed, rel, out_ids, out_ptrs,
-                                        fanout, (uint32_t*)err_scratch, stream);
+                                        fanout, nullptr, (uint32_t*)err_scratch, stream);
   if (st != TCHGEO_OK) return st;
   uint32_t herr = 0;
   TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&herr, err_scratch, 4, cudaMemcpyDeviceToHost, stream));
@@ -273,18 +280,32 @@ __device__ __forceinline__ int pt_owner(const PartFrontier& f, int64_t id) {
   return (int)o;
 }
 
+// warp-aggregated histogram update: lanes with the same owner elect a leader that adds the group's size once;
+// returns this lane's rank inside its owner's bucket of the CTA (frontiers of few owners would otherwise
+// serialise 256 shared-memory atomics on one or two addresses)
+__device__ __forceinline__ unsigned int pt_hist_add(unsigned int* hist, bool ok, int owner) {
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned m = __match_any_sync(0xffffffffu, ok ? owner : -1);
+  const int leader = __ffs(m) - 1;
+  unsigned int base = 0;
+  if (ok && (int)lane == leader) base = atomicAdd(&hist[owner], (unsigned int)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  return base + (unsigned int)__popc(m & ((1u << lane) - 1u));
+}
+
 __global__ void __launch_bounds__(PT_THREADS) part_count_kernel(const PartFrontier f, unsigned long long* counts,
                                                                uint32_t* err) {
   __shared__ unsigned int hist[PT_MAX_WORLD];
   if (threadIdx.x < PT_MAX_WORLD) hist[threadIdx.x] = 0u;
   __syncthreads();
   const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
-  int64_t b, pos, id;
+  int64_t b, pos, id = 0;
   if (t < f.B * f.capF && t % f.capF == 0) {  // first slot of a batch: the frontier must fit the launch geometry
     const int64_t bb = t / f.capF;
     if (f.fr_end[bb] - (f.fr_begin ? f.fr_begin[bb] : 0) > f.capF) atomicOr(err, DEV_ERR_CAPACITY);
   }
-  if (pt_node(f, t, b, pos, id)) atomicAdd(&hist[pt_owner(f, id)], 1u);
+  const bool ok = pt_node(f, t, b, pos, id);
+  pt_hist_add(hist, ok, ok ? pt_owner(f, id) : 0);
   __syncthreads();
   if (threadIdx.x < f.world && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
 }
@@ -298,12 +319,8 @@ __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFron
   const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
   int64_t b = 0, pos = 0, id = 0;
   const bool ok = pt_node(f, t, b, pos, id);
-  int o = 0;
-  unsigned int rank = 0;
-  if (ok) {
-    o = pt_owner(f, id);
-    rank = atomicAdd(&hist[o], 1u);
-  }
+  const int o = ok ? pt_owner(f, id) : 0;
+  const unsigned int rank = pt_hist_add(hist, ok, o);
   __syncthreads();
   if (threadIdx.x < f.world) {
     unsigned long long off = 0;  // exclusive offset of this owner's group in the send buffer
@@ -315,14 +332,16 @@ __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFron
   if (ok) {
     const unsigned long long q = base[o] + rank;
     const uint64_t meta = ((uint64_t)(f.batch_base + (uint32_t)b) << 32) | (uint64_t)(uint32_t)pos;
-    req[2 * q] = id;
-    req[2 * q + 1] = (int64_t)meta;
+    *reinterpret_cast<longlong2*>(req + 2 * q) = make_longlong2((long long)id, (long long)meta);
   }
 }
 
 struct PartFinish {
   const int64_t* req;      // [F, 2] the requests this rank sent (same order as the answers)
-  const int64_t* ans;      // [F, 2k] rows: k ids then k global csc positions, -1 padded
+  const int32_t* ans;      // [F, 2k] int32 rows: k ids then k LOCAL csc positions of the owner, -1 padded
+  const int64_t* edge_base;  // [world] CSC entries owned by lower ranks: global position = edge_base[owner] + local
+  int64_t cols_per_rank;
+  int32_t world;
   int64_t F;
   int32_t k;
   uint32_t batch_base;
@@ -345,7 +364,7 @@ __global__ void __launch_bounds__(PT_THREADS) part_cnt_kernel(const PartFinish p
   const int64_t b = (int64_t)(uint32_t)(meta >> 32) - (int64_t)p.batch_base;
   const int64_t pos = (int64_t)(uint32_t)meta;
   const int64_t j = pos - (p.fr_begin ? p.fr_begin[b] : 0);
-  const int64_t* a = p.ans + q * 2 * p.k + p.k;
+  const int32_t* a = p.ans + q * 2 * p.k + p.k;
   int c = 0;
   for (int s = 0; s < p.k; ++s) c += a[s] >= 0 ? 1 : 0;  // valid slots form a prefix
   p.fcnt[b * p.capF + j] = c;
@@ -366,8 +385,8 @@ __global__ void __launch_bounds__(PT_THREADS) part_emit_kernel(const PartFinish 
   if (t >= p.F * p.k) return;
   const int64_t q = t / p.k;
   const int s = (int)(t - q * p.k);
-  const int64_t gp = p.ans[q * 2 * p.k + p.k + s];
-  if (gp < 0) return;
+  const int32_t lp = p.ans[q * 2 * p.k + p.k + s];
+  if (lp < 0) return;
   const uint64_t meta = (uint64_t)p.req[2 * q + 1];
   const int64_t b = (int64_t)(uint32_t)(meta >> 32) - (int64_t)p.batch_base;
   const int64_t pos = (int64_t)(uint32_t)meta;
@@ -375,10 +394,13 @@ __global__ void __launch_bounds__(PT_THREADS) part_emit_kernel(const PartFinish 
   const int64_t off = (int64_t)p.fcnt[b * p.capF + j] - (int64_t)p.fcnt[b * p.capF] + s;
   const int64_t ni = p.node_len_in[b] + off, ei = p.edge_len_in[b] + off;
   if (ni >= p.samples_stride || ei >= p.edges_stride) return;  // flagged by part_len_kernel
-  p.samples[b * p.samples_stride + ni] = p.ans[q * 2 * p.k + s];
+  int64_t owner = p.req[2 * q] / p.cols_per_rank;  // same rule as pt_owner
+  if (owner < 0) owner = 0;
+  if (owner >= p.world) owner = p.world - 1;
+  p.samples[b * p.samples_stride + ni] = (int64_t)p.ans[q * 2 * p.k + s];
   p.rows[b * p.edges_stride + ei] = ni;     // index of the appended node, neighbor_sampling.rs:213-216
   p.cols[b * p.edges_stride + ei] = pos;    // index of the frontier node
-  p.eidx[b * p.edges_stride + ei] = gp;     // global CSC position
+  p.eidx[b * p.edges_stride + ei] = p.edge_base[owner] + lp;  // global CSC position
 }
 
 }  // namespace
@@ -414,12 +436,14 @@ extern "C" tchgeo_status tchgeo_part_begin_hop(const int64_t* samples, int64_t s
 
 extern "C" tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, const int64_t* indices_local,
                                                     const double* weights_local, int64_t col_begin, int64_t ncols_local,
-                                                    int64_t edge_base, const int64_t* req, int64_t n, int64_t fanout,
-                                                    int32_t sampler_kind, uint64_t seed, uint32_t rel, int64_t* ans,
+                                                    int64_t nnz_local, const int64_t* req, int64_t n, int64_t fanout,
+                                                    int32_t sampler_kind, uint64_t seed, uint32_t rel, int32_t* ans,
                                                     int32_t* err_word, tchgeo_stream stream_) {
-  return serve_launch(ptrs_local, indices_local, weights_local, col_begin, ncols_local, edge_base, req, req ? req + 1 : req,
-                      2, n, fanout, sampler_kind, seed, rel, ans, ans ? ans + fanout : ans, 2 * fanout,
-                      (uint32_t*)err_word, (cudaStream_t)stream_);
+  // compact answers: neighbour ids and LOCAL csc positions travel as int32 (half the all-to-all bytes)
+  TCHGEO_REQUIRE(nnz_local >= 0 && nnz_local < ((int64_t)1 << 31), "a rank's share of the CSC must stay below 2^31 entries");
+  return serve_launch(ptrs_local, indices_local, weights_local, col_begin, ncols_local, 0, req, req ? req + 1 : req, 2, n,
+                      fanout, sampler_kind, seed, rel, nullptr, nullptr, 0, ans, (uint32_t*)err_word,
+                      (cudaStream_t)stream_);
 }
 
 extern "C" size_t tchgeo_part_finish_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap) {
@@ -430,8 +454,9 @@ extern "C" size_t tchgeo_part_finish_hop_workspace_bytes(int64_t num_batches, in
   return 256 + ((size_t)n * 4 + 255) / 256 * 256 + (cub_bytes + 255) / 256 * 256;
 }
 
-extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int64_t* ans, int64_t num_requests,
-                                                int64_t fanout, uint32_t batch_base, const int64_t* fr_begin,
+extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int32_t* ans, int64_t num_requests,
+                                                int64_t fanout, const int64_t* owner_edge_base, int64_t cols_per_rank,
+                                                int32_t world, uint32_t batch_base, const int64_t* fr_begin,
                                                 int64_t num_batches, int64_t frontier_cap, const int64_t* node_len_in,
                                                 const int64_t* edge_len_in, int64_t* node_len_out, int64_t* edge_len_out,
                                                 int64_t* samples, int64_t samples_stride, int64_t* rows, int64_t* cols,
@@ -439,7 +464,8 @@ extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int64_
                                                 void* workspace, size_t workspace_bytes, tchgeo_stream stream_) {
   TCHGEO_REQUIRE(num_requests >= 0 && fanout >= 0 && fanout < (1 << 20) && num_batches >= 0 && frontier_cap >= 0,
                  "bad argument");
-  TCHGEO_REQUIRE(node_len_in && edge_len_in && node_len_out && edge_len_out && err_word, "NULL pointer");
+  TCHGEO_REQUIRE(node_len_in && edge_len_in && node_len_out && edge_len_out && err_word && owner_edge_base, "NULL pointer");
+  TCHGEO_REQUIRE(world >= 1 && world <= PT_MAX_WORLD && cols_per_rank >= 1, "bad partition");
   const size_t need = tchgeo_part_finish_hop_workspace_bytes(num_batches, frontier_cap);
   TCHGEO_REQUIRE(need != 0, "frontier too large for one call");
   TCHGEO_REQUIRE(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes", need);
@@ -449,7 +475,8 @@ extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int64_
   void* cub_tmp = (char*)fcnt + ((size_t)n * 4 + 255) / 256 * 256;
   size_t cub_bytes = need - 256 - ((size_t)n * 4 + 255) / 256 * 256;
   PartFinish p;
-  p.req = req; p.ans = ans; p.F = num_requests; p.k = (int32_t)fanout; p.batch_base = batch_base; p.fr_begin = fr_begin;
+  p.req = req; p.ans = ans; p.edge_base = owner_edge_base; p.cols_per_rank = cols_per_rank; p.world = world;
+  p.F = num_requests; p.k = (int32_t)fanout; p.batch_base = batch_base; p.fr_begin = fr_begin;
   p.B = num_batches; p.capF = frontier_cap; p.fcnt = fcnt;
   p.node_len_in = node_len_in; p.edge_len_in = edge_len_in; p.node_len_out = node_len_out; p.edge_len_out = edge_len_out;
   p.samples = samples; p.samples_stride = samples_stride; p.rows = rows; p.cols = cols; p.eidx = edge_index;

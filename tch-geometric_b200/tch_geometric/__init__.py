@@ -15,6 +15,7 @@ from .ops import (  # noqa: F401
     clear_caches,
     csc_edge_cumsum,
     csc_sort_edges,
+    gather_rows,
     ind2ptr,
     negative_sample_neighbors_heterogenous,
     negative_sample_neighbors_homogenous,

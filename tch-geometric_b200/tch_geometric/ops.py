@@ -771,6 +771,32 @@ def negative_sample_neighbors_heterogenous(node_types: List[str], edge_types: Li
 
 
 # ---------------------------------------------------------------------------------------------
+# downstream gather (the step after the sampler in every loader: x[samples], edge_attr[perm[edge_index]])
+# ---------------------------------------------------------------------------------------------
+def gather_rows(src: Tensor, index: Tensor) -> Tensor:
+    """src[index] along dim 0 for a contiguous CUDA tensor of any dtype and an int64 index vector
+    (examples/neighbor_sampling.py:21-24 / PyG filter_data).  Out-of-range indices raise (no negative wrap-around)."""
+    if not isinstance(src, Tensor) or not src.is_cuda:
+        raise ValueError("src must be a CUDA tensor")
+    if not src.is_contiguous() or src.dim() < 1:
+        raise ValueError("src must be contiguous with at least one dimension")
+    dev = src.device
+    _check(index, torch.int64, "index", dev)
+    if index.dim() != 1:
+        raise ValueError("index must be a vector")
+    n = index.numel()
+    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=dev)
+    row_bytes = (src.numel() // src.shape[0]) * src.element_size() if src.shape[0] > 0 else 0
+    if src.shape[0] == 0 and n > 0:
+        raise N.ReferencePanic("index out of range (src has no rows)")
+    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.tchgeo_gather_rows(_ptr(src), src.shape[0], row_bytes, _ptr(index), n, _ptr(out), _ptr(scratch),
+                                         _stream(dev)))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # dedup + relabel stage (additive; semantic of negative_sampling.rs:20-47)
 # ---------------------------------------------------------------------------------------------
 def unique_relabel(samples: Tensor, num_seeds: int) -> Tuple[Tensor, Tensor]:

@@ -79,6 +79,9 @@ class SingleComm:
     def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts):
         return rows
 
+    def all_gather_int(self, value: int, device):
+        return [int(value)]
+
 
 class DistComm:
     """all-to-all(v) over a torch.distributed group (NCCL on GPUs, gloo in the CPU tests)."""
@@ -107,6 +110,12 @@ class DistComm:
         out = torch.empty((max(sum(rc), 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
         dist.all_to_all_single(out[:sum(rc)], rows[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc, group=self.group)
         return rc, sc, out
+
+    def all_gather_int(self, value: int, device):
+        mine = torch.tensor([int(value)], dtype=torch.int64, device=device)
+        out = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(out, mine, group=self.group)
+        return [int(x.item()) for x in out]
 
     def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts):
         """Answers travel the reverse way: what was received is sent back, split sizes swapped."""
@@ -229,11 +238,12 @@ class PartitionedSampler:
 
 def serve_rows(part: ColumnPartition, req: Tensor, n: int, fanout: int, kind: int, seed: int, ans: Tensor, err: Tensor,
                rel: int = 0):
-    """Owner side on interleaved rows (asynchronous): req [n,2] -> ans [n, 2*fanout]; errors are OR-ed into `err`."""
+    """Owner side on interleaved rows (asynchronous): req [n,2] i64 -> ans [n, 2*fanout] i32 (ids | local csc
+    positions); errors are OR-ed into `err`."""
     dev = part.ptrs.device
     with torch.cuda.device(dev):
         N.check(N.lib.tchgeo_serve_requests_rows(_ptr(part.ptrs), _ptr(part.indices), _ptr(part.weights), part.col_begin,
-                                                 part.col_end - part.col_begin, part.edge_base, _ptr(req), int(n),
+                                                 part.col_end - part.col_begin, part.indices.numel(), _ptr(req), int(n),
                                                  int(fanout), kind, seed, rel, _ptr(ans), _ptr(err), _stream(dev)))
 
 
@@ -266,9 +276,10 @@ class PartitionedPlan:
     """neighbor_sampling_homogenous over a column-partitioned CSC, device pipeline.  `sample` is collective."""
 
     def __init__(self, part: ColumnPartition, num_batches: int, seeds_per_batch: int, num_neighbors: Sequence[int],
-                 sampler=None, comm=None, serve_rows=None):
-        """serve_rows(r_req [n,2], recv_counts, fanout, seed, ans [n,2k]) overrides the owner side (tests simulate
-        several owners on one GPU with it); default: tchgeo_serve_requests_rows over `part`."""
+                 sampler=None, comm=None, serve_rows=None, edge_bases=None):
+        """serve_rows(r_req [n,2], recv_counts, fanout, seed, ans [n,2k] int32) overrides the owner side (tests simulate
+        several owners on one GPU with it); default: tchgeo_serve_requests_rows over `part`.
+        edge_bases: every rank's ColumnPartition.edge_base (default: all-gathered through the communicator)."""
         self.part = part
         self.serve_rows = serve_rows
         self.fanouts = [int(k) for k in num_neighbors]
@@ -279,6 +290,8 @@ class PartitionedPlan:
         _check(part.ptrs, torch.int64, "col_ptrs_local")
         dev = part.ptrs.device
         _check(part.indices, torch.int64, "row_indices_local", dev)
+        if part.num_nodes >= 2 ** 31 or part.indices.numel() >= 2 ** 31:
+            raise ValueError("the compact answer rows need node ids and a rank's CSC share below 2^31")
         self.device, self.B, self.S = dev, int(num_batches), int(seeds_per_batch)
         B, S, H = self.B, self.S, len(self.fanouts)
         # worst-case frontier / output sizes per batch (the recurrence of tchgeo_neighbor_sampling_capacity)
@@ -296,6 +309,11 @@ class PartitionedPlan:
         self.lens = torch.zeros((2, H + 1, B), **i64)               # [0] node_len, [1] edge_len after h hops
         self.counts = torch.zeros((2, max(self.comm.world, 1)), **i64)  # [0] per-owner request counts, [1] cursor
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        if edge_bases is None:
+            edge_bases = self.comm.all_gather_int(part.edge_base, dev)
+        if len(edge_bases) != self.comm.world:
+            raise ValueError("edge_bases must have one entry per rank")
+        self.edge_bases = torch.tensor([int(x) for x in edge_bases], **i64)
         fmax = max(self.capF) if self.capF else 0
         self.req = torch.empty((max(B * fmax, 1), 2), **i64)
         ws = max((N.lib.tchgeo_part_finish_hop_workspace_bytes(B, c) for c in self.capF), default=0)
@@ -303,6 +321,13 @@ class PartitionedPlan:
             raise ValueError("frontier too large for one call: use fewer batches per call")
         self.ws = torch.empty(max(int(ws), 1), dtype=torch.uint8, device=dev)
         self.stats = {"requests_sent": 0, "request_bytes": 0, "answer_bytes": 0}
+        self.profile = None   # set to {} to collect per-phase device times (ms, CUDA events) of the next calls
+
+    def _mark(self, marks, name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
 
     def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> PartitionedBatches:
         """inputs [B, S] i64 (this rank's batches; device or pinned host) -> PartitionedBatches"""
@@ -317,30 +342,42 @@ class PartitionedPlan:
             self.err.zero_()
             self.lens.zero_()
             self.lens[0, 0].fill_(S)
+            marks = [] if self.profile is not None else None
+            self._mark(marks, "start")
             for h, k in enumerate(self.fanouts):
                 fr_begin = self.lens[0, h - 1] if h > 0 else None
                 N.check(lib.tchgeo_part_begin_hop(_ptr(self.samples), self.cap_n, _ptr(fr_begin), _ptr(self.lens[0, h]), B,
                                                   self.capF[h], part.cols_per_rank, world, batch_base,
                                                   _ptr(self.counts[0]), _ptr(self.counts[1]), _ptr(self.req),
                                                   _ptr(self.err), stream))
+                self._mark(marks, "bucket")
                 recv_counts, send_counts, r_req = comm.exchange_rows(self.counts[0], self.req)
+                self._mark(marks, "a2a_requests")
                 F, n_recv = sum(send_counts), sum(recv_counts)
-                ans = torch.empty((max(n_recv, 1), 2 * k), dtype=torch.int64, device=dev)
+                ans = torch.empty((max(n_recv, 1), 2 * k), dtype=torch.int32, device=dev)
                 if self.serve_rows is not None:
                     self.serve_rows(r_req, recv_counts, k, seed, ans)
                 else:
                     serve_rows(part, r_req, n_recv, k, self.kind, seed, ans, self.err)
+                self._mark(marks, "serve")
                 back = comm.return_rows(ans, n_recv, F, send_counts, recv_counts)
-                N.check(lib.tchgeo_part_finish_hop(_ptr(self.req), _ptr(back), F, k, batch_base, _ptr(fr_begin), B,
+                self._mark(marks, "a2a_answers")
+                N.check(lib.tchgeo_part_finish_hop(_ptr(self.req), _ptr(back), F, k, _ptr(self.edge_bases),
+                                                   part.cols_per_rank, world, batch_base, _ptr(fr_begin), B,
                                                    self.capF[h], _ptr(self.lens[0, h]), _ptr(self.lens[1, h]),
                                                    _ptr(self.lens[0, h + 1]), _ptr(self.lens[1, h + 1]),
                                                    _ptr(self.samples), self.cap_n, _ptr(self.rows), _ptr(self.cols),
                                                    _ptr(self.eidx), self.cap_e, _ptr(self.err), _ptr(self.ws),
                                                    self.ws.numel(), stream))
+                self._mark(marks, "layout")
                 self.stats["requests_sent"] += F
                 self.stats["request_bytes"] += 16 * F
-                self.stats["answer_bytes"] += 16 * k * F
+                self.stats["answer_bytes"] += 8 * k * F
             host = torch.cat([self.lens.reshape(-1), self.err.to(torch.int64)]).cpu().numpy()   # the call's last sync
+        if marks is not None:
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                self.profile[name] = self.profile.get(name, 0.0) + e0.elapsed_time(e1)
+            self.profile["calls"] = self.profile.get("calls", 0) + 1
         N.check(lib.tchgeo_status_from_error_word(int(host[-1]) & 0xFFFFFFFF))
         lens = host[:-1].reshape(2, len(self.fanouts) + 1, B)
         return PartitionedBatches(self, lens[0], lens[1])

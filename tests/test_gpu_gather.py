@@ -1,0 +1,55 @@
+"""GPU parity: gather_rows against numpy fancy indexing, bit-exact for every dtype / row width,
+including rows that force the 8-, 4- and 1-byte vector paths."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def thg():
+    import tch_geometric
+    return tch_geometric
+
+
+@pytest.mark.parametrize("dtype,width", [(np.float32, 100), (np.float32, 128), (np.float32, 3), (np.float32, 1),
+                                         (np.float64, 7), (np.int64, 1), (np.int16, 5), (np.uint8, 13), (np.uint8, 1)])
+def test_matches_numpy(thg, dtype, width):
+    rng = np.random.default_rng(width)
+    src = (rng.standard_normal((5000, width)) * 100).astype(dtype)
+    idx = rng.integers(0, 5000, 123457)
+    got = thg.gather_rows(torch.from_numpy(src).cuda(), torch.from_numpy(idx).cuda())
+    assert got.dtype == torch.from_numpy(src).dtype and tuple(got.shape) == (idx.size, width)
+    assert (got.cpu().numpy() == src[idx]).all()
+
+
+def test_shapes_views_and_errors(thg):
+    src = torch.arange(24 * 6, dtype=torch.float32, device="cuda").reshape(24, 2, 3)
+    idx = torch.tensor([5, 0, 23, 5], device="cuda")
+    assert torch.equal(thg.gather_rows(src, idx), src[idx])
+    vec = torch.arange(10, dtype=torch.int64, device="cuda") * 3   # perm[edge_index]
+    assert torch.equal(thg.gather_rows(vec, idx[:2]), vec[idx[:2]])
+    off = src.reshape(-1)[1:1 + 23 * 5].reshape(23, 5)            # misaligned base pointer (4-byte path)
+    assert torch.equal(thg.gather_rows(off, idx[:2]), off[idx[:2]])
+    assert thg.gather_rows(src, idx[:0]).shape == (0, 2, 3)
+    with pytest.raises(thg.ReferencePanic):
+        thg.gather_rows(src, torch.tensor([24], device="cuda"))
+    with pytest.raises(thg.ReferencePanic):
+        thg.gather_rows(src, torch.tensor([-1], device="cuda"))
+    with pytest.raises(ValueError):
+        thg.gather_rows(src.cpu(), idx)
+    with pytest.raises(ValueError):
+        thg.gather_rows(src.transpose(0, 1), idx)
+
+
+def test_sampler_output_feeds_the_gather(thg, fakedataset):
+    """x[samples] and perm[edge_index] for a sampled tree: what filter_data does after the sampler."""
+    ei, n = fakedataset
+    ptrs, idx, perm = thg.to_csc(torch.from_numpy(ei).cuda(), n)
+    x = torch.randn(n, 64, device="cuda")
+    samples, rows, cols, eidx, _ = thg.neighbor_sampling_homogenous(ptrs, idx, torch.arange(32, device="cuda"), [4, 3])
+    assert torch.equal(thg.gather_rows(x, samples), x[samples])
+    orig_edges = thg.gather_rows(perm, eidx)       # positions in the caller's edge_index (quirk Q5)
+    e = torch.from_numpy(ei).cuda()
+    assert torch.equal(e[0][orig_edges], samples[rows]) and torch.equal(e[1][orig_edges], samples[cols])

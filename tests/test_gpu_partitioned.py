@@ -75,6 +75,9 @@ class _FakeWorld:
     def return_rows(self, rows, n_rows, n_back, send_counts, recv_counts):
         return rows
 
+    def all_gather_int(self, value, device):
+        raise AssertionError("the test passes edge_bases explicitly")
+
 
 @pytest.mark.parametrize("world", [1, 3, 8])
 def test_partitioned_plan_equals_replicated(thg, fakedataset, world):
@@ -98,7 +101,7 @@ def test_partitioned_plan_equals_replicated(thg, fakedataset, world):
                 o += c
 
         plan = PartitionedPlan(parts[0], B, S, fan, sampler, comm=_FakeWorld(world) if world > 1 else SingleComm(),
-                               serve_rows=serve if world > 1 else None)
+                               serve_rows=serve if world > 1 else None, edge_bases=[p.edge_base for p in parts])
         for rep in range(2):  # the plan's buffers are reused across calls
             got = plan.sample(inputs, seed=9 + rep, batch_base=4)
             want = thg.neighbor_sampling_homogenous_batched(ptrs, idx, inputs, fan, sampler, seed=9 + rep, batch_base=4)
