@@ -759,7 +759,8 @@ def run_partitioned(args):
         edge_base, e_total = 0, int(e_local.item())
     part = ColumnPartition(ptrs, idx, n, rank, world, edge_base)
     B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
-    ps = PartitionedPlan(part, B, S, FANOUTS, comm=DistComm() if world > 1 else SingleComm())
+    ps = PartitionedPlan(part, B, S, FANOUTS, comm=DistComm() if world > 1 else SingleComm(),
+                         groups=args.groups if args.groups > 0 else None)
     seeds = [torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B)).to(device)
              for s in range(W + K)]
     for s in range(W):
@@ -791,7 +792,7 @@ def run_partitioned(args):
                                      f"CSC range-partitioned over {world} rank(s), fanouts {FANOUTS}, {S} seeds/batch, "
                                      f"{B} batches/step/rank, NCCL all-to-all frontier exchange per hop",
                          "parallelism": "column-range partition + all-to-all(v) of requests and answers"},
-              "phase_ms_per_step_rank0": phases,
+              "phase_ms_per_step_rank0": phases, "pipelined_batch_groups": ps.num_groups,
               "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + 2 * K),
                                                    "answers": ps.stats["answer_bytes"] // (W + 2 * K)},
               "cpu_baseline": None, "e2e": None, "gpu_launches": K * len(FANOUTS) * 8, "clocks": clk})
@@ -813,6 +814,8 @@ def main():
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (0 = leave)")
     ap.add_argument("--sampler", default="uniform", choices=["uniform", "replace", "weighted"],
                     help="sampling workload: neighbour sampler (uniform = the headline configuration)")
+    ap.add_argument("--groups", type=int, default=0,
+                    help="partitioned workload: batch groups pipelined on separate streams (0 = default: 1)")
     ap.add_argument("--walkers", type=int, default=0, help="walk workload: number of walkers (0 = 10 per node)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -261,19 +261,22 @@ TCHGEO_API tchgeo_status tchgeo_part_begin_hop(const int64_t* samples /*DEVICE [
                                                uint32_t batch_base, int64_t* counts /*DEVICE [world]*/,
                                                int64_t* cursor /*DEVICE [world] scratch*/,
                                                int64_t* req /*DEVICE [B*frontier_cap, 2]*/, int32_t* err_word,
-                                               tchgeo_stream stream);
+                                               void* workspace /*DEVICE, tchgeo_part_hop_workspace_bytes; the same
+                                               buffer must be passed to tchgeo_part_finish_hop of this hop*/,
+                                               size_t workspace_bytes, tchgeo_stream stream);
 TCHGEO_API tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, const int64_t* indices_local,
                                                     const double* weights_local, int64_t col_begin, int64_t ncols_local,
                                                     int64_t nnz_local, const int64_t* req /*DEVICE [n,2]*/, int64_t n,
                                                     int64_t fanout, int32_t sampler_kind, uint64_t seed, uint32_t rel,
                                                     int32_t* ans /*DEVICE [n, 2*fanout] int32*/, int32_t* err_word,
                                                     tchgeo_stream stream);
-TCHGEO_API size_t tchgeo_part_finish_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap);
+TCHGEO_API size_t tchgeo_part_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap);
 TCHGEO_API tchgeo_status tchgeo_part_finish_hop(const int64_t* req /*DEVICE [F,2] as sent*/, const int32_t* ans /*DEVICE [F, 2*fanout]*/,
                                                 int64_t num_requests, int64_t fanout,
                                                 const int64_t* owner_edge_base /*DEVICE [world]*/, int64_t cols_per_rank,
-                                                int32_t world, uint32_t batch_base,
-                                                const int64_t* fr_begin, int64_t num_batches, int64_t frontier_cap,
+                                                int32_t world,
+                                                const int64_t* fr_begin, const int64_t* fr_end, int64_t num_batches,
+                                                int64_t frontier_cap,
                                                 const int64_t* node_len_in /*DEVICE [B]*/, const int64_t* edge_len_in,
                                                 int64_t* node_len_out, int64_t* edge_len_out, int64_t* samples,
                                                 int64_t samples_stride, int64_t* rows, int64_t* cols, int64_t* edge_index,
@@ -344,6 +347,23 @@ TCHGEO_API tchgeo_status tchgeo_negative_sampling_capacity(const tchgeo_negative
 TCHGEO_API size_t tchgeo_negative_sampling_workspace_bytes(const tchgeo_negative_args* args);
 /* Synchronises args->stream (lengths are returned to the host). */
 TCHGEO_API tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* args);
+
+/* Temporal random walk.  walks / walks_timestamps: [num_walks, walk_length] (NOT +1), column 0 =
+ * start / start timestamp.  Per step the next node is drawn with the reference's k = 1 reservoir among the
+ * neighbours whose timestamp (edge timestamp, or the neighbour's node timestamp when that is -1) is -1 or lies in
+ * [start_ts + window_lo, start_ts + window_hi) (everything passes when start_ts is -1); a step without such a
+ * neighbour restarts from a uniformly drawn earlier position of the same walk.
+ * replaces src/algo/random_walk.rs:80-158, called from src/python.rs:610-643 */
+TCHGEO_API tchgeo_status tchgeo_tempo_random_walk(const int64_t* row_ptrs /*DEVICE [num_rows+1]*/, int64_t num_rows,
+                                                  const int64_t* col_indices /*DEVICE [nnz]*/,
+                                                  const int64_t* node_timestamps /*DEVICE [num_node_timestamps]*/,
+                                                  int64_t num_node_timestamps,
+                                                  const int64_t* edge_timestamps /*DEVICE [nnz]*/,
+                                                  const int64_t* start /*DEVICE [num_walks]*/,
+                                                  const int64_t* start_timestamps /*DEVICE [num_walks]*/, int64_t num_walks,
+                                                  int64_t walk_length, int64_t window_lo, int64_t window_hi, uint64_t seed,
+                                                  int64_t walker_base, int64_t* walks, int64_t* walks_timestamps,
+                                                  int32_t* scratch /*DEVICE [1]*/, tchgeo_stream stream);
 
 /* -------------------------------------------------------------------------------------------- */
 /* Row gather: dst[i, :] = src[index[i], :] for rows of row_bytes bytes of any     */

@@ -388,6 +388,23 @@ def negative_sample_neighbors_heterogenous(node_types, edge_types, row_ptrs, col
                      rng_mode, seed)
 
 
+def tempo_random_walk(row_ptrs, col_indices, node_timestamps, edge_timestamps, start, start_timestamps, walk_length, window,
+                      rng_mode=RNG_COUNTER, seed=0, walker_base=0):
+    """python.rs:610-643 -> (walks, walk_timestamps), both [S, walk_length]"""
+    row_ptrs, col_indices, start = _i64(row_ptrs), _i64(col_indices), _i64(start)
+    nts, ets, sts = _i64(node_timestamps), _i64(edge_timestamps), _i64(start_timestamps)
+    S, L = start.size, int(walk_length)
+    walks = np.empty((S, max(L, 0)), dtype=np.int64)
+    wts = np.empty_like(walks)
+    rc = lib().orc_tempo_random_walk(_p(row_ptrs), ctypes.c_int64(row_ptrs.size - 1), _p(col_indices), _p(nts),
+                                     ctypes.c_int64(nts.size), _p(ets), _p(start), _p(sts), ctypes.c_int64(S),
+                                     ctypes.c_int64(L), ctypes.c_int64(int(window[0])), ctypes.c_int64(int(window[1])),
+                                     ctypes.c_int(rng_mode), ctypes.c_uint64(seed), ctypes.c_int64(walker_base), _p(walks),
+                                     _p(wts))
+    _check(rc)
+    return walks, wts
+
+
 def unique_relabel(samples, num_seeds):
     """dedup stage (negative_sampling.rs:20-47 semantic) -> (nodes, local)"""
     samples = _i64(samples)

@@ -938,6 +938,82 @@ int orc_negative_sampling(int T, int R, const int32_t* rel_src, const int32_t* r
   return rc;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* F4: tempo_random_walk, src/algo/random_walk.rs:80-158.  walks / walks_ts: [S, L] with L =        */
+/* walk_length (not +1), -1 filled.  Counter mode: the passing item at position i >= 1 of step l     */
+/* draws word i&3 of Philox(walker, l, TAG_TEMPO | (i>>2) << 8); the restart draw uses               */
+/* TAG_TEMPO_RESTART.                                                                               */
+/* ------------------------------------------------------------------------------------------ */
+#define ORC_TAG_TEMPO 6u
+#define ORC_TAG_TEMPO_RESTART 7u
+int orc_tempo_random_walk(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,
+                          const int64_t* node_ts, int64_t num_node_ts, const int64_t* edge_ts,
+                          const int64_t* start, const int64_t* start_ts, int64_t S, int64_t walk_length,
+                          int64_t w0, int64_t w1, int rng_mode, uint64_t seed, int64_t walker_base,
+                          int64_t* walks, int64_t* walks_ts) {
+  orc_rng rng;
+  orc_rng_init(&rng, rng_mode, seed);
+  const int64_t L = walk_length;
+  for (int64_t x = 0; x < S * L; ++x) { walks[x] = -1; walks_ts[x] = -1; } /* :89-98 */
+  if (S > 0 && L <= 0) return ORC_ERR_PANIC;                                  /* walks_data[i * L], :113 */
+  for (int64_t i = 0; i < S; ++i) {
+    int64_t cur = start[i];
+    const int64_t i_ts = start_ts[i];
+    const int64_t lo = i_ts + w0, hi = i_ts + w1; /* i_timestamp + window.0 .. i_timestamp + window.1, :111 */
+    const uint64_t walker = (uint64_t)(walker_base + i);
+    walks[i * L] = cur;
+    walks_ts[i * L] = i_ts;
+    for (int64_t l = 0; l + 1 < L; ++l) {
+      if (cur < 0 || cur >= num_rows) return ORC_ERR_PANIC;
+      int64_t next = -1, next_ts = -1;
+      int64_t n = 0; /* passing items seen so far */
+      uint32_t buf[4] = {0, 0, 0, 0};
+      for (int64_t e = row_ptrs[cur]; e < row_ptrs[cur + 1]; ++e) {
+        const int64_t node = col_indices[e];
+        int64_t ts = edge_ts[e];
+        if (ts == -1) { /* :118-122 */
+          if (node < 0 || node >= num_node_ts) return ORC_ERR_PANIC;
+          ts = node_ts[node];
+        }
+        if (!(ts == -1 || i_ts == -1 || (lo <= ts && ts < hi))) continue; /* :125-135 */
+        if (n == 0) { /* reservoir_sampling with dst.len() == 1: the first item fills the slot */
+          next = node; next_ts = ts;
+        } else {      /* sampling.rs:17-23: j = gen_range(0..i); if j < 1 { dst[0] = item } */
+          uint64_t j;
+          if (rng_mode == ORC_RNG_XOSHIRO) {
+            j = xoshiro_gen_range_u64(&rng, (uint64_t)n);
+          } else {
+            if ((n & 3) == 0 || n == 1) {
+              uint32_t ctr[4] = {(uint32_t)walker, (uint32_t)(walker >> 32), (uint32_t)l,
+                                 ORC_TAG_TEMPO | ((uint32_t)(n >> 2) << 8)};
+              orc_philox4x32_10(ctr, rng.key, buf);
+            }
+            j = mulhi32(buf[n & 3], (uint32_t)n);
+          }
+          if (j < 1) { next = node; next_ts = ts; }
+        }
+        n += 1;
+      }
+      if (n == 0) { /* restart, :140-144 */
+        int64_t ri;
+        if (rng_mode == ORC_RNG_XOSHIRO) {
+          ri = (int64_t)xoshiro_gen_range_u64(&rng, (uint64_t)(l + 1));
+        } else {
+          uint32_t ctr[4] = {(uint32_t)walker, (uint32_t)(walker >> 32), (uint32_t)l, ORC_TAG_TEMPO_RESTART};
+          orc_philox4x32_10(ctr, rng.key, buf);
+          ri = (int64_t)mulhi32(buf[0], (uint32_t)(l + 1));
+        }
+        next_ts = walks_ts[i * L + ri];
+        next = walks[i * L + ri];
+      }
+      cur = next;
+      walks[i * L + l + 1] = cur;
+      walks_ts[i * L + l + 1] = next_ts;
+    }
+  }
+  return ORC_OK;
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -25,31 +25,35 @@ template <typename V>
 __global__ void __launch_bounds__(GT_THREADS) gather_rows_kernel(const V* __restrict__ src, int64_t num_rows,
                                                                 int64_t vecs_per_row, const int64_t* __restrict__ index,
                                                                 int64_t n, V* __restrict__ dst, uint32_t* err) {
-  const int64_t total = n * vecs_per_row;
+  // vector t of the output is (row i = t / vecs_per_row, column c = t % vecs_per_row); the pair is divided out once
+  // per thread and then advanced by the grid stride with adds only (a 64-bit division per vector would cost more
+  // issue slots than the copy itself)
   const int64_t stride = (int64_t)gridDim.x * GT_THREADS;
-  int64_t t = (int64_t)blockIdx.x * GT_THREADS + threadIdx.x;
-  for (; t < total; t += stride * GT_UNROLL) {
+  const int64_t di = stride / vecs_per_row, dc = stride - di * vecs_per_row;
+  const int64_t t0 = (int64_t)blockIdx.x * GT_THREADS + threadIdx.x;
+  int64_t i = t0 / vecs_per_row, c = t0 - i * vecs_per_row;
+  while (i < n) {
     V v[GT_UNROLL];
-    bool ok[GT_UNROLL];
+    int64_t o[GT_UNROLL];
 #pragma unroll
     for (int u = 0; u < GT_UNROLL; ++u) {
-      const int64_t tt = t + u * stride;
-      ok[u] = false;
-      if (tt < total) {
-        const int64_t i = tt / vecs_per_row;
-        const int64_t c = tt - i * vecs_per_row;
+      o[u] = -1;
+      if (i < n) {
         const int64_t r = __ldg(index + i);
         if (r < 0 || r >= num_rows) {
           if (c == 0) atomicOr(err, DEV_ERR_INDEX);
         } else {
           v[u] = ld_row(src + r * vecs_per_row + c);
-          ok[u] = true;
+          o[u] = i * vecs_per_row + c;
         }
       }
+      i += di;
+      c += dc;
+      if (c >= vecs_per_row) { c -= vecs_per_row; ++i; }
     }
 #pragma unroll
     for (int u = 0; u < GT_UNROLL; ++u)
-      if (ok[u]) st_stream(dst + t + u * stride, v[u]);
+      if (o[u] >= 0) st_stream(dst + o[u], v[u]);
   }
 }
 

@@ -260,10 +260,9 @@ struct PartFrontier {
   uint32_t batch_base;
 };
 
-__device__ __forceinline__ bool pt_node(const PartFrontier& f, int64_t t, int64_t& b, int64_t& pos, int64_t& id) {
-  b = t / f.capF;
-  const int64_t j = t - b * f.capF;
-  if (b >= f.B) return false;
+// frontier slot j of batch b (the kernels run on a 2-D grid: blockIdx.y = batch, x covers the frontier capacity)
+__device__ __forceinline__ bool pt_node(const PartFrontier& f, int64_t b, int64_t j, int64_t& pos, int64_t& id) {
+  if (b >= f.B || j >= f.capF) return false;
   const int64_t fb = f.fr_begin ? f.fr_begin[b] : 0;
   int64_t fe = f.fr_end[b];
   if (fe > f.samples_stride) fe = f.samples_stride;
@@ -273,11 +272,17 @@ __device__ __forceinline__ bool pt_node(const PartFrontier& f, int64_t t, int64_
   return true;
 }
 
-__device__ __forceinline__ int pt_owner(const PartFrontier& f, int64_t id) {
-  int64_t o = id / f.cols_per_rank;  // out-of-range ids go to the edge ranks, whose serve kernel reports them
+// owner(w) = min(w / cols_per_rank, world - 1); out-of-range ids go to the edge ranks, whose serve kernel reports them
+__device__ __forceinline__ int pt_owner_of(int64_t id, int64_t cols_per_rank, int world) {
+  int64_t o;
   if (id < 0) o = 0;
-  if (o >= f.world) o = f.world - 1;
+  else if (((uint64_t)id | (uint64_t)cols_per_rank) >> 32) o = id / cols_per_rank;
+  else o = (int64_t)((uint32_t)id / (uint32_t)cols_per_rank);  // the common case: a 32-bit division
+  if (o >= world) o = world - 1;
   return (int)o;
+}
+__device__ __forceinline__ int pt_owner(const PartFrontier& f, int64_t id) {
+  return pt_owner_of(id, f.cols_per_rank, f.world);
 }
 
 // warp-aggregated histogram update: lanes with the same owner elect a leader that adds the group's size once;
@@ -298,27 +303,26 @@ __global__ void __launch_bounds__(PT_THREADS) part_count_kernel(const PartFronti
   __shared__ unsigned int hist[PT_MAX_WORLD];
   if (threadIdx.x < PT_MAX_WORLD) hist[threadIdx.x] = 0u;
   __syncthreads();
-  const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
-  int64_t b, pos, id = 0;
-  if (t < f.B * f.capF && t % f.capF == 0) {  // first slot of a batch: the frontier must fit the launch geometry
-    const int64_t bb = t / f.capF;
-    if (f.fr_end[bb] - (f.fr_begin ? f.fr_begin[bb] : 0) > f.capF) atomicOr(err, DEV_ERR_CAPACITY);
-  }
-  const bool ok = pt_node(f, t, b, pos, id);
+  const int64_t b = blockIdx.y, j = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  int64_t pos, id = 0;
+  if (j == 0 && f.fr_end[b] - (f.fr_begin ? f.fr_begin[b] : 0) > f.capF)  // the frontier must fit the launch geometry
+    atomicOr(err, DEV_ERR_CAPACITY);
+  const bool ok = pt_node(f, b, j, pos, id);
   pt_hist_add(hist, ok, ok ? pt_owner(f, id) : 0);
   __syncthreads();
   if (threadIdx.x < f.world && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
 }
 
 __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFrontier f, const unsigned long long* counts,
-                                                                 unsigned long long* cursor, int64_t* req) {
+                                                                 unsigned long long* cursor, int64_t* req,
+                                                                 int32_t* slot_of) {
   __shared__ unsigned int hist[PT_MAX_WORLD];
   __shared__ unsigned long long base[PT_MAX_WORLD];
   if (threadIdx.x < PT_MAX_WORLD) hist[threadIdx.x] = 0u;
   __syncthreads();
-  const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
-  int64_t b = 0, pos = 0, id = 0;
-  const bool ok = pt_node(f, t, b, pos, id);
+  const int64_t b = blockIdx.y, j = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  int64_t pos = 0, id = 0;
+  const bool ok = pt_node(f, b, j, pos, id);
   const int o = ok ? pt_owner(f, id) : 0;
   const unsigned int rank = pt_hist_add(hist, ok, o);
   __syncthreads();
@@ -333,6 +337,7 @@ __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFron
     const unsigned long long q = base[o] + rank;
     const uint64_t meta = ((uint64_t)(f.batch_base + (uint32_t)b) << 32) | (uint64_t)(uint32_t)pos;
     *reinterpret_cast<longlong2*>(req + 2 * q) = make_longlong2((long long)id, (long long)meta);
+    slot_of[b * f.capF + j] = (int32_t)q;  // where this frontier node's answer will be found (frontier order, coalesced)
   }
 }
 
@@ -344,9 +349,10 @@ struct PartFinish {
   int32_t world;
   int64_t F;
   int32_t k;
-  uint32_t batch_base;
   const int64_t* fr_begin; // [B] or NULL
+  const int64_t* fr_end;   // [B]
   int64_t B, capF;
+  const int32_t* slot_of;  // [B * capF] request slot of every frontier node (written by tchgeo_part_begin_hop)
   int32_t* fcnt;           // [B * capF + 1] answers per frontier node (padding = 0), then its exclusive scan in place
   const int64_t* node_len_in;  // [B]
   const int64_t* edge_len_in;  // [B]
@@ -357,17 +363,20 @@ struct PartFinish {
   uint32_t* err;
 };
 
+// Both kernels walk the frontier in ORDER (2-D grid: blockIdx.y = batch) and fetch the node's answer row through
+// slot_of: the output arrays are then written front to back in full lines whatever the number of owners (walking the
+// answers in arrival order instead sweeps the outputs once per owner and leaves every line half written).
 __global__ void __launch_bounds__(PT_THREADS) part_cnt_kernel(const PartFinish p) {
-  const int64_t q = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
-  if (q >= p.F) return;
-  const uint64_t meta = (uint64_t)p.req[2 * q + 1];
-  const int64_t b = (int64_t)(uint32_t)(meta >> 32) - (int64_t)p.batch_base;
-  const int64_t pos = (int64_t)(uint32_t)meta;
-  const int64_t j = pos - (p.fr_begin ? p.fr_begin[b] : 0);
-  const int32_t* a = p.ans + q * 2 * p.k + p.k;
+  const int64_t b = blockIdx.y, j = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
+  if (j >= p.capF) return;
+  const int64_t fb = p.fr_begin ? p.fr_begin[b] : 0;
   int c = 0;
-  for (int s = 0; s < p.k; ++s) c += a[s] >= 0 ? 1 : 0;  // valid slots form a prefix
+  if (j < p.fr_end[b] - fb) {
+    const int32_t* a = p.ans + (int64_t)p.slot_of[b * p.capF + j] * 2 * p.k + p.k;
+    for (int s = 0; s < p.k; ++s) c += a[s] >= 0 ? 1 : 0;  // valid slots form a prefix
+  }
   p.fcnt[b * p.capF + j] = c;
+  if (b == p.B - 1 && j == p.capF - 1) p.fcnt[p.B * p.capF] = 0;
 }
 
 __global__ void __launch_bounds__(PT_THREADS) part_len_kernel(const PartFinish p) {
@@ -381,26 +390,44 @@ __global__ void __launch_bounds__(PT_THREADS) part_len_kernel(const PartFinish p
 }
 
 __global__ void __launch_bounds__(PT_THREADS) part_emit_kernel(const PartFinish p) {
-  const int64_t t = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
-  if (t >= p.F * p.k) return;
-  const int64_t q = t / p.k;
-  const int s = (int)(t - q * p.k);
-  const int32_t lp = p.ans[q * 2 * p.k + p.k + s];
-  if (lp < 0) return;
-  const uint64_t meta = (uint64_t)p.req[2 * q + 1];
-  const int64_t b = (int64_t)(uint32_t)(meta >> 32) - (int64_t)p.batch_base;
-  const int64_t pos = (int64_t)(uint32_t)meta;
-  const int64_t j = pos - (p.fr_begin ? p.fr_begin[b] : 0);
-  const int64_t off = (int64_t)p.fcnt[b * p.capF + j] - (int64_t)p.fcnt[b * p.capF] + s;
+  const int64_t b = blockIdx.y;
+  const uint32_t t = blockIdx.x * PT_THREADS + threadIdx.x;   // < capF * k < 2^31 (checked by the host)
+  const uint32_t j = t / (uint32_t)p.k;
+  const int s = (int)(t - j * (uint32_t)p.k);
+  if ((int64_t)j >= p.capF) return;
+  const int64_t fb = p.fr_begin ? p.fr_begin[b] : 0;
+  if ((int64_t)j >= p.fr_end[b] - fb) return;
+  const int64_t idx = b * p.capF + j;
+  const int32_t first = p.fcnt[idx];
+  if (s >= p.fcnt[idx + 1] - first) return;   // only this node's valid slots
+  const int64_t q = p.slot_of[idx];
+  const int32_t* a = p.ans + q * 2 * p.k;
+  const int64_t off = (int64_t)first - (int64_t)p.fcnt[b * p.capF] + s;
   const int64_t ni = p.node_len_in[b] + off, ei = p.edge_len_in[b] + off;
   if (ni >= p.samples_stride || ei >= p.edges_stride) return;  // flagged by part_len_kernel
-  int64_t owner = p.req[2 * q] / p.cols_per_rank;  // same rule as pt_owner
-  if (owner < 0) owner = 0;
-  if (owner >= p.world) owner = p.world - 1;
-  p.samples[b * p.samples_stride + ni] = (int64_t)p.ans[q * 2 * p.k + s];
-  p.rows[b * p.edges_stride + ei] = ni;     // index of the appended node, neighbor_sampling.rs:213-216
-  p.cols[b * p.edges_stride + ei] = pos;    // index of the frontier node
-  p.eidx[b * p.edges_stride + ei] = p.edge_base[owner] + lp;  // global CSC position
+  const int owner = pt_owner_of(p.req[2 * q], p.cols_per_rank, p.world);
+  st_cs_i64(p.samples + b * p.samples_stride + ni, (int64_t)a[s]);
+  st_cs_i64(p.rows + b * p.edges_stride + ei, ni);        // index of the appended node, neighbor_sampling.rs:213-216
+  st_cs_i64(p.cols + b * p.edges_stride + ei, fb + j);    // index of the frontier node
+  st_cs_i64(p.eidx + b * p.edges_stride + ei, p.edge_base[owner] + a[p.k + s]);  // global CSC position
+}
+
+struct PartWs {  // layout of the per-plan hop workspace shared by begin_hop (slot_of) and finish_hop
+  size_t off_fcnt, off_slot, off_cub, cub_bytes, total;
+};
+bool part_ws_layout(int64_t num_batches, int64_t frontier_cap, PartWs& w) {
+  const int64_t n = num_batches * frontier_cap + 1;
+  if (n <= 0 || n >= ((int64_t)1 << 31)) return false;
+  size_t cub_bytes = 0;
+  if (cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, n) != cudaSuccess)
+    return false;
+  const size_t arr = ((size_t)n * 4 + 255) / 256 * 256;
+  w.off_fcnt = 256;
+  w.off_slot = w.off_fcnt + arr;
+  w.off_cub = w.off_slot + arr;
+  w.cub_bytes = cub_bytes;
+  w.total = w.off_cub + (cub_bytes + 255) / 256 * 256;
+  return true;
 }
 
 }  // namespace
@@ -410,7 +437,7 @@ extern "C" tchgeo_status tchgeo_part_begin_hop(const int64_t* samples, int64_t s
                                                const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
                                                int64_t cols_per_rank, int32_t world, uint32_t batch_base,
                                                int64_t* counts, int64_t* cursor, int64_t* req, int32_t* err_word,
-                                               tchgeo_stream stream_) {
+                                               void* workspace, size_t workspace_bytes, tchgeo_stream stream_) {
   TCHGEO_REQUIRE(world >= 1 && world <= PT_MAX_WORLD, "world size must be in [1, 64]");
   TCHGEO_REQUIRE(err_word != nullptr, "NULL pointer");
   TCHGEO_REQUIRE(num_batches >= 0 && frontier_cap >= 0 && cols_per_rank >= 1 && samples_stride >= 0, "bad argument");
@@ -418,18 +445,23 @@ extern "C" tchgeo_status tchgeo_part_begin_hop(const int64_t* samples, int64_t s
   cudaStream_t stream = (cudaStream_t)stream_;
   TCHGEO_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)world * 8, stream));
   TCHGEO_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)world * 8, stream));
-  const int64_t total = num_batches * frontier_cap;
-  if (total == 0) return TCHGEO_OK;
+  if (num_batches == 0 || frontier_cap == 0) return TCHGEO_OK;
   TCHGEO_REQUIRE(samples && fr_end && req, "NULL pointer");
-  const int64_t grid = (total + PT_THREADS - 1) / PT_THREADS;
-  TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "frontier too large for one launch");
+  TCHGEO_REQUIRE(num_batches <= 65535, "at most 65535 batches per call");
+  PartWs W;
+  TCHGEO_REQUIRE(part_ws_layout(num_batches, frontier_cap, W), "frontier too large for one call");
+  TCHGEO_REQUIRE(workspace && workspace_bytes >= W.total, "workspace too small: need %zu bytes", W.total);
+  int32_t* slot_of = (int32_t*)((char*)workspace + W.off_slot);
+  const int64_t gx = (frontier_cap + PT_THREADS - 1) / PT_THREADS;
+  TCHGEO_REQUIRE(gx < ((int64_t)1 << 31), "frontier too large for one launch");
+  const dim3 grid((unsigned)gx, (unsigned)num_batches);
   PartFrontier f;
   f.samples = samples; f.samples_stride = samples_stride; f.fr_begin = fr_begin; f.fr_end = fr_end;
   f.B = num_batches; f.capF = frontier_cap; f.cols_per_rank = cols_per_rank; f.world = world; f.batch_base = batch_base;
-  part_count_kernel<<<(unsigned)grid, PT_THREADS, 0, stream>>>(f, (unsigned long long*)counts, (uint32_t*)err_word);
+  part_count_kernel<<<grid, PT_THREADS, 0, stream>>>(f, (unsigned long long*)counts, (uint32_t*)err_word);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
-  part_scatter_kernel<<<(unsigned)grid, PT_THREADS, 0, stream>>>(f, (const unsigned long long*)counts,
-                                                                (unsigned long long*)cursor, req);
+  part_scatter_kernel<<<grid, PT_THREADS, 0, stream>>>(f, (const unsigned long long*)counts,
+                                                      (unsigned long long*)cursor, req, slot_of);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
   return TCHGEO_OK;
 }
@@ -446,17 +478,14 @@ extern "C" tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, c
                       (cudaStream_t)stream_);
 }
 
-extern "C" size_t tchgeo_part_finish_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap) {
-  const int64_t n = num_batches * frontier_cap + 1;
-  if (n <= 0 || n >= ((int64_t)1 << 31)) return 0;
-  size_t cub_bytes = 0;
-  if (cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (const int32_t*)nullptr, (int32_t*)nullptr, n) != cudaSuccess) return 0;
-  return 256 + ((size_t)n * 4 + 255) / 256 * 256 + (cub_bytes + 255) / 256 * 256;
+extern "C" size_t tchgeo_part_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap) {
+  PartWs W;
+  return part_ws_layout(num_batches, frontier_cap, W) ? W.total : 0;
 }
 
 extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int32_t* ans, int64_t num_requests,
                                                 int64_t fanout, const int64_t* owner_edge_base, int64_t cols_per_rank,
-                                                int32_t world, uint32_t batch_base, const int64_t* fr_begin,
+                                                int32_t world, const int64_t* fr_begin, const int64_t* fr_end,
                                                 int64_t num_batches, int64_t frontier_cap, const int64_t* node_len_in,
                                                 const int64_t* edge_len_in, int64_t* node_len_out, int64_t* edge_len_out,
                                                 int64_t* samples, int64_t samples_stride, int64_t* rows, int64_t* cols,
@@ -464,39 +493,43 @@ extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int32_
                                                 void* workspace, size_t workspace_bytes, tchgeo_stream stream_) {
   TCHGEO_REQUIRE(num_requests >= 0 && fanout >= 0 && fanout < (1 << 20) && num_batches >= 0 && frontier_cap >= 0,
                  "bad argument");
-  TCHGEO_REQUIRE(node_len_in && edge_len_in && node_len_out && edge_len_out && err_word && owner_edge_base, "NULL pointer");
+  TCHGEO_REQUIRE(num_batches <= 65535, "at most 65535 batches per call");
+  TCHGEO_REQUIRE(node_len_in && edge_len_in && node_len_out && edge_len_out && err_word && owner_edge_base && fr_end,
+                 "NULL pointer");
   TCHGEO_REQUIRE(world >= 1 && world <= PT_MAX_WORLD && cols_per_rank >= 1, "bad partition");
-  const size_t need = tchgeo_part_finish_hop_workspace_bytes(num_batches, frontier_cap);
-  TCHGEO_REQUIRE(need != 0, "frontier too large for one call");
-  TCHGEO_REQUIRE(workspace && workspace_bytes >= need, "workspace too small: need %zu bytes", need);
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (num_batches == 0) return TCHGEO_OK;
+  if (frontier_cap == 0 || fanout == 0) {  // nothing can be appended: the lengths carry over
+    TCHGEO_CUDA_CHECK(cudaMemcpyAsync(node_len_out, node_len_in, (size_t)num_batches * 8, cudaMemcpyDeviceToDevice, stream));
+    TCHGEO_CUDA_CHECK(cudaMemcpyAsync(edge_len_out, edge_len_in, (size_t)num_batches * 8, cudaMemcpyDeviceToDevice, stream));
+    return TCHGEO_OK;
+  }
+  PartWs W;
+  TCHGEO_REQUIRE(part_ws_layout(num_batches, frontier_cap, W), "frontier too large for one call");
+  TCHGEO_REQUIRE(workspace && workspace_bytes >= W.total, "workspace too small: need %zu bytes", W.total);
+  TCHGEO_REQUIRE(frontier_cap * fanout < ((int64_t)1 << 31), "frontier_cap * fanout must stay below 2^31");
+  TCHGEO_REQUIRE(num_requests == 0 || (req && ans), "NULL pointer");
+  TCHGEO_REQUIRE(samples && rows && cols && edge_index, "NULL pointer");
   const int64_t n = num_batches * frontier_cap + 1;
-  int32_t* fcnt = (int32_t*)((char*)workspace + 256);
-  void* cub_tmp = (char*)fcnt + ((size_t)n * 4 + 255) / 256 * 256;
-  size_t cub_bytes = need - 256 - ((size_t)n * 4 + 255) / 256 * 256;
   PartFinish p;
   p.req = req; p.ans = ans; p.edge_base = owner_edge_base; p.cols_per_rank = cols_per_rank; p.world = world;
-  p.F = num_requests; p.k = (int32_t)fanout; p.batch_base = batch_base; p.fr_begin = fr_begin;
-  p.B = num_batches; p.capF = frontier_cap; p.fcnt = fcnt;
+  p.F = num_requests; p.k = (int32_t)fanout; p.fr_begin = fr_begin; p.fr_end = fr_end;
+  p.B = num_batches; p.capF = frontier_cap;
+  p.slot_of = (const int32_t*)((char*)workspace + W.off_slot);
+  p.fcnt = (int32_t*)((char*)workspace + W.off_fcnt);
   p.node_len_in = node_len_in; p.edge_len_in = edge_len_in; p.node_len_out = node_len_out; p.edge_len_out = edge_len_out;
   p.samples = samples; p.samples_stride = samples_stride; p.rows = rows; p.cols = cols; p.eidx = edge_index;
   p.edges_stride = edges_stride; p.err = (uint32_t*)err_word;
-  TCHGEO_CUDA_CHECK(cudaMemsetAsync(fcnt, 0, (size_t)n * 4, stream));
-  if (num_requests > 0 && fanout > 0) {
-    TCHGEO_REQUIRE(req && ans && samples && rows && cols && edge_index, "NULL pointer");
-    part_cnt_kernel<<<(unsigned)((num_requests + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, stream>>>(p);
-    TCHGEO_CUDA_CHECK(cudaGetLastError());
-  }
-  TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, (const int32_t*)fcnt, fcnt, n, stream));
-  if (num_batches > 0) {
-    part_len_kernel<<<(unsigned)((num_batches + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, stream>>>(p);
-    TCHGEO_CUDA_CHECK(cudaGetLastError());
-  }
-  if (num_requests > 0 && fanout > 0) {
-    const int64_t total = num_requests * fanout;
-    TCHGEO_REQUIRE((total + PT_THREADS - 1) / PT_THREADS < ((int64_t)1 << 31), "too many answers for one launch");
-    part_emit_kernel<<<(unsigned)((total + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, stream>>>(p);
-    TCHGEO_CUDA_CHECK(cudaGetLastError());
-  }
+  const dim3 gcnt((unsigned)((frontier_cap + PT_THREADS - 1) / PT_THREADS), (unsigned)num_batches);
+  part_cnt_kernel<<<gcnt, PT_THREADS, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  size_t cub_bytes = W.cub_bytes;
+  TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum((char*)workspace + W.off_cub, cub_bytes, (const int32_t*)p.fcnt, p.fcnt, n,
+                                                  stream));
+  part_len_kernel<<<(unsigned)((num_batches + PT_THREADS - 1) / PT_THREADS), PT_THREADS, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  const dim3 gemit((unsigned)((frontier_cap * fanout + PT_THREADS - 1) / PT_THREADS), (unsigned)num_batches);
+  part_emit_kernel<<<gemit, PT_THREADS, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
   return TCHGEO_OK;
 }

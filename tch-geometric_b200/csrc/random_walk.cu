@@ -154,6 +154,113 @@ __global__ void __launch_bounds__(WALK_THREADS, MINB) walk_kernel(const WalkPara
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Temporal random walk, src/algo/random_walk.rs:80-158.
+// One warp per walker.  Every step scans cur's whole adjacency (the reference does the same): an edge's
+// timestamp is edge_timestamps[e], or node_timestamps[neighbour] when that is -1 (:118-122); it passes when it
+// is -1, when the walk's start timestamp is -1, or when it lies in [start_ts + w0, start_ts + w1) (:125-135).
+// The next node is reservoir_sampling with k = 1 over the passing neighbours (:138): the item at passing
+// position i >= 1 replaces the pick iff its draw j ~ U[0, i) is 0, so the LAST such item wins, else the first
+// passing item -- evaluated in parallel with ballots (passing position) and a warp max.  A step without passing
+// neighbours restarts from a uniformly drawn earlier position of the same walk (:140-144).
+// Draws: item i uses word i&3 of Philox(walker, step, TAG_TEMPO | (i>>2) << 8); restart uses TAG_TEMPO_RESTART.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t TAG_TEMPO = 6u;
+constexpr uint32_t TAG_TEMPO_RESTART = 7u;
+constexpr int TEMPO_THREADS = 256;
+
+struct TempoParams {
+  const int64_t* row_ptrs;
+  const int64_t* col_indices;
+  const int64_t* node_ts;
+  const int64_t* edge_ts;
+  const int64_t* start;
+  const int64_t* start_ts;
+  int64_t* walks;
+  int64_t* walks_ts;
+  uint32_t* err;
+  int64_t num_rows, num_node_ts, num_walks, L, walker_base, w0, w1;
+  uint32_t key0, key1;
+};
+
+__global__ void __launch_bounds__(TEMPO_THREADS) tempo_walk_kernel(const TempoParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = ((int64_t)blockIdx.x * TEMPO_THREADS + threadIdx.x) >> 5;
+  if (i >= p.num_walks) return;
+  const uint64_t walker = (uint64_t)(p.walker_base + i);
+  const uint32_t wlo = (uint32_t)walker, whi = (uint32_t)(walker >> 32);
+  int64_t* row = p.walks + i * p.L;
+  int64_t* row_ts = p.walks_ts + i * p.L;
+  int64_t cur = p.start[i];
+  const int64_t i_ts = p.start_ts[i];
+  const int64_t lo_w = i_ts + p.w0, hi_w = i_ts + p.w1;  // Range: lo_w <= t < hi_w
+  if (lane == 0) { row[0] = cur; row_ts[0] = i_ts; }
+  bool dead = false;
+  for (int64_t l = 0; l + 1 < p.L; ++l) {
+    int64_t next = -1, next_ts = -1;
+    if (!dead) {
+      if (cur < 0 || cur >= p.num_rows) {  // neighbors_range(cur) out of bounds: the reference panics
+        if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX);
+        dead = true;
+      }
+    }
+    if (!dead) {
+      const int64_t b = __ldg(p.row_ptrs + cur), e = __ldg(p.row_ptrs + cur + 1);
+      uint32_t npass = 0;                 // passing neighbours seen so far (warp-uniform)
+      uint32_t best = 0;                  // largest passing position >= 1 whose draw hit, 0 = none (per lane)
+      bool has_first = false;             // this lane holds passing position 0
+      int64_t best_node = -1, best_ts = -1, first_node = -1, first_ts = -1;
+      for (int64_t base = b; base < e; base += 32) {
+        const int64_t ep = base + lane;
+        bool pass = false;
+        int64_t node = -1, ts = -1;
+        if (ep < e) {
+          node = __ldg(p.col_indices + ep);
+          ts = __ldg(p.edge_ts + ep);
+          if (ts == -1) {  // NAN_TIMESTAMP: fall back to the neighbour's own timestamp, :118-122
+            if (node < 0 || node >= p.num_node_ts) atomicOr(p.err, DEV_ERR_INDEX);
+            else ts = __ldg(p.node_ts + node);
+          }
+          pass = ts == -1 || i_ts == -1 || (lo_w <= ts && ts < hi_w);
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        if (pass) {
+          const uint32_t pos = npass + (uint32_t)__popc(m & ((1u << lane) - 1u));
+          if (pos == 0) {
+            has_first = true; first_node = node; first_ts = ts;
+          } else {
+            const Philox4 r = philox4x32_10(wlo, whi, (uint32_t)l, TAG_TEMPO | ((pos >> 2) << 8), p.key0, p.key1);
+            if (__umulhi(pick4(r, pos & 3u), pos) == 0u) { best = pos; best_node = node; best_ts = ts; }  // later wins
+          }
+        }
+        npass += (uint32_t)__popc(m);
+      }
+      if (npass >= (1u << 24)) { if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX); dead = true; }
+      if (!dead && npass > 0) {
+        uint32_t top = best;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+        // the winner is the passing item at position `top`; top == 0: no later item hit, the first one stays
+        const uint32_t om = __ballot_sync(0xffffffffu, top ? (best == top) : has_first);
+        const int src = __ffs(om) - 1;
+        next = __shfl_sync(0xffffffffu, top ? best_node : first_node, src);
+        next_ts = __shfl_sync(0xffffffffu, top ? best_ts : first_ts, src);
+      } else if (!dead) {
+        // restart: a uniformly drawn earlier position of this walk (lane 0 re-reads what it wrote), :140-144
+        const Philox4 r = philox4x32_10(wlo, whi, (uint32_t)l, TAG_TEMPO_RESTART, p.key0, p.key1);
+        const int64_t ri = (int64_t)__umulhi(r.x, (uint32_t)(l + 1));
+        if (lane == 0) { next = row[ri]; next_ts = row_ts[ri]; }
+        next = __shfl_sync(0xffffffffu, next, 0);
+        next_ts = __shfl_sync(0xffffffffu, next_ts, 0);
+      }
+    }
+    if (dead) { next = -1; next_ts = -1; }
+    cur = next;
+    if (lane == 0) { row[l + 1] = cur; row_ts[l + 1] = next_ts; }
+  }
+}
+
 }  // namespace
 }  // namespace tchgeo
 
@@ -228,4 +335,39 @@ extern "C" tchgeo_status tchgeo_random_walk_ex(const int64_t* row_ptrs, int64_t 
   TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
   if (attempts_out) *attempts_out = h[0];
   return status_from_dev_err((uint32_t)h[1]);
+}
+
+extern "C" tchgeo_status tchgeo_tempo_random_walk(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,
+                                                  const int64_t* node_timestamps, int64_t num_node_timestamps,
+                                                  const int64_t* edge_timestamps, const int64_t* start,
+                                                  const int64_t* start_timestamps, int64_t num_walks, int64_t walk_length,
+                                                  int64_t window_lo, int64_t window_hi, uint64_t seed, int64_t walker_base,
+                                                  int64_t* walks, int64_t* walks_timestamps, int32_t* scratch,
+                                                  tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(num_walks >= 0 && num_rows >= 0 && num_node_timestamps >= 0, "negative size");
+  TCHGEO_REQUIRE(walk_length >= 0 && walk_length < ((int64_t)1 << 31), "walk_length out of range");
+  TCHGEO_REQUIRE(scratch != nullptr, "NULL pointer");
+  if (num_walks == 0) return TCHGEO_OK;
+  if (walk_length == 0) {  // walks_data[i * L] on an empty tensor: index panic, random_walk.rs:113
+    set_last_error("walk_length 0 with a non-empty start (the reference panics)");
+    return TCHGEO_ERR_REFERENCE_PANIC;
+  }
+  TCHGEO_REQUIRE(row_ptrs && start && start_timestamps && walks && walks_timestamps, "NULL pointer");
+  TempoParams tp;
+  tp.row_ptrs = row_ptrs; tp.col_indices = col_indices; tp.node_ts = node_timestamps; tp.edge_ts = edge_timestamps;
+  tp.start = start; tp.start_ts = start_timestamps; tp.walks = walks; tp.walks_ts = walks_timestamps;
+  tp.err = (uint32_t*)scratch;
+  tp.num_rows = num_rows; tp.num_node_ts = num_node_timestamps; tp.num_walks = num_walks; tp.L = walk_length;
+  tp.walker_base = walker_base; tp.w0 = window_lo; tp.w1 = window_hi;
+  tp.key0 = (uint32_t)seed; tp.key1 = (uint32_t)(seed >> 32);
+  cudaStream_t stream = (cudaStream_t)stream_;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4, stream));
+  const int64_t grid = (num_walks * 32 + TEMPO_THREADS - 1) / TEMPO_THREADS;
+  TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many walkers for one launch");
+  tempo_walk_kernel<<<(unsigned)grid, TEMPO_THREADS, 0, stream>>>(tp);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  uint32_t h = 0;
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&h, scratch, 4, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  return status_from_dev_err(h);
 }

@@ -26,6 +26,7 @@ from .ops import (  # noqa: F401
     rel_key,
     rng_reseed,
     set_l2_fetch_granularity,
+    tempo_random_walk,
     to_csc,
     to_csr,
     unique_relabel,

@@ -770,6 +770,37 @@ def negative_sample_neighbors_heterogenous(node_types: List[str], edge_types: Li
                      _rng_get() if seed is None else seed)
 
 
+def tempo_random_walk(row_ptrs: Tensor, col_indices: Tensor, node_timestamps: Tensor, edge_timestamps: Tensor,
+                      start: Tensor, start_timestamps: Tensor, walk_length: int, window: Tuple[int, int], *,
+                      seed: Optional[int] = None, walker_base: int = 0) -> Tuple[Tensor, Tensor]:
+    """python.rs:610-643 -> random_walk.rs:80-158.  Returns (walks, walk_timestamps), both [S, walk_length]."""
+    _check(row_ptrs, torch.int64, "row_ptrs")
+    dev = row_ptrs.device
+    _check(col_indices, torch.int64, "col_indices", dev)
+    _check(node_timestamps, torch.int64, "node_timestamps", dev)
+    _check(edge_timestamps, torch.int64, "edge_timestamps", dev)
+    if edge_timestamps.numel() < col_indices.numel():
+        raise N.ReferencePanic("edge_timestamps is shorter than col_indices")  # get_range slices out of bounds
+    start = _as_seed_matrix(start, dev, "start").reshape(-1)
+    start_timestamps = _as_seed_matrix(start_timestamps, dev, "start_timestamps").reshape(-1)
+    S = start.numel()
+    if start_timestamps.numel() < S:
+        raise N.ReferencePanic("start_timestamps is shorter than start")
+    L = int(walk_length)
+    if L < 0:
+        raise RuntimeError("walk_length must not be negative")  # Tensor::full with a negative size fails in libtorch
+    walks = torch.empty((S, L), dtype=torch.int64, device=dev)
+    walks_ts = torch.empty((S, L), dtype=torch.int64, device=dev)
+    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    w0, w1 = int(window[0]), int(window[1])
+    with torch.cuda.device(dev):
+        N.check(N.lib.tchgeo_tempo_random_walk(_ptr(row_ptrs), row_ptrs.numel() - 1, _ptr(col_indices), _ptr(node_timestamps),
+                                               node_timestamps.numel(), _ptr(edge_timestamps), _ptr(start),
+                                               _ptr(start_timestamps), S, L, w0, w1, _rng_get() if seed is None else seed,
+                                               int(walker_base), _ptr(walks), _ptr(walks_ts), _ptr(scratch), _stream(dev)))
+    return walks, walks_ts
+
+
 # ---------------------------------------------------------------------------------------------
 # downstream gather (the step after the sampler in every loader: x[samples], edge_attr[perm[edge_index]])
 # ---------------------------------------------------------------------------------------------

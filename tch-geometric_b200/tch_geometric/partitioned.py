@@ -272,14 +272,37 @@ class PartitionedBatches:
         return self.samples[b, :ns], self.rows[b, :ne], self.cols[b, :ne], self.edge_index[b, :ne], lo
 
 
+class _PlanGroup:
+    """A contiguous range of a plan's batches with its own stream, request buffer and workspace: the groups of a
+    plan advance through the hop phases in lock step on different streams, so one group's all-to-all overlaps the
+    other group's kernels."""
+
+    def __init__(self, plan, b0, b1):
+        dev = plan.device
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.b0, self.b1, self.B = b0, b1, b1 - b0
+        self.stream = torch.cuda.Stream(device=dev) if plan.num_groups > 1 else None
+        fmax = max(plan.capF) if plan.capF else 0
+        self.req = torch.empty((max(self.B * fmax, 1), 2), **i64)
+        self.counts = torch.zeros((2, max(plan.comm.world, 1)), **i64)   # [0] per-owner request counts, [1] cursor
+        ws = max((N.lib.tchgeo_part_hop_workspace_bytes(self.B, c) for c in plan.capF), default=0)
+        if plan.capF and ws == 0:
+            raise ValueError("frontier too large for one call: use fewer batches per call")
+        self.ws = torch.empty(max(int(ws), 1), dtype=torch.uint8, device=dev)
+        self.samples, self.rows = plan.samples[b0:b1], plan.rows[b0:b1]
+        self.cols, self.eidx = plan.cols[b0:b1], plan.eidx[b0:b1]
+        self.hop = {}   # transient tensors / counts of the hop in flight
+
+
 class PartitionedPlan:
     """neighbor_sampling_homogenous over a column-partitioned CSC, device pipeline.  `sample` is collective."""
 
     def __init__(self, part: ColumnPartition, num_batches: int, seeds_per_batch: int, num_neighbors: Sequence[int],
-                 sampler=None, comm=None, serve_rows=None, edge_bases=None):
+                 sampler=None, comm=None, serve_rows=None, edge_bases=None, groups: Optional[int] = None):
         """serve_rows(r_req [n,2], recv_counts, fanout, seed, ans [n,2k] int32) overrides the owner side (tests simulate
         several owners on one GPU with it); default: tchgeo_serve_requests_rows over `part`.
-        edge_bases: every rank's ColumnPartition.edge_base (default: all-gathered through the communicator)."""
+        edge_bases: every rank's ColumnPartition.edge_base (default: all-gathered through the communicator).
+        groups: batch groups pipelined on separate streams (default 1: the overlap did not pay on 2 B200s)."""
         self.part = part
         self.serve_rows = serve_rows
         self.fanouts = [int(k) for k in num_neighbors]
@@ -307,77 +330,114 @@ class PartitionedPlan:
         self.cols = torch.empty((B, self.cap_e), **i64)
         self.eidx = torch.empty((B, self.cap_e), **i64)
         self.lens = torch.zeros((2, H + 1, B), **i64)               # [0] node_len, [1] edge_len after h hops
-        self.counts = torch.zeros((2, max(self.comm.world, 1)), **i64)  # [0] per-owner request counts, [1] cursor
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         if edge_bases is None:
             edge_bases = self.comm.all_gather_int(part.edge_base, dev)
         if len(edge_bases) != self.comm.world:
             raise ValueError("edge_bases must have one entry per rank")
         self.edge_bases = torch.tensor([int(x) for x in edge_bases], **i64)
-        fmax = max(self.capF) if self.capF else 0
-        self.req = torch.empty((max(B * fmax, 1), 2), **i64)
-        ws = max((N.lib.tchgeo_part_finish_hop_workspace_bytes(B, c) for c in self.capF), default=0)
-        if self.capF and ws == 0:
-            raise ValueError("frontier too large for one call: use fewer batches per call")
-        self.ws = torch.empty(max(int(ws), 1), dtype=torch.uint8, device=dev)
+        if groups is None:
+            groups = 1   # measured on 2 B200s: pipelining batch groups over streams is slower (7.7 ms -> 8.3 ms)
+        self.num_groups = max(1, min(int(groups), max(B, 1)))
+        cuts = [B * g // self.num_groups for g in range(self.num_groups + 1)]
+        with torch.cuda.device(dev):
+            self.groups = [_PlanGroup(self, cuts[g], cuts[g + 1]) for g in range(self.num_groups)]
         self.stats = {"requests_sent": 0, "request_bytes": 0, "answer_bytes": 0}
-        self.profile = None   # set to {} to collect per-phase device times (ms, CUDA events) of the next calls
+        self.profile = None   # set to {} to collect per-phase device times (ms, CUDA events, group 0's stream)
 
-    def _mark(self, marks, name):
-        if marks is not None:
+    def _mark(self, g, marks, name):
+        if marks is not None and g is self.groups[0]:
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             marks.append((name, ev))
+
+    # ---- the five phases of a hop, each issued on the group's stream -------------------------------------
+    def _begin(self, g, h, batch_base):
+        lens = self.lens
+        g.hop = {"fr_begin": lens[0, h - 1, g.b0:g.b1] if h > 0 else None}
+        N.check(N.lib.tchgeo_part_begin_hop(_ptr(g.samples), self.cap_n, _ptr(g.hop["fr_begin"]), _ptr(lens[0, h, g.b0:g.b1]),
+                                            g.B, self.capF[h], self.part.cols_per_rank, self.comm.world, batch_base + g.b0,
+                                            _ptr(g.counts[0]), _ptr(g.counts[1]), _ptr(g.req), _ptr(self.err),
+                                            _ptr(g.ws), g.ws.numel(), _stream(self.device)))
+
+    def _requests(self, g):
+        rc, sc, r_req = self.comm.exchange_rows(g.counts[0], g.req)   # host reads the counts: syncs g's stream only
+        g.hop.update(rc=rc, sc=sc, r_req=r_req, F=sum(sc), n_recv=sum(rc))
+
+    def _serve(self, g, k, seed):
+        hp = g.hop
+        hp["ans"] = torch.empty((max(hp["n_recv"], 1), 2 * k), dtype=torch.int32, device=self.device)
+        if self.serve_rows is not None:
+            self.serve_rows(hp["r_req"], hp["rc"], k, seed, hp["ans"])
+        else:
+            serve_rows(self.part, hp["r_req"], hp["n_recv"], k, self.kind, seed, hp["ans"], self.err)
+
+    def _answers(self, g):
+        hp = g.hop
+        hp["back"] = self.comm.return_rows(hp["ans"], hp["n_recv"], hp["F"], hp["sc"], hp["rc"])
+
+    def _finish(self, g, h, k, batch_base):
+        hp, lens, sl = g.hop, self.lens, slice(g.b0, g.b1)
+        N.check(N.lib.tchgeo_part_finish_hop(_ptr(g.req), _ptr(hp["back"]), hp["F"], k, _ptr(self.edge_bases),
+                                             self.part.cols_per_rank, self.comm.world,
+                                             _ptr(hp["fr_begin"]), _ptr(lens[0, h, sl]), g.B, self.capF[h], _ptr(lens[0, h, sl]),
+                                             _ptr(lens[1, h, sl]), _ptr(lens[0, h + 1, sl]), _ptr(lens[1, h + 1, sl]),
+                                             _ptr(g.samples), self.cap_n, _ptr(g.rows), _ptr(g.cols), _ptr(g.eidx),
+                                             self.cap_e, _ptr(self.err), _ptr(g.ws), g.ws.numel(), _stream(self.device)))
+        self.stats["requests_sent"] += hp["F"]
+        self.stats["request_bytes"] += 16 * hp["F"]
+        self.stats["answer_bytes"] += 8 * k * hp["F"]
 
     def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> PartitionedBatches:
         """inputs [B, S] i64 (this rank's batches; device or pinned host) -> PartitionedBatches"""
         if inputs.dim() != 2 or inputs.dtype != torch.int64 or tuple(inputs.shape) != (self.B, self.S):
             raise ValueError(f"inputs must be an int64 tensor of shape {(self.B, self.S)}")
         seed = _rng_get() if seed is None else seed
-        dev, B, S, part, comm, lib = self.device, self.B, self.S, self.part, self.comm, N.lib
-        world = comm.world
+        dev, S = self.device, self.S
         with torch.cuda.device(dev):
-            stream = _stream(dev)
+            main = torch.cuda.current_stream(dev)
             self.samples[:, :S].copy_(inputs, non_blocking=True)
             self.err.zero_()
             self.lens.zero_()
             self.lens[0, 0].fill_(S)
             marks = [] if self.profile is not None else None
-            self._mark(marks, "start")
+
+            def on(g):
+                return torch.cuda.stream(g.stream) if g.stream is not None else torch.cuda.stream(main)
+
+            for g in self.groups:
+                if g.stream is not None:
+                    g.stream.wait_stream(main)
+                with on(g):
+                    self._mark(g, marks, "start")
             for h, k in enumerate(self.fanouts):
-                fr_begin = self.lens[0, h - 1] if h > 0 else None
-                N.check(lib.tchgeo_part_begin_hop(_ptr(self.samples), self.cap_n, _ptr(fr_begin), _ptr(self.lens[0, h]), B,
-                                                  self.capF[h], part.cols_per_rank, world, batch_base,
-                                                  _ptr(self.counts[0]), _ptr(self.counts[1]), _ptr(self.req),
-                                                  _ptr(self.err), stream))
-                self._mark(marks, "bucket")
-                recv_counts, send_counts, r_req = comm.exchange_rows(self.counts[0], self.req)
-                self._mark(marks, "a2a_requests")
-                F, n_recv = sum(send_counts), sum(recv_counts)
-                ans = torch.empty((max(n_recv, 1), 2 * k), dtype=torch.int32, device=dev)
-                if self.serve_rows is not None:
-                    self.serve_rows(r_req, recv_counts, k, seed, ans)
-                else:
-                    serve_rows(part, r_req, n_recv, k, self.kind, seed, ans, self.err)
-                self._mark(marks, "serve")
-                back = comm.return_rows(ans, n_recv, F, send_counts, recv_counts)
-                self._mark(marks, "a2a_answers")
-                N.check(lib.tchgeo_part_finish_hop(_ptr(self.req), _ptr(back), F, k, _ptr(self.edge_bases),
-                                                   part.cols_per_rank, world, batch_base, _ptr(fr_begin), B,
-                                                   self.capF[h], _ptr(self.lens[0, h]), _ptr(self.lens[1, h]),
-                                                   _ptr(self.lens[0, h + 1]), _ptr(self.lens[1, h + 1]),
-                                                   _ptr(self.samples), self.cap_n, _ptr(self.rows), _ptr(self.cols),
-                                                   _ptr(self.eidx), self.cap_e, _ptr(self.err), _ptr(self.ws),
-                                                   self.ws.numel(), stream))
-                self._mark(marks, "layout")
-                self.stats["requests_sent"] += F
-                self.stats["request_bytes"] += 16 * F
-                self.stats["answer_bytes"] += 8 * k * F
+                # phase-major issue order: while the host waits for one group's counts and that group's
+                # all-to-all runs, the other group's kernels are already queued on its own stream
+                for g in self.groups:
+                    with on(g):
+                        self._begin(g, h, batch_base)
+                        self._mark(g, marks, "bucket")
+                for g in self.groups:
+                    with on(g):
+                        self._requests(g)
+                        self._mark(g, marks, "a2a_requests")
+                        self._serve(g, k, seed)
+                        self._mark(g, marks, "serve")
+                for g in self.groups:
+                    with on(g):
+                        self._answers(g)
+                        self._mark(g, marks, "a2a_answers")
+                        self._finish(g, h, k, batch_base)
+                        self._mark(g, marks, "layout")
+            for g in self.groups:
+                if g.stream is not None:
+                    main.wait_stream(g.stream)
+                g.hop = {}
             host = torch.cat([self.lens.reshape(-1), self.err.to(torch.int64)]).cpu().numpy()   # the call's last sync
         if marks is not None:
             for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
                 self.profile[name] = self.profile.get(name, 0.0) + e0.elapsed_time(e1)
             self.profile["calls"] = self.profile.get("calls", 0) + 1
-        N.check(lib.tchgeo_status_from_error_word(int(host[-1]) & 0xFFFFFFFF))
-        lens = host[:-1].reshape(2, len(self.fanouts) + 1, B)
+        N.check(N.lib.tchgeo_status_from_error_word(int(host[-1]) & 0xFFFFFFFF))
+        lens = host[:-1].reshape(2, len(self.fanouts) + 1, self.B)
         return PartitionedBatches(self, lens[0], lens[1])
