@@ -71,12 +71,12 @@ class SingleComm:
     def exchange(self, send_counts: Tensor, *tensors):
         return (send_counts,) + tuple(tensors)
 
-    def exchange_rows(self, send_counts: Tensor, rows: Tensor):
+    def exchange_rows(self, send_counts: Tensor, rows: Tensor, alloc=None):
         """-> (recv_counts list, send_counts list, received rows); reads the counts on the host (one sync)"""
         sc = send_counts.tolist()
         return sc, sc, rows
 
-    def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts):
+    def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts, alloc=None):
         return rows
 
     def all_gather_int(self, value: int, device):
@@ -101,13 +101,15 @@ class DistComm:
             outs.append(out)
         return (recv_counts,) + tuple(outs)
 
-    def exchange_rows(self, send_counts: Tensor, rows: Tensor):
-        """Requests: all-to-all of the per-owner counts, one host read of both count vectors, all-to-all(v) of the rows."""
+    def exchange_rows(self, send_counts: Tensor, rows: Tensor, alloc=None):
+        """Requests: all-to-all of the per-owner counts, one host read of both count vectors, all-to-all(v) of the rows.
+        alloc(n) -> [max(n,1), ...] output buffer (default: a fresh tensor)."""
         both = torch.empty((2, self.world), dtype=send_counts.dtype, device=send_counts.device)
         both[0].copy_(send_counts)
         dist.all_to_all_single(both[1], both[0], group=self.group)
         sc, rc = both.tolist()
-        out = torch.empty((max(sum(rc), 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        out = alloc(sum(rc)) if alloc is not None else \
+            torch.empty((max(sum(rc), 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
         dist.all_to_all_single(out[:sum(rc)], rows[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc, group=self.group)
         return rc, sc, out
 
@@ -117,9 +119,10 @@ class DistComm:
         dist.all_gather(out, mine, group=self.group)
         return [int(x.item()) for x in out]
 
-    def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts):
+    def return_rows(self, rows: Tensor, n_rows: int, n_back: int, send_counts, recv_counts, alloc=None):
         """Answers travel the reverse way: what was received is sent back, split sizes swapped."""
-        out = torch.empty((max(n_back, 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
+        out = alloc(n_back) if alloc is not None else \
+            torch.empty((max(n_back, 1),) + tuple(rows.shape[1:]), dtype=rows.dtype, device=rows.device)
         dist.all_to_all_single(out[:n_back], rows[:n_rows], output_split_sizes=list(send_counts),
                                input_split_sizes=list(recv_counts), group=self.group)
         return out
@@ -292,6 +295,17 @@ class _PlanGroup:
         self.samples, self.rows = plan.samples[b0:b1], plan.rows[b0:b1]
         self.cols, self.eidx = plan.cols[b0:b1], plan.eidx[b0:b1]
         self.hop = {}   # transient tensors / counts of the hop in flight
+        self._bufs = {}
+
+    def buf(self, name, rows, cols, dtype, device):
+        """[rows, cols] view of a persistent buffer that only ever grows (x1.25): the exchange sees stable addresses
+        and the hot loop never reaches the allocator once the sizes have settled."""
+        need = max(int(rows), 1) * int(cols)
+        t = self._bufs.get(name)
+        if t is None or t.dtype != dtype or t.numel() < need:
+            t = torch.empty(int(need * 1.25) + 16, dtype=dtype, device=device)
+            self._bufs[name] = t
+        return t[:need].view(max(int(rows), 1), int(cols))
 
 
 class PartitionedPlan:
@@ -361,12 +375,14 @@ class PartitionedPlan:
                                             _ptr(g.ws), g.ws.numel(), _stream(self.device)))
 
     def _requests(self, g):
-        rc, sc, r_req = self.comm.exchange_rows(g.counts[0], g.req)   # host reads the counts: syncs g's stream only
+        # host reads the counts: syncs g's stream only
+        rc, sc, r_req = self.comm.exchange_rows(g.counts[0], g.req,
+                                                lambda n: g.buf("r_req", n, 2, torch.int64, self.device))
         g.hop.update(rc=rc, sc=sc, r_req=r_req, F=sum(sc), n_recv=sum(rc))
 
     def _serve(self, g, k, seed):
         hp = g.hop
-        hp["ans"] = torch.empty((max(hp["n_recv"], 1), 2 * k), dtype=torch.int32, device=self.device)
+        hp["ans"] = g.buf("ans", hp["n_recv"], 2 * k, torch.int32, self.device)
         if self.serve_rows is not None:
             self.serve_rows(hp["r_req"], hp["rc"], k, seed, hp["ans"])
         else:
@@ -374,7 +390,8 @@ class PartitionedPlan:
 
     def _answers(self, g):
         hp = g.hop
-        hp["back"] = self.comm.return_rows(hp["ans"], hp["n_recv"], hp["F"], hp["sc"], hp["rc"])
+        hp["back"] = self.comm.return_rows(hp["ans"], hp["n_recv"], hp["F"], hp["sc"], hp["rc"],
+                                           lambda n: g.buf("back", n, hp["ans"].shape[1], torch.int32, self.device))
 
     def _finish(self, g, h, k, batch_base):
         hp, lens, sl = g.hop, self.lens, slice(g.b0, g.b1)

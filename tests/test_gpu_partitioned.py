@@ -68,11 +68,11 @@ class _FakeWorld:
     def __init__(self, world):
         self.rank, self.world = 0, world
 
-    def exchange_rows(self, send_counts, rows):
+    def exchange_rows(self, send_counts, rows, alloc=None):
         sc = send_counts.tolist()
         return sc, sc, rows
 
-    def return_rows(self, rows, n_rows, n_back, send_counts, recv_counts):
+    def return_rows(self, rows, n_rows, n_back, send_counts, recv_counts, alloc=None):
         return rows
 
     def all_gather_int(self, value, device):
