@@ -8,7 +8,8 @@ fn main() {
     let csrc = PathBuf::from(env::var("TCHGEO_CSRC").unwrap_or_else(|_| "cuda/csrc".into()));
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = vec![];
-    for src in ["capi.cu", "csx_build.cu", "neighbor_sampling.cu", "partitioned.cu", "random_walk.cu", "relabel.cu"] {
+    for src in ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu",
+                "partitioned.cu", "random_walk.cu", "relabel.cu"] {
         let obj = out.join(src.replace(".cu", ".o"));
         let ok = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
