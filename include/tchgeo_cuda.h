@@ -368,11 +368,12 @@ TCHGEO_API tchgeo_status tchgeo_tempo_random_walk(const int64_t* row_ptrs /*DEVI
 /* -------------------------------------------------------------------------------------------- */
 /* Row gather: dst[i, :] = src[index[i], :] for rows of row_bytes bytes of any     */
 /* dtype.  The step after the sampler in every loader (x[samples], edge_attr[perm[edge_index]];      */
-/* examples/neighbor_sampling.py:21-24).  TCHGEO_ERR_INDEX for an index outside [0, num_rows).       */
+/* examples/neighbor_sampling.py:21-24).  TCHGEO_ERR_INDEX for an index outside [0, num_rows); with */
+/* scratch == NULL the call is asynchronous and does not validate (bad rows are left unwritten).     */
 /* -------------------------------------------------------------------------------------------- */
 TCHGEO_API tchgeo_status tchgeo_gather_rows(const void* src /*DEVICE [num_rows, row_bytes]*/, int64_t num_rows,
                                             int64_t row_bytes, const int64_t* index /*DEVICE [n]*/, int64_t n,
-                                            void* dst /*DEVICE [n, row_bytes]*/, int32_t* scratch /*DEVICE [1]*/,
+                                            void* dst /*DEVICE [n, row_bytes]*/, int32_t* scratch /*DEVICE [1] or NULL*/,
                                             tchgeo_stream stream);
 
 /* -------------------------------------------------------------------------------------------- */

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(GT_THREADS) gather_rows_kernel(const V* __rest
       if (i < n) {
         const int64_t r = __ldg(index + i);
         if (r < 0 || r >= num_rows) {
-          if (c == 0) atomicOr(err, DEV_ERR_INDEX);
+          if (c == 0 && err) atomicOr(err, DEV_ERR_INDEX);
         } else {
           v[u] = ld_row(src + r * vecs_per_row + c);
           o[u] = i * vecs_per_row + c;
@@ -78,12 +78,11 @@ using namespace tchgeo;
 extern "C" tchgeo_status tchgeo_gather_rows(const void* src, int64_t num_rows, int64_t row_bytes, const int64_t* index,
                                             int64_t n, void* dst, int32_t* scratch, tchgeo_stream stream_) {
   TCHGEO_REQUIRE(num_rows >= 0 && row_bytes >= 0 && n >= 0, "negative size");
-  TCHGEO_REQUIRE(scratch != nullptr, "NULL pointer");
   if (n == 0 || row_bytes == 0) return TCHGEO_OK;
   TCHGEO_REQUIRE(src && index && dst, "NULL pointer");
   TCHGEO_REQUIRE(n <= ((int64_t)1 << 62) / row_bytes, "gather too large");
   cudaStream_t stream = (cudaStream_t)stream_;
-  TCHGEO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4, stream));
+  if (scratch) TCHGEO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4, stream));
   const uintptr_t align = (uintptr_t)src | (uintptr_t)dst | (uintptr_t)row_bytes;
   cudaError_t e;
   if ((align & 15u) == 0) e = launch_gather<uint4>(src, num_rows, row_bytes, index, n, dst, (uint32_t*)scratch, stream);
@@ -91,6 +90,7 @@ extern "C" tchgeo_status tchgeo_gather_rows(const void* src, int64_t num_rows, i
   else if ((align & 3u) == 0) e = launch_gather<uint32_t>(src, num_rows, row_bytes, index, n, dst, (uint32_t*)scratch, stream);
   else e = launch_gather<uint8_t>(src, num_rows, row_bytes, index, n, dst, (uint32_t*)scratch, stream);
   TCHGEO_CUDA_CHECK(e);
+  if (!scratch) return TCHGEO_OK;  // asynchronous: no validation read-back (rows with a bad index are left unwritten)
   uint32_t h = 0;
   TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&h, scratch, 4, cudaMemcpyDeviceToHost, stream));
   TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));

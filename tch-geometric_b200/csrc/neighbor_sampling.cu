@@ -276,7 +276,8 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
     } else {
       cnt = deg < k ? deg : k;
       if (k == 0 && deg > 0) atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0..0), sampling.rs:19
-      if (KIND == TCHGEO_SAMPLER_UNIFORM && deg > k) {
+      // UNIFORM and WEIGHTED-with-prefix-sums evaluate steps k .. deg-1 independently: 4-step work items
+      if ((KIND == TCHGEO_SAMPLER_UNIFORM || (KIND == TCHGEO_SAMPLER_WEIGHTED && p.wcum)) && deg > k) {
         nblocks = (deg - k + 3u) >> 2;
         heavy = nblocks > (uint32_t)LIGHT_BLOCKS_MAX;
       }
@@ -304,7 +305,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
       s_owner[off + s] = (uint8_t)tid;
       if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE) s_slot[off + s] = 0u;
     }
-    if (KIND == TCHGEO_SAMPLER_UNIFORM) {
+    if (KIND == TCHGEO_SAMPLER_UNIFORM || KIND == TCHGEO_SAMPLER_WEIGHTED) {  // (no work items without prefix sums)
       for (uint32_t c = 0; c < light_blocks; ++c) s_chown[choff + c] = (uint8_t)tid;
       if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint8_t)tid;
     }
@@ -383,27 +384,41 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
     const int warp = tid >> 5;
     const uint32_t wtag = TAG_WEIGHTED | (p.rel << 8);
     if (p.wcum) {
-      // w_sum at every step comes from the precomputed serial prefix sums: no scan, and the comparison below
-      // sees exactly the reference's f64 values whatever the weights are (sampling.rs:47-52).
-      for (int n = warp; n < nn; n += NT / 32) {
-        const NodeRec rec = s_rec[n];
-        const uint32_t dn = rec.deg;
-        if (dn <= k) continue;
-        const double* wp = p.weights + s_start[n];
-        const double* cp = p.wcum + s_start[n];
-        uint32_t* slots = s_slot + rec.off;
-        for (uint32_t item = k + lane; item < dn; item += 32) {
-          const double w = __ldg(wp + item);
-          const double w_sum = dn > 1 ? __ldg(cp + item) : w;
-          if (!(w_sum > 0.0)) {
-            atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
-          } else {
-            const Philox4 r = philox4x32_10(pos0 + (uint32_t)n, item, batch, wtag, p.key0, p.key1);
-            const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
-            const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
-            if (__dmul_rn(u, w_sum) < w) atomicMax(slots + __umulhi(r.z, k), item);  // :49-52
-          }
+      // w_sum at every step comes from the precomputed serial prefix sums: no scan, the comparison below sees
+      // exactly the reference's f64 values whatever the weights are (sampling.rs:47-52), and the steps are
+      // independent, so they are spread over the CTA as 4-step work items exactly like the uniform reservoir.
+      auto weighted_step = [&](uint32_t n, const NodeRec& rec, uint32_t item) {
+        const int64_t e = s_start[n] + item;
+        const double w = __ldg(p.weights + e);
+        const double w_sum = __ldg(p.wcum + e);
+        if (!(w_sum > 0.0)) {
+          atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
+          return;
         }
+        const Philox4 r = philox_rk(pos0 + n, item, batch, wtag, p);
+        const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
+        const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
+        if (__dmul_rn(u, w_sum) < w) atomicMax(s_slot + rec.off + __umulhi(r.z, k), item);  // :49-52
+      };
+      while (true) {
+        uint32_t base = 0;
+        if (lane == 0) base = smem_atom_add(&s_work, 128u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= Q) break;
+#pragma unroll 1
+        for (uint32_t q = base + lane; q < min(base + 128u, Q); q += 32) {
+          const uint32_t n = s_chown[q];
+          const NodeRec rec = s_rec[n];
+          const uint32_t item0 = k + 4u * (q - rec.choff);
+#pragma unroll 1
+          for (uint32_t item = item0; item < min(item0 + 4u, rec.deg); ++item) weighted_step(n, rec, item);
+        }
+      }
+      const uint32_t nheavy = s_nheavy;
+      for (uint32_t h = (uint32_t)warp; h < nheavy; h += NT / 32) {
+        const uint32_t n = s_heavy[h];
+        const NodeRec rec = s_rec[n];
+        for (uint32_t item = k + lane; item < rec.deg; item += 32) weighted_step(n, rec, item);
       }
     } else {
     for (int n = warp; n < nn; n += NT / 32) {

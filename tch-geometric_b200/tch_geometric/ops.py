@@ -804,9 +804,11 @@ def tempo_random_walk(row_ptrs: Tensor, col_indices: Tensor, node_timestamps: Te
 # ---------------------------------------------------------------------------------------------
 # downstream gather (the step after the sampler in every loader: x[samples], edge_attr[perm[edge_index]])
 # ---------------------------------------------------------------------------------------------
-def gather_rows(src: Tensor, index: Tensor) -> Tensor:
+def gather_rows(src: Tensor, index: Tensor, out: Optional[Tensor] = None, validate: bool = True) -> Tensor:
     """src[index] along dim 0 for a contiguous CUDA tensor of any dtype and an int64 index vector
-    (examples/neighbor_sampling.py:21-24 / PyG filter_data).  Out-of-range indices raise (no negative wrap-around)."""
+    (examples/neighbor_sampling.py:21-24 / PyG filter_data).  Out-of-range indices raise (no negative wrap-around).
+    out: optional preallocated result; validate=False skips the error read-back, which makes the call asynchronous
+    (use it when the index comes straight from the sampler, whose ids are in range by construction)."""
     if not isinstance(src, Tensor) or not src.is_cuda:
         raise ValueError("src must be a CUDA tensor")
     if not src.is_contiguous() or src.dim() < 1:
@@ -816,11 +818,15 @@ def gather_rows(src: Tensor, index: Tensor) -> Tensor:
     if index.dim() != 1:
         raise ValueError("index must be a vector")
     n = index.numel()
-    out = torch.empty((n,) + tuple(src.shape[1:]), dtype=src.dtype, device=dev)
+    shape = (n,) + tuple(src.shape[1:])
+    if out is None:
+        out = torch.empty(shape, dtype=src.dtype, device=dev)
+    elif tuple(out.shape) != shape or out.dtype != src.dtype or out.device != dev or not out.is_contiguous():
+        raise ValueError(f"out must be a contiguous {src.dtype} tensor of shape {shape} on {dev}")
     row_bytes = (src.numel() // src.shape[0]) * src.element_size() if src.shape[0] > 0 else 0
     if src.shape[0] == 0 and n > 0:
         raise N.ReferencePanic("index out of range (src has no rows)")
-    scratch = torch.empty(1, dtype=torch.int32, device=dev)
+    scratch = torch.empty(1, dtype=torch.int32, device=dev) if validate else None
     with torch.cuda.device(dev):
         N.check(N.lib.tchgeo_gather_rows(_ptr(src), src.shape[0], row_bytes, _ptr(index), n, _ptr(out), _ptr(scratch),
                                          _stream(dev)))

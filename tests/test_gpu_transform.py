@@ -95,3 +95,21 @@ def test_weighted_sampler_arbitrary_weights(thg, fakedataset, monkeypatch, cumsu
         s, r, c, e = (t.cpu().numpy() for t in got[:4])
         assert s.size == want[0].size and (hi[e] == s[r]).all()
     thg.ops._cumsum_cache.clear()
+
+
+def test_weighted_sampler_heavy_columns_bit_exact(thg, fakedataset):
+    """columns far above fanout + 128 take the warp-per-node path of the flattened weighted draw loop"""
+    ei, n = fakedataset
+    rng = np.random.default_rng(12)
+    hubs = [np.stack([rng.choice(n, d, replace=False), np.full(d, c)]) for c, d in ((3, 700), (9, 140), (11, 133))]
+    ptrs, idx, _ = thg.to_csc(i64(np.concatenate([ei] + hubs, axis=1)), n)
+    hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
+    w = rng.uniform(0.2, 5.0, hi.size) * 10.0 ** rng.integers(-3, 3, hi.size)
+    seeds = np.concatenate([[3, 9, 11, 3], rng.integers(0, n, 300)])
+    for fan in ([5], [12, 3]):
+        thg.rng_reseed(5)
+        seed = thg.ops.splitmix64(5)[1]
+        got = thg.neighbor_sampling_homogenous(ptrs, idx, i64(seeds), fan, thg.WeightedEdgeSampler(f64(w)))
+        want = O.neighbor_sampling_homogenous(hp, hi, seeds, fan, sampler=("weighted", w), seed=seed)
+        for g, x in zip(got[:4], want[:4]):
+            assert (g.cpu().numpy() == x).all()

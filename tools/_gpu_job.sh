@@ -1,10 +1,9 @@
 set -x
 mkdir -p gpurun_out
-TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511"
-for p in fresh uneven uneven_fresh_i32; do
-$TR tools/a2a_bench.py --mb 1024 --pattern $p > gpurun_out/a2a_$p.json 2>/dev/null; tail -1 gpurun_out/a2a_$p.json | cut -c1-160
-done
-$TR bench.py --gpus 8 --workload partitioned --batches 256 --steps 5 --warmup 2 > gpurun_out/bench_part_8gpu_b256_g1.json 2> gpurun_out/bench_part_8gpu.err
+python -m pytest tests/test_gpu_transform.py tests/test_gpu_sampling.py tests/test_gpu_fullsize.py -m gpu -x -q > gpurun_out/gpu_tests.log 2>&1; echo "rc=$?" >> gpurun_out/gpu_tests.log
+tail -4 gpurun_out/gpu_tests.log
+python bench.py --sampler weighted --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/bench_weighted2.json 2> /dev/null
 python -c "
 import json
-d=json.load(open('gpurun_out/bench_part_8gpu_b256_g1.json')); print('batches 256', d['ms_per_step'], d['value']/1e9, d['phase_ms_per_step_rank0'])"
+d=json.load(open('gpurun_out/bench_weighted2.json')); r=d['roofline']; print('weighted', d['value']/1e9, d['ms_per_step'], r['frac'], [round(h['ms'],3) for h in r['per_hop']])"
+timeout 300 ncu --set full --clock-control none -k regex:gather_rows_kernel -c 1 -o gpurun_out/r1_gather python bench.py --workload gather --steps 1 --warmup 0 --no-cpu > gpurun_out/ncu_gather.log 2>&1
