@@ -268,7 +268,7 @@ def run_ours(args):
     log(f"[bench] rank {rank}: to_csc {to_csc_ms:.2f} ms (first call {to_csc_first_ms:.2f} ms) for E={E}")
 
     # every rank samples its own global batch indices: step s, rank r -> batches [(s*world + r)*B, +B)
-    steps_total = W + K
+    steps_total = W + 2 * K  # [W, W+K): serial pass with per-launch events; [W+K, W+2K): pipelined pass (value)
     host_seeds = torch.empty((steps_total, B, S), dtype=torch.int64).pin_memory()
     for s in range(steps_total):
         host_seeds[s] = torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B))
@@ -320,19 +320,61 @@ def run_ours(args):
             hop_deg[h] = float((ptrs[ids + 1] - ptrs[ids]).sum().item()) * K
         del pos, ids
     barrier()
-    elapsed_ms = start.elapsed_time(stop)
+    serial_ms = start.elapsed_time(stop)
     from tch_geometric.sharding import reduce_job
+    serial_ms, serial_edges_all = reduce_job(serial_ms, float(edges), device)
+    serial = {"ms_per_step": serial_ms / K, "value": serial_edges_all / (serial_ms * 1e-3),
+              "what": "one plan, one stream, host waits for every step's lengths before enqueueing the next step"}
+
+    # ---- value: the same K-step job with two plans on two streams (HomogenousSampler.sample_async / result) ------
+    # The host enqueues step s+1 before it waits for the lengths of step s, so the device never idles between steps.
+    plans = [plan, thg.HomogenousSampler(ptrs, idx, B, S, FANOUTS, sampler=sampler)]
+    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+
+    def pipelined(first, count):
+        total, pending = 0, []
+        for i, s in enumerate(range(first, first + count)):
+            j = i & 1
+            if len(pending) == 2:
+                total += int(plans[pending.pop(0)].result().edges_len.sum())
+            with torch.cuda.stream(streams[j]):
+                plans[j].sample_async(dev_seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
+            pending.append(j)
+        while pending:
+            total += int(plans[pending.pop(0)].result().edges_len.sum())
+        return total
+
+    pipelined(0, max(W, 2))  # warm-up of both plans
+    barrier()
+    cur = torch.cuda.current_stream(device)
+    for st in streams:
+        st.wait_stream(cur)
+    start.record(cur)
+    for st in streams:
+        st.wait_stream(cur)
+    t0 = time.perf_counter()
+    edges = pipelined(W + K, K)
+    for st in streams:
+        cur.wait_stream(st)
+    stop.record(cur)
+    barrier()
+    elapsed_ms = max(start.elapsed_time(stop), 0.0)
+    wall_ms = (time.perf_counter() - t0) * 1e3
     elapsed_ms, edges_all = reduce_job(elapsed_ms, float(edges), device)
     value = edges_all / (elapsed_ms * 1e-3)
     seeds_per_s = world * B * S * K / (elapsed_ms * 1e-3)
+    serial["pipelined_wall_ms_per_step"] = wall_ms / K
 
+    # kernels of ours per step: fill_i64_kernel + per hop (frontier_max_kernel +) the hop kernel
+    hop_kernel_name = "hop_warp_kernel" if os.environ.get("TCHGEO_HOP_KERNEL") == "warp" else "hop_kernel"
+    launches_per_step = 1 + len(FANOUTS) * (2 if os.environ.get("TCHGEO_HOP_KERNEL") == "warp" else 1)
     peak, peak_src = measured_peak_gbs()
     dom = int(np.argmax(hop_ms))
     # per launch, summed over the K timed launches; the weighted sampler adds 8 B per scanned weight
     alg_bytes = 24.0 * hop_F + 40.0 * hop_E + 8.0 * hop_deg
     achieved = alg_bytes[dom] / (hop_ms[dom] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"hop_kernel<{args.sampler.upper()}> hop {dom + 1} (fanout {FANOUTS[dom]})",
+        "bound": "hbm", "kernel": f"{hop_kernel_name}<{args.sampler.upper()}> hop {dom + 1} (fanout {FANOUTS[dom]})",
         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes[dom] / K, "launch_ms": hop_ms[dom] / K,
@@ -368,8 +410,8 @@ def run_ours(args):
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": workload_config(n, E, B, args.scale, args.sampler),
             "seeds_per_sec": seeds_per_s, "edges_per_step_per_gpu": edges / K,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": K * (len(FANOUTS) + 1),
+            "roofline": roofline, "serial": serial, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": K * launches_per_step,
             "clocks": clk, "l2_fetch_granularity": l2_fetch, "to_csc_ms": to_csc_ms, "to_csc_first_call_ms": to_csc_first_ms,
         }
         emit(out)

@@ -374,7 +374,9 @@ class _Call:
         a.workspace = self.workspace.data_ptr()
         a.workspace_bytes = ws_bytes
 
-    def run(self, seed=None, batch_base=None, timed=False):
+    def run(self, seed=None, batch_base=None, timed=False, collect=True):
+        """collect=False only enqueues the launches on the current stream (no host synchronisation); `collect()`
+        reads the lengths and layer offsets back later.  Nothing else may use this call's buffers in between."""
         a = self.args
         if seed is not None:
             a.seed = seed
@@ -382,13 +384,27 @@ class _Call:
             a.batch_base = batch_base
         with torch.cuda.device(self.device):
             a.stream = torch.cuda.current_stream(self.device).cuda_stream
-            if timed:
+            if not collect:
+                keep = (a.samples_len, a.edges_len, a.layer_offsets)
+                a.samples_len = a.edges_len = a.layer_offsets = None  # tchgeo_neighbor_sampling then does not read back
+                try:
+                    N.check(N.lib.tchgeo_neighbor_sampling(ctypes.byref(a)))
+                finally:
+                    a.samples_len, a.edges_len, a.layer_offsets = keep
+            elif timed:
                 ms = np.zeros(max(self.R * max(self.H, 1), 1), dtype=np.float32)
                 n = ctypes.c_int32(0)
                 N.check(N.lib.tchgeo_neighbor_sampling_timed(ctypes.byref(a), ms.ctypes.data, ms.size, ctypes.addressof(n)))
                 self.launch_ms = ms[:n.value].copy()
             else:
                 N.check(N.lib.tchgeo_neighbor_sampling(ctypes.byref(a)))
+        return self
+
+    def collect(self):
+        """Second half of run(collect=False): one D2H copy of the length table on the stream the launches went to,
+        a synchronisation of that stream only, and the device-side error word turned into an exception."""
+        with torch.cuda.device(self.device):
+            N.check(N.lib.tchgeo_neighbor_sampling_collect(ctypes.byref(self.args)))
         return self
 
 
@@ -491,6 +507,25 @@ class HomogenousSampler:
         self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base, timed=timed)
         res = SampledBatches(self._call)
         res.launch_ms = getattr(self._call, "launch_ms", None) if timed else None
+        return res
+
+    def sample_async(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> "HomogenousSampler":
+        """Enqueue `sample(inputs)` on the current stream without waiting for it; `result()` waits for that stream
+        and returns the SampledBatches.  With two plans on two streams (enqueue plan B, then take plan A's
+        result) the device never idles between steps: the length read-back of one step overlaps the kernels
+        of the next.  The plan's buffers belong to the pending step until `result()` has returned."""
+        if not isinstance(inputs, Tensor) or inputs.dtype != torch.int64:
+            raise ValueError("inputs must be an int64 tensor")
+        if tuple(inputs.shape) != tuple(self._inputs.shape):
+            raise ValueError(f"inputs must have shape {tuple(self._inputs.shape)}")
+        self._inputs.copy_(inputs, non_blocking=True)
+        self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base, collect=False)
+        return self
+
+    def result(self) -> SampledBatches:
+        self._call.collect()
+        res = SampledBatches(self._call)
+        res.launch_ms = None
         return res
 
 

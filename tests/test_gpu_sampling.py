@@ -346,3 +346,50 @@ def test_heterogenous_batched_plan(thg, fakehetero):
         want = O.neighbor_sampling_heterogenous(node_types, edge_types, hcp, hri, {t: v[b] for t, v in inputs.items()},
                                                 nn, 2, seed=77, batch=3 + b)
         _cmp_hetero(plan.batch(b), want)
+
+
+@pytest.mark.parametrize("kind", ["uniform", "replace", "weighted"])
+def test_warp_tile_and_cta_tile_kernels_agree(thg, kind, monkeypatch):
+    """hop_warp_kernel (persistent 32-node warp tiles, default for fanout <= 16) and hop_kernel (CTA tiles) share
+    the Philox counters, so they must produce the same bits; many batches and long per-batch look-back chains
+    (hop 3 has > 64 warp tiles per batch), hubs and zero-degree nodes included.  Both are checked against the
+    oracle on two of the batches."""
+    n = 20000
+    ei = _power_law_graph(n, 11, 3000)
+    ptrs, idx, _ = graph(thg, ei, n)
+    hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
+    B, S, fan = 37, 40, [15, 10, 5]
+    inputs = np.random.default_rng(5).integers(0, n, (B, S))
+    inputs[3, :5] = 0  # the hub, repeatedly
+    sampler, osampler = None, None
+    if kind == "replace":
+        sampler, osampler = thg.UniformEdgeSampler(True), ("uniform", True)
+    elif kind == "weighted":
+        w = np.random.default_rng(6).uniform(0.2, 5.0, hi.size)
+        sampler, osampler = thg.WeightedEdgeSampler(torch.as_tensor(w).cuda()), ("weighted", w)
+    outs = {}
+    for which in ("warp", "cta"):
+        monkeypatch.setenv("TCHGEO_HOP_KERNEL", which)
+        res = thg.neighbor_sampling_homogenous_batched(ptrs, idx, dev(inputs), fan, sampler, seed=4321, batch_base=9)
+        outs[which] = [res.batch(b) for b in range(B)]
+    for b in range(B):
+        for x, y in zip(outs["warp"][b][:4], outs["cta"][b][:4]):
+            assert torch.equal(x, y)
+        assert outs["warp"][b][4] == outs["cta"][b][4]
+    for b in (3, B - 1):
+        want = O.neighbor_sampling_homogenous(hp, hi, inputs[b], fan, sampler=osampler, seed=4321, batch=9 + b)
+        got = [t.cpu().numpy() for t in outs["warp"][b][:4]] + [outs["warp"][b][4]]
+        assert_same(got, want)
+
+
+def test_warp_tile_kernel_many_tiles_single_batch(thg, fakedataset, monkeypatch):
+    """one batch whose last hop spans ~1000 warp tiles: the look-back walks several 32-wide windows"""
+    ei, n = fakedataset
+    ptrs, idx, _ = graph(thg, ei, n)
+    hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
+    inputs = np.random.default_rng(21).integers(0, n, 400)
+    monkeypatch.setenv("TCHGEO_HOP_KERNEL", "warp")
+    for sampler in (None, thg.UniformEdgeSampler(True)):
+        got, seed = run_homo(thg, ptrs, idx, inputs, [16, 8, 4], sampler, state=33)
+        want = O.neighbor_sampling_homogenous(hp, hi, inputs, [16, 8, 4], sampler=oracle_sampler(sampler), seed=seed)
+        assert_same(got, want)
