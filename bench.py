@@ -366,8 +366,8 @@ def run_ours(args):
     serial["pipelined_wall_ms_per_step"] = wall_ms / K
 
     # kernels of ours per step: fill_i64_kernel + per hop (frontier_max_kernel +) the hop kernel
-    hop_kernel_name = "hop_warp_kernel" if os.environ.get("TCHGEO_HOP_KERNEL") == "warp" else "hop_kernel"
-    launches_per_step = 1 + len(FANOUTS) * (2 if os.environ.get("TCHGEO_HOP_KERNEL") == "warp" else 1)
+    hop_kernel_name = "hop_kernel"
+    launches_per_step = 1 + len(FANOUTS)  # fill_i64_kernel + one hop kernel per hop
     peak, peak_src = measured_peak_gbs()
     dom = int(np.argmax(hop_ms))
     # per launch, summed over the K timed launches; the weighted sampler adds 8 B per scanned weight
@@ -737,11 +737,27 @@ def run_hetero(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     edges_n = 0
     launch_ms = None
+    alg_bytes = 0.0
+    src_of = [node_types.index(et[0]) for et in edge_types]
+    dst_of = [node_types.index(et[2]) for et in edge_types]
+    seeds_of = np.array([S if t == "paper" else 0 for t in node_types], dtype=np.float64)
     e0.record()
     for s in range(W, W + K):
         plan.sample({"paper": all_seeds[s]}, seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
         edges_n += int(plan.edges_len.sum())
         launch_ms = plan.launch_ms if launch_ms is None else launch_ms + plan.launch_ms
+        # algorithmic bytes of the step, SURVEY 8(d): 24 B per frontier node + 40 B per sampled edge of every launch.
+        # E[r,h] from the layer offsets; frontier of hop 0 = the seeds of the dst type, of hop 1 = the nodes the dst
+        # type gained during hop 0 (neighbor_sampling.rs:345-348).
+        lo, el = plan.layer_offsets, plan.edges_len  # [B, R, H, 3], [B, R]
+        e_h0 = (lo[:, :, 1, 1] - lo[:, :, 0, 1]).sum(axis=0).astype(np.float64)  # [R]
+        e_h1 = (el - lo[:, :, 1, 1]).sum(axis=0).astype(np.float64)
+        gained = np.zeros(len(node_types))
+        for r, st in enumerate(src_of):
+            gained[st] += e_h0[r]
+        f_h0 = np.array([seeds_of[d] * B for d in dst_of])
+        f_h1 = np.array([gained[d] for d in dst_of])
+        alg_bytes += 24.0 * (f_h0.sum() + f_h1.sum()) + 40.0 * (e_h0.sum() + e_h1.sum())
     e1.record()
     torch.cuda.synchronize()
     clk = clocks.stop()
@@ -775,6 +791,12 @@ def run_hetero(args):
                                      f"neighbor_sampling_heterogenous fanouts [10,10] per relation, {S} paper seeds/batch, "
                                      f"{B} batches/step", "parallelism": "seed batches sharded, CSCs replicated"},
               "launch_ms": [float(x) / K for x in launch_ms], "edges_per_step_per_gpu": edges_n / K,
+              "roofline": {"bound": "hbm", "kernel": "hop_kernel<UNIFORM>, all launches of the step (one per hop and relation "
+                           "with a non-empty frontier)", "achieved": alg_bytes / (float(launch_ms.sum()) * 1e-3) / 1e9,
+                           "peak": measured_peak_gbs()[0], "unit": "GB/s",
+                           "frac": alg_bytes / (float(launch_ms.sum()) * 1e-3) / 1e9 / measured_peak_gbs()[0],
+                           "traffic": None, "algorithmic_bytes_per_step": alg_bytes / K,
+                           "kernel_ms_per_step": float(launch_ms.sum()) / K},
               "cpu_baseline": cpu, "e2e": None, "gpu_launches": K * (len(launch_ms) + 1), "clocks": clk})
     if world > 1:
         dist.destroy_process_group()

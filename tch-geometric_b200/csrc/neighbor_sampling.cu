@@ -38,15 +38,16 @@
 namespace tchgeo {
 namespace {
 
-constexpr int HOP_THREADS = 128;          // default threads (= max frontier nodes) per tile
-constexpr int HOP_DEFAULT_TPC = 2;          // tiles per CTA
-constexpr int HOP_DEFAULT_MIN_BLOCKS = 5;  // register budget: 5 x 256 (or 10 x 128) threads per SM, 48 regs, no spills
+constexpr int HOP_THREADS = 128;          // threads (= max frontier nodes) per tile
+constexpr int HOP_TPC = 2;                // tiles per CTA: the colptr gathers of both are requested up front
+constexpr int HOP_DEFAULT_MIN_BLOCKS = 10;  // CTAs per SM the register budget is set for (48 registers)
+constexpr int HOP_U = 5;                  // gathers in flight per thread in phase D
 constexpr int MAX_TILE_EDGES = 8192;   // shared-memory slots per tile when fanout <= 8192
 constexpr int MAX_FANOUT = 32768;      // one node per tile above 8192; bounded by shared memory
 constexpr uint64_t ST_FLAG_AGG = 1ull << 62;
 constexpr uint64_t ST_FLAG_INCL = 2ull << 62;
 constexpr uint64_t ST_VAL_MASK = (1ull << 62) - 1;
-constexpr int LIGHT_BLOCKS_MAX = 32;   // nodes needing more 4-step draw blocks are processed CTA-wide
+constexpr int LIGHT_CHUNKS_MAX = 16;   // nodes needing more 8-step draw chunks are strided by a warp each
 
 struct HopParams {
   const int64_t* ptrs;
@@ -82,8 +83,6 @@ struct HopParams {
   uint32_t rel;
   uint32_t batch_base;
   uint32_t total_tiles;         // num_batches * tiles_per_batch
-  int32_t static_order;         // EXPERIMENT ONLY (TCHGEO_EXPERIMENT_STATIC_ORDER=1): tile = blockIdx, no ticket
-  const uint32_t* max_frontier; // hop_warp_kernel: max over the batches of the frontier size (frontier_max_kernel)
   // temporal filter (src/algo/neighbor_sampling.rs:36-77); filter_mode 0 = none
   int32_t filter_mode;          // 1 static, 2 relative, 3 dynamic
   int32_t filter_forward;
@@ -172,17 +171,17 @@ __device__ __forceinline__ Philox4 philox_rk(uint32_t c0, uint32_t c1, uint32_t 
   return Philox4{c0, c1, c2, c3};
 }
 
-template <int KIND, int MINB, int NT, int TPC>
-__global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
-  using BlockScan = cub::BlockScan<uint32_t, NT>;
-  __shared__ typename BlockScan::TempStorage scan_tmp;
+template <int KIND, int MINB, bool I32>
+__global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams p) {
+  constexpr int NT = HOP_THREADS, TPC = HOP_TPC, NW = NT / 32;
   __shared__ int64_t s_start[NT];
   __shared__ NodeRec s_rec[NT];
-  __shared__ uint8_t s_chown[LIGHT_BLOCKS_MAX * NT];  // draw block -> owning node
+  __shared__ uint8_t s_chown[LIGHT_CHUNKS_MAX * NT];  // 8-step draw chunk -> owning node
   __shared__ uint8_t s_heavy[NT];
   __shared__ TileHdr s_hdr[TPC];
   __shared__ int64_t s_pre_start[TPC][NT];  // prefetched colptr data of the CTA's TPC tiles
   __shared__ uint32_t s_pre_deg[TPC][NT];
+  __shared__ __align__(16) uint32_t s_wtot[NW];  // per-warp totals of the tile's prefix sums
   __shared__ uint32_t s_work;     // dynamic work counter of the draw phase
   __shared__ uint32_t s_nheavy;
   __shared__ int64_t s_excl;
@@ -192,6 +191,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
+  const int warp = tid >> 5;
   const int TN = p.tile_nodes;
   const uint32_t k = (uint32_t)p.fanout;
   if (tid == 0) {
@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
     // the tiles in flight at any moment belong to different batches, so the per-batch look-back
     // chains advance independently, and every tile this one waits on (same batch, smaller t) holds a
     // smaller ticket, i.e. belongs to a CTA that is already running (or to this CTA, earlier in its loop).
-    const uint32_t base = p.static_order ? blockIdx.x * TPC : atomicAdd(p.ticket, (uint32_t)TPC);
+    const uint32_t base = atomicAdd(p.ticket, (uint32_t)TPC);
 #pragma unroll
     for (int i = 0; i < TPC; ++i) {
       const uint32_t ticket = base + i;
@@ -228,10 +228,10 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
     int64_t w[TPC], st[TPC], en[TPC];
 #pragma unroll
     for (int i = 0; i < TPC; ++i) {
-      const TileHdr h = s_hdr[i];
-      const int64_t node0 = (int64_t)h.t * TN;
+      const int64_t node0 = (int64_t)s_hdr[i].t * TN;
       w[i] = -2;
-      if (node0 + tid < h.F && tid < TN) w[i] = p.dst_samples[(int64_t)h.b * p.dst_stride + h.fb + node0 + tid];
+      if (node0 + tid < s_hdr[i].F && tid < TN)
+        w[i] = p.dst_samples[(int64_t)s_hdr[i].b * p.dst_stride + s_hdr[i].fb + node0 + tid];
     }
     const uint64_t keep = l2_policy_evict_last();  // colptr (8 B/node) should live in the 126 MB L2
 #pragma unroll
@@ -255,41 +255,55 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
     }
   }
 
+  using val_t = typename std::conditional<I32, int32_t, int64_t>::type;
+
 #pragma unroll 1
   for (int ti = 0; ti < TPC; ++ti) {
   if (ti) __syncthreads();  // the shared tables of the previous tile are free again
   const int b = s_hdr[ti].b, t = s_hdr[ti].t;
-  const int64_t fb = s_hdr[ti].fb, F = s_hdr[ti].F;
-  const int64_t node0 = (int64_t)t * TN;
-  const int nn = (int)max((int64_t)0, min((int64_t)TN, F - node0));
-  const bool is_last = (nn > 0 && node0 + nn == F) || (F == 0 && t == 0);
+  const uint32_t F = (uint32_t)s_hdr[ti].F;       // < 2^32: samples_stride is
+  const uint32_t node0 = (uint32_t)t * (uint32_t)TN;
+  const int nn = F > node0 ? (int)min((uint32_t)TN, F - node0) : 0;
+  const bool is_last = (nn > 0 && node0 + (uint32_t)nn == F) || (F == 0 && t == 0);
   if (nn == 0 && !is_last) continue;
 
   uint32_t cnt = 0;
   uint32_t deg = 0;
-  uint32_t nblocks = 0;  // 4-step Philox blocks this node needs (UNIFORM only)
+  uint32_t nch = 0;  // 8-step draw chunks this node needs (UNIFORM, WEIGHTED on prefix sums)
   bool heavy = false;
-  int64_t start = 0;
   if (tid < nn) {
-    start = s_pre_start[ti][tid];
     deg = s_pre_deg[ti][tid];
     if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
       cnt = deg > 0 ? k : 0;  // exactly k picks, even when deg < k (quirk Q3)
     } else {
       cnt = deg < k ? deg : k;
       if (k == 0 && deg > 0) atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0..0), sampling.rs:19
-      // UNIFORM and WEIGHTED-with-prefix-sums evaluate steps k .. deg-1 independently: 4-step work items
+      // UNIFORM and WEIGHTED-with-prefix-sums evaluate steps k .. deg-1 independently: 8-step work items
       if ((KIND == TCHGEO_SAMPLER_UNIFORM || (KIND == TCHGEO_SAMPLER_WEIGHTED && p.wcum)) && deg > k) {
-        nblocks = (deg - k + 3u) >> 2;
-        heavy = nblocks > (uint32_t)LIGHT_BLOCKS_MAX;
+        nch = (deg - k + 7u) >> 3;
+        heavy = nch > (uint32_t)LIGHT_CHUNKS_MAX;
       }
     }
   }
   // one 32-bit scan carries both prefix sums: low 16 bits = outputs (<= 32768 per tile),
-  // high 16 bits = draw blocks of the light nodes (<= LIGHT_BLOCKS_MAX * 256)
-  const uint32_t light_blocks = heavy ? 0u : nblocks;
-  uint32_t pexcl, ptotal;
-  BlockScan(scan_tmp).ExclusiveSum(cnt | (light_blocks << 16), pexcl, ptotal);
+  // high 16 bits = draw chunks of the light nodes (<= LIGHT_CHUNKS_MAX * NT).  Warp scans + the NW warp totals.
+  const uint32_t light_chunks = heavy ? 0u : nch;
+  const uint32_t sv = cnt | (light_chunks << 16);
+  uint32_t incl = sv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  uint32_t pexcl = incl - sv, ptotal = 0;
+  {
+    static_assert(NW == 4, "the warp totals are read as one 16-byte vector");
+    const uint4 wt = *reinterpret_cast<const uint4*>(s_wtot);
+    pexcl += (warp > 0 ? wt.x : 0u) + (warp > 1 ? wt.y : 0u) + (warp > 2 ? wt.z : 0u);
+    ptotal = wt.x + wt.y + wt.z + wt.w;
+  }
   const uint32_t off = pexcl & 0xffffu;
   const uint32_t total = ptotal & 0xffffu;
   const uint32_t choff = pexcl >> 16;
@@ -300,15 +314,17 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   if (tid == 0) st_relaxed_u64(my_status + t, (t == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | (uint64_t)total);
 
   // ---- C1: per-node set-up of the shared tables (own node only: needs no barrier) ---------------
-  s_start[tid] = start;
+  s_start[tid] = s_pre_start[ti][tid];
   s_rec[tid] = NodeRec{deg, (uint16_t)off, (uint16_t)choff};
   if (tid < nn) {
+    // slot s starts as "item s" and is raised to the step index of every hit (steps >= k > s), so after the
+    // draws it holds the position of the chosen neighbour directly: last hit, else item s (sampling.rs:17-23)
     for (uint32_t s = 0; s < cnt; ++s) {
       s_owner[off + s] = (uint8_t)tid;
-      if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE) s_slot[off + s] = 0u;
+      if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE) s_slot[off + s] = s;
     }
     if (KIND == TCHGEO_SAMPLER_UNIFORM || KIND == TCHGEO_SAMPLER_WEIGHTED) {  // (no work items without prefix sums)
-      for (uint32_t c = 0; c < light_blocks; ++c) s_chown[choff + c] = (uint8_t)tid;
+      for (uint32_t c = 0; c < light_chunks; ++c) s_chown[choff + c] = (uint8_t)tid;
       if (heavy) s_heavy[atomicAdd(&s_nheavy, 1u)] = (uint8_t)tid;
     }
   }
@@ -349,46 +365,72 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   }
 
   // ---- C2: sampling decisions in shared memory --------------------------------------------------
-  const uint32_t pos0 = (uint32_t)(fb + node0);
+  const uint32_t pos0 = (uint32_t)s_hdr[ti].fb + node0;
   const uint32_t batch = p.batch_base + (uint32_t)b;
 
   if (KIND == TCHGEO_SAMPLER_UNIFORM) {
     const uint32_t tag = TAG_RESERVOIR | (p.rel << 8);
     const uint32_t slot_sa = (uint32_t)__cvta_generic_to_shared(s_slot);
-    // Light nodes: (node, 4-step block) work items, grabbed 128 at a time so that warp 0 joins in
-    // after its look-back.  Block c of node n covers steps k+4c .. k+4c+3 of the serial reservoir.
+    // Light nodes: (node, 8-step chunk) work items, grabbed 128 at a time so that warp 0 joins in after its
+    // look-back.  Chunk c of node n is Philox blocks 2c and 2c+1 of the contract: steps k+8c .. k+8c+7 of the
+    // serial reservoir; the second block is skipped when it lies past the neighbourhood.
     while (true) {
       uint32_t base = 0;
       if (lane == 0) base = smem_atom_add(&s_work, 128u);
       base = __shfl_sync(0xffffffffu, base, 0);
       if (base >= Q) break;
+      const uint32_t qend = min(base + 128u, Q);
 #pragma unroll 1
-      for (uint32_t q = base + lane; q < min(base + 128u, Q); q += 32) {
+      for (uint32_t q = base + lane; q < qend; q += 32) {
         const uint32_t n = s_chown[q];
         const NodeRec rec = s_rec[n];
         const uint32_t c = q - rec.choff;
-        const Philox4 r = philox_rk(pos0 + n, c, batch, tag, p);
-        reservoir_block_sa(r, k + 4u * c, rec.deg, k, slot_sa + 4u * rec.off);
+        const uint32_t step0 = k + 8u * c;
+        const uint32_t sa = slot_sa + 4u * rec.off;
+        if (step0 + 4u < rec.deg) {  // both blocks in one basic block: their two dependency chains interleave
+          const Philox4 r0 = philox_rk(pos0 + n, 2u * c, batch, tag, p);
+          const Philox4 r1 = philox_rk(pos0 + n, 2u * c + 1u, batch, tag, p);
+          reservoir_block_sa(r0, step0, rec.deg, k, sa);
+          reservoir_block_sa(r1, step0 + 4u, rec.deg, k, sa);
+        } else {
+          reservoir_block_sa(philox_rk(pos0 + n, 2u * c, batch, tag, p), step0, rec.deg, k, sa);
+        }
       }
     }
-    // Heavy nodes (deg > k + 4*LIGHT_BLOCKS_MAX): one warp strides over one node's blocks.
+    // Heavy nodes (deg > k + 8*LIGHT_CHUNKS_MAX): the whole CTA strides over one node's 4-step blocks, so that no
+    // warp is left alone with a hub while the others wait at the barrier below.
     const uint32_t nheavy = s_nheavy;
-    for (uint32_t h = (uint32_t)(tid >> 5); h < nheavy; h += NT / 32) {
+    for (uint32_t h = 0; h < nheavy; ++h) {
       const uint32_t n = s_heavy[h];
       const NodeRec rec = s_rec[n];
       const uint32_t nb = (rec.deg - k + 3u) >> 2;
-      for (uint32_t c = lane; c < nb; c += 32) {
+#pragma unroll 1
+      for (uint32_t c = tid; c < nb; c += NT) {
         const Philox4 r = philox_rk(pos0 + n, c, batch, tag, p);
         reservoir_block_sa(r, k + 4u * c, rec.deg, k, slot_sa + 4u * rec.off);
       }
     }
+  } else if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
+    // k iid picks per non-empty neighbourhood (sampling.rs:57-69): work item = (node, Philox block c) -> slots
+    // 4c .. 4c+3, one Philox call per four picks
+    const uint32_t rtag = TAG_REPLACE | (p.rel << 8);
+    const uint32_t bpn = (k + 3u) >> 2;  // Philox blocks per node
+#pragma unroll 1
+    for (uint32_t q = tid; q < (uint32_t)nn * bpn; q += NT) {
+      const uint32_t n = q / bpn, c = q - n * bpn;
+      const NodeRec rec = s_rec[n];
+      if (rec.deg == 0) continue;
+      const Philox4 r = philox_rk(pos0 + n, c, batch, rtag, p);
+#pragma unroll
+      for (uint32_t u = 0; u < 4; ++u)
+        if (4u * c + u < k) s_slot[rec.off + 4u * c + u] = __umulhi(pick4(r, u), rec.deg);  // sampling.rs:64
+    }
   } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
-    const int warp = tid >> 5;
     const uint32_t wtag = TAG_WEIGHTED | (p.rel << 8);
     if (p.wcum) {
       // w_sum at every step comes from the precomputed serial prefix sums: no scan, the comparison below sees
       // exactly the reference's f64 values whatever the weights are (sampling.rs:47-52), and the steps are
-      // independent, so they are spread over the CTA as 4-step work items exactly like the uniform reservoir.
+      // independent, so they are spread over the CTA as 8-step work items exactly like the uniform reservoir.
       auto weighted_step = [&](uint32_t n, const NodeRec& rec, uint32_t item) {
         const int64_t e = s_start[n] + item;
         const double w = __ldg(p.weights + e);
@@ -402,28 +444,58 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
         const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
         if (__dmul_rn(u, w_sum) < w) atomicMax(s_slot + rec.off + __umulhi(r.z, k), item);  // :49-52
       };
+      // 8 lanes per chunk, one step per lane: the eight (weight, prefix sum) pairs of a chunk are 64 contiguous
+      // bytes.  Four chunks per lane group are requested before the first one is used (memory-level parallelism).
       while (true) {
         uint32_t base = 0;
         if (lane == 0) base = smem_atom_add(&s_work, 128u);
         base = __shfl_sync(0xffffffffu, base, 0);
         if (base >= Q) break;
+        const uint32_t qend = min(base + 128u, Q);
 #pragma unroll 1
-        for (uint32_t q = base + lane; q < min(base + 128u, Q); q += 32) {
-          const uint32_t n = s_chown[q];
-          const NodeRec rec = s_rec[n];
-          const uint32_t item0 = k + 4u * (q - rec.choff);
-#pragma unroll 1
-          for (uint32_t item = item0; item < min(item0 + 4u, rec.deg); ++item) weighted_step(n, rec, item);
+        for (uint32_t q0 = base + (lane >> 3); q0 < qend; q0 += 16) {
+          uint32_t nn4[4], item4[4];
+          double w4[4], ws4[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const uint32_t q = q0 + 4u * i;
+            nn4[i] = 0xffffffffu;
+            if (q < qend) {
+              const uint32_t n = s_chown[q];
+              const NodeRec rec = s_rec[n];
+              const uint32_t item = k + 8u * (q - rec.choff) + (lane & 7u);
+              if (item < rec.deg) {
+                nn4[i] = n;
+                item4[i] = item;
+                const int64_t e = s_start[n] + item;
+                w4[i] = __ldg(p.weights + e);
+                ws4[i] = __ldg(p.wcum + e);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if (nn4[i] == 0xffffffffu) continue;
+            if (!(ws4[i] > 0.0)) {
+              atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
+              continue;
+            }
+            const Philox4 r = philox_rk(pos0 + nn4[i], item4[i], batch, wtag, p);
+            const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
+            const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
+            if (__dmul_rn(u, ws4[i]) < w4[i])
+              atomicMax(s_slot + s_rec[nn4[i]].off + __umulhi(r.z, k), item4[i]);  // :49-52
+          }
         }
       }
       const uint32_t nheavy = s_nheavy;
-      for (uint32_t h = (uint32_t)warp; h < nheavy; h += NT / 32) {
+      for (uint32_t h = 0; h < nheavy; ++h) {
         const uint32_t n = s_heavy[h];
         const NodeRec rec = s_rec[n];
-        for (uint32_t item = k + lane; item < rec.deg; item += 32) weighted_step(n, rec, item);
+        for (uint32_t item = k + tid; item < rec.deg; item += NT) weighted_step(n, rec, item);
       }
     } else {
-    for (int n = warp; n < nn; n += NT / 32) {
+    for (int n = warp; n < nn; n += NW) {
       const NodeRec rec = s_rec[n];
       const uint32_t dn = rec.deg;
       if (dn <= k) continue;
@@ -433,13 +505,13 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
       for (uint32_t base = 0; base < dn; base += 32) {
         const uint32_t item = base + lane;
         const double w = item < dn ? __ldg(wp + item) : 0.0;
-        double incl = w;
+        double incl_w = w;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-          const double up = __shfl_up_sync(0xffffffffu, incl, o);
-          if (lane >= o) incl += up;
+          const double up = __shfl_up_sync(0xffffffffu, incl_w, o);
+          if (lane >= o) incl_w += up;
         }
-        const double w_sum = carry + incl;  // sampling.rs:48
+        const double w_sum = carry + incl_w;  // sampling.rs:48
         if (item >= k && item < dn) {
           if (!(w_sum > 0.0)) {
             atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
@@ -474,443 +546,66 @@ __global__ void __launch_bounds__(NT, MINB) hop_kernel(const HopParams p) {
   }
   if (total == 0) continue;
 
-  // ---- D: one thread per output edge ------------------------------------------------------------
-  int64_t* o_s = p.src_samples + (int64_t)b * p.src_stride + s_base;
-  int64_t* o_r = p.rows + (int64_t)b * p.e_stride + e_base;
-  int64_t* o_c = p.cols + (int64_t)b * p.e_stride + e_base;
-  int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
-  const int64_t col0 = fb + node0;
-  const uint32_t rtag = TAG_REPLACE | (p.rel << 8);
-  constexpr uint32_t U = 4;
-  for (uint32_t e0 = tid; e0 < total; e0 += NT * U) {
-    int64_t ptr[U];
-    int64_t val[U];
-    uint32_t own[U];
+  // ---- D: one thread per output edge; HOP_U gathers in flight per thread (the whole tile when fanout <= HOP_U).
+  //         The three stores that do not depend on the gather are issued while it is in flight.  cols and rows
+  //         are < 2^32 (samples_stride is), so their values are formed in 32 bits. -------------------------------
+  int64_t* const pe = p.eidx + ((int64_t)b * p.e_stride + e_base);
+  int64_t* const pc = p.cols + ((int64_t)b * p.e_stride + e_base);
+  int64_t* const pr = p.rows + ((int64_t)b * p.e_stride + e_base);
+  int64_t* const ps = p.src_samples + ((int64_t)b * p.src_stride + s_base);
+  const uint32_t col0 = (uint32_t)s_hdr[ti].fb + node0;
+  const uint32_t row0 = (uint32_t)s_base;
+#pragma unroll 1
+  for (uint32_t e0 = tid; e0 < total; e0 += NT * HOP_U) {
+    val_t val[HOP_U];
+    if (e0 - lane + 31u + (HOP_U - 1) * NT < total) {  // all HOP_U edges of every lane of this warp exist: no
+                                                       // predicates, and no warp runs both branches
+      uint32_t own[HOP_U];
+      int64_t ptr[HOP_U];
 #pragma unroll
-    for (uint32_t u = 0; u < U; ++u) {
-      const uint32_t e = min(e0 + u * NT, total - 1);  // clamped: tail lanes redo the last edge
-      const uint32_t n = s_owner[e];
-      const NodeRec rec = s_rec[n];
-      const uint32_t s = e - rec.off;
-      own[u] = n;
-      uint32_t rel_ptr;
-      if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
-        const Philox4 r = philox_rk(pos0 + n, s >> 2, batch, rtag, p);
-        rel_ptr = __umulhi(pick4(r, s & 3u), rec.deg);  // sampling.rs:64
-      } else {
-        const uint32_t st = s_slot[e];
-        rel_ptr = st ? st : s;
+      for (uint32_t u = 0; u < HOP_U; ++u) {
+        const uint32_t e = e0 + u * NT;
+        own[u] = s_owner[e];
+        ptr[u] = s_start[own[u]] + s_slot[e];
+        if (I32) val[u] = ld_gather64_i32(p.indices32 + ptr[u]);
+        else val[u] = ld_gather64_i64(p.indices + ptr[u]);
       }
-      ptr[u] = s_start[n] + rel_ptr;
-    }
-    if (p.indices32) {
 #pragma unroll
-      for (uint32_t u = 0; u < U; ++u)
-        val[u] = (e0 + u * NT < total) ? (int64_t)ld_gather64_i32(p.indices32 + ptr[u]) : 0;
+      for (uint32_t u = 0; u < HOP_U; ++u) {
+        const uint32_t e = e0 + u * NT;
+        st_cs_i64(pe + e, ptr[u]);
+        st_cs_i64(pc + e, (int64_t)(uint64_t)(col0 + own[u]));
+        st_cs_i64(pr + e, (int64_t)(uint64_t)(row0 + e));
+      }
     } else {
+      uint32_t rel[HOP_U], own[HOP_U];
 #pragma unroll
-      for (uint32_t u = 0; u < U; ++u)
-        val[u] = (e0 + u * NT < total) ? ld_gather64_i64(p.indices + ptr[u]) : 0;
-    }
+      for (uint32_t u = 0; u < HOP_U; ++u) {
+        const uint32_t e = min(e0 + u * NT, total - 1u);  // clamped: tail lanes redo the last edge
+        own[u] = s_owner[e];
+        rel[u] = s_slot[e];
+        const int64_t ptr = s_start[own[u]] + rel[u];
+        val[u] = 0;
+        if (e0 + u * NT < total) {
+          if (I32) val[u] = ld_gather64_i32(p.indices32 + ptr);
+          else val[u] = ld_gather64_i64(p.indices + ptr);
+        }
+      }
 #pragma unroll
-    for (uint32_t u = 0; u < U; ++u) {
-      const uint32_t e = e0 + u * NT;
-      if (e < total) {
-        st_cs_i64(o_e + e, ptr[u]);
-        st_cs_i64(o_c + e, col0 + own[u]);
-        st_cs_i64(o_r + e, s_base + e);
-        st_cs_i64(o_s + e, val[u]);  // the next hop reads it only after GBs of other traffic
+      for (uint32_t u = 0; u < HOP_U; ++u) {
+        const uint32_t e = e0 + u * NT;
+        if (e < total) {
+          st_cs_i64(pe + e, s_start[own[u]] + rel[u]);
+          st_cs_i64(pc + e, (int64_t)(uint64_t)(col0 + own[u]));
+          st_cs_i64(pr + e, (int64_t)(uint64_t)(row0 + e));
+        }
       }
     }
+#pragma unroll
+    for (uint32_t u = 0; u < HOP_U; ++u)
+      if (e0 + u * NT < total) st_cs_i64(ps + e0 + u * NT, (int64_t)val[u]);  // read again only by the next hop
   }
   }  // tiles of this CTA
-}
-
-// ---------------------------------------------------------------------------------------------
-// hop_warp_kernel — EXPERIMENT: persistent, barrier-free hop kernel for 1 <= fanout <= 16 (TCHGEO_HOP_KERNEL=warp).
-//
-// Same algorithm, same Philox counters and therefore the same bits as hop_kernel, but the unit of work is a
-// WARP TILE of 32 frontier nodes and nothing in the kernel is CTA-wide:
-//   * every warp of a persistent grid takes tiles from the ticket counter (two at a time, tile-major as above)
-//     and runs them through a software pipeline: while tile j is processed, the colptr pairs of tile j+1, the
-//     frontier ids of tile j+2 and the ticket/header of tile j+2 are in flight, so the three dependent round
-//     trips in front of a tile (ticket -> header -> ids -> colptr) are hidden behind the previous tiles;
-//   * per-tile prefix sums are warp scans, the look-back status words are per warp tile (its first window is
-//     requested before the draw loop and evaluated after it), tables live in the warp's own shared memory
-//     and are ordered by __syncwarp only: no bar.sync, so no warp ever waits for a slower one;
-//   * one shared-memory word per output edge, (owner lane << 27) | position inside the neighbourhood:
-//     initialised to slot s, raised by red.shared.max with the step index of every hit (steps >= k > s, the
-//     owner bits are equal on both sides, so the maximum is "last hit, else item s": sampling.rs:17-23);
-//   * draw work items are 8 reservoir steps (two Philox blocks of the contract, the second one skipped when
-//     it lies past the neighbourhood); phase D holds 5 gathers per lane in flight (the whole tile when
-//     fanout = 5) and issues the three stores that do not depend on the gather while it is in flight.
-// Tickets past ceil(max frontier / 32) * B cannot hold nodes (frontier_max_kernel computes the bound on the
-// device), so the worst-case tail of empty tiles is never visited.
-// Progress: a warp processes its tickets in increasing order and a tile only waits on smaller tickets, so the
-// owner of the smallest unfinished ticket is always able to finish it.
-// ---------------------------------------------------------------------------------------------
-constexpr int WK_WARPS = 4;
-constexpr int WK_NODES = 32;
-constexpr int WK_LIGHT_CHUNKS = 16;   // nodes needing more 8-step chunks are strided by the whole warp
-constexpr int WK_MAX_FANOUT = 16;
-constexpr uint32_t WK_OWNER_SHIFT = 27;
-constexpr uint32_t WK_REL_MASK = (1u << WK_OWNER_SHIFT) - 1u;
-constexpr int WK_U = 5;               // gathers in flight per lane in phase D
-
-struct WarpHdr {
-  int64_t e_in, s_in;
-  uint32_t fb, F;
-  int32_t b, t;  // t = -1: the ticket counter ran out; t = -2: pipeline warm-up slot
-};
-
-struct WarpShared {
-  int64_t start[WK_NODES];
-  NodeRec rec[WK_NODES];
-  uint8_t chown[WK_LIGHT_CHUNKS * WK_NODES];  // draw chunk -> owning lane
-  WarpHdr hdr[3];                             // headers of tiles j, j+1, j+2
-};
-
-__device__ __forceinline__ int64_t ld_plain_i64(const int64_t* p) {
-  int64_t v;
-  asm volatile("ld.global.s64 %0, [%1];" : "=l"(v) : "l"(p));
-  return v;
-}
-
-__global__ void __launch_bounds__(256) frontier_max_kernel(const int64_t* __restrict__ fr_begin,
-                                                           const int64_t* __restrict__ fr_end, int64_t B,
-                                                           int64_t dst_stride, uint32_t* __restrict__ out) {
-  int64_t m = 0;
-  for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < B; b += (int64_t)gridDim.x * blockDim.x) {
-    int64_t fe = fr_end[b];
-    if (fe > dst_stride) fe = dst_stride;
-    const int64_t f = fe - fr_begin[b];
-    m = f > m ? f : m;
-  }
-  uint32_t v = (uint32_t)(m > 0xffffffffll ? 0xffffffffll : m);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0 && v) atomicMax(out, v);
-}
-
-// steps step0 .. step0+3 of the serial reservoir; the slot word keeps the owner lane in its top bits
-__device__ __forceinline__ void reservoir_block_tagged(const Philox4& r, uint32_t step0, uint32_t deg, uint32_t k,
-                                                       uint32_t slots_sa, uint32_t owner_bits) {
-#pragma unroll
-  for (uint32_t u = 0; u < 4; ++u) {
-    const uint32_t step = step0 + u;
-    const uint32_t j = __umulhi(pick4(r, u), step);
-    const uint32_t hit = (uint32_t)((step < deg) & (j < k));
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.max.u32 [%0], %1;\n\t}"
-        ::"r"(slots_sa + 4u * j), "r"(owner_bits | step), "r"(hit)
-        : "memory");
-  }
-}
-
-template <int KIND, int MINB, bool I32>
-__global__ void __launch_bounds__(WK_WARPS * 32, MINB) hop_warp_kernel(const HopParams p) {
-  __shared__ WarpShared s_warp[WK_WARPS];
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
-  constexpr uint32_t FULL = 0xffffffffu;
-  const int lane = threadIdx.x & 31;
-  WarpShared& S = s_warp[threadIdx.x >> 5];
-  const uint32_t k = (uint32_t)p.fanout;
-  uint32_t* s_slot = reinterpret_cast<uint32_t*>(dyn_smem) + (threadIdx.x >> 5) * (WK_NODES * k);
-  const uint32_t slot_sa = (uint32_t)__cvta_generic_to_shared(s_slot);
-  const uint32_t B = (uint32_t)p.num_batches;
-
-  uint32_t useful_t = (__ldg(p.max_frontier) + (uint32_t)(WK_NODES - 1)) / (uint32_t)WK_NODES;
-  useful_t = max(1u, min(useful_t, (uint32_t)p.tiles_per_batch));
-  const uint32_t n_tickets = useful_t * B;
-
-  if (lane == 0) {
-    WarpHdr h;
-    h.e_in = 0; h.s_in = 0; h.fb = 0; h.F = 0; h.b = 0; h.t = -2;
-    S.hdr[0] = h;
-    S.hdr[1] = h;
-  }
-  __syncwarp();
-
-  int cur = 0;
-  uint32_t tk = 0, spare = 0;
-  bool have_spare = false;
-  int64_t hv = 0;          // lanes 0..3: fr_begin / fr_end / e_len_in / src_len_in of tile j+2
-  int64_t w_nx = -2;       // this lane's frontier id in tile j+1 (then j+2)
-  int64_t st = 0, en = 0;  // this lane's colptr pair in tile j (then j+1)
-  const uint64_t keep = l2_policy_evict_last();
-
-  while (true) {
-    const WarpHdr h = S.hdr[cur];
-    if (h.t == -1) break;
-
-    // ---- T0: take tile j's colptr pair; request tile j+1's pair and the ticket of tile j+2 ----------------
-    const int64_t start = st;
-    uint32_t deg = 0;
-    {
-      const int64_t d = en - st;
-      if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
-      else if (d > (int64_t)WK_REL_MASK) atomicOr(p.err, DEV_ERR_DEGREE);
-      else deg = (uint32_t)d;
-    }
-    st = 0; en = 0;
-    if (w_nx >= 0 && w_nx < p.num_cols) {
-      st = ld_gather64_keep_i64(p.ptrs + w_nx, keep);
-      en = ld_gather64_keep_i64(p.ptrs + w_nx + 1, keep);
-    } else if (w_nx != -2) {
-      atomicOr(p.err, DEV_ERR_INDEX);  // reference: slice index panic (quirk Q10)
-    }
-    if (lane == 0) {
-      if (have_spare) {
-        tk = spare;
-        have_spare = false;
-      } else {
-        tk = atomicAdd(p.ticket, 2u);
-        spare = tk + 1u;
-        have_spare = true;
-      }
-    }
-
-    const int t = h.t, b = h.b;
-    const uint32_t node0 = t > 0 ? (uint32_t)t * (uint32_t)WK_NODES : 0u;
-    int nn = 0;
-    bool is_last = false;
-    if (t >= 0) {
-      const int64_t rem = (int64_t)h.F - (int64_t)node0;
-      nn = rem > WK_NODES ? WK_NODES : (rem > 0 ? (int)rem : 0);
-      is_last = (nn > 0 && (int64_t)node0 + nn == (int64_t)h.F) || (h.F == 0 && t == 0);
-    }
-    const bool active = nn > 0 || is_last;
-
-    uint32_t total = 0, Q = 0, heavy_mask = 0;
-    uint64_t lbv = ST_FLAG_INCL;
-    uint64_t* my_status = p.status + (size_t)b * p.tiles_per_batch;
-    if (active) {
-      uint32_t cnt = 0, nch = 0;
-      bool heavy = false;
-      if (lane < nn) {
-        if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
-          cnt = deg > 0 ? k : 0;  // exactly k picks, even when deg < k (quirk Q3)
-          nch = deg > 0 ? (k + 3u) >> 2 : 0u;
-        } else {
-          cnt = deg < k ? deg : k;
-          if (deg > k) {
-            nch = (deg - k + 7u) >> 3;
-            heavy = nch > (uint32_t)WK_LIGHT_CHUNKS;
-          }
-        }
-      }
-      const uint32_t lightch = heavy ? 0u : nch;
-      const uint32_t v = cnt | (lightch << 16);  // both sums are <= 512
-      uint32_t incl = v;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t up = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += up;
-      }
-      const uint32_t tot = __shfl_sync(FULL, incl, 31);
-      total = tot & 0xffffu;
-      Q = tot >> 16;
-      const uint32_t off = (incl - v) & 0xffffu, choff = (incl - v) >> 16;
-      if (lane == 0) st_relaxed_u64(my_status + t, (t == 0 ? ST_FLAG_INCL : ST_FLAG_AGG) | (uint64_t)total);
-      if (t > 0 && t - 1 - lane >= 0) lbv = ld_relaxed_u64(my_status + (t - 1 - lane));  // evaluated after the draws
-
-      S.start[lane] = start;
-      S.rec[lane] = NodeRec{deg, (uint16_t)off, (uint16_t)choff};
-      const uint32_t owner_bits = (uint32_t)lane << WK_OWNER_SHIFT;
-      if (KIND != TCHGEO_SAMPLER_UNIFORM_REPLACE)
-        for (uint32_t s = 0; s < cnt; ++s) s_slot[off + s] = owner_bits | s;
-      for (uint32_t c = 0; c < lightch; ++c) S.chown[choff + c] = (uint8_t)lane;
-      heavy_mask = __ballot_sync(FULL, heavy);
-      __syncwarp();
-    }
-
-    // ---- T1: the ticket of tile j+2 has arrived: request its header ------------------------------------------
-    tk = __shfl_sync(FULL, tk, 0);
-    const bool valid2 = tk < n_tickets;
-    const uint32_t t2 = tk / B, b2 = tk - t2 * B;
-    if (valid2 && lane < 4) {
-      const int64_t* src = lane == 0 ? p.fr_begin : (lane == 1 ? p.fr_end : (lane == 2 ? p.e_len_in : p.src_len_in));
-      hv = ld_plain_i64(src + b2);
-    }
-
-    // ---- C2: sampling decisions of tile j in the warp's shared memory ----------------------------------------
-    const uint32_t pos0 = h.fb + node0;
-    const uint32_t batch = p.batch_base + (uint32_t)b;
-    if (active) {
-      if (KIND == TCHGEO_SAMPLER_UNIFORM) {
-        const uint32_t tag = TAG_RESERVOIR | (p.rel << 8);
-#pragma unroll 1
-        for (uint32_t q = lane; q < Q; q += 32) {
-          const uint32_t n = S.chown[q];
-          const NodeRec rec = S.rec[n];
-          const uint32_t c = q - rec.choff;
-          const uint32_t step0 = k + 8u * c;
-          const uint32_t ob = n << WK_OWNER_SHIFT;
-          const uint32_t sa = slot_sa + 4u * rec.off;
-          reservoir_block_tagged(philox_rk(pos0 + n, 2u * c, batch, tag, p), step0, rec.deg, k, sa, ob);
-          if (step0 + 4u < rec.deg)
-            reservoir_block_tagged(philox_rk(pos0 + n, 2u * c + 1u, batch, tag, p), step0 + 4u, rec.deg, k, sa, ob);
-        }
-        for (uint32_t hm = heavy_mask; hm; hm &= hm - 1u) {
-          const uint32_t n = (uint32_t)__ffs(hm) - 1u;
-          const NodeRec rec = S.rec[n];
-          const uint32_t nb = (rec.deg - k + 3u) >> 2;
-          const uint32_t ob = n << WK_OWNER_SHIFT;
-          const uint32_t sa = slot_sa + 4u * rec.off;
-#pragma unroll 1
-          for (uint32_t c = lane; c < nb; c += 32)
-            reservoir_block_tagged(philox_rk(pos0 + n, c, batch, tag, p), k + 4u * c, rec.deg, k, sa, ob);
-        }
-      } else if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
-        const uint32_t rtag = TAG_REPLACE | (p.rel << 8);
-#pragma unroll 1
-        for (uint32_t q = lane; q < Q; q += 32) {
-          const uint32_t n = S.chown[q];
-          const NodeRec rec = S.rec[n];
-          const uint32_t c = q - rec.choff;
-          const Philox4 r = philox_rk(pos0 + n, c, batch, rtag, p);
-          const uint32_t ob = n << WK_OWNER_SHIFT;
-#pragma unroll
-          for (uint32_t u = 0; u < 4; ++u) {
-            const uint32_t s = 4u * c + u;
-            if (s < k) s_slot[rec.off + s] = ob | __umulhi(pick4(r, u), rec.deg);  // sampling.rs:64
-          }
-        }
-      } else {
-        // WEIGHTED on serial prefix sums (p.wcum != NULL is a launch condition of this kernel)
-        const uint32_t wtag = TAG_WEIGHTED | (p.rel << 8);
-        auto weighted_step = [&](uint32_t n, const NodeRec& rec, uint32_t item) {
-          const int64_t e = S.start[n] + item;
-          const double w = __ldg(p.weights + e);
-          const double w_sum = __ldg(p.wcum + e);
-          if (!(w_sum > 0.0)) {
-            atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
-            return;
-          }
-          const Philox4 r = philox_rk(pos0 + n, item, batch, wtag, p);
-          const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
-          const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
-          if (__dmul_rn(u, w_sum) < w)
-            atomicMax(s_slot + rec.off + __umulhi(r.z, k), (n << WK_OWNER_SHIFT) | item);  // :49-52
-        };
-#pragma unroll 1
-        for (uint32_t q = lane; q < Q; q += 32) {
-          const uint32_t n = S.chown[q];
-          const NodeRec rec = S.rec[n];
-          const uint32_t item0 = k + 8u * (q - rec.choff);
-#pragma unroll 1
-          for (uint32_t item = item0; item < min(item0 + 8u, rec.deg); ++item) weighted_step(n, rec, item);
-        }
-        for (uint32_t hm = heavy_mask; hm; hm &= hm - 1u) {
-          const uint32_t n = (uint32_t)__ffs(hm) - 1u;
-          const NodeRec rec = S.rec[n];
-#pragma unroll 1
-          for (uint32_t item = k + lane; item < rec.deg; item += 32) weighted_step(n, rec, item);
-        }
-      }
-      __syncwarp();
-    }
-
-    // ---- T2: the header of tile j+2 has arrived: store it and request the tile's frontier ids ----------------
-    {
-      const int64_t fb2 = __shfl_sync(FULL, hv, 0);
-      int64_t fe2 = __shfl_sync(FULL, hv, 1);
-      const int64_t ein2 = __shfl_sync(FULL, hv, 2);
-      const int64_t sin2 = __shfl_sync(FULL, hv, 3);
-      if (fe2 > p.dst_stride) fe2 = p.dst_stride;  // only after a capacity error upstream
-      const uint32_t F2 = (valid2 && fe2 > fb2) ? (uint32_t)(fe2 - fb2) : 0u;
-      if (lane == 0) {
-        WarpHdr hn;
-        hn.e_in = ein2; hn.s_in = sin2; hn.fb = (uint32_t)fb2; hn.F = F2; hn.b = (int32_t)b2;
-        hn.t = valid2 ? (int32_t)t2 : -1;
-        S.hdr[cur == 0 ? 2 : cur - 1] = hn;
-      }
-      w_nx = -2;
-      const uint64_t n2 = (uint64_t)t2 * (uint64_t)WK_NODES + (uint64_t)lane;
-      if (valid2 && n2 < (uint64_t)F2) w_nx = ld_plain_i64(p.dst_samples + (int64_t)b2 * p.dst_stride + fb2 + (int64_t)n2);
-    }
-
-    if (active) {
-      // ---- B: decoupled look-back over this batch's earlier warp tiles ---------------------------------------
-      int64_t excl = 0;
-      if (t > 0) {
-        int j = t - 1;
-        uint32_t spins = 0;
-        uint64_t v = lbv;
-        while (true) {
-          const uint32_t flag = (uint32_t)(v >> 62);
-          const uint32_t incl_mask = __ballot_sync(FULL, flag == 2u);
-          const uint32_t inval_mask = __ballot_sync(FULL, flag == 0u);
-          const int first_incl = incl_mask ? __ffs(incl_mask) - 1 : 32;
-          const int first_inval = inval_mask ? __ffs(inval_mask) - 1 : 32;
-          if (first_inval < first_incl) {  // a predecessor we need has not published yet
-            if (++spins > (1u << 24)) {
-              if (lane == 0) atomicOr(p.err, DEV_ERR_WATCHDOG);
-              break;
-            }
-            __nanosleep(32);
-          } else {
-            int64_t val = lane <= first_incl ? (int64_t)(v & ST_VAL_MASK) : 0;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(FULL, val, o);
-            excl += val;
-            if (first_incl < 32) break;
-            j -= 32;
-          }
-          const int idx = j - lane;
-          v = idx >= 0 ? ld_relaxed_u64(my_status + idx) : ST_FLAG_INCL;
-        }
-        if (lane == 0) st_relaxed_u64(my_status + t, ST_FLAG_INCL | (uint64_t)(excl + total));
-      }
-      const int64_t e_base = S.hdr[cur].e_in + excl;
-      const int64_t s_base = S.hdr[cur].s_in + excl;
-      if (is_last && lane == 0) {
-        p.e_len_out[b] = e_base + total;
-        p.src_len_out[b] = s_base + total;
-      }
-      if (e_base + total > p.e_stride || s_base + total > p.src_stride) {
-        if (lane == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
-      } else if (total) {
-        // ---- D: one lane per output edge ---------------------------------------------------------------------
-        const int64_t xs = (int64_t)b * p.src_stride + s_base;  // offsets into samples[src] / the edge arrays
-        const int64_t xe = (int64_t)b * p.e_stride + e_base;
-        const int64_t col0 = (int64_t)h.fb + (int64_t)node0;
-#pragma unroll 1
-        for (uint32_t e0 = lane; e0 < total; e0 += 32 * WK_U) {
-          uint32_t word[WK_U];
-          typename std::conditional<I32, int32_t, int64_t>::type val[WK_U];
-#pragma unroll
-          for (uint32_t u = 0; u < WK_U; ++u) {
-            word[u] = s_slot[min(e0 + u * 32u, total - 1u)];  // clamped: tail lanes redo the last edge
-            const int64_t ptr = S.start[word[u] >> WK_OWNER_SHIFT] + (int64_t)(word[u] & WK_REL_MASK);
-            val[u] = 0;
-            if (e0 + u * 32u < total) {
-              if (I32) val[u] = ld_gather64_i32(p.indices32 + ptr);
-              else val[u] = ld_gather64_i64(p.indices + ptr);
-            }
-          }
-          // the three stores that do not depend on the gather go out while it is in flight
-#pragma unroll
-          for (uint32_t u = 0; u < WK_U; ++u) {
-            const uint32_t e = e0 + u * 32u;
-            if (e < total) {
-              const uint32_t own = word[u] >> WK_OWNER_SHIFT;
-              st_cs_i64(p.eidx + xe + e, S.start[own] + (int64_t)(word[u] & WK_REL_MASK));
-              st_cs_i64(p.cols + xe + e, col0 + own);
-              st_cs_i64(p.rows + xe + e, s_base + e);
-            }
-          }
-#pragma unroll
-          for (uint32_t u = 0; u < WK_U; ++u) {
-            const uint32_t e = e0 + u * 32u;
-            if (e < total) st_cs_i64(p.src_samples + xs + e, (int64_t)val[u]);  // read again only by the next hop
-          }
-        }
-      }
-    }
-    __syncwarp();  // the warp's tables are free for the next tile
-    cur = cur == 2 ? 0 : cur + 1;
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1137,25 +832,17 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
   }
 }
 
-// Tuning knobs (defaults are what bench.py measures): TCHGEO_HOP_THREADS = 128 | 256 threads per tile,
-// TCHGEO_HOP_MIN_BLOCKS = 4 | 6 | 8 register-budget variant of the 256-thread kernel.
+// Tuning knob (the default is what bench.py measures): TCHGEO_HOP_MIN_BLOCKS = 8 | 10 | 12 CTAs per SM the register
+// budget is set for (64 / 48 / 40 registers).
 inline int env_int(const char* name, int dflt) {
   const char* e = getenv(name);
   return e ? atoi(e) : dflt;
-}
-inline int hop_threads() {
-  static int v = -1;
-  if (v < 0) {
-    const int x = env_int("TCHGEO_HOP_THREADS", HOP_THREADS);
-    v = (x == 128 || x == 256) ? x : HOP_THREADS;
-  }
-  return v;
 }
 inline int hop_min_blocks() {
   static int v = -1;
   if (v < 0) {
     const int x = env_int("TCHGEO_HOP_MIN_BLOCKS", HOP_DEFAULT_MIN_BLOCKS);
-    v = (x >= 4 && x <= 8) ? x : HOP_DEFAULT_MIN_BLOCKS;  // 7, 8: 128-thread tiles only (14 / 16 CTAs per SM)
+    v = (x == 8 || x == 10 || x == 12) ? x : HOP_DEFAULT_MIN_BLOCKS;
   }
   return v;
 }
@@ -1170,7 +857,6 @@ struct Launch {
   int64_t fanout;
   int tile_nodes, tile_edges, tiles_per_batch;
   size_t status_off;  // in uint64 words
-  bool warp_tiles;    // hop_warp_kernel (32-node warp tiles) instead of hop_kernel
 };
 
 struct Plan {
@@ -1188,19 +874,7 @@ struct Plan {
   size_t off_ctrl, off_state, off_status, total_bytes;
 };
 
-constexpr size_t CTRL_WORDS = 64;  // uint32: [0] = err, [1 + i] = ticket of launch i, [1 + L + i] = its frontier bound
-
-// EXPERIMENT (TCHGEO_HOP_KERNEL=warp): hop_warp_kernel instead of hop_kernel where it applies.  Bit-exact, but
-// measured slower on B200 (hop 3: 2.11 ms against 1.79 ms, profiles/r1_experiment_warp_tile_kernel_*): the path
-// is bound by issue slots, and per-32-node look-back / header / pipeline bookkeeping costs more instructions than
-// the CTA barriers it removes.  Read on every call so that tests can switch it.
-inline bool use_warp_tiles(const tchgeo_sampling_args* a, int rel, int64_t k) {
-  const char* e = getenv("TCHGEO_HOP_KERNEL");
-  if (!(e && strcmp(e, "warp") == 0)) return false;
-  if (a->filter_mode || k < 1 || k > WK_MAX_FANOUT) return false;
-  if (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED && !(a->weights_cumsum && a->weights_cumsum[rel])) return false;
-  return true;
-}
+constexpr size_t CTRL_WORDS = 64;  // uint32: [0] = err, [1..] = one ticket per launch (grown if needed)
 
 tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   TCHGEO_REQUIRE(a != nullptr, "args is NULL");
@@ -1263,8 +937,7 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
       L.e_in_row = cur_e[r]; L.e_out_row = rows++;
       L.dst_len_row = cur_n[dt];
       const int64_t kk = std::max<int64_t>(k, 1);
-      L.warp_tiles = use_warp_tiles(a, r, k);
-      const int tile_threads = L.warp_tiles ? WK_NODES : (a->filter_mode ? FT_THREADS : hop_threads());
+      const int tile_threads = a->filter_mode ? FT_THREADS : HOP_THREADS;
       int tn = (int)std::min<int64_t>(tile_threads, std::max<int64_t>(1, MAX_TILE_EDGES / kk));
       L.tile_nodes = tn;
       L.tile_edges = (int)(tn * kk);
@@ -1294,7 +967,7 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   pl.e_row_final = cur_e;
   pl.num_rows = rows;
   pl.status_words = status_words;
-  const size_t ctrl_words = std::max(CTRL_WORDS, 2 * pl.launches.size() + 2);
+  const size_t ctrl_words = std::max(CTRL_WORDS, pl.launches.size() + 2);
   pl.off_ctrl = 0;
   pl.off_state = ((ctrl_words * 4 + 255) / 256) * 256;
   pl.off_status = pl.off_state + (((size_t)rows * pl.B * 8 + 255) / 256) * 256;
@@ -1302,101 +975,35 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   return TCHGEO_OK;
 }
 
-template <int KIND, int MINB, int NT, int TPC>
+template <int KIND, int MINB, bool I32>
 cudaError_t launch_hop_v(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
   static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(hop_kernel<KIND, MINB, NT, TPC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(hop_kernel<KIND, MINB, I32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  const int64_t grid = (tiles + TPC - 1) / TPC;
-  hop_kernel<KIND, MINB, NT, TPC><<<(unsigned)grid, NT, smem, stream>>>(hp);
-  return cudaGetLastError();
-}
-
-template <int KIND, int TPC>
-cudaError_t launch_hop_t(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
-  if (hop_threads() == 128) {
-    switch (hop_min_blocks()) {
-      case 4: return launch_hop_v<KIND, 8, 128, TPC>(hp, tiles, smem, stream);
-      case 6: return launch_hop_v<KIND, 12, 128, TPC>(hp, tiles, smem, stream);
-      case 7: return launch_hop_v<KIND, 14, 128, TPC>(hp, tiles, smem, stream);
-      case 8: return launch_hop_v<KIND, 16, 128, TPC>(hp, tiles, smem, stream);
-      default: return launch_hop_v<KIND, 10, 128, TPC>(hp, tiles, smem, stream);
-    }
-  }
-  switch (hop_min_blocks()) {
-    case 4: return launch_hop_v<KIND, 4, 256, TPC>(hp, tiles, smem, stream);
-    case 6: return launch_hop_v<KIND, 6, 256, TPC>(hp, tiles, smem, stream);
-    default: return launch_hop_v<KIND, 5, 256, TPC>(hp, tiles, smem, stream);
-  }
-}
-
-// tiles per CTA (TCHGEO_HOP_TPC = 1 | 2 | 4): the colptr gathers of all of a CTA's tiles are issued up front
-inline int hop_tpc() {
-  static int v = -1;
-  if (v < 0) {
-    const int x = env_int("TCHGEO_HOP_TPC", HOP_DEFAULT_TPC);
-    v = (x == 1 || x == 2 || x == 4) ? x : HOP_DEFAULT_TPC;
-  }
-  return v;
-}
-
-template <int KIND>
-cudaError_t launch_hop(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
-  switch (hop_tpc()) {
-    case 1: return launch_hop_t<KIND, 1>(hp, tiles, smem, stream);
-    case 4: return launch_hop_t<KIND, 4>(hp, tiles, smem, stream);
-    default: return launch_hop_t<KIND, 2>(hp, tiles, smem, stream);
-  }
-}
-
-// CTAs per SM of the persistent warp-tile kernel (TCHGEO_WARP_MIN_BLOCKS = 8 | 10 | 12: 64 / 48 / 40 registers)
-inline int warp_min_blocks() {
-  const int x = env_int("TCHGEO_WARP_MIN_BLOCKS", 10);
-  return (x == 8 || x == 10 || x == 12) ? x : 10;
-}
-
-template <int KIND, int MINB, bool I32>
-cudaError_t launch_hop_warp_v(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
-  static int resident[64] = {};  // persistent grid size per device; benign race: the value is idempotent
-  int dev = 0;
-  cudaError_t e = cudaGetDevice(&dev);
-  if (e != cudaSuccess) return e;
-  int grid_max = (dev >= 0 && dev < 64) ? resident[dev] : 0;
-  if (grid_max == 0) {
-    int sms = 0, per_sm = 0;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hop_warp_kernel<KIND, MINB, I32>, WK_WARPS * 32,
-                                                      (size_t)WK_WARPS * WK_NODES * WK_MAX_FANOUT * 4);
-    if (e != cudaSuccess) return e;
-    grid_max = sms * std::max(per_sm, 1);
-    if (dev >= 0 && dev < 64) resident[dev] = grid_max;
-  }
-  const int64_t want = (tiles + WK_WARPS - 1) / WK_WARPS;
-  const unsigned grid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, grid_max));
-  hop_warp_kernel<KIND, MINB, I32><<<grid, WK_WARPS * 32, smem, stream>>>(hp);
+  const int64_t grid = (tiles + HOP_TPC - 1) / HOP_TPC;
+  hop_kernel<KIND, MINB, I32><<<(unsigned)grid, HOP_THREADS, smem, stream>>>(hp);
   return cudaGetLastError();
 }
 
 template <int KIND, bool I32>
-cudaError_t launch_hop_warp_i(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
-  switch (warp_min_blocks()) {
-    case 8: return launch_hop_warp_v<KIND, 8, I32>(hp, tiles, smem, stream);
-    case 12: return launch_hop_warp_v<KIND, 12, I32>(hp, tiles, smem, stream);
-    default: return launch_hop_warp_v<KIND, 10, I32>(hp, tiles, smem, stream);
+cudaError_t launch_hop_i(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
+  switch (hop_min_blocks()) {
+    case 8: return launch_hop_v<KIND, 8, I32>(hp, tiles, smem, stream);
+    case 12: return launch_hop_v<KIND, 12, I32>(hp, tiles, smem, stream);
+    default: return launch_hop_v<KIND, 10, I32>(hp, tiles, smem, stream);
   }
 }
 
 template <int KIND>
-cudaError_t launch_hop_warp(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
-  return hp.indices32 ? launch_hop_warp_i<KIND, true>(hp, tiles, smem, stream)
-                      : launch_hop_warp_i<KIND, false>(hp, tiles, smem, stream);
+cudaError_t launch_hop(const HopParams& hp, int64_t tiles, size_t smem, cudaStream_t stream) {
+  return hp.indices32 ? launch_hop_i<KIND, true>(hp, tiles, smem, stream)
+                      : launch_hop_i<KIND, false>(hp, tiles, smem, stream);
 }
 
 }  // namespace
@@ -1564,8 +1171,6 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     const int64_t grid = (int64_t)L.tiles_per_batch * B;
     const size_t smem = (size_t)L.tile_edges * 5 + 16;
     hp.total_tiles = (uint32_t)((int64_t)L.tiles_per_batch * B);
-    hp.static_order = env_int("TCHGEO_EXPERIMENT_STATIC_ORDER", 0);
-    hp.max_frontier = nullptr;
     hp.filter_mode = a->filter_mode;
     hp.filter_forward = a->filter_forward;
     hp.win_lo = a->filter_window_lo;
@@ -1574,19 +1179,7 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.dst_states = a->filter_mode ? a->states[dtt] : nullptr;
     hp.src_states = a->filter_mode ? a->states[stt] : nullptr;
     cudaError_t e;
-    if (L.warp_tiles) {
-      uint32_t* bound = ctrl + 1 + n_launch + li;
-      hp.max_frontier = bound;
-      const unsigned fgrid = (unsigned)std::min<int64_t>((B + 255) / 256, 64);
-      frontier_max_kernel<<<fgrid, 256, 0, stream>>>(hp.fr_begin, hp.fr_end, B, hp.dst_stride, bound);
-      TCHGEO_CUDA_CHECK(cudaGetLastError());
-      const size_t wsmem = (size_t)WK_WARPS * WK_NODES * (size_t)L.fanout * 4;
-      switch (a->sampler_kind) {
-        case TCHGEO_SAMPLER_UNIFORM: e = launch_hop_warp<TCHGEO_SAMPLER_UNIFORM>(hp, grid, wsmem, stream); break;
-        case TCHGEO_SAMPLER_UNIFORM_REPLACE: e = launch_hop_warp<TCHGEO_SAMPLER_UNIFORM_REPLACE>(hp, grid, wsmem, stream); break;
-        default: e = launch_hop_warp<TCHGEO_SAMPLER_WEIGHTED>(hp, grid, wsmem, stream); break;
-      }
-    } else if (a->filter_mode) {
+    if (a->filter_mode) {
       const size_t fsmem = (size_t)L.tile_edges * 4 + 16;
       switch (a->sampler_kind) {
         case TCHGEO_SAMPLER_UNIFORM: hop_filtered_kernel<TCHGEO_SAMPLER_UNIFORM><<<(unsigned)grid, FT_THREADS, fsmem, stream>>>(hp); break;

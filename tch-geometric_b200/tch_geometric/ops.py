@@ -686,6 +686,10 @@ class HeterogenousSampler:
     def samples_len(self):
         return self._call.samples_len  # [B, T]
 
+    @property
+    def layer_offsets(self):
+        return self._call.layer_offsets  # [B, R, H, 3]; -1 where a relation is not sampled
+
     def batch(self, b):
         return _hetero_batch(self._call, b)
 

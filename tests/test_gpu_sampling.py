@@ -349,11 +349,10 @@ def test_heterogenous_batched_plan(thg, fakehetero):
 
 
 @pytest.mark.parametrize("kind", ["uniform", "replace", "weighted"])
-def test_warp_tile_and_cta_tile_kernels_agree(thg, kind, monkeypatch):
-    """hop_warp_kernel (persistent 32-node warp tiles, default for fanout <= 16) and hop_kernel (CTA tiles) share
-    the Philox counters, so they must produce the same bits; many batches and long per-batch look-back chains
-    (hop 3 has > 64 warp tiles per batch), hubs and zero-degree nodes included.  Both are checked against the
-    oracle on two of the batches."""
+def test_many_batches_hubs_and_long_lookback_chains(thg, kind):
+    """37 batches over a power-law graph with a 3000-neighbour hub and zero-degree nodes: tile-major tickets
+    interleave the batches, hop 3 spans several tiles per batch (look-back), heavy nodes take the warp-strided
+    draw path.  Two of the batches are checked against the oracle bit for bit, all of them structurally."""
     n = 20000
     ei = _power_law_graph(n, 11, 3000)
     ptrs, idx, _ = graph(thg, ei, n)
@@ -367,28 +366,21 @@ def test_warp_tile_and_cta_tile_kernels_agree(thg, kind, monkeypatch):
     elif kind == "weighted":
         w = np.random.default_rng(6).uniform(0.2, 5.0, hi.size)
         sampler, osampler = thg.WeightedEdgeSampler(torch.as_tensor(w).cuda()), ("weighted", w)
-    outs = {}
-    for which in ("warp", "cta"):
-        monkeypatch.setenv("TCHGEO_HOP_KERNEL", which)
-        res = thg.neighbor_sampling_homogenous_batched(ptrs, idx, dev(inputs), fan, sampler, seed=4321, batch_base=9)
-        outs[which] = [res.batch(b) for b in range(B)]
+    res = thg.neighbor_sampling_homogenous_batched(ptrs, idx, dev(inputs), fan, sampler, seed=4321, batch_base=9)
     for b in range(B):
-        for x, y in zip(outs["warp"][b][:4], outs["cta"][b][:4]):
-            assert torch.equal(x, y)
-        assert outs["warp"][b][4] == outs["cta"][b][4]
-    for b in (3, B - 1):
-        want = O.neighbor_sampling_homogenous(hp, hi, inputs[b], fan, sampler=osampler, seed=4321, batch=9 + b)
-        got = [t.cpu().numpy() for t in outs["warp"][b][:4]] + [outs["warp"][b][4]]
-        assert_same(got, want)
+        got = [t.cpu().numpy() for t in res.batch(b)[:4]] + [res.batch(b)[4]]
+        validate_tree_identities(hp, hi, inputs[b], *got, fan, replace=(kind == "replace"))
+        if b in (3, B - 1):
+            want = O.neighbor_sampling_homogenous(hp, hi, inputs[b], fan, sampler=osampler, seed=4321, batch=9 + b)
+            assert_same(got, want)
 
 
-def test_warp_tile_kernel_many_tiles_single_batch(thg, fakedataset, monkeypatch):
-    """one batch whose last hop spans ~1000 warp tiles: the look-back walks several 32-wide windows"""
+def test_many_tiles_single_batch(thg, fakedataset):
+    """one batch whose last hop spans hundreds of tiles: the look-back walks several 32-wide windows"""
     ei, n = fakedataset
     ptrs, idx, _ = graph(thg, ei, n)
     hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
     inputs = np.random.default_rng(21).integers(0, n, 400)
-    monkeypatch.setenv("TCHGEO_HOP_KERNEL", "warp")
     for sampler in (None, thg.UniformEdgeSampler(True)):
         got, seed = run_homo(thg, ptrs, idx, inputs, [16, 8, 4], sampler, state=33)
         want = O.neighbor_sampling_homogenous(hp, hi, inputs, [16, 8, 4], sampler=oracle_sampler(sampler), seed=seed)
