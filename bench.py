@@ -866,8 +866,13 @@ def run_partitioned(args):
               "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
               "config": {"workload": f"papers100M-shaped synthetic graph (N={n}, E={e_total}; {cols_rank} columns per rank), "
                                      f"CSC range-partitioned over {world} rank(s), fanouts {FANOUTS}, {S} seeds/batch, "
-                                     f"{B} batches/step/rank, NCCL all-to-all frontier exchange per hop",
-                         "parallelism": "column-range partition + all-to-all(v) of requests and answers"},
+                                     f"{B} batches/step/rank, per hop an NCCL all-to-all of the requests and "
+                                     + ("answers stored by the serve kernel straight into the requesters' buffers "
+                                        "(NVLink peer memory)" if ps.peer is not None else "an NCCL all-to-all of the answers"),
+                         "parallelism": "column-range partition; request all-to-all(v); answers: "
+                                        + ("peer-memory stores fused into the serve kernel" if ps.peer is not None
+                                           else "all-to-all(v)")},
+              "answer_exchange": "peer" if ps.peer is not None else "all_to_all",
               "phase_ms_per_step_rank0": phases, "pipelined_batch_groups": ps.num_groups,
               "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + 2 * K),
                                                    "answers": ps.stats["answer_bytes"] // (W + 2 * K)},

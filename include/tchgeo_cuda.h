@@ -270,6 +270,22 @@ TCHGEO_API tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, c
                                                     int64_t fanout, int32_t sampler_kind, uint64_t seed, uint32_t rel,
                                                     int32_t* ans /*DEVICE [n, 2*fanout] int32*/, int32_t* err_word,
                                                     tchgeo_stream stream);
+/* Same owner side with the answer exchange fused into the kernel: the requests received from rank q are rows
+ * [sum(recv_counts[:q]), +recv_counts[q]) of `req`, and the answer row of the i-th of them is stored directly into
+ * rank q's answer buffer peer_ans[q] (DEVICE pointers into NVLink peer memory, e.g. the buffer_ptrs of a torch
+ * symmetric-memory allocation; HOST array of `world` pointers) at row peer_row0[q] + i -- where the answer all-to-all
+ * would have delivered it (peer_row0[q] = number of requests rank q sent to lower-ranked owners).  The caller
+ * synchronises the ranks (a symmetric-memory barrier) before tchgeo_part_finish_hop reads its own buffer.
+ * recv_counts / peer_row0: HOST [world].  Asynchronous. */
+TCHGEO_API tchgeo_status tchgeo_serve_requests_rows_peer(const int64_t* ptrs_local, const int64_t* indices_local,
+                                                         const double* weights_local, int64_t col_begin,
+                                                         int64_t ncols_local, int64_t nnz_local,
+                                                         const int64_t* req /*DEVICE [n,2]*/, int64_t n, int64_t fanout,
+                                                         int32_t sampler_kind, uint64_t seed, uint32_t rel, int32_t world,
+                                                         void* const* peer_ans /*HOST [world] of DEVICE int32 buffers*/,
+                                                         const int64_t* recv_counts /*HOST [world]*/,
+                                                         const int64_t* peer_row0 /*HOST [world]*/, int32_t* err_word,
+                                                         tchgeo_stream stream);
 TCHGEO_API size_t tchgeo_part_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap);
 TCHGEO_API tchgeo_status tchgeo_part_finish_hop(const int64_t* req /*DEVICE [F,2] as sent*/, const int32_t* ans /*DEVICE [F, 2*fanout]*/,
                                                 int64_t num_requests, int64_t fanout,

@@ -21,6 +21,7 @@ namespace {
 constexpr int SV_THREADS = 128;
 constexpr int SV_LIGHT_MAX = 32;
 constexpr int SV_MAX_TILE_SLOTS = 8192;
+constexpr int SV_MAX_WORLD = 64;
 
 struct ServeParams {
   const int64_t* ptrs;      // local colptr [ncols+1], rebased to the local indices array
@@ -37,6 +38,13 @@ struct ServeParams {
   int64_t col_begin, ncols, edge_base, n;
   int32_t fanout, tile_reqs;
   uint32_t key0, key1, rel;
+  // peer mode (tchgeo_serve_requests_rows_peer): the requests are grouped by requesting rank; request i of rank q's
+  // segment [peer_seg[q], peer_seg[q+1]) is answered into rank q's OWN answer buffer (NVLink peer memory) at row
+  // peer_row0[q] + (i - peer_seg[q]), i.e. where the answer all-to-all would have put it
+  int32_t peer_world;                    // 0: answers go to out32 / out_ids
+  int32_t* peer_base[SV_MAX_WORLD];
+  int64_t peer_seg[SV_MAX_WORLD + 1];
+  int64_t peer_row0[SV_MAX_WORLD];
 };
 
 __device__ __forceinline__ void sv_block(const Philox4& r, uint32_t step0, uint32_t deg, uint32_t k, uint32_t* slots) {
@@ -57,6 +65,7 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
   __shared__ uint8_t s_chown[SV_LIGHT_MAX * SV_THREADS];
   __shared__ uint8_t s_heavy[SV_THREADS];
   __shared__ uint32_t s_nheavy;
+  __shared__ int32_t* s_row[SV_THREADS];  // compact answers: where request n's row goes (local buffer or a peer's)
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   uint32_t* s_slot = reinterpret_cast<uint32_t*>(dyn_smem);  // [tile_reqs * fanout]
 
@@ -69,6 +78,13 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
   uint32_t deg = 0, nblocks = 0;
   int64_t start = 0;
   bool heavy = false;
+  if (tid < nn && p.out32) s_row[tid] = p.out32 + (r0 + tid) * 2 * (int64_t)k;
+  if (tid < nn && p.peer_world > 0) {
+    const int64_t i = r0 + tid;
+    int q = 0;
+    while (q + 1 < p.peer_world && i >= p.peer_seg[q + 1]) ++q;
+    s_row[tid] = p.peer_base[q] + (p.peer_row0[q] + (i - p.peer_seg[q])) * 2 * (int64_t)k;
+  }
   if (tid < nn) {
     const int64_t w = p.req_ids[(r0 + tid) * p.req_stride] - p.col_begin;
     const int64_t meta = p.req_meta[(r0 + tid) * p.req_stride];
@@ -167,8 +183,8 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
       id = ld_gather64_i64(p.indices + lp);
       gp = p.edge_base + lp;
     }
-    if (p.out32) {
-      int32_t* row = p.out32 + (r0 + n) * 2 * (int64_t)k;
+    if (p.out32 || p.peer_world > 0) {
+      int32_t* row = s_row[n];
       row[s] = (int32_t)id;
       row[k + s] = gp < 0 ? -1 : (int32_t)(gp - p.edge_base);
     } else {
@@ -187,13 +203,29 @@ static tchgeo_status serve_launch(const int64_t* ptrs_local, const int64_t* indi
                                   int64_t col_begin, int64_t ncols_local, int64_t edge_base, const int64_t* req_ids,
                                   const int64_t* req_meta, int64_t req_stride, int64_t n, int64_t fanout,
                                   int32_t sampler_kind, uint64_t seed, uint32_t rel, int64_t* out_ids, int64_t* out_ptrs,
-                                  int64_t out_stride, int32_t* out32, uint32_t* err, cudaStream_t stream) {
+                                  int64_t out_stride, int32_t* out32, uint32_t* err, cudaStream_t stream,
+                                  int32_t peer_world = 0, void* const* peer_base = nullptr,
+                                  const int64_t* peer_counts = nullptr, const int64_t* peer_row0 = nullptr) {
   TCHGEO_REQUIRE(n >= 0 && fanout >= 0 && fanout <= SV_MAX_TILE_SLOTS && ncols_local >= 0, "bad serve argument");
   TCHGEO_REQUIRE(sampler_kind >= 0 && sampler_kind <= 2 && err != nullptr, "bad serve argument");
   TCHGEO_REQUIRE(sampler_kind != TCHGEO_SAMPLER_WEIGHTED || weights_local != nullptr, "weighted serve without weights");
   if (n == 0 || fanout == 0) return TCHGEO_OK;
-  TCHGEO_REQUIRE(ptrs_local && req_ids && req_meta && (out32 || (out_ids && out_ptrs)), "NULL pointer");
+  TCHGEO_REQUIRE(ptrs_local && req_ids && req_meta && (out32 || peer_world > 0 || (out_ids && out_ptrs)), "NULL pointer");
   ServeParams sp;
+  sp.peer_world = peer_world;
+  if (peer_world > 0) {
+    TCHGEO_REQUIRE(peer_world <= SV_MAX_WORLD && peer_base && peer_counts && peer_row0, "bad peer table");
+    int64_t at = 0;
+    for (int q = 0; q < peer_world; ++q) {
+      TCHGEO_REQUIRE(peer_counts[q] >= 0 && peer_row0[q] >= 0 && (peer_counts[q] == 0 || peer_base[q]), "bad peer table entry %d", q);
+      sp.peer_base[q] = (int32_t*)peer_base[q];
+      sp.peer_seg[q] = at;
+      sp.peer_row0[q] = peer_row0[q];
+      at += peer_counts[q];
+    }
+    sp.peer_seg[peer_world] = at;
+    TCHGEO_REQUIRE(at == n, "peer segment sizes must add up to the number of requests");
+  }
   sp.ptrs = ptrs_local; sp.indices = indices_local; sp.weights = weights_local;
   sp.req_ids = req_ids; sp.req_meta = req_meta; sp.req_stride = req_stride;
   sp.out_ids = out_ids; sp.out_ptrs = out_ptrs; sp.out_stride = out_stride; sp.out32 = out32;
@@ -476,6 +508,22 @@ extern "C" tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, c
   return serve_launch(ptrs_local, indices_local, weights_local, col_begin, ncols_local, 0, req, req ? req + 1 : req, 2, n,
                       fanout, sampler_kind, seed, rel, nullptr, nullptr, 0, ans, (uint32_t*)err_word,
                       (cudaStream_t)stream_);
+}
+
+extern "C" tchgeo_status tchgeo_serve_requests_rows_peer(const int64_t* ptrs_local, const int64_t* indices_local,
+                                                         const double* weights_local, int64_t col_begin,
+                                                         int64_t ncols_local, int64_t nnz_local, const int64_t* req,
+                                                         int64_t n, int64_t fanout, int32_t sampler_kind, uint64_t seed,
+                                                         uint32_t rel, int32_t world, void* const* peer_ans,
+                                                         const int64_t* recv_counts, const int64_t* peer_row0,
+                                                         int32_t* err_word, tchgeo_stream stream_) {
+  // The owner's half of the answer exchange fused into the serve kernel: every answer row is stored straight into the
+  // REQUESTER's answer buffer over NVLink peer memory, at the row the all-to-all would have delivered it to.
+  TCHGEO_REQUIRE(nnz_local >= 0 && nnz_local < ((int64_t)1 << 31), "a rank's share of the CSC must stay below 2^31 entries");
+  TCHGEO_REQUIRE(world >= 1, "world must be positive");
+  return serve_launch(ptrs_local, indices_local, weights_local, col_begin, ncols_local, 0, req, req ? req + 1 : req, 2, n,
+                      fanout, sampler_kind, seed, rel, nullptr, nullptr, 0, nullptr, (uint32_t*)err_word,
+                      (cudaStream_t)stream_, world, peer_ans, recv_counts, peer_row0);
 }
 
 extern "C" size_t tchgeo_part_hop_workspace_bytes(int64_t num_batches, int64_t frontier_cap) {

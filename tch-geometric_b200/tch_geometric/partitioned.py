@@ -22,6 +22,8 @@ Two drivers share the partition, the communicator and the serve kernel:
                           it on the CPU with the oracle as the owner, and the GPU tests use it as a cross-check.
 """
 import ctypes
+import os
+import warnings
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -308,15 +310,60 @@ class _PlanGroup:
         return t[:need].view(max(int(rows), 1), int(cols))
 
 
+class _PeerAnswers:
+    """Answer exchange fused into the owner's serve kernel (NVLink peer memory instead of an all-to-all).
+
+    Every rank owns one persistent answer buffer in torch symmetric memory; `buffer_ptrs` gives every rank the device
+    address of every other rank's buffer.  Per hop the ranks all-gather the [world, world] matrix of request counts, so
+    an owner knows at which row of the REQUESTER's buffer each of its answers belongs (the row the answer all-to-all
+    would have delivered it to), and tchgeo_serve_requests_rows_peer stores the rows there directly.  A symmetric-memory
+    barrier on the stream separates the owners' stores from the requester's layout kernel.  The request all-to-all of
+    the next hop orders the next round of stores after that kernel (an owner only has a rank's requests once that
+    rank's previous kernels are done), so one buffer per rank is enough."""
+
+    def __init__(self, plan):
+        import torch.distributed._symmetric_memory as symm
+        comm, dev = plan.comm, plan.device
+        group = comm.group if comm.group is not None else dist.group.WORLD
+        words = max((plan.B * f * 2 * k for f, k in zip(plan.capF, plan.fanouts)), default=1)
+        self.buf = symm.empty(max(int(words), 1), dtype=torch.int32, device=dev)
+        self.hdl = symm.rendezvous(self.buf, group)
+        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
+        if len(ptrs) != comm.world or int(self.hdl.rank) != comm.rank:
+            raise RuntimeError("symmetric memory rendezvous does not match the communicator")
+        self.ptrs = np.array(ptrs, dtype=np.uint64)
+        self.cmat = torch.zeros((comm.world, comm.world), dtype=torch.int64, device=dev)
+        self.group = group
+
+    def exchange_requests(self, comm, counts, req, alloc):
+        """-> (recv_counts, send_counts, received request rows, row0 of this owner's answers in every requester's buffer)"""
+        dist.all_gather_into_tensor(self.cmat.reshape(-1), counts.contiguous(), group=self.group)
+        C = self.cmat.tolist()                       # the hop's one host synchronisation
+        me = comm.rank
+        sc = C[me]
+        rc = [C[q][me] for q in range(comm.world)]
+        row0 = [sum(C[q][:me]) for q in range(comm.world)]
+        out = alloc(sum(rc))
+        dist.all_to_all_single(out[:sum(rc)], req[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc, group=self.group)
+        return rc, sc, out, row0
+
+    def barrier(self):
+        self.hdl.barrier(channel=0)
+
+
 class PartitionedPlan:
     """neighbor_sampling_homogenous over a column-partitioned CSC, device pipeline.  `sample` is collective."""
 
     def __init__(self, part: ColumnPartition, num_batches: int, seeds_per_batch: int, num_neighbors: Sequence[int],
-                 sampler=None, comm=None, serve_rows=None, edge_bases=None, groups: Optional[int] = None):
+                 sampler=None, comm=None, serve_rows=None, edge_bases=None, groups: Optional[int] = None,
+                 peer_answers: Optional[bool] = None):
         """serve_rows(r_req [n,2], recv_counts, fanout, seed, ans [n,2k] int32) overrides the owner side (tests simulate
         several owners on one GPU with it); default: tchgeo_serve_requests_rows over `part`.
         edge_bases: every rank's ColumnPartition.edge_base (default: all-gathered through the communicator).
-        groups: batch groups pipelined on separate streams (default 1: the overlap did not pay on 2 B200s)."""
+        groups: batch groups pipelined on separate streams (default 1: the overlap did not pay on 2 B200s).
+        peer_answers: store the answers straight into the requesters' buffers over NVLink peer memory instead of an
+        answer all-to-all (_PeerAnswers).  None = when it applies (several CUDA ranks, one group, default owner side;
+        TCHGEO_PEER_ANSWERS=0 turns it off) and the symmetric-memory rendezvous succeeds; True = required."""
         self.part = part
         self.serve_rows = serve_rows
         self.fanouts = [int(k) for k in num_neighbors]
@@ -358,6 +405,28 @@ class PartitionedPlan:
             self.groups = [_PlanGroup(self, cuts[g], cuts[g + 1]) for g in range(self.num_groups)]
         self.stats = {"requests_sent": 0, "request_bytes": 0, "answer_bytes": 0}
         self.profile = None   # set to {} to collect per-phase device times (ms, CUDA events, group 0's stream)
+        self.peer = None
+        applies = (isinstance(self.comm, DistComm) and self.comm.world > 1 and dev.type == "cuda"
+                   and self.serve_rows is None and self.num_groups == 1 and H > 0)
+        want = peer_answers if peer_answers is not None else os.environ.get("TCHGEO_PEER_ANSWERS", "1") != "0"
+        if peer_answers and not applies:
+            raise ValueError("peer_answers needs several CUDA ranks, one batch group and the default owner side")
+        if want and applies:
+            # collective: every rank takes the same branch, and a failure is agreed on before anyone proceeds
+            ok = 1
+            try:
+                with torch.cuda.device(dev):
+                    self.peer = _PeerAnswers(self)
+            except Exception as e:  # noqa: BLE001  (no symmetric memory on this system: keep the all-to-all)
+                ok, self.peer, err = 0, None, e
+            flag = torch.tensor([ok], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.comm.group)
+            if int(flag.item()) == 0:
+                if peer_answers:
+                    raise RuntimeError(f"symmetric-memory rendezvous failed on some rank{'' if ok else ': %r' % (err,)}")
+                if not ok:
+                    warnings.warn(f"peer-memory answers unavailable, using the answer all-to-all: {err!r}")
+                self.peer = None
 
     def _mark(self, g, marks, name):
         if marks is not None and g is self.groups[0]:
@@ -376,20 +445,38 @@ class PartitionedPlan:
 
     def _requests(self, g):
         # host reads the counts: syncs g's stream only
-        rc, sc, r_req = self.comm.exchange_rows(g.counts[0], g.req,
-                                                lambda n: g.buf("r_req", n, 2, torch.int64, self.device))
+        alloc = lambda n: g.buf("r_req", n, 2, torch.int64, self.device)
+        if self.peer is not None:
+            rc, sc, r_req, row0 = self.peer.exchange_requests(self.comm, g.counts[0], g.req, alloc)
+            g.hop.update(row0=row0)
+        else:
+            rc, sc, r_req = self.comm.exchange_rows(g.counts[0], g.req, alloc)
         g.hop.update(rc=rc, sc=sc, r_req=r_req, F=sum(sc), n_recv=sum(rc))
 
     def _serve(self, g, k, seed):
         hp = g.hop
+        if self.peer is not None:
+            part, dev = self.part, self.device
+            rc = np.array(hp["rc"], dtype=np.int64)
+            row0 = np.array(hp["row0"], dtype=np.int64)
+            with torch.cuda.device(dev):
+                N.check(N.lib.tchgeo_serve_requests_rows_peer(
+                    _ptr(part.ptrs), _ptr(part.indices), _ptr(part.weights), part.col_begin, part.col_end - part.col_begin,
+                    part.indices.numel(), _ptr(hp["r_req"]), int(hp["n_recv"]), int(k), self.kind, seed, 0, self.comm.world,
+                    self.peer.ptrs.ctypes.data, rc.ctypes.data, row0.ctypes.data, _ptr(self.err), _stream(dev)))
+            return
         hp["ans"] = g.buf("ans", hp["n_recv"], 2 * k, torch.int32, self.device)
         if self.serve_rows is not None:
             self.serve_rows(hp["r_req"], hp["rc"], k, seed, hp["ans"])
         else:
             serve_rows(self.part, hp["r_req"], hp["n_recv"], k, self.kind, seed, hp["ans"], self.err)
 
-    def _answers(self, g):
+    def _answers(self, g, k):
         hp = g.hop
+        if self.peer is not None:
+            self.peer.barrier()      # every owner's stores have landed in every requester's buffer
+            hp["back"] = self.peer.buf[:max(hp["F"], 1) * 2 * k].view(max(hp["F"], 1), 2 * k)
+            return
         hp["back"] = self.comm.return_rows(hp["ans"], hp["n_recv"], hp["F"], hp["sc"], hp["rc"],
                                            lambda n: g.buf("back", n, hp["ans"].shape[1], torch.int32, self.device))
 
@@ -442,7 +529,7 @@ class PartitionedPlan:
                         self._mark(g, marks, "serve")
                 for g in self.groups:
                     with on(g):
-                        self._answers(g)
+                        self._answers(g, k)
                         self._mark(g, marks, "a2a_answers")
                         self._finish(g, h, k, batch_base)
                         self._mark(g, marks, "layout")

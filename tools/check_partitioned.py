@@ -46,13 +46,19 @@ def main():
         ok &= all(torch.equal(g, x) for g, x in zip(got[b][:4], want.batch(b)[:4]))
         ok &= list(got[b][4]) == list(want.batch(b)[4])
     edges = sum(int(g[1].numel()) for g in got)
-    # the device pipeline (what bench.py --workload partitioned times)
+    # the device pipeline (what bench.py --workload partitioned times): with the answer all-to-all, and with the answers
+    # stored straight into the requesters' buffers over NVLink peer memory (the default when symmetric memory works)
+    plan_a2a = PartitionedPlan(part, B, S, fan, comm=DistComm(), peer_answers=False)
     plan = PartitionedPlan(part, B, S, fan, comm=DistComm())
-    res = plan.sample(seeds, seed=31, batch_base=rank * B)
-    ok_plan = bool((res.layer_offsets == want.layer_offsets).all())
-    for b in range(B):
-        ok_plan &= all(torch.equal(g, x) for g, x in zip(res.batch(b)[:4], want.batch(b)[:4]))
-    ok &= ok_plan
+    peer_mode = plan.peer is not None
+    for pl in (plan_a2a, plan):
+        for sd in (31, 32):   # twice: the second call reuses the persistent buffers
+            res = pl.sample(seeds, seed=sd, batch_base=rank * B)
+            ref = want if sd == 31 else thg.neighbor_sampling_homogenous_batched(ptrs, idx, seeds, fan, seed=sd, batch_base=rank * B)
+            ok_plan = bool((res.layer_offsets == ref.layer_offsets).all())
+            for b in range(B):
+                ok_plan &= all(torch.equal(g, x) for g, x in zip(res.batch(b)[:4], ref.batch(b)[:4]))
+            ok &= ok_plan
     dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
@@ -61,6 +67,12 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     dt_torch = (time.perf_counter() - t0) / args.iters
+    t0 = time.perf_counter()
+    for it in range(args.iters):
+        plan_a2a.sample(seeds, seed=100 + it, batch_base=rank * B)
+    torch.cuda.synchronize()
+    dist.barrier()
+    dt_a2a = (time.perf_counter() - t0) / args.iters
     t0 = time.perf_counter()
     for it in range(args.iters):
         plan.sample(seeds, seed=100 + it, batch_base=rank * B)
@@ -73,6 +85,8 @@ def main():
         print(json.dumps({"check": "partitioned == replicated (bit-exact)", "ranks_ok": int(flag[0].item()), "world": world,
                           "graph": {"nodes": n, "edges": int(idx.numel())}, "batches_per_rank": B,
                           "edges_per_call_all_ranks": flag[1].item(), "sec_per_call": dt,
+                          "answer_exchange": "peer-memory stores from the serve kernel" if peer_mode else "all-to-all",
+                          "sec_per_call_answer_all_to_all": dt_a2a,
                           "sec_per_call_torch_orchestration": dt_torch,
                           "edges_per_sec": flag[1].item() / dt, "request_bytes": ps.stats["request_bytes"],
                           "answer_bytes": ps.stats["answer_bytes"]}), flush=True)
