@@ -264,6 +264,27 @@ TCHGEO_API tchgeo_status tchgeo_part_begin_hop(const int64_t* samples /*DEVICE [
                                                void* workspace /*DEVICE, tchgeo_part_hop_workspace_bytes; the same
                                                buffer must be passed to tchgeo_part_finish_hop of this hop*/,
                                                size_t workspace_bytes, tchgeo_stream stream);
+/* tchgeo_part_begin_hop in two halves, for the request exchange fused into the scatter kernel: count_hop fills
+ * counts[world]; the ranks all-gather the [world, world] count matrix; scatter_hop then writes every request row into
+ * the local `req` (the layout kernel reads it) AND, when peer_req != NULL, straight into the owning rank's request
+ * buffer peer_req[o] (HOST array of `world` DEVICE pointers into NVLink peer memory) at row peer_row0[o] + its index
+ * inside this rank's group for owner o -- the row the request all-to-all would have delivered it to (peer_row0[o] =
+ * number of requests lower-ranked requesters send to owner o).  The caller synchronises the ranks before the owners
+ * serve.  Both asynchronous; same workspace as tchgeo_part_finish_hop. */
+TCHGEO_API tchgeo_status tchgeo_part_count_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
+                                               const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
+                                               int64_t cols_per_rank, int32_t world, int64_t* counts /*DEVICE [world]*/,
+                                               int64_t* cursor /*DEVICE [world] scratch*/, int32_t* err_word,
+                                               void* workspace, size_t workspace_bytes, tchgeo_stream stream);
+TCHGEO_API tchgeo_status tchgeo_part_scatter_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
+                                                 const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
+                                                 int64_t cols_per_rank, int32_t world, uint32_t batch_base,
+                                                 const int64_t* counts /*DEVICE [world], from count_hop*/,
+                                                 int64_t* cursor /*DEVICE [world], zeroed by count_hop*/,
+                                                 int64_t* req /*DEVICE [B*frontier_cap, 2]*/,
+                                                 void* const* peer_req /*HOST [world] of DEVICE buffers, or NULL*/,
+                                                 const int64_t* peer_row0 /*HOST [world]*/, int32_t* err_word,
+                                                 void* workspace, size_t workspace_bytes, tchgeo_stream stream);
 TCHGEO_API tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, const int64_t* indices_local,
                                                     const double* weights_local, int64_t col_begin, int64_t ncols_local,
                                                     int64_t nnz_local, const int64_t* req /*DEVICE [n,2]*/, int64_t n,

@@ -345,11 +345,20 @@ __global__ void __launch_bounds__(PT_THREADS) part_count_kernel(const PartFronti
   if (threadIdx.x < f.world && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
 }
 
+// peer mode of part_scatter_kernel: the request rows are ALSO stored straight into the owners' request buffers
+// (NVLink peer memory), at the rows the request all-to-all would have delivered them to
+struct PeerReq {
+  int32_t world;                // 0: off
+  int64_t* base[PT_MAX_WORLD];  // owner o's request buffer [rows, 2]
+  int64_t row0[PT_MAX_WORLD];   // first row of this rank's segment in owner o's buffer
+};
+
 __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFrontier f, const unsigned long long* counts,
                                                                  unsigned long long* cursor, int64_t* req,
-                                                                 int32_t* slot_of) {
+                                                                 int32_t* slot_of, const PeerReq peer) {
   __shared__ unsigned int hist[PT_MAX_WORLD];
-  __shared__ unsigned long long base[PT_MAX_WORLD];
+  __shared__ unsigned long long base[PT_MAX_WORLD];    // row in the local send buffer
+  __shared__ unsigned long long within[PT_MAX_WORLD];  // the same row counted from the start of the owner's group
   if (threadIdx.x < PT_MAX_WORLD) hist[threadIdx.x] = 0u;
   __syncthreads();
   const int64_t b = blockIdx.y, j = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
@@ -362,13 +371,18 @@ __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFron
     unsigned long long off = 0;  // exclusive offset of this owner's group in the send buffer
     for (int r = 0; r < threadIdx.x; ++r) off += counts[r];
     const unsigned int h = hist[threadIdx.x];
-    base[threadIdx.x] = off + (h ? atomicAdd(cursor + threadIdx.x, (unsigned long long)h) : 0ull);
+    const unsigned long long w = h ? atomicAdd(cursor + threadIdx.x, (unsigned long long)h) : 0ull;
+    within[threadIdx.x] = w;
+    base[threadIdx.x] = off + w;
   }
   __syncthreads();
   if (ok) {
     const unsigned long long q = base[o] + rank;
     const uint64_t meta = ((uint64_t)(f.batch_base + (uint32_t)b) << 32) | (uint64_t)(uint32_t)pos;
-    *reinterpret_cast<longlong2*>(req + 2 * q) = make_longlong2((long long)id, (long long)meta);
+    const longlong2 row = make_longlong2((long long)id, (long long)meta);
+    *reinterpret_cast<longlong2*>(req + 2 * q) = row;  // the layout kernel reads the local copy (owner of a slot)
+    if (peer.world > 0)
+      *reinterpret_cast<longlong2*>(peer.base[o] + 2 * (peer.row0[o] + (int64_t)(within[o] + rank))) = row;
     slot_of[b * f.capF + j] = (int32_t)q;  // where this frontier node's answer will be found (frontier order, coalesced)
   }
 }
@@ -465,20 +479,21 @@ bool part_ws_layout(int64_t num_batches, int64_t frontier_cap, PartWs& w) {
 }  // namespace
 }  // namespace tchgeo
 
-extern "C" tchgeo_status tchgeo_part_begin_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
-                                               const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
-                                               int64_t cols_per_rank, int32_t world, uint32_t batch_base,
-                                               int64_t* counts, int64_t* cursor, int64_t* req, int32_t* err_word,
-                                               void* workspace, size_t workspace_bytes, tchgeo_stream stream_) {
+static tchgeo_status part_begin(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
+                                const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap, int64_t cols_per_rank,
+                                int32_t world, uint32_t batch_base, int64_t* counts, int64_t* cursor, int64_t* req,
+                                int32_t* err_word, void* workspace, size_t workspace_bytes, cudaStream_t stream,
+                                bool do_count, bool do_scatter, void* const* peer_req, const int64_t* peer_row0) {
   TCHGEO_REQUIRE(world >= 1 && world <= PT_MAX_WORLD, "world size must be in [1, 64]");
   TCHGEO_REQUIRE(err_word != nullptr, "NULL pointer");
   TCHGEO_REQUIRE(num_batches >= 0 && frontier_cap >= 0 && cols_per_rank >= 1 && samples_stride >= 0, "bad argument");
   TCHGEO_REQUIRE(counts && cursor, "NULL pointer");
-  cudaStream_t stream = (cudaStream_t)stream_;
-  TCHGEO_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)world * 8, stream));
-  TCHGEO_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)world * 8, stream));
+  if (do_count) {
+    TCHGEO_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)world * 8, stream));
+    TCHGEO_CUDA_CHECK(cudaMemsetAsync(cursor, 0, (size_t)world * 8, stream));
+  }
   if (num_batches == 0 || frontier_cap == 0) return TCHGEO_OK;
-  TCHGEO_REQUIRE(samples && fr_end && req, "NULL pointer");
+  TCHGEO_REQUIRE(samples && fr_end && (req || !do_scatter), "NULL pointer");
   TCHGEO_REQUIRE(num_batches <= 65535, "at most 65535 batches per call");
   PartWs W;
   TCHGEO_REQUIRE(part_ws_layout(num_batches, frontier_cap, W), "frontier too large for one call");
@@ -490,12 +505,58 @@ extern "C" tchgeo_status tchgeo_part_begin_hop(const int64_t* samples, int64_t s
   PartFrontier f;
   f.samples = samples; f.samples_stride = samples_stride; f.fr_begin = fr_begin; f.fr_end = fr_end;
   f.B = num_batches; f.capF = frontier_cap; f.cols_per_rank = cols_per_rank; f.world = world; f.batch_base = batch_base;
-  part_count_kernel<<<grid, PT_THREADS, 0, stream>>>(f, (unsigned long long*)counts, (uint32_t*)err_word);
-  TCHGEO_CUDA_CHECK(cudaGetLastError());
-  part_scatter_kernel<<<grid, PT_THREADS, 0, stream>>>(f, (const unsigned long long*)counts,
-                                                      (unsigned long long*)cursor, req, slot_of);
-  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  if (do_count) {
+    part_count_kernel<<<grid, PT_THREADS, 0, stream>>>(f, (unsigned long long*)counts, (uint32_t*)err_word);
+    TCHGEO_CUDA_CHECK(cudaGetLastError());
+  }
+  if (do_scatter) {
+    PeerReq peer;
+    peer.world = 0;
+    if (peer_req) {
+      TCHGEO_REQUIRE(peer_row0 != nullptr, "peer_row0 is NULL");
+      peer.world = world;
+      for (int o = 0; o < world; ++o) {
+        TCHGEO_REQUIRE(peer_req[o] != nullptr && peer_row0[o] >= 0, "bad peer request table entry %d", o);
+        peer.base[o] = (int64_t*)peer_req[o];
+        peer.row0[o] = peer_row0[o];
+      }
+    }
+    part_scatter_kernel<<<grid, PT_THREADS, 0, stream>>>(f, (const unsigned long long*)counts,
+                                                        (unsigned long long*)cursor, req, slot_of, peer);
+    TCHGEO_CUDA_CHECK(cudaGetLastError());
+  }
   return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_part_begin_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
+                                               const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
+                                               int64_t cols_per_rank, int32_t world, uint32_t batch_base,
+                                               int64_t* counts, int64_t* cursor, int64_t* req, int32_t* err_word,
+                                               void* workspace, size_t workspace_bytes, tchgeo_stream stream_) {
+  return part_begin(samples, samples_stride, fr_begin, fr_end, num_batches, frontier_cap, cols_per_rank, world, batch_base,
+                    counts, cursor, req, err_word, workspace, workspace_bytes, (cudaStream_t)stream_, true, true, nullptr,
+                    nullptr);
+}
+
+extern "C" tchgeo_status tchgeo_part_count_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
+                                               const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
+                                               int64_t cols_per_rank, int32_t world, int64_t* counts, int64_t* cursor,
+                                               int32_t* err_word, void* workspace, size_t workspace_bytes,
+                                               tchgeo_stream stream_) {
+  return part_begin(samples, samples_stride, fr_begin, fr_end, num_batches, frontier_cap, cols_per_rank, world, 0, counts,
+                    cursor, nullptr, err_word, workspace, workspace_bytes, (cudaStream_t)stream_, true, false, nullptr,
+                    nullptr);
+}
+
+extern "C" tchgeo_status tchgeo_part_scatter_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
+                                                 const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,
+                                                 int64_t cols_per_rank, int32_t world, uint32_t batch_base,
+                                                 const int64_t* counts, int64_t* cursor, int64_t* req,
+                                                 void* const* peer_req, const int64_t* peer_row0, int32_t* err_word,
+                                                 void* workspace, size_t workspace_bytes, tchgeo_stream stream_) {
+  return part_begin(samples, samples_stride, fr_begin, fr_end, num_batches, frontier_cap, cols_per_rank, world, batch_base,
+                    const_cast<int64_t*>(counts), cursor, req, err_word, workspace, workspace_bytes, (cudaStream_t)stream_,
+                    false, true, peer_req, peer_row0);
 }
 
 extern "C" tchgeo_status tchgeo_serve_requests_rows(const int64_t* ptrs_local, const int64_t* indices_local,

@@ -97,6 +97,11 @@ def _load():
     lib.tchgeo_serve_requests_rows.restype = c_i32
     lib.tchgeo_serve_requests_rows.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_u64, c_u32,
                                                c_vp, c_vp, c_vp]
+    lib.tchgeo_part_count_hop.restype = c_i32
+    lib.tchgeo_part_count_hop.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]
+    lib.tchgeo_part_scatter_hop.restype = c_i32
+    lib.tchgeo_part_scatter_hop.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_u32, c_vp, c_vp, c_vp, c_vp,
+                                            c_vp, c_vp, c_vp, c_sz, c_vp]
     lib.tchgeo_serve_requests_rows_peer.restype = c_i32
     lib.tchgeo_serve_requests_rows_peer.argtypes = [c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, c_i64, c_i32, c_u64,
                                                     c_u32, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]
@@ -140,7 +145,7 @@ EXPORTS = [
     "tchgeo_abi_version", "tchgeo_last_error", "tchgeo_device_set_l2_fetch_granularity", "tchgeo_ind2ptr", "tchgeo_coo_to_csx_workspace_bytes",
     "tchgeo_coo_to_csx", "tchgeo_csc_edge_cumsum_f64", "tchgeo_csc_sort_edges_workspace_bytes", "tchgeo_csc_sort_edges", "tchgeo_compress_indices", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
     "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_timed", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
-    "tchgeo_serve_requests", "tchgeo_part_begin_hop", "tchgeo_serve_requests_rows", "tchgeo_serve_requests_rows_peer", "tchgeo_part_hop_workspace_bytes", "tchgeo_part_finish_hop", "tchgeo_status_from_error_word", "tchgeo_negative_sampling_capacity", "tchgeo_negative_sampling_workspace_bytes", "tchgeo_negative_sampling", "tchgeo_random_walk", "tchgeo_random_walk_ex", "tchgeo_tempo_random_walk", "tchgeo_gather_rows", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
+    "tchgeo_serve_requests", "tchgeo_part_begin_hop", "tchgeo_part_count_hop", "tchgeo_part_scatter_hop", "tchgeo_serve_requests_rows", "tchgeo_serve_requests_rows_peer", "tchgeo_part_hop_workspace_bytes", "tchgeo_part_finish_hop", "tchgeo_status_from_error_word", "tchgeo_negative_sampling_capacity", "tchgeo_negative_sampling_workspace_bytes", "tchgeo_negative_sampling", "tchgeo_random_walk", "tchgeo_random_walk_ex", "tchgeo_tempo_random_walk", "tchgeo_gather_rows", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
 ]
 
 

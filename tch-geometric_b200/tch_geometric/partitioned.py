@@ -310,45 +310,58 @@ class _PlanGroup:
         return t[:need].view(max(int(rows), 1), int(cols))
 
 
-class _PeerAnswers:
-    """Answer exchange fused into the owner's serve kernel (NVLink peer memory instead of an all-to-all).
+class _PeerExchange:
+    """Both exchanges of a hop fused into the kernels on either side of them (NVLink peer memory instead of all-to-alls).
 
-    Every rank owns one persistent answer buffer in torch symmetric memory; `buffer_ptrs` gives every rank the device
-    address of every other rank's buffer.  Per hop the ranks all-gather the [world, world] matrix of request counts, so
-    an owner knows at which row of the REQUESTER's buffer each of its answers belongs (the row the answer all-to-all
-    would have delivered it to), and tchgeo_serve_requests_rows_peer stores the rows there directly.  A symmetric-memory
-    barrier on the stream separates the owners' stores from the requester's layout kernel.  The request all-to-all of
-    the next hop orders the next round of stores after that kernel (an owner only has a rank's requests once that
-    rank's previous kernels are done), so one buffer per rank is enough."""
+    Every rank owns a persistent request buffer and a persistent answer buffer in torch symmetric memory; `buffer_ptrs`
+    gives every rank the device address of every other rank's buffers.  Per hop the ranks all-gather the [world, world]
+    matrix of request counts (the hop's one host synchronisation), which tells every rank at which row of which peer
+    buffer each of its rows belongs -- the row the all-to-all would have delivered it to:
+      * tchgeo_part_scatter_hop stores every request row straight into the OWNER's request buffer,
+      * tchgeo_serve_requests_rows_peer stores every answer row straight into the REQUESTER's answer buffer,
+    and a symmetric-memory barrier on the stream follows each of the two kernels (requests landed -> serve; answers
+    landed -> layout).  Those two barriers also order the next round of stores after the previous round's readers, so
+    one buffer of each kind per rank is enough.  The request buffer is sized for `slack` times the mean load; a hop in
+    which some owner would receive more falls back to the request all-to-all (every rank sees the same matrix, so all
+    of them take the same branch)."""
 
-    def __init__(self, plan):
+    def __init__(self, plan, slack=2.0):
         import torch.distributed._symmetric_memory as symm
         comm, dev = plan.comm, plan.device
         group = comm.group if comm.group is not None else dist.group.WORLD
         words = max((plan.B * f * 2 * k for f, k in zip(plan.capF, plan.fanouts)), default=1)
-        self.buf = symm.empty(max(int(words), 1), dtype=torch.int32, device=dev)
-        self.hdl = symm.rendezvous(self.buf, group)
-        ptrs = [int(x) for x in self.hdl.buffer_ptrs]
-        if len(ptrs) != comm.world or int(self.hdl.rank) != comm.rank:
-            raise RuntimeError("symmetric memory rendezvous does not match the communicator")
-        self.ptrs = np.array(ptrs, dtype=np.uint64)
+        self.ans = symm.empty(max(int(words), 1), dtype=torch.int32, device=dev)
+        self.ans_hdl = symm.rendezvous(self.ans, group)
+        self.req_rows = int(slack * plan.B * max(plan.capF)) + 1024
+        self.req = symm.empty(self.req_rows * 2, dtype=torch.int64, device=dev)
+        self.req_hdl = symm.rendezvous(self.req, group)
+        for hdl in (self.ans_hdl, self.req_hdl):
+            if len(hdl.buffer_ptrs) != comm.world or int(hdl.rank) != comm.rank:
+                raise RuntimeError("symmetric memory rendezvous does not match the communicator")
+        self.ans_ptrs = np.array([int(x) for x in self.ans_hdl.buffer_ptrs], dtype=np.uint64)
+        self.req_ptrs = np.array([int(x) for x in self.req_hdl.buffer_ptrs], dtype=np.uint64)
         self.cmat = torch.zeros((comm.world, comm.world), dtype=torch.int64, device=dev)
         self.group = group
+        self.fallback_hops = 0
 
-    def exchange_requests(self, comm, counts, req, alloc):
-        """-> (recv_counts, send_counts, received request rows, row0 of this owner's answers in every requester's buffer)"""
+    def count_matrix(self, comm, counts):
+        """-> (recv_counts, send_counts, row0 of my requests in every owner's buffer, row0 of my answers in every
+        requester's buffer, whether every owner's load fits its request buffer)"""
         dist.all_gather_into_tensor(self.cmat.reshape(-1), counts.contiguous(), group=self.group)
         C = self.cmat.tolist()                       # the hop's one host synchronisation
-        me = comm.rank
+        me, world = comm.rank, comm.world
         sc = C[me]
-        rc = [C[q][me] for q in range(comm.world)]
-        row0 = [sum(C[q][:me]) for q in range(comm.world)]
-        out = alloc(sum(rc))
-        dist.all_to_all_single(out[:sum(rc)], req[:sum(sc)], output_split_sizes=rc, input_split_sizes=sc, group=self.group)
-        return rc, sc, out, row0
+        rc = [C[q][me] for q in range(world)]
+        req_row0 = [sum(C[q][o] for q in range(me)) for o in range(world)]
+        ans_row0 = [sum(C[q][:me]) for q in range(world)]
+        fits = all(sum(C[q][o] for q in range(world)) <= self.req_rows for o in range(world))
+        return rc, sc, req_row0, ans_row0, fits
 
-    def barrier(self):
-        self.hdl.barrier(channel=0)
+    def requests_landed(self):
+        self.req_hdl.barrier(channel=0)
+
+    def answers_landed(self):
+        self.ans_hdl.barrier(channel=0)
 
 
 class PartitionedPlan:
@@ -361,8 +374,8 @@ class PartitionedPlan:
         several owners on one GPU with it); default: tchgeo_serve_requests_rows over `part`.
         edge_bases: every rank's ColumnPartition.edge_base (default: all-gathered through the communicator).
         groups: batch groups pipelined on separate streams (default 1: the overlap did not pay on 2 B200s).
-        peer_answers: store the answers straight into the requesters' buffers over NVLink peer memory instead of an
-        answer all-to-all (_PeerAnswers).  None = when it applies (several CUDA ranks, one group, default owner side;
+        peer_answers: store requests and answers straight into the peers' buffers over NVLink peer memory instead of
+        two all-to-alls (_PeerExchange).  None = when it applies (several CUDA ranks, one group, default owner side;
         TCHGEO_PEER_ANSWERS=0 turns it off) and the symmetric-memory rendezvous succeeds; True = required."""
         self.part = part
         self.serve_rows = serve_rows
@@ -416,7 +429,7 @@ class PartitionedPlan:
             ok = 1
             try:
                 with torch.cuda.device(dev):
-                    self.peer = _PeerAnswers(self)
+                    self.peer = _PeerExchange(self)
             except Exception as e:  # noqa: BLE001  (no symmetric memory on this system: keep the all-to-all)
                 ok, self.peer, err = 0, None, e
             flag = torch.tensor([ok], dtype=torch.int32, device=dev)
@@ -425,7 +438,7 @@ class PartitionedPlan:
                 if peer_answers:
                     raise RuntimeError(f"symmetric-memory rendezvous failed on some rank{'' if ok else ': %r' % (err,)}")
                 if not ok:
-                    warnings.warn(f"peer-memory answers unavailable, using the answer all-to-all: {err!r}")
+                    warnings.warn(f"peer-memory exchange unavailable, using the all-to-alls: {err!r}")
                 self.peer = None
 
     def _mark(self, g, marks, name):
@@ -438,19 +451,41 @@ class PartitionedPlan:
     def _begin(self, g, h, batch_base):
         lens = self.lens
         g.hop = {"fr_begin": lens[0, h - 1, g.b0:g.b1] if h > 0 else None}
+        if self.peer is not None:
+            # count -> all-gather of the count matrix -> scatter straight into the owners' request buffers
+            common = (_ptr(g.samples), self.cap_n, _ptr(g.hop["fr_begin"]), _ptr(lens[0, h, g.b0:g.b1]), g.B, self.capF[h],
+                      self.part.cols_per_rank, self.comm.world)
+            N.check(N.lib.tchgeo_part_count_hop(*common, _ptr(g.counts[0]), _ptr(g.counts[1]), _ptr(self.err),
+                                                _ptr(g.ws), g.ws.numel(), _stream(self.device)))
+            rc, sc, req_row0, ans_row0, fits = self.peer.count_matrix(self.comm, g.counts[0])
+            g.hop.update(rc=rc, sc=sc, row0=ans_row0, F=sum(sc), n_recv=sum(rc), peer_req=fits)
+            row0 = np.array(req_row0, dtype=np.int64)
+            N.check(N.lib.tchgeo_part_scatter_hop(*common, batch_base + g.b0, _ptr(g.counts[0]), _ptr(g.counts[1]),
+                                                  _ptr(g.req), self.peer.req_ptrs.ctypes.data if fits else None,
+                                                  row0.ctypes.data, _ptr(self.err), _ptr(g.ws), g.ws.numel(),
+                                                  _stream(self.device)))
+            return
         N.check(N.lib.tchgeo_part_begin_hop(_ptr(g.samples), self.cap_n, _ptr(g.hop["fr_begin"]), _ptr(lens[0, h, g.b0:g.b1]),
                                             g.B, self.capF[h], self.part.cols_per_rank, self.comm.world, batch_base + g.b0,
                                             _ptr(g.counts[0]), _ptr(g.counts[1]), _ptr(g.req), _ptr(self.err),
                                             _ptr(g.ws), g.ws.numel(), _stream(self.device)))
 
     def _requests(self, g):
-        # host reads the counts: syncs g's stream only
         alloc = lambda n: g.buf("r_req", n, 2, torch.int64, self.device)
         if self.peer is not None:
-            rc, sc, r_req, row0 = self.peer.exchange_requests(self.comm, g.counts[0], g.req, alloc)
-            g.hop.update(row0=row0)
-        else:
-            rc, sc, r_req = self.comm.exchange_rows(g.counts[0], g.req, alloc)
+            hp = g.hop
+            if hp["peer_req"]:
+                self.peer.requests_landed()          # every requester's stores are in every owner's buffer
+                hp["r_req"] = self.peer.req[:max(hp["n_recv"], 1) * 2].view(max(hp["n_recv"], 1), 2)
+            else:                                    # an owner's load exceeds its peer buffer: all-to-all for this hop
+                self.peer.fallback_hops += 1
+                out = alloc(hp["n_recv"])
+                dist.all_to_all_single(out[:hp["n_recv"]], g.req[:hp["F"]], output_split_sizes=hp["rc"],
+                                       input_split_sizes=hp["sc"], group=self.peer.group)
+                hp["r_req"] = out
+            return
+        # host reads the counts: syncs g's stream only
+        rc, sc, r_req = self.comm.exchange_rows(g.counts[0], g.req, alloc)
         g.hop.update(rc=rc, sc=sc, r_req=r_req, F=sum(sc), n_recv=sum(rc))
 
     def _serve(self, g, k, seed):
@@ -463,7 +498,7 @@ class PartitionedPlan:
                 N.check(N.lib.tchgeo_serve_requests_rows_peer(
                     _ptr(part.ptrs), _ptr(part.indices), _ptr(part.weights), part.col_begin, part.col_end - part.col_begin,
                     part.indices.numel(), _ptr(hp["r_req"]), int(hp["n_recv"]), int(k), self.kind, seed, 0, self.comm.world,
-                    self.peer.ptrs.ctypes.data, rc.ctypes.data, row0.ctypes.data, _ptr(self.err), _stream(dev)))
+                    self.peer.ans_ptrs.ctypes.data, rc.ctypes.data, row0.ctypes.data, _ptr(self.err), _stream(dev)))
             return
         hp["ans"] = g.buf("ans", hp["n_recv"], 2 * k, torch.int32, self.device)
         if self.serve_rows is not None:
@@ -474,8 +509,8 @@ class PartitionedPlan:
     def _answers(self, g, k):
         hp = g.hop
         if self.peer is not None:
-            self.peer.barrier()      # every owner's stores have landed in every requester's buffer
-            hp["back"] = self.peer.buf[:max(hp["F"], 1) * 2 * k].view(max(hp["F"], 1), 2 * k)
+            self.peer.answers_landed()   # every owner's stores are in every requester's buffer
+            hp["back"] = self.peer.ans[:max(hp["F"], 1) * 2 * k].view(max(hp["F"], 1), 2 * k)
             return
         hp["back"] = self.comm.return_rows(hp["ans"], hp["n_recv"], hp["F"], hp["sc"], hp["rc"],
                                            lambda n: g.buf("back", n, hp["ans"].shape[1], torch.int32, self.device))
