@@ -266,10 +266,10 @@ TCHGEO_API tchgeo_status tchgeo_part_begin_hop(const int64_t* samples /*DEVICE [
                                                size_t workspace_bytes, tchgeo_stream stream);
 /* tchgeo_part_begin_hop in two halves, for the request exchange fused into the scatter kernel: count_hop fills
  * counts[world]; the ranks all-gather the [world, world] count matrix; scatter_hop then writes every request row into
- * the local `req` (the layout kernel reads it) AND, when peer_req != NULL, straight into the owning rank's request
- * buffer peer_req[o] (HOST array of `world` DEVICE pointers into NVLink peer memory) at row peer_row0[o] + its index
- * inside this rank's group for owner o -- the row the request all-to-all would have delivered it to (peer_row0[o] =
- * number of requests lower-ranked requesters send to owner o).  The caller synchronises the ranks before the owners
+ * the local `req`, grouped by owner (the layout kernel reads it) and, when peer_req != NULL, a second kernel copies group
+ * o, a contiguous run of rows, into the owning rank's request buffer peer_req[o] (HOST array of `world` DEVICE pointers
+ * into NVLink peer memory) from row peer_row0[o] on -- the rows the request all-to-all would have delivered it to
+ * (peer_row0[o] = number of requests lower-ranked requesters send to owner o); whole lines per warp.  The caller synchronises the ranks before the owners
  * serve.  Both asynchronous; same workspace as tchgeo_part_finish_hop. */
 TCHGEO_API tchgeo_status tchgeo_part_count_hop(const int64_t* samples, int64_t samples_stride, const int64_t* fr_begin,
                                                const int64_t* fr_end, int64_t num_batches, int64_t frontier_cap,

@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
   __shared__ int32_t* s_row[SV_THREADS];  // compact answers: where request n's row goes (local buffer or a peer's)
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   uint32_t* s_slot = reinterpret_cast<uint32_t*>(dyn_smem);  // [tile_reqs * fanout]
+  int32_t* s_ans = reinterpret_cast<int32_t*>(s_slot + (size_t)p.tile_reqs * p.fanout);  // [tile_reqs * 2 * fanout]
 
   const int tid = threadIdx.x, lane = tid & 31;
   const uint32_t k = (uint32_t)p.fanout;
@@ -184,12 +185,22 @@ __global__ void __launch_bounds__(SV_THREADS) serve_kernel(const ServeParams p) 
       gp = p.edge_base + lp;
     }
     if (p.out32 || p.peer_world > 0) {
-      int32_t* row = s_row[n];
-      row[s] = (int32_t)id;
-      row[k + s] = gp < 0 ? -1 : (int32_t)(gp - p.edge_base);
+      // compact rows are staged in shared memory and leave in row-major order below: consecutive lanes then write
+      // consecutive words of consecutive rows, i.e. whole lines (what NVLink peer stores need: two interleaved
+      // 4k-byte halves per row fill every packet only half)
+      s_ans[n * 2u * k + s] = (int32_t)id;
+      s_ans[n * 2u * k + k + s] = gp < 0 ? -1 : (int32_t)(gp - p.edge_base);
     } else {
       st_cs_i64(p.out_ids + (r0 + n) * p.out_stride + s, id);
       st_cs_i64(p.out_ptrs + (r0 + n) * p.out_stride + s, gp);
+    }
+  }
+  if (p.out32 || p.peer_world > 0) {
+    __syncthreads();
+    const uint32_t w2 = 2u * k;
+    for (uint32_t i = tid; i < (uint32_t)nn * w2; i += SV_THREADS) {
+      const uint32_t n = i / w2;
+      s_row[n][i - n * w2] = s_ans[i];
     }
   }
 }
@@ -236,7 +247,22 @@ static tchgeo_status serve_launch(const int64_t* ptrs_local, const int64_t* indi
   sp.key0 = (uint32_t)seed; sp.key1 = (uint32_t)(seed >> 32); sp.rel = rel;
   const int64_t grid = (n + sp.tile_reqs - 1) / sp.tile_reqs;
   TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many requests for one launch");
-  const size_t smem = (size_t)sp.tile_reqs * fanout * 4 + 16;
+  const bool compact = out32 != nullptr || peer_world > 0;
+  const size_t smem = (size_t)sp.tile_reqs * fanout * (compact ? 12 : 4) + 16;  // slots (+ staged compact answer rows)
+  {
+    static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
+    int dev = 0;
+    TCHGEO_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(serve_kernel<TCHGEO_SAMPLER_UNIFORM>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(serve_kernel<TCHGEO_SAMPLER_UNIFORM_REPLACE>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(serve_kernel<TCHGEO_SAMPLER_WEIGHTED>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024));
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+  }
   switch (sampler_kind) {
     case TCHGEO_SAMPLER_UNIFORM: serve_kernel<TCHGEO_SAMPLER_UNIFORM><<<(unsigned)grid, SV_THREADS, smem, stream>>>(sp); break;
     case TCHGEO_SAMPLER_UNIFORM_REPLACE: serve_kernel<TCHGEO_SAMPLER_UNIFORM_REPLACE><<<(unsigned)grid, SV_THREADS, smem, stream>>>(sp); break;
@@ -345,8 +371,11 @@ __global__ void __launch_bounds__(PT_THREADS) part_count_kernel(const PartFronti
   if (threadIdx.x < f.world && hist[threadIdx.x]) atomicAdd(counts + threadIdx.x, (unsigned long long)hist[threadIdx.x]);
 }
 
-// peer mode of part_scatter_kernel: the request rows are ALSO stored straight into the owners' request buffers
-// (NVLink peer memory), at the rows the request all-to-all would have delivered them to
+// The request exchange as peer-memory stores: the send buffer is grouped by owner, so group o is one contiguous run of
+// 16-byte rows that goes to rows [row0[o], row0[o] + counts[o]) of owner o's request buffer -- the rows the request
+// all-to-all would have delivered it to.  Consecutive threads move consecutive rows: whole lines per warp (scattering
+// the rows to the peers one by one from part_scatter_kernel filled every NVLink packet with 16 bytes and took 6 ms of
+// an 8-GPU step).
 struct PeerReq {
   int32_t world;                // 0: off
   int64_t* base[PT_MAX_WORLD];  // owner o's request buffer [rows, 2]
@@ -355,10 +384,9 @@ struct PeerReq {
 
 __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFrontier f, const unsigned long long* counts,
                                                                  unsigned long long* cursor, int64_t* req,
-                                                                 int32_t* slot_of, const PeerReq peer) {
+                                                                 int32_t* slot_of) {
   __shared__ unsigned int hist[PT_MAX_WORLD];
   __shared__ unsigned long long base[PT_MAX_WORLD];    // row in the local send buffer
-  __shared__ unsigned long long within[PT_MAX_WORLD];  // the same row counted from the start of the owner's group
   if (threadIdx.x < PT_MAX_WORLD) hist[threadIdx.x] = 0u;
   __syncthreads();
   const int64_t b = blockIdx.y, j = (int64_t)blockIdx.x * PT_THREADS + threadIdx.x;
@@ -371,19 +399,38 @@ __global__ void __launch_bounds__(PT_THREADS) part_scatter_kernel(const PartFron
     unsigned long long off = 0;  // exclusive offset of this owner's group in the send buffer
     for (int r = 0; r < threadIdx.x; ++r) off += counts[r];
     const unsigned int h = hist[threadIdx.x];
-    const unsigned long long w = h ? atomicAdd(cursor + threadIdx.x, (unsigned long long)h) : 0ull;
-    within[threadIdx.x] = w;
-    base[threadIdx.x] = off + w;
+    base[threadIdx.x] = off + (h ? atomicAdd(cursor + threadIdx.x, (unsigned long long)h) : 0ull);
   }
   __syncthreads();
   if (ok) {
     const unsigned long long q = base[o] + rank;
     const uint64_t meta = ((uint64_t)(f.batch_base + (uint32_t)b) << 32) | (uint64_t)(uint32_t)pos;
     const longlong2 row = make_longlong2((long long)id, (long long)meta);
-    *reinterpret_cast<longlong2*>(req + 2 * q) = row;  // the layout kernel reads the local copy (owner of a slot)
-    if (peer.world > 0)
-      *reinterpret_cast<longlong2*>(peer.base[o] + 2 * (peer.row0[o] + (int64_t)(within[o] + rank))) = row;
+    *reinterpret_cast<longlong2*>(req + 2 * q) = row;  // grouped by owner; part_put_kernel ships the groups
     slot_of[b * f.capF + j] = (int32_t)q;  // where this frontier node's answer will be found (frontier order, coalesced)
+  }
+}
+
+__global__ void __launch_bounds__(PT_THREADS) part_put_kernel(const int64_t* __restrict__ req,
+                                                             const unsigned long long* __restrict__ counts,
+                                                             const PeerReq peer) {
+  __shared__ unsigned long long seg[PT_MAX_WORLD + 1];
+  if (threadIdx.x == 0) {
+    unsigned long long at = 0;
+    for (int o = 0; o < peer.world; ++o) {
+      seg[o] = at;
+      at += counts[o];
+    }
+    seg[peer.world] = at;
+  }
+  __syncthreads();
+  const unsigned long long total = seg[peer.world];
+  for (unsigned long long q = (unsigned long long)blockIdx.x * PT_THREADS + threadIdx.x; q < total;
+       q += (unsigned long long)gridDim.x * PT_THREADS) {
+    int o = 0;
+    while (o + 1 < peer.world && q >= seg[o + 1]) ++o;
+    const longlong2 row = *reinterpret_cast<const longlong2*>(req + 2 * q);
+    *reinterpret_cast<longlong2*>(peer.base[o] + 2 * (peer.row0[o] + (int64_t)(q - seg[o]))) = row;
   }
 }
 
@@ -522,8 +569,14 @@ static tchgeo_status part_begin(const int64_t* samples, int64_t samples_stride, 
       }
     }
     part_scatter_kernel<<<grid, PT_THREADS, 0, stream>>>(f, (const unsigned long long*)counts,
-                                                        (unsigned long long*)cursor, req, slot_of, peer);
+                                                        (unsigned long long*)cursor, req, slot_of);
     TCHGEO_CUDA_CHECK(cudaGetLastError());
+    if (peer.world > 0) {
+      const int64_t rows_max = num_batches * frontier_cap;
+      const unsigned pgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>((rows_max + PT_THREADS - 1) / PT_THREADS, 148 * 8));
+      part_put_kernel<<<pgrid, PT_THREADS, 0, stream>>>(req, (const unsigned long long*)counts, peer);
+      TCHGEO_CUDA_CHECK(cudaGetLastError());
+    }
   }
   return TCHGEO_OK;
 }

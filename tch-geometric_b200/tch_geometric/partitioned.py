@@ -375,8 +375,9 @@ class PartitionedPlan:
         edge_bases: every rank's ColumnPartition.edge_base (default: all-gathered through the communicator).
         groups: batch groups pipelined on separate streams (default 1: the overlap did not pay on 2 B200s).
         peer_answers: store requests and answers straight into the peers' buffers over NVLink peer memory instead of
-        two all-to-alls (_PeerExchange).  None = when it applies (several CUDA ranks, one group, default owner side;
-        TCHGEO_PEER_ANSWERS=0 turns it off) and the symmetric-memory rendezvous succeeds; True = required."""
+        two all-to-alls (_PeerExchange).  None = when it applies (2 CUDA ranks -- more with TCHGEO_PEER_ANSWERS=1, never
+        with TCHGEO_PEER_ANSWERS=0 --, one group, default owner side) and the symmetric-memory rendezvous succeeds;
+        True = required."""
         self.part = part
         self.serve_rows = serve_rows
         self.fanouts = [int(k) for k in num_neighbors]
@@ -421,7 +422,10 @@ class PartitionedPlan:
         self.peer = None
         applies = (isinstance(self.comm, DistComm) and self.comm.world > 1 and dev.type == "cuda"
                    and self.serve_rows is None and self.num_groups == 1 and H > 0)
-        want = peer_answers if peer_answers is not None else os.environ.get("TCHGEO_PEER_ANSWERS", "1") != "0"
+        # measured default: on 2 B200s the peer-memory exchange wins (6.56 -> 4.58 ms per step); on 8 the fine-grained
+        # remote stores (16-byte request rows, half-filled answer lines) lose to NCCL's bulk copies (9.1 vs 8.5 ms)
+        env = os.environ.get("TCHGEO_PEER_ANSWERS")
+        want = peer_answers if peer_answers is not None else (env != "0" and (env == "1" or self.comm.world <= 2))
         if peer_answers and not applies:
             raise ValueError("peer_answers needs several CUDA ranks, one batch group and the default owner side")
         if want and applies:
