@@ -310,6 +310,23 @@ class _PlanGroup:
         return t[:need].view(max(int(rows), 1), int(cols))
 
 
+def peer_offsets(C, me):
+    """Where rank `me`'s rows go when the two all-to-all(v)s of a hop are replaced by direct stores.
+    C[q][o] = number of requests rank q sends to owner o (the all-gathered count matrix).  Returns
+      recv_counts[q]  requests `me` receives from q,
+      send_counts[o]  requests `me` sends to o,
+      req_row0[o]     first row of me's group in owner o's request buffer (an all-to-all delivers the groups of the
+                      lower-ranked requesters first),
+      ans_row0[q]     first row of me's answers in requester q's answer buffer (q's requests to lower-ranked owners
+                      come first)."""
+    world = len(C)
+    sc = list(C[me])
+    rc = [C[q][me] for q in range(world)]
+    req_row0 = [sum(C[q][o] for q in range(me)) for o in range(world)]
+    ans_row0 = [sum(C[q][:me]) for q in range(world)]
+    return rc, sc, req_row0, ans_row0
+
+
 class _PeerExchange:
     """Both exchanges of a hop fused into the kernels on either side of them (NVLink peer memory instead of all-to-alls).
 
@@ -349,12 +366,8 @@ class _PeerExchange:
         requester's buffer, whether every owner's load fits its request buffer)"""
         dist.all_gather_into_tensor(self.cmat.reshape(-1), counts.contiguous(), group=self.group)
         C = self.cmat.tolist()                       # the hop's one host synchronisation
-        me, world = comm.rank, comm.world
-        sc = C[me]
-        rc = [C[q][me] for q in range(world)]
-        req_row0 = [sum(C[q][o] for q in range(me)) for o in range(world)]
-        ans_row0 = [sum(C[q][:me]) for q in range(world)]
-        fits = all(sum(C[q][o] for q in range(world)) <= self.req_rows for o in range(world))
+        rc, sc, req_row0, ans_row0 = peer_offsets(C, comm.rank)
+        fits = all(sum(C[q][o] for q in range(comm.world)) <= self.req_rows for o in range(comm.world))
         return rc, sc, req_row0, ans_row0, fits
 
     def requests_landed(self):

@@ -129,3 +129,89 @@ def test_partitioned_plan_errors_and_edge_cases(thg, fakedataset):
     # no hops
     got = PartitionedPlan(part, 2, 3, [], comm=SingleComm()).sample(dev([[0, 1, 2], [3, 4, 5]]), seed=1)
     assert got.samples_len.tolist() == [3, 3] and got.batch(0)[4] == []
+
+
+@pytest.mark.parametrize("fanout,kind", [(5, 0), (15, 0), (3, 1), (70, 0)])
+def test_peer_serve_kernel_places_rows_like_the_answer_all_to_all(thg, fakedataset, fanout, kind):
+    """tchgeo_serve_requests_rows_peer with the 'peers' being three local buffers: the answers to requester q's segment
+    must land in buffer q from row peer_row0[q] on, and equal what tchgeo_serve_requests_rows writes locally."""
+    from tch_geometric import _native as N
+    from tch_geometric.partitioned import ColumnPartition, serve_rows
+    from tch_geometric.ops import _ptr, _stream
+    ei, n = fakedataset
+    ptrs, idx, _ = thg.to_csc(dev(ei), n)
+    part = ColumnPartition.from_full(ptrs, idx, 1, 3)
+    rng = np.random.default_rng(fanout)
+    rc = np.array([300, 0, 411], dtype=np.int64)            # requests received from requesters 0, 1, 2
+    row0 = np.array([17, 5, 1000], dtype=np.int64)          # where this owner's answers start in each requester's buffer
+    m = int(rc.sum())
+    req = torch.stack([dev(rng.integers(part.col_begin, part.col_end, m)),
+                       dev((rng.integers(0, 50, m) << 32) | rng.integers(0, 100000, m))], dim=1).contiguous()
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    want = torch.full((m, 2 * fanout), -7, dtype=torch.int32, device="cuda")
+    serve_rows(part, req, m, fanout, kind, 4242, want, err)
+    bufs = [torch.full((2000, 2 * fanout), -7, dtype=torch.int32, device="cuda") for _ in range(3)]
+    peer = np.array([b.data_ptr() for b in bufs], dtype=np.uint64)
+    N.check(N.lib.tchgeo_serve_requests_rows_peer(_ptr(part.ptrs), _ptr(part.indices), None, part.col_begin,
+                                                  part.col_end - part.col_begin, part.indices.numel(), _ptr(req), m, fanout,
+                                                  kind, 4242, 0, 3, peer.ctypes.data, rc.ctypes.data, row0.ctypes.data,
+                                                  _ptr(err), _stream(req.device)))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    seg = 0
+    for q in range(3):
+        c, r = int(rc[q]), int(row0[q])
+        assert torch.equal(bufs[q][r:r + c], want[seg:seg + c])
+        untouched = torch.ones(2000, dtype=torch.bool, device="cuda")
+        untouched[r:r + c] = False
+        assert (bufs[q][untouched] == -7).all()
+        seg += c
+
+
+def test_peer_request_scatter_places_groups_like_the_request_all_to_all(thg, fakedataset):
+    """count_hop + scatter_hop with three local 'owner' buffers: the counts equal begin_hop's, and owner o's buffer
+    holds, from row peer_row0[o] on, exactly this rank's group for owner o of the local send buffer."""
+    from tch_geometric import _native as N
+    from tch_geometric.ops import _ptr, _stream
+    ei, n = fakedataset
+    B, F, world = 5, 700, 3
+    cpr = (n + world - 1) // world
+    rng = np.random.default_rng(8)
+    samples = dev(rng.integers(0, n, (B, F + 10)))
+    fr_end = dev(rng.integers(F - 50, F + 1, B))
+    i64 = dict(dtype=torch.int64, device="cuda")
+    counts, cursor = torch.zeros(world, **i64), torch.zeros(world, **i64)
+    counts2, cursor2 = torch.zeros(world, **i64), torch.zeros(world, **i64)
+    req, req2 = torch.zeros((B * F, 2), **i64), torch.zeros((B * F, 2), **i64)
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ws = torch.empty(int(N.lib.tchgeo_part_hop_workspace_bytes(B, F)), dtype=torch.uint8, device="cuda")
+    ws2 = torch.empty_like(ws)
+    st = _stream(samples.device)
+    common = (_ptr(samples), F + 10, None, _ptr(fr_end), B, F, cpr, world)
+    N.check(N.lib.tchgeo_part_begin_hop(*common, 3, _ptr(counts2), _ptr(cursor2), _ptr(req2), _ptr(err), _ptr(ws2),
+                                        ws2.numel(), st))
+    N.check(N.lib.tchgeo_part_count_hop(*common, _ptr(counts), _ptr(cursor), _ptr(err), _ptr(ws), ws.numel(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(counts, counts2)
+    c = counts.tolist()
+    assert sum(c) == int(fr_end.sum())
+    row0 = np.array([11, 0, 333], dtype=np.int64)
+    bufs = [torch.full((B * F + 400, 2), -7, **i64) for _ in range(world)]
+    peer = np.array([b.data_ptr() for b in bufs], dtype=np.uint64)
+    N.check(N.lib.tchgeo_part_scatter_hop(*common, 3, _ptr(counts), _ptr(cursor), _ptr(req), peer.ctypes.data,
+                                          row0.ctypes.data, _ptr(err), _ptr(ws), ws.numel(), st))
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0
+    off = 0
+    for o in range(world):
+        r = int(row0[o])
+        assert torch.equal(bufs[o][r:r + c[o]], req[off:off + c[o]])
+        assert (bufs[o][:r] == -7).all() and (bufs[o][r + c[o]:] == -7).all()
+        # same multiset of requests as the one-call entry point (the order inside a group is arbitrary)
+        a = req[off:off + c[o]]
+        b = req2[off:off + c[o]]
+        ka, kb = a[:, 1].sort().values, b[:, 1].sort().values     # (batch << 32 | pos) is unique per request
+        assert torch.equal(ka, kb)
+        owner = torch.clamp(a[:, 0] // cpr, max=world - 1)
+        assert (owner == o).all()
+        off += c[o]

@@ -385,3 +385,47 @@ def test_many_tiles_single_batch(thg, fakedataset):
         got, seed = run_homo(thg, ptrs, idx, inputs, [16, 8, 4], sampler, state=33)
         want = O.neighbor_sampling_homogenous(hp, hi, inputs, [16, 8, 4], sampler=oracle_sampler(sampler), seed=seed)
         assert_same(got, want)
+
+
+def test_sample_async_on_two_streams_equals_sample(thg, fakedataset):
+    """HomogenousSampler.sample_async()/result(): two plans on two streams, step s+1 enqueued before step s is
+    collected, give the same bits as the synchronous call; device-side errors surface in result()."""
+    ei, n = fakedataset
+    ptrs, idx, _ = graph(thg, ei, n)
+    B, S, fan = 9, 21, [15, 10, 5]
+    rng = np.random.default_rng(77)
+    steps = [dev(rng.integers(0, n, (B, S))) for _ in range(5)]
+    ref_plan = thg.HomogenousSampler(ptrs, idx, B, S, fan)
+    want = []
+    for s, inp in enumerate(steps):
+        r = ref_plan.sample(inp, seed=500 + s, batch_base=s * B)
+        want.append([[t.clone() for t in r.batch(b)[:4]] + [r.batch(b)[4]] for b in range(B)])
+    plans = [thg.HomogenousSampler(ptrs, idx, B, S, fan) for _ in range(2)]
+    streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+    torch.cuda.synchronize()
+    pending, got = [], {}
+
+    def take():
+        s, j = pending.pop(0)
+        r = plans[j].result()
+        got[s] = [[t.clone() for t in r.batch(b)[:4]] + [r.batch(b)[4]] for b in range(B)]
+
+    for s, inp in enumerate(steps):
+        j = s & 1
+        if len(pending) == 2:
+            take()
+        with torch.cuda.stream(streams[j]):
+            plans[j].sample_async(inp, seed=500 + s, batch_base=s * B)
+        pending.append((s, j))
+    while pending:
+        take()
+    torch.cuda.synchronize()
+    for s in range(len(steps)):
+        for b in range(B):
+            for x, y in zip(got[s][b][:4], want[s][b][:4]):
+                assert torch.equal(x, y)
+            assert got[s][b][4] == want[s][b][4]
+    bad = steps[0].clone()
+    bad[2, 3] = n + 9
+    with pytest.raises(thg.ReferencePanic):
+        plans[0].sample_async(bad, seed=1).result()

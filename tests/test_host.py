@@ -131,3 +131,25 @@ def test_shard_range_partitions_exactly():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(5, 2, 2)
+
+
+def test_peer_offsets_reproduce_the_all_to_all_layout():
+    """The peer-memory exchange of the partitioned path stores every row where the all-to-all(v) would have delivered
+    it; check the offsets against an explicit simulation of both all-to-alls."""
+    from tch_geometric.partitioned import peer_offsets
+    rng = np.random.default_rng(5)
+    for world in (1, 2, 5, 8):
+        C = rng.integers(0, 7, (world, world)).tolist()
+        # requests: rank q's send buffer is grouped by owner; owner o receives the groups in requester order
+        recv = [[(q, o, i) for q in range(world) for i in range(C[q][o])] for o in range(world)]
+        # answers: owner o's answers (in received order) go back; requester q receives them in owner order
+        back = [[(q, o, i) for o in range(world) for i in range(C[q][o])] for q in range(world)]
+        for me in range(world):
+            rc, sc, req_row0, ans_row0 = peer_offsets(C, me)
+            assert sc == C[me] and rc == [C[q][me] for q in range(world)]
+            for o in range(world):      # me as requester: my group for owner o
+                for i in range(C[me][o]):
+                    assert recv[o][req_row0[o] + i] == (me, o, i)
+            for q in range(world):      # me as owner: my answers to requester q
+                for i in range(C[q][me]):
+                    assert back[q][ans_row0[q] + i] == (q, me, i)
