@@ -7,24 +7,26 @@
 // frontier node in samples[dst], edge_index[e] = CSC position (neighbor_sampling.rs:210-218).
 //
 // One kernel launch per (hop, relation) processes that hop's frontier of *all* batches:
-//   tile = up to 256 frontier nodes of one batch, handled by one 256-thread CTA
-//   A. coalesced load of frontier ids, gather of the (ptrs[w], ptrs[w+1]) pair, per-node count
-//      cnt = min(deg, k) (or k*[deg>0] with replacement), block scan
+//   tile = up to 128 frontier nodes of one batch; a 128-thread CTA works through two tiles
+//   A. coalesced load of frontier ids, gather of the (ptrs[w], ptrs[w+1]) pair (both tiles up front), per-node
+//      count cnt = min(deg, k) (or k*[deg>0] with replacement), prefix sums by warp scans
 //   B. the tile's exclusive output offset inside its batch comes from a decoupled look-back over the
 //      batch's earlier tiles (single pass, no separate count/scan kernels, no host sync)
-//   C. sampling decisions in shared memory
+//   C. sampling decisions in shared memory, one word per output slot that ends up holding the position of the
+//      chosen neighbour inside the neighbourhood
 //        UNIFORM : the serial reservoir of sampling.rs:6-26 is replayed exactly in parallel:
 //                  slot s ends up holding the item of the LAST step i>=k whose draw j_i == s, else
-//                  item s.  Steps are independent given i, so the tile's (node, 4-step block) pairs
-//                  are flattened over all 256 threads; each draws Philox(seed; pos, block, batch)
-//                  and does atomicMax(slot, step) in shared memory for the hits.
-//        REPLACE : k iid draws per non-empty neighbourhood (sampling.rs:57-69).
-//        WEIGHTED: warp per node; inclusive warp scan of the f64 weights gives w_sum at every step;
-//                  step i fires iff u*w_sum_i < w_i and then overwrites a uniform slot
-//                  (sampling.rs:28-55); last firing writer per slot wins via atomicMax.
-//   D. thread-per-output-edge epilogue: one random 8-byte gather from row_indices and four fully
+//                  item s.  Steps are independent given i, so the tile's (node, 8-step chunk) pairs
+//                  are flattened over the CTA; a chunk is Philox blocks (seed; pos, 2c | 2c+1, batch) and
+//                  red.shared.max(slot, step) for the hits (the slot starts as s, and steps >= k > s).
+//        REPLACE : k iid draws per non-empty neighbourhood (sampling.rs:57-69), one Philox block per four.
+//        WEIGHTED: step i fires iff u*w_sum_i < w_i and then overwrites a uniform slot (sampling.rs:28-55);
+//                  last firing writer per slot wins via atomicMax.  w_sum_i comes from serial per-column
+//                  prefix sums (eight lanes per 8-step chunk), or, without them, from a warp scan per node.
+//   D. thread-per-output-edge epilogue: one random 4/8-byte gather from row_indices and four fully
 //      coalesced 8-byte streaming stores (samples, rows, cols, edge_index).
-// HBM-bound integer work: no tensor cores.  See DESIGN.md for the byte model and RNG contract.
+// HBM-bound integer work: no tensor cores.  See DESIGN.md for the byte model, the RNG contract and what was
+// measured and rejected (warp tiles, four tiles per CTA, deferred stores).
 #include <cub/block/block_scan.cuh>
 
 #include <algorithm>

@@ -1,3 +1,5 @@
+# A/B of hop-kernel variants inside ONE gpurun call (boxes differ by +-2 %, so variants are only comparable within a call).
+# The TPC / DEFER switches it names were experiments of session 3 and no longer exist; TCHGEO_HOP_MIN_BLOCKS does.
 set -x
 O=gpurun_out/r2f; mkdir -p $O
 timeout 600 python -m pytest tests/test_gpu_sampling.py tests/test_gpu_partitioned.py tests/test_gpu_fullsize.py -m gpu -x -q > $O/tests.log 2>&1; rc=$?; echo "rc=$rc" >> $O/tests.log; tail -5 $O/tests.log

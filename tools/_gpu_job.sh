@@ -1,3 +1,4 @@
+# gpurun (1 GPU): the measurement job whose outputs are copied into profiles/ (tests, smoke, bench lines, ncu launch list + full capture)
 set -x
 mkdir -p gpurun_out/final4
 O=gpurun_out/final4

@@ -1,3 +1,4 @@
+# gpurun --gpus 2: single-GPU partitioned tests, bit-exact check of both exchange protocols, 2-GPU bench of the peer-memory exchange
 set -x
 O=gpurun_out/r2j; mkdir -p $O
 export NCCL_DEBUG=WARN
