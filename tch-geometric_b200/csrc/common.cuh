@@ -35,7 +35,6 @@ enum : uint32_t {
   DEV_ERR_INDEX = 2u,
   DEV_ERR_PANIC = 4u,
   DEV_ERR_WATCHDOG = 8u,
-  DEV_ERR_DEGREE = 16u,  // a neighbourhood of 2^27 or more entries met the warp-tile hop kernel
 };
 
 inline tchgeo_status status_from_dev_err(uint32_t e) {
@@ -47,10 +46,6 @@ inline tchgeo_status status_from_dev_err(uint32_t e) {
   if (e & DEV_ERR_INDEX) {
     set_last_error("node id out of range (the reference panics on this input)");
     return TCHGEO_ERR_INDEX;
-  }
-  if (e & DEV_ERR_DEGREE) {
-    set_last_error("a column with 2^27 or more entries is not supported by the warp-tile hop kernel; set TCHGEO_HOP_KERNEL=cta");
-    return TCHGEO_ERR_BAD_ARG;
   }
   if (e & DEV_ERR_PANIC) {
     set_last_error("input on which the reference panics (fanout 0 with non-empty neighbourhood, or non-positive weight sum)");
