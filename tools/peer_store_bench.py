@@ -57,9 +57,12 @@ def main():
     share = nbytes // len(peers)
     res = {}
 
+    def slot(p):  # which share of peer p's buffer this rank writes (writers of p are all ranks but p)
+        return (rank if rank < p else rank - 1) if args.all else 0
+
     # contiguous
     src = torch.arange(share // 8, dtype=torch.int64, device=device)
-    views = [hdl.get_buffer(p, (share // 8,), torch.int64, rank * (share // 8) if args.all else 0) for p in peers]
+    views = [hdl.get_buffer(p, (share // 8,), torch.int64, slot(p) * (share // 8)) for p in peers]
 
     def contiguous():
         for v in views:
@@ -70,7 +73,7 @@ def main():
     rows = share // 16
     src16 = torch.arange(rows * 2, dtype=torch.int64, device=device).view(rows, 2)
     perm = torch.randperm(rows, device=device)
-    views16 = [hdl.get_buffer(p, (rows, 2), torch.int64, rank * rows * 2 if args.all else 0) for p in peers]
+    views16 = [hdl.get_buffer(p, (rows, 2), torch.int64, slot(p) * rows * 2) for p in peers]
 
     def rows16():
         for v in views16:
@@ -80,7 +83,7 @@ def main():
     # 40-byte rows written as two 20-byte halves
     rows40 = share // 40
     a = torch.ones((rows40, 5), dtype=torch.int32, device=device)
-    views40 = [hdl.get_buffer(p, (rows40, 10), torch.int32, rank * rows40 * 10 if args.all else 0) for p in peers]
+    views40 = [hdl.get_buffer(p, (rows40, 10), torch.int32, slot(p) * rows40 * 10) for p in peers]
 
     def rows40_half():
         for v in views40:
