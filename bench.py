@@ -18,6 +18,10 @@ Prints ONE JSON line:
              duration, against MEASURED_PEAKS.json hbm_gbs.
   cpu_baseline  the CPU oracle (C restatement of the reference algorithm) on this box's host cores,
              on a bounded sample of the same workload.
+  with_relabel  the same step with the dedup + insertion-order relabel stage (K7) enqueued after the hops.
+  walk_steps_per_sec / hetero_edges_per_sec (+ "walk", "hetero" objects with their own roofline): BASELINE.json
+             configs[2] (node2vec walk, walkers sharded over the ranks) and configs[3] (mag-shaped heterogeneous
+             sampling, seed batches sharded), measured in the same run (--headline-only skips them).
 
 --impl reference times the reference's CPU algorithm (the oracle port: the reference is Rust and
 cannot be built in this image) with all host threads on bounded samples of the same workload.
@@ -146,6 +150,20 @@ def dist_env():
     return rank, world, local
 
 
+def setup_device():
+    """-> (rank, world, local, device); one NCCL process group per run when launched by torchrun"""
+    import torch.distributed as dist
+    rank, world, local = dist_env()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1 and not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+    return rank, world, local, device
+
+
 def build_graph(device, scale):
     t0 = time.time()
     ei, n = synth.products_like(device, scale=scale)
@@ -185,7 +203,7 @@ def run_reference_arm(args):
     log(f"[bench] reference arm: CSC built on the CPU in {time.time() - t0:.1f}s; {cores} host threads")
     del ei
     osampler = oracle_sampler(args.sampler, idx.size, device)
-    per_step = max(cores * 8, 32) if args.ref_batches <= 0 else args.ref_batches
+    per_step = args.batches if args.ref_batches <= 0 else args.ref_batches  # same batches per step as our arm
     for w in range(args.warmup):
         cpu_sampling_rate(ptrs, idx, n, per_step, cores, first_batch=w * per_step, sampler=osampler)
     tot_e, tot_t = 0, 0.0
@@ -235,14 +253,7 @@ def run_ours(args):
     import tch_geometric as thg
     import torch.distributed as dist
 
-    rank, world, local = dist_env()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback); use --impl reference for the CPU arm")
-    device = torch.device("cuda", local)
-    torch.cuda.set_device(device)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    rank, world, local, device = setup_device()
     B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
     l2_fetch = None
     if args.l2_fetch:
@@ -367,7 +378,7 @@ def run_ours(args):
 
     # kernels of ours per step: fill_i64_kernel + per hop (frontier_max_kernel +) the hop kernel
     hop_kernel_name = "hop_kernel"
-    launches_per_step = 1 + len(FANOUTS)  # fill_i64_kernel + one hop kernel per hop
+    launches_per_step = plan.num_launches  # fill_i64_kernel + one hop kernel per hop (counted by the library)
     peak, peak_src = measured_peak_gbs()
     dom = int(np.argmax(hop_ms))
     # per launch, summed over the K timed launches; the weighted sampler adds 8 B per scanned weight
@@ -393,7 +404,12 @@ def run_ours(args):
     # ---- end-to-end with host buffers (e2e) ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(thg, plan, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier)
+        e2e = run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier)
+
+    # ---- the same step with the dedup + insertion-order relabel stage (K7) ------------------------
+    with_relabel = None
+    if not args.headline_only:
+        with_relabel = run_relabel(thg, ptrs, idx, dev_seeds, sampler, B, S, K, W, world, rank, device, barrier)
 
     clk = clocks.stop()
 
@@ -402,74 +418,164 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu = run_cpu_baseline(ptrs, idx, n, args, oracle_sampler(args.sampler, E, device))
 
+    # ---- BASELINE.json's other single-box configurations, in the same line -----------------------
+    walk = hetero = None
+    if not args.headline_only:
+        res = None
+        del plans, plan, dev_seeds, ptrs, idx
+        thg.clear_caches()
+        torch.cuda.empty_cache()
+        walk = measure_walk(args, rank, world, local, device, K=min(K, 5), W=3, with_cpu=False)
+        thg.clear_caches()
+        torch.cuda.empty_cache()
+        hetero = measure_hetero(args, rank, world, local, device, K=K, W=3, with_cpu=False)
+
     if world > 1:
         dist.barrier()
     if rank == 0:
+        extra_launches = sum(x["gpu_launches"] for x in (walk, hetero, with_relabel) if x)
         out = {
             "metric": metric_name(args.sampler), "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int64", "data": "synthetic", "config": workload_config(n, E, B, args.scale, args.sampler),
             "seeds_per_sec": seeds_per_s, "edges_per_step_per_gpu": edges / K,
             "roofline": roofline, "serial": serial, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": K * launches_per_step,
+            "gpu_launches": K * launches_per_step, "gpu_launches_other_measurements": extra_launches,
+            "with_relabel": with_relabel,
+            "walk_steps_per_sec": walk["value"] if walk else None, "walk": walk,
+            "hetero_edges_per_sec": hetero["value"] if hetero else None, "hetero": hetero,
             "clocks": clk, "l2_fetch_granularity": l2_fetch, "to_csc_ms": to_csc_ms, "to_csc_first_call_ms": to_csc_first_ms,
         }
         emit(out)
-    if world > 1:
-        dist.destroy_process_group()
 
 
-def run_e2e(thg, plan, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier):
-    """Public plan API with HOST buffers: pinned seeds -> H2D -> sample -> D2H of the four outputs."""
+def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier):
+    """Public plan API with HOST buffers.  Per step: pinned seeds -> H2D -> sample (HomogenousSampler.sample_async) ->
+    SampledBatches.to_host: the used prefixes of samples / cols / edge_index are packed on the device and copied to
+    pinned host buffers, one D2H per tensor and group of batches (`rows` is arange(S, S + E) for every batch and is
+    served from a cached host arange instead of travelling).  Two plans on two streams: step s+1 is sampled while
+    step s drains over PCIe."""
     from tch_geometric.sharding import reduce_job
-    HB = min(B, 64)  # pinned landing zone for 64 batches (1.9 GB), reused round-robin: 8 ranks stay under 16 GB
+    HB = min(B, 64)  # pinned landing zone per plan for 64 batches, reused group by group
     try:
-        h_samples = torch.empty((HB, cap_n), dtype=torch.int64).pin_memory()
-        h_edges = [torch.empty((HB, cap_e), dtype=torch.int64).pin_memory() for _ in range(3)]
+        hosts = [thg.HostBatches(HB, cap_n, cap_e, S, device, fill=0.8) for _ in plans]
     except RuntimeError as e:
         log(f"[bench] could not pin host output buffers: {e}")
         return None
+    thg.ops.host_arange(S + cap_e)
 
-    h_flat_s = h_samples.reshape(-1)
-    h_flat_e = [h.reshape(-1) for h in h_edges]
+    def drain(j):
+        """lengths of plan j's pending step, then its packed D2H copies on plan j's stream"""
+        res = plans[j].result()
+        d2h = res.layer_offsets.nbytes + res.samples_len.nbytes + res.edges_len.nbytes  # already on the host
+        with torch.cuda.stream(streams[j]):
+            for g0 in range(0, B, HB):
+                d2h += res.to_host(hosts[j], g0, min(HB, B - g0))
+        return int(res.edges_len.sum()), d2h
 
-    def step(s):
-        res = plan.sample(host_seeds[s], seed=2000 + s, batch_base=(s * world + rank) * B)  # H2D inside
-        ns, ne = res.samples_len, res.edges_len
-        d2h = 0
-        # batches are packed on the device group by group (one cat per tensor), then each packed tensor goes to the
-        # pinned landing zone with a single copy: 4 D2H copies per group instead of 4 per batch
-        for g0 in range(0, B, HB):
-            bs = range(g0, min(g0 + HB, B))
-            n_tot = int(sum(int(ns[b]) for b in bs))
-            e_tot = int(sum(int(ne[b]) for b in bs))
-            h_flat_s[:n_tot].copy_(torch.cat([res.samples[b, :int(ns[b])] for b in bs]), non_blocking=True)
-            for h, src in zip(h_flat_e, (res.rows, res.cols, res.edge_index)):
-                h[:e_tot].copy_(torch.cat([src[b, :int(ne[b])] for b in bs]), non_blocking=True)
-            d2h += 8 * (n_tot + 3 * e_tot)
-        d2h += res.layer_offsets.nbytes + ns.nbytes + ne.nbytes  # already on the host (read back by the call)
-        return int(ne.sum()), d2h
+    def job(first, count):
+        edges, d2h, pending = 0, 0, []
+        for i, s in enumerate(range(first, first + count)):
+            j = i & 1
+            if len(pending) == 2:
+                e, d = drain(pending.pop(0))
+                edges, d2h = edges + e, d2h + d
+            with torch.cuda.stream(streams[j]):
+                plans[j].sample_async(host_seeds[s], seed=2000 + s, batch_base=(s * world + rank) * B)  # H2D inside
+            pending.append(j)
+        while pending:
+            e, d = drain(pending.pop(0))
+            edges, d2h = edges + e, d2h + d
+        return edges, d2h
 
-    for s in range(min(W, 2)):
-        step(s)
+    job(0, max(min(W, 3), 2))
     barrier()
+    cur = torch.cuda.current_stream(device)
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t0 = time.perf_counter()
-    start.record()
-    edges, d2h = 0, 0
-    for s in range(W, W + K):
-        e, d = step(s)
-        edges += e
-        d2h += d
-    stop.record()
+    start.record(cur)
+    for st in streams:
+        st.wait_stream(cur)
+    edges, d2h = job(W, K)
+    for st in streams:
+        cur.wait_stream(st)
+    stop.record(cur)
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms = max(start.elapsed_time(stop), wall_ms)
+    # spot check of the landing zone: the last group of the last drained plan equals the device result
+    last = plans[(K - 1) & 1]._call
+    got = hosts[(K - 1) & 1].batch(0)
+    b = (B - 1) // HB * HB
+    ok = bool(torch.equal(got[0], last.samples[0][b, :int(last.samples_len[b, 0])].cpu()))
     ms, edges_all = reduce_job(ms, float(edges), device)
     return {"value": edges_all / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
-            "d2h_bytes_per_step": d2h // K, "ms_per_step": ms / K,
-            "path": "HomogenousSampler.sample(pinned host seeds) + D2H of the packed samples/rows/cols/edge_index "
-                    "prefixes and layer offsets into pinned host buffers"}
+            "d2h_bytes_per_step": d2h // K, "ms_per_step": ms / K, "landing_zone_verified": ok,
+            "d2h_GBps_per_gpu": d2h / K / (ms / K * 1e-3) / 1e9,
+            "path": "HomogenousSampler.sample_async(pinned host seeds) on two plans / two streams + "
+                    "SampledBatches.to_host: device-side ragged pack, then one D2H per tensor (samples, cols, edge_index) "
+                    "and group of 64 batches into pinned host buffers; rows = arange(S, S+E) is served from a cached host "
+                    "arange (neighbor_sampling.rs:210-218) and layer offsets / lengths come back with the length table"}
+
+
+def run_relabel(thg, ptrs, idx, dev_seeds, sampler, B, S, K, W, world, rank, device, barrier):
+    """The headline step with the K7 stage (frontier dedup + insertion-order relabel of every batch's tree) enqueued
+    after the hops.  Per-interval CUDA events (hop launches, then the whole relabel stage) on the launching stream."""
+    from tch_geometric.sharding import reduce_job
+    plan = thg.HomogenousSampler(ptrs, idx, B, S, FANOUTS, sampler=sampler, relabel=True)
+    for s in range(W):
+        plan.sample(dev_seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
+    barrier()
+    ms = np.zeros(len(FANOUTS) + 1)
+    n_samples = n_nodes = edges = 0
+    for s in range(W, W + K):
+        res = plan.sample(dev_seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B, timed=True)
+        ms += res.launch_ms
+        n_samples += int(res.samples_len.sum())
+        n_nodes += int(res.nodes_len.sum())
+        edges += int(res.edges_len.sum())
+    step_ms = float(ms.sum())
+    step_ms, edges_all = reduce_job(step_ms, float(edges), device)
+    peak, peak_src = measured_peak_gbs()
+    # algorithmic bytes of the stage: every id is read once (8 B) and gets a local id (8 B); every distinct node is
+    # written once (8 B).  Hash-table traffic stays in the L2 by construction (waves) and is not counted.
+    alg = 16.0 * n_samples + 8.0 * n_nodes
+    rl_ms = float(ms[-1])
+    out = {"value": edges_all / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms / K,
+           "hops_ms_per_step": float(ms[:-1].sum()) / K, "relabel_ms_per_step": rl_ms / K,
+           "ids_per_step": n_samples / K, "distinct_nodes_per_step": n_nodes / K,
+           "what": "sum of the per-launch CUDA-event intervals of one plan (hop kernels + relabel stage)",
+           "roofline": {"bound": "hbm", "kernel": "relabel stage: rl_insert_kernel + rl_compact_kernel + rl_lookup_kernel, "
+                        "all waves of the step", "achieved": alg / (rl_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                        "frac": alg / (rl_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_step": alg / K,
+                        "byte_model": "16 B per id (8 read + 8 local written) + 8 B per distinct node"},
+           "gpu_launches": K * plan.num_launches}
+    del plan
+    return out
+
+
+def run_relabel_only(args):
+    """--workload relabel: only the with_relabel measurement of the headline configuration (tuning runs)."""
+    import tch_geometric as thg
+    rank, world, local, device = setup_device()
+    B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
+    ei, n = build_graph(device, args.scale)
+    ptrs, idx, _ = thg.to_csc(ei, n)
+    del ei
+    dev_seeds = torch.stack([torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B)) for s in range(W + K)]).to(device)
+
+    def barrier():
+        torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    out = run_relabel(thg, ptrs, idx, dev_seeds, None, B, S, K, W, world, rank, device, barrier)
+    out["clocks"] = clocks.stop()
+    out["wave_mb"] = os.environ.get("TCHGEO_RELABEL_WAVE_MB", "64 (default)")
+    if rank == 0:
+        emit({"metric": METRIC + "_with_relabel", "n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+              "config": workload_config(n, int(idx.numel()), B, args.scale), **out})
 
 
 def run_cpu_baseline(ptrs, idx, n, args, osampler=None):
@@ -489,16 +595,17 @@ def run_cpu_baseline(ptrs, idx, n, args, osampler=None):
 # secondary workloads (BASELINE.json configs[2] and configs[3]); same JSON shape, own metric names
 # ---------------------------------------------------------------------------------------------
 def run_walk(args):
-    """configs[2]: node2vec random_walk, walk_length 80, p=1, q=0.5, 10 walks per node, walkers sharded."""
+    rank, world, local, device = setup_device()
+    out = measure_walk(args, rank, world, local, device, args.steps, args.warmup, with_cpu=not args.no_cpu)
+    if rank == 0:
+        emit(out)
+
+
+def measure_walk(args, rank, world, local, device, K, W, with_cpu):
+    """configs[2]: node2vec random_walk, walk_length 80, p=1, q=0.5, 10 walks per node, walkers sharded (strong scaling)."""
     import tch_geometric as thg
     import torch.distributed as dist
     from tch_geometric.sharding import reduce_job, shard_range
-    rank, world, local = dist_env()
-    device = torch.device("cuda", local)
-    torch.cuda.set_device(device)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
     ei, n = build_graph(device, args.scale)
     rp, ci, _ = thg.to_csr(ei, n)
     del ei
@@ -507,7 +614,6 @@ def run_walk(args):
     total_walkers = n * 10 if not args.walkers else int(args.walkers)  # --walkers: profiling runs only
     w0, w1 = shard_range(total_walkers, rank, world)          # strong scaling: the job is fixed
     start = (torch.arange(w0, w1, device=device, dtype=torch.int64) // 10)  # arange(N).repeat_interleave(10)
-    K, W = args.steps, args.warmup
     for s in range(W):
         thg.random_walk(rp, ci, start, L, P, Q, seed=s, walker_base=w0)
     if world > 1:
@@ -536,7 +642,7 @@ def run_walk(args):
     alg = (att_all * bytes_per_attempt + steps_all * 8) / world  # per-GPU bytes over the timed region
     achieved = alg / (ms * 1e-3) / 1e9
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and with_cpu:
         from oracle import oracle as O
         cores = os.cpu_count() or 1
         sub = 1_000_000 if args.scale == 1.0 else min(100_000, total_walkers)
@@ -547,8 +653,8 @@ def run_walk(args):
         dt = time.perf_counter() - t0
         cpu = {"value": float((wk[:, 1:] >= 0).sum()) / dt, "unit": "steps/s", "cores": cores, "kind": "port",
                "sample": f"{sub} walkers x {L} steps on {cores} threads ({dt:.1f} s)"}
-    if rank == 0:
-        emit({"metric": "node2vec_walk_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K,
+    del walks
+    return ({"metric": "node2vec_walk_steps_per_sec", "value": value, "unit": "steps/s", "n_gpus": world, "steps": K,
               "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
               "dtype": "int64", "data": "synthetic",
               "config": {"workload": f"products-shaped synthetic graph (N={n}, E={ci.numel()}), random_walk "
@@ -564,8 +670,6 @@ def run_walk(args):
                                    "pair + binary search per attempt); the kernel skips the searches the uniform already decides "
                                    "(about half of them at p=1, q=0.5)"},
               "cpu_baseline": cpu, "e2e": None, "gpu_launches": K, "clocks": clk})
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def run_negative(args):
@@ -699,16 +803,18 @@ def run_gather(args):
 
 
 def run_hetero(args):
-    """configs[3]: ogbn-mag-shaped heterogeneous sampling, fanouts [10,10] per relation, 1024 paper seeds."""
+    rank, world, local, device = setup_device()
+    out = measure_hetero(args, rank, world, local, device, args.steps, args.warmup, with_cpu=not args.no_cpu)
+    if rank == 0:
+        emit(out)
+
+
+def measure_hetero(args, rank, world, local, device, K, W, with_cpu):
+    """configs[3]: ogbn-mag-shaped heterogeneous sampling, fanouts [10,10] per relation, 1024 paper seeds per batch,
+    seed batches sharded over the ranks (weak scaling), all four CSCs replicated."""
     import tch_geometric as thg
     import torch.distributed as dist
     from tch_geometric.sharding import reduce_job
-    rank, world, local = dist_env()
-    device = torch.device("cuda", local)
-    torch.cuda.set_device(device)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
     counts, edges = synth.mag_like(device, scale=args.scale)
     node_types = list(counts)
     edge_types = list(edges)
@@ -716,7 +822,7 @@ def run_hetero(args):
     for et, ei in edges.items():
         p_, i_, _ = thg.to_csc(ei, (counts[et[0]], counts[et[2]]))
         cp[thg.rel_key(et)], ri[thg.rel_key(et)] = p_, i_
-    B, S, K, W, H = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup, 2
+    B, S, H = args.batches, SEEDS_PER_BATCH, 2
     nn = {thg.rel_key(et): [10, 10] for et in edge_types}
     plan = thg.HeterogenousSampler(node_types, edge_types, cp, ri, B, {"paper": S}, nn, H)
 
@@ -764,7 +870,7 @@ def run_hetero(args):
     ms = e0.elapsed_time(e1)
     ms, edges_all = reduce_job(ms, float(edges_n), device)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and with_cpu:
         from concurrent.futures import ThreadPoolExecutor
         from oracle import oracle as O
         cores = os.cpu_count() or 1
@@ -783,8 +889,9 @@ def run_hetero(args):
         dt = time.perf_counter() - t0
         cpu = {"value": tot / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{nb} batches x {S} paper seeds on {cores} threads ({dt:.1f} s)"}
-    if rank == 0:
-        emit({"metric": "sampled_edges_per_sec_hetero_mag_10_10", "value": edges_all / (ms * 1e-3), "unit": UNIT,
+    launches = plan.num_launches
+    del plan
+    return ({"metric": "sampled_edges_per_sec_hetero_mag_10_10", "value": edges_all / (ms * 1e-3), "unit": UNIT,
               "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
               "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
               "config": {"workload": f"ogbn-mag-shaped synthetic hetero graph {counts}, 4 relations, "
@@ -797,9 +904,7 @@ def run_hetero(args):
                            "frac": alg_bytes / (float(launch_ms.sum()) * 1e-3) / 1e9 / measured_peak_gbs()[0],
                            "traffic": None, "algorithmic_bytes_per_step": alg_bytes / K,
                            "kernel_ms_per_step": float(launch_ms.sum()) / K},
-              "cpu_baseline": cpu, "e2e": None, "gpu_launches": K * (len(launch_ms) + 1), "clocks": clk})
-    if world > 1:
-        dist.destroy_process_group()
+              "cpu_baseline": cpu, "e2e": None, "gpu_launches": K * launches, "clocks": clk})
 
 
 def run_partitioned(args):
@@ -810,12 +915,7 @@ def run_partitioned(args):
     import torch.distributed as dist
     from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedPlan, SingleComm, partition_bounds
     from tch_geometric.sharding import reduce_job
-    rank, world, local = dist_env()
-    device = torch.device("cuda", local)
-    torch.cuda.set_device(device)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+    rank, world, local, device = setup_device()
     cols_full, edges_full = 111_059_956 // 8 + 1, 1_615_685_872 // 8
     cols_rank = max(int(cols_full * args.scale), 64)
     n = cols_rank * world
@@ -877,8 +977,6 @@ def run_partitioned(args):
               "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + 2 * K),
                                                    "answers": ps.stats["answer_bytes"] // (W + 2 * K)},
               "cpu_baseline": None, "e2e": None, "gpu_launches": K * len(FANOUTS) * 8, "clocks": clk})
-    if world > 1:
-        dist.destroy_process_group()
 
 
 def main():
@@ -887,11 +985,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned", "negative", "gather"],
+    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned", "negative", "gather", "relabel"],
                     help="sampling = headline (configs[1]); walk = configs[2]; hetero = configs[3]")
     ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
-    ap.add_argument("--ref-batches", type=int, default=0, help="batches per step of the reference arm (0 = 8 x cores)")
+    ap.add_argument("--ref-batches", type=int, default=0, help="batches per step of the reference arm (0 = --batches)")
+    ap.add_argument("--headline-only", action="store_true",
+                    help="sampling workload: skip the walk / hetero / relabel measurements attached to the default line")
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (0 = leave)")
     ap.add_argument("--sampler", default="uniform", choices=["uniform", "replace", "weighted"],
                     help="sampling workload: neighbour sampler (uniform = the headline configuration)")
@@ -913,8 +1013,13 @@ def main():
         run_negative(args)
     elif args.workload == "gather":
         run_gather(args)
+    elif args.workload == "relabel":
+        run_relabel_only(args)
     else:
         run_ours(args)
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TCHGEO_ABI_VERSION 4
+#define TCHGEO_ABI_VERSION 5
 
 #if defined(__GNUC__)
 #define TCHGEO_API __attribute__((visibility("default")))
@@ -118,6 +118,33 @@ TCHGEO_API tchgeo_status tchgeo_csc_sort_edges(const int64_t* col_ptrs /*DEVICE 
                                                void* workspace /*DEVICE*/, size_t workspace_bytes, tchgeo_stream stream);
 
 /* -------------------------------------------------------------------------------------------- */
+/* Graph handle: R relations' CSC (or CSR) arrays plus the DERIVED device arrays the fast paths read -- the      */
+/* int32 replica of the indices (random gathers then span half as many DRAM lines) and the interleaved         */
+/* (weight, per-column prefix sum) records of the weighted sampler (one 16-byte load per step; the prefix sums   */
+/* are src/data/transform.rs:36-60 summed serially, i.e. the reference's own w_sum sequence,                     */
+/* src/utils/sampling.rs:37-48).  The caller's arrays are BORROWED (they must outlive the handle and must not    */
+/* change); derived arrays are owned by the handle (cudaMalloc, freed by tchgeo_graph_destroy) and are built by   */
+/* tchgeo_graph_prepare or on first use.  A handle is what a host keeps per graph in place of the reference's     */
+/* borrowed CscGraph views (src/data/graph.rs:33-50, built per call at src/python.rs:204-206, :294-300).          */
+/* Not thread-safe while it is being prepared; read-only afterwards.                                             */
+/* -------------------------------------------------------------------------------------------- */
+typedef struct tchgeo_graph tchgeo_graph_t;
+enum { TCHGEO_PREPARE_INDEX_REPLICA = 1, TCHGEO_PREPARE_WEIGHT_RECORDS = 2 };
+TCHGEO_API tchgeo_status tchgeo_graph_create(int32_t num_rels, const int64_t* const* ptrs /*HOST [R] of DEVICE [num_major[r]+1]*/,
+                                             const int64_t* num_major /*HOST [R] columns (CSC) or rows (CSR)*/,
+                                             const int64_t* const* indices /*HOST [R] of DEVICE [nnz[r]]*/,
+                                             const int64_t* nnz /*HOST [R]*/, tchgeo_graph_t** out);
+/* Per-entry edge data aligned with `indices` (entries may be NULL): sampler weights (f64) / edge timestamps (i64).
+ * Setting new weights drops the derived weight records. */
+TCHGEO_API tchgeo_status tchgeo_graph_set_weights(tchgeo_graph_t* g, const double* const* weights /*HOST [R] of DEVICE [nnz[r]]*/);
+TCHGEO_API tchgeo_status tchgeo_graph_set_timestamps(tchgeo_graph_t* g, const int64_t* const* timestamps /*HOST [R]*/);
+/* Build the derived arrays named by `what` (TCHGEO_PREPARE_* bits) now; synchronises the stream.  Relations whose ids
+ * do not fit int32 simply keep no replica (not an error). */
+TCHGEO_API tchgeo_status tchgeo_graph_prepare(tchgeo_graph_t* g, int32_t what, tchgeo_stream stream);
+TCHGEO_API size_t tchgeo_graph_derived_bytes(const tchgeo_graph_t* g);
+TCHGEO_API void tchgeo_graph_destroy(tchgeo_graph_t* g);
+
+/* -------------------------------------------------------------------------------------------- */
 /* Multi-hop neighbor sampling.  One call samples `num_batches` independent seed batches (the     */
 /* reference call is num_batches == 1); batch b's outputs are exactly what the reference returns   */
 /* for inputs[b] and live at offset b*stride of each output buffer.                                */
@@ -134,16 +161,13 @@ typedef struct tchgeo_sampling_args {
   const int64_t* num_cols;          /* HOST [R] number of dst nodes of the relation                */
   const int64_t* const* row_indices;/* HOST [R] of DEVICE [nnz_r]                                  */
   const double* const* weights;     /* HOST [R] of DEVICE [nnz_r] (f64) or NULL unless WEIGHTED    */
-  const int32_t* const* row_indices32; /* optional (table or entries may be NULL): HOST [R] of DEVICE
-                                       [nnz_r] int32 copies of row_indices made by
-                                       tchgeo_compress_indices.  HBM layout optimisation only: the
-                                       random gathers then touch half as many DRAM lines; outputs are
-                                       unchanged (i64).                                            */
-  const double* const* weights_cumsum; /* optional (table or entries may be NULL): HOST [R] of DEVICE [nnz_r]
-                                       f64 = tchgeo_csc_edge_cumsum_f64 of weights[r] (serial per-column prefix
-                                       sums = the w_sum sequence of sampling.rs:37-48).  The weighted kernel then
-                                       reads w_sum instead of scanning the weights, which also makes weighted
-                                       output bit-exact for arbitrary weights.  Ignored with a temporal filter. */
+  const int64_t* nnz;              /* HOST [R] entries of row_indices[r] (and of weights[r] / timestamps[r]); a column
+                                       that ends beyond it raises TCHGEO_ERR_INDEX (the reference panics on the slice,
+                                       src/data/graph.rs:72-78).  NULL = unchecked.                                */
+  const tchgeo_graph_t* graph;      /* optional: take col_ptrs / num_cols / row_indices / nnz / weights / timestamps from
+                                       this handle (the tables above and `timestamps` below may then be NULL) and use its
+                                       derived arrays: int32 gathers, and weighted sampling on (weight, prefix sum)
+                                       records, which is bit-exact for arbitrary weights.  Outputs do not change.  */
   const int64_t* fanouts;           /* HOST [R*H] num_neighbors[r][hop]                            */
   const uint8_t* rel_active;        /* HOST [R] 0 = relation absent from num_neighbors, or NULL    */
   /* ---- seeds ---- */
@@ -167,6 +191,14 @@ typedef struct tchgeo_sampling_args {
   int64_t* layer_offsets;           /* HOST [B*R*H*3] LayerOffset = (len(samples[src]),
                                        len(edges[rel]), len(samples[dst])) at relation start,
                                        src/algo/neighbor_sampling.rs:193,:314-315                  */
+  /* ---- dedup + insertion-order relabel of every batch's tree (K7; semantic of src/algo/negative_sampling.rs:20-47),
+   *      an ADDITIVE stage enqueued after the hops: never alters the outputs above.  All NULL = skipped. ---- */
+  int64_t* const* nodes;            /* HOST [T] of DEVICE [B, samples_stride[t]]: seeds (duplicates kept) ++ every other id
+                                       of samples[t] at its first appearance                                        */
+  int64_t* const* local;            /* HOST [T] of DEVICE [B, samples_stride[t]]: local[i] = index into nodes of
+                                       samples[t][i] (a duplicated seed maps to its LAST seed slot); relabelled edges of
+                                       relation r are (local[src][rows[e]], local[dst][cols[e]])                    */
+  int64_t* nodes_len;               /* HOST [B*T] result, like samples_len                                          */
   /* ---- temporal filter (src/algo/neighbor_sampling.rs:36-77, src/python.rs:137-168); 0 = IdentityFilter ---- */
   int32_t filter_mode;              /* 0 none, 1 TEMPORAL_SAMPLE_STATIC, 2 _RELATIVE, 3 _DYNAMIC (reference mode + 1) */
   int32_t filter_forward;           /* FORWARD const generic (ignored for STATIC)                  */
@@ -222,6 +254,38 @@ TCHGEO_API tchgeo_status tchgeo_neighbor_sampling_homogenous(
     int64_t* rows /*DEVICE [B,edges_stride]*/, int64_t* cols, int64_t* edge_index, int64_t edges_stride,
     int64_t* out_lens /*HOST or NULL*/, int64_t* layer_offsets /*HOST or NULL*/,
     void* workspace /*DEVICE*/, size_t workspace_bytes, tchgeo_stream stream);
+
+/* -------------------------------------------------------------------------------------------- */
+/* Sampling plan handle: everything a host would otherwise rebuild per call, kept behind the ABI.  A plan is a    */
+/* deep copy of a tchgeo_sampling_args (so the caller's host arrays may go away), the launch plan derived from    */
+/* it, pinned host memory for the length table and an event, so that a step is                                     */
+/*     tchgeo_plan_enqueue(plan, seed, batch_base, stream)   H launches (+ the relabel stage), no host sync        */
+/*     tchgeo_plan_collect(plan)                             waits for THAT enqueue only (an event, not the        */
+/*                                                           stream), decodes lengths / layer offsets / errors    */
+/* and two plans on two streams keep the device busy while the host reads the previous step's lengths.            */
+/* The output buffers, the inputs buffers ([B, seeds_per_batch[t]], refilled by the caller before every enqueue,   */
+/* e.g. with one H2D copy on the same stream) and the workspace named in `args` are BORROWED: caller-allocated     */
+/* (tchgeo_neighbor_sampling_capacity / _workspace_bytes), they must outlive the plan.  args->samples_len /         */
+/* edges_len / layer_offsets / nodes_len are ignored: results are read through tchgeo_plan_results.               */
+/* replaces what src/python.rs:187-271 / :273-395 do around the algorithm call, for a host that samples repeatedly. */
+/* -------------------------------------------------------------------------------------------- */
+typedef struct tchgeo_plan tchgeo_plan_t;
+TCHGEO_API tchgeo_status tchgeo_plan_create(const tchgeo_sampling_args* args, tchgeo_plan_t** out);
+TCHGEO_API tchgeo_status tchgeo_plan_enqueue(tchgeo_plan_t* plan, uint64_t seed, uint32_t batch_base, tchgeo_stream stream);
+/* Same, bracketing every hop launch (and the relabel stage as one interval) with CUDA events; synchronises and
+ * collects.  launch_ms: HOST [cap]; the relabel interval, if any, comes last. */
+TCHGEO_API tchgeo_status tchgeo_plan_enqueue_timed(tchgeo_plan_t* plan, uint64_t seed, uint32_t batch_base,
+                                                   tchgeo_stream stream, float* launch_ms, int32_t launch_ms_cap,
+                                                   int32_t* num_intervals);
+TCHGEO_API tchgeo_status tchgeo_plan_collect(tchgeo_plan_t* plan);
+/* HOST arrays owned by the plan, valid until the next collect: samples_len [B*T], edges_len [B*R],
+ * layer_offsets [B*R*H*3], nodes_len [B*T] (NULL without relabel).  Any out pointer may be NULL. */
+TCHGEO_API tchgeo_status tchgeo_plan_results(const tchgeo_plan_t* plan, const int64_t** samples_len,
+                                             const int64_t** edges_len, const int64_t** layer_offsets,
+                                             const int64_t** nodes_len);
+/* Kernel launches one enqueue issues (hop kernels + fill + relabel kernels), for accounting. */
+TCHGEO_API int32_t tchgeo_plan_num_launches(const tchgeo_plan_t* plan);
+TCHGEO_API void tchgeo_plan_destroy(tchgeo_plan_t* plan);
 
 /* -------------------------------------------------------------------------------------------- */
 /* Range-partitioned CSC (graph split over ranks by column range; BASELINE config 5): owner side. */
@@ -342,6 +406,12 @@ TCHGEO_API tchgeo_status tchgeo_random_walk_ex(const int64_t* row_ptrs, int64_t 
                                                int64_t walker_base, int64_t* walks, int64_t* stats,
                                                int64_t* attempts_out, tchgeo_stream stream);
 
+/* Same over relation `rel` of a graph handle holding the CSR (row_ptrs / col_indices); uses the handle's int32 replica. */
+TCHGEO_API tchgeo_status tchgeo_random_walk_graph(const tchgeo_graph_t* graph, int32_t rel, const int64_t* start,
+                                                  int64_t num_walks, int64_t walk_length, float p, float q, uint64_t seed,
+                                                  int64_t walker_base, int64_t* walks, int64_t* stats,
+                                                  int64_t* attempts_out, tchgeo_stream stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* Negative neighbour sampling over CSR.  For every input v of every node type    */
 /* and each of num_neg slots: pick one of the relations that start at v's type (uniformly, only     */
@@ -413,12 +483,34 @@ TCHGEO_API tchgeo_status tchgeo_gather_rows(const void* src /*DEVICE [num_rows, 
                                             void* dst /*DEVICE [n, row_bytes]*/, int32_t* scratch /*DEVICE [1] or NULL*/,
                                             tchgeo_stream stream);
 
+/* Ragged pack: dst[off[b] + i] = src[b*stride + i] for i < min(lens[b*lens_stride], max_len), off = exclusive prefix
+ * sum of the clamped lengths, written to offsets[0..B] (offsets[B] = total).  The sampler's outputs live in padded
+ * [B, capacity] buffers; a host consumer packs the used prefixes and copies them back with ONE transfer per tensor
+ * (what src/python.rs:259-262 does per call with Vec -> Tensor copies).  lens / offsets: DEVICE.  Asynchronous. */
+TCHGEO_API tchgeo_status tchgeo_pack_ragged(const int64_t* src /*DEVICE [B, stride]*/, int64_t stride,
+                                            const int64_t* lens /*DEVICE*/, int64_t lens_stride, int64_t num_batches,
+                                            int64_t max_len, int64_t* dst /*DEVICE [sum]*/, int64_t* offsets /*DEVICE [B+1]*/,
+                                            tchgeo_stream stream);
+
 /* -------------------------------------------------------------------------------------------- */
 /* Dedup + insertion-order relabel of one sampled tree (additive stage).                          */
 /*   nodes      = seeds (duplicates kept) ++ every other id at first appearance                    */
 /*   local[i]   = index into `nodes` of samples[i] (a duplicated seed maps to its LAST seed slot)  */
 /* semantic of src/algo/negative_sampling.rs:20-47                                               */
 /* -------------------------------------------------------------------------------------------- */
+/* Batched form: B trees in padded [B, stride] rows, tree b holding lens[b] <= n_max ids (DEVICE lengths: no host
+ * round trip), the first num_seeds of them seeds.  nodes / local: [B, stride]; nodes_len: DEVICE [B].  key32 != 0
+ * selects 8-byte hash slots for ids < 2^32-1 (an id outside raises TCHGEO_ERR_INDEX); 0 handles any non-negative i64.
+ * Asynchronous; device-side errors are OR-ed into *err_word (DEVICE u32, caller-zeroed; tchgeo_status_from_error_word).
+ * The batches are processed in waves whose hash tables stay in the L2 (see csrc/relabel.cu). */
+TCHGEO_API size_t tchgeo_unique_relabel_batched_workspace_bytes(int64_t num_batches, int64_t n_max, int32_t key32);
+TCHGEO_API tchgeo_status tchgeo_unique_relabel_batched(const int64_t* samples /*DEVICE [B, stride]*/, int64_t stride,
+                                                       const int64_t* lens /*DEVICE [B]*/, int64_t num_batches,
+                                                       int64_t num_seeds, int64_t n_max, int32_t key32,
+                                                       int64_t* nodes /*DEVICE [B, stride]*/, int64_t* local /*DEVICE [B, stride]*/,
+                                                       int64_t* nodes_len /*DEVICE [B]*/, void* workspace /*DEVICE*/,
+                                                       size_t workspace_bytes, int32_t* err_word /*DEVICE*/,
+                                                       tchgeo_stream stream);
 TCHGEO_API size_t tchgeo_unique_relabel_workspace_bytes(int64_t n);
 TCHGEO_API tchgeo_status tchgeo_unique_relabel(const int64_t* samples /*DEVICE [n]*/, int64_t n, int64_t num_seeds,
                                     int64_t* nodes /*DEVICE [n]*/, int64_t* local /*DEVICE [n]*/,

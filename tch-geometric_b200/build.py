@@ -12,7 +12,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "tch_geometric", "libtchgeo_cuda.so")
 OBJ = os.path.join(HERE, "build")
 SOURCES = ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu", "partitioned.cu", "random_walk.cu", "relabel.cu"]
-DEPS = [os.path.join(CSRC, "common.cuh"), os.path.join(HERE, "..", "include", "tchgeo_cuda.h")]
+DEPS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "graph.cuh"), os.path.join(HERE, "..", "include", "tchgeo_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

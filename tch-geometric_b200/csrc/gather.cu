@@ -70,6 +70,64 @@ cudaError_t launch_gather(const void* src, int64_t num_rows, int64_t row_bytes, 
   return cudaGetLastError();
 }
 
+// ---- ragged pack: the used prefixes of B padded rows, back to back -------------------------------------------
+// dst[off[b] + i] = src[b * stride + i] for i < lens[b], off = exclusive prefix sum of lens.  What a host-side consumer
+// wants before a D2H copy: the sampler's outputs live in padded [B, capacity] buffers (about 60 % used), and one copy of
+// the packed prefixes moves only the used bytes.  The offsets are computed on the device by one CTA (B is small).
+constexpr int PK_THREADS = 256;
+constexpr int PK_CHUNK = PK_THREADS * 8;  // elements per CTA
+
+__global__ void __launch_bounds__(1024) pack_offsets_kernel(const int64_t* __restrict__ lens, int64_t lens_stride, int64_t B,
+                                                            int64_t max_len, int64_t* __restrict__ off) {
+  __shared__ int64_t s_warp[32];
+  __shared__ int64_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int64_t b0 = 0; b0 < B; b0 += 1024) {
+    const int64_t b = b0 + tid;
+    int64_t v = b < B ? lens[b * lens_stride] : 0;
+    v = v < 0 ? 0 : (v > max_len ? max_len : v);
+    int64_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    int64_t before = s_carry;
+    for (int w = 0; w < warp; ++w) before += s_warp[w];
+    if (b < B) off[b] = before + incl - v;
+    __syncthreads();
+    if (tid == 1023) s_carry = before + incl;
+    __syncthreads();
+  }
+  if (tid == 0) off[B] = s_carry;
+}
+
+__global__ void __launch_bounds__(PK_THREADS) pack_kernel(const int64_t* __restrict__ src, int64_t stride,
+                                                         const int64_t* __restrict__ off, int64_t* __restrict__ dst) {
+  const int64_t b = blockIdx.y;
+  const int64_t n = off[b + 1] - off[b];
+  const int64_t i0 = (int64_t)blockIdx.x * PK_CHUNK;
+  if (i0 >= n) return;
+  const int64_t* s = src + b * stride + i0;
+  int64_t* d = dst + off[b] + i0;
+  const int64_t m = min((int64_t)PK_CHUNK, n - i0);
+  int64_t v[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int64_t i = u * PK_THREADS + threadIdx.x;
+    v[u] = i < m ? __ldcs(s + i) : 0;
+  }
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int64_t i = u * PK_THREADS + threadIdx.x;
+    if (i < m) __stcs(d + i, v[u]);
+  }
+}
+
 }  // namespace
 }  // namespace tchgeo
 
@@ -95,4 +153,21 @@ extern "C" tchgeo_status tchgeo_gather_rows(const void* src, int64_t num_rows, i
   TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&h, scratch, 4, cudaMemcpyDeviceToHost, stream));
   TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
   return status_from_dev_err(h);
+}
+
+extern "C" tchgeo_status tchgeo_pack_ragged(const int64_t* src, int64_t stride, const int64_t* lens, int64_t lens_stride,
+                                            int64_t num_batches, int64_t max_len, int64_t* dst, int64_t* offsets,
+                                            tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(num_batches >= 0 && num_batches <= 65535 && stride >= 0 && max_len >= 0 && max_len <= stride && lens_stride >= 1,
+                 "bad pack geometry");
+  if (num_batches == 0) return TCHGEO_OK;
+  TCHGEO_REQUIRE(lens && offsets && (max_len == 0 || (src && dst)), "NULL pointer");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  pack_offsets_kernel<<<1, 1024, 0, stream>>>(lens, lens_stride, num_batches, max_len, offsets);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  if (max_len == 0) return TCHGEO_OK;
+  const dim3 grid((unsigned)((max_len + PK_CHUNK - 1) / PK_CHUNK), (unsigned)num_batches);
+  pack_kernel<<<grid, PK_THREADS, 0, stream>>>(src, stride, offsets, dst);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  return TCHGEO_OK;
 }

@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "graph.cuh"
 
 namespace tchgeo {
 namespace {
@@ -56,8 +57,9 @@ struct HopParams {
   const int64_t* indices;
   const int32_t* indices32;  // optional compressed replica of `indices`
   const double* weights;
-  const double* wcum;        // optional serial per-column prefix sums of `weights` (csc_edge_cumsum)
+  const double2* wrec;       // optional (weight, serial per-column prefix sum) records (graph handle): one 16-byte load per step
   int64_t num_cols;
+  int64_t nnz;               // entries of indices / weights / timestamps (INT64_MAX = unchecked)
   const int64_t* dst_samples;  // frontier ids live here (may alias src_samples)
   int64_t dst_stride;
   int64_t* src_samples;        // sampled nodes are appended here
@@ -250,7 +252,8 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
     for (int i = 0; i < TPC; ++i) {
       const int64_t d = en[i] - st[i];
       uint32_t deg = 0;
-      if (d < 0 || d > 0x7fffffffll) atomicOr(p.err, DEV_ERR_INDEX);
+      // a column that ends beyond the edge arrays: the reference panics on the slice (graph.rs:72-78)
+      if (d < 0 || d > 0x7fffffffll || st[i] < 0 || en[i] > p.nnz) atomicOr(p.err, DEV_ERR_INDEX);
       else deg = (uint32_t)d;
       s_pre_start[i][tid] = st[i];
       s_pre_deg[i][tid] = deg;
@@ -281,7 +284,7 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
       cnt = deg < k ? deg : k;
       if (k == 0 && deg > 0) atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0..0), sampling.rs:19
       // UNIFORM and WEIGHTED-with-prefix-sums evaluate steps k .. deg-1 independently: 8-step work items
-      if ((KIND == TCHGEO_SAMPLER_UNIFORM || (KIND == TCHGEO_SAMPLER_WEIGHTED && p.wcum)) && deg > k) {
+      if ((KIND == TCHGEO_SAMPLER_UNIFORM || (KIND == TCHGEO_SAMPLER_WEIGHTED && p.wrec)) && deg > k) {
         nch = (deg - k + 7u) >> 3;
         heavy = nch > (uint32_t)LIGHT_CHUNKS_MAX;
       }
@@ -426,14 +429,13 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
     }
   } else if (KIND == TCHGEO_SAMPLER_WEIGHTED) {
     const uint32_t wtag = TAG_WEIGHTED | (p.rel << 8);
-    if (p.wcum) {
+    if (p.wrec) {
       // w_sum at every step comes from the precomputed serial prefix sums: no scan, the comparison below sees
       // exactly the reference's f64 values whatever the weights are (sampling.rs:47-52), and the steps are
       // independent, so they are spread over the CTA as 8-step work items exactly like the uniform reservoir.
       auto weighted_step = [&](uint32_t n, const NodeRec& rec, uint32_t item) {
-        const int64_t e = s_start[n] + item;
-        const double w = __ldg(p.weights + e);
-        const double w_sum = __ldg(p.wcum + e);
+        const double2 wr = __ldg(p.wrec + s_start[n] + item);
+        const double w = wr.x, w_sum = wr.y;
         if (!(w_sum > 0.0)) {
           atomicOr(p.err, DEV_ERR_PANIC);  // gen_range(0.0..w_sum) on an empty range
           return;
@@ -443,8 +445,8 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
         const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
         if (__dmul_rn(u, w_sum) < w) atomicMax(s_slot + rec.off + __umulhi(r.z, k), item);  // :49-52
       };
-      // 8 lanes per chunk, one step per lane: the eight (weight, prefix sum) pairs of a chunk are 64 contiguous
-      // bytes.  Four chunks per lane group are requested before the first one is used (memory-level parallelism).
+      // 8 lanes per chunk, one step per lane: the eight (weight, prefix sum) records of a chunk are 128 contiguous
+      // bytes, one line.  Four chunks per lane group are requested before the first one is used (memory-level parallelism).
       while (true) {
         uint32_t base = 0;
         if (lane == 0) base = smem_atom_add(&s_work, 128u);
@@ -466,9 +468,9 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
               if (item < rec.deg) {
                 nn4[i] = n;
                 item4[i] = item;
-                const int64_t e = s_start[n] + item;
-                w4[i] = __ldg(p.weights + e);
-                ws4[i] = __ldg(p.wcum + e);
+                const double2 wr = __ldg(p.wrec + s_start[n] + item);
+                w4[i] = wr.x;
+                ws4[i] = wr.y;
               }
             }
           }
@@ -670,7 +672,7 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
     } else {
       start = __ldg(p.ptrs + w);
       const int64_t d = __ldg(p.ptrs + w + 1) - start;
-      if (d < 0 || d > 0x7fffffffll) { if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX); }
+      if (d < 0 || d > 0x7fffffffll || start < 0 || start + d > p.nnz) { if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX); }
       else deg = (uint32_t)d;
     }
     for (uint32_t base = 0; base < deg; base += 32) {
@@ -831,6 +833,24 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
   }
 }
 
+// ---- derived-array kernels of the graph handle ------------------------------------------------
+// (weight, serial prefix sum) records of one relation: one thread per column accumulates in CSC order, exactly the
+// reference's `w_sum = w_sum + w` sequence (sampling.rs:37-48; = csc_edge_cumsum, transform.rs:36-60).  One-time work.
+__global__ void __launch_bounds__(256) wrec_kernel(const int64_t* __restrict__ ptrs, int64_t n_cols,
+                                                   const double* __restrict__ w, int64_t nnz, double2* __restrict__ rec) {
+  const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= n_cols) return;
+  int64_t s = ptrs[c], e = ptrs[c + 1];
+  if (s < 0) s = 0;
+  if (e > nnz) e = nnz;
+  double acc = 0.0;
+  for (int64_t q = s; q < e; ++q) {
+    const double x = w[q];
+    acc = acc + x;
+    rec[q] = make_double2(x, acc);
+  }
+}
+
 // Tuning knob (the default is what bench.py measures): TCHGEO_HOP_MIN_BLOCKS = 8 | 10 | 12 CTAs per SM the register
 // budget is set for (64 / 48 / 40 registers).
 inline int env_int(const char* name, int dflt) {
@@ -846,7 +866,137 @@ inline int hop_min_blocks() {
   return v;
 }
 
+}  // namespace
+}  // namespace tchgeo
+
+// ---- graph handle (struct tchgeo_graph: graph.cuh) ---------------------------------------------
+
+namespace tchgeo {
+
+// Builds the derived arrays named by `what` that are still missing.  Synchronises `stream` when it builds something.
+tchgeo_status graph_ensure(tchgeo_graph* g, int32_t what, cudaStream_t stream) {
+  TCHGEO_REQUIRE(g != nullptr, "graph is NULL");
+  if ((what & TCHGEO_PREPARE_INDEX_REPLICA) && env_int("TCHGEO_INDEX_REPLICA", 1) != 0) {
+    uint32_t* d_err = nullptr;
+    for (int r = 0; r < g->R; ++r) {
+      if (g->replica_state[(size_t)r] != 0) continue;
+      g->replica_state[(size_t)r] = 2;
+      const int64_t n = g->nnz[(size_t)r];
+      if (n <= 0 || !g->indices[(size_t)r]) continue;
+      if (!d_err) TCHGEO_CUDA_CHECK(cudaMalloc(&d_err, 4));
+      int32_t* dst = nullptr;
+      TCHGEO_CUDA_CHECK(cudaMalloc(&dst, (size_t)n * 4));
+      const tchgeo_status st = tchgeo_compress_indices(g->indices[(size_t)r], n, dst, (int32_t*)d_err, stream);
+      if (st == TCHGEO_OK) {
+        g->indices32[(size_t)r] = dst;
+        g->replica_state[(size_t)r] = 1;
+        g->derived_bytes += (size_t)n * 4;
+      } else {
+        cudaFree(dst);  // ids beyond int32 (or negative): sample from the i64 array; the kernels report bad ids
+        if (st != TCHGEO_ERR_INDEX) {
+          cudaFree(d_err);
+          return st;
+        }
+      }
+    }
+    if (d_err) cudaFree(d_err);
+  }
+  if ((what & TCHGEO_PREPARE_WEIGHT_RECORDS) && env_int("TCHGEO_WEIGHT_CUMSUM", 1) != 0) {
+    bool built = false;
+    for (int r = 0; r < g->R; ++r) {
+      if (g->wrec[(size_t)r] || !g->weights[(size_t)r] || g->nnz[(size_t)r] <= 0 || !g->ptrs[(size_t)r]) continue;
+      double2* rec = nullptr;
+      TCHGEO_CUDA_CHECK(cudaMalloc(&rec, (size_t)g->nnz[(size_t)r] * 16));
+      const int64_t nc = g->num_major[(size_t)r];
+      if (nc > 0) {
+        wrec_kernel<<<(unsigned)((nc + 255) / 256), 256, 0, stream>>>(g->ptrs[(size_t)r], nc, g->weights[(size_t)r],
+                                                                     g->nnz[(size_t)r], rec);
+        const cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+          cudaFree(rec);
+          TCHGEO_CUDA_CHECK(e);
+        }
+      }
+      g->wrec[(size_t)r] = rec;
+      g->derived_bytes += (size_t)g->nnz[(size_t)r] * 16;
+      built = true;
+    }
+    if (built) TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  }
+  return TCHGEO_OK;
+}
+
+}  // namespace tchgeo
+
+using namespace tchgeo;
+
+extern "C" tchgeo_status tchgeo_graph_create(int32_t num_rels, const int64_t* const* ptrs, const int64_t* num_major,
+                                             const int64_t* const* indices, const int64_t* nnz, tchgeo_graph_t** out) {
+  TCHGEO_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  TCHGEO_REQUIRE(num_rels > 0 && ptrs && num_major && indices && nnz, "bad graph argument");
+  for (int r = 0; r < num_rels; ++r)
+    TCHGEO_REQUIRE(num_major[r] >= 0 && nnz[r] >= 0 && (nnz[r] == 0 || indices[r]), "relation %d: bad sizes", r);
+  tchgeo_graph* g = new tchgeo_graph();
+  const size_t R = (size_t)num_rels;
+  g->R = num_rels;
+  TCHGEO_CUDA_CHECK(cudaGetDevice(&g->device));
+  g->ptrs.assign(ptrs, ptrs + R);
+  g->indices.assign(indices, indices + R);
+  g->num_major.assign(num_major, num_major + R);
+  g->nnz.assign(nnz, nnz + R);
+  g->weights.assign(R, nullptr);
+  g->timestamps.assign(R, nullptr);
+  g->indices32.assign(R, nullptr);
+  g->replica_state.assign(R, 0);
+  g->wrec.assign(R, nullptr);
+  *out = g;
+  return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_graph_set_weights(tchgeo_graph_t* g, const double* const* weights) {
+  TCHGEO_REQUIRE(g != nullptr, "graph is NULL");
+  for (int r = 0; r < g->R; ++r) {
+    if (g->wrec[(size_t)r]) {
+      cudaFree(g->wrec[(size_t)r]);
+      g->derived_bytes -= (size_t)g->nnz[(size_t)r] * 16;
+      g->wrec[(size_t)r] = nullptr;
+    }
+    g->weights[(size_t)r] = weights ? weights[r] : nullptr;
+  }
+  return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_graph_set_timestamps(tchgeo_graph_t* g, const int64_t* const* timestamps) {
+  TCHGEO_REQUIRE(g != nullptr, "graph is NULL");
+  for (int r = 0; r < g->R; ++r) g->timestamps[(size_t)r] = timestamps ? timestamps[r] : nullptr;
+  return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_graph_prepare(tchgeo_graph_t* g, int32_t what, tchgeo_stream stream) {
+  return graph_ensure(g, what, (cudaStream_t)stream);
+}
+
+extern "C" size_t tchgeo_graph_derived_bytes(const tchgeo_graph_t* g) { return g ? g->derived_bytes : 0; }
+
+extern "C" void tchgeo_graph_destroy(tchgeo_graph_t* g) {
+  if (!g) return;
+  for (auto p : g->indices32) if (p) cudaFree(p);
+  for (auto p : g->wrec) if (p) cudaFree(p);
+  delete g;
+}
+
 // ---- host-side plan: which launches, which version rows of the length table ------------------
+namespace tchgeo {
+// csrc/relabel.cu
+size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, bool k32);
+int relabel_launches(int64_t num_trees, int64_t n_max, bool k32);
+tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
+                              int64_t num_seeds, int64_t n_max, bool k32, int64_t* nodes, int64_t* local,
+                              int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
+                              cudaStream_t stream);
+namespace {
+
 struct Launch {
   int rel, hop;
   int fr_begin_row, fr_end_row;
@@ -856,6 +1006,15 @@ struct Launch {
   int64_t fanout;
   int tile_nodes, tile_edges, tiles_per_batch;
   size_t status_off;  // in uint64 words
+};
+
+// effective per-relation device arrays of a call: the tables of the args, or those of its graph handle
+struct Resolved {
+  std::vector<const int64_t*> ptrs, indices, timestamps;
+  std::vector<int64_t> num_cols, nnz;
+  std::vector<const double*> weights;
+  std::vector<const int32_t*> indices32;
+  std::vector<const double2*> wrec;
 };
 
 struct Plan {
@@ -869,12 +1028,53 @@ struct Plan {
   std::vector<int64_t> samples_cap, edges_cap;  // worst case per batch
   int num_rows;                         // V
   size_t status_words;
+  // dedup + relabel stage (K7): one length row per node type, 8-byte hash slots where the ids are known to fit
+  bool relabel;
+  std::vector<int> nodes_row;           // [T] or -1
+  std::vector<uint8_t> key32;           // [T]
+  int relabel_kernels;
   // workspace layout (bytes)
-  size_t off_ctrl, off_state, off_status, total_bytes;
+  size_t off_ctrl, off_state, off_status, off_relabel, relabel_bytes, total_bytes;
+  Resolved rs;
 };
 
 constexpr size_t CTRL_WORDS = 64;  // uint32: [0] = err, [1..] = one ticket per launch (grown if needed)
 
+tchgeo_status resolve(const tchgeo_sampling_args* a, Resolved& rs, bool want_derived, cudaStream_t stream) {
+  const size_t R = (size_t)a->num_rels;
+  rs.ptrs.assign(R, nullptr); rs.indices.assign(R, nullptr); rs.timestamps.assign(R, nullptr);
+  rs.num_cols.assign(R, 0); rs.nnz.assign(R, INT64_MAX);
+  rs.weights.assign(R, nullptr); rs.indices32.assign(R, nullptr); rs.wrec.assign(R, nullptr);
+  const bool weighted = a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED;
+  if (a->graph) {
+    tchgeo_graph* g = const_cast<tchgeo_graph*>(a->graph);
+    TCHGEO_REQUIRE(g->R == a->num_rels, "graph handle has %d relations, the call %d", g->R, a->num_rels);
+    if (want_derived) {
+      int what = TCHGEO_PREPARE_INDEX_REPLICA;
+      if (weighted && !a->filter_mode) what |= TCHGEO_PREPARE_WEIGHT_RECORDS;  // with a filter w_sum runs over the passing edges
+      const tchgeo_status st = graph_ensure(g, what, stream);
+      if (st != TCHGEO_OK) return st;
+    }
+    for (size_t r = 0; r < R; ++r) {
+      rs.ptrs[r] = g->ptrs[r]; rs.indices[r] = g->indices[r]; rs.num_cols[r] = g->num_major[r]; rs.nnz[r] = g->nnz[r];
+      rs.weights[r] = weighted ? g->weights[r] : nullptr;
+      rs.timestamps[r] = (a->timestamps && a->timestamps[r]) ? a->timestamps[r] : g->timestamps[r];
+      rs.indices32[r] = env_int("TCHGEO_INDEX_REPLICA", 1) != 0 ? g->indices32[r] : nullptr;
+      rs.wrec[r] = (weighted && !a->filter_mode) ? g->wrec[r] : nullptr;
+    }
+    return TCHGEO_OK;
+  }
+  if (!(a->col_ptrs && a->row_indices && a->num_cols)) return TCHGEO_OK;  // geometry queries; check_args refuses to run
+  for (size_t r = 0; r < R; ++r) {
+    rs.ptrs[r] = a->col_ptrs[r]; rs.indices[r] = a->row_indices[r]; rs.num_cols[r] = a->num_cols[r];
+    if (a->nnz) rs.nnz[r] = a->nnz[r];
+    if (weighted && a->weights) rs.weights[r] = a->weights[r];
+    if (a->filter_mode && a->timestamps) rs.timestamps[r] = a->timestamps[r];
+  }
+  return TCHGEO_OK;
+}
+
+// geometry only (capacities, rows, launches): needs no device arrays
 tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   TCHGEO_REQUIRE(a != nullptr, "args is NULL");
   TCHGEO_REQUIRE(a->num_node_types > 0 && a->num_rels > 0 && a->num_hops >= 0, "bad T/R/H");
@@ -964,13 +1164,50 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   for (int t = 0; t < T; ++t) pl.samples_cap[t] = wc_len[t];
   pl.n_row_final = cur_n;
   pl.e_row_final = cur_e;
+  pl.relabel = a->nodes != nullptr || a->local != nullptr;
+  pl.nodes_row.assign(T, -1);
+  if (pl.relabel)
+    for (int t = 0; t < T; ++t) pl.nodes_row[t] = rows++;
   pl.num_rows = rows;
   pl.status_words = status_words;
   const size_t ctrl_words = std::max(CTRL_WORDS, pl.launches.size() + 2);
   pl.off_ctrl = 0;
   pl.off_state = ((ctrl_words * 4 + 255) / 256) * 256;
   pl.off_status = pl.off_state + (((size_t)rows * pl.B * 8 + 255) / 256) * 256;
-  pl.total_bytes = pl.off_status + status_words * 8 + 256;
+  pl.off_relabel = pl.off_status + ((status_words * 8 + 255) / 256) * 256;
+  pl.relabel_bytes = 0;
+  pl.relabel_kernels = 0;
+  pl.key32.assign(T, 0);
+  pl.total_bytes = pl.off_relabel + 256;
+  return TCHGEO_OK;
+}
+
+// everything: geometry + the device arrays the launches read + the relabel stage's share of the workspace
+tchgeo_status make_plan(const tchgeo_sampling_args* a, Plan& pl, bool want_derived) {
+  tchgeo_status st = build_plan(a, pl);
+  if (st != TCHGEO_OK) return st;
+  st = resolve(a, pl.rs, want_derived, (cudaStream_t)a->stream);
+  if (st != TCHGEO_OK) return st;
+  if (pl.relabel) {
+    TCHGEO_REQUIRE(a->nodes && a->local, "relabel needs both nodes and local");
+    for (int t = 0; t < pl.T; ++t) {
+      // 8-byte slots when every id of the type is known to be below 2^31: all relations that append to it read an
+      // int32 replica (seeds beyond 2^32-2 are then reported as TCHGEO_ERR_INDEX by the stage)
+      bool k32 = true, fed = false;
+      for (int r = 0; r < pl.R; ++r)
+        if (a->rel_src[r] == t && (!a->rel_active || a->rel_active[r])) {
+          fed = true;
+          k32 = k32 && pl.rs.indices32[(size_t)r] != nullptr;
+        }
+      pl.key32[t] = (uint8_t)(k32 && fed);
+      if (pl.samples_cap[t] == 0) continue;
+      const size_t need = relabel_workspace_bytes(pl.B, pl.samples_cap[t], pl.key32[t] != 0);
+      TCHGEO_REQUIRE(need > 0, "relabel: tree of node type %d too large", t);
+      pl.relabel_bytes = std::max(pl.relabel_bytes, need);
+      pl.relabel_kernels += relabel_launches(pl.B, pl.samples_cap[t], pl.key32[t] != 0);
+    }
+    pl.total_bytes = pl.off_relabel + pl.relabel_bytes + 256;
+  }
   return TCHGEO_OK;
 }
 
@@ -1005,67 +1242,53 @@ cudaError_t launch_hop(const HopParams& hp, int64_t tiles, size_t smem, cudaStre
                       : launch_hop_i<KIND, false>(hp, tiles, smem, stream);
 }
 
-}  // namespace
-}  // namespace tchgeo
-
-using namespace tchgeo;
-
-extern "C" tchgeo_status tchgeo_neighbor_sampling_capacity(const tchgeo_sampling_args* args, int64_t* samples_cap,
-                                                           int64_t* edges_cap) {
-  Plan pl;
-  tchgeo_status st = build_plan(args, pl);
-  if (st != TCHGEO_OK) return st;
-  if (samples_cap) for (int t = 0; t < pl.T; ++t) samples_cap[t] = pl.samples_cap[t];
-  if (edges_cap) for (int r = 0; r < pl.R; ++r) edges_cap[r] = pl.edges_cap[r];
-  return TCHGEO_OK;
+template <int KIND>
+cudaError_t launch_filtered(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+  static bool configured[64] = {};  // per device: fanouts above ~11 k need more than the default 48 KB
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    e = cudaFuncSetAttribute(hop_filtered_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  hop_filtered_kernel<KIND><<<(unsigned)grid, FT_THREADS, smem, stream>>>(hp);
+  return cudaGetLastError();
 }
 
-extern "C" size_t tchgeo_neighbor_sampling_workspace_bytes(const tchgeo_sampling_args* args) {
-  Plan pl;
-  if (build_plan(args, pl) != TCHGEO_OK) return 0;
-  return pl.total_bytes;
-}
+struct EventList {  // destroyed on every exit path
+  std::vector<cudaEvent_t> ev;
+  ~EventList() {
+    for (auto e : ev) cudaEventDestroy(e);
+  }
+};
 
-extern "C" tchgeo_status tchgeo_neighbor_sampling_collect(const tchgeo_sampling_args* a) {
-  Plan pl;
-  tchgeo_status st = build_plan(a, pl);
-  if (st != TCHGEO_OK) return st;
-  TCHGEO_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= pl.total_bytes, "workspace too small");
-  cudaStream_t stream = (cudaStream_t)a->stream;
-  char* ws = (char*)a->workspace;
-  const size_t n_state = (size_t)pl.num_rows * pl.B;
-  std::vector<int64_t> state(n_state);
-  uint32_t err = 0;
-  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(state.data(), ws + pl.off_state, n_state * 8, cudaMemcpyDeviceToHost, stream));
-  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&err, ws + pl.off_ctrl, 4, cudaMemcpyDeviceToHost, stream));
-  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+// decode a host copy of the length table into the result arrays (any may be NULL)
+void decode_state(const Plan& pl, const int64_t* state, int64_t* samples_len, int64_t* edges_len, int64_t* layer_offsets,
+                  int64_t* nodes_len) {
   const int T = pl.T, R = pl.R, H = pl.H;
   const int64_t B = pl.B;
   for (int64_t b = 0; b < B; ++b) {
-    if (a->samples_len)
-      for (int t = 0; t < T; ++t) a->samples_len[b * T + t] = state[(size_t)pl.n_row_final[t] * B + b];
-    if (a->edges_len)
-      for (int r = 0; r < R; ++r) a->edges_len[b * R + r] = state[(size_t)pl.e_row_final[r] * B + b];
-    if (a->layer_offsets)
+    if (samples_len)
+      for (int t = 0; t < T; ++t) samples_len[b * T + t] = state[(size_t)pl.n_row_final[t] * B + b];
+    if (edges_len)
+      for (int r = 0; r < R; ++r) edges_len[b * R + r] = state[(size_t)pl.e_row_final[r] * B + b];
+    if (layer_offsets)
       for (int r = 0; r < R; ++r)
         for (int h = 0; h < H; ++h)
           for (int c = 0; c < 3; ++c) {
             const int row = pl.lo_rows[((size_t)r * H + h) * 3 + c];
-            a->layer_offsets[(((size_t)b * R + r) * H + h) * 3 + c] = row < 0 ? -1 : state[(size_t)row * B + b];
+            layer_offsets[(((size_t)b * R + r) * H + h) * 3 + c] = row < 0 ? -1 : state[(size_t)row * B + b];
           }
+    if (nodes_len && pl.relabel)
+      for (int t = 0; t < T; ++t) nodes_len[b * T + t] = pl.nodes_row[t] < 0 ? 0 : state[(size_t)pl.nodes_row[t] * B + b];
   }
-  return status_from_dev_err(err);
 }
 
-static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_ms, int32_t launch_ms_cap,
-                                  int32_t* num_launches) {
-  Plan pl;
-  tchgeo_status st = build_plan(a, pl);
-  if (st != TCHGEO_OK) return st;
-  const int T = pl.T, R = pl.R;
-  const int64_t B = pl.B;
-  TCHGEO_REQUIRE(a->col_ptrs && a->row_indices && a->num_cols && a->inputs && a->samples && a->samples_stride &&
-                     a->rows && a->cols && a->edge_index && a->edges_stride,
+tchgeo_status check_args(const tchgeo_sampling_args* a, const Plan& pl) {
+  const int T = pl.T;
+  TCHGEO_REQUIRE(a->inputs && a->samples && a->samples_stride && a->rows && a->cols && a->edge_index && a->edges_stride,
                  "NULL pointer table");
   TCHGEO_REQUIRE(a->workspace != nullptr, "workspace is NULL");
   if (a->workspace_bytes < pl.total_bytes) {
@@ -1080,32 +1303,43 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     }
     if (a->samples_stride[t] > 0) TCHGEO_REQUIRE(a->samples[t] != nullptr, "samples[%d] is NULL", t);
     TCHGEO_REQUIRE(a->samples_stride[t] < ((int64_t)1 << 32), "samples_stride[%d] must be < 2^32", t);
+    if (pl.relabel && a->samples_stride[t] > 0)
+      TCHGEO_REQUIRE(a->nodes[t] && a->local[t], "relabel: nodes[%d] / local[%d] is NULL", t, t);
   }
   for (const Launch& L : pl.launches) {
     const int r = L.rel;
-    TCHGEO_REQUIRE(a->col_ptrs[r] && a->num_cols[r] >= 0, "relation %d: col_ptrs is NULL", r);
+    TCHGEO_REQUIRE(pl.rs.ptrs[(size_t)r] && pl.rs.num_cols[(size_t)r] >= 0, "relation %d: col_ptrs is NULL", r);
     // row_indices[r] may be NULL for a relation without edges: it is only dereferenced when deg > 0
     if (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED)
-      TCHGEO_REQUIRE(a->weights && a->weights[r], "relation %d: weighted sampler without weights", r);
+      TCHGEO_REQUIRE(pl.rs.weights[(size_t)r], "relation %d: weighted sampler without weights", r);
+    if (a->filter_mode) TCHGEO_REQUIRE(pl.rs.timestamps[(size_t)r], "relation %d: temporal filter without timestamps", r);
     if (a->edges_stride[r] > 0)
       TCHGEO_REQUIRE(a->rows[r] && a->cols[r] && a->edge_index[r], "relation %d: NULL edge output", r);
   }
   if (a->filter_mode) {
     TCHGEO_REQUIRE(a->filter_mode >= 1 && a->filter_mode <= 3, "unknown filter mode");
-    TCHGEO_REQUIRE(a->timestamps && a->states && a->inputs_state, "temporal filter needs timestamps, states, inputs_state");
+    TCHGEO_REQUIRE(a->states && a->inputs_state, "temporal filter needs states and inputs_state");
     for (int t = 0; t < T; ++t) {
       if (a->samples_stride[t] > 0) TCHGEO_REQUIRE(a->states[t] != nullptr, "states[%d] is NULL", t);
       if (a->seeds_per_batch[t] > 0) TCHGEO_REQUIRE(a->inputs_state[t] != nullptr, "inputs_state[%d] is NULL", t);
     }
   }
-  cudaStream_t stream = (cudaStream_t)a->stream;
+  return TCHGEO_OK;
+}
+
+// Enqueues one sampling step on `stream`: no host synchronisation.  ev (optional): n_launch + 1 (+ 1 with relabel)
+// events recorded around the launches.
+tchgeo_status enqueue_step(const tchgeo_sampling_args* a, const Plan& pl, uint64_t seed, uint32_t batch_base,
+                           cudaStream_t stream, std::vector<cudaEvent_t>* ev) {
+  const int T = pl.T;
+  const int64_t B = pl.B;
   char* ws = (char*)a->workspace;
   uint32_t* ctrl = (uint32_t*)(ws + pl.off_ctrl);
   int64_t* state = (int64_t*)(ws + pl.off_state);
   uint64_t* status = (uint64_t*)(ws + pl.off_status);
 
   // control words, length table and look-back status all start at zero
-  TCHGEO_CUDA_CHECK(cudaMemsetAsync(ws, 0, pl.total_bytes, stream));
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(ws, 0, pl.off_relabel, stream));
   for (int t = 0; t < T; ++t) {
     const int64_t S = a->seeds_per_batch[t];
     if (S == 0) continue;
@@ -1119,24 +1353,17 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
                                           (size_t)S * 8, (size_t)S * 8, (size_t)B, cudaMemcpyDeviceToDevice, stream));
   }
   int li = 0;
-  const int n_launch = (int)pl.launches.size();
-  if (num_launches) *num_launches = n_launch;
-  std::vector<cudaEvent_t> ev;
-  if (launch_ms) {
-    TCHGEO_REQUIRE(launch_ms_cap >= n_launch, "launch_ms too small: %d launches", n_launch);
-    ev.resize((size_t)n_launch + 1);
-    for (auto& e : ev) TCHGEO_CUDA_CHECK(cudaEventCreate(&e));
-    TCHGEO_CUDA_CHECK(cudaEventRecord(ev[0], stream));
-  }
+  if (ev) TCHGEO_CUDA_CHECK(cudaEventRecord((*ev)[0], stream));
   for (const Launch& L : pl.launches) {
     const int r = L.rel, stt = a->rel_src[r], dtt = a->rel_dst[r];
     HopParams hp;
-    hp.ptrs = a->col_ptrs[r];
-    hp.indices = a->row_indices[r];
-    hp.indices32 = a->row_indices32 ? a->row_indices32[r] : nullptr;
-    hp.weights = (a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED) ? a->weights[r] : nullptr;
-    hp.wcum = (hp.weights && a->weights_cumsum) ? a->weights_cumsum[r] : nullptr;
-    hp.num_cols = a->num_cols[r];
+    hp.ptrs = pl.rs.ptrs[(size_t)r];
+    hp.indices = pl.rs.indices[(size_t)r];
+    hp.indices32 = pl.rs.indices32[(size_t)r];
+    hp.weights = pl.rs.weights[(size_t)r];
+    hp.wrec = pl.rs.wrec[(size_t)r];
+    hp.num_cols = pl.rs.num_cols[(size_t)r];
+    hp.nnz = pl.rs.nnz[(size_t)r];
     hp.dst_samples = a->samples[dtt];
     hp.dst_stride = a->samples_stride[dtt];
     hp.src_samples = a->samples[stt];
@@ -1159,14 +1386,14 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.tile_nodes = L.tile_nodes;
     hp.tile_edges = L.tile_edges;
     hp.fanout = (int32_t)L.fanout;
-    hp.key0 = (uint32_t)a->seed;
-    hp.key1 = (uint32_t)(a->seed >> 32);
-    for (uint32_t r = 0; r < 10; ++r) {
-      hp.rk[2 * r] = hp.key0 + r * 0x9E3779B9u;
-      hp.rk[2 * r + 1] = hp.key1 + r * 0xBB67AE85u;
+    hp.key0 = (uint32_t)seed;
+    hp.key1 = (uint32_t)(seed >> 32);
+    for (uint32_t q = 0; q < 10; ++q) {
+      hp.rk[2 * q] = hp.key0 + q * 0x9E3779B9u;
+      hp.rk[2 * q + 1] = hp.key1 + q * 0xBB67AE85u;
     }
     hp.rel = (uint32_t)r;
-    hp.batch_base = a->batch_base;
+    hp.batch_base = batch_base;
     const int64_t grid = (int64_t)L.tiles_per_batch * B;
     const size_t smem = (size_t)L.tile_edges * 5 + 16;
     hp.total_tiles = (uint32_t)((int64_t)L.tiles_per_batch * B);
@@ -1174,18 +1401,17 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     hp.filter_forward = a->filter_forward;
     hp.win_lo = a->filter_window_lo;
     hp.win_hi = a->filter_window_hi;
-    hp.timestamps = a->filter_mode ? a->timestamps[r] : nullptr;
+    hp.timestamps = a->filter_mode ? pl.rs.timestamps[(size_t)r] : nullptr;
     hp.dst_states = a->filter_mode ? a->states[dtt] : nullptr;
     hp.src_states = a->filter_mode ? a->states[stt] : nullptr;
     cudaError_t e;
     if (a->filter_mode) {
       const size_t fsmem = (size_t)L.tile_edges * 4 + 16;
       switch (a->sampler_kind) {
-        case TCHGEO_SAMPLER_UNIFORM: hop_filtered_kernel<TCHGEO_SAMPLER_UNIFORM><<<(unsigned)grid, FT_THREADS, fsmem, stream>>>(hp); break;
-        case TCHGEO_SAMPLER_UNIFORM_REPLACE: hop_filtered_kernel<TCHGEO_SAMPLER_UNIFORM_REPLACE><<<(unsigned)grid, FT_THREADS, fsmem, stream>>>(hp); break;
-        default: hop_filtered_kernel<TCHGEO_SAMPLER_WEIGHTED><<<(unsigned)grid, FT_THREADS, fsmem, stream>>>(hp); break;
+        case TCHGEO_SAMPLER_UNIFORM: e = launch_filtered<TCHGEO_SAMPLER_UNIFORM>(hp, grid, fsmem, stream); break;
+        case TCHGEO_SAMPLER_UNIFORM_REPLACE: e = launch_filtered<TCHGEO_SAMPLER_UNIFORM_REPLACE>(hp, grid, fsmem, stream); break;
+        default: e = launch_filtered<TCHGEO_SAMPLER_WEIGHTED>(hp, grid, fsmem, stream); break;
       }
-      e = cudaGetLastError();
     } else {
       switch (a->sampler_kind) {
         case TCHGEO_SAMPLER_UNIFORM: e = launch_hop<TCHGEO_SAMPLER_UNIFORM>(hp, grid, smem, stream); break;
@@ -1195,19 +1421,105 @@ static tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_m
     }
     TCHGEO_CUDA_CHECK(e);
     ++li;
-    if (launch_ms) TCHGEO_CUDA_CHECK(cudaEventRecord(ev[(size_t)li], stream));
+    if (ev) TCHGEO_CUDA_CHECK(cudaEventRecord((*ev)[(size_t)li], stream));
   }
-  tchgeo_status rc = TCHGEO_OK;
-  if (launch_ms || a->samples_len || a->edges_len || a->layer_offsets) rc = tchgeo_neighbor_sampling_collect(a);
-  if (launch_ms) {
-    for (int i = 0; i < n_launch; ++i) {
-      float ms = 0.f;
-      if (cudaEventElapsedTime(&ms, ev[(size_t)i], ev[(size_t)i + 1]) != cudaSuccess) ms = -1.f;
-      launch_ms[i] = ms;
+  if (pl.relabel) {
+    // K7: dedup + insertion-order relabel of every batch's tree, per node type, from the device-side lengths
+    for (int t = 0; t < T; ++t) {
+      const int64_t cap = std::min(pl.samples_cap[t], a->samples_stride[t]);
+      if (cap <= 0) continue;
+      const tchgeo_status st = relabel_enqueue(a->samples[t], a->samples_stride[t], state + (size_t)pl.n_row_final[t] * B, B,
+                                               a->seeds_per_batch[t], cap, pl.key32[t] != 0, a->nodes[t], a->local[t],
+                                               state + (size_t)pl.nodes_row[t] * B, ws + pl.off_relabel, pl.relabel_bytes + 256,
+                                               ctrl, stream);
+      if (st != TCHGEO_OK) return st;
     }
-    for (auto& e : ev) cudaEventDestroy(e);
+    if (ev) TCHGEO_CUDA_CHECK(cudaEventRecord((*ev)[(size_t)li + 1], stream));
   }
-  return rc;
+  return TCHGEO_OK;
+}
+
+tchgeo_status make_events(EventList& evs, size_t n) {
+  evs.ev.reserve(n);
+  for (size_t i = 0; i < n; ++i) {
+    cudaEvent_t e;
+    TCHGEO_CUDA_CHECK(cudaEventCreate(&e));
+    evs.ev.push_back(e);
+  }
+  return TCHGEO_OK;
+}
+
+int read_intervals(const EventList& evs, float* launch_ms) {
+  const int n = (int)evs.ev.size() - 1;
+  for (int i = 0; i < n; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, evs.ev[(size_t)i], evs.ev[(size_t)i + 1]) != cudaSuccess) ms = -1.f;
+    launch_ms[i] = ms;
+  }
+  return n;
+}
+
+tchgeo_status collect_with_plan(const tchgeo_sampling_args* a, const Plan& pl) {
+  TCHGEO_REQUIRE(a->workspace != nullptr && a->workspace_bytes >= pl.total_bytes, "workspace too small");
+  cudaStream_t stream = (cudaStream_t)a->stream;
+  char* ws = (char*)a->workspace;
+  const size_t n_state = (size_t)pl.num_rows * pl.B;
+  std::vector<int64_t> state(n_state);
+  uint32_t err = 0;
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(state.data(), ws + pl.off_state, n_state * 8, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&err, ws + pl.off_ctrl, 4, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  decode_state(pl, state.data(), a->samples_len, a->edges_len, a->layer_offsets, a->nodes_len);
+  return status_from_dev_err(err);
+}
+
+tchgeo_status run_sampling(const tchgeo_sampling_args* a, float* launch_ms, int32_t launch_ms_cap, int32_t* num_launches) {
+  Plan pl;
+  tchgeo_status st = make_plan(a, pl, true);
+  if (st != TCHGEO_OK) return st;
+  st = check_args(a, pl);
+  if (st != TCHGEO_OK) return st;
+  const int n_iv = (int)pl.launches.size() + (pl.relabel ? 1 : 0);
+  if (num_launches) *num_launches = n_iv;
+  EventList evs;
+  if (launch_ms) {
+    TCHGEO_REQUIRE(launch_ms_cap >= n_iv, "launch_ms too small: %d intervals", n_iv);
+    st = make_events(evs, (size_t)n_iv + 1);
+    if (st != TCHGEO_OK) return st;
+  }
+  st = enqueue_step(a, pl, a->seed, a->batch_base, (cudaStream_t)a->stream, launch_ms ? &evs.ev : nullptr);
+  if (st != TCHGEO_OK) return st;
+  if (launch_ms || a->samples_len || a->edges_len || a->layer_offsets || a->nodes_len) st = collect_with_plan(a, pl);
+  if (launch_ms) read_intervals(evs, launch_ms);
+  return st;
+}
+
+}  // namespace
+}  // namespace tchgeo
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling_capacity(const tchgeo_sampling_args* args, int64_t* samples_cap,
+                                                           int64_t* edges_cap) {
+  Plan pl;
+  tchgeo_status st = build_plan(args, pl);
+  if (st != TCHGEO_OK) return st;
+  if (samples_cap) for (int t = 0; t < pl.T; ++t) samples_cap[t] = pl.samples_cap[t];
+  if (edges_cap) for (int r = 0; r < pl.R; ++r) edges_cap[r] = pl.edges_cap[r];
+  return TCHGEO_OK;
+}
+
+// (with a graph handle this builds the handle's derived arrays if they are missing: the relabel stage sizes its hash
+//  slots by whether the int32 replica exists)
+extern "C" size_t tchgeo_neighbor_sampling_workspace_bytes(const tchgeo_sampling_args* args) {
+  Plan pl;
+  if (make_plan(args, pl, true) != TCHGEO_OK) return 0;
+  return pl.total_bytes;
+}
+
+extern "C" tchgeo_status tchgeo_neighbor_sampling_collect(const tchgeo_sampling_args* a) {
+  Plan pl;
+  tchgeo_status st = make_plan(a, pl, false);
+  if (st != TCHGEO_OK) return st;
+  return collect_with_plan(a, pl);
 }
 
 extern "C" tchgeo_status tchgeo_neighbor_sampling(const tchgeo_sampling_args* a) {
@@ -1218,6 +1530,165 @@ extern "C" tchgeo_status tchgeo_neighbor_sampling_timed(const tchgeo_sampling_ar
                                                         int32_t launch_ms_cap, int32_t* num_launches) {
   TCHGEO_REQUIRE(launch_ms != nullptr, "launch_ms is NULL");
   return run_sampling(a, launch_ms, launch_ms_cap, num_launches);
+}
+
+// ---- plan handle -------------------------------------------------------------------------------
+struct tchgeo_plan {
+  tchgeo_sampling_args a;  // deep copy: every HOST table below is owned by the handle
+  std::vector<int32_t> rel_src, rel_dst;
+  std::vector<const int64_t*> col_ptrs, row_indices, inputs, timestamps, inputs_state;
+  std::vector<const double*> weights;
+  std::vector<int64_t> num_cols, nnz, fanouts, seeds_per_batch, samples_stride, edges_stride;
+  std::vector<uint8_t> rel_active;
+  std::vector<int64_t*> samples, rows, cols, edge_index, states, nodes, local;
+  Plan pl;
+  int device = 0;
+  int64_t* h_state = nullptr;  // pinned: length table + [n_state] = error word
+  size_t n_state = 0;
+  cudaEvent_t done = nullptr;
+  bool pending = false;
+  std::vector<int64_t> samples_len, edges_len, layer_offsets, nodes_len;
+};
+
+namespace {
+template <typename V, typename P>
+void copy_table(V& v, P*& field, size_t n) {
+  if (field == nullptr || n == 0) {
+    field = nullptr;
+    return;
+  }
+  v.assign(field, field + n);
+  field = v.data();
+}
+}  // namespace
+
+extern "C" void tchgeo_plan_destroy(tchgeo_plan_t* p) {
+  if (!p) return;
+  if (p->done) cudaEventDestroy(p->done);
+  if (p->h_state) cudaFreeHost(p->h_state);
+  delete p;
+}
+
+extern "C" tchgeo_status tchgeo_plan_create(const tchgeo_sampling_args* args, tchgeo_plan_t** out) {
+  TCHGEO_REQUIRE(out != nullptr, "out is NULL");
+  *out = nullptr;
+  TCHGEO_REQUIRE(args != nullptr && args->num_node_types > 0 && args->num_rels > 0 && args->num_hops >= 0, "bad T/R/H");
+  tchgeo_plan* p = new tchgeo_plan();
+  p->a = *args;
+  tchgeo_sampling_args& a = p->a;
+  const size_t T = (size_t)a.num_node_types, R = (size_t)a.num_rels, H = (size_t)a.num_hops;
+  copy_table(p->rel_src, a.rel_src, R);
+  copy_table(p->rel_dst, a.rel_dst, R);
+  copy_table(p->col_ptrs, a.col_ptrs, R);
+  copy_table(p->num_cols, a.num_cols, R);
+  copy_table(p->row_indices, a.row_indices, R);
+  copy_table(p->weights, a.weights, R);
+  copy_table(p->nnz, a.nnz, R);
+  copy_table(p->fanouts, a.fanouts, R * H);
+  copy_table(p->rel_active, a.rel_active, R);
+  copy_table(p->inputs, a.inputs, T);
+  copy_table(p->seeds_per_batch, a.seeds_per_batch, T);
+  copy_table(p->samples, a.samples, T);
+  copy_table(p->samples_stride, a.samples_stride, T);
+  copy_table(p->rows, a.rows, R);
+  copy_table(p->cols, a.cols, R);
+  copy_table(p->edge_index, a.edge_index, R);
+  copy_table(p->edges_stride, a.edges_stride, R);
+  copy_table(p->timestamps, a.timestamps, R);
+  copy_table(p->inputs_state, a.inputs_state, T);
+  copy_table(p->states, a.states, T);
+  copy_table(p->nodes, a.nodes, T);
+  copy_table(p->local, a.local, T);
+  a.samples_len = a.edges_len = a.layer_offsets = a.nodes_len = nullptr;
+  tchgeo_status st = make_plan(&a, p->pl, true);
+  if (st == TCHGEO_OK) st = check_args(&a, p->pl);
+  if (st != TCHGEO_OK) {
+    tchgeo_plan_destroy(p);
+    return st;
+  }
+  const Plan& pl = p->pl;
+  p->n_state = (size_t)pl.num_rows * pl.B;
+  cudaError_t e = cudaGetDevice(&p->device);
+  if (e == cudaSuccess) e = cudaMallocHost(&p->h_state, (p->n_state + 1) * 8);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->done, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    tchgeo_plan_destroy(p);
+    TCHGEO_CUDA_CHECK(e);
+  }
+  p->samples_len.assign((size_t)pl.B * T, 0);
+  p->edges_len.assign((size_t)pl.B * R, 0);
+  p->layer_offsets.assign((size_t)pl.B * R * std::max<size_t>(H, 1) * 3, 0);
+  if (pl.relabel) p->nodes_len.assign((size_t)pl.B * T, 0);
+  *out = p;
+  return TCHGEO_OK;
+}
+
+static tchgeo_status plan_enqueue(tchgeo_plan_t* p, uint64_t seed, uint32_t batch_base, cudaStream_t stream,
+                                  std::vector<cudaEvent_t>* ev) {
+  TCHGEO_REQUIRE(p != nullptr, "plan is NULL");
+  TCHGEO_REQUIRE(!p->pending, "the previous enqueue of this plan has not been collected");
+  p->a.stream = stream;
+  p->a.seed = seed;
+  p->a.batch_base = batch_base;
+  tchgeo_status st = enqueue_step(&p->a, p->pl, seed, batch_base, stream, ev);
+  if (st != TCHGEO_OK) return st;
+  // the step's only read-back: length table + error word into pinned memory, then the event collect() waits for
+  char* ws = (char*)p->a.workspace;
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(p->h_state, ws + p->pl.off_state, p->n_state * 8, cudaMemcpyDeviceToHost, stream));
+  p->h_state[p->n_state] = 0;
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(p->h_state + p->n_state, ws + p->pl.off_ctrl, 4, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaEventRecord(p->done, stream));
+  p->pending = true;
+  return TCHGEO_OK;
+}
+
+extern "C" tchgeo_status tchgeo_plan_enqueue(tchgeo_plan_t* p, uint64_t seed, uint32_t batch_base, tchgeo_stream stream) {
+  return plan_enqueue(p, seed, batch_base, (cudaStream_t)stream, nullptr);
+}
+
+extern "C" tchgeo_status tchgeo_plan_collect(tchgeo_plan_t* p) {
+  TCHGEO_REQUIRE(p != nullptr, "plan is NULL");
+  TCHGEO_REQUIRE(p->pending, "nothing to collect: call tchgeo_plan_enqueue first");
+  p->pending = false;
+  TCHGEO_CUDA_CHECK(cudaEventSynchronize(p->done));
+  decode_state(p->pl, p->h_state, p->samples_len.data(), p->edges_len.data(), p->layer_offsets.data(),
+               p->pl.relabel ? p->nodes_len.data() : nullptr);
+  return status_from_dev_err((uint32_t)p->h_state[p->n_state]);
+}
+
+extern "C" tchgeo_status tchgeo_plan_enqueue_timed(tchgeo_plan_t* p, uint64_t seed, uint32_t batch_base,
+                                                   tchgeo_stream stream, float* launch_ms, int32_t launch_ms_cap,
+                                                   int32_t* num_intervals) {
+  TCHGEO_REQUIRE(p != nullptr && launch_ms != nullptr, "NULL pointer");
+  const int n_iv = (int)p->pl.launches.size() + (p->pl.relabel ? 1 : 0);
+  if (num_intervals) *num_intervals = n_iv;
+  TCHGEO_REQUIRE(launch_ms_cap >= n_iv, "launch_ms too small: %d intervals", n_iv);
+  EventList evs;
+  tchgeo_status st = make_events(evs, (size_t)n_iv + 1);
+  if (st != TCHGEO_OK) return st;
+  st = plan_enqueue(p, seed, batch_base, (cudaStream_t)stream, &evs.ev);
+  if (st != TCHGEO_OK) return st;
+  st = tchgeo_plan_collect(p);
+  read_intervals(evs, launch_ms);
+  return st;
+}
+
+extern "C" tchgeo_status tchgeo_plan_results(const tchgeo_plan_t* p, const int64_t** samples_len, const int64_t** edges_len,
+                                             const int64_t** layer_offsets, const int64_t** nodes_len) {
+  TCHGEO_REQUIRE(p != nullptr, "plan is NULL");
+  if (samples_len) *samples_len = p->samples_len.data();
+  if (edges_len) *edges_len = p->edges_len.data();
+  if (layer_offsets) *layer_offsets = p->layer_offsets.data();
+  if (nodes_len) *nodes_len = p->pl.relabel ? p->nodes_len.data() : nullptr;
+  return TCHGEO_OK;
+}
+
+extern "C" int32_t tchgeo_plan_num_launches(const tchgeo_plan_t* p) {
+  if (!p) return 0;
+  int n = (int)p->pl.launches.size() + p->pl.relabel_kernels;
+  for (int t = 0; t < p->pl.T; ++t)
+    if (p->a.seeds_per_batch[t] > 0) ++n;  // fill_i64_kernel
+  return n;
 }
 
 extern "C" tchgeo_status tchgeo_neighbor_sampling_homogenous(

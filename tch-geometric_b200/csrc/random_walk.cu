@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "common.cuh"
+#include "graph.cuh"
 
 namespace tchgeo {
 namespace {
@@ -272,6 +273,18 @@ extern "C" tchgeo_status tchgeo_random_walk(const int64_t* row_ptrs, int64_t num
                                             int64_t* stats, int64_t* attempts_out, tchgeo_stream stream_) {
   return tchgeo_random_walk_ex(row_ptrs, num_rows, col_indices, nullptr, start, num_walks, walk_length, p, q, seed,
                                walker_base, walks, stats, attempts_out, stream_);
+}
+
+extern "C" tchgeo_status tchgeo_random_walk_graph(const tchgeo_graph_t* graph, int32_t rel, const int64_t* start,
+                                                  int64_t num_walks, int64_t walk_length, float p, float q, uint64_t seed,
+                                                  int64_t walker_base, int64_t* walks, int64_t* stats,
+                                                  int64_t* attempts_out, tchgeo_stream stream_) {
+  TCHGEO_REQUIRE(graph != nullptr && rel >= 0 && rel < graph->R, "bad graph handle / relation");
+  const tchgeo_status st = graph_ensure(const_cast<tchgeo_graph*>(graph), TCHGEO_PREPARE_INDEX_REPLICA, (cudaStream_t)stream_);
+  if (st != TCHGEO_OK) return st;
+  const size_t r = (size_t)rel;
+  return tchgeo_random_walk_ex(graph->ptrs[r], graph->num_major[r], graph->indices[r], graph->indices32[r], start, num_walks,
+                               walk_length, p, q, seed, walker_base, walks, stats, attempts_out, stream_);
 }
 
 extern "C" tchgeo_status tchgeo_random_walk_ex(const int64_t* row_ptrs, int64_t num_rows, const int64_t* col_indices,

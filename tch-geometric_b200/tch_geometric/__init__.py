@@ -9,8 +9,10 @@ libtchgeo_cuda.so and fails if it has not been built: there is no CPU fallback.
 """
 from . import _native  # noqa: F401  (loads the CUDA library, raises if missing)
 from .ops import (  # noqa: F401
+    GraphHandle,
     HeterogenousSampler,
     HomogenousSampler,
+    HostBatches,
     SampledBatches,
     clear_caches,
     csc_edge_cumsum,
@@ -30,6 +32,7 @@ from .ops import (  # noqa: F401
     to_csc,
     to_csr,
     unique_relabel,
+    unique_relabel_batched,
 )
 from .utils import (  # noqa: F401
     TEMPORAL_SAMPLE_DYNAMIC,

@@ -12,7 +12,8 @@ LIB_PATH = os.path.join(_HERE, "libtchgeo_cuda.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_INDEX, ERR_REFERENCE_PANIC, ERR_INTERNAL = range(7)
 SAMPLER_UNIFORM, SAMPLER_UNIFORM_REPLACE, SAMPLER_WEIGHTED = 0, 1, 2
-ABI_VERSION = 4
+ABI_VERSION = 5
+PREPARE_INDEX_REPLICA, PREPARE_WEIGHT_RECORDS = 1, 2
 
 c_i64, c_i32, c_u64, c_u32, c_vp, c_sz = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32,
                                           ctypes.c_void_p, ctypes.c_size_t)
@@ -23,14 +24,15 @@ class SamplingArgs(ctypes.Structure):
     _fields_ = [
         ("num_node_types", c_i32), ("num_rels", c_i32), ("num_hops", c_i32), ("sampler_kind", c_i32),
         ("rel_src", c_vp), ("rel_dst", c_vp),
-        ("col_ptrs", c_vp), ("num_cols", c_vp), ("row_indices", c_vp), ("weights", c_vp), ("row_indices32", c_vp),
-        ("weights_cumsum", c_vp),
+        ("col_ptrs", c_vp), ("num_cols", c_vp), ("row_indices", c_vp), ("weights", c_vp), ("nnz", c_vp),
+        ("graph", c_vp),
         ("fanouts", c_vp), ("rel_active", c_vp),
         ("num_batches", c_i64), ("inputs", c_vp), ("seeds_per_batch", c_vp),
         ("seed", c_u64), ("batch_base", c_u32), ("reserved0", c_u32),
         ("samples", c_vp), ("samples_stride", c_vp),
         ("rows", c_vp), ("cols", c_vp), ("edge_index", c_vp), ("edges_stride", c_vp),
         ("samples_len", c_vp), ("edges_len", c_vp), ("layer_offsets", c_vp),
+        ("nodes", c_vp), ("local", c_vp), ("nodes_len", c_vp),
         ("filter_mode", c_i32), ("filter_forward", c_i32), ("filter_window_lo", c_i64), ("filter_window_hi", c_i64),
         ("timestamps", c_vp), ("inputs_state", c_vp), ("states", c_vp),
         ("workspace", c_vp), ("workspace_bytes", c_sz), ("stream", c_vp),
@@ -71,7 +73,41 @@ def _load():
     lib.tchgeo_csc_sort_edges_workspace_bytes.argtypes = [c_i64, c_i64]
     lib.tchgeo_csc_sort_edges.restype = c_i32
     lib.tchgeo_csc_sort_edges.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]
+    lib.tchgeo_graph_create.restype = c_i32
+    lib.tchgeo_graph_create.argtypes = [c_i32, c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.tchgeo_graph_set_weights.restype = c_i32
+    lib.tchgeo_graph_set_weights.argtypes = [c_vp, c_vp]
+    lib.tchgeo_graph_set_timestamps.restype = c_i32
+    lib.tchgeo_graph_set_timestamps.argtypes = [c_vp, c_vp]
+    lib.tchgeo_graph_prepare.restype = c_i32
+    lib.tchgeo_graph_prepare.argtypes = [c_vp, c_i32, c_vp]
+    lib.tchgeo_graph_derived_bytes.restype = c_sz
+    lib.tchgeo_graph_derived_bytes.argtypes = [c_vp]
+    lib.tchgeo_graph_destroy.restype = None
+    lib.tchgeo_graph_destroy.argtypes = [c_vp]
     P = ctypes.POINTER(SamplingArgs)
+    lib.tchgeo_plan_create.restype = c_i32
+    lib.tchgeo_plan_create.argtypes = [P, c_vp]
+    lib.tchgeo_plan_enqueue.restype = c_i32
+    lib.tchgeo_plan_enqueue.argtypes = [c_vp, c_u64, c_u32, c_vp]
+    lib.tchgeo_plan_enqueue_timed.restype = c_i32
+    lib.tchgeo_plan_enqueue_timed.argtypes = [c_vp, c_u64, c_u32, c_vp, c_vp, c_i32, c_vp]
+    lib.tchgeo_plan_collect.restype = c_i32
+    lib.tchgeo_plan_collect.argtypes = [c_vp]
+    lib.tchgeo_plan_results.restype = c_i32
+    lib.tchgeo_plan_results.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.tchgeo_plan_num_launches.restype = c_i32
+    lib.tchgeo_plan_num_launches.argtypes = [c_vp]
+    lib.tchgeo_plan_destroy.restype = None
+    lib.tchgeo_plan_destroy.argtypes = [c_vp]
+    lib.tchgeo_random_walk_graph.restype = c_i32
+    lib.tchgeo_random_walk_graph.argtypes = [c_vp, c_i32, c_vp, c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_u64, c_i64,
+                                             c_vp, c_vp, c_vp, c_vp]
+    lib.tchgeo_unique_relabel_batched_workspace_bytes.restype = c_sz
+    lib.tchgeo_unique_relabel_batched_workspace_bytes.argtypes = [c_i64, c_i64, c_i32]
+    lib.tchgeo_unique_relabel_batched.restype = c_i32
+    lib.tchgeo_unique_relabel_batched.argtypes = [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz,
+                                                  c_vp, c_vp]
     lib.tchgeo_neighbor_sampling_capacity.restype = c_i32
     lib.tchgeo_neighbor_sampling_capacity.argtypes = [P, c_vp, c_vp]
     lib.tchgeo_neighbor_sampling_workspace_bytes.restype = c_sz
@@ -130,6 +166,8 @@ def _load():
                                              c_i64, c_vp, c_vp, c_vp, c_vp]
     lib.tchgeo_gather_rows.restype = c_i32
     lib.tchgeo_gather_rows.argtypes = [c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]
+    lib.tchgeo_pack_ragged.restype = c_i32
+    lib.tchgeo_pack_ragged.argtypes = [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp]
     lib.tchgeo_unique_relabel_workspace_bytes.restype = c_sz
     lib.tchgeo_unique_relabel_workspace_bytes.argtypes = [c_i64]
     lib.tchgeo_unique_relabel.restype = c_i32
@@ -146,6 +184,11 @@ EXPORTS = [
     "tchgeo_coo_to_csx", "tchgeo_csc_edge_cumsum_f64", "tchgeo_csc_sort_edges_workspace_bytes", "tchgeo_csc_sort_edges", "tchgeo_compress_indices", "tchgeo_neighbor_sampling_capacity", "tchgeo_neighbor_sampling_workspace_bytes",
     "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_timed", "tchgeo_neighbor_sampling_collect", "tchgeo_neighbor_sampling_homogenous",
     "tchgeo_serve_requests", "tchgeo_part_begin_hop", "tchgeo_part_count_hop", "tchgeo_part_scatter_hop", "tchgeo_serve_requests_rows", "tchgeo_serve_requests_rows_peer", "tchgeo_part_hop_workspace_bytes", "tchgeo_part_finish_hop", "tchgeo_status_from_error_word", "tchgeo_negative_sampling_capacity", "tchgeo_negative_sampling_workspace_bytes", "tchgeo_negative_sampling", "tchgeo_random_walk", "tchgeo_random_walk_ex", "tchgeo_tempo_random_walk", "tchgeo_gather_rows", "tchgeo_unique_relabel_workspace_bytes", "tchgeo_unique_relabel",
+    "tchgeo_unique_relabel_batched_workspace_bytes", "tchgeo_unique_relabel_batched",
+    "tchgeo_graph_create", "tchgeo_graph_set_weights", "tchgeo_graph_set_timestamps", "tchgeo_graph_prepare",
+    "tchgeo_graph_derived_bytes", "tchgeo_graph_destroy",
+    "tchgeo_plan_create", "tchgeo_plan_enqueue", "tchgeo_plan_enqueue_timed", "tchgeo_plan_collect", "tchgeo_plan_results",
+    "tchgeo_plan_num_launches", "tchgeo_plan_destroy", "tchgeo_random_walk_graph", "tchgeo_pack_ragged",
 ]
 
 

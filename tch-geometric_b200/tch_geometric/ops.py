@@ -178,74 +178,84 @@ def _extract_filter(filter, hetero: bool):
 
 
 # ---------------------------------------------------------------------------------------------
-# compressed row_indices replica (HBM layout optimisation, outputs unchanged): the sampling kernel's
-# random gathers read int32 entries, so a neighbourhood spans half as many DRAM lines.  The reference
-# API is stateless (tensors are passed on every call), so replicas are cached per tensor and
-# invalidated by the tensor's version counter.  Measured on B200 (products-shaped graph, hop 3):
-# DRAM reads 6.28 GB -> 4.86 GB per launch, 2.24 ms -> 1.88 ms.  TCHGEO_INDEX_REPLICA=0 disables it.
+# graph handles (tchgeo_graph_t).  The derived arrays of the fast paths -- the int32 replica of the indices (random
+# gathers span half as many DRAM lines; hop 3 on B200: DRAM reads 6.28 -> 4.86 GB, 2.24 -> 1.88 ms) and the
+# (weight, prefix sum) records of the weighted sampler -- are built and owned by the library behind the handle.  The
+# reference API is stateless (tensors are passed on every call), so this mirror keeps one handle per set of graph
+# tensors, found again by storage address + version counter.  TCHGEO_INDEX_REPLICA=0 / TCHGEO_WEIGHT_CUMSUM=0 (read by
+# the library) disable the derived arrays.
 # ---------------------------------------------------------------------------------------------
-_REPLICA_CACHE_MAX = 16
+_GRAPH_CACHE_MAX = 16
 
 
-class _DerivedCache:
-    """Derived device arrays (int32 replica, weight prefix sums) keyed by their source tensors' storage.  An entry
-    keeps a reference to its source tensors: the memory cannot be freed and handed to a different tensor at the same
-    address while the entry lives, so a hit can never be stale (in-place edits bump `_version` and miss).  LRU,
-    at most _REPLICA_CACHE_MAX entries; `clear_caches()` drops everything (and releases the sources)."""
+class GraphHandle:
+    """Owns a tchgeo_graph_t over R relations' (ptrs, indices[, weights]) tensors and keeps those tensors alive: the
+    memory cannot be freed and handed to a different tensor at the same address while the handle lives."""
+
+    def __init__(self, ptrs, indices, weights=None):
+        R = len(ptrs)
+        self._tensors = (list(ptrs), list(indices), list(weights) if weights is not None else None)
+        tab = lambda ts: np.array([(t.data_ptr() if t is not None else 0) for t in ts], dtype=np.uint64)
+        num_major = np.array([(max(t.numel() - 1, 0) if t is not None else 0) for t in ptrs], dtype=np.int64)
+        nnz = np.array([(t.numel() if t is not None else 0) for t in indices], dtype=np.int64)
+        h = ctypes.c_void_p(0)
+        p_tab, i_tab = tab(ptrs), tab(indices)
+        N.check(N.lib.tchgeo_graph_create(R, p_tab.ctypes.data, num_major.ctypes.data, i_tab.ctypes.data, nnz.ctypes.data,
+                                          ctypes.addressof(h)))
+        self.handle, self.num_rels = h, R
+        if weights is not None:
+            w_tab = tab(weights)
+            N.check(N.lib.tchgeo_graph_set_weights(self.handle, w_tab.ctypes.data))
+
+    def prepare(self, what, device):
+        with torch.cuda.device(device):
+            N.check(N.lib.tchgeo_graph_prepare(self.handle, int(what), _stream(device)))
+
+    @property
+    def derived_bytes(self):
+        return int(N.lib.tchgeo_graph_derived_bytes(self.handle))
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h:
+            try:
+                N.lib.tchgeo_graph_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
+
+
+class _GraphCache:
+    """LRU of GraphHandles keyed by their source tensors' storage; an in-place edit bumps `_version` and misses."""
 
     def __init__(self):
         self._d = {}
 
     @staticmethod
-    def _key(srcs):
-        return tuple((t.data_ptr(), t.numel(), t.dtype, t.device.index) for t in srcs)
+    def _key(groups):
+        return tuple(None if g is None else tuple(None if t is None else (t.data_ptr(), t.numel(), t.device.index, t._version)
+                                                  for t in g) for g in groups)
 
-    def get(self, srcs):
-        k = self._key(srcs)
-        hit = self._d.get(k)
-        if hit is not None and hit[0] == tuple(t._version for t in srcs):
-            self._d[k] = self._d.pop(k)  # most recently used last
-            return hit[2]
-        return None
-
-    def put(self, srcs, value):
-        k = self._key(srcs)
-        self._d.pop(k, None)
-        while len(self._d) >= _REPLICA_CACHE_MAX:
-            self._d.pop(next(iter(self._d)))
-        self._d[k] = (tuple(t._version for t in srcs), tuple(srcs), value)
+    def get(self, ptrs, indices, weights=None):
+        k = self._key((ptrs, indices, weights))
+        hit = self._d.pop(k, None)
+        if hit is None:
+            while len(self._d) >= _GRAPH_CACHE_MAX:
+                self._d.pop(next(iter(self._d)))
+            hit = GraphHandle(ptrs, indices, weights)
+        self._d[k] = hit  # most recently used last
+        return hit
 
     def clear(self):
         self._d.clear()
 
 
-_MISSING = object()
-_replica_cache = _DerivedCache()
-_cumsum_cache = _DerivedCache()
+_graph_cache = _GraphCache()
 
 
 def clear_caches() -> None:
-    """Drop the cached int32 index replicas and weight prefix sums (they keep their source tensors alive)."""
-    _replica_cache.clear()
-    _cumsum_cache.clear()
-
-
-def _compressed_indices(t: Optional[Tensor]) -> Optional[Tensor]:
-    if t is None or t.numel() == 0 or os.environ.get("TCHGEO_INDEX_REPLICA", "1") == "0":
-        return None
-    hit = _replica_cache.get((t,))
-    if hit is not None:
-        return None if hit is _MISSING else hit
-    out = torch.empty(t.numel(), dtype=torch.int32, device=t.device)
-    scratch = torch.empty(1, dtype=torch.int32, device=t.device)
-    with torch.cuda.device(t.device):
-        st = N.lib.tchgeo_compress_indices(_ptr(t), t.numel(), _ptr(out), _ptr(scratch), _stream(t.device))
-    if st == N.ERR_INDEX:
-        _replica_cache.put((t,), _MISSING)
-        return None  # ids beyond int32 (or negative): sample from the i64 array; the kernel reports bad ids
-    N.check(st)
-    _replica_cache.put((t,), out)
-    return out
+    """Drop the cached graph handles: frees their derived device arrays and releases the source tensors.  Call it when
+    switching graphs (a handle pins its tensors, so a dropped graph is not freed while its handle is cached)."""
+    _graph_cache.clear()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -281,32 +291,27 @@ def csc_sort_edges(col_ptrs: Tensor, perm: Tensor, row_weights: Tensor, descendi
     return out
 
 
-def _weights_cumsum(col_ptrs: Tensor, weights: Optional[Tensor]) -> Optional[Tensor]:
-    """Serial per-column prefix sums of the sampler weights (= the reference's w_sum sequence), cached per
-    (col_ptrs, weights) pair like the int32 replica.  TCHGEO_WEIGHT_CUMSUM=0 disables it (the kernel then scans
-    the weights with warp shuffles, which rounds differently for weights that are not exactly summable)."""
-    if weights is None or weights.numel() == 0 or os.environ.get("TCHGEO_WEIGHT_CUMSUM", "1") == "0":
-        return None
-    hit = _cumsum_cache.get((col_ptrs, weights))
-    if hit is not None:
-        return hit
-    out = weights.clone()
-    csc_edge_cumsum(col_ptrs, out)
-    _cumsum_cache.put((col_ptrs, weights), out)
-    return out
-
-
 # ---------------------------------------------------------------------------------------------
 # generic driver over tchgeo_neighbor_sampling
 # ---------------------------------------------------------------------------------------------
 class _Call:
-    """Owns the host arrays, output tensors and workspace of one tchgeo_neighbor_sampling call."""
+    """One tchgeo_plan_t: the argument tables, the output tensors and the workspace it borrows.  The plan handle keeps a
+    deep copy of the arguments, the launch plan and the pinned length table behind the ABI; this class only allocates
+    device memory through torch and hands pointers over."""
 
     def __init__(self, device, rel_src, rel_dst, col_ptrs, row_indices, weights, fanouts, rel_active, inputs, seeds,
-                 num_batches, num_hops, sampler_kind, seed, batch_base=0, filt=None):
+                 num_batches, num_hops, sampler_kind, seed, batch_base=0, filt=None, relabel=False):
         """filt: None | (abi_mode, forward, (lo, hi), [timestamps per relation], [inputs_state per node type])"""
         T, R, H, B = len(seeds), len(rel_src), num_hops, num_batches
         self.T, self.R, self.H, self.B, self.device = T, R, H, B, device
+        self.plan = None
+        # the reference slices weights / timestamps with the column's range and panics when they are short
+        # (EdgeAttr::get, src/data/graph.rs:103-120); the kernels check every column against nnz as well
+        for r in range(R):
+            nnz = row_indices[r].numel() if row_indices[r] is not None else 0
+            for name, ts in (("weights", weights), ("timestamps", filt[3] if filt is not None else None)):
+                if ts is not None and ts[r] is not None and ts[r].numel() < nnz:
+                    raise N.ReferencePanic(f"{name} of relation {r} has {ts[r].numel()} entries, row_indices {nnz}")
         a = N.SamplingArgs()
         self.args = a
         k = self._keep = []
@@ -325,13 +330,8 @@ class _Call:
         a.num_node_types, a.num_rels, a.num_hops, a.sampler_kind = T, R, H, sampler_kind
         a.rel_src = host(rel_src, np.int32).ctypes.data
         a.rel_dst = host(rel_dst, np.int32).ctypes.data
-        a.col_ptrs = ptr_table(col_ptrs).ctypes.data
-        a.num_cols = host([(t.numel() - 1 if t is not None else 0) for t in col_ptrs], np.int64).ctypes.data
-        a.row_indices = ptr_table(row_indices).ctypes.data
-        a.weights = ptr_table(weights).ctypes.data if weights is not None else None
-        a.row_indices32 = ptr_table([_compressed_indices(t) for t in row_indices]).ctypes.data
-        if weights is not None and filt is None:
-            a.weights_cumsum = ptr_table([_weights_cumsum(c, w) for c, w in zip(col_ptrs, weights)]).ctypes.data
+        self.graph = _graph_cache.get(col_ptrs, row_indices, weights)
+        a.graph = self.graph.handle
         a.fanouts = host(fanouts, np.int64).ctypes.data
         a.rel_active = host(rel_active, np.uint8).ctypes.data
         a.num_batches = B
@@ -355,6 +355,12 @@ class _Call:
         a.cols = ptr_table(self.cols).ctypes.data
         a.edge_index = ptr_table(self.eidx).ctypes.data
         a.edges_stride = cap_e.ctypes.data
+        self.nodes = self.local = None
+        if relabel:
+            self.nodes = [torch.empty((B, int(c)), **i64) for c in cap_n]
+            self.local = [torch.empty((B, int(c)), **i64) for c in cap_n]
+            a.nodes = ptr_table(self.nodes).ctypes.data
+            a.local = ptr_table(self.local).ctypes.data
         self.states = None
         if filt is not None:
             a.filter_mode, a.filter_forward = int(filt[0]), int(filt[1])
@@ -363,48 +369,59 @@ class _Call:
             a.inputs_state = ptr_table(filt[4]).ctypes.data
             self.states = [torch.empty((B, int(c)), **i64) for c in cap_n]
             a.states = ptr_table(self.states).ctypes.data
-        self.samples_len = np.zeros((B, T), dtype=np.int64)
-        self.edges_len = np.zeros((B, R), dtype=np.int64)
-        self.layer_offsets = np.zeros((B, R, max(H, 1), 3), dtype=np.int64)
-        a.samples_len = self.samples_len.ctypes.data
-        a.edges_len = self.edges_len.ctypes.data
-        a.layer_offsets = self.layer_offsets.ctypes.data
-        ws_bytes = N.lib.tchgeo_neighbor_sampling_workspace_bytes(ctypes.byref(a))
-        self.workspace = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=device)
-        a.workspace = self.workspace.data_ptr()
-        a.workspace_bytes = ws_bytes
+        with torch.cuda.device(device):
+            a.stream = torch.cuda.current_stream(device).cuda_stream
+            ws_bytes = N.lib.tchgeo_neighbor_sampling_workspace_bytes(ctypes.byref(a))  # builds the derived arrays
+            if ws_bytes == 0:
+                raise ValueError(N.last_error() or "cannot plan this call")
+            self.workspace = torch.empty(int(ws_bytes), dtype=torch.uint8, device=device)
+            a.workspace = self.workspace.data_ptr()
+            a.workspace_bytes = ws_bytes
+            h = ctypes.c_void_p(0)
+            N.check(N.lib.tchgeo_plan_create(ctypes.byref(a), ctypes.addressof(h)))
+        self.plan = h
+        self.num_launches = int(N.lib.tchgeo_plan_num_launches(h))
+        # results live in host arrays owned by the plan (rewritten by every collect)
+        ptrs = [ctypes.POINTER(ctypes.c_int64)() for _ in range(4)]
+        N.check(N.lib.tchgeo_plan_results(h, *[ctypes.byref(x) for x in ptrs]))
+        view = lambda ptr, shape: np.ctypeslib.as_array(ptr, shape=shape)
+        self.samples_len = view(ptrs[0], (B, T))
+        self.edges_len = view(ptrs[1], (B, R))
+        self.layer_offsets = view(ptrs[2], (B, R, max(H, 1), 3))
+        self.nodes_len = view(ptrs[3], (B, T)) if relabel else None
+
+    def __del__(self):
+        h, self.plan = getattr(self, "plan", None), None
+        if h:
+            try:
+                N.lib.tchgeo_plan_destroy(h)
+            except Exception:  # noqa: BLE001  (interpreter shutdown)
+                pass
 
     def run(self, seed=None, batch_base=None, timed=False, collect=True):
         """collect=False only enqueues the launches on the current stream (no host synchronisation); `collect()`
-        reads the lengths and layer offsets back later.  Nothing else may use this call's buffers in between."""
+        waits for them and decodes lengths and layer offsets.  Nothing else may use this call's buffers in between."""
         a = self.args
         if seed is not None:
             a.seed = seed
         if batch_base is not None:
             a.batch_base = batch_base
         with torch.cuda.device(self.device):
-            a.stream = torch.cuda.current_stream(self.device).cuda_stream
-            if not collect:
-                keep = (a.samples_len, a.edges_len, a.layer_offsets)
-                a.samples_len = a.edges_len = a.layer_offsets = None  # tchgeo_neighbor_sampling then does not read back
-                try:
-                    N.check(N.lib.tchgeo_neighbor_sampling(ctypes.byref(a)))
-                finally:
-                    a.samples_len, a.edges_len, a.layer_offsets = keep
-            elif timed:
-                ms = np.zeros(max(self.R * max(self.H, 1), 1), dtype=np.float32)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            if timed:
+                ms = np.zeros(max(self.R * max(self.H, 1) + 1, 1), dtype=np.float32)
                 n = ctypes.c_int32(0)
-                N.check(N.lib.tchgeo_neighbor_sampling_timed(ctypes.byref(a), ms.ctypes.data, ms.size, ctypes.addressof(n)))
+                N.check(N.lib.tchgeo_plan_enqueue_timed(self.plan, a.seed, a.batch_base, stream, ms.ctypes.data, ms.size,
+                                                        ctypes.addressof(n)))
                 self.launch_ms = ms[:n.value].copy()
-            else:
-                N.check(N.lib.tchgeo_neighbor_sampling(ctypes.byref(a)))
-        return self
+                return self
+            N.check(N.lib.tchgeo_plan_enqueue(self.plan, a.seed, a.batch_base, stream))
+        return self.collect() if collect else self
 
     def collect(self):
-        """Second half of run(collect=False): one D2H copy of the length table on the stream the launches went to,
-        a synchronisation of that stream only, and the device-side error word turned into an exception."""
-        with torch.cuda.device(self.device):
-            N.check(N.lib.tchgeo_neighbor_sampling_collect(ctypes.byref(self.args)))
+        """Second half of run(collect=False): waits for the event recorded behind the step's launches (not for the whole
+        stream) and turns the device-side error word into an exception."""
+        N.check(N.lib.tchgeo_plan_collect(self.plan))
         return self
 
 
@@ -435,7 +452,7 @@ def neighbor_sampling_homogenous(
     return call.samples[0][0, :ns], call.rows[0][0, :ne], call.cols[0][0, :ne], call.eidx[0][0, :ne], lo
 
 
-def _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, filter, batched):
+def _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, filter, batched, relabel=False):
     flt = _extract_filter(filter, hetero=False)
     _check(col_ptrs, torch.int64, "col_ptrs")
     dev = col_ptrs.device
@@ -463,7 +480,7 @@ def _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, filt
             raise N.ReferencePanic("inputs_state must have one entry per input")
         filt = (mode, forward, window, [ts], [st])
     return _Call(dev, [0], [0], [col_ptrs], [row_indices], [w] if w is not None else None, fan, [1], [inputs], [S],
-                 max(B, 1), len(fan), kind, 0, filt=filt)
+                 max(B, 1), len(fan), kind, 0, filt=filt, relabel=relabel)
 
 
 class SampledBatches:
@@ -476,6 +493,10 @@ class SampledBatches:
         self.samples_len = call.samples_len[:, 0]
         self.edges_len = call.edges_len[:, 0]
         self.layer_offsets = call.layer_offsets[:, 0]
+        # dedup + insertion-order relabel stage (K7), when the call asked for it
+        self.nodes = call.nodes[0] if call.nodes is not None else None
+        self.local = call.local[0] if call.local is not None else None
+        self.nodes_len = call.nodes_len[:, 0] if call.nodes_len is not None else None
 
     def __len__(self):
         return self._call.B
@@ -485,15 +506,102 @@ class SampledBatches:
         lo = [tuple(int(x) for x in self.layer_offsets[b, h]) for h in range(self._call.H)]
         return self.samples[b, :ns], self.rows[b, :ne], self.cols[b, :ne], self.edge_index[b, :ne], lo
 
+    def to_host(self, host: "HostBatches", first: int = 0, count: Optional[int] = None) -> int:
+        """Pack the used prefixes of batches [first, first + count) on the device (tchgeo_pack_ragged) and copy them to
+        the pinned buffers of `host` on the current stream: three D2H copies of exactly the used bytes (`rows` is not
+        copied: it is arange(S, S + E), HostBatches.batch serves it from a cached host arange).  Asynchronous; returns
+        the number of bytes that travel."""
+        call = self._call
+        count = call.B - first if count is None else int(count)
+        if count > host.B:
+            raise ValueError("HostBatches is smaller than the group of batches")
+        ns, ne = self.samples_len[first:first + count], self.edges_len[first:first + count]
+        n_off = np.concatenate([[0], np.cumsum(ns)])
+        e_off = np.concatenate([[0], np.cumsum(ne)])
+        if n_off[-1] > host.cap_n or e_off[-1] > host.cap_e:
+            raise MemoryError("HostBatches too small for this group: create it with a larger `fill`")
+        dev = call.device
+        h = host._h_lens
+        h[:count].copy_(torch.from_numpy(np.ascontiguousarray(ns)))
+        h[host.B:host.B + count].copy_(torch.from_numpy(np.ascontiguousarray(ne)))
+        with torch.cuda.device(dev):
+            stream = _stream(dev)
+            host._d_lens.copy_(h, non_blocking=True)
+            for src, lens_at, dst, off_at, cap in (
+                    (self.samples, 0, host._d_samples, 0, call.cap_n[0]),
+                    (self.cols, host.B, host._d_cols, host.B + 1, call.cap_e[0]),
+                    (self.edge_index, host.B, host._d_eidx, host.B + 1, call.cap_e[0])):
+                N.check(N.lib.tchgeo_pack_ragged(_ptr(src[first]), src.shape[1], _ptr(host._d_lens[lens_at:]), 1, count,
+                                                 int(cap), _ptr(dst), _ptr(host._d_off[off_at:]), stream))
+            nt, et = int(n_off[-1]), int(e_off[-1])
+            host.samples[:nt].copy_(host._d_samples[:nt], non_blocking=True)
+            host.cols[:et].copy_(host._d_cols[:et], non_blocking=True)
+            host.edge_index[:et].copy_(host._d_eidx[:et], non_blocking=True)
+        host.n_off, host.e_off = n_off, e_off
+        host.nbytes = 8 * (nt + 2 * et)
+        return host.nbytes
+
+    def relabeled(self, b):
+        """-> (nodes, local) of batch b: nodes = seeds ++ every other id of samples at its first appearance,
+        local[i] = index into nodes of samples[i] (negative_sampling.rs:20-47 semantic); the relabelled edges are
+        (local[rows], local[cols])."""
+        if self.nodes is None:
+            raise ValueError("the sampler was created without relabel=True")
+        return self.nodes[b, :int(self.nodes_len[b])], self.local[b, :int(self.samples_len[b])]
+
+
+_host_arange_cache = {}
+
+
+def host_arange(n: int) -> Tensor:
+    """A cached host arange(n) (int64): `rows` of a homogeneous result is arange(S, S + E) for every batch
+    (neighbor_sampling.rs:210-218: every sampled edge appends exactly one node), so the host serves it from a view of
+    this instead of copying it back from the device."""
+    t = _host_arange_cache.get("t")
+    if t is None or t.numel() < n:
+        t = torch.arange(max(int(n), 1 << 20), dtype=torch.int64)
+        _host_arange_cache["t"] = t
+    return t
+
+
+class HostBatches:
+    """Pinned host landing zone (+ its device staging buffers) for `SampledBatches.to_host`: the used prefixes of
+    `samples`, `cols` and `edge_index` of a group of batches arrive packed back to back, one D2H copy per tensor.
+    `fill` = fraction of the worst-case capacity to provide (sampled trees typically use about 0.65 of it)."""
+
+    def __init__(self, num_batches: int, cap_samples: int, cap_edges: int, num_seeds: int, device, fill: float = 0.8):
+        self.B, self.S, self.device = int(num_batches), int(num_seeds), device
+        self.cap_n = int(num_batches * cap_samples * fill) + 1
+        self.cap_e = int(num_batches * cap_edges * fill) + 1
+        host = lambda n: torch.empty(n, dtype=torch.int64).pin_memory()
+        devb = lambda n: torch.empty(n, dtype=torch.int64, device=device)
+        self.samples, self.cols, self.edge_index = host(self.cap_n), host(self.cap_e), host(self.cap_e)
+        self._d_samples, self._d_cols, self._d_eidx = devb(self.cap_n), devb(self.cap_e), devb(self.cap_e)
+        self._d_lens = devb(2 * self.B)
+        self._d_off = devb(2 * (self.B + 1))
+        self._h_lens = host(2 * self.B)
+        self.n_off = self.e_off = None       # host offsets [count + 1] of the last to_host
+        self.nbytes = 0
+
+    def batch(self, i):
+        """(samples, rows, cols, edge_index) of the i-th batch of the last transfer, as host views (valid once the
+        stream the transfer went to has been synchronised)"""
+        n0, n1, e0, e1 = int(self.n_off[i]), int(self.n_off[i + 1]), int(self.e_off[i]), int(self.e_off[i + 1])
+        rows = host_arange(self.S + (e1 - e0))[self.S:self.S + (e1 - e0)]
+        return self.samples[n0:n1], rows, self.cols[e0:e1], self.edge_index[e0:e1]
+
 
 class HomogenousSampler:
     """Reusable plan for repeated batched sampling over one graph (extension; not in the reference).
     Output buffers and workspace are allocated once; `sample(inputs)` enqueues B batches in H launches."""
 
-    def __init__(self, col_ptrs, row_indices, num_batches, seeds_per_batch, num_neighbors, sampler=None):
+    def __init__(self, col_ptrs, row_indices, num_batches, seeds_per_batch, num_neighbors, sampler=None, relabel=False):
+        """relabel=True adds the dedup + insertion-order relabel stage to every step (results: SampledBatches.nodes /
+        .local / .nodes_len, `relabeled(b)`); the reference-layout outputs are unchanged."""
         dev = col_ptrs.device
         self._inputs = torch.zeros((num_batches, seeds_per_batch), dtype=torch.int64, device=dev)
-        self._call = _homogenous_call(col_ptrs, row_indices, self._inputs, num_neighbors, sampler, None, batched=True)
+        self._call = _homogenous_call(col_ptrs, row_indices, self._inputs, num_neighbors, sampler, None, batched=True,
+                                      relabel=relabel)
 
     def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0,
                timed: bool = False) -> SampledBatches:
@@ -528,11 +636,17 @@ class HomogenousSampler:
         res.launch_ms = None
         return res
 
+    @property
+    def num_launches(self):
+        """kernel launches of one step (hop kernels, the seed-length fill, the relabel stage's kernels)"""
+        return self._call.num_launches
+
 
 def neighbor_sampling_homogenous_batched(col_ptrs, row_indices, inputs, num_neighbors, sampler=None,
-                                         seed: Optional[int] = None, batch_base: int = 0) -> SampledBatches:
+                                         seed: Optional[int] = None, batch_base: int = 0,
+                                         relabel: bool = False) -> SampledBatches:
     """Extension: inputs [B, S] -> B independent neighbor_sampling_homogenous results in one call."""
-    call = _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, None, batched=True)
+    call = _homogenous_call(col_ptrs, row_indices, inputs, num_neighbors, sampler, None, batched=True, relabel=relabel)
     call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base)
     return SampledBatches(call)
 
@@ -543,7 +657,7 @@ def rel_key(edge_type) -> str:
 
 
 def _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, inputs, num_neighbors, num_hops, sampler,
-                       filter, num_batches=None):
+                       filter, num_batches=None, relabel=False):
     """Argument checking + plan for the heterogeneous sampler.  inputs[t]: [S_t] (single call) or
     [B, S_t] when num_batches is given."""
     flt = _extract_filter(filter, hetero=True)
@@ -613,7 +727,7 @@ def _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, inputs, nu
         filt = (mode, forward, window, ts, st)
     call = _Call(dev, [tix[e[0]] for e in edge_types], [tix[e[2]] for e in edge_types], cp, ri,
                  ws if kind == N.SAMPLER_WEIGHTED else None, fan[:, :num_hops].reshape(-1) if num_hops > 0 else [],
-                 active, inp, seeds, B, num_hops, kind, 0, filt=filt)
+                 active, inp, seeds, B, num_hops, kind, 0, filt=filt, relabel=relabel)
     call.meta = (node_types, rels, [r in col_ptrs for r in rels], active, num_hops)
     call.seed_inputs = inp
     return call
@@ -658,11 +772,11 @@ class HeterogenousSampler:
     independent neighbor_sampling_heterogenous calls with one launch per (hop, relation)."""
 
     def __init__(self, node_types, edge_types, col_ptrs, row_indices, num_batches, seeds_per_batch: Dict[str, int],
-                 num_neighbors, num_hops, sampler=None):
+                 num_neighbors, num_hops, sampler=None, relabel=False):
         dev = next(iter(col_ptrs.values())).device
         proto = {t: torch.zeros((num_batches, int(s)), dtype=torch.int64, device=dev) for t, s in seeds_per_batch.items()}
         self._call = _heterogenous_call(node_types, edge_types, col_ptrs, row_indices, proto, num_neighbors, num_hops,
-                                        sampler, None, num_batches=num_batches)
+                                        sampler, None, num_batches=num_batches, relabel=relabel)
         self._proto = proto
         self.num_batches = num_batches
 
@@ -693,6 +807,18 @@ class HeterogenousSampler:
     def batch(self, b):
         return _hetero_batch(self._call, b)
 
+    def relabeled(self, b):
+        """-> {node_type: (nodes, local)} of batch b (K7 per node type; needs relabel=True)"""
+        c = self._call
+        if c.nodes is None:
+            raise ValueError("the sampler was created without relabel=True")
+        return {t: (c.nodes[i][b, :int(c.nodes_len[b, i])], c.local[i][b, :int(c.samples_len[b, i])])
+                for i, t in enumerate(c.meta[0])}
+
+    @property
+    def num_launches(self):
+        return self._call.num_launches
+
 
 # ---------------------------------------------------------------------------------------------
 # random_walk (python.rs:583-608 -> random_walk.rs:10-75)
@@ -707,11 +833,11 @@ def random_walk(row_ptrs: Tensor, col_indices: Tensor, start: Tensor, walk_lengt
     walks = torch.empty((S, walk_length + 1), dtype=torch.int64, device=dev)
     stats = torch.empty(2, dtype=torch.int64, device=dev)
     attempts = ctypes.c_int64(0)
+    graph = _graph_cache.get([row_ptrs], [col_indices])   # owns the int32 replica of col_indices
     with torch.cuda.device(dev):
-        st = N.lib.tchgeo_random_walk_ex(_ptr(row_ptrs), row_ptrs.numel() - 1, _ptr(col_indices),
-                                         _ptr(_compressed_indices(col_indices)), _ptr(start), S, int(walk_length),
-                                         float(p), float(q), _rng_get() if seed is None else seed, int(walker_base),
-                                         _ptr(walks), _ptr(stats), ctypes.addressof(attempts), _stream(dev))
+        st = N.lib.tchgeo_random_walk_graph(graph.handle, 0, _ptr(start), S, int(walk_length), float(p), float(q),
+                                            _rng_get() if seed is None else seed, int(walker_base), _ptr(walks),
+                                            _ptr(stats), ctypes.addressof(attempts), _stream(dev))
     N.check(st)
     return (walks, attempts.value) if return_attempts else walks
 
@@ -890,3 +1016,26 @@ def unique_relabel(samples: Tensor, num_seeds: int) -> Tuple[Tensor, Tensor]:
                                          ctypes.addressof(num), _ptr(ws), ws_bytes, _stream(dev))
     N.check(st)
     return nodes[:num.value], local
+
+
+def unique_relabel_batched(samples: Tensor, lens: Tensor, num_seeds: int, key32: bool = False
+                           ) -> Tuple[Tensor, Tensor, Tensor]:
+    """B trees in padded rows: samples [B, stride], lens [B] (device) -> (nodes [B, stride], local [B, stride],
+    nodes_len [B]).  The stage HomogenousSampler(relabel=True) runs after the hops, exposed on its own."""
+    _check(samples, torch.int64, "samples")
+    dev = samples.device
+    _check(lens, torch.int64, "lens", dev)
+    if samples.dim() != 2 or lens.numel() != samples.shape[0]:
+        raise ValueError("samples must be [B, stride] and lens [B]")
+    B, stride = samples.shape
+    nodes, local = torch.empty_like(samples), torch.empty_like(samples)
+    nodes_len = torch.zeros(B, dtype=torch.int64, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = N.lib.tchgeo_unique_relabel_batched_workspace_bytes(B, stride, 1 if key32 else 0)
+    ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib.tchgeo_unique_relabel_batched(_ptr(samples), stride, _ptr(lens), B, int(num_seeds), stride,
+                                                    1 if key32 else 0, _ptr(nodes), _ptr(local), _ptr(nodes_len), _ptr(ws),
+                                                    ws_bytes, _ptr(err), _stream(dev)))
+    N.check(N.lib.tchgeo_status_from_error_word(int(err.item()) & 0xFFFFFFFF))
+    return nodes, local, nodes_len

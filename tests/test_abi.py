@@ -27,7 +27,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 34
+    assert len(syms) == 51
     for s in ("tchgeo_coo_to_csx", "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_homogenous",
               "tchgeo_random_walk", "tchgeo_unique_relabel", "tchgeo_ind2ptr", "tchgeo_last_error"):
         assert s in syms
@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(native):
     for s in declared_symbols():
         assert hasattr(lib, s), s
     assert sorted(native.EXPORTS) == declared_symbols()
-    assert lib.tchgeo_abi_version() == native.ABI_VERSION == 4
+    assert lib.tchgeo_abi_version() == native.ABI_VERSION == 5
 
 
 def test_library_is_sm100a_native(native):

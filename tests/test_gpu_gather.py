@@ -53,3 +53,27 @@ def test_sampler_output_feeds_the_gather(thg, fakedataset):
     orig_edges = thg.gather_rows(perm, eidx)       # positions in the caller's edge_index (quirk Q5)
     e = torch.from_numpy(ei).cuda()
     assert torch.equal(e[0][orig_edges], samples[rows]) and torch.equal(e[1][orig_edges], samples[cols])
+
+
+def test_packed_host_transfer_of_sampled_batches(thg):
+    """SampledBatches.to_host: the packed D2H path of the end-to-end benchmark returns exactly the per-batch results
+    (rows comes from the cached host arange)."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "fakedataset.npz"))
+    ei, n = torch.as_tensor(d["edge_index"]).cuda(), int(d["num_nodes"])
+    ptrs, idx, _ = thg.to_csc(ei, n)
+    B, S = 7, 33
+    seeds = torch.randint(0, n, (B, S), device="cuda")
+    plan = thg.HomogenousSampler(ptrs, idx, B, S, [6, 4, 2])
+    res = plan.sample(seeds, seed=3)
+    call = plan._call
+    host = thg.HostBatches(4, int(call.cap_n[0]), int(call.cap_e[0]), S, seeds.device, fill=1.0)
+    for first, count in ((0, 4), (4, 3)):
+        nbytes = res.to_host(host, first, count)
+        torch.cuda.synchronize()
+        assert nbytes == 8 * int(res.samples_len[first:first + count].sum() + 2 * res.edges_len[first:first + count].sum())
+        for i in range(count):
+            want = res.batch(first + i)
+            got = host.batch(i)
+            for g, w in zip(got, want[:4]):
+                assert torch.equal(g, w.cpu())

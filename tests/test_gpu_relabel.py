@@ -39,3 +39,88 @@ def test_sampled_trees(thg, fakedataset, fan):
         # relabeled edges reference the deduplicated node list consistently
         assert torch.equal(nodes[local], samples)
         assert torch.equal(nodes[local[rows]], idx[eidx])
+
+
+def _check_tree(samples, n, num_seeds, nodes, local, nodes_len):
+    wn, wl = O.unique_relabel(samples[:n], num_seeds)
+    assert nodes_len == wn.size
+    assert (nodes[:nodes_len] == wn).all() and (local[:n] == wl).all()
+
+
+@pytest.mark.parametrize("key32", [True, False])
+def test_batched_stage_ragged_trees(thg, key32):
+    """tchgeo_unique_relabel_batched on padded rows of different lengths: empty, seeds only, duplicated seeds,
+    one tile, several tiles -- each tree bit-exact against the serial oracle."""
+    rng = np.random.default_rng(5)
+    S, stride = 8, 5000
+    lens = np.array([8, 8, 9, 1024, 1025, 4999, 5000, 2048, 8, 3000], dtype=np.int64)
+    samples = rng.integers(0, 700, (lens.size, stride))          # few distinct ids: long duplicate chains
+    samples[1, :8] = [3, 3, 9, 3, 9, 1, 1, 3]                    # duplicated seeds keep all copies, map to the last one
+    samples[5, :8] = 42
+    if not key32:
+        samples[6] += 1 << 40                                     # ids beyond 32 bits need the 64-bit slots
+    nodes, local, nlen = thg.unique_relabel_batched(dev(samples), dev(lens), S, key32=key32)
+    nodes, local, nlen = nodes.cpu().numpy(), local.cpu().numpy(), nlen.cpu().numpy()
+    for b in range(lens.size):
+        _check_tree(samples[b], int(lens[b]), S, nodes[b], local[b], int(nlen[b]))
+
+
+def test_batched_stage_rejects_ids_beyond_32_bits_in_key32_mode(thg):
+    samples = np.arange(64, dtype=np.int64).reshape(2, 32)
+    samples[1, 5] = (1 << 32) + 7
+    with pytest.raises(thg.ReferencePanic):
+        thg.unique_relabel_batched(dev(samples), dev([32, 32]), 4, key32=True)
+
+
+def test_sampler_with_relabel_products_size(thg):
+    """The stage inside the plan (HomogenousSampler(relabel=True)) on products-size trees (~0.6 M ids per batch, 1024
+    seeds, several L2 waves): reference-layout outputs unchanged, nodes / local bit-exact against the oracle."""
+    from tools import synth
+    ei, n = synth.products_like(torch.device("cuda", 0))
+    ptrs, idx, _ = thg.to_csc(ei, n)
+    del ei
+    B, S, fan = 12, 1024, [15, 10, 5]
+    seeds = synth.seed_batches(n, B, S)
+    seeds[3, 100:200] = seeds[3, :100]                            # duplicated seeds
+    plain = thg.HomogenousSampler(ptrs, idx, B, S, fan).sample(dev(seeds), seed=11)
+    plan = thg.HomogenousSampler(ptrs, idx, B, S, fan, relabel=True)
+    res = plan.sample(dev(seeds), seed=11)
+    assert (res.samples_len == plain.samples_len).all() and (res.edges_len == plain.edges_len).all()
+    for b in (0, 3, B - 1):
+        for g, w in zip(res.batch(b)[:4], plain.batch(b)[:4]):
+            assert torch.equal(g, w)
+        ns = int(res.samples_len[b])
+        nodes, local = res.relabeled(b)
+        _check_tree(res.samples[b].cpu().numpy(), ns, S, nodes.cpu().numpy(), local.cpu().numpy(), nodes.numel())
+        samples, rows, cols, eidx, _ = res.batch(b)
+        assert torch.equal(nodes[local], samples)
+        assert torch.equal(nodes[local[rows]], idx[eidx])         # relabelled edge endpoints are the sampled CSC entries
+        assert nodes.numel() == torch.unique(samples[S:]).numel() + S - int(
+            torch.isin(torch.unique(samples[S:]), samples[:S]).sum().item())
+    # the async pair gives the same result
+    plan.sample_async(dev(seeds), seed=11)
+    again = plan.result()
+    assert (again.nodes_len == res.nodes_len).all()
+    thg.clear_caches()
+
+
+def test_hetero_sampler_with_relabel(thg, fakehetero):
+    """K7 per node type: the batched heterogeneous plan relabels every type's samples vector."""
+    counts, edges = fakehetero
+    node_types, edge_types = list(counts), list(edges)
+    cp, ri = {}, {}
+    for et, e in edges.items():
+        cp[thg.rel_key(et)], ri[thg.rel_key(et)], _ = thg.to_csc(dev(e), (counts[et[0]], counts[et[2]]))
+    B, S = 3, 16
+    rng = np.random.default_rng(2)
+    inputs = {t: dev(rng.integers(0, counts[t], (B, S))) for t in node_types}
+    nn = {thg.rel_key(et): [4, 3] for et in edge_types}
+    plan = thg.HeterogenousSampler(node_types, edge_types, cp, ri, B, {t: S for t in node_types}, nn, 2, relabel=True)
+    plan.sample(inputs, seed=9)
+    for b in range(B):
+        out_s = plan.batch(b)[0]
+        rl = plan.relabeled(b)
+        for t in node_types:
+            nodes, local = rl[t]
+            s = out_s[t].cpu().numpy()
+            _check_tree(s, s.size, S, nodes.cpu().numpy(), local.cpu().numpy(), nodes.numel())

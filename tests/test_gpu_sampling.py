@@ -429,3 +429,34 @@ def test_sample_async_on_two_streams_equals_sample(thg, fakedataset):
     bad[2, 3] = n + 9
     with pytest.raises(thg.ReferencePanic):
         plans[0].sample_async(bad, seed=1).result()
+
+
+def test_short_edge_attributes_are_refused(thg, fakedataset):
+    """weights / timestamps shorter than row_indices: the reference panics on EdgeAttr::get (graph.rs:103-120); a
+    col_ptrs that runs past row_indices is caught by the kernels (nnz check) instead of reading out of bounds."""
+    ei, n = fakedataset
+    ptrs, idx, _ = graph(thg, ei, n)
+    inputs = dev(np.arange(64))
+    w = torch.ones(idx.numel() - 5, dtype=torch.float64, device="cuda")
+    with pytest.raises(thg.ReferencePanic):
+        thg.neighbor_sampling_homogenous(ptrs, idx, inputs, [3], thg.WeightedEdgeSampler(w))
+    ts = torch.zeros(idx.numel() - 1, dtype=torch.int64, device="cuda")
+    flt = (thg.TemporalEdgeFilter((0, 2), ts, True, thg.TEMPORAL_SAMPLE_STATIC), torch.zeros(64, dtype=torch.int64, device="cuda"))
+    with pytest.raises(thg.ReferencePanic):
+        thg.neighbor_sampling_homogenous(ptrs, idx, inputs, [3], None, flt)
+    with pytest.raises(thg.ReferencePanic):
+        thg.neighbor_sampling_homogenous(ptrs, idx[:-40].contiguous(), dev(np.arange(n)), [3])
+    thg.clear_caches()
+
+
+def test_temporal_filter_with_large_fanout(thg, fakedataset):
+    """fanout above 11 k needs more than the default 48 KB of dynamic shared memory in hop_filtered_kernel"""
+    ei, n = fakedataset
+    ptrs, idx, _ = graph(thg, ei, n)
+    hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
+    ts = np.random.default_rng(0).integers(0, 4, hi.size)
+    seeds = np.arange(20)
+    flt = (thg.TemporalEdgeFilter((0, 2), dev(ts), True, thg.TEMPORAL_SAMPLE_STATIC), dev(np.zeros(20)))
+    got = thg.neighbor_sampling_homogenous(ptrs, idx, dev(seeds), [20000], None, flt)
+    keep = [(ts[hp[w]:hp[w + 1]] <= 2).sum() for w in seeds]
+    assert got[1].numel() == int(np.sum(keep))

@@ -76,7 +76,7 @@ def test_weighted_sampler_arbitrary_weights(thg, fakedataset, monkeypatch, cumsu
     serial oracle bit for bit for weights whose sums depend on the order of addition.  The scan path (cumsum off)
     is checked on the same input for structure only."""
     monkeypatch.setenv("TCHGEO_WEIGHT_CUMSUM", cumsum)
-    thg.ops._cumsum_cache.clear()
+    thg.clear_caches()
     ei, n = fakedataset
     ptrs, idx, _ = thg.to_csc(i64(ei), n)
     hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
@@ -94,7 +94,7 @@ def test_weighted_sampler_arbitrary_weights(thg, fakedataset, monkeypatch, cumsu
     else:
         s, r, c, e = (t.cpu().numpy() for t in got[:4])
         assert s.size == want[0].size and (hi[e] == s[r]).all()
-    thg.ops._cumsum_cache.clear()
+    thg.clear_caches()
 
 
 def test_weighted_sampler_heavy_columns_bit_exact(thg, fakedataset):
