@@ -26,6 +26,8 @@
 namespace tchgeo {
 namespace {
 
+inline size_t rl_align(size_t x) { return (x + 255) / 256 * 256; }
+
 constexpr int RL_THREADS = 256;
 constexpr int RL_ITEMS = 4;                        // positions per thread in the compaction kernel
 constexpr int RL_TILE = RL_THREADS * RL_ITEMS;     // positions per tile of the per-tree scan
@@ -282,6 +284,356 @@ __global__ void __launch_bounds__(RL_THREADS) rl_lookup_kernel(const RlParams p)
   }
 }
 
+// =================================================================================================
+// Persistent form (the one the sampling plan uses when the ids fit 32 bits): ONE cooperative launch per call.
+// The grid is G groups of C co-resident CTAs; group g owns one hash table and walks trees g, g+G, ... through
+//   clear -> insert -> count -> assign -> lookup
+// with a group barrier between the phases (an arrive counter + generation word per group: only the C CTAs that share
+// a tree ever wait for each other).  At any moment only G tables (8 MB each for the products configuration), G slot
+// maps and the G trees in flight are live, so every table access and every re-read of the ids is an L2 hit, and DRAM
+// sees 8 B read + (8 B local + <= 8 B nodes) written per id.  One table slot is ONE 64-bit word (key << 32 | priority),
+// so the common insert (a new id) is a single atomicCAS; a second occurrence adds one 64-bit atomicMin (equal keys:
+// the smaller priority wins); the winner later overwrites the priority with (1 << 31 | rank) in place.
+// Everything the CTAs of a group hand to each other (table, slot map, state bytes, CTA counts) is read with ld.cg:
+// the L1 is not coherent and the same addresses are reused tree after tree.
+// The co-residency the barriers rely on is what cudaLaunchCooperativeKernel guarantees (two plans on two streams would
+// otherwise be able to starve each other's CTAs).
+// =================================================================================================
+constexpr int RP_THREADS = 512;
+constexpr int RP_ITEMS = 4;                       // consecutive positions per thread in the scan phases
+constexpr int RP_TILE = RP_THREADS * RP_ITEMS;
+constexpr int RP_MAX_GROUPS = 32;
+constexpr int RP_MAX_CTAS = 4096;                 // bound of the grid (cta_count scratch)
+constexpr unsigned long long RP_EMPTY = ~0ull;
+constexpr uint32_t RP_RANKED = 0x80000000u;
+// per-position state byte written by the count phase
+constexpr uint32_t RP_F_NODE = 1u;      // emits a node (every seed; a non-seed holding its id's minimum)
+constexpr uint32_t RP_F_PUBLISH = 2u;   // first occurrence of a non-seed id: publishes its rank in the table
+constexpr uint32_t RP_F_PENDING = 4u;   // later occurrence of a non-seed id: local[] comes from the published rank
+
+struct RpParams {
+  const int64_t* samples;
+  int64_t stride;
+  const int64_t* lens;
+  int64_t* nodes;
+  int64_t* local;
+  int64_t* nodes_len;
+  int64_t num_seeds, n_max, n_pad;   // n_pad: n_max rounded up to a multiple of RP_ITEMS (row pitch of the scratch maps)
+  int32_t num_trees, groups, ctas_per_group;
+  uint32_t cap_mask;
+  int32_t hash_shift;
+  unsigned long long* tables;        // [groups, slots]
+  uint32_t* slot_of;                 // [groups, n_pad]
+  uint8_t* fbytes;                   // [groups, n_pad]
+  uint32_t* cta_count;               // [groups, ctas_per_group]
+  uint32_t* bars;                    // [groups, 32]: [0] arrivals, [1] generation (zero-initialised)
+  uint32_t* err;
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// barrier over the `n` CTAs of one group (all co-resident).  Returns false when the watchdog trips.
+__device__ __forceinline__ bool group_sync(uint32_t* bar, uint32_t n, uint32_t* err) {
+  __shared__ uint32_t s_ok;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t ok = 1u;
+    const uint32_t gen = ld_acquire_u32(bar + 1);
+    __threadfence();
+    if (atomicAdd(bar, 1u) == n - 1u) {
+      atomicExch(bar, 0u);
+      __threadfence();
+      atomicAdd(bar + 1, 1u);
+    } else {
+      uint32_t spins = 0;
+      while (ld_acquire_u32(bar + 1) == gen) {
+        if (++spins > (1u << 26)) {
+          atomicOr(err, DEV_ERR_WATCHDOG);
+          ok = 0u;
+          break;
+        }
+        __nanosleep(64);
+      }
+    }
+    __threadfence();
+    s_ok = ok;
+  }
+  __syncthreads();
+  return s_ok != 0u;
+}
+
+__global__ void __launch_bounds__(RP_THREADS, 2) rl_persistent_kernel(const RpParams p) {
+  __shared__ uint32_t s_wtot[RP_THREADS / 32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = blockIdx.x / p.ctas_per_group, c = blockIdx.x - g * p.ctas_per_group;
+  const uint32_t C = (uint32_t)p.ctas_per_group;
+  const int64_t gthreads = (int64_t)C * RP_THREADS;
+  const int64_t gtid = (int64_t)c * RP_THREADS + tid;
+  unsigned long long* tab = p.tables + (size_t)g * ((size_t)p.cap_mask + 1);
+  uint32_t* slot_of = p.slot_of + (size_t)g * p.n_pad;
+  uint8_t* fbytes = p.fbytes + (size_t)g * p.n_pad;
+  uint32_t* cta_count = p.cta_count + (size_t)g * C;
+  uint32_t* bar = p.bars + (size_t)g * 32;
+  const int64_t S = p.num_seeds;
+  const uint32_t mask = p.cap_mask;
+
+  for (int b = g; b < p.num_trees; b += p.groups) {
+    int64_t n = p.lens[b];
+    n = n < 0 ? 0 : (n > p.n_max ? p.n_max : n);
+    const int64_t* src = p.samples + (int64_t)b * p.stride;
+    int64_t* local = p.local + (int64_t)b * p.stride;
+    int64_t* nodes = p.nodes + (int64_t)b * p.stride;
+
+    // ---- clear the group's table (16-byte stores; the table stays in the L2) -----------------------------------
+    {
+      ulonglong2* t2 = reinterpret_cast<ulonglong2*>(tab);
+      const int64_t n2 = ((int64_t)mask + 1) >> 1;
+      for (int64_t q = gtid; q < n2; q += gthreads) t2[q] = make_ulonglong2(RP_EMPTY, RP_EMPTY);
+    }
+    if (!group_sync(bar, C, p.err)) return;
+
+    // ---- insert: four ids per thread in flight ------------------------------------------------------------------
+    for (int64_t i0 = gtid; i0 < n; i0 += 4 * gthreads) {
+      int64_t key[4];
+      unsigned long long want[4], old[4];
+      uint32_t h[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * gthreads;
+        key[u] = i < n ? __ldg(src + i) : -1;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * gthreads;
+        old[u] = RP_EMPTY;
+        want[u] = 0ull;
+        h[u] = RL_NOSLOT;
+        if (i >= n) continue;
+        if ((uint64_t)key[u] >= 0xFFFFFFFFull) {
+          atomicOr(p.err, DEV_ERR_INDEX);
+          continue;
+        }
+        const uint32_t prio = i < S ? (uint32_t)(S - 1 - i) : (uint32_t)i;
+        want[u] = ((unsigned long long)(uint32_t)key[u] << 32) | prio;
+        h[u] = (((uint32_t)key[u] * 0x9E3779B1u) >> p.hash_shift) & mask;
+        old[u] = atomicCAS(tab + h[u], RP_EMPTY, want[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t i = i0 + u * gthreads;
+        if (i >= n) continue;
+        if (h[u] != RL_NOSLOT) {
+          unsigned long long o = old[u];
+          while (o != RP_EMPTY) {                                  // slot taken
+            if ((uint32_t)(o >> 32) == (uint32_t)key[u]) {          // by the same id: the smaller priority wins
+              atomicMin(tab + h[u], want[u]);
+              break;
+            }
+            h[u] = (h[u] + 1) & mask;                               // by another id: linear probing
+            o = atomicCAS(tab + h[u], RP_EMPTY, want[u]);
+          }
+        }
+        slot_of[i] = h[u];
+      }
+    }
+    if (!group_sync(bar, C, p.err)) return;
+
+    // ---- count: per-position state, local[] of everything that needs no rank, flags per CTA chunk ---------------
+    // CTA c owns the contiguous positions [c0, c1); a thread owns RP_ITEMS consecutive ones (one uint4 of slot_of)
+    int64_t chunk = (n + C - 1) / C;
+    chunk = (chunk + RP_TILE - 1) / RP_TILE * RP_TILE;
+    const int64_t c0 = min(n, (int64_t)c * chunk), c1 = min(n, c0 + chunk);
+    uint32_t my_flags = 0;
+    for (int64_t t0 = c0; t0 < c1; t0 += RP_TILE) {
+      const int64_t ibase = t0 + (int64_t)tid * RP_ITEMS;
+      if (ibase >= c1) continue;
+      const uint4 sv = __ldcg(reinterpret_cast<const uint4*>(slot_of + ibase));
+      const uint32_t sl[4] = {sv.x, sv.y, sv.z, sv.w};
+      unsigned long long e[4];
+#pragma unroll
+      for (int u = 0; u < RP_ITEMS; ++u) e[u] = (ibase + u < c1 && sl[u] != RL_NOSLOT) ? __ldcg(tab + sl[u]) : 0ull;
+      uint32_t st4 = 0;
+#pragma unroll
+      for (int u = 0; u < RP_ITEMS; ++u) {
+        const int64_t i = ibase + u;
+        if (i >= c1) continue;
+        uint32_t st = 0;
+        if (sl[u] == RL_NOSLOT) {                 // id outside the 32-bit range (already reported)
+          st = i < S ? RP_F_NODE : 0u;
+          local[i] = -1;
+        } else {
+          const uint32_t pr = (uint32_t)e[u];
+          if (pr < (uint32_t)S) {                 // a seed carries this id: the map points at its LAST seed slot (:26)
+            st_cs_i64(local + i, S - 1 - (int64_t)pr);
+            if (i < S) st = RP_F_NODE;            // every seed is kept (:25); its rank is its own index
+          } else if (pr == (uint32_t)i) {
+            st = RP_F_NODE | RP_F_PUBLISH;        // first occurrence of an id no seed carries (:36-39)
+          } else {
+            st = RP_F_PENDING;
+          }
+        }
+        my_flags += st & RP_F_NODE;
+        st4 |= st << (8 * u);
+      }
+      *reinterpret_cast<uint32_t*>(fbytes + ibase) = st4;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) my_flags += __shfl_xor_sync(0xffffffffu, my_flags, o);
+    if (lane == 0) s_wtot[warp] = my_flags;
+    __syncthreads();
+    if (tid == 0) {
+      uint32_t tot = 0;
+      for (int w = 0; w < RP_THREADS / 32; ++w) tot += s_wtot[w];
+      cta_count[c] = tot;
+    }
+    if (!group_sync(bar, C, p.err)) return;
+
+    // ---- assign: ranks in position order, node list, ranks published in the table -----------------------------
+    {
+      uint32_t before = 0, total = 0;
+      for (uint32_t q = lane; q < C; q += 32) {
+        const uint32_t v = __ldcg(cta_count + q);
+        total += v;
+        if (q < (uint32_t)c) before += v;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+      }
+      if (c == 0 && tid == 0) p.nodes_len[b] = (int64_t)total;
+      if (tid == 0) s_carry = before;
+    }
+    __syncthreads();
+    for (int64_t t0 = c0; t0 < c1; t0 += RP_TILE) {
+      const int64_t ibase = t0 + (int64_t)tid * RP_ITEMS;
+      const uint32_t st4 = ibase < c1 ? __ldcg(reinterpret_cast<const uint32_t*>(fbytes + ibase)) : 0u;
+      const uint32_t cnt = __popc(st4 & 0x01010101u);
+      uint32_t incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+      }
+      if (lane == 31) s_wtot[warp] = incl;
+      __syncthreads();
+      uint32_t excl = incl - cnt, tile_total = 0;
+#pragma unroll
+      for (int w = 0; w < RP_THREADS / 32; ++w) {
+        const uint32_t v = s_wtot[w];
+        if (w < warp) excl += v;
+        tile_total += v;
+      }
+      uint32_t r = s_carry + excl;
+      if (cnt) {
+        const uint4 sv = __ldcg(reinterpret_cast<const uint4*>(slot_of + ibase));
+        const uint32_t sl[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+        for (int u = 0; u < RP_ITEMS; ++u) {
+          const uint32_t st = (st4 >> (8 * u)) & 0xffu;
+          if (!(st & RP_F_NODE)) continue;
+          const int64_t i = ibase + u;
+          const int64_t key = __ldg(src + i);
+          st_cs_i64(nodes + r, key);
+          if (st & RP_F_PUBLISH) {
+            st_cs_i64(local + i, (int64_t)r);
+            __stcg(tab + sl[u], ((unsigned long long)(uint32_t)key << 32) | RP_RANKED | r);
+          }
+          ++r;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) s_carry += tile_total;
+      __syncthreads();
+    }
+    if (!group_sync(bar, C, p.err)) return;
+
+    // ---- lookup: later occurrences of non-seed ids take the rank their first occurrence published -----------
+    for (int64_t i4 = gtid * 4; i4 < n; i4 += 4 * gthreads) {
+      const uint32_t st4 = __ldcg(reinterpret_cast<const uint32_t*>(fbytes + i4));
+      if (!(st4 & 0x04040404u)) continue;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (((st4 >> (8 * u)) & RP_F_PENDING) && i4 + u < n)
+          st_cs_i64(local + i4 + u, (int64_t)((uint32_t)__ldcg(tab + __ldcg(slot_of + i4 + u)) & 0x7fffffffu));
+    }
+    if (!group_sync(bar, C, p.err)) return;   // the next tree's clear must not overtake these reads
+  }
+}
+
+struct RpLayout {
+  uint32_t slots;
+  int log2_slots, groups;
+  int64_t n_pad;
+  size_t off_bars, off_cta, off_tables, off_slot_of, off_fbytes, total;
+};
+
+bool rp_layout(int64_t num_trees, int64_t n_max, RpLayout& L) {
+  if (num_trees <= 0 || n_max < 0 || n_max >= ((int64_t)1 << 30)) return false;
+  uint64_t slots = 1024;
+  while (slots < (uint64_t)n_max + 2) slots <<= 1;   // at least one empty slot ends every probe sequence
+  L.slots = (uint32_t)slots;
+  L.log2_slots = 0;
+  while ((1ull << L.log2_slots) < slots) ++L.log2_slots;
+  L.n_pad = (n_max + RP_ITEMS - 1) / RP_ITEMS * RP_ITEMS + RP_ITEMS;
+  // groups: as many trees in flight as keep tables + slot maps + state bytes + ids inside the L2 budget
+  const size_t per_group = slots * 8 + (size_t)L.n_pad * 13;
+  const char* e = getenv("TCHGEO_RELABEL_GROUPS");
+  int64_t groups = e ? atoi(e) : (int64_t)(((size_t)72 << 20) / std::max<size_t>(per_group, 1));
+  groups = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(groups, num_trees), RP_MAX_GROUPS));
+  L.groups = (int)groups;
+  size_t o = 0;
+  L.off_bars = o; o += rl_align((size_t)RP_MAX_GROUPS * 128);
+  L.off_cta = o; o += rl_align((size_t)RP_MAX_CTAS * 4);
+  L.off_tables = o; o += rl_align((size_t)groups * slots * 8);
+  L.off_slot_of = o; o += rl_align((size_t)groups * L.n_pad * 4);
+  L.off_fbytes = o; o += rl_align((size_t)groups * L.n_pad);
+  L.total = o + 256;
+  return true;
+}
+
+// -> cudaErrorNotSupported when the device cannot launch cooperatively (the caller then runs the wave form)
+cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees, int64_t num_seeds,
+                       int64_t n_max, int64_t* nodes, int64_t* local, int64_t* nodes_len, char* ws, const RpLayout& L,
+                       uint32_t* err, cudaStream_t stream) {
+  static int resident[64] = {};  // co-resident CTAs of the kernel per device (0 = not queried, -1 = no cooperative launch)
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev < 0 || dev >= 64) return cudaErrorNotSupported;
+  if (resident[dev] == 0) {
+    int coop = 0, sms = 0, per_sm = 0;
+    e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rl_persistent_kernel, RP_THREADS, 0);
+    if (e != cudaSuccess) return e;
+    resident[dev] = (coop && sms * per_sm > 0) ? sms * per_sm : -1;
+  }
+  if (resident[dev] < 0) return cudaErrorNotSupported;
+  RpParams p;
+  p.samples = samples; p.stride = stride; p.lens = lens; p.nodes = nodes; p.local = local; p.nodes_len = nodes_len;
+  p.num_seeds = num_seeds; p.n_max = n_max; p.n_pad = L.n_pad; p.num_trees = (int32_t)num_trees;
+  p.groups = std::min(L.groups, resident[dev]);
+  p.ctas_per_group = std::min(resident[dev], RP_MAX_CTAS) / p.groups;
+  p.cap_mask = L.slots - 1; p.hash_shift = 32 - L.log2_slots;
+  p.tables = (unsigned long long*)(ws + L.off_tables);
+  p.slot_of = (uint32_t*)(ws + L.off_slot_of);
+  p.fbytes = (uint8_t*)(ws + L.off_fbytes);
+  p.cta_count = (uint32_t*)(ws + L.off_cta);
+  p.bars = (uint32_t*)(ws + L.off_bars);
+  p.err = err;
+  e = cudaMemsetAsync(ws + L.off_bars, 0, (size_t)RP_MAX_GROUPS * 128, stream);
+  if (e != cudaSuccess) return e;
+  void* args[] = {(void*)&p};
+  return cudaLaunchCooperativeKernel((const void*)rl_persistent_kernel, dim3((unsigned)(p.groups * p.ctas_per_group)),
+                                     dim3(RP_THREADS), args, 0, stream);
+}
+
 __global__ void rl_set_len_kernel(int64_t* p, int64_t v) { *p = v; }
 
 struct RlLayout {
@@ -297,7 +649,6 @@ struct RlLayout {
   size_t off_rank, off_slot_of, total;
   int num_waves;
 };
-inline size_t rl_align(size_t x) { return (x + 255) / 256 * 256; }
 
 bool rl_layout(int64_t num_trees, int64_t n_max, bool k32, RlLayout& L) {
   if (num_trees <= 0 || n_max < 0 || n_max >= ((int64_t)1 << 31)) return false;
@@ -363,12 +714,22 @@ tchgeo_status rl_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
 
 }  // namespace
 
-// used by the sampling plan (neighbor_sampling.cu): size and enqueue the stage for one node type
+// used by the sampling plan (neighbor_sampling.cu): size and enqueue the stage for one node type.  k32 (ids < 2^32-1): the
+// persistent form, with the wave form as its fallback on devices without cooperative launch (TCHGEO_RELABEL_WAVES=1
+// forces it); any i64 id: the wave form with 64-bit keys.
+static bool use_persistent(bool k32) {
+  const char* e = getenv("TCHGEO_RELABEL_WAVES");
+  return k32 && !(e && atoi(e) != 0);
+}
 size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, bool k32) {
   RlLayout L;
-  return rl_layout(num_trees, n_max, k32, L) ? L.total : 0;
+  if (!rl_layout(num_trees, n_max, k32, L)) return 0;
+  RpLayout P;
+  if (use_persistent(k32) && rp_layout(num_trees, n_max, P)) return std::max(L.total, P.total);
+  return L.total;
 }
 int relabel_launches(int64_t num_trees, int64_t n_max, bool k32) {
+  if (use_persistent(k32)) return 1;
   RlLayout L;
   return rl_layout(num_trees, n_max, k32, L) ? 3 * L.num_waves : 0;
 }
@@ -378,7 +739,16 @@ tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int6
                               cudaStream_t stream) {
   RlLayout L;
   TCHGEO_REQUIRE(rl_layout(num_trees, n_max, k32, L), "relabel: tree too large");
-  TCHGEO_REQUIRE(workspace && workspace_bytes >= L.total, "relabel: workspace too small (need %zu bytes)", L.total);
+  TCHGEO_REQUIRE(workspace && workspace_bytes >= relabel_workspace_bytes(num_trees, n_max, k32),
+                 "relabel: workspace too small (need %zu bytes)", relabel_workspace_bytes(num_trees, n_max, k32));
+  RpLayout P;
+  if (use_persistent(k32) && rp_layout(num_trees, n_max, P)) {
+    const cudaError_t e = rp_enqueue(samples, stride, lens, num_trees, num_seeds, n_max, nodes, local, nodes_len,
+                                     (char*)workspace, P, err, stream);
+    if (e == cudaSuccess) return TCHGEO_OK;
+    if (e != cudaErrorNotSupported) TCHGEO_CUDA_CHECK(e);
+    (void)cudaGetLastError();
+  }
   return rl_enqueue(samples, stride, lens, num_trees, num_seeds, n_max, k32, nodes, local, nodes_len, (char*)workspace, L,
                     err, stream);
 }
