@@ -908,75 +908,126 @@ def measure_hetero(args, rank, world, local, device, K, W, with_cpu):
 
 
 def run_partitioned(args):
-    """configs[4]: papers100M-shaped graph, CSC range-partitioned over the ranks, 3-hop [15,10,5] sampling with an
-    NCCL all-to-all frontier exchange per hop.  Weak scaling: every rank owns 13 882 495 columns / ~202 M edges, so
-    8 ranks hold exactly the 111 059 956-node, 1 615 685 872-edge shape."""
+    """configs[4]: papers100M-shaped graph, CSC range-partitioned over the ranks, 3-hop [15,10,5] sampling with the
+    frontier exchanged per hop (requests out, sampled neighbours back).  --protocol fixed (default): both exchanges are
+    NVLink peer-memory stores into fixed per-pair segments, counts stay on the device, no host synchronisation inside a
+    step; --protocol legacy: round 1's count matrix + host read per hop (NCCL all-to-alls or peer stores)."""
     import tch_geometric as thg
     import torch.distributed as dist
-    from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedPlan, SingleComm, partition_bounds
+    from tch_geometric.partitioned import DistComm, PartitionedPlan, PartitionedPlanF, SingleComm
     from tch_geometric.sharding import reduce_job
     rank, world, local, device = setup_device()
-    cols_full, edges_full = 111_059_956 // 8 + 1, 1_615_685_872 // 8
-    cols_rank = max(int(cols_full * args.scale), 64)
-    n = cols_rank * world
-    b, e = partition_bounds(n, rank, world)
-    deg = synth.lognormal_degrees(e - b, max(int(edges_full * args.scale), e - b), dmax=17_481, seed=42 + rank)
-    ei = synth.edges_from_degrees(deg, n, device, seed=42 + rank)            # rows over all N nodes, cols local
-    ptrs, idx, _ = thg.to_csc(ei, (n, e - b))
-    del ei
-    torch.cuda.empty_cache()
-    e_local = torch.tensor([idx.numel()], dtype=torch.int64, device=device)
-    if world > 1:
-        allc = [torch.zeros_like(e_local) for _ in range(world)]
-        dist.all_gather(allc, e_local)
-        edge_base = int(sum(int(x.item()) for x in allc[:rank]))
-        e_total = int(sum(int(x.item()) for x in allc))
-    else:
-        edge_base, e_total = 0, int(e_local.item())
-    part = ColumnPartition(ptrs, idx, n, rank, world, edge_base)
+    part, n, e_total, cols_rank = synth.papers_partition(thg, rank, world, device, args.scale)
     B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
-    ps = PartitionedPlan(part, B, S, FANOUTS, comm=DistComm() if world > 1 else SingleComm(),
-                         groups=args.groups if args.groups > 0 else None)
-    seeds = [torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B)).to(device)
-             for s in range(W + K)]
+    comm = DistComm() if world > 1 else SingleComm()
+    if args.protocol == "fixed":
+        ps = PartitionedPlanF(part, B, S, FANOUTS, comm=comm if world > 1 else None, world=world, rank=rank, slack=args.slack)
+    else:
+        ps = PartitionedPlan(part, B, S, FANOUTS, comm=comm, groups=args.groups if args.groups > 0 else None)
+    host_seeds = torch.empty((W + K, B, S), dtype=torch.int64).pin_memory()
+    for s in range(W + K):
+        host_seeds[s] = torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B))
+    seeds = host_seeds.to(device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     for s in range(W):
         ps.sample(seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     clocks = ClockSampler(local)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     edges_n = 0
+    F_hop = np.zeros(len(FANOUTS))          # frontier nodes per hop, summed over the timed steps
     e0.record()
     for s in range(W, W + K):
         out = ps.sample(seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
         edges_n += int(out.edges_len.sum())
+        nl = out._node_len.sum(axis=1).astype(np.float64)      # [H+1] len(samples) after h hops
+        F_hop += np.diff(np.concatenate([[0.0], nl[:-1]]))
     e1.record()
     torch.cuda.synchronize()
-    clk = clocks.stop()
     ps.profile = {}   # untimed extra pass: device time per phase (CUDA events between the phases)
     for s in range(W, W + K):
         ps.sample(seeds[s], seed=1000 + s, batch_base=(s * world + rank) * B)
     phases = {k: v / ps.profile["calls"] for k, v in ps.profile.items() if k != "calls"}
+    ps.profile = None
     ms, edges_all = reduce_job(e0.elapsed_time(e1), float(edges_n), device)
+
+    # ---- e2e: pinned host seeds -> H2D -> sample -> packed D2H of samples / cols / edge_index ----------------------
+    e2e = None
+    if not args.no_e2e:
+        HB = min(B, 64)
+        host = thg.HostBatches(HB, ps.cap_n, ps.cap_e, S, device, fill=0.8)
+        thg.ops.host_arange(S + ps.cap_e)
+
+        def e2e_step(s):
+            out = ps.sample(host_seeds[s], seed=2000 + s, batch_base=(s * world + rank) * B)
+            d = 0
+            for g0 in range(0, B, HB):
+                d += out.to_host(host, g0, min(HB, B - g0))
+            return int(out.edges_len.sum()), d
+        e2e_step(0)
+        barrier()
+        t0 = time.perf_counter()
+        ee, dd = 0, 0
+        for s in range(W, W + K):
+            a, d = e2e_step(s)
+            ee, dd = ee + a, dd + d
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3
+        e2e_ms, ee_all = reduce_job(e2e_ms, float(ee), device)
+        e2e = {"value": ee_all / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * S * 8, "d2h_bytes_per_step": dd // K,
+               "ms_per_step": e2e_ms / K,
+               "path": "plan.sample(pinned host seeds) + PartitionedBatches.to_host (device-side ragged pack, one D2H per tensor "
+                       "and group of 64 batches; rows = arange served from the host)"}
+    clk = clocks.stop()
+
+    # ---- CPU baseline (N = 1 only): the oracle port on this rank's 13.9 M-column share ----------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu = run_cpu_baseline(part.ptrs, part.indices, n, args, None)
+
+    peak, peak_src = measured_peak_gbs()
+    nvlink_gbs = 600.0   # all_to_all_single with static buffers on this box class (profiles/r1_a2a_probe_8gpu.txt)
+    F_tot = float(F_hop.sum())
+    req_b = 16.0 * F_tot / K                                   # per rank per step: 16-byte request rows
+    ans_b = float(sum(8.0 * k * f for k, f in zip(FANOUTS, F_hop))) / K   # 2k int32 words per frontier node of hop h
+    remote = (world - 1) / world
+    exch_ms = sum(v for k_, v in phases.items() if "barrier" in k_ or "a2a" in k_)
+    kern_ms = sum(v for k_, v in phases.items() if not ("barrier" in k_ or "a2a" in k_))
+    alg = 24.0 * F_tot / K + 40.0 * edges_n / K                # SURVEY 8(d): what the replicated kernel moves for the same step
     if rank == 0:
         emit({"metric": "sampled_edges_per_sec_3hop_15_10_5_partitioned_csc", "value": edges_all / (ms * 1e-3),
               "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
               "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
               "config": {"workload": f"papers100M-shaped synthetic graph (N={n}, E={e_total}; {cols_rank} columns per rank), "
                                      f"CSC range-partitioned over {world} rank(s), fanouts {FANOUTS}, {S} seeds/batch, "
-                                     f"{B} batches/step/rank, per hop an NCCL all-to-all of the requests and "
-                                     + ("answers stored by the serve kernel straight into the requesters' buffers "
-                                        "(NVLink peer memory)" if ps.peer is not None else "an NCCL all-to-all of the answers"),
-                         "parallelism": "column-range partition; request all-to-all(v); answers: "
-                                        + ("peer-memory stores fused into the serve kernel" if ps.peer is not None
-                                           else "all-to-all(v)")},
-              "answer_exchange": "peer" if ps.peer is not None else "all_to_all",
-              "phase_ms_per_step_rank0": phases, "pipelined_batch_groups": ps.num_groups,
-              "exchange_bytes_per_step_per_rank": {"requests": ps.stats["request_bytes"] // (W + 2 * K),
-                                                   "answers": ps.stats["answer_bytes"] // (W + 2 * K)},
-              "cpu_baseline": None, "e2e": None, "gpu_launches": K * len(FANOUTS) * 8, "clocks": clk})
+                                     f"{B} batches/step/rank",
+                         "protocol": args.protocol,
+                         "parallelism": "column-range partition; per hop the frontier goes to the owners and the sampled "
+                                        "neighbours come back"
+                                        + (" as NVLink peer-memory stores into fixed per-pair segments (no host sync, no "
+                                           "count matrix)" if args.protocol == "fixed" else " (count matrix + host read per hop)"),
+                         "l2_policy": "inputs larger than L2 (row_indices 1.6 GB per rank; GBs of outputs per step); seeds "
+                                      "differ every step"},
+              "phase_ms_per_step_rank0": phases, "kernels_ms_per_step_rank0": kern_ms, "exchange_wait_ms_per_step_rank0": exch_ms,
+              "exchange_bytes_per_step_per_rank": {"requests": req_b, "answers": ans_b, "leaving_the_gpu": (req_b + ans_b) * remote},
+              "roofline": {"bound": "hbm", "kernel": "whole step (scatter + put, serve, finish per hop)",
+                           "achieved": alg / (ms / K * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                           "frac": alg / (ms / K * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                           "algorithmic_bytes_per_step": alg,
+                           "byte_model": "24 B per frontier node + 40 B per sampled edge (SURVEY 8d: the bytes of the replicated "
+                                         "step; request and answer rows are protocol overhead on top)",
+                           "exchange": {"bytes_leaving_per_step": (req_b + ans_b) * remote, "nvlink_GBps_reference": nvlink_gbs,
+                                        "ms_at_reference_rate": (req_b + ans_b) * remote / nvlink_gbs / 1e6,
+                                        "note": "the stores ride inside the scatter/put and serve kernels; the barrier "
+                                                "phases are what is left of the exchange as waiting time"}},
+              "cpu_baseline": cpu, "e2e": e2e,
+              "gpu_launches": K * len(FANOUTS) * (4 if args.protocol == "fixed" else 8), "clocks": clk})
 
 
 def main():
@@ -997,6 +1048,10 @@ def main():
                     help="sampling workload: neighbour sampler (uniform = the headline configuration)")
     ap.add_argument("--groups", type=int, default=0,
                     help="partitioned workload: batch groups pipelined on separate streams (0 = default: 1)")
+    ap.add_argument("--protocol", default="fixed", choices=["fixed", "legacy"],
+                    help="partitioned workload: exchange protocol (fixed = device-only fixed segments; legacy = round 1)")
+    ap.add_argument("--slack", type=float, default=1.5,
+                    help="partitioned workload, fixed protocol: segment size as a multiple of the mean per-pair load")
     ap.add_argument("--walkers", type=int, default=0, help="walk workload: number of walkers (0 = 10 per node)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")

@@ -383,6 +383,43 @@ TCHGEO_API tchgeo_status tchgeo_part_finish_hop(const int64_t* req /*DEVICE [F,2
                                                 int64_t samples_stride, int64_t* rows, int64_t* cols, int64_t* edge_index,
                                                 int64_t edges_stride, int32_t* err_word, void* workspace,
                                                 size_t workspace_bytes, tchgeo_stream stream);
+/* ---- the same path with BOTH exchanges and every count kept on the device ("fixed segments", csrc/partitioned_fixed.cu):
+ * every (requester q, owner o) pair owns `seg_rows` rows in o's request buffer req_in [world, seg_rows, 2] (+ one entry of
+ * o's count table cnt_in [world]) and in q's answer buffer ans_in [world, seg_rows, 2*fanout] (int32).  The buffers live in
+ * NVLink peer memory (e.g. torch symmetric memory); peer_* are HOST arrays of `world` DEVICE pointers to every rank's
+ * buffer.  A hop is: tchgeo_partf_scatter (frontier -> rows grouped by owner -> whole-line stores into the owners'
+ * request segments + counts), a barrier over the ranks, tchgeo_partf_serve (the owner samples every segment it holds,
+ * counts read on the device, and stores the answer rows at the same row index of the requester's answer segment), a
+ * barrier, tchgeo_partf_finish (one pass: slot map -> answer row -> scan with decoupled look-back -> tree layout of
+ * src/algo/neighbor_sampling.rs:210-218 and the new lengths).  No host synchronisation inside a hop; a segment that
+ * overflows raises TCHGEO_ERR_CAPACITY through *err_word (DEVICE u32, caller-zeroed).  All asynchronous.
+ * `me` = this rank; slot_of: DEVICE u32 [B * frontier_cap] scratch shared by scatter and finish of one hop; send: DEVICE
+ * [world, seg_rows, 2] scratch; cursor: DEVICE [world] scratch.  Results equal tchgeo_neighbor_sampling bit for bit. */
+TCHGEO_API size_t tchgeo_partf_workspace_bytes(int64_t num_batches, int64_t frontier_cap);
+TCHGEO_API tchgeo_status tchgeo_partf_scatter(const int64_t* samples /*DEVICE [B, samples_stride]*/, int64_t samples_stride,
+                                              const int64_t* fr_begin /*DEVICE [B] or NULL*/, const int64_t* fr_end /*DEVICE [B]*/,
+                                              int64_t num_batches, int64_t frontier_cap, int64_t cols_per_rank, int32_t world,
+                                              int32_t me, uint32_t batch_base, int64_t seg_rows, int64_t* send, int64_t* cursor,
+                                              uint32_t* slot_of, void* const* peer_req /*HOST [world]*/,
+                                              void* const* peer_cnt /*HOST [world]*/, int32_t* err_word, tchgeo_stream stream);
+TCHGEO_API tchgeo_status tchgeo_partf_serve(const int64_t* ptrs_local, const int64_t* indices_local,
+                                            const int32_t* indices32_local /*DEVICE or NULL: int32 replica*/,
+                                            const double* weights_local, int64_t col_begin, int64_t ncols_local,
+                                            int64_t nnz_local, const int64_t* req_in /*DEVICE [world, seg_rows, 2]*/,
+                                            const int64_t* cnt_in /*DEVICE [world]*/, int64_t seg_rows,
+                                            int64_t max_requests /*bound of cnt_in entries (grid size); 0 = seg_rows*/,
+                                            int64_t fanout, int32_t sampler_kind, uint64_t seed, uint32_t rel, int32_t world,
+                                            int32_t me, void* const* peer_ans /*HOST [world]*/, int32_t* err_word,
+                                            tchgeo_stream stream);
+TCHGEO_API tchgeo_status tchgeo_partf_finish(const int32_t* ans_in /*DEVICE [world, seg_rows, 2*fanout]*/,
+                                             const uint32_t* slot_of, int64_t seg_rows, int64_t fanout,
+                                             const int64_t* owner_edge_base /*DEVICE [world]*/, int32_t world,
+                                             const int64_t* fr_begin, const int64_t* fr_end, int64_t num_batches,
+                                             int64_t frontier_cap, const int64_t* node_len_in /*DEVICE [B]*/,
+                                             const int64_t* edge_len_in, int64_t* node_len_out, int64_t* edge_len_out,
+                                             int64_t* samples, int64_t samples_stride, int64_t* rows, int64_t* cols,
+                                             int64_t* edge_index, int64_t edges_stride, int32_t* err_word, void* workspace,
+                                             size_t workspace_bytes, tchgeo_stream stream);
 /* Map a device error word (as accumulated by the asynchronous entry points) to a status + last-error string. */
 TCHGEO_API tchgeo_status tchgeo_status_from_error_word(uint32_t word);
 

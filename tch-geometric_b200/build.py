@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "tch_geometric", "libtchgeo_cuda.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu", "partitioned.cu", "random_walk.cu", "relabel.cu"]
+SOURCES = ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu", "partitioned.cu", "partitioned_fixed.cu", "random_walk.cu", "relabel.cu"]
 DEPS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "graph.cuh"), os.path.join(HERE, "..", "include", "tchgeo_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [

@@ -366,7 +366,8 @@ __device__ __forceinline__ bool group_sync(uint32_t* bar, uint32_t n, uint32_t* 
   return s_ok != 0u;
 }
 
-__global__ void __launch_bounds__(RP_THREADS, 2) rl_persistent_kernel(const RpParams p) {
+template <int MINB>
+__global__ void __launch_bounds__(RP_THREADS, MINB) rl_persistent_kernel(const RpParams p) {
   __shared__ uint32_t s_wtot[RP_THREADS / 32];
   __shared__ uint32_t s_carry;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -421,7 +422,7 @@ __global__ void __launch_bounds__(RP_THREADS, 2) rl_persistent_kernel(const RpPa
         const uint32_t prio = i < S ? (uint32_t)(S - 1 - i) : (uint32_t)i;
         want[u] = ((unsigned long long)(uint32_t)key[u] << 32) | prio;
         h[u] = (((uint32_t)key[u] * 0x9E3779B1u) >> p.hash_shift) & mask;
-        old[u] = atomicCAS(tab + h[u], RP_EMPTY, want[u]);
+        old[u] = atomicCAS(tab + h[u], RP_EMPTY, want[u]);  // the common case (a new id, a free slot): one atomic
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -429,12 +430,15 @@ __global__ void __launch_bounds__(RP_THREADS, 2) rl_persistent_kernel(const RpPa
         if (i >= n) continue;
         if (h[u] != RL_NOSLOT) {
           unsigned long long o = old[u];
+          // double hashing (odd step: every slot of the power-of-two table is visited): a group waits at its barrier
+          // for the LONGEST probe sequence of the tree, and linear probing's clusters made that 30 % of the kernel
+          const uint32_t step = (((uint32_t)key[u] * 0x85EBCA6Bu) >> 7) | 1u;
           while (o != RP_EMPTY) {                                  // slot taken
             if ((uint32_t)(o >> 32) == (uint32_t)key[u]) {          // by the same id: the smaller priority wins
               atomicMin(tab + h[u], want[u]);
               break;
             }
-            h[u] = (h[u] + 1) & mask;                               // by another id: linear probing
+            h[u] = (h[u] + step) & mask;                            // by another id: next slot of the id's sequence
             o = atomicCAS(tab + h[u], RP_EMPTY, want[u]);
           }
         }
@@ -576,7 +580,7 @@ struct RpLayout {
 bool rp_layout(int64_t num_trees, int64_t n_max, RpLayout& L) {
   if (num_trees <= 0 || n_max < 0 || n_max >= ((int64_t)1 << 30)) return false;
   uint64_t slots = 1024;
-  while (slots < (uint64_t)n_max + 2) slots <<= 1;   // at least one empty slot ends every probe sequence
+  while (slots < 2 * (uint64_t)n_max + 2) slots <<= 1;   // load <= 0.5 in the worst case, about 0.3 for sampled trees
   L.slots = (uint32_t)slots;
   L.log2_slots = 0;
   while ((1ull << L.log2_slots) < slots) ++L.log2_slots;
@@ -601,6 +605,9 @@ bool rp_layout(int64_t num_trees, int64_t n_max, RpLayout& L) {
 cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees, int64_t num_seeds,
                        int64_t n_max, int64_t* nodes, int64_t* local, int64_t* nodes_len, char* ws, const RpLayout& L,
                        uint32_t* err, cudaStream_t stream) {
+  // tuning knob: CTAs per SM the register budget is set for (2: 64 registers, 3: 40)
+  static const int minb = [] { const char* e = getenv("TCHGEO_RELABEL_MINB"); return (e && atoi(e) == 3) ? 3 : 2; }();
+  const void* kernel = minb == 3 ? (const void*)rl_persistent_kernel<3> : (const void*)rl_persistent_kernel<2>;
   static int resident[64] = {};  // co-resident CTAs of the kernel per device (0 = not queried, -1 = no cooperative launch)
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
@@ -610,7 +617,10 @@ cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* le
     int coop = 0, sms = 0, per_sm = 0;
     e = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rl_persistent_kernel, RP_THREADS, 0);
+    if (e == cudaSuccess) {
+      e = minb == 3 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rl_persistent_kernel<3>, RP_THREADS, 0)
+                    : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, rl_persistent_kernel<2>, RP_THREADS, 0);
+    }
     if (e != cudaSuccess) return e;
     resident[dev] = (coop && sms * per_sm > 0) ? sms * per_sm : -1;
   }
@@ -630,7 +640,7 @@ cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* le
   e = cudaMemsetAsync(ws + L.off_bars, 0, (size_t)RP_MAX_GROUPS * 128, stream);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&p};
-  return cudaLaunchCooperativeKernel((const void*)rl_persistent_kernel, dim3((unsigned)(p.groups * p.ctas_per_group)),
+  return cudaLaunchCooperativeKernel(kernel, dim3((unsigned)(p.groups * p.ctas_per_group)),
                                      dim3(RP_THREADS), args, 0, stream);
 }
 

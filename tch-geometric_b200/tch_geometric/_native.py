@@ -146,6 +146,17 @@ def _load():
     lib.tchgeo_part_finish_hop.restype = c_i32
     lib.tchgeo_part_finish_hop.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp,
                                            c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]
+    lib.tchgeo_partf_workspace_bytes.restype = c_sz
+    lib.tchgeo_partf_workspace_bytes.argtypes = [c_i64, c_i64]
+    lib.tchgeo_partf_scatter.restype = c_i32
+    lib.tchgeo_partf_scatter.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32, c_i32, c_u32, c_i64, c_vp, c_vp,
+                                         c_vp, c_vp, c_vp, c_vp, c_vp]
+    lib.tchgeo_partf_serve.restype = c_i32
+    lib.tchgeo_partf_serve.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_i32,
+                                       c_u64, c_u32, c_i32, c_i32, c_vp, c_vp, c_vp]
+    lib.tchgeo_partf_finish.restype = c_i32
+    lib.tchgeo_partf_finish.argtypes = [c_vp, c_vp, c_i64, c_i64, c_vp, c_i32, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp,
+                                        c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_sz, c_vp]
     lib.tchgeo_status_from_error_word.restype = c_i32
     lib.tchgeo_status_from_error_word.argtypes = [c_u32]
     lib.tchgeo_random_walk.restype = c_i32
@@ -189,6 +200,7 @@ EXPORTS = [
     "tchgeo_graph_derived_bytes", "tchgeo_graph_destroy",
     "tchgeo_plan_create", "tchgeo_plan_enqueue", "tchgeo_plan_enqueue_timed", "tchgeo_plan_collect", "tchgeo_plan_results",
     "tchgeo_plan_num_launches", "tchgeo_plan_destroy", "tchgeo_random_walk_graph", "tchgeo_pack_ragged",
+    "tchgeo_partf_workspace_bytes", "tchgeo_partf_scatter", "tchgeo_partf_serve", "tchgeo_partf_finish",
 ]
 
 

@@ -512,34 +512,9 @@ class SampledBatches:
         copied: it is arange(S, S + E), HostBatches.batch serves it from a cached host arange).  Asynchronous; returns
         the number of bytes that travel."""
         call = self._call
-        count = call.B - first if count is None else int(count)
-        if count > host.B:
-            raise ValueError("HostBatches is smaller than the group of batches")
-        ns, ne = self.samples_len[first:first + count], self.edges_len[first:first + count]
-        n_off = np.concatenate([[0], np.cumsum(ns)])
-        e_off = np.concatenate([[0], np.cumsum(ne)])
-        if n_off[-1] > host.cap_n or e_off[-1] > host.cap_e:
-            raise MemoryError("HostBatches too small for this group: create it with a larger `fill`")
-        dev = call.device
-        h = host._h_lens
-        h[:count].copy_(torch.from_numpy(np.ascontiguousarray(ns)))
-        h[host.B:host.B + count].copy_(torch.from_numpy(np.ascontiguousarray(ne)))
-        with torch.cuda.device(dev):
-            stream = _stream(dev)
-            host._d_lens.copy_(h, non_blocking=True)
-            for src, lens_at, dst, off_at, cap in (
-                    (self.samples, 0, host._d_samples, 0, call.cap_n[0]),
-                    (self.cols, host.B, host._d_cols, host.B + 1, call.cap_e[0]),
-                    (self.edge_index, host.B, host._d_eidx, host.B + 1, call.cap_e[0])):
-                N.check(N.lib.tchgeo_pack_ragged(_ptr(src[first]), src.shape[1], _ptr(host._d_lens[lens_at:]), 1, count,
-                                                 int(cap), _ptr(dst), _ptr(host._d_off[off_at:]), stream))
-            nt, et = int(n_off[-1]), int(e_off[-1])
-            host.samples[:nt].copy_(host._d_samples[:nt], non_blocking=True)
-            host.cols[:et].copy_(host._d_cols[:et], non_blocking=True)
-            host.edge_index[:et].copy_(host._d_eidx[:et], non_blocking=True)
-        host.n_off, host.e_off = n_off, e_off
-        host.nbytes = 8 * (nt + 2 * et)
-        return host.nbytes
+        return packed_to_host(self.samples, self.cols, self.edge_index, self.samples_len, self.edges_len,
+                              int(call.cap_n[0]), int(call.cap_e[0]), call.device, host, first,
+                              call.B - first if count is None else int(count))
 
     def relabeled(self, b):
         """-> (nodes, local) of batch b: nodes = seeds ++ every other id of samples at its first appearance,
@@ -589,6 +564,36 @@ class HostBatches:
         n0, n1, e0, e1 = int(self.n_off[i]), int(self.n_off[i + 1]), int(self.e_off[i]), int(self.e_off[i + 1])
         rows = host_arange(self.S + (e1 - e0))[self.S:self.S + (e1 - e0)]
         return self.samples[n0:n1], rows, self.cols[e0:e1], self.edge_index[e0:e1]
+
+
+def packed_to_host(samples, cols, edge_index, samples_len, edges_len, cap_n, cap_e, device, host: "HostBatches",
+                   first: int, count: int) -> int:
+    """Shared by SampledBatches.to_host and the partitioned plans' results (same padded [B, capacity] layout)."""
+    if count > host.B:
+        raise ValueError("HostBatches is smaller than the group of batches")
+    ns, ne = samples_len[first:first + count], edges_len[first:first + count]
+    n_off = np.concatenate([[0], np.cumsum(ns)])
+    e_off = np.concatenate([[0], np.cumsum(ne)])
+    if n_off[-1] > host.cap_n or e_off[-1] > host.cap_e:
+        raise MemoryError("HostBatches too small for this group: create it with a larger `fill`")
+    h = host._h_lens
+    h[:count].copy_(torch.from_numpy(np.ascontiguousarray(ns)))
+    h[host.B:host.B + count].copy_(torch.from_numpy(np.ascontiguousarray(ne)))
+    with torch.cuda.device(device):
+        stream = _stream(device)
+        host._d_lens.copy_(h, non_blocking=True)
+        for src, lens_at, dst, off_at, cap in ((samples, 0, host._d_samples, 0, cap_n),
+                                               (cols, host.B, host._d_cols, host.B + 1, cap_e),
+                                               (edge_index, host.B, host._d_eidx, host.B + 1, cap_e)):
+            N.check(N.lib.tchgeo_pack_ragged(_ptr(src[first]), src.shape[1], _ptr(host._d_lens[lens_at:]), 1, count,
+                                             int(cap), _ptr(dst), _ptr(host._d_off[off_at:]), stream))
+        nt, et = int(n_off[-1]), int(e_off[-1])
+        host.samples[:nt].copy_(host._d_samples[:nt], non_blocking=True)
+        host.cols[:et].copy_(host._d_cols[:et], non_blocking=True)
+        host.edge_index[:et].copy_(host._d_eidx[:et], non_blocking=True)
+    host.n_off, host.e_off = n_off, e_off
+    host.nbytes = 8 * (nt + 2 * et)
+    return host.nbytes
 
 
 class HomogenousSampler:

@@ -276,6 +276,14 @@ class PartitionedBatches:
         lo = [(int(self._node_len[h, b]), int(self._edge_len[h, b]), int(self._node_len[h, b])) for h in range(self._H)]
         return self.samples[b, :ns], self.rows[b, :ne], self.cols[b, :ne], self.edge_index[b, :ne], lo
 
+    def to_host(self, host, first: int = 0, count: Optional[int] = None) -> int:
+        """packed D2H of batches [first, first + count), like ops.SampledBatches.to_host"""
+        from .ops import packed_to_host
+        B = self.samples.shape[0]
+        return packed_to_host(self.samples, self.cols, self.edge_index, self.samples_len, self.edges_len,
+                              self.samples.shape[1], self.rows.shape[1], self.samples.device, host, first,
+                              B - first if count is None else int(count))
+
 
 class _PlanGroup:
     """A contiguous range of a plan's batches with its own stream, request buffer and workspace: the groups of a
@@ -597,3 +605,250 @@ class PartitionedPlan:
         N.check(N.lib.tchgeo_status_from_error_word(int(host[-1]) & 0xFFFFFFFF))
         lens = host[:-1].reshape(2, len(self.fanouts) + 1, self.B)
         return PartitionedBatches(self, lens[0], lens[1])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Device-only protocol ("fixed segments", csrc/partitioned_fixed.cu): both exchanges of a hop are peer-memory stores
+# into fixed per-pair segments, every count stays on the device, and the host never waits inside a step.
+# ---------------------------------------------------------------------------------------------------------------
+def segment_rows(num_batches: int, frontier_cap: int, world: int, slack: float) -> int:
+    """rows a (requester, owner) pair owns in a hop whose frontier has at most num_batches * frontier_cap nodes"""
+    total = num_batches * frontier_cap
+    if world == 1:
+        return max(total, 1)
+    return min(max(int(slack * total / world) + 1024, 1), max(total, 1))
+
+
+def frontier_caps(seeds_per_batch: int, fanouts: Sequence[int]) -> List[int]:
+    """worst-case frontier size per batch of every hop (the recurrence of tchgeo_neighbor_sampling_capacity)"""
+    caps, f = [], int(seeds_per_batch)
+    for k in fanouts:
+        caps.append(f)
+        f *= int(k)
+    return caps
+
+
+class SegmentBuffers:
+    """One rank's exchange buffers plus the device addresses of every rank's: req_in [world, seg, 2] i64 and cnt_in
+    [world] i64 (written by the requesters), ans_in [world, seg, 2k] i32 (written by the owners).  `barrier()` orders
+    the ranks on the current stream."""
+
+    def __init__(self, req_in, cnt_in, ans_in, req_ptrs, cnt_ptrs, ans_ptrs, barrier):
+        self.req_in, self.cnt_in, self.ans_in = req_in, cnt_in, ans_in
+        self.req_ptrs = np.array([int(x) for x in req_ptrs], dtype=np.uint64)
+        self.cnt_ptrs = np.array([int(x) for x in cnt_ptrs], dtype=np.uint64)
+        self.ans_ptrs = np.array([int(x) for x in ans_ptrs], dtype=np.uint64)
+        self.barrier = barrier
+
+    @staticmethod
+    def sizes(num_batches, capF, fanouts, world, slack):
+        segs = [segment_rows(num_batches, f, world, slack) for f in capF]
+        req_words = world * max(segs, default=1) * 2
+        ans_words = world * max((s * 2 * max(k, 1) for s, k in zip(segs, fanouts)), default=1)
+        return segs, req_words, ans_words
+
+    @staticmethod
+    def symmetric(num_batches, capF, fanouts, comm, device, slack):
+        """torch symmetric memory over the communicator's group (NVLink peer memory): allocation, the rendezvous that
+        gives every rank every peer's device address and the stream-ordered barrier are torch's plumbing; the stores
+        are this library's kernels."""
+        import torch.distributed._symmetric_memory as symm
+        group = comm.group if comm.group is not None else dist.group.WORLD
+        _, req_words, ans_words = SegmentBuffers.sizes(num_batches, capF, fanouts, comm.world, slack)
+        with torch.cuda.device(device):
+            req = symm.empty(req_words, dtype=torch.int64, device=device)
+            cnt = symm.empty(max(comm.world, 16), dtype=torch.int64, device=device)
+            ans = symm.empty(ans_words, dtype=torch.int32, device=device)
+            hdls = [symm.rendezvous(t, group) for t in (req, cnt, ans)]
+        for h in hdls:
+            if len(h.buffer_ptrs) != comm.world or int(h.rank) != comm.rank:
+                raise RuntimeError("symmetric memory rendezvous does not match the communicator")
+        cnt.zero_()
+        out = SegmentBuffers(req, cnt, ans, hdls[0].buffer_ptrs, hdls[1].buffer_ptrs, hdls[2].buffer_ptrs,
+                             lambda: hdls[2].barrier(channel=0))
+        out._hdls = hdls
+        return out
+
+    @staticmethod
+    def virtual(num_batches, capF, fanouts, world, device, slack):
+        """`world` ranks' buffers on ONE device (tests, single-GPU runs): plain tensors, stream order is the barrier.
+        -> list of SegmentBuffers, one per virtual rank."""
+        _, req_words, ans_words = SegmentBuffers.sizes(num_batches, capF, fanouts, world, slack)
+        reqs = [torch.empty(req_words, dtype=torch.int64, device=device) for _ in range(world)]
+        cnts = [torch.zeros(max(world, 16), dtype=torch.int64, device=device) for _ in range(world)]
+        anss = [torch.empty(ans_words, dtype=torch.int32, device=device) for _ in range(world)]
+        ptrs = lambda ts: [t.data_ptr() for t in ts]
+        return [SegmentBuffers(reqs[r], cnts[r], anss[r], ptrs(reqs), ptrs(cnts), ptrs(anss), lambda: None)
+                for r in range(world)]
+
+
+class PartitionedPlanF:
+    """neighbor_sampling_homogenous over a column-partitioned CSC with the device-only exchange.  `sample` is collective
+    (every rank calls it the same number of times); the phase methods (`begin`, `scatter`, `serve`, `finish`, `end`)
+    let a test drive several virtual ranks of one device in lock step."""
+
+    def __init__(self, part: ColumnPartition, num_batches: int, seeds_per_batch: int, num_neighbors: Sequence[int],
+                 sampler=None, world: Optional[int] = None, rank: Optional[int] = None, comm=None, buffers=None,
+                 edge_bases=None, slack: float = 1.5):
+        self.part = part
+        self.fanouts = [int(k) for k in num_neighbors]
+        self.kind, _ = _extract_sampler(sampler, hetero=False)
+        if self.kind == N.SAMPLER_WEIGHTED and part.weights is None:
+            raise ValueError("weighted sampling needs ColumnPartition.weights_local")
+        self.comm = comm
+        self.world = int(world if world is not None else (comm.world if comm is not None else 1))
+        self.rank = int(rank if rank is not None else (comm.rank if comm is not None else 0))
+        _check(part.ptrs, torch.int64, "col_ptrs_local")
+        dev = part.ptrs.device
+        _check(part.indices, torch.int64, "row_indices_local", dev)
+        if part.num_nodes >= 2 ** 31 or part.indices.numel() >= 2 ** 31:
+            raise ValueError("the compact answer rows need node ids and a rank's CSC share below 2^31")
+        self.device, self.B, self.S = dev, int(num_batches), int(seeds_per_batch)
+        B, S, H = self.B, self.S, len(self.fanouts)
+        self.capF, cap_e, f = [], 0, S
+        for k in self.fanouts:
+            self.capF.append(f)
+            f *= k
+            cap_e += f
+        self.cap_n, self.cap_e = S + cap_e, max(cap_e, 1)
+        self.slack = 1.0 if self.world == 1 else float(slack)
+        self.segs, _, _ = SegmentBuffers.sizes(B, self.capF, self.fanouts, self.world, self.slack)
+        if buffers is None:
+            if self.world == 1:
+                buffers = SegmentBuffers.virtual(B, self.capF, self.fanouts, 1, dev, self.slack)[0]
+            else:
+                buffers = SegmentBuffers.symmetric(B, self.capF, self.fanouts, comm, dev, self.slack)
+        self.buf = buffers
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.samples = torch.empty((B, self.cap_n), **i64)
+        self.rows = torch.empty((B, self.cap_e), **i64)
+        self.cols = torch.empty((B, self.cap_e), **i64)
+        self.eidx = torch.empty((B, self.cap_e), **i64)
+        self.lens = torch.zeros((2, H + 1, B), **i64)               # [0] node_len, [1] edge_len after h hops
+        self.err = torch.zeros(1, dtype=torch.int32, device=dev)
+        fmax = max(self.capF, default=0)
+        self.send = torch.empty(self.world * max(self.segs, default=1) * 2, **i64)
+        self.cursor = torch.zeros(max(self.world, 16), **i64)
+        self.slot_of = torch.empty(max(B * fmax, 1), dtype=torch.int32, device=dev)
+        ws = max((N.lib.tchgeo_partf_workspace_bytes(B, c) for c in self.capF), default=0)
+        self.ws = torch.empty(max(int(ws), 1), dtype=torch.uint8, device=dev)
+        # int32 replica of this rank's share of row_indices: the serve kernel's random gathers span half the DRAM lines
+        self.indices32 = None
+        if part.indices.numel() and os.environ.get("TCHGEO_INDEX_REPLICA", "1") != "0":
+            i32 = torch.empty(part.indices.numel(), dtype=torch.int32, device=dev)
+            scratch = torch.empty(1, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                st = N.lib.tchgeo_compress_indices(_ptr(part.indices), part.indices.numel(), _ptr(i32), _ptr(scratch), _stream(dev))
+            if st == N.OK:
+                self.indices32 = i32
+            elif st != N.ERR_INDEX:
+                N.check(st)
+        if edge_bases is None:
+            edge_bases = comm.all_gather_int(part.edge_base, dev) if comm is not None else [part.edge_base]
+        if len(edge_bases) != self.world:
+            raise ValueError("edge_bases must have one entry per rank")
+        self.edge_bases = torch.tensor([int(x) for x in edge_bases], **i64)
+        self.stats = {"requests_sent": 0, "request_bytes": 0, "answer_bytes": 0}
+        self.profile = None
+        self.peer = self.buf          # (bench.py reports which exchange ran)
+        self.num_groups = 1
+
+    # ---- phases (all asynchronous on the current stream) -------------------------------------------------
+    def begin(self, inputs: Tensor, seed: int, batch_base: int):
+        if inputs.dim() != 2 or inputs.dtype != torch.int64 or tuple(inputs.shape) != (self.B, self.S):
+            raise ValueError(f"inputs must be an int64 tensor of shape {(self.B, self.S)}")
+        self._seed, self._batch_base = seed, batch_base
+        self.samples[:, :self.S].copy_(inputs, non_blocking=True)
+        self.err.zero_()
+        self.lens.zero_()
+        self.lens[0, 0].fill_(self.S)
+
+    def _frontier(self, h):
+        lens = self.lens
+        return (lens[0, h - 1] if h > 0 else None), lens[0, h]
+
+    def scatter(self, h):
+        fb, fe = self._frontier(h)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.tchgeo_partf_scatter(_ptr(self.samples), self.cap_n, _ptr(fb), _ptr(fe), self.B, self.capF[h],
+                                               self.part.cols_per_rank, self.world, self.rank, self._batch_base,
+                                               self.segs[h], _ptr(self.send), _ptr(self.cursor), _ptr(self.slot_of),
+                                               self.buf.req_ptrs.ctypes.data, self.buf.cnt_ptrs.ctypes.data,
+                                               _ptr(self.err), _stream(self.device)))
+
+    def serve(self, h):
+        part, k = self.part, self.fanouts[h]
+        with torch.cuda.device(self.device):
+            N.check(N.lib.tchgeo_partf_serve(_ptr(part.ptrs), _ptr(part.indices), _ptr(self.indices32), _ptr(part.weights),
+                                             part.col_begin, part.col_end - part.col_begin, part.indices.numel(),
+                                             _ptr(self.buf.req_in), _ptr(self.buf.cnt_in), self.segs[h], 0, k, self.kind,
+                                             self._seed, 0, self.world, self.rank, self.buf.ans_ptrs.ctypes.data,
+                                             _ptr(self.err), _stream(self.device)))
+
+    def finish(self, h):
+        k, lens = self.fanouts[h], self.lens
+        fb, fe = self._frontier(h)
+        with torch.cuda.device(self.device):
+            N.check(N.lib.tchgeo_partf_finish(_ptr(self.buf.ans_in), _ptr(self.slot_of), self.segs[h], k,
+                                              _ptr(self.edge_bases), self.world, _ptr(fb), _ptr(fe), self.B, self.capF[h],
+                                              _ptr(lens[0, h]), _ptr(lens[1, h]), _ptr(lens[0, h + 1]), _ptr(lens[1, h + 1]),
+                                              _ptr(self.samples), self.cap_n, _ptr(self.rows), _ptr(self.cols),
+                                              _ptr(self.eidx), self.cap_e, _ptr(self.err), _ptr(self.ws), self.ws.numel(),
+                                              _stream(self.device)))
+
+    def end(self) -> PartitionedBatches:
+        host = torch.cat([self.lens.reshape(-1), self.err.to(torch.int64)]).cpu().numpy()   # the call's only sync
+        N.check(N.lib.tchgeo_status_from_error_word(int(host[-1]) & 0xFFFFFFFF))
+        lens = host[:-1].reshape(2, len(self.fanouts) + 1, self.B)
+        front = lens[0, :-1].sum(axis=1) - np.concatenate([[0], lens[0, :-2].sum(axis=1)]) if len(self.fanouts) else []
+        for F, k in zip(front, self.fanouts):
+            self.stats["requests_sent"] += int(F)
+            self.stats["request_bytes"] += 16 * int(F)
+            self.stats["answer_bytes"] += 8 * k * int(F)
+        return PartitionedBatches(self, lens[0], lens[1])
+
+    def _mark(self, marks, name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> PartitionedBatches:
+        """inputs [B, S] i64 (this rank's batches; device or pinned host) -> PartitionedBatches"""
+        seed = _rng_get() if seed is None else seed
+        marks = [] if self.profile is not None else None
+        with torch.cuda.device(self.device):
+            self.begin(inputs, seed, batch_base)
+            self._mark(marks, "start")
+            for h in range(len(self.fanouts)):
+                self.scatter(h)
+                self._mark(marks, "scatter_put")
+                self.buf.barrier()       # every requester's rows and counts are in every owner's buffers
+                self._mark(marks, "barrier_requests")
+                self.serve(h)
+                self._mark(marks, "serve")
+                self.buf.barrier()       # every owner's answer rows are in every requester's buffer
+                self._mark(marks, "barrier_answers")
+                self.finish(h)
+                self._mark(marks, "layout")
+            out = self.end()
+        if marks is not None:
+            for (_, e0), (name, e1) in zip(marks[:-1], marks[1:]):
+                self.profile[name] = self.profile.get(name, 0.0) + e0.elapsed_time(e1)
+            self.profile["calls"] = self.profile.get("calls", 0) + 1
+        return out
+
+
+def sample_virtual_ranks(plans: List[PartitionedPlanF], inputs: List[Tensor], seed: int, batch_bases: List[int]):
+    """Drive the plans of `world` virtual ranks that share ONE device through a step in lock step (phase by phase, in
+    stream order): what the barriers do on real ranks.  -> one PartitionedBatches per rank."""
+    for p, x, bb in zip(plans, inputs, batch_bases):
+        p.begin(x, seed, bb)
+    for h in range(len(plans[0].fanouts)):
+        for p in plans:
+            p.scatter(h)
+        for p in plans:
+            p.serve(h)
+        for p in plans:
+            p.finish(h)
+    return [p.end() for p in plans]

@@ -215,3 +215,63 @@ def test_peer_request_scatter_places_groups_like_the_request_all_to_all(thg, fak
         owner = torch.clamp(a[:, 0] // cpr, max=world - 1)
         assert (owner == o).all()
         off += c[o]
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_fixed_segment_protocol_equals_replicated(thg, fakedataset, world):
+    """The device-only protocol (csrc/partitioned_fixed.cu: scatter + put -> serve -> one-pass finish, fixed per-pair
+    segments, counts on the device) with `world` virtual ranks on this GPU, each sampling its OWN batches from its
+    own column range: every rank's result equals the replicated sampler bit for bit, for all three samplers."""
+    from tch_geometric.partitioned import (ColumnPartition, PartitionedPlanF, SegmentBuffers, frontier_caps,
+                                           sample_virtual_ranks)
+    ei, n = fakedataset
+    ptrs, idx, _ = thg.to_csc(dev(ei), n)
+    w = dev(np.random.default_rng(3).integers(1, 40, idx.numel()) / 8.0, torch.float64)
+    parts = [ColumnPartition.from_full(ptrs, idx, r, world, w) for r in range(world)]
+    B, S, fan = 5, 33, [15, 10, 5]
+    rng = np.random.default_rng(1)
+    inputs = [dev(rng.integers(0, n, (B, S))) for _ in range(world)]
+    inputs[0][1, :4] = inputs[0][1, 4]                               # duplicated seeds
+    bases = [4 + r * B for r in range(world)]
+    for sampler in (None, thg.UniformEdgeSampler(True), thg.WeightedEdgeSampler(w)):
+        bufs = SegmentBuffers.virtual(B, frontier_caps(S, fan), fan, world, ptrs.device, slack=3.0)
+        plans = [PartitionedPlanF(parts[r], B, S, fan, sampler, world=world, rank=r, buffers=bufs[r],
+                                  edge_bases=[p.edge_base for p in parts], slack=3.0) for r in range(world)]
+        for rep in range(2):                                         # the buffers are reused across steps
+            outs = sample_virtual_ranks(plans, inputs, 9 + rep, bases)
+            for r in range(world):
+                want = thg.neighbor_sampling_homogenous_batched(ptrs, idx, inputs[r], fan, sampler, seed=9 + rep,
+                                                                batch_base=bases[r])
+                got = outs[r]
+                assert (got.samples_len == want.samples_len).all() and (got.edges_len == want.edges_len).all()
+                assert (got.layer_offsets == want.layer_offsets).all()
+                for b in range(B):
+                    for g, x in zip(got.batch(b)[:4], want.batch(b)[:4]):
+                        assert torch.equal(g, x)
+    thg.clear_caches()
+
+
+def test_fixed_segment_protocol_errors(thg, fakedataset):
+    from tch_geometric.partitioned import (ColumnPartition, PartitionedPlanF, SegmentBuffers, frontier_caps,
+                                           sample_virtual_ranks)
+    ei, n = fakedataset
+    ptrs, idx, _ = thg.to_csc(dev(ei), n)
+    world, B, S, fan = 2, 2, 64, [6, 3]
+    parts = [ColumnPartition.from_full(ptrs, idx, r, world) for r in range(world)]
+
+    def plans_with(slack):
+        bufs = SegmentBuffers.virtual(B, frontier_caps(S, fan), fan, world, ptrs.device, slack=slack)
+        return [PartitionedPlanF(parts[r], B, S, fan, None, world=world, rank=r, buffers=bufs[r],
+                                 edge_bases=[p.edge_base for p in parts], slack=slack) for r in range(world)]
+    # every seed belongs to rank 0's range: rank 0's segment at a tight slack overflows -> capacity error, no corruption
+    skew = [dev(np.random.default_rng(r).integers(0, parts[0].col_end, (B, S))) for r in range(world)]
+    ps = plans_with(0.6)
+    if ps[0].segs[0] < B * S:
+        with pytest.raises(MemoryError):
+            sample_virtual_ranks(ps, skew, 1, [0, B])
+    # an out-of-range seed is reported by the owner it is routed to
+    bad = [x.clone() for x in skew]
+    bad[1][0, 0] = n + 77
+    with pytest.raises((thg.ReferencePanic, MemoryError)):
+        sample_virtual_ranks(plans_with(4.0), bad, 1, [0, B])
+    thg.clear_caches()

@@ -1,10 +1,12 @@
-"""Multi-GPU check + timing of the range-partitioned CSC path (BASELINE config 5 shape, scaled).
+"""Multi-GPU parity check of the range-partitioned CSC path at the FULL BASELINE config-5 shape.
 
-    torchrun --nproc-per-node G tools/check_partitioned.py [--scale 0.05] [--batches 16]
+    torchrun --nproc-per-node G tools/check_partitioned.py [--scale 1.0] [--batches 32] [--protocol fixed|legacy]
 
-Every rank builds the same synthetic graph, keeps only its column range for sampling, and verifies that
-the partitioned result (NCCL all-to-all frontier exchange) equals the replicated single-GPU sampler bit
-for bit.  Prints one JSON line from rank 0."""
+Every rank builds its share of the papers100M-shaped graph (13.9 M columns / 202 M edges per rank at scale 1: with 8
+ranks exactly N = 111 059 956, E = 1 615 685 872), the shares are gathered so that every rank ALSO holds the whole CSC
+(13.8 GB: it fits one B200), and the partitioned sampler (frontier exchange over NVLink, this rank's own seed batches)
+is compared with the replicated sampler on the same seeds bit for bit: samples, rows, cols, edge_index, layer offsets of
+every batch.  Prints one JSON line from rank 0; exit code 1 on a mismatch."""
 import argparse
 import json
 import os
@@ -18,81 +20,80 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import tch_geometric as thg  # noqa: E402
-from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedPlan, PartitionedSampler  # noqa: E402
+from tch_geometric.partitioned import DistComm, PartitionedPlan, PartitionedPlanF  # noqa: E402
 from tools import synth  # noqa: E402
+
+
+def gather_full_csc(part, world, rank, device):
+    """every rank's (rebased colptr, row_indices) -> the whole CSC on every rank (one broadcast per owner)"""
+    ptr_parts, idx_parts = [], []
+    for r in range(world):
+        meta = torch.tensor([part.ptrs.numel(), part.indices.numel(), part.edge_base], dtype=torch.int64, device=device)
+        dist.broadcast(meta, src=r)
+        np_, ni_, base = (int(x) for x in meta.tolist())
+        p = part.ptrs.clone() if r == rank else torch.empty(np_, dtype=torch.int64, device=device)
+        i = part.indices if r == rank else torch.empty(ni_, dtype=torch.int64, device=device)
+        dist.broadcast(p, src=r)
+        dist.broadcast(i, src=r)
+        ptr_parts.append((p[:-1] if r < world - 1 else p) + base)
+        idx_parts.append(i)
+    return torch.cat(ptr_parts), torch.cat(idx_parts)
 
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--scale", type=float, default=0.05)
-    ap.add_argument("--batches", type=int, default=16)
-    ap.add_argument("--iters", type=int, default=3)
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--batches", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--protocol", default="fixed", choices=["fixed", "legacy"])
+    ap.add_argument("--slack", type=float, default=1.5)
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     device = torch.device("cuda", local)
     torch.cuda.set_device(device)
     os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
     dist.init_process_group("nccl", device_id=device)
-    ei, n = synth.products_like(device, scale=args.scale)
-    ptrs, idx, _ = thg.to_csc(ei, n)
-    part = ColumnPartition.from_full(ptrs, idx, rank, world)
+    t0 = time.time()
+    part, n, e_total, cols_rank = synth.papers_partition(thg, rank, world, device, args.scale)
+    ptrs, idx = gather_full_csc(part, world, rank, device)
+    assert ptrs.numel() == n + 1 and idx.numel() == e_total and int(ptrs[-1].item()) == e_total
+    torch.cuda.synchronize()
+    t_build = time.time() - t0
     fan, S, B = [15, 10, 5], 1024, args.batches
-    seeds = torch.from_numpy(synth.seed_batches(n, B, S, first_batch=rank * B)).to(device)
-    ps = PartitionedSampler(part, fan, comm=DistComm())
-    got = ps.sample(seeds, seed=31, batch_base=rank * B)
-    want = thg.neighbor_sampling_homogenous_batched(ptrs, idx, seeds, fan, seed=31, batch_base=rank * B)
-    ok = True
-    for b in range(B):
-        ok &= all(torch.equal(g, x) for g, x in zip(got[b][:4], want.batch(b)[:4]))
-        ok &= list(got[b][4]) == list(want.batch(b)[4])
-    edges = sum(int(g[1].numel()) for g in got)
-    # the device pipeline (what bench.py --workload partitioned times): with the answer all-to-all, and with the answers
-    # stored straight into the requesters' buffers over NVLink peer memory (the default when symmetric memory works)
-    plan_a2a = PartitionedPlan(part, B, S, fan, comm=DistComm(), peer_answers=False)
-    plan = PartitionedPlan(part, B, S, fan, comm=DistComm())
-    peer_mode = plan.peer is not None
-    for pl in (plan_a2a, plan):
-        for sd in (31, 32):   # twice: the second call reuses the persistent buffers
-            res = pl.sample(seeds, seed=sd, batch_base=rank * B)
-            ref = want if sd == 31 else thg.neighbor_sampling_homogenous_batched(ptrs, idx, seeds, fan, seed=sd, batch_base=rank * B)
-            ok_plan = bool((res.layer_offsets == ref.layer_offsets).all())
-            for b in range(B):
-                ok_plan &= all(torch.equal(g, x) for g, x in zip(res.batch(b)[:4], ref.batch(b)[:4]))
-            ok &= ok_plan
-    dist.barrier()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for it in range(args.iters):
-        ps.sample(seeds, seed=100 + it, batch_base=rank * B)
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt_torch = (time.perf_counter() - t0) / args.iters
-    t0 = time.perf_counter()
-    for it in range(args.iters):
-        plan_a2a.sample(seeds, seed=100 + it, batch_base=rank * B)
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt_a2a = (time.perf_counter() - t0) / args.iters
-    t0 = time.perf_counter()
-    for it in range(args.iters):
-        plan.sample(seeds, seed=100 + it, batch_base=rank * B)
-    torch.cuda.synchronize()
-    dist.barrier()
-    dt = (time.perf_counter() - t0) / args.iters
-    flag = torch.tensor([1.0 if ok else 0.0, float(edges)], device=device, dtype=torch.float64)
-    dist.all_reduce(flag, op=dist.ReduceOp.SUM)
+    if args.protocol == "fixed":
+        plan = PartitionedPlanF(part, B, S, fan, comm=DistComm(), slack=args.slack)
+    else:
+        plan = PartitionedPlan(part, B, S, fan, comm=DistComm())
+    ref = thg.HomogenousSampler(ptrs, idx, B, S, fan)
+    ok, edges, mism = True, 0, []
+    for step in range(args.steps):          # twice: the second step reuses the exchange buffers
+        bb = (step * world + rank) * B
+        seeds = torch.from_numpy(synth.seed_batches(n, B, S, first_batch=bb)).to(device)
+        got = plan.sample(seeds, seed=31 + step, batch_base=bb)
+        want = ref.sample(seeds, seed=31 + step, batch_base=bb)
+        same = bool((got.samples_len == want.samples_len).all() and (got.edges_len == want.edges_len).all()
+                    and (got.layer_offsets == want.layer_offsets).all())
+        for b in range(B):
+            if not same:
+                break
+            same &= all(torch.equal(g, x) for g, x in zip(got.batch(b)[:4], want.batch(b)[:4]))
+        if not same:
+            mism.append(step)
+        ok &= same
+        edges += int(got.edges_len.sum())
+    flag = torch.tensor([1 if ok else 0], device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    tot = torch.tensor([edges], dtype=torch.int64, device=device)
+    dist.all_reduce(tot)
     if rank == 0:
-        print(json.dumps({"check": "partitioned == replicated (bit-exact)", "ranks_ok": int(flag[0].item()), "world": world,
-                          "graph": {"nodes": n, "edges": int(idx.numel())}, "batches_per_rank": B,
-                          "edges_per_call_all_ranks": flag[1].item(), "sec_per_call": dt,
-                          "answer_exchange": "peer-memory stores from the serve kernel" if peer_mode else "all-to-all",
-                          "sec_per_call_answer_all_to_all": dt_a2a,
-                          "sec_per_call_torch_orchestration": dt_torch,
-                          "edges_per_sec": flag[1].item() / dt, "request_bytes": ps.stats["request_bytes"],
-                          "answer_bytes": ps.stats["answer_bytes"]}), flush=True)
+        print(json.dumps({"check": "partitioned == replicated, bit for bit, every batch of every rank",
+                          "ok": bool(flag.item()), "protocol": args.protocol, "world": world, "N": n, "E": e_total,
+                          "columns_per_rank": cols_rank, "batches_per_rank": B, "steps": args.steps,
+                          "edges_compared": int(tot.item()), "rank0_mismatching_steps": mism,
+                          "full_csc_bytes_per_rank": int(ptrs.numel() + idx.numel()) * 8, "build_s": round(t_build, 1),
+                          "slack": args.slack if args.protocol == "fixed" else None}), flush=True)
     dist.destroy_process_group()
-    if not ok:
-        sys.exit(1)
+    sys.exit(0 if flag.item() else 1)
 
 
 if __name__ == "__main__":

@@ -97,3 +97,29 @@ def seed_batches(num_nodes, num_batches, seeds_per_batch, first_batch=0):
     for b in range(num_batches):
         out[b] = np.random.default_rng(1234 + first_batch + b).choice(num_nodes, seeds_per_batch, replace=False)
     return out
+
+
+def papers_partition(thg, rank, world, device, scale=1.0):
+    """This rank's share of the papers100M-shaped graph (BASELINE config 5): 13 882 495 columns / ~202 M edges per rank,
+    so 8 ranks hold exactly the 111 059 956-node, 1 615 685 872-edge shape (weak scaling in the number of ranks).
+    -> (ColumnPartition, n, e_total, cols_per_rank).  Collective when world > 1 (all-gather of the edge counts)."""
+    import torch.distributed as dist
+    from tch_geometric.partitioned import ColumnPartition, partition_bounds
+    cols_full, edges_full = 111_059_956 // 8 + 1, 1_615_685_872 // 8
+    cols_rank = max(int(cols_full * scale), 64)
+    n = cols_rank * world
+    b, e = partition_bounds(n, rank, world)
+    deg = lognormal_degrees(e - b, max(int(edges_full * scale), e - b), dmax=17_481, seed=42 + rank)
+    ei = edges_from_degrees(deg, n, device, seed=42 + rank)            # rows over all N nodes, cols local
+    ptrs, idx, _ = thg.to_csc(ei, (n, e - b))
+    del ei
+    torch.cuda.empty_cache()
+    e_local = torch.tensor([idx.numel()], dtype=torch.int64, device=device)
+    if world > 1:
+        allc = [torch.zeros_like(e_local) for _ in range(world)]
+        dist.all_gather(allc, e_local)
+        edge_base = int(sum(int(x.item()) for x in allc[:rank]))
+        e_total = int(sum(int(x.item()) for x in allc))
+    else:
+        edge_base, e_total = 0, int(e_local.item())
+    return ColumnPartition(ptrs, idx, n, rank, world, edge_base), n, e_total, cols_rank
