@@ -172,17 +172,22 @@ __device__ __forceinline__ Philox4 philox_rk(uint32_t c0, uint32_t c1, uint32_t 
 
 // steps step0 .. step0+3 of the serial reservoir (sampling.rs:17-23): a hit (j < k) overwrites slot j, the LAST hit of a
 // slot wins -> max of the step index
-__device__ __forceinline__ void reservoir_block(const Philox4& r, uint32_t step0, uint32_t deg, uint32_t k, uint32_t* slots) {
+// (`slots_sa` is a 32-bit shared-state-space address; the update is a predicated red.shared.max: no branch)
+__device__ __forceinline__ void reservoir_block(const Philox4& r, uint32_t step0, uint32_t deg, uint32_t k, uint32_t slots_sa) {
 #pragma unroll
   for (uint32_t u = 0; u < 4; ++u) {
     const uint32_t step = step0 + u;
     const uint32_t j = __umulhi(pick4(r, u), step);
-    if ((step < deg) & (j < k)) atomicMax(slots + j, step);
+    const uint32_t hit = (uint32_t)((step < deg) & (j < k));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p red.shared.max.u32 [%0], %1;\n\t}"
+        ::"r"(slots_sa + 4u * j), "r"(step), "r"(hit)
+        : "memory");
   }
 }
 
 template <int KIND, bool I32>
-__global__ void __launch_bounds__(SV_THREADS, 8) pf_serve_kernel(const ServeParams p) {
+__global__ void __launch_bounds__(SV_THREADS, 10) pf_serve_kernel(const ServeParams p) {
   constexpr int NT = SV_THREADS, NW = NT / 32;
   __shared__ int64_t s_start[NT];
   __shared__ uint32_t s_deg[NT], s_pos[NT], s_batch[NT], s_choff[NT];
@@ -260,14 +265,15 @@ __global__ void __launch_bounds__(SV_THREADS, 8) pf_serve_kernel(const ServePara
   // ---- C: sampling decisions in shared memory (same Philox counters as hop_kernel) ------------------------------
   if (KIND == TCHGEO_SAMPLER_UNIFORM) {
     const uint32_t tag = TAG_RESERVOIR | (p.rel << 8);
+    const uint32_t slot_sa = (uint32_t)__cvta_generic_to_shared(s_slot);
 #pragma unroll 1
     for (uint32_t qi = tid; qi < Q; qi += NT) {  // (request, 8-step chunk) work items: Philox blocks 2c and 2c+1
       const uint32_t n = s_chown[qi];
       const uint32_t c = qi - s_choff[n];
       const uint32_t dn = s_deg[n], step0 = k + 8u * c;
-      uint32_t* slots = s_slot + n * k;
-      reservoir_block(philox_rk(s_pos[n], 2u * c, s_batch[n], tag, p.rk), step0, dn, k, slots);
-      if (step0 + 4u < dn) reservoir_block(philox_rk(s_pos[n], 2u * c + 1u, s_batch[n], tag, p.rk), step0 + 4u, dn, k, slots);
+      const uint32_t sa = slot_sa + 4u * n * k;
+      reservoir_block(philox_rk(s_pos[n], 2u * c, s_batch[n], tag, p.rk), step0, dn, k, sa);
+      if (step0 + 4u < dn) reservoir_block(philox_rk(s_pos[n], 2u * c + 1u, s_batch[n], tag, p.rk), step0 + 4u, dn, k, sa);
     }
     const uint32_t nheavy = s_nheavy;
     for (uint32_t h = 0; h < nheavy; ++h) {   // hubs: the whole CTA strides over one request's 4-step blocks
@@ -275,7 +281,7 @@ __global__ void __launch_bounds__(SV_THREADS, 8) pf_serve_kernel(const ServePara
       const uint32_t dn = s_deg[n], nb = (dn - k + 3u) >> 2;
 #pragma unroll 1
       for (uint32_t c = tid; c < nb; c += NT)
-        reservoir_block(philox_rk(s_pos[n], c, s_batch[n], tag, p.rk), k + 4u * c, dn, k, s_slot + n * k);
+        reservoir_block(philox_rk(s_pos[n], c, s_batch[n], tag, p.rk), k + 4u * c, dn, k, slot_sa + 4u * n * k);
     }
   } else if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
     const uint32_t rtag = TAG_REPLACE | (p.rel << 8);
@@ -324,19 +330,34 @@ __global__ void __launch_bounds__(SV_THREADS, 8) pf_serve_kernel(const ServePara
 
   // ---- D: gathers, answer rows staged in shared memory, one linear run of stores into the requester's segment ----
   const uint32_t w2 = 2u * k;
+  constexpr uint32_t U = 5;  // gathers in flight per thread (the whole tile in one round when fanout <= 5)
+  const uint32_t total = (uint32_t)nn * k;
 #pragma unroll 1
-  for (uint32_t e = tid; e < (uint32_t)nn * k; e += NT) {
-    const uint32_t n = e / k, s = e - n * k;
-    const uint32_t dn = s_deg[n];
-    const uint32_t cnt = KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE ? (dn > 0 ? k : 0u) : min(dn, k);
-    int32_t id = -1, lp32 = -1;
-    if (s < cnt) {
-      const int64_t lp = s_start[n] + s_slot[e];
-      id = I32 ? ld_gather64_i32(p.indices32 + lp) : (int32_t)ld_gather64_i64(p.indices + lp);
-      lp32 = (int32_t)lp;
+  for (uint32_t e0 = tid; e0 < total; e0 += NT * U) {
+    uint32_t at[U];
+    int32_t id[U], lp32[U];
+#pragma unroll
+    for (uint32_t u = 0; u < U; ++u) {
+      const uint32_t e = e0 + u * NT;
+      id[u] = -1; lp32[u] = -1; at[u] = 0xffffffffu;
+      if (e < total) {
+        const uint32_t n = e / k, s = e - n * k;
+        const uint32_t dn = s_deg[n];
+        const uint32_t cnt = KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE ? (dn > 0 ? k : 0u) : min(dn, k);
+        at[u] = n * w2 + s;
+        if (s < cnt) {
+          const int64_t lp = s_start[n] + s_slot[e];
+          id[u] = I32 ? ld_gather64_i32(p.indices32 + lp) : (int32_t)ld_gather64_i64(p.indices + lp);
+          lp32[u] = (int32_t)lp;
+        }
+      }
     }
-    s_ans[n * w2 + s] = id;
-    s_ans[n * w2 + k + s] = lp32;
+#pragma unroll
+    for (uint32_t u = 0; u < U; ++u)
+      if (at[u] != 0xffffffffu) {
+        s_ans[at[u]] = id[u];
+        s_ans[at[u] + k] = lp32[u];
+      }
   }
   __syncthreads();
   int32_t* dst = p.peer_ans[q] + ((int64_t)p.me * p.seg + r0) * w2;
