@@ -286,30 +286,36 @@ __global__ void __launch_bounds__(RL_THREADS) rl_lookup_kernel(const RlParams p)
 
 // =================================================================================================
 // Persistent form (the one the sampling plan uses when the ids fit 32 bits): ONE cooperative launch per call.
-// The grid is G groups of C co-resident CTAs; group g owns one hash table and walks trees g, g+G, ... through
-//   clear -> insert -> count -> assign -> lookup
-// with a group barrier between the phases (an arrive counter + generation word per group: only the C CTAs that share
-// a tree ever wait for each other).  At any moment only G tables (8 MB each for the products configuration), G slot
-// maps and the G trees in flight are live, so every table access and every re-read of the ids is an L2 hit, and DRAM
-// sees 8 B read + (8 B local + <= 8 B nodes) written per id.  One table slot is ONE 64-bit word (key << 32 | priority),
-// so the common insert (a new id) is a single atomicCAS; a second occurrence adds one 64-bit atomicMin (equal keys:
-// the smaller priority wins); the winner later overwrites the priority with (1 << 31 | rank) in place.
-// Everything the CTAs of a group hand to each other (table, slot map, state bytes, CTA counts) is read with ld.cg:
-// the L1 is not coherent and the same addresses are reused tree after tree.
-// The co-residency the barriers rely on is what cudaLaunchCooperativeKernel guarantees (two plans on two streams would
+// The grid is G groups of C co-resident CTAs; a group owns TWO hash tables and walks its trees two at a time:
+//     insert(a) insert(b) compact(a) compact(b) clear(a) clear(b) insert(a') ...
+// Only two things make a phase wait -- "every CTA of the group has finished the previous phase ON THE SAME TABLE" --
+// and between that arrival and the wait lies a whole phase of the OTHER tree, so the barrier latency and the spread of
+// the CTAs' finishing times are hidden (split arrive / wait on monotonic counters; the first version had five blocking
+// barriers per tree and spent 52 % of its warp time in them).
+//   insert   one table slot is ONE 64-bit word (key << 32 | priority): a new id is a single atomicCAS, a second
+//            occurrence adds one 64-bit atomicMin (equal keys: the smaller priority wins); double hashing (a group waits
+//            for the LONGEST probe sequence of the tree); eight ids per thread in flight
+//   compact  flags, block scan, decoupled look-back over the tree's tiles (tiles are taken in order, so every tile a
+//            look-back waits for is running or done), node list, local ids.  The first occurrence of an id overwrites its
+//            priority with (1 << 31 | rank); a later occurrence spins on that bit -- its winner sits at a smaller
+//            position, i.e. in an earlier tile or in this one -- so no separate lookup pass and no state bytes
+// At any moment only 2G tables, slot maps and trees are live, so table accesses and re-reads of the ids are L2 hits and
+// DRAM sees 8 B read + (8 B local + <= 8 B nodes) written per id.  Everything CTAs hand to each other is read with ld.cg /
+// ld.relaxed.gpu: the L1 is not coherent and the same addresses are reused tree after tree.
+// The co-residency the waits rely on is what cudaLaunchCooperativeKernel guarantees (two plans on two streams would
 // otherwise be able to starve each other's CTAs).
 // =================================================================================================
 constexpr int RP_THREADS = 512;
-constexpr int RP_ITEMS = 4;                       // consecutive positions per thread in the scan phases
+constexpr int RP_ITEMS = 4;                       // consecutive positions per thread in the compact phase
 constexpr int RP_TILE = RP_THREADS * RP_ITEMS;
-constexpr int RP_MAX_GROUPS = 32;
-constexpr int RP_MAX_CTAS = 4096;                 // bound of the grid (cta_count scratch)
+constexpr int RP_INS = 8;                         // ids per thread in flight in the insert phase
+constexpr int RP_MAX_GROUPS = 16;
+constexpr int RP_MAX_CTAS = 4096;
 constexpr unsigned long long RP_EMPTY = ~0ull;
 constexpr uint32_t RP_RANKED = 0x80000000u;
-// per-position state byte written by the count phase
-constexpr uint32_t RP_F_NODE = 1u;      // emits a node (every seed; a non-seed holding its id's minimum)
-constexpr uint32_t RP_F_PUBLISH = 2u;   // first occurrence of a non-seed id: publishes its rank in the table
-constexpr uint32_t RP_F_PENDING = 4u;   // later occurrence of a non-seed id: local[] comes from the published rank
+constexpr uint64_t RP_EPOCH_SHIFT = 40;           // look-back word: flag (2) | epoch (22) | value (40)
+constexpr uint64_t RP_VAL_MASK = (1ull << RP_EPOCH_SHIFT) - 1;
+enum { RP_EV_CLEAR = 0, RP_EV_INSERT = 1, RP_EV_COMPACT = 2 };
 
 struct RpParams {
   const int64_t* samples;
@@ -318,15 +324,14 @@ struct RpParams {
   int64_t* nodes;
   int64_t* local;
   int64_t* nodes_len;
-  int64_t num_seeds, n_max, n_pad;   // n_pad: n_max rounded up to a multiple of RP_ITEMS (row pitch of the scratch maps)
-  int32_t num_trees, groups, ctas_per_group;
+  int64_t num_seeds, n_max, n_pad;   // n_pad: row pitch of the slot maps (multiple of RP_ITEMS)
+  int32_t num_trees, groups, ctas_per_group, tiles_per_tree;
   uint32_t cap_mask;
   int32_t hash_shift;
-  unsigned long long* tables;        // [groups, slots]
-  uint32_t* slot_of;                 // [groups, n_pad]
-  uint8_t* fbytes;                   // [groups, n_pad]
-  uint32_t* cta_count;               // [groups, ctas_per_group]
-  uint32_t* bars;                    // [groups, 32]: [0] arrivals, [1] generation (zero-initialised)
+  unsigned long long* tables;        // [groups, 2, slots]
+  uint32_t* slot_of;                 // [groups, 2, n_pad]
+  unsigned long long* status;        // [groups, 2, tiles_per_tree] look-back words, tagged with the tree's epoch
+  uint32_t* events;                  // [groups, 32]: monotonic arrival counters [kind * 2 + table] (zero-initialised)
   uint32_t* err;
 };
 
@@ -336,188 +341,169 @@ __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   return v;
 }
 
-// barrier over the `n` CTAs of one group (all co-resident).  Returns false when the watchdog trips.
-__device__ __forceinline__ bool group_sync(uint32_t* bar, uint32_t n, uint32_t* err) {
-  __shared__ uint32_t s_ok;
+// this CTA has finished a phase: everything it wrote becomes visible before the counter moves
+__device__ __forceinline__ void rp_arrive(uint32_t* ev) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    uint32_t ok = 1u;
-    const uint32_t gen = ld_acquire_u32(bar + 1);
     __threadfence();
-    if (atomicAdd(bar, 1u) == n - 1u) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      uint32_t spins = 0;
-      while (ld_acquire_u32(bar + 1) == gen) {
-        if (++spins > (1u << 26)) {
-          atomicOr(err, DEV_ERR_WATCHDOG);
-          ok = 0u;
-          break;
-        }
-        __nanosleep(64);
+    atomicAdd(ev, 1u);
+  }
+}
+// every CTA of the group has arrived `target` times.  Returns false when the watchdog trips.
+__device__ __forceinline__ bool rp_wait(const uint32_t* ev, uint32_t target, uint32_t* err) {
+  __shared__ uint32_t s_ok;
+  if (threadIdx.x == 0) {
+    uint32_t ok = 1u, spins = 0;
+    while ((int32_t)(ld_acquire_u32(ev) - target) < 0) {
+      if (++spins > (1u << 26)) {
+        atomicOr(err, DEV_ERR_WATCHDOG);
+        ok = 0u;
+        break;
       }
+      __nanosleep(40);
     }
-    __threadfence();
     s_ok = ok;
   }
   __syncthreads();
-  return s_ok != 0u;
+  const bool ok = s_ok != 0u;
+  __syncthreads();   // s_ok may be rewritten by the next wait
+  return ok;
 }
+
+struct RpTree {
+  const int64_t* src;
+  int64_t* local;
+  int64_t* nodes;
+  int64_t n;
+  int b;
+};
 
 template <int MINB>
 __global__ void __launch_bounds__(RP_THREADS, MINB) rl_persistent_kernel(const RpParams p) {
   __shared__ uint32_t s_wtot[RP_THREADS / 32];
-  __shared__ uint32_t s_carry;
+  __shared__ int64_t s_excl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = blockIdx.x / p.ctas_per_group, c = blockIdx.x - g * p.ctas_per_group;
   const uint32_t C = (uint32_t)p.ctas_per_group;
-  const int64_t gthreads = (int64_t)C * RP_THREADS;
-  const int64_t gtid = (int64_t)c * RP_THREADS + tid;
-  unsigned long long* tab = p.tables + (size_t)g * ((size_t)p.cap_mask + 1);
-  uint32_t* slot_of = p.slot_of + (size_t)g * p.n_pad;
-  uint8_t* fbytes = p.fbytes + (size_t)g * p.n_pad;
-  uint32_t* cta_count = p.cta_count + (size_t)g * C;
-  uint32_t* bar = p.bars + (size_t)g * 32;
+  const size_t slots = (size_t)p.cap_mask + 1;
+  unsigned long long* tab2 = p.tables + (size_t)g * 2 * slots;
+  uint32_t* slot2 = p.slot_of + (size_t)g * 2 * p.n_pad;
+  unsigned long long* status2 = p.status + (size_t)g * 2 * p.tiles_per_tree;
+  uint32_t* ev = p.events + (size_t)g * 32;
   const int64_t S = p.num_seeds;
   const uint32_t mask = p.cap_mask;
+  const int M = p.num_trees > g ? (p.num_trees - g + p.groups - 1) / p.groups : 0;  // trees of this group: g, g+G, ...
 
-  for (int b = g; b < p.num_trees; b += p.groups) {
-    int64_t n = p.lens[b];
-    n = n < 0 ? 0 : (n > p.n_max ? p.n_max : n);
-    const int64_t* src = p.samples + (int64_t)b * p.stride;
-    int64_t* local = p.local + (int64_t)b * p.stride;
-    int64_t* nodes = p.nodes + (int64_t)b * p.stride;
+  auto tree_of = [&](int m) {
+    RpTree t;
+    t.b = g + m * p.groups;
+    int64_t n = p.lens[t.b];
+    t.n = n < 0 ? 0 : (n > p.n_max ? p.n_max : n);
+    t.src = p.samples + (int64_t)t.b * p.stride;
+    t.local = p.local + (int64_t)t.b * p.stride;
+    t.nodes = p.nodes + (int64_t)t.b * p.stride;
+    return t;
+  };
 
-    // ---- clear the group's table (16-byte stores; the table stays in the L2) -----------------------------------
-    {
-      ulonglong2* t2 = reinterpret_cast<ulonglong2*>(tab);
-      const int64_t n2 = ((int64_t)mask + 1) >> 1;
-      for (int64_t q = gtid; q < n2; q += gthreads) t2[q] = make_ulonglong2(RP_EMPTY, RP_EMPTY);
-    }
-    if (!group_sync(bar, C, p.err)) return;
+  auto clear = [&](int tb) {   // 16-byte stores; the table stays in the L2
+    ulonglong2* t2 = reinterpret_cast<ulonglong2*>(tab2 + (size_t)tb * slots);
+    const int64_t n2 = (int64_t)(slots >> 1);
+    for (int64_t q = (int64_t)c * RP_THREADS + tid; q < n2; q += (int64_t)C * RP_THREADS)
+      t2[q] = make_ulonglong2(RP_EMPTY, RP_EMPTY);
+  };
 
-    // ---- insert: four ids per thread in flight ------------------------------------------------------------------
-    for (int64_t i0 = gtid; i0 < n; i0 += 4 * gthreads) {
-      int64_t key[4];
-      unsigned long long want[4], old[4];
-      uint32_t h[4];
+  auto insert = [&](int m) {
+    const RpTree t = tree_of(m);
+    unsigned long long* tab = tab2 + (size_t)(m & 1) * slots;
+    uint32_t* slot_of = slot2 + (size_t)(m & 1) * p.n_pad;
+    constexpr int64_t BLK = (int64_t)RP_THREADS * RP_INS;
+    for (int64_t i0 = (int64_t)c * BLK; i0 < t.n; i0 += (int64_t)C * BLK) {
+      // (32-bit keys and no `want` array: eight inserts in flight must fit the 64-register budget)
+      uint32_t key[RP_INS], h[RP_INS];
+      unsigned long long old[RP_INS];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + u * gthreads;
-        key[u] = i < n ? __ldg(src + i) : -1;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + u * gthreads;
-        old[u] = RP_EMPTY;
-        want[u] = 0ull;
+      for (int u = 0; u < RP_INS; ++u) {
+        const int64_t i = i0 + u * RP_THREADS + tid;
         h[u] = RL_NOSLOT;
-        if (i >= n) continue;
-        if ((uint64_t)key[u] >= 0xFFFFFFFFull) {
-          atomicOr(p.err, DEV_ERR_INDEX);
-          continue;
+        key[u] = 0xFFFFFFFFu;
+        if (i < t.n) {
+          const int64_t k64 = __ldg(t.src + i);
+          if ((uint64_t)k64 >= 0xFFFFFFFFull) atomicOr(p.err, DEV_ERR_INDEX);
+          else key[u] = (uint32_t)k64;
         }
+      }
+      auto want_of = [&](int u) {
+        const int64_t i = i0 + u * RP_THREADS + tid;
         const uint32_t prio = i < S ? (uint32_t)(S - 1 - i) : (uint32_t)i;
-        want[u] = ((unsigned long long)(uint32_t)key[u] << 32) | prio;
-        h[u] = (((uint32_t)key[u] * 0x9E3779B1u) >> p.hash_shift) & mask;
-        old[u] = atomicCAS(tab + h[u], RP_EMPTY, want[u]);  // the common case (a new id, a free slot): one atomic
+        return ((unsigned long long)key[u] << 32) | prio;
+      };
+#pragma unroll
+      for (int u = 0; u < RP_INS; ++u) {
+        old[u] = RP_EMPTY;
+        if (key[u] == 0xFFFFFFFFu) continue;
+        h[u] = ((key[u] * 0x9E3779B1u) >> p.hash_shift) & mask;
+        old[u] = atomicCAS(tab + h[u], RP_EMPTY, want_of(u));  // the common case (a new id, a free slot): one atomic
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int64_t i = i0 + u * gthreads;
-        if (i >= n) continue;
+      for (int u = 0; u < RP_INS; ++u) {
+        const int64_t i = i0 + u * RP_THREADS + tid;
+        if (i >= t.n) continue;
         if (h[u] != RL_NOSLOT) {
           unsigned long long o = old[u];
-          // double hashing (odd step: every slot of the power-of-two table is visited): a group waits at its barrier
-          // for the LONGEST probe sequence of the tree, and linear probing's clusters made that 30 % of the kernel
-          const uint32_t step = (((uint32_t)key[u] * 0x85EBCA6Bu) >> 7) | 1u;
+          const uint32_t step = ((key[u] * 0x85EBCA6Bu) >> 7) | 1u;  // odd: visits every slot
           while (o != RP_EMPTY) {                                  // slot taken
-            if ((uint32_t)(o >> 32) == (uint32_t)key[u]) {          // by the same id: the smaller priority wins
-              atomicMin(tab + h[u], want[u]);
+            if ((uint32_t)(o >> 32) == key[u]) {                    // by the same id: the smaller priority wins
+              atomicMin(tab + h[u], want_of(u));
               break;
             }
             h[u] = (h[u] + step) & mask;                            // by another id: next slot of the id's sequence
-            o = atomicCAS(tab + h[u], RP_EMPTY, want[u]);
+            o = atomicCAS(tab + h[u], RP_EMPTY, want_of(u));
           }
         }
         slot_of[i] = h[u];
       }
     }
-    if (!group_sync(bar, C, p.err)) return;
+  };
 
-    // ---- count: per-position state, local[] of everything that needs no rank, flags per CTA chunk ---------------
-    // CTA c owns the contiguous positions [c0, c1); a thread owns RP_ITEMS consecutive ones (one uint4 of slot_of)
-    int64_t chunk = (n + C - 1) / C;
-    chunk = (chunk + RP_TILE - 1) / RP_TILE * RP_TILE;
-    const int64_t c0 = min(n, (int64_t)c * chunk), c1 = min(n, c0 + chunk);
-    uint32_t my_flags = 0;
-    for (int64_t t0 = c0; t0 < c1; t0 += RP_TILE) {
-      const int64_t ibase = t0 + (int64_t)tid * RP_ITEMS;
-      if (ibase >= c1) continue;
-      const uint4 sv = __ldcg(reinterpret_cast<const uint4*>(slot_of + ibase));
-      const uint32_t sl[4] = {sv.x, sv.y, sv.z, sv.w};
-      unsigned long long e[4];
+  auto compact = [&](int m) {
+    const RpTree t = tree_of(m);
+    unsigned long long* tab = tab2 + (size_t)(m & 1) * slots;
+    const uint32_t* slot_of = slot2 + (size_t)(m & 1) * p.n_pad;
+    unsigned long long* status = status2 + (size_t)(m & 1) * p.tiles_per_tree;
+    const uint64_t epoch = (uint64_t)(t.b + 1) << RP_EPOCH_SHIFT;   // words of earlier trees read as "not published"
+    const int64_t ntiles = t.n > 0 ? (t.n + RP_TILE - 1) / RP_TILE : 1;
+    for (int64_t tile = c; tile < ntiles; tile += C) {   // in increasing order: look-backs only wait for smaller tiles
+      const int64_t ibase = tile * RP_TILE + (int64_t)tid * RP_ITEMS;
+      uint32_t sl[RP_ITEMS] = {RL_NOSLOT, RL_NOSLOT, RL_NOSLOT, RL_NOSLOT};
+      unsigned long long e[RP_ITEMS];
+      if (ibase < t.n) {
+        const uint4 sv = __ldcg(reinterpret_cast<const uint4*>(slot_of + ibase));
+        sl[0] = sv.x; sl[1] = sv.y; sl[2] = sv.z; sl[3] = sv.w;
+      }
 #pragma unroll
-      for (int u = 0; u < RP_ITEMS; ++u) e[u] = (ibase + u < c1 && sl[u] != RL_NOSLOT) ? __ldcg(tab + sl[u]) : 0ull;
-      uint32_t st4 = 0;
+      for (int u = 0; u < RP_ITEMS; ++u) e[u] = (ibase + u < t.n && sl[u] != RL_NOSLOT) ? __ldcg(tab + sl[u]) : 0ull;
+      uint32_t node = 0, pend = 0;   // bit u: position ibase+u emits a node / waits for its winner's rank
+      uint32_t cnt = 0;
 #pragma unroll
       for (int u = 0; u < RP_ITEMS; ++u) {
         const int64_t i = ibase + u;
-        if (i >= c1) continue;
-        uint32_t st = 0;
+        if (i >= t.n) continue;
         if (sl[u] == RL_NOSLOT) {                 // id outside the 32-bit range (already reported)
-          st = i < S ? RP_F_NODE : 0u;
-          local[i] = -1;
-        } else {
-          const uint32_t pr = (uint32_t)e[u];
-          if (pr < (uint32_t)S) {                 // a seed carries this id: the map points at its LAST seed slot (:26)
-            st_cs_i64(local + i, S - 1 - (int64_t)pr);
-            if (i < S) st = RP_F_NODE;            // every seed is kept (:25); its rank is its own index
-          } else if (pr == (uint32_t)i) {
-            st = RP_F_NODE | RP_F_PUBLISH;        // first occurrence of an id no seed carries (:36-39)
-          } else {
-            st = RP_F_PENDING;
-          }
+          if (i < S) node |= 1u << u;
+          t.local[i] = -1;
+          continue;
         }
-        my_flags += st & RP_F_NODE;
-        st4 |= st << (8 * u);
+        const uint32_t pr = (uint32_t)e[u];
+        if (pr < (uint32_t)S) {                   // a seed carries this id: the map points at its LAST seed slot (:26)
+          st_cs_i64(t.local + i, S - 1 - (int64_t)pr);
+          if (i < S) node |= 1u << u;             // every seed is kept (:25); its rank is its own index
+        } else if (pr == (uint32_t)i) {
+          node |= 1u << u;                        // first occurrence of an id no seed carries (:36-39)
+        } else {
+          pend |= 1u << u;
+        }
       }
-      *reinterpret_cast<uint32_t*>(fbytes + ibase) = st4;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) my_flags += __shfl_xor_sync(0xffffffffu, my_flags, o);
-    if (lane == 0) s_wtot[warp] = my_flags;
-    __syncthreads();
-    if (tid == 0) {
-      uint32_t tot = 0;
-      for (int w = 0; w < RP_THREADS / 32; ++w) tot += s_wtot[w];
-      cta_count[c] = tot;
-    }
-    if (!group_sync(bar, C, p.err)) return;
-
-    // ---- assign: ranks in position order, node list, ranks published in the table -----------------------------
-    {
-      uint32_t before = 0, total = 0;
-      for (uint32_t q = lane; q < C; q += 32) {
-        const uint32_t v = __ldcg(cta_count + q);
-        total += v;
-        if (q < (uint32_t)c) before += v;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        before += __shfl_xor_sync(0xffffffffu, before, o);
-        total += __shfl_xor_sync(0xffffffffu, total, o);
-      }
-      if (c == 0 && tid == 0) p.nodes_len[b] = (int64_t)total;
-      if (tid == 0) s_carry = before;
-    }
-    __syncthreads();
-    for (int64_t t0 = c0; t0 < c1; t0 += RP_TILE) {
-      const int64_t ibase = t0 + (int64_t)tid * RP_ITEMS;
-      const uint32_t st4 = ibase < c1 ? __ldcg(reinterpret_cast<const uint32_t*>(fbytes + ibase)) : 0u;
-      const uint32_t cnt = __popc(st4 & 0x01010101u);
+      cnt = __popc(node);
       uint32_t incl = cnt;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
@@ -526,77 +512,140 @@ __global__ void __launch_bounds__(RP_THREADS, MINB) rl_persistent_kernel(const R
       }
       if (lane == 31) s_wtot[warp] = incl;
       __syncthreads();
-      uint32_t excl = incl - cnt, tile_total = 0;
+      uint32_t excl = incl - cnt, total = 0;
 #pragma unroll
       for (int w = 0; w < RP_THREADS / 32; ++w) {
         const uint32_t v = s_wtot[w];
         if (w < warp) excl += v;
-        tile_total += v;
+        total += v;
       }
-      uint32_t r = s_carry + excl;
-      if (cnt) {
-        const uint4 sv = __ldcg(reinterpret_cast<const uint4*>(slot_of + ibase));
-        const uint32_t sl[4] = {sv.x, sv.y, sv.z, sv.w};
+      if (tid == 0) st_relaxed_u64((uint64_t*)status + tile, ((tile == 0 ? 2ull : 1ull) << 62) | epoch | (uint64_t)total);
+      if (warp == 0) {
+        int64_t before = 0;
+        if (tile > 0) {
+          int64_t j = tile - 1;
+          uint32_t spins = 0;
+          while (true) {
+            const int64_t idx = j - lane;
+            uint64_t v = idx >= 0 ? ld_relaxed_u64((const uint64_t*)status + idx) : (2ull << 62) | epoch;
+            if ((v & (((1ull << 22) - 1) << RP_EPOCH_SHIFT)) != epoch) v = 0;   // an earlier tree's word
+            const uint32_t flag = (uint32_t)(v >> 62);
+            const uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+            const uint32_t inval_mask = __ballot_sync(0xffffffffu, flag == 0u);
+            const int first_incl = incl_mask ? __ffs(incl_mask) - 1 : 32;
+            const int first_inval = inval_mask ? __ffs(inval_mask) - 1 : 32;
+            if (first_inval < first_incl) {
+              if (++spins > (1u << 24)) {
+                if (lane == 0) atomicOr(p.err, DEV_ERR_WATCHDOG);
+                break;
+              }
+              __nanosleep(20);
+              continue;
+            }
+            int64_t val = lane <= first_incl ? (int64_t)(v & RP_VAL_MASK) : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            before += val;
+            if (first_incl < 32) break;
+            j -= 32;
+          }
+          if (lane == 0) st_relaxed_u64((uint64_t*)status + tile, (2ull << 62) | epoch | (uint64_t)(before + total));
+        }
+        if (lane == 0) s_excl = before;
+      }
+      __syncthreads();
+      const int64_t tile_excl = s_excl;
+      if (tid == 0 && tile == ntiles - 1) p.nodes_len[t.b] = tile_excl + total;
+      uint32_t r = (uint32_t)tile_excl + excl;
+#pragma unroll
+      for (int u = 0; u < RP_ITEMS; ++u) {
+        if (!((node >> u) & 1u)) continue;
+        const int64_t i = ibase + u;
+        const int64_t key = __ldg(t.src + i);
+        st_cs_i64(t.nodes + r, key);
+        if (i >= S && sl[u] != RL_NOSLOT) {     // the occurrence the map points at publishes its rank in place
+          st_cs_i64(t.local + i, (int64_t)r);
+          st_relaxed_u64((uint64_t*)tab + sl[u], ((uint64_t)(uint32_t)key << 32) | RP_RANKED | r);
+        }
+        ++r;
+      }
+      __syncthreads();   // this tile's ranks are on their way before anyone of the CTA starts to wait for ranks
+      if (pend) {
 #pragma unroll
         for (int u = 0; u < RP_ITEMS; ++u) {
-          const uint32_t st = (st4 >> (8 * u)) & 0xffu;
-          if (!(st & RP_F_NODE)) continue;
-          const int64_t i = ibase + u;
-          const int64_t key = __ldg(src + i);
-          st_cs_i64(nodes + r, key);
-          if (st & RP_F_PUBLISH) {
-            st_cs_i64(local + i, (int64_t)r);
-            __stcg(tab + sl[u], ((unsigned long long)(uint32_t)key << 32) | RP_RANKED | r);
+          if (!((pend >> u) & 1u)) continue;
+          uint32_t lo = (uint32_t)e[u], spins = 0;
+          while (!(lo & RP_RANKED)) {             // the winner sits at a smaller position: an earlier tile, or this one
+            lo = (uint32_t)ld_relaxed_u64((const uint64_t*)tab + sl[u]);
+            if (++spins > (1u << 24)) {
+              atomicOr(p.err, DEV_ERR_WATCHDOG);
+              break;
+            }
           }
-          ++r;
+          st_cs_i64(t.local + ibase + u, (int64_t)(lo & 0x7fffffffu));
         }
       }
-      __syncthreads();
-      if (tid == 0) s_carry += tile_total;
-      __syncthreads();
     }
-    if (!group_sync(bar, C, p.err)) return;
+  };
 
-    // ---- lookup: later occurrences of non-seed ids take the rank their first occurrence published -----------
-    for (int64_t i4 = gtid * 4; i4 < n; i4 += 4 * gthreads) {
-      const uint32_t st4 = __ldcg(reinterpret_cast<const uint32_t*>(fbytes + i4));
-      if (!(st4 & 0x04040404u)) continue;
-#pragma unroll
-      for (int u = 0; u < 4; ++u)
-        if (((st4 >> (8 * u)) & RP_F_PENDING) && i4 + u < n)
-          st_cs_i64(local + i4 + u, (int64_t)((uint32_t)__ldcg(tab + __ldcg(slot_of + i4 + u)) & 0x7fffffffu));
+  // ---- the group's schedule: two trees in flight, every wait separated from its arrival by a phase of the other tree ----
+  clear(0);
+  rp_arrive(ev + RP_EV_CLEAR * 2 + 0);
+  clear(1);
+  rp_arrive(ev + RP_EV_CLEAR * 2 + 1);
+  for (int pr = 0; 2 * pr < M; ++pr) {
+    const uint32_t target = C * (uint32_t)(pr + 1);
+    for (int tb = 0; tb < 2; ++tb) {
+      const int m = 2 * pr + tb;
+      if (m >= M) continue;
+      if (!rp_wait(ev + RP_EV_CLEAR * 2 + tb, target, p.err)) return;
+      insert(m);
+      rp_arrive(ev + RP_EV_INSERT * 2 + tb);
     }
-    if (!group_sync(bar, C, p.err)) return;   // the next tree's clear must not overtake these reads
+    for (int tb = 0; tb < 2; ++tb) {
+      const int m = 2 * pr + tb;
+      if (m >= M) continue;
+      if (!rp_wait(ev + RP_EV_INSERT * 2 + tb, target, p.err)) return;
+      compact(m);
+      rp_arrive(ev + RP_EV_COMPACT * 2 + tb);
+    }
+    for (int tb = 0; tb < 2; ++tb) {
+      const int m = 2 * pr + tb;
+      if (m + 2 >= M) continue;
+      if (!rp_wait(ev + RP_EV_COMPACT * 2 + tb, target, p.err)) return;
+      clear(tb);
+      rp_arrive(ev + RP_EV_CLEAR * 2 + tb);
+    }
   }
 }
 
 struct RpLayout {
   uint32_t slots;
-  int log2_slots, groups;
+  int log2_slots, groups, tiles_per_tree;
   int64_t n_pad;
-  size_t off_bars, off_cta, off_tables, off_slot_of, off_fbytes, total;
+  size_t off_events, off_status, off_tables, off_slot_of, total;
 };
 
 bool rp_layout(int64_t num_trees, int64_t n_max, RpLayout& L) {
-  if (num_trees <= 0 || n_max < 0 || n_max >= ((int64_t)1 << 30)) return false;
+  if (num_trees <= 0 || num_trees >= (1 << 21) || n_max < 0 || n_max >= ((int64_t)1 << 30)) return false;
   uint64_t slots = 1024;
   while (slots < 2 * (uint64_t)n_max + 2) slots <<= 1;   // load <= 0.5 in the worst case, about 0.3 for sampled trees
   L.slots = (uint32_t)slots;
   L.log2_slots = 0;
   while ((1ull << L.log2_slots) < slots) ++L.log2_slots;
   L.n_pad = (n_max + RP_ITEMS - 1) / RP_ITEMS * RP_ITEMS + RP_ITEMS;
-  // groups: as many trees in flight as keep tables + slot maps + state bytes + ids inside the L2 budget
-  const size_t per_group = slots * 8 + (size_t)L.n_pad * 13;
+  L.tiles_per_tree = (int)std::max<int64_t>(1, (n_max + RP_TILE - 1) / RP_TILE);
+  // groups: as many trees in flight (two per group) as keep tables + slot maps + ids inside the L2 budget
+  const size_t per_group = 2 * (slots * 8 + (size_t)L.n_pad * 12);
   const char* e = getenv("TCHGEO_RELABEL_GROUPS");
-  int64_t groups = e ? atoi(e) : (int64_t)(((size_t)72 << 20) / std::max<size_t>(per_group, 1));
-  groups = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(groups, num_trees), RP_MAX_GROUPS));
+  int64_t groups = e ? atoi(e) : (int64_t)(((size_t)88 << 20) / std::max<size_t>(per_group, 1));
+  groups = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(groups, (num_trees + 1) / 2), RP_MAX_GROUPS));
   L.groups = (int)groups;
   size_t o = 0;
-  L.off_bars = o; o += rl_align((size_t)RP_MAX_GROUPS * 128);
-  L.off_cta = o; o += rl_align((size_t)RP_MAX_CTAS * 4);
-  L.off_tables = o; o += rl_align((size_t)groups * slots * 8);
-  L.off_slot_of = o; o += rl_align((size_t)groups * L.n_pad * 4);
-  L.off_fbytes = o; o += rl_align((size_t)groups * L.n_pad);
+  L.off_events = o; o += rl_align((size_t)RP_MAX_GROUPS * 128);
+  L.off_status = o; o += rl_align((size_t)groups * 2 * L.tiles_per_tree * 8);
+  L.off_tables = o; o += rl_align((size_t)groups * 2 * slots * 8);
+  L.off_slot_of = o; o += rl_align((size_t)groups * 2 * L.n_pad * 4);
   L.total = o + 256;
   return true;
 }
@@ -630,18 +679,18 @@ cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* le
   p.num_seeds = num_seeds; p.n_max = n_max; p.n_pad = L.n_pad; p.num_trees = (int32_t)num_trees;
   p.groups = std::min(L.groups, resident[dev]);
   p.ctas_per_group = std::min(resident[dev], RP_MAX_CTAS) / p.groups;
+  p.tiles_per_tree = L.tiles_per_tree;
   p.cap_mask = L.slots - 1; p.hash_shift = 32 - L.log2_slots;
   p.tables = (unsigned long long*)(ws + L.off_tables);
   p.slot_of = (uint32_t*)(ws + L.off_slot_of);
-  p.fbytes = (uint8_t*)(ws + L.off_fbytes);
-  p.cta_count = (uint32_t*)(ws + L.off_cta);
-  p.bars = (uint32_t*)(ws + L.off_bars);
+  p.status = (unsigned long long*)(ws + L.off_status);
+  p.events = (uint32_t*)(ws + L.off_events);
   p.err = err;
-  e = cudaMemsetAsync(ws + L.off_bars, 0, (size_t)RP_MAX_GROUPS * 128, stream);
+  // arrival counters and look-back words start at zero (epoch 0 = no tree)
+  e = cudaMemsetAsync(ws + L.off_events, 0, L.off_tables - L.off_events, stream);
   if (e != cudaSuccess) return e;
   void* args[] = {(void*)&p};
-  return cudaLaunchCooperativeKernel(kernel, dim3((unsigned)(p.groups * p.ctas_per_group)),
-                                     dim3(RP_THREADS), args, 0, stream);
+  return cudaLaunchCooperativeKernel(kernel, dim3((unsigned)(p.groups * p.ctas_per_group)), dim3(RP_THREADS), args, 0, stream);
 }
 
 __global__ void rl_set_len_kernel(int64_t* p, int64_t v) { *p = v; }
