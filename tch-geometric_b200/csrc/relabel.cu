@@ -19,7 +19,9 @@
 // three kernels (insert, flag + scan + compact, lookup), whose table accesses and re-reads of the ids are L2 hits; DRAM
 // sees 8 B read + (8 B local + <= 8 B nodes) written per id.  Integer work, HBM/L2-bound: no tensor cores.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "common.cuh"
 
@@ -333,7 +335,9 @@ struct RpParams {
   unsigned long long* status;        // [groups, 2, tiles_per_tree] look-back words, tagged with the tree's epoch
   uint32_t* events;                  // [groups, 32]: monotonic arrival counters [kind * 2 + table] (zero-initialised)
   uint32_t* err;
+  unsigned long long* trace;         // debug (TCHGEO_RELABEL_TRACE): [CTAs, RP_TRACE] globaltimer stamps, or NULL
 };
+constexpr int RP_TRACE = 128;
 
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
   uint32_t v;
@@ -394,6 +398,14 @@ __global__ void __launch_bounds__(RP_THREADS, MINB) rl_persistent_kernel(const R
   const uint32_t mask = p.cap_mask;
   const int M = p.num_trees > g ? (p.num_trees - g + p.groups - 1) / p.groups : 0;  // trees of this group: g, g+G, ...
 
+  int n_stamp = 0;
+  auto stamp = [&]() {   // debug: when did this CTA pass this point (after a wait / after a phase body)
+    if (p.trace && tid == 0 && n_stamp < RP_TRACE) {
+      unsigned long long ns;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns));
+      p.trace[(size_t)blockIdx.x * RP_TRACE + n_stamp++] = ns;
+    }
+  };
   auto tree_of = [&](int m) {
     RpTree t;
     t.b = g + m * p.groups;
@@ -444,23 +456,29 @@ __global__ void __launch_bounds__(RP_THREADS, MINB) rl_persistent_kernel(const R
         h[u] = ((key[u] * 0x9E3779B1u) >> p.hash_shift) & mask;
         old[u] = atomicCAS(tab + h[u], RP_EMPTY, want_of(u));  // the common case (a new id, a free slot): one atomic
       }
+      // collisions are resolved in ROUNDS: every unresolved id of the thread issues its next probe before any result is
+      // looked at, so a thread pays max (not sum) of its ids' probe lengths in L2 round trips
+      bool again = true;
+      while (again) {
+        again = false;
+#pragma unroll
+        for (int u = 0; u < RP_INS; ++u) {
+          if (h[u] == RL_NOSLOT || old[u] == RP_EMPTY) continue;          // resolved (or no id)
+          if ((uint32_t)(old[u] >> 32) == key[u]) {                          // slot holds the same id: the smaller priority wins
+            atomicMin(tab + h[u], want_of(u));
+            old[u] = RP_EMPTY;
+          } else {                                                           // another id: next slot of the id's sequence
+            const uint32_t step = ((key[u] * 0x85EBCA6Bu) >> 7) | 1u;        // odd: visits every slot (double hashing)
+            h[u] = (h[u] + step) & mask;
+            old[u] = atomicCAS(tab + h[u], RP_EMPTY, want_of(u));
+            again = true;
+          }
+        }
+      }
 #pragma unroll
       for (int u = 0; u < RP_INS; ++u) {
         const int64_t i = i0 + u * RP_THREADS + tid;
-        if (i >= t.n) continue;
-        if (h[u] != RL_NOSLOT) {
-          unsigned long long o = old[u];
-          const uint32_t step = ((key[u] * 0x85EBCA6Bu) >> 7) | 1u;  // odd: visits every slot
-          while (o != RP_EMPTY) {                                  // slot taken
-            if ((uint32_t)(o >> 32) == key[u]) {                    // by the same id: the smaller priority wins
-              atomicMin(tab + h[u], want_of(u));
-              break;
-            }
-            h[u] = (h[u] + step) & mask;                            // by another id: next slot of the id's sequence
-            o = atomicCAS(tab + h[u], RP_EMPTY, want_of(u));
-          }
-        }
-        slot_of[i] = h[u];
+        if (i < t.n) slot_of[i] = h[u];
       }
     }
   };
@@ -589,32 +607,40 @@ __global__ void __launch_bounds__(RP_THREADS, MINB) rl_persistent_kernel(const R
   };
 
   // ---- the group's schedule: two trees in flight, every wait separated from its arrival by a phase of the other tree ----
+  stamp();
   clear(0);
   rp_arrive(ev + RP_EV_CLEAR * 2 + 0);
   clear(1);
   rp_arrive(ev + RP_EV_CLEAR * 2 + 1);
+  stamp();
   for (int pr = 0; 2 * pr < M; ++pr) {
     const uint32_t target = C * (uint32_t)(pr + 1);
     for (int tb = 0; tb < 2; ++tb) {
       const int m = 2 * pr + tb;
       if (m >= M) continue;
       if (!rp_wait(ev + RP_EV_CLEAR * 2 + tb, target, p.err)) return;
+      stamp();
       insert(m);
       rp_arrive(ev + RP_EV_INSERT * 2 + tb);
+      stamp();
     }
     for (int tb = 0; tb < 2; ++tb) {
       const int m = 2 * pr + tb;
       if (m >= M) continue;
       if (!rp_wait(ev + RP_EV_INSERT * 2 + tb, target, p.err)) return;
+      stamp();
       compact(m);
       rp_arrive(ev + RP_EV_COMPACT * 2 + tb);
+      stamp();
     }
     for (int tb = 0; tb < 2; ++tb) {
       const int m = 2 * pr + tb;
       if (m + 2 >= M) continue;
       if (!rp_wait(ev + RP_EV_COMPACT * 2 + tb, target, p.err)) return;
+      stamp();
       clear(tb);
       rp_arrive(ev + RP_EV_CLEAR * 2 + tb);
+      stamp();
     }
   }
 }
@@ -686,11 +712,36 @@ cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* le
   p.status = (unsigned long long*)(ws + L.off_status);
   p.events = (uint32_t*)(ws + L.off_events);
   p.err = err;
+  p.trace = nullptr;
   // arrival counters and look-back words start at zero (epoch 0 = no tree)
   e = cudaMemsetAsync(ws + L.off_events, 0, L.off_tables - L.off_events, stream);
   if (e != cudaSuccess) return e;
+  const unsigned grid = (unsigned)(p.groups * p.ctas_per_group);
+  // debug: TCHGEO_RELABEL_TRACE=<file> dumps per-CTA phase time stamps of the first trees of every call (synchronises)
+  static const char* trace_path = getenv("TCHGEO_RELABEL_TRACE");
+  const size_t trace_bytes = (size_t)grid * RP_TRACE * 8;
+  if (trace_path) {
+    e = cudaMalloc(&p.trace, trace_bytes);
+    if (e == cudaSuccess) e = cudaMemsetAsync(p.trace, 0, trace_bytes, stream);
+    if (e != cudaSuccess) return e;
+  }
   void* args[] = {(void*)&p};
-  return cudaLaunchCooperativeKernel(kernel, dim3((unsigned)(p.groups * p.ctas_per_group)), dim3(RP_THREADS), args, 0, stream);
+  e = cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(RP_THREADS), args, 0, stream);
+  if (trace_path && e == cudaSuccess) {
+    std::vector<unsigned long long> h((size_t)grid * RP_TRACE);
+    e = cudaMemcpyAsync(h.data(), p.trace, trace_bytes, cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) {
+      if (FILE* f = fopen(trace_path, "wb")) {
+        const int hdr[4] = {(int)grid, RP_TRACE, p.groups, p.ctas_per_group};
+        fwrite(hdr, sizeof(int), 4, f);
+        fwrite(h.data(), 8, h.size(), f);
+        fclose(f);
+      }
+    }
+    cudaFree(p.trace);
+  }
+  return e;
 }
 
 __global__ void rl_set_len_kernel(int64_t* p, int64_t v) { *p = v; }
