@@ -578,6 +578,81 @@ def run_relabel_only(args):
               "config": workload_config(n, int(idx.numel()), B, args.scale), **out})
 
 
+def run_temporal(args):
+    """the headline configuration with a TemporalFilter (neighbor_sampling.rs:36-77) on the edges:
+    --filter static | relative | dynamic.  Edge timestamps ~ U{0..999}, seed states ~ U{0..999}; windows chosen so that
+    about half (static) / a quarter (relative, dynamic) of the edges pass."""
+    import tch_geometric as thg
+    rank, world, local, device = setup_device()
+    B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
+    ei, n = build_graph(device, args.scale)
+    ptrs, idx, _ = thg.to_csc(ei, n)
+    del ei
+    E = int(idx.numel())
+    g = torch.Generator(device=device)
+    g.manual_seed(777)
+    ts = torch.randint(0, 1000, (E,), generator=g, dtype=torch.int64, device=device)
+    mode = {"static": thg.TEMPORAL_SAMPLE_STATIC, "relative": thg.TEMPORAL_SAMPLE_RELATIVE,
+            "dynamic": thg.TEMPORAL_SAMPLE_DYNAMIC}[args.filter]
+    window = (0, 499) if args.filter == "static" else (0, 249)
+    flt = thg.TemporalEdgeFilter(window, ts, True, mode)
+    plan = thg.HomogenousSampler(ptrs, idx, B, S, FANOUTS, filter=flt)
+    seeds = torch.stack([torch.from_numpy(synth.seed_batches(n, B, S, first_batch=(s * world + rank) * B)) for s in range(W + K)]).to(device)
+    states = torch.randint(0, 1000, (W + K, B, S), generator=g, dtype=torch.int64, device=device)
+    for s in range(W):
+        plan.sample(seeds[s], seed=1000 + s, batch_base=s * B, timed=True, inputs_state=states[s])
+    torch.cuda.synchronize()
+    clocks = ClockSampler(local)
+    clocks.start()
+    hop_ms = np.zeros(len(FANOUTS))
+    edges = nodes = 0
+    deg_sum = 0.0
+    for s in range(W, W + K):
+        res = plan.sample(seeds[s], seed=1000 + s, batch_base=s * B, timed=True, inputs_state=states[s])
+        hop_ms += res.launch_ms
+        edges += int(res.edges_len.sum())
+        lo = res.layer_offsets
+        nodes += int(lo[:, -1, 0].sum())              # frontier nodes of all hops = len(samples) before the last hop
+    # untimed: degrees of the last step's frontier nodes (the timestamps the filter has to look at)
+    pos = torch.arange(int(plan._call.cap_n[0]), device=device)[None, :]
+    f_end = torch.as_tensor(res.layer_offsets[:, -1, 0], device=device)[:, None]
+    ids = res.samples[pos < f_end]
+    deg_sum = float((ptrs[ids + 1] - ptrs[ids]).sum().item()) * K
+    clk = clocks.stop()
+    ms = float(hop_ms.sum())
+    peak, peak_src = measured_peak_gbs()
+    alg = 32.0 * nodes + 48.0 * edges + 8.0 * deg_sum
+    cpu = None
+    if not args.no_cpu:
+        from oracle import oracle as O
+        cores = os.cpu_count() or 1
+        hp, hi, hts = ptrs.cpu().numpy(), idx.cpu().numpy(), ts.cpu().numpy()
+        nb = 8
+        hs, hst = seeds[W, :nb].cpu().numpy(), states[W, :nb].cpu().numpy()
+        t0 = time.perf_counter()
+        tot = 0
+        for b in range(nb):
+            o = O.neighbor_sampling_homogenous(hp, hi, hs[b], FANOUTS, filter=dict(mode=mode, forward=True, window=window, timestamps=hts, inputs_state=hst[b]),
+                                               rng_mode=O.RNG_XOSHIRO, seed=b)
+            tot += o[1].size
+        dt = time.perf_counter() - t0
+        cpu = {"value": tot / dt, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{nb} batches x {S} seeds, one thread like the reference ({dt:.1f} s)"}
+    emit({"metric": f"{METRIC}_temporal_{args.filter}", "value": edges / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": K,
+          "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "int64", "data": "synthetic",
+          "config": {"workload": workload_config(n, E, B, args.scale)["workload"] + f", TemporalFilter {args.filter} "
+                     f"window {window}, forward, edge timestamps and seed states ~ U{{0..999}}",
+                     "l2_policy": "inputs larger than L2; seeds and states differ every step"},
+          "edges_per_step": edges / K, "frontier_nodes_per_step": nodes / K, "frontier_degree_sum_per_step": deg_sum / K,
+          "roofline": {"bound": "hbm", "kernel": "hop_filtered_kernel<UNIFORM>, all hops of the step",
+                       "achieved": alg / (ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s", "frac": alg / (ms * 1e-3) / 1e9 / peak,
+                       "traffic": None, "peak_source": peak_src, "per_hop_ms": [float(x) / K for x in hop_ms],
+                       "byte_model": "32 B per frontier node (id, colptr pair, state) + 48 B per sampled edge (gather, four "
+                                     "outputs, state) + 8 B per timestamp of the frontier's neighbourhoods"},
+          "cpu_baseline": cpu, "e2e": None, "gpu_launches": K * plan.num_launches, "clocks": clk})
+
+
 def run_cpu_baseline(ptrs, idx, n, args, osampler=None):
     cores = os.cpu_count() or 1
     hp, hi = ptrs.cpu().numpy(), idx.cpu().numpy()
@@ -914,13 +989,16 @@ def run_partitioned(args):
     step; --protocol legacy: round 1's count matrix + host read per hop (NCCL all-to-alls or peer stores)."""
     import tch_geometric as thg
     import torch.distributed as dist
-    from tch_geometric.partitioned import DistComm, PartitionedPlan, PartitionedPlanF, SingleComm
+    from tch_geometric.partitioned import DistComm, PartitionedPlan, PartitionedPlanF, PartitionedPlanGroups, SingleComm
     from tch_geometric.sharding import reduce_job
     rank, world, local, device = setup_device()
     part, n, e_total, cols_rank = synth.papers_partition(thg, rank, world, device, args.scale)
     B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
     comm = DistComm() if world > 1 else SingleComm()
-    if args.protocol == "fixed":
+    n_groups = args.groups if args.groups > 0 else (2 if world > 1 else 1)
+    if args.protocol == "fixed" and n_groups > 1:
+        ps = PartitionedPlanGroups(part, B, S, FANOUTS, comm=comm if world > 1 else None, groups=n_groups, slack=args.slack)
+    elif args.protocol == "fixed":
         ps = PartitionedPlanF(part, B, S, FANOUTS, comm=comm if world > 1 else None, world=world, rank=rank, slack=args.slack)
     else:
         ps = PartitionedPlan(part, B, S, FANOUTS, comm=comm, groups=args.groups if args.groups > 0 else None)
@@ -1007,7 +1085,7 @@ def run_partitioned(args):
               "config": {"workload": f"papers100M-shaped synthetic graph (N={n}, E={e_total}; {cols_rank} columns per rank), "
                                      f"CSC range-partitioned over {world} rank(s), fanouts {FANOUTS}, {S} seeds/batch, "
                                      f"{B} batches/step/rank",
-                         "protocol": args.protocol,
+                         "protocol": args.protocol, "pipelined_batch_groups": getattr(ps, "num_groups", 1),
                          "parallelism": "column-range partition; per hop the frontier goes to the owners and the sampled "
                                         "neighbours come back"
                                         + (" as NVLink peer-memory stores into fixed per-pair segments (no host sync, no "
@@ -1036,7 +1114,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned", "negative", "gather", "relabel"],
+    ap.add_argument("--workload", default="sampling", choices=["sampling", "walk", "hetero", "partitioned", "negative", "gather", "relabel", "temporal"],
                     help="sampling = headline (configs[1]); walk = configs[2]; hetero = configs[3]")
     ap.add_argument("--batches", type=int, default=256, help="seed batches per step per GPU")
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (debugging only)")
@@ -1046,8 +1124,11 @@ def main():
     ap.add_argument("--l2-fetch", type=int, default=0, help="set cudaLimitMaxL2FetchGranularity (0 = leave)")
     ap.add_argument("--sampler", default="uniform", choices=["uniform", "replace", "weighted"],
                     help="sampling workload: neighbour sampler (uniform = the headline configuration)")
+    ap.add_argument("--filter", default="static", choices=["static", "relative", "dynamic"],
+                    help="temporal workload: TemporalFilter mode")
     ap.add_argument("--groups", type=int, default=0,
-                    help="partitioned workload: batch groups pipelined on separate streams (0 = default: 1)")
+                    help="partitioned workload: batch groups pipelined on separate streams (0 = default: fixed protocol 2 "
+                         "on several GPUs, else 1)")
     ap.add_argument("--protocol", default="fixed", choices=["fixed", "legacy"],
                     help="partitioned workload: exchange protocol (fixed = device-only fixed segments; legacy = round 1)")
     ap.add_argument("--slack", type=float, default=1.5,
@@ -1070,6 +1151,8 @@ def main():
         run_gather(args)
     elif args.workload == "relabel":
         run_relabel_only(args)
+    elif args.workload == "temporal":
+        run_temporal(args)
     else:
         run_ours(args)
     import torch.distributed as dist

@@ -744,21 +744,21 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
   }
   if (total == 0) return;
 
-  // ---- pass 2: decisions + emission, one warp per node ------------------------------------------
+  // ---- pass 2: decisions, one warp per node; q[s] = position AMONG THE PASSING EDGES chosen for slot s ----------
   const uint32_t pos0 = (uint32_t)(fb + node0);
   const uint32_t batch = p.batch_base + (uint32_t)b;
-  int64_t* o_s = p.src_samples + (int64_t)b * p.src_stride + s_base;
-  int64_t* o_st = p.src_states + (int64_t)b * p.src_stride + s_base;
-  int64_t* o_r = p.rows + (int64_t)b * p.e_stride + e_base;
-  int64_t* o_c = p.cols + (int64_t)b * p.e_stride + e_base;
-  int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
+  uint8_t* s_owner = reinterpret_cast<uint8_t*>(s_slot + p.tile_edges);  // [tile_edges] output edge -> node of the tile
+  constexpr uint32_t RESOLVED = 0x80000000u;
   for (int n = warp; n < nn; n += NWARP) {
     const uint32_t np = s_pass[n], deg = s_deg[n], o = s_off[n];
     const uint32_t c_n = KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE ? (np > 0 ? k : 0u) : min(np, k);
     if (c_n == 0) continue;
     const int64_t start = s_start[n], state = s_state[n];
-    uint32_t* q = s_slot + o;  // q[s] = passing position chosen for slot s
-    for (uint32_t s = lane; s < c_n; s += 32) q[s] = 0u;
+    uint32_t* q = s_slot + o;
+    for (uint32_t s = lane; s < c_n; s += 32) {
+      q[s] = 0u;
+      s_owner[o + s] = (uint8_t)n;
+    }
     __syncwarp();
     if (KIND == TCHGEO_SAMPLER_UNIFORM && np > k) {
       const uint32_t nb = (np - k + 3u) >> 2;
@@ -804,32 +804,41 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
       }
     }
     __syncwarp();
-    // sweep: the passing edge with position `rank` feeds every slot that chose it
+    // select: passing position -> position inside the column.  One sweep over the timestamps; a chunk's ballot mask
+    // tells which passing positions it holds, and the r-th set bit (__fns) is the edge: O(deg/32) per 32 slots instead
+    // of the O(deg * k) match of every passing edge against every slot
     uint32_t rank0 = 0;
-    for (uint32_t base = 0; base < deg; base += 32) {
+    for (uint32_t base = 0; base < deg && rank0 < np; base += 32) {
       const uint32_t item = base + lane;
-      const int64_t ptr = start + item;
-      const int64_t ts = item < deg ? __ldg(p.timestamps + ptr) : 0;
-      const bool ok = item < deg && filter_pass(p, ts, state);
+      const bool ok = item < deg && filter_pass(p, __ldg(p.timestamps + start + item), state);
       const uint32_t m = __ballot_sync(0xffffffffu, ok);
-      if (ok) {
-        const uint32_t rank = rank0 + __popc(m & ((1u << lane) - 1u));
-        int64_t v = 0;
-        bool loaded = false;
-        for (uint32_t s = 0; s < c_n; ++s) {
-          if (q[s] == rank) {
-            if (!loaded) { v = __ldg(p.indices + ptr); loaded = true; }
-            const uint32_t e = o + s;
-            o_s[e] = v;
-            o_st[e] = p.filter_mode == 3 ? ts : state;  // mutate(), :69-76
-            o_r[e] = s_base + e;
-            o_c[e] = fb + node0 + n;
-            o_e[e] = ptr;
-          }
-        }
+      const uint32_t cm = __popc(m);
+      for (uint32_t s = lane; s < c_n; s += 32) {
+        const uint32_t r = q[s];
+        if (!(r & RESOLVED) && r >= rank0 && r < rank0 + cm) q[s] = RESOLVED | (base + __fns(m, 0, (int)(r - rank0) + 1));
       }
-      rank0 += __popc(m);
+      rank0 += cm;
     }
+  }
+  __syncthreads();
+
+  // ---- emission: one thread per output edge, coalesced stores (the layout of neighbor_sampling.rs:210-218) ----------
+  int64_t* o_s = p.src_samples + (int64_t)b * p.src_stride + s_base;
+  int64_t* o_st = p.src_states + (int64_t)b * p.src_stride + s_base;
+  int64_t* o_r = p.rows + (int64_t)b * p.e_stride + e_base;
+  int64_t* o_c = p.cols + (int64_t)b * p.e_stride + e_base;
+  int64_t* o_e = p.eidx + (int64_t)b * p.e_stride + e_base;
+#pragma unroll 1
+  for (uint32_t e = tid; e < total; e += FT_THREADS) {
+    const uint32_t n = s_owner[e];
+    const int64_t ptr = s_start[n] + (int64_t)(s_slot[e] & ~RESOLVED);
+    const int64_t v = p.indices32 ? (int64_t)ld_gather64_i32(p.indices32 + ptr) : ld_gather64_i64(p.indices + ptr);
+    const int64_t st_out = p.filter_mode == 3 ? __ldg(p.timestamps + ptr) : s_state[n];  // mutate(), :69-76
+    st_cs_i64(o_s + e, v);
+    st_cs_i64(o_st + e, st_out);
+    st_cs_i64(o_r + e, s_base + e);
+    st_cs_i64(o_c + e, fb + node0 + n);
+    st_cs_i64(o_e + e, ptr);
   }
 }
 
@@ -1406,7 +1415,7 @@ tchgeo_status enqueue_step(const tchgeo_sampling_args* a, const Plan& pl, uint64
     hp.src_states = a->filter_mode ? a->states[stt] : nullptr;
     cudaError_t e;
     if (a->filter_mode) {
-      const size_t fsmem = (size_t)L.tile_edges * 4 + 16;
+      const size_t fsmem = (size_t)L.tile_edges * 5 + 16;  // chosen positions + owner bytes
       switch (a->sampler_kind) {
         case TCHGEO_SAMPLER_UNIFORM: e = launch_filtered<TCHGEO_SAMPLER_UNIFORM>(hp, grid, fsmem, stream); break;
         case TCHGEO_SAMPLER_UNIFORM_REPLACE: e = launch_filtered<TCHGEO_SAMPLER_UNIFORM_REPLACE>(hp, grid, fsmem, stream); break;

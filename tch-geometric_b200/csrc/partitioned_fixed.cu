@@ -360,8 +360,18 @@ __global__ void __launch_bounds__(SV_THREADS, 10) pf_serve_kernel(const ServePar
       }
   }
   __syncthreads();
+  // the tile's rows are one contiguous run in the requester's segment: 16-byte stores when the run is 16-byte aligned
+  // (NVLink peer stores bypass the L2: every store instruction is a fabric transaction, so wider is cheaper)
   int32_t* dst = p.peer_ans[q] + ((int64_t)p.me * p.seg + r0) * w2;
-  for (uint32_t i = tid; i < (uint32_t)nn * w2; i += NT) dst[i] = s_ans[i];
+  const uint32_t words = (uint32_t)nn * w2;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+    const uint4* s4 = reinterpret_cast<const uint4*>(s_ans);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (uint32_t i = tid; i < (words >> 2); i += NT) d4[i] = s4[i];
+    for (uint32_t i = (words & ~3u) + tid; i < words; i += NT) dst[i] = s_ans[i];
+  } else {
+    for (uint32_t i = tid; i < words; i += NT) dst[i] = s_ans[i];
+  }
 }
 
 // ---- finish: answers -> tree layout, one pass in frontier order ------------------------------------------------------

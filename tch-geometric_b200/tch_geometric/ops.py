@@ -600,16 +600,19 @@ class HomogenousSampler:
     """Reusable plan for repeated batched sampling over one graph (extension; not in the reference).
     Output buffers and workspace are allocated once; `sample(inputs)` enqueues B batches in H launches."""
 
-    def __init__(self, col_ptrs, row_indices, num_batches, seeds_per_batch, num_neighbors, sampler=None, relabel=False):
+    def __init__(self, col_ptrs, row_indices, num_batches, seeds_per_batch, num_neighbors, sampler=None, relabel=False,
+                 filter=None):
         """relabel=True adds the dedup + insertion-order relabel stage to every step (results: SampledBatches.nodes /
-        .local / .nodes_len, `relabeled(b)`); the reference-layout outputs are unchanged."""
+        .local / .nodes_len, `relabeled(b)`); the reference-layout outputs are unchanged.
+        filter: a TemporalEdgeFilter (python.rs:137-168); every `sample` call then takes `inputs_state` [B, S]."""
         dev = col_ptrs.device
         self._inputs = torch.zeros((num_batches, seeds_per_batch), dtype=torch.int64, device=dev)
-        self._call = _homogenous_call(col_ptrs, row_indices, self._inputs, num_neighbors, sampler, None, batched=True,
-                                      relabel=relabel)
+        self._state = torch.zeros_like(self._inputs) if filter is not None else None
+        self._call = _homogenous_call(col_ptrs, row_indices, self._inputs, num_neighbors, sampler,
+                                      (filter, self._state) if filter is not None else None, batched=True, relabel=relabel)
 
     def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0,
-               timed: bool = False) -> SampledBatches:
+               timed: bool = False, inputs_state: Optional[Tensor] = None) -> SampledBatches:
         """inputs: [B, S] i64 on the device or in (pinned) host memory.  With timed=True the result
         carries `launch_ms`, the device duration of each hop kernel (CUDA events on the current stream)."""
         if not isinstance(inputs, Tensor) or inputs.dtype != torch.int64:
@@ -617,6 +620,10 @@ class HomogenousSampler:
         if tuple(inputs.shape) != tuple(self._inputs.shape):
             raise ValueError(f"inputs must have shape {tuple(self._inputs.shape)}")
         self._inputs.copy_(inputs, non_blocking=True)
+        if self._state is not None:
+            if inputs_state is None or tuple(inputs_state.shape) != tuple(self._state.shape):
+                raise N.ReferencePanic("inputs_state must have one entry per input")  # states[i] index panic (quirk Q10)
+            self._state.copy_(inputs_state, non_blocking=True)
         self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base, timed=timed)
         res = SampledBatches(self._call)
         res.launch_ms = getattr(self._call, "launch_ms", None) if timed else None

@@ -615,8 +615,9 @@ def segment_rows(num_batches: int, frontier_cap: int, world: int, slack: float) 
     """rows a (requester, owner) pair owns in a hop whose frontier has at most num_batches * frontier_cap nodes"""
     total = num_batches * frontier_cap
     if world == 1:
-        return max(total, 1)
-    return min(max(int(slack * total / world) + 1024, 1), max(total, 1))
+        return max(total, 1) + (total & 1)
+    rows = min(max(int(slack * total / world) + 1024, 1), max(total, 1))
+    return rows + (rows & 1)      # even: a segment's answer rows then start 16-byte aligned (vector stores)
 
 
 def frontier_caps(seeds_per_batch: int, fanouts: Sequence[int]) -> List[int]:
@@ -689,7 +690,9 @@ class PartitionedPlanF:
 
     def __init__(self, part: ColumnPartition, num_batches: int, seeds_per_batch: int, num_neighbors: Sequence[int],
                  sampler=None, world: Optional[int] = None, rank: Optional[int] = None, comm=None, buffers=None,
-                 edge_bases=None, slack: float = 1.5):
+                 edge_bases=None, slack: float = 1.5, outputs=None, indices32=None):
+        """outputs: optional (samples, rows, cols, edge_index) [B, capacity] tensors to write into (views of a larger
+        plan's buffers); indices32: an int32 replica of part.indices that already exists."""
         self.part = part
         self.fanouts = [int(k) for k in num_neighbors]
         self.kind, _ = _extract_sampler(sampler, hetero=False)
@@ -720,10 +723,16 @@ class PartitionedPlanF:
                 buffers = SegmentBuffers.symmetric(B, self.capF, self.fanouts, comm, dev, self.slack)
         self.buf = buffers
         i64 = dict(dtype=torch.int64, device=dev)
-        self.samples = torch.empty((B, self.cap_n), **i64)
-        self.rows = torch.empty((B, self.cap_e), **i64)
-        self.cols = torch.empty((B, self.cap_e), **i64)
-        self.eidx = torch.empty((B, self.cap_e), **i64)
+        if outputs is not None:
+            self.samples, self.rows, self.cols, self.eidx = outputs
+            for t, c in ((self.samples, self.cap_n), (self.rows, self.cap_e), (self.cols, self.cap_e), (self.eidx, self.cap_e)):
+                if tuple(t.shape) != (B, c) or not t.is_contiguous():
+                    raise ValueError("outputs must be contiguous [num_batches, capacity] tensors")
+        else:
+            self.samples = torch.empty((B, self.cap_n), **i64)
+            self.rows = torch.empty((B, self.cap_e), **i64)
+            self.cols = torch.empty((B, self.cap_e), **i64)
+            self.eidx = torch.empty((B, self.cap_e), **i64)
         self.lens = torch.zeros((2, H + 1, B), **i64)               # [0] node_len, [1] edge_len after h hops
         self.err = torch.zeros(1, dtype=torch.int32, device=dev)
         fmax = max(self.capF, default=0)
@@ -733,8 +742,8 @@ class PartitionedPlanF:
         ws = max((N.lib.tchgeo_partf_workspace_bytes(B, c) for c in self.capF), default=0)
         self.ws = torch.empty(max(int(ws), 1), dtype=torch.uint8, device=dev)
         # int32 replica of this rank's share of row_indices: the serve kernel's random gathers span half the DRAM lines
-        self.indices32 = None
-        if part.indices.numel() and os.environ.get("TCHGEO_INDEX_REPLICA", "1") != "0":
+        self.indices32 = indices32
+        if indices32 is None and part.indices.numel() and os.environ.get("TCHGEO_INDEX_REPLICA", "1") != "0":
             i32 = torch.empty(part.indices.numel(), dtype=torch.int32, device=dev)
             scratch = torch.empty(1, dtype=torch.int32, device=dev)
             with torch.cuda.device(dev):
@@ -852,3 +861,83 @@ def sample_virtual_ranks(plans: List[PartitionedPlanF], inputs: List[Tensor], se
         for p in plans:
             p.finish(h)
     return [p.end() for p in plans]
+
+
+class PartitionedPlanGroups:
+    """PartitionedPlanF over `groups` contiguous ranges of a rank's batches, every range with its own exchange buffers
+    and its own stream: while one group's rows are in flight over NVLink (and its barrier waits for the slowest rank),
+    the other group's kernels run, so the exchange is hidden behind compute instead of being added to it.  Results land
+    in one set of [B, capacity] buffers.  `sample` is collective."""
+
+    def __init__(self, part: ColumnPartition, num_batches: int, seeds_per_batch: int, num_neighbors: Sequence[int],
+                 sampler=None, comm=None, groups: int = 2, slack: float = 1.5, edge_bases=None):
+        dev = part.ptrs.device
+        self.B, self.S, self.device = int(num_batches), int(seeds_per_batch), dev
+        self.fanouts = [int(k) for k in num_neighbors]
+        G = max(1, min(int(groups), self.B))
+        cuts = [self.B * g // G for g in range(G + 1)]
+        caps = frontier_caps(self.S, self.fanouts)
+        cap_e = sum(c * k for c, k in zip(caps, self.fanouts))
+        self.cap_n, self.cap_e = self.S + cap_e, max(cap_e, 1)
+        i64 = dict(dtype=torch.int64, device=dev)
+        self.samples = torch.empty((self.B, self.cap_n), **i64)
+        self.rows = torch.empty((self.B, self.cap_e), **i64)
+        self.cols = torch.empty((self.B, self.cap_e), **i64)
+        self.eidx = torch.empty((self.B, self.cap_e), **i64)
+        if edge_bases is None and comm is not None:
+            edge_bases = comm.all_gather_int(part.edge_base, dev)
+        self.plans, i32 = [], None
+        for g in range(G):
+            b0, b1 = cuts[g], cuts[g + 1]
+            outs = (self.samples[b0:b1], self.rows[b0:b1], self.cols[b0:b1], self.eidx[b0:b1])
+            pl = PartitionedPlanF(part, b1 - b0, self.S, self.fanouts, sampler, comm=comm, slack=slack, outputs=outs,
+                                  indices32=i32, edge_bases=edge_bases)
+            i32 = pl.indices32
+            pl.b0 = b0
+            self.plans.append(pl)
+        with torch.cuda.device(dev):
+            self.streams = [torch.cuda.Stream(device=dev) for _ in self.plans]
+        self.comm, self.world, self.rank = comm, self.plans[0].world, self.plans[0].rank
+        self.num_groups = G
+        self.peer = self.plans[0].buf
+        self.profile = None
+        self.slack = self.plans[0].slack
+
+    @property
+    def stats(self):
+        return {k: sum(p.stats[k] for p in self.plans) for k in self.plans[0].stats}
+
+    def sample(self, inputs: Tensor, seed: Optional[int] = None, batch_base: int = 0) -> PartitionedBatches:
+        if inputs.dim() != 2 or inputs.dtype != torch.int64 or tuple(inputs.shape) != (self.B, self.S):
+            raise ValueError(f"inputs must be an int64 tensor of shape {(self.B, self.S)}")
+        seed = _rng_get() if seed is None else seed
+        marks = [] if self.profile is not None else None
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream(self.device)
+            for pl, st in zip(self.plans, self.streams):
+                st.wait_stream(main)
+                with torch.cuda.stream(st):
+                    pl.begin(inputs[pl.b0:pl.b0 + pl.B], seed, batch_base + pl.b0)
+            # phase-major issue order: both groups' kernels of a phase are queued before anyone reaches a barrier
+            for h in range(len(self.fanouts)):
+                for pl, st in zip(self.plans, self.streams):
+                    with torch.cuda.stream(st):
+                        pl.scatter(h)
+                for pl, st in zip(self.plans, self.streams):
+                    with torch.cuda.stream(st):
+                        pl.buf.barrier()
+                        pl.serve(h)
+                for pl, st in zip(self.plans, self.streams):
+                    with torch.cuda.stream(st):
+                        pl.buf.barrier()
+                        pl.finish(h)
+            outs = []
+            for pl, st in zip(self.plans, self.streams):
+                with torch.cuda.stream(st):
+                    outs.append(pl.end())
+                main.wait_stream(st)
+        if marks is not None:
+            self.profile["calls"] = self.profile.get("calls", 0) + 1
+        node_len = np.concatenate([o._node_len for o in outs], axis=1)
+        edge_len = np.concatenate([o._edge_len for o in outs], axis=1)
+        return PartitionedBatches(self, node_len, edge_len)

@@ -127,3 +127,40 @@ def test_walks_at_scale(thg, products):
     # a 4096-walker slice matches the oracle bit for bit
     o = O.random_walk(hrp, hci, start[:4096].cpu().numpy(), L, 1.0, 0.5, seed=1)
     assert (walks[:4096].cpu().numpy() == o).all()
+
+
+def test_mag_shaped_hetero_batch_bit_exact_vs_oracle(thg):
+    """BASELINE configs[3] at its full shape (ogbn-mag-shaped: paper 736 389 / author 1 134 649 / institution 8 740 /
+    field_of_study 59 965 nodes, 4 relations, 21 M edges), 1024 paper seeds per batch, fanouts [10, 10] per relation:
+    two batches of the batched plan equal the oracle bit for bit (samples per node type, rows / cols / edge_index and
+    layer offsets per relation), and the relabel stage per node type equals the serial map."""
+    dev0 = torch.device("cuda", 0)
+    counts, edges = synth.mag_like(dev0)
+    node_types, edge_types = list(counts), list(edges)
+    cp, ri, hcp, hri = {}, {}, {}, {}
+    for et, ei in edges.items():
+        k = thg.rel_key(et)
+        cp[k], ri[k], _ = thg.to_csc(ei, (counts[et[0]], counts[et[2]]))
+        hcp[k], hri[k] = cp[k].cpu().numpy(), ri[k].cpu().numpy()
+    B, S, H = 3, 1024, 2
+    nn = {thg.rel_key(et): [10, 10] for et in edge_types}
+    rng = np.random.default_rng(77)
+    seeds = np.stack([rng.choice(counts["paper"], S, replace=False) for _ in range(B)])
+    plan = thg.HeterogenousSampler(node_types, edge_types, cp, ri, B, {"paper": S}, nn, H, relabel=True)
+    plan.sample({"paper": torch.from_numpy(seeds).to(dev0)}, seed=2024, batch_base=5)
+    for b in (0, B - 1):
+        want = O.neighbor_sampling_heterogenous(node_types, edge_types, hcp, hri, {"paper": seeds[b]}, nn, H,
+                                                seed=2024, batch=5 + b)
+        got = plan.batch(b)
+        for t in node_types:
+            assert (got[0][t].cpu().numpy() == want[0][t]).all(), t
+        for k in nn:
+            for i in (1, 2, 3):
+                assert (got[i][k].cpu().numpy() == want[i][k]).all(), (k, i)
+            assert [tuple(x) for x in got[4][k]] == [tuple(x) for x in want[4][k]], k
+        assert sum(v.numel() for v in got[1].values()) > 50_000          # a real 2-hop sample, not a degenerate one
+        for t, (nodes, local) in plan.relabeled(b).items():
+            s = got[0][t].cpu().numpy()
+            wn, wl = O.unique_relabel(s, S if t == "paper" else 0)
+            assert (nodes.cpu().numpy() == wn).all() and (local.cpu().numpy() == wl).all(), t
+    thg.clear_caches()

@@ -275,3 +275,23 @@ def test_fixed_segment_protocol_errors(thg, fakedataset):
     with pytest.raises((thg.ReferencePanic, MemoryError)):
         sample_virtual_ranks(plans_with(4.0), bad, 1, [0, B])
     thg.clear_caches()
+
+
+def test_pipelined_groups_equal_replicated(thg, fakedataset):
+    """PartitionedPlanGroups: two batch groups on two streams with their own exchange buffers write into one set of
+    output buffers; the result equals the replicated sampler (single rank: the exchange is local)."""
+    from tch_geometric.partitioned import ColumnPartition, PartitionedPlanGroups
+    ei, n = fakedataset
+    ptrs, idx, _ = thg.to_csc(dev(ei), n)
+    part = ColumnPartition.from_full(ptrs, idx, 0, 1)
+    B, S, fan = 7, 33, [15, 10, 5]
+    inputs = dev(np.random.default_rng(4).integers(0, n, (B, S)))
+    plan = PartitionedPlanGroups(part, B, S, fan, groups=3)
+    for rep in range(2):
+        got = plan.sample(inputs, seed=21 + rep, batch_base=11)
+        want = thg.neighbor_sampling_homogenous_batched(ptrs, idx, inputs, fan, seed=21 + rep, batch_base=11)
+        assert (got.samples_len == want.samples_len).all() and (got.layer_offsets == want.layer_offsets).all()
+        for b in range(B):
+            for g, x in zip(got.batch(b)[:4], want.batch(b)[:4]):
+                assert torch.equal(g, x)
+    thg.clear_caches()

@@ -20,7 +20,7 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 
 import tch_geometric as thg  # noqa: E402
-from tch_geometric.partitioned import DistComm, PartitionedPlan, PartitionedPlanF  # noqa: E402
+from tch_geometric.partitioned import DistComm, PartitionedPlan, PartitionedPlanF, PartitionedPlanGroups  # noqa: E402
 from tools import synth  # noqa: E402
 
 
@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--protocol", default="fixed", choices=["fixed", "legacy"])
     ap.add_argument("--slack", type=float, default=1.5)
+    ap.add_argument("--groups", type=int, default=2, help="fixed protocol: batch groups pipelined on separate streams")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     device = torch.device("cuda", local)
@@ -60,7 +61,9 @@ def main():
     torch.cuda.synchronize()
     t_build = time.time() - t0
     fan, S, B = [15, 10, 5], 1024, args.batches
-    if args.protocol == "fixed":
+    if args.protocol == "fixed" and args.groups > 1:
+        plan = PartitionedPlanGroups(part, B, S, fan, comm=DistComm(), groups=args.groups, slack=args.slack)
+    elif args.protocol == "fixed":
         plan = PartitionedPlanF(part, B, S, fan, comm=DistComm(), slack=args.slack)
     else:
         plan = PartitionedPlan(part, B, S, fan, comm=DistComm())
@@ -91,7 +94,8 @@ def main():
                           "columns_per_rank": cols_rank, "batches_per_rank": B, "steps": args.steps,
                           "edges_compared": int(tot.item()), "rank0_mismatching_steps": mism,
                           "full_csc_bytes_per_rank": int(ptrs.numel() + idx.numel()) * 8, "build_s": round(t_build, 1),
-                          "slack": args.slack if args.protocol == "fixed" else None}), flush=True)
+                          "slack": args.slack if args.protocol == "fixed" else None,
+                          "pipelined_batch_groups": args.groups if args.protocol == "fixed" else None}), flush=True)
     dist.destroy_process_group()
     sys.exit(0 if flag.item() else 1)
 
