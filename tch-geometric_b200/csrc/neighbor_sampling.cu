@@ -618,15 +618,18 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
 // the neighbourhood emits the chosen edges and the new per-sample states.
 // ---------------------------------------------------------------------------------------------
 constexpr int FT_THREADS = 128;
+constexpr int FT_MASKW = 16;  // ballot masks of a node's first 16 chunks (512 edges) are kept in shared memory by pass 1
 
+// STATIC: a fixed window on the timestamp (:59); RELATIVE / DYNAMIC: a window on the distance to the sample's state (:60-65)
+template <bool STATIC>
 __device__ __forceinline__ bool filter_pass(const HopParams& p, int64_t t, int64_t state) {
-  if (p.filter_mode == 1) return p.win_lo <= t && t <= p.win_hi;  // STATIC, :59
-  int64_t d = t - state;                                            // RELATIVE / DYNAMIC, :60-65
+  if (STATIC) return p.win_lo <= t && t <= p.win_hi;
+  int64_t d = t - state;
   if (!p.filter_forward) d = -d;
   return p.win_lo <= d && d <= p.win_hi;
 }
 
-template <int KIND>
+template <int KIND, bool STATIC>
 __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParams p) {
   using BlockScan = cub::BlockScan<uint32_t, FT_THREADS>;
   __shared__ typename BlockScan::TempStorage scan_tmp;
@@ -636,6 +639,7 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
   __shared__ int64_t s_excl;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   uint32_t* s_slot = reinterpret_cast<uint32_t*>(dyn_smem);  // [tile_edges]
+  uint32_t* s_mask = s_slot + p.tile_edges;                  // [FT_THREADS * FT_MASKW] passing-edge masks from pass 1
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NWARP = FT_THREADS / 32;
@@ -677,8 +681,10 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
     }
     for (uint32_t base = 0; base < deg; base += 32) {
       const uint32_t item = base + lane;
-      const bool ok = item < deg && filter_pass(p, __ldg(p.timestamps + start + item), state);
-      npass += __popc(__ballot_sync(0xffffffffu, ok));
+      const bool ok = item < deg && filter_pass<STATIC>(p, __ldg(p.timestamps + start + item), state);
+      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      if (lane == 0 && base < 32u * FT_MASKW) s_mask[n * FT_MASKW + (base >> 5)] = m;  // the select pass reuses it
+      npass += __popc(m);
     }
     if (lane == 0) { s_start[n] = start; s_state[n] = state; s_deg[n] = deg; s_pass[n] = npass; }
   }
@@ -747,7 +753,7 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
   // ---- pass 2: decisions, one warp per node; q[s] = position AMONG THE PASSING EDGES chosen for slot s ----------
   const uint32_t pos0 = (uint32_t)(fb + node0);
   const uint32_t batch = p.batch_base + (uint32_t)b;
-  uint8_t* s_owner = reinterpret_cast<uint8_t*>(s_slot + p.tile_edges);  // [tile_edges] output edge -> node of the tile
+  uint8_t* s_owner = reinterpret_cast<uint8_t*>(s_mask + FT_THREADS * FT_MASKW);  // [tile_edges] output edge -> node of the tile
   constexpr uint32_t RESOLVED = 0x80000000u;
   for (int n = warp; n < nn; n += NWARP) {
     const uint32_t np = s_pass[n], deg = s_deg[n], o = s_off[n];
@@ -769,7 +775,7 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
       uint32_t rank0 = 0;
       for (uint32_t base = 0; base < deg; base += 32) {
         const uint32_t item = base + lane;
-        const bool ok = item < deg && filter_pass(p, __ldg(p.timestamps + start + item), state);
+        const bool ok = item < deg && filter_pass<STATIC>(p, __ldg(p.timestamps + start + item), state);
         const uint32_t m = __ballot_sync(0xffffffffu, ok);
         const uint32_t rank = rank0 + __popc(m & ((1u << lane) - 1u));
         const double w = ok ? __ldg(p.weights + start + item) : 0.0;
@@ -809,9 +815,14 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
     // of the O(deg * k) match of every passing edge against every slot
     uint32_t rank0 = 0;
     for (uint32_t base = 0; base < deg && rank0 < np; base += 32) {
-      const uint32_t item = base + lane;
-      const bool ok = item < deg && filter_pass(p, __ldg(p.timestamps + start + item), state);
-      const uint32_t m = __ballot_sync(0xffffffffu, ok);
+      uint32_t m;
+      if (base < 32u * FT_MASKW) {
+        m = s_mask[n * FT_MASKW + (base >> 5)];   // written by this warp's lane 0 in pass 1 (a barrier lies in between)
+      } else {
+        const uint32_t item = base + lane;
+        const bool ok = item < deg && filter_pass<STATIC>(p, __ldg(p.timestamps + start + item), state);
+        m = __ballot_sync(0xffffffffu, ok);
+      }
       const uint32_t cm = __popc(m);
       for (uint32_t s = lane; s < c_n; s += 32) {
         const uint32_t r = q[s];
@@ -1251,19 +1262,24 @@ cudaError_t launch_hop(const HopParams& hp, int64_t tiles, size_t smem, cudaStre
                       : launch_hop_i<KIND, false>(hp, tiles, smem, stream);
 }
 
-template <int KIND>
-cudaError_t launch_filtered(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
-  static bool configured[64] = {};  // per device: fanouts above ~11 k need more than the default 48 KB
+template <int KIND, bool STATIC>
+cudaError_t launch_filtered_m(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+  static bool configured[64] = {};  // per device: fanouts above ~9 k need more than the default 48 KB
   int dev = 0;
   cudaError_t e = cudaGetDevice(&dev);
   if (e != cudaSuccess) return e;
   if (dev < 0 || dev >= 64 || !configured[dev]) {
-    e = cudaFuncSetAttribute(hop_filtered_kernel<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = cudaFuncSetAttribute(hop_filtered_kernel<KIND, STATIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (dev >= 0 && dev < 64) configured[dev] = true;
   }
-  hop_filtered_kernel<KIND><<<(unsigned)grid, FT_THREADS, smem, stream>>>(hp);
+  hop_filtered_kernel<KIND, STATIC><<<(unsigned)grid, FT_THREADS, smem, stream>>>(hp);
   return cudaGetLastError();
+}
+template <int KIND>
+cudaError_t launch_filtered(const HopParams& hp, int64_t grid, size_t smem, cudaStream_t stream) {
+  return hp.filter_mode == 1 ? launch_filtered_m<KIND, true>(hp, grid, smem, stream)
+                             : launch_filtered_m<KIND, false>(hp, grid, smem, stream);
 }
 
 struct EventList {  // destroyed on every exit path
@@ -1415,7 +1431,7 @@ tchgeo_status enqueue_step(const tchgeo_sampling_args* a, const Plan& pl, uint64
     hp.src_states = a->filter_mode ? a->states[stt] : nullptr;
     cudaError_t e;
     if (a->filter_mode) {
-      const size_t fsmem = (size_t)L.tile_edges * 5 + 16;  // chosen positions + owner bytes
+      const size_t fsmem = (size_t)L.tile_edges * 5 + (size_t)FT_THREADS * FT_MASKW * 4 + 16;  // positions, masks, owners
       switch (a->sampler_kind) {
         case TCHGEO_SAMPLER_UNIFORM: e = launch_filtered<TCHGEO_SAMPLER_UNIFORM>(hp, grid, fsmem, stream); break;
         case TCHGEO_SAMPLER_UNIFORM_REPLACE: e = launch_filtered<TCHGEO_SAMPLER_UNIFORM_REPLACE>(hp, grid, fsmem, stream); break;

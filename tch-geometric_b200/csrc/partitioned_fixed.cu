@@ -128,7 +128,10 @@ struct PutParams {
 };
 
 __global__ void __launch_bounds__(PF_THREADS) pf_put_kernel(const PutParams p) {
-  const int o = blockIdx.y;
+  // peers are visited in a rank-dependent rotation: at any moment the ranks then store into DIFFERENT peers (a
+  // permutation schedule).  With the same order on every rank all of them hit one receiver at a time (incast), which
+  // held the 8-GPU exchange at ~200 GB/s per rank.
+  const int o = (int)((blockIdx.y + (unsigned)p.me + 1u) % (unsigned)p.world);
   unsigned long long n = p.cursor[o];
   if (n > (unsigned long long)p.seg) n = (unsigned long long)p.seg;
   if (blockIdx.x == 0 && threadIdx.x == 0) p.peer_cnt[o][p.me] = (int64_t)n;
@@ -201,7 +204,9 @@ __global__ void __launch_bounds__(SV_THREADS, 10) pf_serve_kernel(const ServePar
   int32_t* s_ans = reinterpret_cast<int32_t*>(s_slot + (size_t)NT * k);  // [NT * 2k] the tile's answer rows
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int q = blockIdx.y;                              // requester
+  // requester whose segment this CTA serves; rotated by the rank so that the ranks' answer stores go to different
+  // peers at any moment (see pf_put_kernel)
+  const int q = (int)((blockIdx.y + (unsigned)p.me + 1u) % (unsigned)p.world);
   int64_t n_req = p.cnt_in[q];
   if (n_req > p.seg) n_req = p.seg;
   const int64_t r0 = (int64_t)blockIdx.x * NT;
