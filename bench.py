@@ -941,8 +941,41 @@ def measure_hetero(args, rank, world, local, device, K, W, with_cpu):
         alg_bytes += 24.0 * (f_h0.sum() + f_h1.sum()) + 40.0 * (e_h0.sum() + e_h1.sum())
     e1.record()
     torch.cuda.synchronize()
+    serial_ms = e0.elapsed_time(e1)
+    # value: the same K steps with two plans on two streams (sample_async / result): the host enqueues step s+1 before it
+    # waits for the lengths of step s
+    plans = [plan, thg.HeterogenousSampler(node_types, edge_types, cp, ri, B, {"paper": S}, nn, H)]
+    streams = [torch.cuda.Stream(device), torch.cuda.Stream(device)]
+
+    def pipelined(first, count):
+        total, pending = 0, []
+        for i, s in enumerate(range(first, first + count)):
+            j = i & 1
+            if len(pending) == 2:
+                total += int(plans[pending.pop(0)].result().edges_len.sum())
+            with torch.cuda.stream(streams[j]):
+                plans[j].sample_async({"paper": all_seeds[s]}, seed=1000 + s, batch_base=(s * world + rank) * B)
+            pending.append(j)
+        while pending:
+            total += int(plans[pending.pop(0)].result().edges_len.sum())
+        return total
+
+    pipelined(0, min(W, len(all_seeds)))
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    cur = torch.cuda.current_stream(device)
+    e0.record(cur)
+    for st in streams:
+        st.wait_stream(cur)
+    edges_p = pipelined(W, K)
+    for st in streams:
+        cur.wait_stream(st)
+    e1.record(cur)
+    torch.cuda.synchronize()
     clk = clocks.stop()
     ms = e0.elapsed_time(e1)
+    assert edges_p == edges_n
     ms, edges_all = reduce_job(ms, float(edges_n), device)
     cpu = None
     if rank == 0 and world == 1 and with_cpu:
@@ -965,7 +998,7 @@ def measure_hetero(args, rank, world, local, device, K, W, with_cpu):
         cpu = {"value": tot / dt, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{nb} batches x {S} paper seeds on {cores} threads ({dt:.1f} s)"}
     launches = plan.num_launches
-    del plan
+    del plan, plans
     return ({"metric": "sampled_edges_per_sec_hetero_mag_10_10", "value": edges_all / (ms * 1e-3), "unit": UNIT,
               "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
               "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",
@@ -973,6 +1006,7 @@ def measure_hetero(args, rank, world, local, device, K, W, with_cpu):
                                      f"neighbor_sampling_heterogenous fanouts [10,10] per relation, {S} paper seeds/batch, "
                                      f"{B} batches/step", "parallelism": "seed batches sharded, CSCs replicated"},
               "launch_ms": [float(x) / K for x in launch_ms], "edges_per_step_per_gpu": edges_n / K,
+              "serial_ms_per_step": serial_ms / K,
               "roofline": {"bound": "hbm", "kernel": "hop_kernel<UNIFORM>, all launches of the step (one per hop and relation "
                            "with a non-empty frontier)", "achieved": alg_bytes / (float(launch_ms.sum()) * 1e-3) / 1e9,
                            "peak": measured_peak_gbs()[0], "unit": "GB/s",
@@ -995,7 +1029,7 @@ def run_partitioned(args):
     part, n, e_total, cols_rank = synth.papers_partition(thg, rank, world, device, args.scale)
     B, S, K, W = args.batches, SEEDS_PER_BATCH, args.steps, args.warmup
     comm = DistComm() if world > 1 else SingleComm()
-    n_groups = args.groups if args.groups > 0 else (2 if world > 1 else 1)
+    n_groups = args.groups if args.groups > 0 else 1   # measured on 8 B200s: 1 group 3.50 ms, 2 groups 4.23, 4 groups 5.13
     if args.protocol == "fixed" and n_groups > 1:
         ps = PartitionedPlanGroups(part, B, S, FANOUTS, comm=comm if world > 1 else None, groups=n_groups, slack=args.slack)
     elif args.protocol == "fixed":
@@ -1127,8 +1161,7 @@ def main():
     ap.add_argument("--filter", default="static", choices=["static", "relative", "dynamic"],
                     help="temporal workload: TemporalFilter mode")
     ap.add_argument("--groups", type=int, default=0,
-                    help="partitioned workload: batch groups pipelined on separate streams (0 = default: fixed protocol 2 "
-                         "on several GPUs, else 1)")
+                    help="partitioned workload: batch groups pipelined on separate streams (0 = default: 1)")
     ap.add_argument("--protocol", default="fixed", choices=["fixed", "legacy"],
                     help="partitioned workload: exchange protocol (fixed = device-only fixed segments; legacy = round 1)")
     ap.add_argument("--slack", type=float, default=1.5,

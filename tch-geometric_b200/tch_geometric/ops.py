@@ -800,6 +800,20 @@ class HeterogenousSampler:
         self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base, timed=timed)
         return self
 
+    def sample_async(self, inputs: Dict[str, Tensor], seed: Optional[int] = None, batch_base: int = 0):
+        """Enqueue `sample(inputs)` on the current stream without waiting; `result()` waits for that step only.  Two plans
+        on two streams keep the device busy while the host reads the previous step's lengths."""
+        for t, buf in self._proto.items():
+            if tuple(inputs[t].shape) != tuple(buf.shape):
+                raise ValueError(f"inputs[{t}] must have shape {tuple(buf.shape)}")
+            buf.copy_(inputs[t], non_blocking=True)
+        self._call.run(seed=_rng_get() if seed is None else seed, batch_base=batch_base, collect=False)
+        return self
+
+    def result(self):
+        self._call.collect()
+        return self
+
     @property
     def launch_ms(self):
         return getattr(self._call, "launch_ms", None)

@@ -47,7 +47,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--protocol", default="fixed", choices=["fixed", "legacy"])
     ap.add_argument("--slack", type=float, default=1.5)
-    ap.add_argument("--groups", type=int, default=2, help="fixed protocol: batch groups pipelined on separate streams")
+    ap.add_argument("--groups", type=int, default=1, help="fixed protocol: batch groups pipelined on separate streams")
     args = ap.parse_args()
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     device = torch.device("cuda", local)
