@@ -220,8 +220,11 @@ static tchgeo_status serve_launch(const int64_t* ptrs_local, const int64_t* indi
   TCHGEO_REQUIRE(n >= 0 && fanout >= 0 && fanout <= SV_MAX_TILE_SLOTS && ncols_local >= 0, "bad serve argument");
   TCHGEO_REQUIRE(sampler_kind >= 0 && sampler_kind <= 2 && err != nullptr, "bad serve argument");
   TCHGEO_REQUIRE(sampler_kind != TCHGEO_SAMPLER_WEIGHTED || weights_local != nullptr, "weighted serve without weights");
-  if (n == 0 || fanout == 0) return TCHGEO_OK;
-  TCHGEO_REQUIRE(ptrs_local && req_ids && req_meta && (out32 || peer_world > 0 || (out_ids && out_ptrs)), "NULL pointer");
+  // fanout 0: sampling with replacement yields nothing; the other samplers panic in the reference as soon as a
+  // requested column is not empty (gen_range(0..0), src/utils/sampling.rs:19), which the kernel reports
+  if (n == 0 || (fanout == 0 && sampler_kind == TCHGEO_SAMPLER_UNIFORM_REPLACE)) return TCHGEO_OK;
+  TCHGEO_REQUIRE(ptrs_local && req_ids && req_meta && (fanout == 0 || out32 || peer_world > 0 || (out_ids && out_ptrs)),
+                 "NULL pointer");
   ServeParams sp;
   sp.peer_world = peer_world;
   if (peer_world > 0) {
@@ -243,7 +246,7 @@ static tchgeo_status serve_launch(const int64_t* ptrs_local, const int64_t* indi
   sp.err = err;
   sp.col_begin = col_begin; sp.ncols = ncols_local; sp.edge_base = edge_base; sp.n = n;
   sp.fanout = (int32_t)fanout;
-  sp.tile_reqs = (int32_t)std::min<int64_t>(SV_THREADS, std::max<int64_t>(1, SV_MAX_TILE_SLOTS / fanout));
+  sp.tile_reqs = (int32_t)std::min<int64_t>(SV_THREADS, std::max<int64_t>(1, SV_MAX_TILE_SLOTS / std::max<int64_t>(fanout, 1)));
   sp.key0 = (uint32_t)seed; sp.key1 = (uint32_t)(seed >> 32); sp.rel = rel;
   const int64_t grid = (n + sp.tile_reqs - 1) / sp.tile_reqs;
   TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many requests for one launch");
@@ -670,6 +673,9 @@ extern "C" tchgeo_status tchgeo_part_finish_hop(const int64_t* req, const int32_
   TCHGEO_REQUIRE(part_ws_layout(num_batches, frontier_cap, W), "frontier too large for one call");
   TCHGEO_REQUIRE(workspace && workspace_bytes >= W.total, "workspace too small: need %zu bytes", W.total);
   TCHGEO_REQUIRE(frontier_cap * fanout < ((int64_t)1 << 31), "frontier_cap * fanout must stay below 2^31");
+  // the per-node answer counts of ALL batches are scanned together in int32
+  TCHGEO_REQUIRE(num_batches * frontier_cap * fanout < ((int64_t)1 << 31),
+                 "num_batches * frontier_cap * fanout must stay below 2^31: use fewer batches per call");
   TCHGEO_REQUIRE(num_requests == 0 || (req && ans), "NULL pointer");
   TCHGEO_REQUIRE(samples && rows && cols && edge_index, "NULL pointer");
   const int64_t n = num_batches * frontier_cap + 1;

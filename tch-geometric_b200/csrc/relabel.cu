@@ -655,7 +655,11 @@ struct RpLayout {
 bool rp_layout(int64_t num_trees, int64_t n_max, RpLayout& L) {
   if (num_trees <= 0 || num_trees >= (1 << 21) || n_max < 0 || n_max >= ((int64_t)1 << 30)) return false;
   uint64_t slots = 1024;
-  while (slots < 2 * (uint64_t)n_max + 2) slots <<= 1;   // load <= 0.5 in the worst case, about 0.3 for sampled trees
+  // TCHGEO_RELABEL_DENSE=1: tables of n_max + 2 slots rounded up (load up to ~0.9, about 0.57 for sampled trees) instead
+  // of 2 n_max + 2 (<= 0.5 / ~0.3): half the L2 footprint per tree, so twice the trees in flight, against longer probes
+  const char* dense = getenv("TCHGEO_RELABEL_DENSE");
+  const uint64_t want = (dense && atoi(dense) != 0) ? (uint64_t)n_max + 2 : 2 * (uint64_t)n_max + 2;
+  while (slots < want) slots <<= 1;
   L.slots = (uint32_t)slots;
   L.log2_slots = 0;
   while ((1ull << L.log2_slots) < slots) ++L.log2_slots;
@@ -744,6 +748,403 @@ cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* le
   return e;
 }
 
+// =================================================================================================
+// Bucketed form (default for ids < 2^32-1): no global hash table at all.
+// A tree's ids are split by a hash into NB buckets of ~3 k ids (pairs (id, position), counting sort: count, offsets,
+// scatter), and every bucket is resolved by ONE CTA in a SHARED-MEMORY hash table (8192 x 8 B; shared-memory atomics cost
+// a few cycles, against the ~50 G/s the L2 sustains for global atomicCAS, which is what held the persistent form at
+// 7 ms per step): per id the position its map entry points at ("winner": the last seed carrying the id, else the first
+// occurrence).  Positions are then walked once in order -- flags, block scan, decoupled look-back per tree, node list,
+// ranks -- and a last pass gives later occurrences the rank of their winner.  Everything is streaming traffic:
+//   count 8 B | scatter 8 + 8 B | resolve 8 + 4 B | compact 12 + ~26 B | lookup 4 + ~1 B      per id,
+// about 80 B against the 24 B of the byte model, all of it coalesced except the 4-byte winner scatter (merged in the L2).
+// A bucket with more distinct ids than its table holds (hash skew; ~2x headroom over the mean at the worst-case tree
+// size) raises TCHGEO_ERR_CAPACITY rather than a wrong answer; TCHGEO_RELABEL_PERSISTENT=1 selects the global-table form.
+// =================================================================================================
+constexpr int BK_THREADS = 512;
+constexpr int BK_ITEMS = 8;
+constexpr int BK_TILE = BK_THREADS * BK_ITEMS;    // ids per CTA in the count / scatter kernels
+constexpr int BK_MAX_BUCKETS = 4096;              // shared-memory histogram
+constexpr int BK_TABLE = 8192;                    // slots of a bucket's shared-memory table
+constexpr int BK_TARGET = 3072;                   // ids per bucket the bucket count is chosen for (worst-case tree)
+constexpr uint32_t BK_NONE = 0xFFFFFFFFu;
+
+struct BkParams {
+  const int64_t* samples;
+  int64_t stride;
+  const int64_t* lens;
+  int64_t* nodes;
+  int64_t* local;
+  int64_t* nodes_len;
+  int64_t num_seeds, n_max;
+  int32_t num_trees, nb, log2_nb, tiles_per_tree;   // nb buckets per tree; tiles of BK_TILE (count/scatter) positions
+  uint32_t* counts;    // [trees, nb] ids per bucket
+  uint32_t* offs;      // [trees, nb] exclusive offsets inside the tree's pair region
+  uint32_t* cursor;    // [trees, nb] scatter cursors (zero)
+  uint2* pairs;        // [trees, n_max] (id, position) grouped by bucket
+  uint32_t* win;       // [trees, n_max] position the map entry of samples[i] points at (BK_NONE: id out of range)
+  uint32_t* rank_of;   // [trees, n_max] rank of a first occurrence
+  uint64_t* status;    // [trees, ctiles] look-back words of the compact kernel (zero)
+  uint32_t* ticket;    // (zero)
+  int32_t ctiles;      // tiles of RL_TILE positions per tree
+  uint32_t* err;
+};
+
+__device__ __forceinline__ int64_t bk_len(const BkParams& p, int b) {
+  int64_t n = p.lens[b];
+  if (n > p.n_max) n = p.n_max;
+  return n < 0 ? 0 : n;
+}
+__device__ __forceinline__ uint32_t bk_bucket(uint32_t key, int log2_nb) {
+  return log2_nb ? (key * 0x9E3779B1u) >> (32 - log2_nb) : 0u;
+}
+
+// ---- count: ids per (tree, bucket) ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS) bk_count_kernel(const BkParams p) {
+  __shared__ uint32_t s_hist[BK_MAX_BUCKETS];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int64_t n = bk_len(p, b);
+  const int64_t i0 = (int64_t)blockIdx.x * BK_TILE;
+  if (i0 >= n) return;
+  for (int j = tid; j < p.nb; j += BK_THREADS) s_hist[j] = 0u;
+  __syncthreads();
+  const int64_t* src = p.samples + (int64_t)b * p.stride;
+#pragma unroll
+  for (int u = 0; u < BK_ITEMS; ++u) {
+    const int64_t i = i0 + u * BK_THREADS + tid;
+    if (i >= n) continue;
+    const int64_t k64 = __ldg(src + i);
+    if ((uint64_t)k64 >= 0xFFFFFFFFull) atomicOr(p.err, DEV_ERR_INDEX);
+    else atomicAdd(&s_hist[bk_bucket((uint32_t)k64, p.log2_nb)], 1u);
+  }
+  __syncthreads();
+  for (int j = tid; j < p.nb; j += BK_THREADS)
+    if (s_hist[j]) atomicAdd(p.counts + (size_t)b * p.nb + j, s_hist[j]);
+}
+
+// ---- offsets: exclusive scan of every tree's bucket counts (one CTA per tree; nb <= 4096) ----------------------------
+__global__ void __launch_bounds__(256) bk_offsets_kernel(const BkParams p) {
+  __shared__ uint32_t s_wtot[8];
+  __shared__ uint32_t s_carry;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_carry = 0u;
+  __syncthreads();
+  for (int j0 = 0; j0 < p.nb; j0 += 256) {
+    const int j = j0 + tid;
+    const uint32_t v = j < p.nb ? p.counts[(size_t)b * p.nb + j] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += up;
+    }
+    if (lane == 31) s_wtot[warp] = incl;
+    __syncthreads();
+    uint32_t before = s_carry, total = 0;
+    for (int w = 0; w < 8; ++w) {
+      if (w < warp) before += s_wtot[w];
+      total += s_wtot[w];
+    }
+    if (j < p.nb) p.offs[(size_t)b * p.nb + j] = before + incl - v;
+    __syncthreads();
+    if (tid == 0) s_carry += total;
+    __syncthreads();
+  }
+}
+
+// ---- scatter: (id, position) pairs grouped by bucket ---------------------------------------------------------------
+__global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p) {
+  __shared__ uint32_t s_hist[BK_MAX_BUCKETS];   // per-bucket count of the tile, then the tile's base in the bucket
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const int64_t n = bk_len(p, b);
+  const int64_t i0 = (int64_t)blockIdx.x * BK_TILE;
+  if (i0 >= n) return;
+  for (int j = tid; j < p.nb; j += BK_THREADS) s_hist[j] = 0u;
+  __syncthreads();
+  const int64_t* src = p.samples + (int64_t)b * p.stride;
+  uint32_t key[BK_ITEMS], rnk[BK_ITEMS];
+  bool ok[BK_ITEMS];
+#pragma unroll
+  for (int u = 0; u < BK_ITEMS; ++u) {
+    const int64_t i = i0 + u * BK_THREADS + tid;
+    ok[u] = false;
+    key[u] = 0u; rnk[u] = 0u;
+    if (i >= n) continue;
+    const int64_t k64 = __ldg(src + i);
+    if ((uint64_t)k64 >= 0xFFFFFFFFull) {
+      p.win[(size_t)b * p.n_max + i] = BK_NONE;   // reported by the count kernel
+      continue;
+    }
+    ok[u] = true;
+    key[u] = (uint32_t)k64;
+    rnk[u] = atomicAdd(&s_hist[bk_bucket(key[u], p.log2_nb)], 1u);   // rank inside the tile's share of the bucket
+  }
+  __syncthreads();
+  for (int j = tid; j < p.nb; j += BK_THREADS) {
+    const uint32_t c = s_hist[j];
+    s_hist[j] = p.offs[(size_t)b * p.nb + j] + (c ? atomicAdd(p.cursor + (size_t)b * p.nb + j, c) : 0u);
+  }
+  __syncthreads();
+  uint2* dst = p.pairs + (size_t)b * p.n_max;
+#pragma unroll
+  for (int u = 0; u < BK_ITEMS; ++u) {
+    if (!ok[u]) continue;
+    const int64_t i = i0 + u * BK_THREADS + tid;
+    dst[s_hist[bk_bucket(key[u], p.log2_nb)] + rnk[u]] = make_uint2(key[u], (uint32_t)i);
+  }
+}
+
+// ---- resolve: one CTA per (tree, bucket); the bucket's ids in a shared-memory table ----------------------------------
+__global__ void __launch_bounds__(256) bk_resolve_kernel(const BkParams p) {
+  extern __shared__ __align__(16) unsigned long long s_tab[];   // [BK_TABLE] (64 KB: dynamic, opt-in)
+  __shared__ uint32_t s_distinct;
+  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const uint32_t cnt = p.counts[(size_t)b * p.nb + j];
+  if (cnt == 0) return;
+  for (int q = tid; q < BK_TABLE; q += 256) s_tab[q] = ~0ull;
+  if (tid == 0) s_distinct = 0u;
+  __syncthreads();
+  const uint2* pr = p.pairs + (size_t)b * p.n_max + p.offs[(size_t)b * p.nb + j];
+  const uint32_t S = (uint32_t)p.num_seeds;
+  constexpr uint32_t MASK = BK_TABLE - 1;
+  bool overflow = false;
+  for (uint32_t q = tid; q < cnt; q += 256) {
+    const uint2 e = pr[q];
+    const uint32_t prio = e.y < S ? S - 1u - e.y : e.y;
+    const unsigned long long want = ((unsigned long long)e.x << 32) | prio;
+    uint32_t h = (e.x * 0x85EBCA6Bu) >> (32 - 13);
+    const uint32_t step = ((e.x * 0xC2B2AE35u) >> 9) | 1u;
+    for (int tries = 0;; ++tries) {
+      const unsigned long long old = atomicCAS(&s_tab[h], ~0ull, want);
+      if (old == ~0ull) {
+        if (atomicAdd(&s_distinct, 1u) >= (uint32_t)(BK_TABLE - BK_TABLE / 8)) overflow = true;  // keep probes finite
+        break;
+      }
+      if ((uint32_t)(old >> 32) == e.x) {
+        atomicMin(&s_tab[h], want);
+        break;
+      }
+      h = (h + step) & MASK;
+      if (tries > BK_TABLE) { overflow = true; break; }
+    }
+    if (overflow) break;
+  }
+  if (__syncthreads_or(overflow)) {
+    if (tid == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
+    return;
+  }
+  uint32_t* win = p.win + (size_t)b * p.n_max;
+  for (uint32_t q = tid; q < cnt; q += 256) {
+    const uint2 e = pr[q];
+    uint32_t h = (e.x * 0x85EBCA6Bu) >> (32 - 13);
+    const uint32_t step = ((e.x * 0xC2B2AE35u) >> 9) | 1u;
+    unsigned long long v = s_tab[h];
+    while ((uint32_t)(v >> 32) != e.x) {
+      h = (h + step) & MASK;
+      v = s_tab[h];
+    }
+    const uint32_t prio = (uint32_t)v;
+    win[e.y] = prio < S ? S - 1u - prio : prio;   // the last seed carrying the id (:26), else its first occurrence
+  }
+}
+
+// ---- compact: flags, scan in position order (decoupled look-back per tree), node list, ranks, local ids --------------
+__global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p) {
+  __shared__ uint32_t s_wtot[RL_THREADS / 32];
+  __shared__ uint32_t s_tile;
+  __shared__ int64_t s_excl;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);   // tiles in start order, tree-major
+  __syncthreads();
+  const int b = (int)(s_tile / (uint32_t)p.ctiles), t = (int)(s_tile - (uint32_t)b * (uint32_t)p.ctiles);
+  const int64_t n = bk_len(p, b);
+  const int64_t i0 = (int64_t)t * RL_TILE;
+  if (i0 >= n && t > 0) return;
+  const int64_t* src = p.samples + (int64_t)b * p.stride;
+  const uint32_t* win = p.win + (size_t)b * p.n_max;
+  uint32_t* rank_of = p.rank_of + (size_t)b * p.n_max;
+  int64_t* local = p.local + (int64_t)b * p.stride;
+  const int64_t S = p.num_seeds;
+  const int64_t ibase = i0 + (int64_t)tid * RL_ITEMS;
+  uint32_t w[RL_ITEMS];
+  uint32_t node = 0;
+#pragma unroll
+  for (int u = 0; u < RL_ITEMS; ++u) w[u] = ibase + u < n ? win[ibase + u] : BK_NONE;
+#pragma unroll
+  for (int u = 0; u < RL_ITEMS; ++u) {
+    const int64_t i = ibase + u;
+    if (i >= n) continue;
+    if (i < S) {                                   // every seed is kept (:25) and maps to the last seed with its id (:26)
+      node |= 1u << u;
+      st_cs_i64(local + i, w[u] == BK_NONE ? -1 : (int64_t)w[u]);
+    } else if (w[u] == BK_NONE) {
+      local[i] = -1;
+    } else if (w[u] < (uint32_t)S) {
+      st_cs_i64(local + i, (int64_t)w[u]);          // a seed carries this id
+    } else if (w[u] == (uint32_t)i) {
+      node |= 1u << u;                              // first occurrence of an id no seed carries (:36-39)
+    }                                               // else: a later occurrence, bk_lookup_kernel
+  }
+  const uint32_t cnt = __popc(node);
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_wtot[warp] = incl;
+  __syncthreads();
+  uint32_t excl = incl - cnt, total = 0;
+#pragma unroll
+  for (int k = 0; k < RL_THREADS / 32; ++k) {
+    const uint32_t v = s_wtot[k];
+    if (k < warp) excl += v;
+    total += v;
+  }
+  uint64_t* st = p.status + (size_t)b * p.ctiles;
+  if (tid == 0) st_relaxed_u64(st + t, (t == 0 ? 2ull << 62 : 1ull << 62) | (uint64_t)total);
+  if (warp == 0) {
+    int64_t before = 0;
+    if (t > 0) {
+      int j = t - 1;
+      uint32_t spins = 0;
+      while (true) {
+        const int idx = j - lane;
+        const uint64_t v = idx >= 0 ? ld_relaxed_u64(st + idx) : 2ull << 62;
+        const uint32_t flag = (uint32_t)(v >> 62);
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+        const uint32_t inval_mask = __ballot_sync(0xffffffffu, flag == 0u);
+        const int first_incl = incl_mask ? __ffs(incl_mask) - 1 : 32;
+        const int first_inval = inval_mask ? __ffs(inval_mask) - 1 : 32;
+        if (first_inval < first_incl) {
+          if (++spins > (1u << 24)) {
+            if (lane == 0) atomicOr(p.err, DEV_ERR_WATCHDOG);
+            break;
+          }
+          __nanosleep(32);
+          continue;
+        }
+        int64_t val = lane <= first_incl ? (int64_t)(v & ((1ull << 62) - 1)) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        before += val;
+        if (first_incl < 32) break;
+        j -= 32;
+      }
+      if (lane == 0) st_relaxed_u64(st + t, (2ull << 62) | (uint64_t)(before + total));
+    }
+    if (lane == 0) s_excl = before;
+  }
+  __syncthreads();
+  const int64_t tile_excl = s_excl;
+  if (tid == 0 && i0 + RL_TILE >= n) p.nodes_len[b] = tile_excl + total;
+  int64_t* nodes = p.nodes + (int64_t)b * p.stride;
+  uint32_t r = (uint32_t)tile_excl + excl;
+#pragma unroll
+  for (int u = 0; u < RL_ITEMS; ++u) {
+    if (!((node >> u) & 1u)) continue;
+    const int64_t i = ibase + u;
+    st_cs_i64(nodes + r, __ldg(src + i));
+    if (i >= S) {
+      st_cs_i64(local + i, (int64_t)r);
+      rank_of[i] = r;
+    }
+    ++r;
+  }
+}
+
+// ---- lookup: later occurrences of a non-seed id take the rank of its first occurrence -------------------------------
+__global__ void __launch_bounds__(RL_THREADS) bk_lookup_kernel(const BkParams p) {
+  const int b = blockIdx.y;
+  const int64_t n = bk_len(p, b);
+  const int64_t i0 = (int64_t)blockIdx.x * RL_TILE;
+  if (i0 >= n) return;
+  const uint32_t* win = p.win + (size_t)b * p.n_max;
+  const uint32_t* rank_of = p.rank_of + (size_t)b * p.n_max;
+  int64_t* local = p.local + (int64_t)b * p.stride;
+  const uint32_t S = (uint32_t)p.num_seeds;
+  uint32_t w[RL_ITEMS];
+#pragma unroll
+  for (int u = 0; u < RL_ITEMS; ++u) {
+    const int64_t i = i0 + u * RL_THREADS + threadIdx.x;
+    w[u] = (i < n && i >= (int64_t)S) ? win[i] : BK_NONE;
+  }
+#pragma unroll
+  for (int u = 0; u < RL_ITEMS; ++u) {
+    const int64_t i = i0 + u * RL_THREADS + threadIdx.x;
+    if (w[u] != BK_NONE && w[u] >= S && w[u] != (uint32_t)i) st_cs_i64(local + i, (int64_t)rank_of[w[u]]);
+  }
+}
+
+struct BkLayout {
+  int nb, log2_nb, tiles_per_tree, ctiles;
+  size_t off_zero, zero_bytes;   // counts | cursor | status | ticket: one memset
+  size_t off_counts, off_cursor, off_status, off_ticket, off_offs, off_pairs, off_win, off_rank, total;
+};
+
+bool bk_layout(int64_t num_trees, int64_t n_max, BkLayout& L) {
+  if (num_trees <= 0 || num_trees > 65535 || n_max < 0 || n_max >= ((int64_t)1 << 31)) return false;
+  int nb = 1, lg = 0;
+  while ((int64_t)nb * BK_TARGET < n_max) { nb <<= 1; ++lg; }
+  if (nb > BK_MAX_BUCKETS) return false;        // trees beyond ~12 M ids: the global-table form
+  L.nb = nb; L.log2_nb = lg;
+  L.tiles_per_tree = (int)std::max<int64_t>(1, (n_max + BK_TILE - 1) / BK_TILE);
+  L.ctiles = (int)std::max<int64_t>(1, (n_max + RL_TILE - 1) / RL_TILE);
+  if ((int64_t)L.ctiles * num_trees >= ((int64_t)1 << 31)) return false;
+  const size_t tb = (size_t)num_trees * nb * 4, nn = (size_t)num_trees * (size_t)std::max<int64_t>(n_max, 1);
+  size_t o = 0;
+  L.off_zero = o;
+  L.off_counts = o; o += rl_align(tb);
+  L.off_cursor = o; o += rl_align(tb);
+  L.off_status = o; o += rl_align((size_t)num_trees * L.ctiles * 8);
+  L.off_ticket = o; o += 256;
+  L.zero_bytes = o - L.off_zero;
+  L.off_offs = o; o += rl_align(tb);
+  L.off_pairs = o; o += rl_align(nn * 8);
+  L.off_win = o; o += rl_align(nn * 4);
+  L.off_rank = o; o += rl_align(nn * 4);
+  L.total = o + 256;
+  return true;
+}
+
+tchgeo_status bk_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees, int64_t num_seeds,
+                         int64_t n_max, int64_t* nodes, int64_t* local, int64_t* nodes_len, char* ws, const BkLayout& L,
+                         uint32_t* err, cudaStream_t stream) {
+  BkParams p;
+  p.samples = samples; p.stride = stride; p.lens = lens; p.nodes = nodes; p.local = local; p.nodes_len = nodes_len;
+  p.num_seeds = num_seeds; p.n_max = n_max; p.num_trees = (int32_t)num_trees;
+  p.nb = L.nb; p.log2_nb = L.log2_nb; p.tiles_per_tree = L.tiles_per_tree; p.ctiles = L.ctiles;
+  p.counts = (uint32_t*)(ws + L.off_counts); p.cursor = (uint32_t*)(ws + L.off_cursor);
+  p.offs = (uint32_t*)(ws + L.off_offs); p.pairs = (uint2*)(ws + L.off_pairs);
+  p.win = (uint32_t*)(ws + L.off_win); p.rank_of = (uint32_t*)(ws + L.off_rank);
+  p.status = (uint64_t*)(ws + L.off_status); p.ticket = (uint32_t*)(ws + L.off_ticket);
+  p.err = err;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(ws + L.off_zero, 0, L.zero_bytes, stream));
+  const dim3 tiles((unsigned)L.tiles_per_tree, (unsigned)num_trees);
+  bk_count_kernel<<<tiles, BK_THREADS, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  bk_offsets_kernel<<<(unsigned)num_trees, 256, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  bk_scatter_kernel<<<tiles, BK_THREADS, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  {
+    static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
+    int dev = 0;
+    TCHGEO_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(bk_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_TABLE * 8));
+      if (dev >= 0 && dev < 64) configured[dev] = true;
+    }
+  }
+  bk_resolve_kernel<<<dim3((unsigned)L.nb, (unsigned)num_trees), 256, BK_TABLE * 8, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  bk_compact_kernel<<<(unsigned)L.ctiles * (unsigned)num_trees, RL_THREADS, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  bk_lookup_kernel<<<dim3((unsigned)L.ctiles, (unsigned)num_trees), RL_THREADS, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  return TCHGEO_OK;
+}
+
 __global__ void rl_set_len_kernel(int64_t* p, int64_t v) { *p = v; }
 
 struct RlLayout {
@@ -824,22 +1225,40 @@ tchgeo_status rl_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
 
 }  // namespace
 
-// used by the sampling plan (neighbor_sampling.cu): size and enqueue the stage for one node type.  k32 (ids < 2^32-1): the
-// persistent form, with the wave form as its fallback on devices without cooperative launch (TCHGEO_RELABEL_WAVES=1
-// forces it); any i64 id: the wave form with 64-bit keys.
-static bool use_persistent(bool k32) {
-  const char* e = getenv("TCHGEO_RELABEL_WAVES");
-  return k32 && !(e && atoi(e) != 0);
+// used by the sampling plan (neighbor_sampling.cu): size and enqueue the stage for one node type.
+//   ids < 2^32-1 (k32): the bucketed form (shared-memory tables); TCHGEO_RELABEL_PERSISTENT=1 selects the persistent
+//   global-table form instead (also the fallback for trees beyond ~12 M ids), TCHGEO_RELABEL_WAVES=1 the wave form;
+//   any i64 id: the wave form with 64-bit keys.
+enum { FORM_WAVES = 0, FORM_PERSISTENT = 1, FORM_BUCKETED = 2 };
+static int relabel_form(int64_t num_trees, int64_t n_max, bool k32) {
+  const char* w = getenv("TCHGEO_RELABEL_WAVES");
+  if (!k32 || (w && atoi(w) != 0)) return FORM_WAVES;
+  const char* pe = getenv("TCHGEO_RELABEL_PERSISTENT");
+  BkLayout B;
+  if (!(pe && atoi(pe) != 0) && bk_layout(num_trees, n_max, B)) return FORM_BUCKETED;
+  RpLayout P;
+  return rp_layout(num_trees, n_max, P) ? FORM_PERSISTENT : FORM_WAVES;
 }
 size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, bool k32) {
   RlLayout L;
   if (!rl_layout(num_trees, n_max, k32, L)) return 0;
-  RpLayout P;
-  if (use_persistent(k32) && rp_layout(num_trees, n_max, P)) return std::max(L.total, P.total);
+  const int form = relabel_form(num_trees, n_max, k32);
+  if (form == FORM_BUCKETED) {
+    BkLayout B;
+    bk_layout(num_trees, n_max, B);
+    return B.total;
+  }
+  if (form == FORM_PERSISTENT) {
+    RpLayout P;
+    rp_layout(num_trees, n_max, P);
+    return std::max(L.total, P.total);   // (the wave form is its fallback without cooperative launch)
+  }
   return L.total;
 }
 int relabel_launches(int64_t num_trees, int64_t n_max, bool k32) {
-  if (use_persistent(k32)) return 1;
+  const int form = relabel_form(num_trees, n_max, k32);
+  if (form == FORM_BUCKETED) return 6;
+  if (form == FORM_PERSISTENT) return 1;
   RlLayout L;
   return rl_layout(num_trees, n_max, k32, L) ? 3 * L.num_waves : 0;
 }
@@ -851,8 +1270,16 @@ tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int6
   TCHGEO_REQUIRE(rl_layout(num_trees, n_max, k32, L), "relabel: tree too large");
   TCHGEO_REQUIRE(workspace && workspace_bytes >= relabel_workspace_bytes(num_trees, n_max, k32),
                  "relabel: workspace too small (need %zu bytes)", relabel_workspace_bytes(num_trees, n_max, k32));
-  RpLayout P;
-  if (use_persistent(k32) && rp_layout(num_trees, n_max, P)) {
+  const int form = relabel_form(num_trees, n_max, k32);
+  if (form == FORM_BUCKETED) {
+    BkLayout B;
+    bk_layout(num_trees, n_max, B);
+    return bk_enqueue(samples, stride, lens, num_trees, num_seeds, n_max, nodes, local, nodes_len, (char*)workspace, B, err,
+                      stream);
+  }
+  if (form == FORM_PERSISTENT) {
+    RpLayout P;
+    rp_layout(num_trees, n_max, P);
     const cudaError_t e = rp_enqueue(samples, stride, lens, num_trees, num_seeds, n_max, nodes, local, nodes_len,
                                      (char*)workspace, P, err, stream);
     if (e == cudaSuccess) return TCHGEO_OK;

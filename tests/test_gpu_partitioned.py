@@ -44,7 +44,8 @@ def test_serve_kernel_matches_oracle(thg, fakedataset, rank, world, fanout):
 
 
 def test_partitioned_single_rank_equals_replicated(thg, fakedataset):
-    from tch_geometric.partitioned import ColumnPartition, PartitionedSampler, SingleComm
+    from tch_geometric.partitioned import ColumnPartition, SingleComm
+    from partitioned_reference import PartitionedSampler
     ei, n = fakedataset
     ptrs, idx, _ = thg.to_csc(dev(ei), n)
     part = ColumnPartition.from_full(ptrs, idx, 0, 1)
@@ -295,3 +296,25 @@ def test_pipelined_groups_equal_replicated(thg, fakedataset):
             for g, x in zip(got.batch(b)[:4], want.batch(b)[:4]):
                 assert torch.equal(g, x)
     thg.clear_caches()
+
+
+@pytest.mark.parametrize("groups", [1, 2])
+def test_real_ranks_fixed_protocol_equals_replicated(groups):
+    """Two real ranks (torchrun, NCCL for the set-up, torch symmetric memory for the exchange buffers): the shipped
+    protocol against the replicated sampler on a scaled papers100M-shaped graph, every batch of every rank bit for bit
+    (tools/check_partitioned.py; the full-shape runs on 2 and 8 B200s are recorded under profiles/r2_check_partitioned_*).
+    Needs two GPUs: skipped on a single-GPU box."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(29600 + groups), os.path.join(root, "tools", "check_partitioned.py"), "--scale", "0.02",
+           "--batches", "8", "--groups", str(groups)]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [ln for ln in out.stdout.splitlines() if ln.startswith("{")][-1]
+    assert json.loads(line)["ok"] is True

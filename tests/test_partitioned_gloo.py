@@ -38,7 +38,8 @@ def _worker(rank, world, port, out_dir):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle import oracle as O
-    from tch_geometric.partitioned import ColumnPartition, DistComm, PartitionedSampler
+    from tch_geometric.partitioned import ColumnPartition, DistComm
+    from partitioned_reference import PartitionedSampler
     from tch_geometric import UniformEdgeSampler, WeightedEdgeSampler
     d = np.load(os.path.join(ROOT, "tests", "golden", "fakedataset.npz"))
     n = int(d["num_nodes"])
