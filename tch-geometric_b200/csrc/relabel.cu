@@ -765,8 +765,8 @@ constexpr int BK_THREADS = 512;
 constexpr int BK_ITEMS = 8;
 constexpr int BK_TILE = BK_THREADS * BK_ITEMS;    // ids per CTA in the count / scatter kernels
 constexpr int BK_MAX_BUCKETS = 4096;              // shared-memory histogram
-constexpr int BK_TABLE = 8192;                    // slots of a bucket's shared-memory table
-constexpr int BK_TARGET = 3072;                   // ids per bucket the bucket count is chosen for (worst-case tree)
+constexpr int BK_TABLE = 4096;                    // slots of a bucket's shared-memory table (32 KB: 7 CTAs per SM)
+constexpr int BK_TARGET = 1536;                   // ids per bucket the bucket count is chosen for (worst-case tree)
 constexpr uint32_t BK_NONE = 0xFFFFFFFFu;
 
 struct BkParams {
@@ -896,67 +896,83 @@ __global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p
 
 // ---- resolve: one CTA per (tree, bucket); the bucket's ids in a shared-memory table ----------------------------------
 __global__ void __launch_bounds__(256) bk_resolve_kernel(const BkParams p) {
-  extern __shared__ __align__(16) unsigned long long s_tab[];   // [BK_TABLE] (64 KB: dynamic, opt-in)
+  // keys and priorities in two 32-bit arrays: native shared-memory atomicCAS / atomicMin (a 64-bit (key | priority) word
+  // needs 64-bit shared atomics, which cost several times more; with those, halving the table to raise the load factor
+  // made the kernel 70 % slower)
+  extern __shared__ __align__(16) uint32_t s_keys[];   // [BK_TABLE] keys, then [BK_TABLE] priorities (64 KB: dynamic, opt-in)
+  uint32_t* s_prio = s_keys + BK_TABLE;
   __shared__ uint32_t s_distinct;
   const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
   const uint32_t cnt = p.counts[(size_t)b * p.nb + j];
   if (cnt == 0) return;
-  for (int q = tid; q < BK_TABLE; q += 256) s_tab[q] = ~0ull;
+  for (int q = tid; q < BK_TABLE / 2; q += 256) reinterpret_cast<uint4*>(s_keys)[q] = make_uint4(~0u, ~0u, ~0u, ~0u);
   if (tid == 0) s_distinct = 0u;
   __syncthreads();
   const uint2* pr = p.pairs + (size_t)b * p.n_max + p.offs[(size_t)b * p.nb + j];
   const uint32_t S = (uint32_t)p.num_seeds;
-  constexpr uint32_t MASK = BK_TABLE - 1;
+  constexpr uint32_t MASK = BK_TABLE - 1, LIMIT = BK_TABLE - BK_TABLE / 8;
+  constexpr int U = 8;   // pairs per thread in flight: the kernel is otherwise bound by one DRAM latency per pair
   bool overflow = false;
-  for (uint32_t q = tid; q < cnt; q += 256) {
-    const uint2 e = pr[q];
-    const uint32_t prio = e.y < S ? S - 1u - e.y : e.y;
-    const unsigned long long want = ((unsigned long long)e.x << 32) | prio;
-    uint32_t h = (e.x * 0x85EBCA6Bu) >> (32 - 13);
-    const uint32_t step = ((e.x * 0xC2B2AE35u) >> 9) | 1u;
-    for (int tries = 0;; ++tries) {
-      const unsigned long long old = atomicCAS(&s_tab[h], ~0ull, want);
-      if (old == ~0ull) {
-        if (atomicAdd(&s_distinct, 1u) >= (uint32_t)(BK_TABLE - BK_TABLE / 8)) overflow = true;  // keep probes finite
-        break;
-      }
-      if ((uint32_t)(old >> 32) == e.x) {
-        atomicMin(&s_tab[h], want);
-        break;
-      }
-      h = (h + step) & MASK;
-      if (tries > BK_TABLE) { overflow = true; break; }
+  for (uint32_t q0 = 0; q0 < cnt && !overflow; q0 += 256 * U) {
+    uint2 e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t q = q0 + u * 256 + tid;
+      e[u] = q < cnt ? __ldcs(pr + q) : make_uint2(0u, BK_NONE);
     }
-    if (overflow) break;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (e[u].y == BK_NONE || overflow) continue;
+      const uint32_t prio = e[u].y < S ? S - 1u - e[u].y : e[u].y;
+      uint32_t h = (e[u].x * 0x85EBCA6Bu) >> (32 - 12);
+      const uint32_t step = ((e[u].x * 0xC2B2AE35u) >> 9) | 1u;
+      for (int tries = 0;; ++tries) {
+        const uint32_t old = atomicCAS(&s_keys[h], BK_NONE, e[u].x);
+        if (old == BK_NONE && atomicAdd(&s_distinct, 1u) >= LIMIT) overflow = true;  // keeps probe sequences finite
+        if (old == BK_NONE || old == e[u].x) {
+          atomicMin(&s_prio[h], prio);   // the smallest priority of the id wins
+          break;
+        }
+        h = (h + step) & MASK;
+        if (tries > BK_TABLE) { overflow = true; break; }
+      }
+    }
   }
   if (__syncthreads_or(overflow)) {
     if (tid == 0) atomicOr(p.err, DEV_ERR_CAPACITY);
     return;
   }
   uint32_t* win = p.win + (size_t)b * p.n_max;
-  for (uint32_t q = tid; q < cnt; q += 256) {
-    const uint2 e = pr[q];
-    uint32_t h = (e.x * 0x85EBCA6Bu) >> (32 - 13);
-    const uint32_t step = ((e.x * 0xC2B2AE35u) >> 9) | 1u;
-    unsigned long long v = s_tab[h];
-    while ((uint32_t)(v >> 32) != e.x) {
-      h = (h + step) & MASK;
-      v = s_tab[h];
+  for (uint32_t q0 = 0; q0 < cnt; q0 += 256 * U) {
+    uint2 e[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t q = q0 + u * 256 + tid;
+      e[u] = q < cnt ? __ldcs(pr + q) : make_uint2(0u, BK_NONE);   // second read of the bucket: an L2 hit
     }
-    const uint32_t prio = (uint32_t)v;
-    win[e.y] = prio < S ? S - 1u - prio : prio;   // the last seed carrying the id (:26), else its first occurrence
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (e[u].y == BK_NONE) continue;
+      uint32_t h = (e[u].x * 0x85EBCA6Bu) >> (32 - 12);
+      const uint32_t step = ((e[u].x * 0xC2B2AE35u) >> 9) | 1u;
+      while (s_keys[h] != e[u].x) h = (h + step) & MASK;
+      const uint32_t prio = s_prio[h];
+      win[e[u].y] = prio < S ? S - 1u - prio : prio;   // the last seed carrying the id (:26), else its first occurrence
+    }
   }
 }
 
 // ---- compact: flags, scan in position order (decoupled look-back per tree), node list, ranks, local ids --------------
 __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p) {
-  __shared__ uint32_t s_wtot[RL_THREADS / 32];
   __shared__ uint32_t s_tile;
   __shared__ int64_t s_excl;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);   // tiles in start order, tree-major
+  // tiles in start order and TILE-major (ticket -> tile t of tree ticket % trees): the tiles in flight belong to many
+  // trees, so a tile's predecessors in its own tree finished long ago and the look-back finds an inclusive prefix at once
+  // (tree-major, all tiles of a tree start together and the late ones sum hundreds of aggregates: 2.2 ms instead of 1.x)
+  if (tid == 0) s_tile = atomicAdd(p.ticket, 1u);
   __syncthreads();
-  const int b = (int)(s_tile / (uint32_t)p.ctiles), t = (int)(s_tile - (uint32_t)b * (uint32_t)p.ctiles);
+  const int t = (int)(s_tile / (uint32_t)p.num_trees), b = (int)(s_tile - (uint32_t)t * (uint32_t)p.num_trees);
   const int64_t n = bk_len(p, b);
   const int64_t i0 = (int64_t)t * RL_TILE;
   if (i0 >= n && t > 0) return;
@@ -965,14 +981,18 @@ __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p
   uint32_t* rank_of = p.rank_of + (size_t)b * p.n_max;
   int64_t* local = p.local + (int64_t)b * p.stride;
   const int64_t S = p.num_seeds;
-  const int64_t ibase = i0 + (int64_t)tid * RL_ITEMS;
+  // position of (u, tid) = i0 + u * RL_THREADS + tid: consecutive threads touch consecutive positions in every load and
+  // store (a thread owning 4 consecutive positions made every 8-byte store instruction hit 32 different sectors)
   uint32_t w[RL_ITEMS];
   uint32_t node = 0;
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) w[u] = ibase + u < n ? win[ibase + u] : BK_NONE;
+  for (int u = 0; u < RL_ITEMS; ++u) {
+    const int64_t i = i0 + u * RL_THREADS + tid;
+    w[u] = i < n ? win[i] : BK_NONE;
+  }
 #pragma unroll
   for (int u = 0; u < RL_ITEMS; ++u) {
-    const int64_t i = ibase + u;
+    const int64_t i = i0 + u * RL_THREADS + tid;
     if (i >= n) continue;
     if (i < S) {                                   // every seed is kept (:25) and maps to the last seed with its id (:26)
       node |= 1u << u;
@@ -985,21 +1005,27 @@ __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p
       node |= 1u << u;                              // first occurrence of an id no seed carries (:36-39)
     }                                               // else: a later occurrence, bk_lookup_kernel
   }
-  const uint32_t cnt = __popc(node);
-  uint32_t incl = cnt;
+  // exclusive rank of (u, tid) in position order = nodes of rows u' < u  +  nodes of row u in earlier warps / lanes
+  __shared__ uint32_t s_cnt[RL_ITEMS][RL_THREADS / 32];
+  uint32_t lane_excl[RL_ITEMS];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += up;
+  for (int u = 0; u < RL_ITEMS; ++u) {
+    const uint32_t m = __ballot_sync(0xffffffffu, (node >> u) & 1u);
+    lane_excl[u] = __popc(m & ((1u << lane) - 1u));
+    if (lane == 0) s_cnt[u][warp] = __popc(m);
   }
-  if (lane == 31) s_wtot[warp] = incl;
   __syncthreads();
-  uint32_t excl = incl - cnt, total = 0;
+  uint32_t excl_u[RL_ITEMS];
+  uint32_t total = 0;
 #pragma unroll
-  for (int k = 0; k < RL_THREADS / 32; ++k) {
-    const uint32_t v = s_wtot[k];
-    if (k < warp) excl += v;
-    total += v;
+  for (int u = 0; u < RL_ITEMS; ++u) {
+    excl_u[u] = total + lane_excl[u];
+#pragma unroll
+    for (int k = 0; k < RL_THREADS / 32; ++k) {
+      const uint32_t v = s_cnt[u][k];
+      if (k < warp) excl_u[u] += v;
+      total += v;
+    }
   }
   uint64_t* st = p.status + (size_t)b * p.ctiles;
   if (tid == 0) st_relaxed_u64(st + t, (t == 0 ? 2ull << 62 : 1ull << 62) | (uint64_t)total);
@@ -1039,17 +1065,16 @@ __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p
   const int64_t tile_excl = s_excl;
   if (tid == 0 && i0 + RL_TILE >= n) p.nodes_len[b] = tile_excl + total;
   int64_t* nodes = p.nodes + (int64_t)b * p.stride;
-  uint32_t r = (uint32_t)tile_excl + excl;
 #pragma unroll
   for (int u = 0; u < RL_ITEMS; ++u) {
     if (!((node >> u) & 1u)) continue;
-    const int64_t i = ibase + u;
+    const int64_t i = i0 + u * RL_THREADS + tid;
+    const uint32_t r = (uint32_t)tile_excl + excl_u[u];
     st_cs_i64(nodes + r, __ldg(src + i));
     if (i >= S) {
       st_cs_i64(local + i, (int64_t)r);
       rank_of[i] = r;
     }
-    ++r;
   }
 }
 
