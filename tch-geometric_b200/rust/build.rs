@@ -9,7 +9,7 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = vec![];
     for src in ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu",
-                "partitioned.cu", "random_walk.cu", "relabel.cu"] {
+                "partitioned.cu", "partitioned_fixed.cu", "random_walk.cu", "relabel.cu"] {
         let obj = out.join(src.replace(".cu", ".o"));
         let ok = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -27,4 +27,13 @@ fn main() {
     println!("cargo:rustc-link-search=native=/usr/local/cuda/lib64");
     println!("cargo:rustc-link-lib=cudart");
     println!("cargo:rustc-link-lib=stdc++");
+    // torch's current CUDA stream for the bindings (tch-rs does not expose it): one C++ file against the libtorch headers
+    // the reference's torch-sys build already requires (LIBTORCH)
+    let libtorch = env::var("LIBTORCH").expect("LIBTORCH must point at the libtorch the crate links against");
+    let shim = out.join("torch_stream_shim.o");
+    assert!(Command::new("g++").args(["-std=c++17", "-O2", "-fPIC", "-c"]).arg(csrc.join("torch_stream_shim.cpp"))
+        .arg(format!("-I{libtorch}/include")).arg("-I/usr/local/cuda/include").arg("-o").arg(&shim).status().unwrap().success());
+    assert!(Command::new("ar").arg("crs").arg(out.join("libtchgeo_shim.a")).arg(&shim).status().unwrap().success());
+    println!("cargo:rustc-link-lib=static=tchgeo_shim");
+    println!("cargo:rustc-link-lib=c10_cuda");
 }
