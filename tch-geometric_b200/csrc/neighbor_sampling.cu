@@ -618,7 +618,8 @@ __global__ void __launch_bounds__(HOP_THREADS, MINB) hop_kernel(const HopParams 
 // the neighbourhood emits the chosen edges and the new per-sample states.
 // ---------------------------------------------------------------------------------------------
 constexpr int FT_THREADS = 128;
-constexpr int FT_MASKW = 16;  // ballot masks of a node's first 16 chunks (512 edges) are kept in shared memory by pass 1
+constexpr int FT_MASKW = 2;   // passing-edge masks of a node's first 64 edges are kept in shared memory by pass 1
+constexpr uint32_t FT_LIGHT = 32u * FT_MASKW;  // nodes up to this degree are handled by ONE THREAD each, hubs by a warp
 
 // STATIC: a fixed window on the timestamp (:59); RELATIVE / DYNAMIC: a window on the distance to the sample's state (:60-65)
 template <bool STATIC>
@@ -665,28 +666,57 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
   if (nn == 0 && !is_last) return;
 
   // ---- pass 1: number of passing edges per node ------------------------------------------------
-  for (int n = warp; n < nn; n += NWARP) {
-    const int64_t gi = (int64_t)b * p.dst_stride + fb + node0 + n;
+  // Light nodes (deg <= 64: nearly all of them, the mean degree is 25) take ONE THREAD each: the thread walks its
+  // column's timestamps and keeps the passing mask in two registers.  With a warp per node the kernel was bound by the
+  // fixed per-node cost of the warp loop (id -> colptr -> timestamps chain, 71 % issue utilisation, most lanes idle);
+  // a thread per node shares that cost over 32 nodes.  Hubs keep the warp loop below.
+  __shared__ uint8_t s_hub[FT_THREADS];
+  __shared__ uint32_t s_nhub;
+  if (tid == 0) s_nhub = 0u;
+  __syncthreads();
+  if (tid < nn) {
+    const int64_t gi = (int64_t)b * p.dst_stride + fb + node0 + tid;
     const int64_t w = p.dst_samples[gi];
     const int64_t state = p.dst_states[gi];
     int64_t start = 0;
-    uint32_t deg = 0, npass = 0;
+    uint32_t deg = 0;
     if (w < 0 || w >= p.num_cols) {
-      if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX);
+      atomicOr(p.err, DEV_ERR_INDEX);
     } else {
       start = __ldg(p.ptrs + w);
       const int64_t d = __ldg(p.ptrs + w + 1) - start;
-      if (d < 0 || d > 0x7fffffffll || start < 0 || start + d > p.nnz) { if (lane == 0) atomicOr(p.err, DEV_ERR_INDEX); }
+      if (d < 0 || d > 0x7fffffffll || start < 0 || start + d > p.nnz) atomicOr(p.err, DEV_ERR_INDEX);
       else deg = (uint32_t)d;
     }
+    s_start[tid] = start; s_state[tid] = state; s_deg[tid] = deg;
+    if (deg <= FT_LIGHT) {
+      uint32_t lo = 0, hi = 0;
+      const int64_t* ts = p.timestamps + start;
+      for (uint32_t e = 0; e < deg; ++e) {
+        const uint32_t ok = filter_pass<STATIC>(p, __ldg(ts + e), state) ? 1u : 0u;
+        if (e < 32u) lo |= ok << e; else hi |= ok << (e - 32u);
+      }
+      s_mask[tid * FT_MASKW] = lo;
+      s_mask[tid * FT_MASKW + 1] = hi;
+      s_pass[tid] = __popc(lo) + __popc(hi);
+    } else {
+      s_hub[atomicAdd(&s_nhub, 1u)] = (uint8_t)tid;
+    }
+  }
+  __syncthreads();
+  for (uint32_t hb = warp; hb < s_nhub; hb += NWARP) {   // hubs: one warp sweeps the column
+    const int n = s_hub[hb];
+    const int64_t start = s_start[n], state = s_state[n];
+    const uint32_t deg = s_deg[n];
+    uint32_t npass = 0;
     for (uint32_t base = 0; base < deg; base += 32) {
       const uint32_t item = base + lane;
       const bool ok = item < deg && filter_pass<STATIC>(p, __ldg(p.timestamps + start + item), state);
       const uint32_t m = __ballot_sync(0xffffffffu, ok);
-      if (lane == 0 && base < 32u * FT_MASKW) s_mask[n * FT_MASKW + (base >> 5)] = m;  // the select pass reuses it
+      if (lane == 0 && base < FT_LIGHT) s_mask[n * FT_MASKW + (base >> 5)] = m;  // the select pass reuses it
       npass += __popc(m);
     }
-    if (lane == 0) { s_start[n] = start; s_state[n] = state; s_deg[n] = deg; s_pass[n] = npass; }
+    if (lane == 0) s_pass[n] = npass;
   }
   __syncthreads();
   uint32_t cnt = 0;
@@ -755,7 +785,64 @@ __global__ void __launch_bounds__(FT_THREADS) hop_filtered_kernel(const HopParam
   const uint32_t batch = p.batch_base + (uint32_t)b;
   uint8_t* s_owner = reinterpret_cast<uint8_t*>(s_mask + FT_THREADS * FT_MASKW);  // [tile_edges] output edge -> node of the tile
   constexpr uint32_t RESOLVED = 0x80000000u;
-  for (int n = warp; n < nn; n += NWARP) {
+  // light nodes: the node's thread makes the decisions serially on its own slots (no atomics) and selects the chosen
+  // edges from its two mask words
+  if (tid < nn && s_deg[tid] <= FT_LIGHT) {
+    const int n = tid;
+    const uint32_t np = s_pass[n], o = s_off[n];
+    const uint32_t c_n = KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE ? (np > 0 ? k : 0u) : min(np, k);
+    if (c_n > 0) {
+      uint32_t* q = s_slot + o;
+      const uint32_t lo = s_mask[n * FT_MASKW], hi = s_mask[n * FT_MASKW + 1], nlo = __popc(lo);
+      auto nth_passing = [&](uint32_t r) { return r < nlo ? __fns(lo, 0, (int)r + 1) : 32u + __fns(hi, 0, (int)(r - nlo) + 1); };
+      for (uint32_t s2 = 0; s2 < c_n; ++s2) {
+        q[s2] = 0u;
+        s_owner[o + s2] = (uint8_t)n;
+      }
+      if (KIND == TCHGEO_SAMPLER_UNIFORM && np > k) {
+        const uint32_t nb = (np - k + 3u) >> 2;
+        for (uint32_t c = 0; c < nb; ++c) {          // sampling.rs:17-23 in step order: the last hit of a slot wins
+          const Philox4 r = philox4x32_10(pos0 + n, c, batch, TAG_RESERVOIR | (p.rel << 8), p.key0, p.key1);
+#pragma unroll
+          for (uint32_t u = 0; u < 4; ++u) {
+            const uint32_t step = k + 4u * c + u;
+            const uint32_t jj = __umulhi(pick4(r, u), step);
+            if (step < np && jj < k) q[jj] = step;
+          }
+        }
+      } else if (KIND == TCHGEO_SAMPLER_WEIGHTED && np > k) {
+        // w_sum in the reference's own order (w_sum = w_sum + w over the passing edges, sampling.rs:37-48)
+        double w_sum = 0.0;
+        const int64_t start = s_start[n];
+        for (uint32_t rank = 0; rank < np; ++rank) {
+          const double wv = __ldg(p.weights + start + nth_passing(rank));
+          w_sum = w_sum + wv;
+          if (rank < k) continue;
+          if (!(w_sum > 0.0)) {
+            atomicOr(p.err, DEV_ERR_PANIC);
+            continue;
+          }
+          const Philox4 r = philox4x32_10(pos0 + n, rank, batch, TAG_WEIGHTED | (p.rel << 8), p.key0, p.key1);
+          const uint64_t u53 = ((uint64_t)r.x << 21) | (uint64_t)(r.y >> 11);
+          const double u = __dmul_rn((double)u53, 1.0 / 9007199254740992.0);
+          if (__dmul_rn(u, w_sum) < wv) q[__umulhi(r.z, k)] = rank;
+        }
+      }
+      for (uint32_t s2 = 0; s2 < c_n; ++s2) {
+        uint32_t r;
+        if (KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE) {
+          const Philox4 rr = philox4x32_10(pos0 + n, s2 >> 2, batch, TAG_REPLACE | (p.rel << 8), p.key0, p.key1);
+          r = __umulhi(pick4(rr, s2 & 3u), np);
+        } else {
+          r = q[s2] ? q[s2] : s2;
+        }
+        q[s2] = RESOLVED | nth_passing(r);
+      }
+    }
+  }
+  // hubs: one warp per node
+  for (uint32_t hb = warp; hb < s_nhub; hb += NWARP) {
+    const int n = s_hub[hb];
     const uint32_t np = s_pass[n], deg = s_deg[n], o = s_off[n];
     const uint32_t c_n = KIND == TCHGEO_SAMPLER_UNIFORM_REPLACE ? (np > 0 ? k : 0u) : min(np, k);
     if (c_n == 0) continue;
