@@ -153,3 +153,55 @@ def test_peer_offsets_reproduce_the_all_to_all_layout():
             for q in range(world):      # me as owner: my answers to requester q
                 for i in range(C[q][me]):
                     assert back[q][ans_row0[q] + i] == (q, me, i)
+
+
+def test_partition_geometry_helpers():
+    """Pure host arithmetic of the partitioned plans: column ranges, worst-case frontiers, segment sizes, and the row
+    offsets round 1's peer protocol derives from the count matrix."""
+    from tch_geometric.partitioned import (cols_per_rank, frontier_caps, partition_bounds, peer_offsets, segment_rows,
+                                           SegmentBuffers)
+    assert cols_per_rank(10, 4) == 3 and [partition_bounds(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 9), (9, 10)]
+    assert frontier_caps(1024, [15, 10, 5]) == [1024, 15360, 153600]
+    # one rank: the segment is the whole frontier (no slack needed); several: slack x the mean load, even, never more than all
+    assert segment_rows(256, 153600, 1, 1.5) == 256 * 153600
+    s8 = segment_rows(256, 153600, 8, 1.5)
+    assert s8 % 2 == 0 and 1.5 * 256 * 153600 / 8 <= s8 <= 1.5 * 256 * 153600 / 8 + 1026
+    assert segment_rows(2, 4, 8, 1.5) == 8                       # capped by the frontier itself
+    assert segment_rows(256, 153600, 8, 1.5) < 2 ** 26           # fits the slot map's 26-bit row index
+    segs, req_words, ans_words = SegmentBuffers.sizes(256, frontier_caps(1024, [15, 10, 5]), [15, 10, 5], 8, 1.5)
+    assert req_words == 8 * max(segs) * 2 and ans_words == 8 * max(s * 2 * k for s, k in zip(segs, [15, 10, 5]))
+    C = [[1, 2, 3], [4, 5, 6], [7, 8, 9]]                         # C[q][o]: requests of q for owner o
+    rc, sc, req_row0, ans_row0 = peer_offsets(C, 1)
+    assert sc == [4, 5, 6] and rc == [2, 5, 8]
+    assert req_row0 == [1, 2, 3] and ans_row0 == [1, 4, 7]
+
+
+def test_handles_and_partitioned_entries_validate_on_the_host():
+    """The new entry points reject bad arguments before any CUDA call (no GPU needed): graph / plan handles, the batched
+    relabel stage and the fixed-segment protocol."""
+    lib = N.lib
+    h = ctypes.c_void_p(0)
+    assert lib.tchgeo_graph_create(0, None, None, None, None, ctypes.addressof(h)) == N.ERR_BAD_ARG
+    assert lib.tchgeo_graph_create(1, None, None, None, None, None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_graph_derived_bytes(None) == 0
+    lib.tchgeo_graph_destroy(None)
+    lib.tchgeo_plan_destroy(None)
+    assert lib.tchgeo_plan_create(None, ctypes.addressof(h)) == N.ERR_BAD_ARG
+    assert lib.tchgeo_plan_enqueue(None, 0, 0, None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_plan_collect(None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_plan_num_launches(None) == 0
+    # relabel geometry: workspace grows with the tree size; absurd sizes are refused
+    small = lib.tchgeo_unique_relabel_batched_workspace_bytes(4, 1000, 1)
+    big = lib.tchgeo_unique_relabel_batched_workspace_bytes(256, 937984, 1)
+    assert 0 < small < big and lib.tchgeo_unique_relabel_batched_workspace_bytes(4, 1 << 40, 1) == 0
+    assert lib.tchgeo_unique_relabel_batched(None, 10, None, 4, 2, 20, 1, None, None, None, None, 0, None, None) == N.ERR_BAD_ARG
+    # fixed-segment protocol
+    assert lib.tchgeo_partf_workspace_bytes(256, 153600) > 0 and lib.tchgeo_partf_workspace_bytes(0, 10) == 0
+    assert lib.tchgeo_partf_scatter(None, 0, None, None, 1, 1, 1, 0, 0, 0, 8, None, None, None, None, None, None, None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_partf_scatter(None, 0, None, None, 1, 1, 1, 2, 0, 0, 1 << 26, None, None, None, None, None, None, None) == N.ERR_BAD_ARG
+    assert b"segment" in lib.tchgeo_last_error()
+    assert lib.tchgeo_partf_serve(None, None, None, None, 0, 1, 1, None, None, 8, 0, 65, 0, 0, 0, 1, 0, None, None, None) == N.ERR_BAD_ARG
+    assert b"fanout" in lib.tchgeo_last_error()
+    assert lib.tchgeo_partf_finish(None, None, 8, 5, None, 1, None, None, 1, 1, None, None, None, None, None, 0, None, None,
+                                   None, 0, None, None, 0, None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_pack_ragged(None, 4, None, 1, 70000, 4, None, None, None) == N.ERR_BAD_ARG
