@@ -538,15 +538,15 @@ def run_relabel(thg, ptrs, idx, dev_seeds, sampler, B, S, K, W, world, rank, dev
     step_ms, edges_all = reduce_job(step_ms, float(edges), device)
     peak, peak_src = measured_peak_gbs()
     # algorithmic bytes of the stage: every id is read once (8 B) and gets a local id (8 B); every distinct node is
-    # written once (8 B).  Hash-table traffic stays in the L2 by construction (waves) and is not counted.
+    # written once (8 B).  The stage's own pair / winner arrays are its overhead, not algorithmic bytes.
     alg = 16.0 * n_samples + 8.0 * n_nodes
     rl_ms = float(ms[-1])
     out = {"value": edges_all / (step_ms * 1e-3), "unit": UNIT, "ms_per_step": step_ms / K,
            "hops_ms_per_step": float(ms[:-1].sum()) / K, "relabel_ms_per_step": rl_ms / K,
            "ids_per_step": n_samples / K, "distinct_nodes_per_step": n_nodes / K,
            "what": "sum of the per-launch CUDA-event intervals of one plan (hop kernels + relabel stage)",
-           "roofline": {"bound": "hbm", "kernel": "relabel stage: rl_insert_kernel + rl_compact_kernel + rl_lookup_kernel, "
-                        "all waves of the step", "achieved": alg / (rl_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+           "roofline": {"bound": "hbm", "kernel": "relabel stage (csrc/relabel.cu, bucketed form): bk_count / bk_offsets / "
+                        "bk_scatter / bk_resolve_direct / bk_compact / bk_lookup over all batches of the step", "achieved": alg / (rl_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg / (rl_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_step": alg / K,
                         "byte_model": "16 B per id (8 read + 8 local written) + 8 B per distinct node"},
@@ -571,7 +571,8 @@ def run_relabel_only(args):
     clocks.start()
     out = run_relabel(thg, ptrs, idx, dev_seeds, None, B, S, K, W, world, rank, device, barrier)
     out["clocks"] = clocks.stop()
-    out["wave_mb"] = os.environ.get("TCHGEO_RELABEL_WAVE_MB", "64 (default)")
+    out["form"] = {k: os.environ[k] for k in ("TCHGEO_RELABEL_DIRECT", "TCHGEO_RELABEL_PERSISTENT", "TCHGEO_RELABEL_WAVES",
+                                              "TCHGEO_RELABEL_WAVE_MB") if k in os.environ} or "default (bucketed, direct)"
     if rank == 0:
         emit({"metric": METRIC + "_with_relabel", "n_gpus": world, "steps": K, "warmup": W, "higher_is_better": True,
               "scaling": "weak", "vs_baseline": None, "dtype": "int64", "data": "synthetic",

@@ -39,7 +39,7 @@
 extern "C" {
 #endif
 
-#define TCHGEO_ABI_VERSION 5
+#define TCHGEO_ABI_VERSION 6
 
 #if defined(__GNUC__)
 #define TCHGEO_API __attribute__((visibility("default")))
@@ -536,14 +536,18 @@ TCHGEO_API tchgeo_status tchgeo_pack_ragged(const int64_t* src /*DEVICE [B, stri
 /* semantic of src/algo/negative_sampling.rs:20-47                                               */
 /* -------------------------------------------------------------------------------------------- */
 /* Batched form: B trees in padded [B, stride] rows, tree b holding lens[b] <= n_max ids (DEVICE lengths: no host
- * round trip), the first num_seeds of them seeds.  nodes / local: [B, stride]; nodes_len: DEVICE [B].  key32 != 0
- * selects 8-byte hash slots for ids < 2^32-1 (an id outside raises TCHGEO_ERR_INDEX); 0 handles any non-negative i64.
+ * round trip), the first num_seeds of them seeds.  nodes / local: [B, stride]; nodes_len: DEVICE [B].
+ * id_bound states what the caller knows about the ids:
+ *   0               any non-negative i64 (global hash tables with 16-byte slots, processed in L2-sized waves);
+ *   1 .. 2^32-1     every id is in [0, id_bound); an id outside raises TCHGEO_ERR_INDEX.  Pass the node count when it is
+ *                   known (the sampling plan does, from the graph handle): bounds up to 2^25 select direct-address
+ *                   shared-memory tables, larger ones (2^32-1 = "fits 32 bits, nothing else known") hashed ones.
  * Asynchronous; device-side errors are OR-ed into *err_word (DEVICE u32, caller-zeroed; tchgeo_status_from_error_word).
- * The batches are processed in waves whose hash tables stay in the L2 (see csrc/relabel.cu). */
-TCHGEO_API size_t tchgeo_unique_relabel_batched_workspace_bytes(int64_t num_batches, int64_t n_max, int32_t key32);
+ * The workspace size depends on id_bound: pass the same value to the query and to the call (see csrc/relabel.cu). */
+TCHGEO_API size_t tchgeo_unique_relabel_batched_workspace_bytes(int64_t num_batches, int64_t n_max, int64_t id_bound);
 TCHGEO_API tchgeo_status tchgeo_unique_relabel_batched(const int64_t* samples /*DEVICE [B, stride]*/, int64_t stride,
                                                        const int64_t* lens /*DEVICE [B]*/, int64_t num_batches,
-                                                       int64_t num_seeds, int64_t n_max, int32_t key32,
+                                                       int64_t num_seeds, int64_t n_max, int64_t id_bound,
                                                        int64_t* nodes /*DEVICE [B, stride]*/, int64_t* local /*DEVICE [B, stride]*/,
                                                        int64_t* nodes_len /*DEVICE [B]*/, void* workspace /*DEVICE*/,
                                                        size_t workspace_bytes, int32_t* err_word /*DEVICE*/,

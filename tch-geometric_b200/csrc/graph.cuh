@@ -15,6 +15,7 @@ struct tchgeo_graph {
   // derived, owned
   std::vector<int32_t*> indices32;
   std::vector<uint8_t> replica_state;  // 0 = not tried, 1 = built, 2 = not representable (ids >= 2^31) or disabled
+  std::vector<int64_t> max_index;      // largest entry of indices[r], found while the replica is built (-1 = unknown)
   std::vector<double2*> wrec;
   size_t derived_bytes = 0;
 };

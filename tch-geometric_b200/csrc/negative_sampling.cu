@@ -25,9 +25,9 @@
 
 namespace tchgeo {
 // csrc/relabel.cu: the batched dedup + relabel stage (device-side lengths, asynchronous)
-size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, bool k32);
+size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound);
 tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
-                              int64_t num_seeds, int64_t n_max, bool k32, int64_t* nodes, int64_t* local,
+                              int64_t num_seeds, int64_t n_max, int64_t id_bound, int64_t* nodes, int64_t* local,
                               int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
                               cudaStream_t stream);
 namespace {
@@ -212,7 +212,7 @@ tchgeo_status neg_plan(const tchgeo_negative_args* a, NegPlan& P, bool layout = 
   TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, cub, (const int*)nullptr, (int*)nullptr,
                                                   (int64_t)(G > 0 ? G : 1)));
   P.cub_bytes = cub;
-  P.rl_bytes = relabel_workspace_bytes(1, std::max<int64_t>(P.max_seq, 1), P.k32);
+  P.rl_bytes = relabel_workspace_bytes(1, std::max<int64_t>(P.max_seq, 1), P.k32 ? 0xFFFFFFFFll : 0);
   TCHGEO_REQUIRE(P.rl_bytes != 0, "relabel workspace query failed");
   const size_t g = (size_t)(G > 0 ? G : 1), sq = (size_t)(P.seq_total > 0 ? P.seq_total : 1);
   size_t o = 0;
@@ -352,7 +352,7 @@ extern "C" tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* a)
     TCHGEO_CUDA_CHECK(cudaGetLastError());
     if (P.seq_cap[t] == 0) continue;
     TCHGEO_REQUIRE(a->samples[t], "samples[%d] is NULL", t);
-    st = relabel_enqueue(seq_t, P.seq_cap[t], d_len + t, 1, P.S[t], P.seq_cap[t], P.k32, a->samples[t], local_t, d_nodes + t,
+    st = relabel_enqueue(seq_t, P.seq_cap[t], d_len + t, 1, P.S[t], P.seq_cap[t], P.k32 ? 0xFFFFFFFFll : 0, a->samples[t], local_t, d_nodes + t,
                          ws + P.off_rl, P.rl_bytes, d_err, stream);
     if (st != TCHGEO_OK) return st;
   }

@@ -96,16 +96,24 @@ struct HopParams {
   int64_t* src_states;          // [B, src_stride] states of appended samples are written here
 };
 
+// err[0] |= DEV_ERR_INDEX when an id does not fit; WITH_MAX: err[1] = max id (the relabel stage's id bound)
+template <bool WITH_MAX>
 __global__ void __launch_bounds__(256) compress_kernel(const int64_t* __restrict__ src, int64_t n,
                                                        int32_t* __restrict__ dst, uint32_t* err) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   bool bad = false;
+  uint32_t mx = 0u;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const int64_t v = src[i];
     bad |= (v < 0 || v > 0x7fffffffll);
     dst[i] = (int32_t)v;
+    if (WITH_MAX && (uint32_t)v > mx) mx = (uint32_t)v;
   }
   if (bad) atomicOr(err, DEV_ERR_INDEX);
+  if (WITH_MAX) {
+    mx = __reduce_max_sync(0xffffffffu, mx);
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(err + 1, mx);
+  }
 }
 
 __global__ void fill_i64_kernel(int64_t* p, int64_t v, int64_t n) {
@@ -990,13 +998,31 @@ tchgeo_status graph_ensure(tchgeo_graph* g, int32_t what, cudaStream_t stream) {
       g->replica_state[(size_t)r] = 2;
       const int64_t n = g->nnz[(size_t)r];
       if (n <= 0 || !g->indices[(size_t)r]) continue;
-      if (!d_err) TCHGEO_CUDA_CHECK(cudaMalloc(&d_err, 4));
+      if (!d_err) TCHGEO_CUDA_CHECK(cudaMalloc(&d_err, 8));
       int32_t* dst = nullptr;
       TCHGEO_CUDA_CHECK(cudaMalloc(&dst, (size_t)n * 4));
-      const tchgeo_status st = tchgeo_compress_indices(g->indices[(size_t)r], n, dst, (int32_t*)d_err, stream);
+      uint32_t h[2] = {0u, 0u};
+      tchgeo_status st = TCHGEO_OK;
+      {
+        cudaError_t e = cudaMemsetAsync(d_err, 0, 8, stream);
+        if (e == cudaSuccess) {
+          compress_kernel<true><<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(
+              g->indices[(size_t)r], n, dst, d_err);
+          e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_err, 8, cudaMemcpyDeviceToHost, stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+        if (e != cudaSuccess) {
+          cudaFree(dst);
+          cudaFree(d_err);
+          TCHGEO_CUDA_CHECK(e);
+        }
+        st = status_from_dev_err(h[0]);
+      }
       if (st == TCHGEO_OK) {
         g->indices32[(size_t)r] = dst;
         g->replica_state[(size_t)r] = 1;
+        g->max_index[(size_t)r] = (int64_t)h[1];
         g->derived_bytes += (size_t)n * 4;
       } else {
         cudaFree(dst);  // ids beyond int32 (or negative): sample from the i64 array; the kernels report bad ids
@@ -1056,6 +1082,7 @@ extern "C" tchgeo_status tchgeo_graph_create(int32_t num_rels, const int64_t* co
   g->timestamps.assign(R, nullptr);
   g->indices32.assign(R, nullptr);
   g->replica_state.assign(R, 0);
+  g->max_index.assign(R, -1);
   g->wrec.assign(R, nullptr);
   *out = g;
   return TCHGEO_OK;
@@ -1096,10 +1123,10 @@ extern "C" void tchgeo_graph_destroy(tchgeo_graph_t* g) {
 // ---- host-side plan: which launches, which version rows of the length table ------------------
 namespace tchgeo {
 // csrc/relabel.cu
-size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, bool k32);
-int relabel_launches(int64_t num_trees, int64_t n_max, bool k32);
+size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound);
+int relabel_launches(int64_t num_trees, int64_t n_max, int64_t id_bound);
 tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
-                              int64_t num_seeds, int64_t n_max, bool k32, int64_t* nodes, int64_t* local,
+                              int64_t num_seeds, int64_t n_max, int64_t id_bound, int64_t* nodes, int64_t* local,
                               int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
                               cudaStream_t stream);
 namespace {
@@ -1122,6 +1149,7 @@ struct Resolved {
   std::vector<const double*> weights;
   std::vector<const int32_t*> indices32;
   std::vector<const double2*> wrec;
+  std::vector<int64_t> max_index;   // largest id of indices[r], -1 = unknown (no graph handle / no replica)
 };
 
 struct Plan {
@@ -1135,10 +1163,11 @@ struct Plan {
   std::vector<int64_t> samples_cap, edges_cap;  // worst case per batch
   int num_rows;                         // V
   size_t status_words;
-  // dedup + relabel stage (K7): one length row per node type, 8-byte hash slots where the ids are known to fit
+  // dedup + relabel stage (K7): one length row per node type; id_bound = what is known about the type's ids
+  // (0: any i64; 2^32-1: they fit 32 bits; less: the type's node count, which lets the stage use direct-address tables)
   bool relabel;
   std::vector<int> nodes_row;           // [T] or -1
-  std::vector<uint8_t> key32;           // [T]
+  std::vector<int64_t> id_bound;        // [T]
   int relabel_kernels;
   // workspace layout (bytes)
   size_t off_ctrl, off_state, off_status, off_relabel, relabel_bytes, total_bytes;
@@ -1152,6 +1181,7 @@ tchgeo_status resolve(const tchgeo_sampling_args* a, Resolved& rs, bool want_der
   rs.ptrs.assign(R, nullptr); rs.indices.assign(R, nullptr); rs.timestamps.assign(R, nullptr);
   rs.num_cols.assign(R, 0); rs.nnz.assign(R, INT64_MAX);
   rs.weights.assign(R, nullptr); rs.indices32.assign(R, nullptr); rs.wrec.assign(R, nullptr);
+  rs.max_index.assign(R, -1);
   const bool weighted = a->sampler_kind == TCHGEO_SAMPLER_WEIGHTED;
   if (a->graph) {
     tchgeo_graph* g = const_cast<tchgeo_graph*>(a->graph);
@@ -1167,6 +1197,7 @@ tchgeo_status resolve(const tchgeo_sampling_args* a, Resolved& rs, bool want_der
       rs.weights[r] = weighted ? g->weights[r] : nullptr;
       rs.timestamps[r] = (a->timestamps && a->timestamps[r]) ? a->timestamps[r] : g->timestamps[r];
       rs.indices32[r] = env_int("TCHGEO_INDEX_REPLICA", 1) != 0 ? g->indices32[r] : nullptr;
+      rs.max_index[r] = g->max_index[r];
       rs.wrec[r] = (weighted && !a->filter_mode) ? g->wrec[r] : nullptr;
     }
     return TCHGEO_OK;
@@ -1284,7 +1315,7 @@ tchgeo_status build_plan(const tchgeo_sampling_args* a, Plan& pl) {
   pl.off_relabel = pl.off_status + ((status_words * 8 + 255) / 256) * 256;
   pl.relabel_bytes = 0;
   pl.relabel_kernels = 0;
-  pl.key32.assign(T, 0);
+  pl.id_bound.assign(T, 0);
   pl.total_bytes = pl.off_relabel + 256;
   return TCHGEO_OK;
 }
@@ -1298,20 +1329,32 @@ tchgeo_status make_plan(const tchgeo_sampling_args* a, Plan& pl, bool want_deriv
   if (pl.relabel) {
     TCHGEO_REQUIRE(a->nodes && a->local, "relabel needs both nodes and local");
     for (int t = 0; t < pl.T; ++t) {
-      // 8-byte slots when every id of the type is known to be below 2^31: all relations that append to it read an
-      // int32 replica (seeds beyond 2^32-2 are then reported as TCHGEO_ERR_INDEX by the stage)
-      bool k32 = true, fed = false;
-      for (int r = 0; r < pl.R; ++r)
-        if (a->rel_src[r] == t && (!a->rel_active || a->rel_active[r])) {
+      // 32-bit keys when every id of the type is known to be below 2^31: all relations that append to it read an
+      // int32 replica (seeds beyond the bound are then reported as TCHGEO_ERR_INDEX by the stage).  The bound itself:
+      // the type's node count as far as the graph tells -- the columns of the relations it is the destination of (its
+      // seeds are checked against those by the hop kernels) and the largest source id of the relations that append to it.
+      bool k32 = true, fed = false, known = true, is_dst = false;
+      int64_t bound = 0;
+      for (int r = 0; r < pl.R; ++r) {
+        if (a->rel_active && !a->rel_active[r]) continue;
+        if (a->rel_src[r] == t) {
           fed = true;
           k32 = k32 && pl.rs.indices32[(size_t)r] != nullptr;
+          if (pl.rs.max_index[(size_t)r] < 0) known = false;
+          else bound = std::max(bound, pl.rs.max_index[(size_t)r] + 1);
         }
-      pl.key32[t] = (uint8_t)(k32 && fed);
+        if (a->rel_dst[r] == t) {
+          is_dst = true;
+          bound = std::max(bound, pl.rs.num_cols[(size_t)r]);
+        }
+      }
+      if (a->seeds_per_batch[t] > 0 && !is_dst) known = false;   // nothing checks those seeds
+      pl.id_bound[t] = !(k32 && fed) ? 0 : (known && bound > 0 && bound < 0xFFFFFFFFll ? bound : 0xFFFFFFFFll);
       if (pl.samples_cap[t] == 0) continue;
-      const size_t need = relabel_workspace_bytes(pl.B, pl.samples_cap[t], pl.key32[t] != 0);
+      const size_t need = relabel_workspace_bytes(pl.B, pl.samples_cap[t], pl.id_bound[t]);
       TCHGEO_REQUIRE(need > 0, "relabel: tree of node type %d too large", t);
       pl.relabel_bytes = std::max(pl.relabel_bytes, need);
-      pl.relabel_kernels += relabel_launches(pl.B, pl.samples_cap[t], pl.key32[t] != 0);
+      pl.relabel_kernels += relabel_launches(pl.B, pl.samples_cap[t], pl.id_bound[t]);
     }
     pl.total_bytes = pl.off_relabel + pl.relabel_bytes + 256;
   }
@@ -1541,7 +1584,7 @@ tchgeo_status enqueue_step(const tchgeo_sampling_args* a, const Plan& pl, uint64
       const int64_t cap = std::min(pl.samples_cap[t], a->samples_stride[t]);
       if (cap <= 0) continue;
       const tchgeo_status st = relabel_enqueue(a->samples[t], a->samples_stride[t], state + (size_t)pl.n_row_final[t] * B, B,
-                                               a->seeds_per_batch[t], cap, pl.key32[t] != 0, a->nodes[t], a->local[t],
+                                               a->seeds_per_batch[t], cap, pl.id_bound[t], a->nodes[t], a->local[t],
                                                state + (size_t)pl.nodes_row[t] * B, ws + pl.off_relabel, pl.relabel_bytes + 256,
                                                ctrl, stream);
       if (st != TCHGEO_OK) return st;
@@ -1846,7 +1889,7 @@ extern "C" tchgeo_status tchgeo_compress_indices(const int64_t* src, int64_t n, 
   TCHGEO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4, stream));
   int64_t grid = (n + 255) / 256;
   if (grid > 148 * 16) grid = 148 * 16;
-  compress_kernel<<<(unsigned)grid, 256, 0, stream>>>(src, n, dst, (uint32_t*)scratch);
+  compress_kernel<false><<<(unsigned)grid, 256, 0, stream>>>(src, n, dst, (uint32_t*)scratch);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
   uint32_t herr = 0;
   TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&herr, scratch, 4, cudaMemcpyDeviceToHost, stream));

@@ -750,24 +750,37 @@ cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* le
 
 // =================================================================================================
 // Bucketed form (default for ids < 2^32-1): no global hash table at all.
-// A tree's ids are split by a hash into NB buckets of ~3 k ids (pairs (id, position), counting sort: count, offsets,
-// scatter), and every bucket is resolved by ONE CTA in a SHARED-MEMORY hash table (8192 x 8 B; shared-memory atomics cost
-// a few cycles, against the ~50 G/s the L2 sustains for global atomicCAS, which is what held the persistent form at
-// 7 ms per step): per id the position its map entry points at ("winner": the last seed carrying the id, else the first
-// occurrence).  Positions are then walked once in order -- flags, block scan, decoupled look-back per tree, node list,
-// ranks -- and a last pass gives later occurrences the rank of their winner.  Everything is streaming traffic:
-//   count 8 B | scatter 8 + 8 B | resolve 8 + 4 B | compact 12 + ~26 B | lookup 4 + ~1 B      per id,
-// about 80 B against the 24 B of the byte model, all of it coalesced except the 4-byte winner scatter (merged in the L2).
-// A bucket with more distinct ids than its table holds (hash skew; ~2x headroom over the mean at the worst-case tree
-// size) raises TCHGEO_ERR_CAPACITY rather than a wrong answer; TCHGEO_RELABEL_PERSISTENT=1 selects the global-table form.
+// A tree's ids are split into NB buckets (pairs (id, position), counting sort: count, offsets, scatter), and every bucket
+// is resolved by ONE CTA in SHARED MEMORY (shared-memory atomics cost a few cycles, against the ~50 G/s the L2 sustains
+// for global atomicCAS, which is what held the persistent form at 7 ms per step): per id the position its map entry
+// points at ("winner": the last seed carrying the id, else the first occurrence).  Positions are then walked once in
+// order -- flags, block scan, decoupled look-back per tree, node list, local ids of the winners -- and a last pass gives
+// later occurrences the local id of their winner.  Two ways to bucket:
+//   * direct (the caller states an id bound, as the sampling plan does from the graph): bucket = id mod NB and the
+//     bucket's table is a DIRECT-ADDRESS array indexed by id / NB (<= 8192 slots x 4 B) -- one atomicMin per id, no keys,
+//     no probing, no capacity to overflow; when bits(bound / NB) + bits(n_max) <= 32 a pair is ONE 32-bit word
+//     (slot << pos_bits | position), which halves the scatter's writes and the resolve's reads;
+//   * hashed (bound unknown or beyond NB x 8192): bucket = hash(id), open addressing in a 4096 x (key, priority) table.
+//     A bucket with more distinct ids than its table holds (hash skew; ~2x headroom over the mean at the worst-case
+//     tree size) raises TCHGEO_ERR_CAPACITY rather than a wrong answer.
+// Everything is streaming traffic, per id:
+//   count 8 B | scatter 8 + 4 (8) B | resolve 4 (8) + 4 B | compact 4 + 8 + ~15 B | lookup 4 + ~2 B
+// about 60 B (packed) against the 24 B of the byte model (samples in, nodes + local out), all of it coalesced except the
+// 4-byte winner scatter (merged in the L2).  TCHGEO_RELABEL_DIRECT=0 forces the hashed tables,
+// TCHGEO_RELABEL_PERSISTENT=1 selects the global-table form.
 // =================================================================================================
 constexpr int BK_THREADS = 512;
 constexpr int BK_ITEMS = 8;
 constexpr int BK_TILE = BK_THREADS * BK_ITEMS;    // ids per CTA in the count / scatter kernels
+constexpr int BK_RTHREADS = 128;                  // resolve: threads per bucket (many short CTAs in flight)
 constexpr int BK_MAX_BUCKETS = 4096;              // shared-memory histogram
-constexpr int BK_TABLE = 4096;                    // slots of a bucket's shared-memory table (32 KB: 7 CTAs per SM)
+constexpr int BK_TABLE = 4096;                    // hashed: slots of a bucket's shared-memory table (32 KB: 7 CTAs per SM)
 constexpr int BK_TARGET = 1536;                   // ids per bucket the bucket count is chosen for (worst-case tree)
+constexpr int BK_DSLOTS = 8192;                   // direct: slots of a bucket's direct-address table (32 KB)
+constexpr int BKC_ITEMS = 8;                      // positions per thread in the compact / lookup kernels
+constexpr int BKC_TILE = RL_THREADS * BKC_ITEMS;
 constexpr uint32_t BK_NONE = 0xFFFFFFFFu;
+enum { BK_HASHED = 0, BK_DIRECT = 1, BK_PACKED = 2 };
 
 struct BkParams {
   const int64_t* samples;
@@ -778,15 +791,18 @@ struct BkParams {
   int64_t* nodes_len;
   int64_t num_seeds, n_max;
   int32_t num_trees, nb, log2_nb, tiles_per_tree;   // nb buckets per tree; tiles of BK_TILE (count/scatter) positions
+  uint32_t id_bound;   // ids are valid below this (hashed: 2^32-1)
+  int32_t pos_bits;    // packed pairs: slot << pos_bits | position
+  int32_t slots;       // direct: entries of a bucket's table = ceil(id_bound / nb)
   uint32_t* counts;    // [trees, nb] ids per bucket
   uint32_t* offs;      // [trees, nb] exclusive offsets inside the tree's pair region
-  uint32_t* cursor;    // [trees, nb] scatter cursors (zero)
-  uint2* pairs;        // [trees, n_max] (id, position) grouped by bucket
+  uint32_t* tile_hist; // [trees, tiles_per_tree, nb] ids of tile t in bucket j, then (bk_tilescan_kernel) the ids of the
+                       // bucket in earlier tiles: the scatter needs no atomic cursor
+  void* pairs;         // [trees, n_max] uint2 (id, position) or packed uint32, grouped by bucket
   uint32_t* win;       // [trees, n_max] position the map entry of samples[i] points at (BK_NONE: id out of range)
-  uint32_t* rank_of;   // [trees, n_max] rank of a first occurrence
   uint64_t* status;    // [trees, ctiles] look-back words of the compact kernel (zero)
   uint32_t* ticket;    // (zero)
-  int32_t ctiles;      // tiles of RL_TILE positions per tree
+  int32_t ctiles;      // tiles of BKC_TILE positions per tree
   uint32_t* err;
 };
 
@@ -795,31 +811,68 @@ __device__ __forceinline__ int64_t bk_len(const BkParams& p, int b) {
   if (n > p.n_max) n = p.n_max;
   return n < 0 ? 0 : n;
 }
+template <int MODE>
 __device__ __forceinline__ uint32_t bk_bucket(uint32_t key, int log2_nb) {
-  return log2_nb ? (key * 0x9E3779B1u) >> (32 - log2_nb) : 0u;
+  if (MODE == BK_HASHED) return log2_nb ? (key * 0x9E3779B1u) >> (32 - log2_nb) : 0u;
+  return key & ((1u << log2_nb) - 1u);
 }
 
-// ---- count: ids per (tree, bucket) ---------------------------------------------------------------------------------
+// ---- count: ids of every tile per bucket (a row of tile_hist) ---------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(BK_THREADS) bk_count_kernel(const BkParams p) {
   __shared__ uint32_t s_hist[BK_MAX_BUCKETS];
   const int b = blockIdx.y, tid = threadIdx.x;
   const int64_t n = bk_len(p, b);
   const int64_t i0 = (int64_t)blockIdx.x * BK_TILE;
-  if (i0 >= n) return;
+  if (i0 >= n) return;                              // bk_tilescan_kernel reads the rows of non-empty tiles only
   for (int j = tid; j < p.nb; j += BK_THREADS) s_hist[j] = 0u;
   __syncthreads();
   const int64_t* src = p.samples + (int64_t)b * p.stride;
+  int64_t k64[BK_ITEMS];
 #pragma unroll
   for (int u = 0; u < BK_ITEMS; ++u) {
     const int64_t i = i0 + u * BK_THREADS + tid;
-    if (i >= n) continue;
-    const int64_t k64 = __ldg(src + i);
-    if ((uint64_t)k64 >= 0xFFFFFFFFull) atomicOr(p.err, DEV_ERR_INDEX);
-    else atomicAdd(&s_hist[bk_bucket((uint32_t)k64, p.log2_nb)], 1u);
+    k64[u] = i < n ? __ldg(src + i) : 0;
   }
+  bool bad = false;
+#pragma unroll
+  for (int u = 0; u < BK_ITEMS; ++u) {
+    if (i0 + u * BK_THREADS + tid >= n) continue;
+    if ((uint64_t)k64[u] >= (uint64_t)p.id_bound) bad = true;
+    else atomicAdd(&s_hist[bk_bucket<MODE>((uint32_t)k64[u], p.log2_nb)], 1u);
+  }
+  if (bad) atomicOr(p.err, DEV_ERR_INDEX);
   __syncthreads();
-  for (int j = tid; j < p.nb; j += BK_THREADS)
-    if (s_hist[j]) atomicAdd(p.counts + (size_t)b * p.nb + j, s_hist[j]);
+  uint32_t* row = p.tile_hist + ((size_t)b * p.tiles_per_tree + blockIdx.x) * p.nb;
+  for (int j = tid; j < p.nb; j += BK_THREADS) row[j] = s_hist[j];
+}
+
+// ---- tile scan: per (tree, bucket) the exclusive prefix over the tree's tiles, and the bucket's total ------------------
+__global__ void __launch_bounds__(256) bk_tilescan_kernel(const BkParams p) {
+  const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= p.nb) return;
+  const int64_t n = bk_len(p, b);
+  const int nt = (int)((n + BK_TILE - 1) / BK_TILE);
+  uint32_t* col = p.tile_hist + (size_t)b * p.tiles_per_tree * p.nb + j;
+  uint32_t run = 0u;
+  int t = 0;
+  constexpr int V = 8;
+  for (; t + V <= nt; t += V) {
+    uint32_t c[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) c[v] = __ldcg(col + (size_t)(t + v) * p.nb);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      col[(size_t)(t + v) * p.nb] = run;
+      run += c[v];
+    }
+  }
+  for (; t < nt; ++t) {
+    const uint32_t c = __ldcg(col + (size_t)t * p.nb);
+    col[(size_t)t * p.nb] = run;
+    run += c;
+  }
+  p.counts[(size_t)b * p.nb + j] = run;
 }
 
 // ---- offsets: exclusive scan of every tree's bucket counts (one CTA per tree; nb <= 4096) ----------------------------
@@ -853,8 +906,9 @@ __global__ void __launch_bounds__(256) bk_offsets_kernel(const BkParams p) {
 }
 
 // ---- scatter: (id, position) pairs grouped by bucket ---------------------------------------------------------------
+template <int MODE>
 __global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p) {
-  __shared__ uint32_t s_hist[BK_MAX_BUCKETS];   // per-bucket count of the tile, then the tile's base in the bucket
+  __shared__ uint32_t s_hist[BK_MAX_BUCKETS];   // rank counters of the tile, then the tile's base in every bucket
   const int b = blockIdx.y, tid = threadIdx.x;
   const int64_t n = bk_len(p, b);
   const int64_t i0 = (int64_t)blockIdx.x * BK_TILE;
@@ -864,37 +918,209 @@ __global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p
   const int64_t* src = p.samples + (int64_t)b * p.stride;
   uint32_t key[BK_ITEMS], rnk[BK_ITEMS];
   bool ok[BK_ITEMS];
+  int64_t k64[BK_ITEMS];
+#pragma unroll
+  for (int u = 0; u < BK_ITEMS; ++u) {
+    const int64_t i = i0 + u * BK_THREADS + tid;
+    k64[u] = i < n ? __ldg(src + i) : 0;
+  }
 #pragma unroll
   for (int u = 0; u < BK_ITEMS; ++u) {
     const int64_t i = i0 + u * BK_THREADS + tid;
     ok[u] = false;
     key[u] = 0u; rnk[u] = 0u;
     if (i >= n) continue;
-    const int64_t k64 = __ldg(src + i);
-    if ((uint64_t)k64 >= 0xFFFFFFFFull) {
+    if ((uint64_t)k64[u] >= (uint64_t)p.id_bound) {
       p.win[(size_t)b * p.n_max + i] = BK_NONE;   // reported by the count kernel
       continue;
     }
-    ok[u] = true;
-    key[u] = (uint32_t)k64;
-    rnk[u] = atomicAdd(&s_hist[bk_bucket(key[u], p.log2_nb)], 1u);   // rank inside the tile's share of the bucket
+    p.win[(size_t)b * p.n_max + i] = (uint32_t)i;  // "its own winner" until bk_resolve says otherwise (coalesced here,
+    ok[u] = true;                                  // so that the resolve kernel scatters the exceptions only)
+    key[u] = (uint32_t)k64[u];
+    rnk[u] = atomicAdd(&s_hist[bk_bucket<MODE>(key[u], p.log2_nb)], 1u);   // rank inside the tile's share of the bucket
   }
   __syncthreads();
-  for (int j = tid; j < p.nb; j += BK_THREADS) {
-    const uint32_t c = s_hist[j];
-    s_hist[j] = p.offs[(size_t)b * p.nb + j] + (c ? atomicAdd(p.cursor + (size_t)b * p.nb + j, c) : 0u);
-  }
+  const uint32_t* row = p.tile_hist + ((size_t)b * p.tiles_per_tree + blockIdx.x) * p.nb;
+  for (int j = tid; j < p.nb; j += BK_THREADS) s_hist[j] = p.offs[(size_t)b * p.nb + j] + row[j];
   __syncthreads();
-  uint2* dst = p.pairs + (size_t)b * p.n_max;
 #pragma unroll
   for (int u = 0; u < BK_ITEMS; ++u) {
     if (!ok[u]) continue;
-    const int64_t i = i0 + u * BK_THREADS + tid;
-    dst[s_hist[bk_bucket(key[u], p.log2_nb)] + rnk[u]] = make_uint2(key[u], (uint32_t)i);
+    const uint32_t i = (uint32_t)(i0 + u * BK_THREADS + tid);
+    const size_t at = (size_t)b * p.n_max + s_hist[bk_bucket<MODE>(key[u], p.log2_nb)] + rnk[u];
+    if (MODE == BK_PACKED) reinterpret_cast<uint32_t*>(p.pairs)[at] = ((key[u] >> p.log2_nb) << p.pos_bits) | i;
+    else reinterpret_cast<uint2*>(p.pairs)[at] = make_uint2(key[u], i);
   }
 }
 
-// ---- resolve: one CTA per (tree, bucket); the bucket's ids in a shared-memory table ----------------------------------
+// ---- scatter, packed pairs: the tile is first grouped by bucket in shared memory, then written out in that order --------
+// A warp's store then covers a few runs of consecutive words instead of 32 different sectors.  The kernel is a chain of
+// phases (ids, ranks, scan, staging, stores) separated by barriers, so what matters is how many CTAs an SM holds to
+// overlap them: 512 threads and <= 40 registers give three (the first version, 1024 threads x 61 registers, ran ONE CTA
+// per SM and was no faster than the unstaged scatter).
+__global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter_staged_kernel(const BkParams p) {
+  extern __shared__ __align__(16) uint32_t s_mem[];
+  uint32_t* s_start = s_mem;                       // [nb] rank counters, then the bucket's first slot in the staged tile
+  uint32_t* s_base = s_mem + p.nb;                 // [nb] bucket's global base minus its first staged slot
+  uint32_t* s_stage = s_mem + 2 * p.nb;            // [BK_TILE] packed pairs grouped by bucket
+  uint16_t* s_bkt = reinterpret_cast<uint16_t*>(s_stage + BK_TILE);   // [BK_TILE] bucket of every staged pair
+  __shared__ uint32_t s_wsum[32];
+  __shared__ uint32_t s_total;
+  const int b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t n = bk_len(p, b);
+  const int64_t i0 = (int64_t)blockIdx.x * BK_TILE;
+  if (i0 >= n) return;
+  const uint32_t* row = p.tile_hist + ((size_t)b * p.tiles_per_tree + blockIdx.x) * p.nb;
+  const uint32_t* offs = p.offs + (size_t)b * p.nb;
+  for (int j = tid; j < p.nb; j += BK_THREADS) {
+    s_start[j] = 0u;
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(row + j));   // wanted after the scan, two barriers from here
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(offs + j));
+  }
+  if (tid < 32) s_wsum[tid] = 0u;
+  __syncthreads();
+  const int64_t* src = p.samples + (int64_t)b * p.stride;
+  uint32_t* win = p.win + (size_t)b * p.n_max;
+  const uint32_t bmask = (1u << p.log2_nb) - 1u;
+  uint32_t word[BK_ITEMS], rb[BK_ITEMS];           // rb = bucket << 16 | rank in the tile's share of it; ~0 = not staged
+  {
+    int64_t k64[BK_ITEMS];
+#pragma unroll
+    for (int u = 0; u < BK_ITEMS; ++u) {
+      const int64_t i = i0 + u * BK_THREADS + tid;
+      k64[u] = i < n ? __ldg(src + i) : -1;
+    }
+#pragma unroll
+    for (int u = 0; u < BK_ITEMS; ++u) {
+      const int64_t i = i0 + u * BK_THREADS + tid;
+      rb[u] = BK_NONE; word[u] = 0u;
+      if (i >= n) continue;
+      if ((uint64_t)k64[u] >= (uint64_t)p.id_bound) {
+        win[i] = BK_NONE;                          // reported by the count kernel
+        continue;
+      }
+      win[i] = (uint32_t)i;                        // "its own winner" until bk_resolve says otherwise
+      const uint32_t key = (uint32_t)k64[u];
+      const uint32_t bkt = key & bmask;
+      word[u] = ((key >> p.log2_nb) << p.pos_bits) | (uint32_t)i;
+      rb[u] = (bkt << 16) | atomicAdd(&s_start[bkt], 1u);
+    }
+  }
+  __syncthreads();
+  // exclusive scan of the tile's bucket counts: thread tid owns buckets [tid * per, tid * per + per)
+  const int per = (p.nb + BK_THREADS - 1) / BK_THREADS;
+  uint32_t sum = 0u;
+  for (int v = 0; v < per; ++v) {
+    const int j = tid * per + v;
+    if (j < p.nb) sum += s_start[j];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t up = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += up;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = s_wsum[lane];
+    uint32_t wi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t up = __shfl_up_sync(0xffffffffu, wi, o);
+      if (lane >= o) wi += up;
+    }
+    s_wsum[lane] = wi - v;
+    if (lane == 31) s_total = wi;
+  }
+  __syncthreads();
+  uint32_t excl = s_wsum[warp] + incl - sum;
+  for (int v = 0; v < per; ++v) {
+    const int j = tid * per + v;
+    if (j >= p.nb) break;
+    const uint32_t c = s_start[j];
+    s_start[j] = excl;
+    s_base[j] = __ldcg(offs + j) + __ldcg(row + j) - excl;
+    excl += c;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < BK_ITEMS; ++u) {
+    if (rb[u] == BK_NONE) continue;
+    const uint32_t bkt = rb[u] >> 16;
+    const uint32_t k = s_start[bkt] + (rb[u] & 0xFFFFu);
+    s_stage[k] = word[u];
+    s_bkt[k] = (uint16_t)bkt;
+  }
+  __syncthreads();
+  uint32_t* dst = reinterpret_cast<uint32_t*>(p.pairs) + (size_t)b * p.n_max;
+  const uint32_t total = s_total;
+  for (uint32_t k = tid; k < total; k += BK_THREADS) dst[s_base[s_bkt[k]] + k] = s_stage[k];
+}
+
+// ---- resolve (direct): one CTA per (tree, bucket); min priority per id in a direct-address shared-memory array -------
+// The CTAs are short (a few hundred pairs) and bound by their chain of latencies -- counts, offsets, pairs, atomics,
+// stores -- so they are small (128 threads: twice as many in flight per SM) and issue the pair loads before they clear
+// the table.
+template <bool PACKED>
+__global__ void __launch_bounds__(BK_RTHREADS) bk_resolve_direct_kernel(const BkParams p) {
+  extern __shared__ __align__(16) uint32_t s_prio[];   // [slots]
+  const int j = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const uint32_t cnt = p.counts[(size_t)b * p.nb + j];
+  if (cnt == 0) return;
+  const size_t base = (size_t)b * p.n_max + p.offs[(size_t)b * p.nb + j];
+  const uint32_t* pr1 = reinterpret_cast<const uint32_t*>(p.pairs) + base;
+  const uint2* pr2 = reinterpret_cast<const uint2*>(p.pairs) + base;
+  const uint32_t S = (uint32_t)p.num_seeds;
+  const uint32_t pos_mask = PACKED ? (1u << p.pos_bits) - 1u : 0u;
+  uint32_t* win = p.win + (size_t)b * p.n_max;
+  constexpr int U = 8;
+  uint32_t slot[U], pos[U];
+  auto load = [&](uint32_t q0) {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const uint32_t q = q0 + u * BK_RTHREADS + tid;
+      pos[u] = BK_NONE; slot[u] = 0u;
+      if (q >= cnt) continue;
+      if (PACKED) {
+        const uint32_t w = __ldcs(pr1 + q);
+        slot[u] = w >> p.pos_bits; pos[u] = w & pos_mask;
+      } else {
+        const uint2 e = __ldcs(pr2 + q);
+        slot[u] = e.x >> p.log2_nb; pos[u] = e.y;
+      }
+    }
+  };
+  auto vote = [&]() {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (pos[u] != BK_NONE) atomicMin(&s_prio[slot[u]], pos[u] < S ? S - 1u - pos[u] : pos[u]);   // smallest priority wins
+  };
+  auto emit = [&]() {
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (pos[u] == BK_NONE) continue;
+      const uint32_t prio = s_prio[slot[u]];
+      const uint32_t w = prio < S ? S - 1u - prio : prio;   // the last seed carrying the id (:26), else its first occurrence
+      if (w != pos[u]) win[pos[u]] = w;                     // (the scatter kernel wrote win[i] = i)
+    }
+  };
+  load(0u);
+  for (int q = tid; q < p.slots; q += BK_RTHREADS) s_prio[q] = BK_NONE;
+  __syncthreads();
+  if (cnt <= (uint32_t)BK_RTHREADS * U) {   // the usual case: the bucket's pairs stay in registers between the two phases
+    vote();
+    __syncthreads();
+    emit();
+    return;
+  }
+  vote();
+  for (uint32_t q0 = BK_RTHREADS * U; q0 < cnt; q0 += BK_RTHREADS * U) { load(q0); vote(); }
+  __syncthreads();
+  for (uint32_t q0 = 0; q0 < cnt; q0 += BK_RTHREADS * U) { load(q0); emit(); }   // second read of the bucket: an L2 hit
+}
+
+// ---- resolve (hashed): one CTA per (tree, bucket); the bucket's ids in a shared-memory hash table -------------------
 __global__ void __launch_bounds__(256) bk_resolve_kernel(const BkParams p) {
   // keys and priorities in two 32-bit arrays: native shared-memory atomicCAS / atomicMin (a 64-bit (key | priority) word
   // needs 64-bit shared atomics, which cost several times more; with those, halving the table to raise the load factor
@@ -908,7 +1134,7 @@ __global__ void __launch_bounds__(256) bk_resolve_kernel(const BkParams p) {
   for (int q = tid; q < BK_TABLE / 2; q += 256) reinterpret_cast<uint4*>(s_keys)[q] = make_uint4(~0u, ~0u, ~0u, ~0u);
   if (tid == 0) s_distinct = 0u;
   __syncthreads();
-  const uint2* pr = p.pairs + (size_t)b * p.n_max + p.offs[(size_t)b * p.nb + j];
+  const uint2* pr = reinterpret_cast<const uint2*>(p.pairs) + (size_t)b * p.n_max + p.offs[(size_t)b * p.nb + j];
   const uint32_t S = (uint32_t)p.num_seeds;
   constexpr uint32_t MASK = BK_TABLE - 1, LIMIT = BK_TABLE - BK_TABLE / 8;
   constexpr int U = 8;   // pairs per thread in flight: the kernel is otherwise bound by one DRAM latency per pair
@@ -957,12 +1183,13 @@ __global__ void __launch_bounds__(256) bk_resolve_kernel(const BkParams p) {
       const uint32_t step = ((e[u].x * 0xC2B2AE35u) >> 9) | 1u;
       while (s_keys[h] != e[u].x) h = (h + step) & MASK;
       const uint32_t prio = s_prio[h];
-      win[e[u].y] = prio < S ? S - 1u - prio : prio;   // the last seed carrying the id (:26), else its first occurrence
+      const uint32_t w = prio < S ? S - 1u - prio : prio;   // the last seed carrying the id (:26), else its first occurrence
+      if (w != e[u].y) win[e[u].y] = w;                     // (the scatter kernel wrote win[i] = i)
     }
   }
 }
 
-// ---- compact: flags, scan in position order (decoupled look-back per tree), node list, ranks, local ids --------------
+// ---- compact: flags, scan in position order (decoupled look-back per tree), node list, local ids of the winners ------
 __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p) {
   __shared__ uint32_t s_tile;
   __shared__ int64_t s_excl;
@@ -974,24 +1201,25 @@ __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p
   __syncthreads();
   const int t = (int)(s_tile / (uint32_t)p.num_trees), b = (int)(s_tile - (uint32_t)t * (uint32_t)p.num_trees);
   const int64_t n = bk_len(p, b);
-  const int64_t i0 = (int64_t)t * RL_TILE;
+  const int64_t i0 = (int64_t)t * BKC_TILE;
   if (i0 >= n && t > 0) return;
   const int64_t* src = p.samples + (int64_t)b * p.stride;
   const uint32_t* win = p.win + (size_t)b * p.n_max;
-  uint32_t* rank_of = p.rank_of + (size_t)b * p.n_max;
   int64_t* local = p.local + (int64_t)b * p.stride;
   const int64_t S = p.num_seeds;
   // position of (u, tid) = i0 + u * RL_THREADS + tid: consecutive threads touch consecutive positions in every load and
-  // store (a thread owning 4 consecutive positions made every 8-byte store instruction hit 32 different sectors)
-  uint32_t w[RL_ITEMS];
-  uint32_t node = 0;
+  // store (a thread owning consecutive positions made every 8-byte store instruction hit 32 different sectors)
+  uint32_t w[BKC_ITEMS];
+  int64_t id[BKC_ITEMS];    // loaded up front (nearly every position of a sampled tree is a first occurrence): the node
+  uint32_t node = 0;        // stores at the end of the kernel then wait for nothing
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) {
+  for (int u = 0; u < BKC_ITEMS; ++u) {
     const int64_t i = i0 + u * RL_THREADS + tid;
-    w[u] = i < n ? win[i] : BK_NONE;
+    w[u] = i < n ? __ldcs(win + i) : BK_NONE;
+    id[u] = i < n ? __ldcs(src + i) : 0;
   }
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) {
+  for (int u = 0; u < BKC_ITEMS; ++u) {
     const int64_t i = i0 + u * RL_THREADS + tid;
     if (i >= n) continue;
     if (i < S) {                                   // every seed is kept (:25) and maps to the last seed with its id (:26)
@@ -1006,19 +1234,19 @@ __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p
     }                                               // else: a later occurrence, bk_lookup_kernel
   }
   // exclusive rank of (u, tid) in position order = nodes of rows u' < u  +  nodes of row u in earlier warps / lanes
-  __shared__ uint32_t s_cnt[RL_ITEMS][RL_THREADS / 32];
-  uint32_t lane_excl[RL_ITEMS];
+  __shared__ uint32_t s_cnt[BKC_ITEMS][RL_THREADS / 32];
+  uint32_t lane_excl[BKC_ITEMS];
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) {
+  for (int u = 0; u < BKC_ITEMS; ++u) {
     const uint32_t m = __ballot_sync(0xffffffffu, (node >> u) & 1u);
     lane_excl[u] = __popc(m & ((1u << lane) - 1u));
     if (lane == 0) s_cnt[u][warp] = __popc(m);
   }
   __syncthreads();
-  uint32_t excl_u[RL_ITEMS];
+  uint32_t excl_u[BKC_ITEMS];
   uint32_t total = 0;
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) {
+  for (int u = 0; u < BKC_ITEMS; ++u) {
     excl_u[u] = total + lane_excl[u];
 #pragma unroll
     for (int k = 0; k < RL_THREADS / 32; ++k) {
@@ -1063,71 +1291,106 @@ __global__ void __launch_bounds__(RL_THREADS) bk_compact_kernel(const BkParams p
   }
   __syncthreads();
   const int64_t tile_excl = s_excl;
-  if (tid == 0 && i0 + RL_TILE >= n) p.nodes_len[b] = tile_excl + total;
+  if (tid == 0 && i0 + BKC_TILE >= n) p.nodes_len[b] = tile_excl + total;
   int64_t* nodes = p.nodes + (int64_t)b * p.stride;
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) {
+  for (int u = 0; u < BKC_ITEMS; ++u) {
     if (!((node >> u) & 1u)) continue;
     const int64_t i = i0 + u * RL_THREADS + tid;
     const uint32_t r = (uint32_t)tile_excl + excl_u[u];
-    st_cs_i64(nodes + r, __ldg(src + i));
-    if (i >= S) {
-      st_cs_i64(local + i, (int64_t)r);
-      rank_of[i] = r;
-    }
+    st_cs_i64(nodes + r, id[u]);
+    if (i >= S) local[i] = (int64_t)r;            // (a plain store: bk_lookup_kernel reads it back for the later occurrences)
   }
 }
 
-// ---- lookup: later occurrences of a non-seed id take the rank of its first occurrence -------------------------------
+// ---- lookup: later occurrences of a non-seed id take the local id of its first occurrence ----------------------------
 __global__ void __launch_bounds__(RL_THREADS) bk_lookup_kernel(const BkParams p) {
   const int b = blockIdx.y;
   const int64_t n = bk_len(p, b);
-  const int64_t i0 = (int64_t)blockIdx.x * RL_TILE;
+  const int64_t i0 = (int64_t)blockIdx.x * BKC_TILE;
   if (i0 >= n) return;
   const uint32_t* win = p.win + (size_t)b * p.n_max;
-  const uint32_t* rank_of = p.rank_of + (size_t)b * p.n_max;
   int64_t* local = p.local + (int64_t)b * p.stride;
   const uint32_t S = (uint32_t)p.num_seeds;
-  uint32_t w[RL_ITEMS];
+  uint32_t w[BKC_ITEMS];
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) {
+  for (int u = 0; u < BKC_ITEMS; ++u) {
     const int64_t i = i0 + u * RL_THREADS + threadIdx.x;
-    w[u] = (i < n && i >= (int64_t)S) ? win[i] : BK_NONE;
+    w[u] = (i < n && i >= (int64_t)S) ? __ldcs(win + i) : BK_NONE;
+  }
+  // local[w] of a first occurrence w was written by bk_compact_kernel and is never written here; all gathers are issued
+  // before the first store (reads and writes of the same array: the compiler would otherwise order them pair by pair)
+  int64_t r[BKC_ITEMS];
+  uint32_t later = 0u;
+#pragma unroll
+  for (int u = 0; u < BKC_ITEMS; ++u) {
+    const int64_t i = i0 + u * RL_THREADS + threadIdx.x;
+    r[u] = 0;
+    if (w[u] != BK_NONE && w[u] >= S && w[u] != (uint32_t)i) {
+      later |= 1u << u;
+      r[u] = __ldcg(local + w[u]);
+    }
   }
 #pragma unroll
-  for (int u = 0; u < RL_ITEMS; ++u) {
-    const int64_t i = i0 + u * RL_THREADS + threadIdx.x;
-    if (w[u] != BK_NONE && w[u] >= S && w[u] != (uint32_t)i) st_cs_i64(local + i, (int64_t)rank_of[w[u]]);
-  }
+  for (int u = 0; u < BKC_ITEMS; ++u)
+    if ((later >> u) & 1u) st_cs_i64(local + i0 + u * RL_THREADS + threadIdx.x, r[u]);
 }
 
 struct BkLayout {
   int nb, log2_nb, tiles_per_tree, ctiles;
-  size_t off_zero, zero_bytes;   // counts | cursor | status | ticket: one memset
-  size_t off_counts, off_cursor, off_status, off_ticket, off_offs, off_pairs, off_win, off_rank, total;
+  int mode, pos_bits, slots;
+  uint32_t id_bound;
+  size_t off_zero, zero_bytes;   // status | ticket: one memset
+  size_t off_counts, off_status, off_ticket, off_offs, off_tile_hist, off_pairs, off_win, total;
 };
 
-bool bk_layout(int64_t num_trees, int64_t n_max, BkLayout& L) {
+inline int bk_bits(uint64_t n) {   // bits needed for values in [0, n)
+  int b = 0;
+  while (b < 63 && (1ull << b) < n) ++b;
+  return b;
+}
+
+// id_bound: every valid id is below it (1 .. 2^32-1)
+bool bk_layout(int64_t num_trees, int64_t n_max, int64_t id_bound, BkLayout& L) {
   if (num_trees <= 0 || num_trees > 65535 || n_max < 0 || n_max >= ((int64_t)1 << 31)) return false;
+  if (id_bound <= 0 || id_bound > 0xFFFFFFFFll) return false;
   int nb = 1, lg = 0;
   while ((int64_t)nb * BK_TARGET < n_max) { nb <<= 1; ++lg; }
-  if (nb > BK_MAX_BUCKETS) return false;        // trees beyond ~12 M ids: the global-table form
+  if (nb > BK_MAX_BUCKETS) return false;        // trees beyond ~6 M ids: the global-table form
+  L.mode = BK_HASHED; L.pos_bits = 0; L.slots = 0; L.id_bound = 0xFFFFFFFFu;
+  const char* de = getenv("TCHGEO_RELABEL_DIRECT");
+  if (id_bound < 0xFFFFFFFFll && !(de && atoi(de) == 0)) {
+    auto slots_for = [&](int l) { return (int64_t)(((uint64_t)id_bound - 1) >> l) + 1; };
+    int nbd = nb, lgd = lg;
+    while (nbd <= BK_MAX_BUCKETS && slots_for(lgd) > BK_DSLOTS) { nbd <<= 1; ++lgd; }
+    if (nbd <= BK_MAX_BUCKETS) {
+      L.mode = BK_DIRECT; L.id_bound = (uint32_t)id_bound;
+      const int pos_bits = bk_bits((uint64_t)std::max<int64_t>(n_max, 1));
+      int nbp = nbd, lgp = lgd;   // a few more (smaller) buckets if that makes a pair fit one word
+      while (nbp <= BK_MAX_BUCKETS && nbp <= 4 * nbd && bk_bits((uint64_t)slots_for(lgp)) + pos_bits > 32) { nbp <<= 1; ++lgp; }
+      if (nbp <= BK_MAX_BUCKETS && nbp <= 4 * nbd && bk_bits((uint64_t)slots_for(lgp)) + pos_bits <= 32) {
+        L.mode = BK_PACKED; L.pos_bits = pos_bits;
+        nbd = nbp; lgd = lgp;
+      }
+      nb = nbd; lg = lgd;
+      L.slots = (int)slots_for(lg);
+    }
+  }
   L.nb = nb; L.log2_nb = lg;
   L.tiles_per_tree = (int)std::max<int64_t>(1, (n_max + BK_TILE - 1) / BK_TILE);
-  L.ctiles = (int)std::max<int64_t>(1, (n_max + RL_TILE - 1) / RL_TILE);
+  L.ctiles = (int)std::max<int64_t>(1, (n_max + BKC_TILE - 1) / BKC_TILE);
   if ((int64_t)L.ctiles * num_trees >= ((int64_t)1 << 31)) return false;
   const size_t tb = (size_t)num_trees * nb * 4, nn = (size_t)num_trees * (size_t)std::max<int64_t>(n_max, 1);
   size_t o = 0;
   L.off_zero = o;
-  L.off_counts = o; o += rl_align(tb);
-  L.off_cursor = o; o += rl_align(tb);
   L.off_status = o; o += rl_align((size_t)num_trees * L.ctiles * 8);
   L.off_ticket = o; o += 256;
   L.zero_bytes = o - L.off_zero;
+  L.off_counts = o; o += rl_align(tb);
   L.off_offs = o; o += rl_align(tb);
+  L.off_tile_hist = o; o += rl_align((size_t)num_trees * L.tiles_per_tree * (size_t)nb * 4);   // depends on the bound
   L.off_pairs = o; o += rl_align(nn * 8);
   L.off_win = o; o += rl_align(nn * 4);
-  L.off_rank = o; o += rl_align(nn * 4);
   L.total = o + 256;
   return true;
 }
@@ -1139,20 +1402,44 @@ tchgeo_status bk_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
   p.samples = samples; p.stride = stride; p.lens = lens; p.nodes = nodes; p.local = local; p.nodes_len = nodes_len;
   p.num_seeds = num_seeds; p.n_max = n_max; p.num_trees = (int32_t)num_trees;
   p.nb = L.nb; p.log2_nb = L.log2_nb; p.tiles_per_tree = L.tiles_per_tree; p.ctiles = L.ctiles;
-  p.counts = (uint32_t*)(ws + L.off_counts); p.cursor = (uint32_t*)(ws + L.off_cursor);
-  p.offs = (uint32_t*)(ws + L.off_offs); p.pairs = (uint2*)(ws + L.off_pairs);
-  p.win = (uint32_t*)(ws + L.off_win); p.rank_of = (uint32_t*)(ws + L.off_rank);
+  p.id_bound = L.id_bound; p.pos_bits = L.pos_bits; p.slots = L.slots;
+  p.counts = (uint32_t*)(ws + L.off_counts); p.tile_hist = (uint32_t*)(ws + L.off_tile_hist);
+  p.offs = (uint32_t*)(ws + L.off_offs); p.pairs = (void*)(ws + L.off_pairs);
+  p.win = (uint32_t*)(ws + L.off_win);
   p.status = (uint64_t*)(ws + L.off_status); p.ticket = (uint32_t*)(ws + L.off_ticket);
   p.err = err;
   TCHGEO_CUDA_CHECK(cudaMemsetAsync(ws + L.off_zero, 0, L.zero_bytes, stream));
   const dim3 tiles((unsigned)L.tiles_per_tree, (unsigned)num_trees);
-  bk_count_kernel<<<tiles, BK_THREADS, 0, stream>>>(p);
+  switch (L.mode) {
+    case BK_PACKED: bk_count_kernel<BK_PACKED><<<tiles, BK_THREADS, 0, stream>>>(p); break;
+    case BK_DIRECT: bk_count_kernel<BK_DIRECT><<<tiles, BK_THREADS, 0, stream>>>(p); break;
+    default: bk_count_kernel<BK_HASHED><<<tiles, BK_THREADS, 0, stream>>>(p); break;
+  }
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  bk_tilescan_kernel<<<dim3((unsigned)((L.nb + 255) / 256), (unsigned)num_trees), 256, 0, stream>>>(p);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
   bk_offsets_kernel<<<(unsigned)num_trees, 256, 0, stream>>>(p);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
-  bk_scatter_kernel<<<tiles, BK_THREADS, 0, stream>>>(p);
+  switch (L.mode) {
+    case BK_PACKED: {
+      const size_t smem = (size_t)(2 * L.nb + BK_TILE) * 4 + (size_t)BK_TILE * 2;
+      static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
+      int dev = 0;
+      TCHGEO_CUDA_CHECK(cudaGetDevice(&dev));
+      if (dev < 0 || dev >= 64 || !configured[dev]) {
+        TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(bk_scatter_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                               (2 * BK_MAX_BUCKETS + BK_TILE) * 4 + BK_TILE * 2));
+        if (dev >= 0 && dev < 64) configured[dev] = true;
+      }
+      bk_scatter_staged_kernel<<<tiles, BK_THREADS, smem, stream>>>(p);
+      break;
+    }
+    case BK_DIRECT: bk_scatter_kernel<BK_DIRECT><<<tiles, BK_THREADS, 0, stream>>>(p); break;
+    default: bk_scatter_kernel<BK_HASHED><<<tiles, BK_THREADS, 0, stream>>>(p); break;
+  }
   TCHGEO_CUDA_CHECK(cudaGetLastError());
-  {
+  const dim3 buckets((unsigned)L.nb, (unsigned)num_trees);
+  if (L.mode == BK_HASHED) {
     static bool configured[64] = {};  // per device; benign race: the attribute is idempotent
     int dev = 0;
     TCHGEO_CUDA_CHECK(cudaGetDevice(&dev));
@@ -1160,8 +1447,12 @@ tchgeo_status bk_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
       TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(bk_resolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BK_TABLE * 8));
       if (dev >= 0 && dev < 64) configured[dev] = true;
     }
+    bk_resolve_kernel<<<buckets, 256, BK_TABLE * 8, stream>>>(p);
+  } else if (L.mode == BK_PACKED) {
+    bk_resolve_direct_kernel<true><<<buckets, BK_RTHREADS, (size_t)L.slots * 4, stream>>>(p);
+  } else {
+    bk_resolve_direct_kernel<false><<<buckets, BK_RTHREADS, (size_t)L.slots * 4, stream>>>(p);
   }
-  bk_resolve_kernel<<<dim3((unsigned)L.nb, (unsigned)num_trees), 256, BK_TABLE * 8, stream>>>(p);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
   bk_compact_kernel<<<(unsigned)L.ctiles * (unsigned)num_trees, RL_THREADS, 0, stream>>>(p);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
@@ -1251,26 +1542,30 @@ tchgeo_status rl_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
 }  // namespace
 
 // used by the sampling plan (neighbor_sampling.cu): size and enqueue the stage for one node type.
-//   ids < 2^32-1 (k32): the bucketed form (shared-memory tables); TCHGEO_RELABEL_PERSISTENT=1 selects the persistent
-//   global-table form instead (also the fallback for trees beyond ~12 M ids), TCHGEO_RELABEL_WAVES=1 the wave form;
-//   any i64 id: the wave form with 64-bit keys.
+//   id_bound = 0: any non-negative i64 id -- the wave form with 64-bit keys;
+//   0 < id_bound <= 2^32-1: every id is below id_bound (an id outside raises TCHGEO_ERR_INDEX) -- the bucketed form
+//   (direct-address shared-memory tables when the bound allows, hashed ones otherwise); TCHGEO_RELABEL_PERSISTENT=1
+//   selects the persistent global-table form instead (also the fallback for trees beyond ~6 M ids),
+//   TCHGEO_RELABEL_WAVES=1 the wave form.
 enum { FORM_WAVES = 0, FORM_PERSISTENT = 1, FORM_BUCKETED = 2 };
-static int relabel_form(int64_t num_trees, int64_t n_max, bool k32) {
+static int relabel_form(int64_t num_trees, int64_t n_max, int64_t id_bound) {
   const char* w = getenv("TCHGEO_RELABEL_WAVES");
-  if (!k32 || (w && atoi(w) != 0)) return FORM_WAVES;
+  if (id_bound <= 0 || (w && atoi(w) != 0)) return FORM_WAVES;
   const char* pe = getenv("TCHGEO_RELABEL_PERSISTENT");
   BkLayout B;
-  if (!(pe && atoi(pe) != 0) && bk_layout(num_trees, n_max, B)) return FORM_BUCKETED;
+  if (!(pe && atoi(pe) != 0) && bk_layout(num_trees, n_max, id_bound, B)) return FORM_BUCKETED;
   RpLayout P;
   return rp_layout(num_trees, n_max, P) ? FORM_PERSISTENT : FORM_WAVES;
 }
-size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, bool k32) {
+size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound) {
+  if (id_bound < 0 || id_bound > 0xFFFFFFFFll) return 0;
+  const bool k32 = id_bound != 0;
   RlLayout L;
   if (!rl_layout(num_trees, n_max, k32, L)) return 0;
-  const int form = relabel_form(num_trees, n_max, k32);
+  const int form = relabel_form(num_trees, n_max, id_bound);
   if (form == FORM_BUCKETED) {
     BkLayout B;
-    bk_layout(num_trees, n_max, B);
+    bk_layout(num_trees, n_max, id_bound, B);
     return B.total;
   }
   if (form == FORM_PERSISTENT) {
@@ -1280,25 +1575,27 @@ size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, bool k32) {
   }
   return L.total;
 }
-int relabel_launches(int64_t num_trees, int64_t n_max, bool k32) {
-  const int form = relabel_form(num_trees, n_max, k32);
-  if (form == FORM_BUCKETED) return 6;
+int relabel_launches(int64_t num_trees, int64_t n_max, int64_t id_bound) {
+  const int form = relabel_form(num_trees, n_max, id_bound);
+  if (form == FORM_BUCKETED) return 7;
   if (form == FORM_PERSISTENT) return 1;
   RlLayout L;
-  return rl_layout(num_trees, n_max, k32, L) ? 3 * L.num_waves : 0;
+  return rl_layout(num_trees, n_max, id_bound != 0, L) ? 3 * L.num_waves : 0;
 }
 tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
-                              int64_t num_seeds, int64_t n_max, bool k32, int64_t* nodes, int64_t* local,
+                              int64_t num_seeds, int64_t n_max, int64_t id_bound, int64_t* nodes, int64_t* local,
                               int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
                               cudaStream_t stream) {
+  TCHGEO_REQUIRE(id_bound >= 0 && id_bound <= 0xFFFFFFFFll, "relabel: id_bound must be 0 (any i64) or at most 2^32-1");
+  const bool k32 = id_bound != 0;
   RlLayout L;
   TCHGEO_REQUIRE(rl_layout(num_trees, n_max, k32, L), "relabel: tree too large");
-  TCHGEO_REQUIRE(workspace && workspace_bytes >= relabel_workspace_bytes(num_trees, n_max, k32),
-                 "relabel: workspace too small (need %zu bytes)", relabel_workspace_bytes(num_trees, n_max, k32));
-  const int form = relabel_form(num_trees, n_max, k32);
+  TCHGEO_REQUIRE(workspace && workspace_bytes >= relabel_workspace_bytes(num_trees, n_max, id_bound),
+                 "relabel: workspace too small (need %zu bytes)", relabel_workspace_bytes(num_trees, n_max, id_bound));
+  const int form = relabel_form(num_trees, n_max, id_bound);
   if (form == FORM_BUCKETED) {
     BkLayout B;
-    bk_layout(num_trees, n_max, B);
+    bk_layout(num_trees, n_max, id_bound, B);
     return bk_enqueue(samples, stride, lens, num_trees, num_seeds, n_max, nodes, local, nodes_len, (char*)workspace, B, err,
                       stream);
   }
@@ -1319,26 +1616,26 @@ tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int6
 
 using namespace tchgeo;
 
-extern "C" size_t tchgeo_unique_relabel_batched_workspace_bytes(int64_t num_batches, int64_t n_max, int32_t key32) {
-  return relabel_workspace_bytes(num_batches, n_max, key32 != 0);
+extern "C" size_t tchgeo_unique_relabel_batched_workspace_bytes(int64_t num_batches, int64_t n_max, int64_t id_bound) {
+  return relabel_workspace_bytes(num_batches, n_max, id_bound);
 }
 
 extern "C" tchgeo_status tchgeo_unique_relabel_batched(const int64_t* samples, int64_t stride, const int64_t* lens,
                                                        int64_t num_batches, int64_t num_seeds, int64_t n_max,
-                                                       int32_t key32, int64_t* nodes, int64_t* local, int64_t* nodes_len,
+                                                       int64_t id_bound, int64_t* nodes, int64_t* local, int64_t* nodes_len,
                                                        void* workspace, size_t workspace_bytes, int32_t* err_word,
                                                        tchgeo_stream stream_) {
   TCHGEO_REQUIRE(num_batches >= 0 && stride >= 0 && n_max >= 0 && n_max <= stride, "bad relabel geometry");
   TCHGEO_REQUIRE(num_seeds >= 0 && num_seeds <= n_max, "num_seeds out of range");
   if (num_batches == 0) return TCHGEO_OK;
   TCHGEO_REQUIRE(samples && lens && nodes && local && nodes_len && err_word, "NULL pointer");
-  return relabel_enqueue(samples, stride, lens, num_batches, num_seeds, n_max, key32 != 0, nodes, local, nodes_len, workspace,
+  return relabel_enqueue(samples, stride, lens, num_batches, num_seeds, n_max, id_bound, nodes, local, nodes_len, workspace,
                          workspace_bytes, (uint32_t*)err_word, (cudaStream_t)stream_);
 }
 
 extern "C" size_t tchgeo_unique_relabel_workspace_bytes(int64_t n) {
   if (n < 0 || n >= ((int64_t)1 << 30)) return 0;
-  return relabel_workspace_bytes(1, n, false);
+  return relabel_workspace_bytes(1, n, 0);
 }
 
 // One tree (the B = 1 case of the batched stage, any i64 ids), synchronous: returns the number of nodes.

@@ -1,4 +1,4 @@
-//! `extern "C"` declarations of include/tchgeo_cuda.h (ABI version 5) for the reference crate: new file
+//! `extern "C"` declarations of include/tchgeo_cuda.h (ABI version 6) for the reference crate: new file
 //! `src/cuda_ffi.rs`.  One declaration per entry point of the header, same order.
 //! NOT COMPILED IN THIS REPOSITORY'S IMAGE (no cargo/rustc); tests/test_abi.py checks the same layout through ctypes
 //! and tests/cpp/abi_harness.cpp drives the same calls from C++.
@@ -6,7 +6,7 @@
 use std::os::raw::{c_char, c_void};
 
 pub type tchgeo_status = i32;
-pub const TCHGEO_ABI_VERSION: i32 = 5;
+pub const TCHGEO_ABI_VERSION: i32 = 6;
 pub const TCHGEO_OK: tchgeo_status = 0;
 pub const TCHGEO_ERR_BAD_ARG: tchgeo_status = 1;
 pub const TCHGEO_ERR_CUDA: tchgeo_status = 2;
@@ -170,9 +170,9 @@ extern "C" {
                               scratch: *mut i32, stream: tchgeo_stream) -> tchgeo_status;
     pub fn tchgeo_pack_ragged(src: *const i64, stride: i64, lens: *const i64, lens_stride: i64, num_batches: i64, max_len: i64,
                               dst: *mut i64, offsets: *mut i64, stream: tchgeo_stream) -> tchgeo_status;
-    pub fn tchgeo_unique_relabel_batched_workspace_bytes(num_batches: i64, n_max: i64, key32: i32) -> usize;
+    pub fn tchgeo_unique_relabel_batched_workspace_bytes(num_batches: i64, n_max: i64, id_bound: i64) -> usize;
     pub fn tchgeo_unique_relabel_batched(samples: *const i64, stride: i64, lens: *const i64, num_batches: i64, num_seeds: i64,
-        n_max: i64, key32: i32, nodes: *mut i64, local: *mut i64, nodes_len: *mut i64, workspace: *mut c_void,
+        n_max: i64, id_bound: i64, nodes: *mut i64, local: *mut i64, nodes_len: *mut i64, workspace: *mut c_void,
         workspace_bytes: usize, err_word: *mut i32, stream: tchgeo_stream) -> tchgeo_status;
     pub fn tchgeo_unique_relabel_workspace_bytes(n: i64) -> usize;
     pub fn tchgeo_unique_relabel(samples: *const i64, n: i64, num_seeds: i64, nodes: *mut i64, local: *mut i64,

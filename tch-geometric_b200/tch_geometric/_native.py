@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libtchgeo_cuda.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_INDEX, ERR_REFERENCE_PANIC, ERR_INTERNAL = range(7)
 SAMPLER_UNIFORM, SAMPLER_UNIFORM_REPLACE, SAMPLER_WEIGHTED = 0, 1, 2
-ABI_VERSION = 5
+ABI_VERSION = 6
 PREPARE_INDEX_REPLICA, PREPARE_WEIGHT_RECORDS = 1, 2
 
 c_i64, c_i32, c_u64, c_u32, c_vp, c_sz = (ctypes.c_int64, ctypes.c_int32, ctypes.c_uint64, ctypes.c_uint32,
@@ -104,9 +104,9 @@ def _load():
     lib.tchgeo_random_walk_graph.argtypes = [c_vp, c_i32, c_vp, c_i64, c_i64, ctypes.c_float, ctypes.c_float, c_u64, c_i64,
                                              c_vp, c_vp, c_vp, c_vp]
     lib.tchgeo_unique_relabel_batched_workspace_bytes.restype = c_sz
-    lib.tchgeo_unique_relabel_batched_workspace_bytes.argtypes = [c_i64, c_i64, c_i32]
+    lib.tchgeo_unique_relabel_batched_workspace_bytes.argtypes = [c_i64, c_i64, c_i64]
     lib.tchgeo_unique_relabel_batched.restype = c_i32
-    lib.tchgeo_unique_relabel_batched.argtypes = [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_sz,
+    lib.tchgeo_unique_relabel_batched.argtypes = [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz,
                                                   c_vp, c_vp]
     lib.tchgeo_neighbor_sampling_capacity.restype = c_i32
     lib.tchgeo_neighbor_sampling_capacity.argtypes = [P, c_vp, c_vp]

@@ -1044,10 +1044,15 @@ def unique_relabel(samples: Tensor, num_seeds: int) -> Tuple[Tensor, Tensor]:
     return nodes[:num.value], local
 
 
-def unique_relabel_batched(samples: Tensor, lens: Tensor, num_seeds: int, key32: bool = False
-                           ) -> Tuple[Tensor, Tensor, Tensor]:
+def unique_relabel_batched(samples: Tensor, lens: Tensor, num_seeds: int, key32: bool = False,
+                           id_bound: Optional[int] = None) -> Tuple[Tensor, Tensor, Tensor]:
     """B trees in padded rows: samples [B, stride], lens [B] (device) -> (nodes [B, stride], local [B, stride],
-    nodes_len [B]).  The stage HomogenousSampler(relabel=True) runs after the hops, exposed on its own."""
+    nodes_len [B]).  The stage HomogenousSampler(relabel=True) runs after the hops, exposed on its own.
+    id_bound: every id is in [0, id_bound) (the node count; lets the stage use direct-address tables); key32=True is
+    id_bound = 2**32 - 1; neither: any non-negative i64."""
+    bound = int(id_bound) if id_bound is not None else (0xFFFFFFFF if key32 else 0)
+    if not 0 <= bound <= 0xFFFFFFFF:
+        raise ValueError("id_bound must be in [0, 2**32 - 1]")
     _check(samples, torch.int64, "samples")
     dev = samples.device
     _check(lens, torch.int64, "lens", dev)
@@ -1057,11 +1062,11 @@ def unique_relabel_batched(samples: Tensor, lens: Tensor, num_seeds: int, key32:
     nodes, local = torch.empty_like(samples), torch.empty_like(samples)
     nodes_len = torch.zeros(B, dtype=torch.int64, device=dev)
     err = torch.zeros(1, dtype=torch.int32, device=dev)
-    ws_bytes = N.lib.tchgeo_unique_relabel_batched_workspace_bytes(B, stride, 1 if key32 else 0)
+    ws_bytes = N.lib.tchgeo_unique_relabel_batched_workspace_bytes(B, stride, bound)
     ws = torch.empty(max(int(ws_bytes), 1), dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         N.check(N.lib.tchgeo_unique_relabel_batched(_ptr(samples), stride, _ptr(lens), B, int(num_seeds), stride,
-                                                    1 if key32 else 0, _ptr(nodes), _ptr(local), _ptr(nodes_len), _ptr(ws),
+                                                    bound, _ptr(nodes), _ptr(local), _ptr(nodes_len), _ptr(ws),
                                                     ws_bytes, _ptr(err), _stream(dev)))
     N.check(N.lib.tchgeo_status_from_error_word(int(err.item()) & 0xFFFFFFFF))
     return nodes, local, nodes_len

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(native):
     for s in declared_symbols():
         assert hasattr(lib, s), s
     assert sorted(native.EXPORTS) == declared_symbols()
-    assert lib.tchgeo_abi_version() == native.ABI_VERSION == 5
+    assert lib.tchgeo_abi_version() == native.ABI_VERSION == 6
 
 
 def test_library_is_sm100a_native(native):

@@ -65,6 +65,53 @@ def test_batched_stage_ragged_trees(thg, key32):
         _check_tree(samples[b], int(lens[b]), S, nodes[b], local[b], int(nlen[b]))
 
 
+@pytest.mark.parametrize("bound", [700, 701, 5000, 9000, 70_000, 20_000_000])
+def test_batched_stage_with_id_bound(thg, bound):
+    """A stated id bound selects the direct-address buckets (bucket = id mod NB, slot = id / NB): same answers, for
+    bounds that need one bucket, several, and more buckets than the tree size alone would ask for."""
+    rng = np.random.default_rng(bound)
+    S, stride = 8, 5000
+    lens = np.array([0, 8, 9, 1024, 1025, 4999, 5000, 2048, 8, 3000], dtype=np.int64)
+    samples = rng.integers(0, min(bound, 700), (lens.size, stride))
+    samples[3] = rng.integers(0, bound, stride)                  # the whole id range, high slots included
+    samples[4, ::7] = bound - 1
+    samples[1, :8] = [3, 3, 9, 3, 9, 1, 1, 3]
+    nodes, local, nlen = thg.unique_relabel_batched(dev(samples), dev(lens), S, id_bound=bound)
+    nodes, local, nlen = nodes.cpu().numpy(), local.cpu().numpy(), nlen.cpu().numpy()
+    for b in range(lens.size):
+        _check_tree(samples[b], int(lens[b]), S, nodes[b], local[b], int(nlen[b]))
+
+
+def test_batched_stage_id_bound_modes_on_large_trees(thg):
+    """Trees of > 2^19 positions: with a small bound a pair still packs into one word, with a bound of 2^25 it does not
+    (13 slot bits + 20 position bits) and the unpacked direct form runs; both match the hashed form bit for bit."""
+    rng = np.random.default_rng(77)
+    S, stride = 64, (1 << 19) + 4097
+    lens = np.array([stride, stride - 4321], dtype=np.int64)
+    samples = rng.integers(0, 2_000_000, (2, stride))
+    samples[0, S:S + 1000] = samples[0, :1000][::-1]             # seeds reappear later (and duplicated seeds exist)
+    want = thg.unique_relabel_batched(dev(samples), dev(lens), S, key32=True)
+    for bound in (2_000_000, 1 << 25):
+        got = thg.unique_relabel_batched(dev(samples), dev(lens), S, id_bound=bound)
+        assert torch.equal(got[2], want[2])
+        for b in range(2):
+            k, m = int(want[2][b]), int(lens[b])
+            assert torch.equal(got[0][b, :k], want[0][b, :k]) and torch.equal(got[1][b, :m], want[1][b, :m])
+    nodes, local, nlen = (x.cpu().numpy() for x in want)
+    _check_tree(samples[1], int(lens[1]), S, nodes[1], local[1], int(nlen[1]))
+
+
+def test_batched_stage_rejects_ids_beyond_the_stated_bound(thg):
+    samples = np.arange(64, dtype=np.int64).reshape(2, 32)
+    with pytest.raises(thg.ReferencePanic):
+        thg.unique_relabel_batched(dev(samples), dev([32, 32]), 4, id_bound=63)
+    samples[1, 5] = -3
+    with pytest.raises(thg.ReferencePanic):
+        thg.unique_relabel_batched(dev(samples), dev([32, 32]), 4, id_bound=64)
+    with pytest.raises(ValueError):
+        thg.unique_relabel_batched(dev(samples), dev([32, 32]), 4, id_bound=1 << 33)
+
+
 def test_batched_stage_rejects_ids_beyond_32_bits_in_key32_mode(thg):
     samples = np.arange(64, dtype=np.int64).reshape(2, 32)
     samples[1, 5] = (1 << 32) + 7
