@@ -20,12 +20,14 @@
 #include <vector>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
 namespace tchgeo {
 // csrc/relabel.cu: the batched dedup + relabel stage (device-side lengths, asynchronous)
 size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound);
+bool relabel_is_bucketed(int64_t num_trees, int64_t n_max, int64_t id_bound);
 tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
                               int64_t num_seeds, int64_t n_max, int64_t id_bound, int64_t* nodes, int64_t* local,
                               int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
@@ -159,7 +161,7 @@ struct NegPlan {
   std::vector<int64_t> seq_off;     // offset of type t's segment in seq / local
   int64_t seq_total = 0, max_seq = 0;
   size_t cub_bytes = 0, rl_bytes = 0;
-  bool k32 = true;                  // every id of the call fits 32 bits: the relabel stage's fast forms
+  std::vector<int64_t> id_bound;    // [T] what the relabel stage may assume about the type's ids (0: any i64)
   size_t off_cnts = 0;              // device counters: accepted[T] | seq_len[T] | nodes_len[T] | edges_len[R]
   size_t off_hdr, off_rels, off_rel_dst, off_cand, off_crel, off_tpos, off_flags, off_ranks, off_seq, off_local, off_cub,
       off_rl, total;
@@ -179,9 +181,26 @@ tchgeo_status neg_plan(const tchgeo_negative_args* a, NegPlan& P, bool layout = 
     TCHGEO_REQUIRE(a->rel_src[r] >= 0 && a->rel_src[r] < T && a->rel_dst[r] >= 0 && a->rel_dst[r] < T,
                    "relation %d: node type out of range", r);
     TCHGEO_REQUIRE(a->node_count[r] >= 0 && a->node_count[r] < ((int64_t)1 << 32), "relation %d: size out of range", r);
-    if (a->node_count[r] >= 0xFFFFFFFFll || a->num_rows[r] >= 0xFFFFFFFFll) P.k32 = false;
-    if (!getenv("TCHGEO_NEG_RELABEL_K32")) P.k32 = false;  // ONE tree of millions of ids: the wave form (64-bit keys) measured
-                                                           // 0.83 ms per call against 0.92 ms for the bucketed form
+  }
+  // ids of type t: its inputs (checked against num_rows by the draw kernel when the type is the source of a relation)
+  // and the candidates drawn from [0, node_count) of the relations it is the destination of.  With a bound the relabel
+  // stage can use its direct-address buckets -- but that form is built for hundreds of trees per call: for the ONE tree
+  // of millions of ids here it measured 1.04 ms per call against 0.80 ms for the 64-bit wave form, which stays the
+  // default (TCHGEO_NEG_RELABEL=direct selects the buckets).
+  P.id_bound.assign(T, 0);
+  {
+    const char* f = getenv("TCHGEO_NEG_RELABEL");
+    const bool waves = !(f && strcmp(f, "direct") == 0);
+    for (int t = 0; t < T && !waves; ++t) {
+      int64_t bound = 0;
+      bool is_src = false;
+      for (int r = 0; r < R; ++r) {
+        if (a->rel_src[r] == t) { is_src = true; bound = std::max(bound, a->num_rows[r]); }
+        if (a->rel_dst[r] == t) bound = std::max(bound, a->node_count[r]);
+      }
+      const bool has_inputs = a->num_inputs[t] > 0;
+      if (bound > 0 && bound < 0xFFFFFFFFll && (is_src || !has_inputs)) P.id_bound[t] = bound;
+    }
   }
   int64_t G = 0;
   for (int t = 0; t < T; ++t) {
@@ -212,8 +231,14 @@ tchgeo_status neg_plan(const tchgeo_negative_args* a, NegPlan& P, bool layout = 
   TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, cub, (const int*)nullptr, (int*)nullptr,
                                                   (int64_t)(G > 0 ? G : 1)));
   P.cub_bytes = cub;
-  P.rl_bytes = relabel_workspace_bytes(1, std::max<int64_t>(P.max_seq, 1), P.k32 ? 0xFFFFFFFFll : 0);
-  TCHGEO_REQUIRE(P.rl_bytes != 0, "relabel workspace query failed");
+  P.rl_bytes = 0;
+  for (int t = 0; t < T; ++t) {
+    // (one tree of millions of ids: only the bucketed form beats the 64-bit wave form here)
+    if (!relabel_is_bucketed(1, std::max<int64_t>(P.seq_cap[t], 1), P.id_bound[t])) P.id_bound[t] = 0;
+    const size_t need = relabel_workspace_bytes(1, std::max<int64_t>(P.seq_cap[t], 1), P.id_bound[t]);
+    TCHGEO_REQUIRE(need != 0, "relabel workspace query failed");
+    P.rl_bytes = std::max(P.rl_bytes, need);
+  }
   const size_t g = (size_t)(G > 0 ? G : 1), sq = (size_t)(P.seq_total > 0 ? P.seq_total : 1);
   size_t o = 0;
   P.off_hdr = o; o += 256;  // [8] err (u32)
@@ -352,7 +377,7 @@ extern "C" tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* a)
     TCHGEO_CUDA_CHECK(cudaGetLastError());
     if (P.seq_cap[t] == 0) continue;
     TCHGEO_REQUIRE(a->samples[t], "samples[%d] is NULL", t);
-    st = relabel_enqueue(seq_t, P.seq_cap[t], d_len + t, 1, P.S[t], P.seq_cap[t], P.k32 ? 0xFFFFFFFFll : 0, a->samples[t], local_t, d_nodes + t,
+    st = relabel_enqueue(seq_t, P.seq_cap[t], d_len + t, 1, P.S[t], P.seq_cap[t], P.id_bound[t], a->samples[t], local_t, d_nodes + t,
                          ws + P.off_rl, P.rl_bytes, d_err, stream);
     if (st != TCHGEO_OK) return st;
   }

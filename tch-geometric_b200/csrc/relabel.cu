@@ -1355,8 +1355,8 @@ bool bk_layout(int64_t num_trees, int64_t n_max, int64_t id_bound, BkLayout& L) 
   if (num_trees <= 0 || num_trees > 65535 || n_max < 0 || n_max >= ((int64_t)1 << 31)) return false;
   if (id_bound <= 0 || id_bound > 0xFFFFFFFFll) return false;
   int nb = 1, lg = 0;
-  while ((int64_t)nb * BK_TARGET < n_max) { nb <<= 1; ++lg; }
-  if (nb > BK_MAX_BUCKETS) return false;        // trees beyond ~6 M ids: the global-table form
+  while ((int64_t)nb * BK_TARGET < n_max && nb < BK_MAX_BUCKETS) { nb <<= 1; ++lg; }
+  const bool hashed_fits = (int64_t)nb * BK_TARGET >= n_max;   // hashed tables: trees up to ~6 M ids
   L.mode = BK_HASHED; L.pos_bits = 0; L.slots = 0; L.id_bound = 0xFFFFFFFFu;
   const char* de = getenv("TCHGEO_RELABEL_DIRECT");
   if (id_bound < 0xFFFFFFFFll && !(de && atoi(de) == 0)) {
@@ -1376,6 +1376,7 @@ bool bk_layout(int64_t num_trees, int64_t n_max, int64_t id_bound, BkLayout& L) 
       L.slots = (int)slots_for(lg);
     }
   }
+  if (L.mode == BK_HASHED && !hashed_fits) return false;       // the global-table forms
   L.nb = nb; L.log2_nb = lg;
   L.tiles_per_tree = (int)std::max<int64_t>(1, (n_max + BK_TILE - 1) / BK_TILE);
   L.ctiles = (int)std::max<int64_t>(1, (n_max + BKC_TILE - 1) / BKC_TILE);
@@ -1556,6 +1557,9 @@ static int relabel_form(int64_t num_trees, int64_t n_max, int64_t id_bound) {
   if (!(pe && atoi(pe) != 0) && bk_layout(num_trees, n_max, id_bound, B)) return FORM_BUCKETED;
   RpLayout P;
   return rp_layout(num_trees, n_max, P) ? FORM_PERSISTENT : FORM_WAVES;
+}
+bool relabel_is_bucketed(int64_t num_trees, int64_t n_max, int64_t id_bound) {
+  return id_bound > 0 && id_bound <= 0xFFFFFFFFll && relabel_form(num_trees, n_max, id_bound) == FORM_BUCKETED;
 }
 size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound) {
   if (id_bound < 0 || id_bound > 0xFFFFFFFFll) return 0;
