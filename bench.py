@@ -404,7 +404,23 @@ def run_ours(args):
     # ---- end-to-end with host buffers (e2e) ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier)
+        # every transport of SampledBatches.to_host is timed; the line's e2e is the fastest one on this box, the others
+        # are kept beside it (which wins depends on the host: PCIe rate against the rate its cores write memory at)
+        runs = {}
+        for tr in (["plain", "compact", "hybrid"] if args.e2e_transport == "all" else [args.e2e_transport]):
+            try:
+                runs[tr] = run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier,
+                                   transport=tr)
+            except Exception as exc:  # e.g. ids beyond int32 for the compact transport
+                log(f"[bench] e2e transport {tr} failed: {exc}")
+                runs[tr] = None
+        good = {k: v for k, v in runs.items() if v}
+        if good:
+            best = max(good, key=lambda k: good[k]["value"])
+            e2e = dict(good[best])
+            e2e["other_transports"] = [{kk: v[kk] for kk in ("transport", "value", "ms_per_step", "d2h_bytes_per_step",
+                                                              "d2h_GBps_per_gpu", "landing_zone_verified")}
+                                       for k, v in good.items() if k != best]
 
     # ---- the same step with the dedup + insertion-order relabel stage (K7) ------------------------
     with_relabel = None
@@ -449,16 +465,28 @@ def run_ours(args):
         emit(out)
 
 
-def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier):
+def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier, transport="plain"):
     """Public plan API with HOST buffers.  Per step: pinned seeds -> H2D -> sample (HomogenousSampler.sample_async) ->
-    SampledBatches.to_host: the used prefixes of samples / cols / edge_index are packed on the device and copied to
-    pinned host buffers, one D2H per tensor and group of batches (`rows` is arange(S, S + E) for every batch and is
-    served from a cached host arange instead of travelling).  Two plans on two streams: step s+1 is sampled while
-    step s drains over PCIe."""
+    SampledBatches.to_host: the used prefixes of samples / cols / edge_index of every group of 64 batches are packed on
+    the device and land in host memory as the reference's i64 vectors (`rows` is arange(S, S + E) for every batch and is
+    served from a cached host arange instead of travelling).  Two plans on two streams: step s+1 is sampled while step s
+    drains over PCIe.  transport="plain": the packed i64 vectors travel as they are (24 B per edge); "compact": i32 ids
+    and one u8 edge count per node travel (9 B per edge) and host threads rebuild the i64 vectors (inside the timed
+    region) while the next group is on the bus."""
     from tch_geometric.sharding import reduce_job
-    HB = min(B, 64)  # pinned landing zone per plan for 64 batches, reused group by group
+    HB = min(B, int(os.environ.get("TCHGEO_BENCH_HB", 64)))  # host landing zone per plan for 64 batches, reused group by group
+    # compact / hybrid: a group's staging buffers stay busy until the host threads have rebuilt it, so each plan
+    # rotates through three landing zones -- one on the bus, up to two being rebuilt
+    ring = 1 if transport == "plain" else int(os.environ.get("TCHGEO_BENCH_RING", 3))
     try:
-        hosts = [thg.HostBatches(HB, cap_n, cap_e, S, device, fill=0.8) for _ in plans]
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 2
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    threads = int(os.environ.get("TCHGEO_BENCH_THREADS", max(2, min(16, ncpu // (2 * max(local_world, 1))))))
+    try:
+        hosts = [[thg.HostBatches(HB, cap_n, cap_e, S, device, fill=0.8, transport=transport, threads=threads)
+                  for _ in range(ring)] for _ in plans]
     except RuntimeError as e:
         log(f"[bench] could not pin host output buffers: {e}")
         return None
@@ -469,8 +497,8 @@ def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, ca
         res = plans[j].result()
         d2h = res.layer_offsets.nbytes + res.samples_len.nbytes + res.edges_len.nbytes  # already on the host
         with torch.cuda.stream(streams[j]):
-            for g0 in range(0, B, HB):
-                d2h += res.to_host(hosts[j], g0, min(HB, B - g0))
+            for gi, g0 in enumerate(range(0, B, HB)):
+                d2h += res.to_host(hosts[j][gi % ring], g0, min(HB, B - g0))
         return int(res.edges_len.sum()), d2h
 
     def job(first, count):
@@ -486,6 +514,9 @@ def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, ca
         while pending:
             e, d = drain(pending.pop(0))
             edges, d2h = edges + e, d2h + d
+        for hs in hosts:
+            for h in hs:
+                h.wait()                     # compact: the last groups' vectors are rebuilt
         return edges, d2h
 
     job(0, max(min(W, 3), 2))
@@ -505,17 +536,30 @@ def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, ca
     ms = max(start.elapsed_time(stop), wall_ms)
     # spot check of the landing zone: the last group of the last drained plan equals the device result
     last = plans[(K - 1) & 1]._call
-    got = hosts[(K - 1) & 1].batch(0)
+    got = hosts[(K - 1) & 1][((B - 1) // HB) % ring].batch(0)
     b = (B - 1) // HB * HB
-    ok = bool(torch.equal(got[0], last.samples[0][b, :int(last.samples_len[b, 0])].cpu()))
+    ne = int(last.edges_len[b, 0])
+    ok = bool(torch.equal(got[0], last.samples[0][b, :int(last.samples_len[b, 0])].cpu())
+              and torch.equal(got[2], last.cols[0][b, :ne].cpu()) and torch.equal(got[3], last.eidx[0][b, :ne].cpu()))
     ms, edges_all = reduce_job(ms, float(edges), device)
+    path = ("HomogenousSampler.sample_async(pinned host seeds) on two plans / two streams + SampledBatches.to_host per "
+            "group of 64 batches; rows = arange(S, S+E) is served from a cached host arange (neighbor_sampling.rs:210-218) "
+            "and layer offsets / lengths come back with the length table; ")
+    if transport == "compact":
+        path += (f"transport=compact: tchgeo_pack_transport packs i32 samples / edge positions and one u8 edge count per "
+                 f"node, three D2H copies into pinned staging, then tchgeo_host_unpack_transport rebuilds the reference's "
+                 f"i64 samples / cols / edge_index in host memory with {threads} threads (inside the timed region)")
+    elif transport == "hybrid":
+        path += (f"transport=hybrid: edge_index travels as packed i64 straight into its pinned vector; samples travel as "
+                 f"i32 and cols as one u8 edge count per node (tchgeo_pack_transport) and tchgeo_host_unpack_transport "
+                 f"rebuilds their i64 vectors in host memory with {threads} threads (inside the timed region)")
+    else:
+        path += "transport=plain: device-side ragged pack, then one D2H per i64 tensor (samples, cols, edge_index) into pinned host buffers"
+    del hosts
     return {"value": edges_all / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": B * S * 8,
             "d2h_bytes_per_step": d2h // K, "ms_per_step": ms / K, "landing_zone_verified": ok,
-            "d2h_GBps_per_gpu": d2h / K / (ms / K * 1e-3) / 1e9,
-            "path": "HomogenousSampler.sample_async(pinned host seeds) on two plans / two streams + "
-                    "SampledBatches.to_host: device-side ragged pack, then one D2H per tensor (samples, cols, edge_index) "
-                    "and group of 64 batches into pinned host buffers; rows = arange(S, S+E) is served from a cached host "
-                    "arange (neighbor_sampling.rs:210-218) and layer offsets / lengths come back with the length table"}
+            "d2h_GBps_per_gpu": d2h / K / (ms / K * 1e-3) / 1e9, "transport": transport,
+            "host_bytes_landed_per_step": int(8 * (3 * edges / K + B * S)), "path": path}
 
 
 def run_relabel(thg, ptrs, idx, dev_seeds, sampler, B, S, K, W, world, rank, device, barrier):
@@ -1169,6 +1213,8 @@ def main():
                     help="partitioned workload, fixed protocol: segment size as a multiple of the mean per-pair load")
     ap.add_argument("--walkers", type=int, default=0, help="walk workload: number of walkers (0 = 10 per node)")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-transport", choices=["all", "plain", "compact", "hybrid"], default="all",
+                    help="SampledBatches.to_host transport(s) to time for the e2e number")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -529,6 +529,34 @@ TCHGEO_API tchgeo_status tchgeo_pack_ragged(const int64_t* src /*DEVICE [B, stri
                                             int64_t max_len, int64_t* dst /*DEVICE [sum]*/, int64_t* offsets /*DEVICE [B+1]*/,
                                             tchgeo_stream stream);
 
+/* Compact host transport of a group of homogeneous batches (extension; the reference builds its output Vecs in host
+ * memory to begin with, src/python.rs:259-262, so it has no counterpart to cite).  The reference layout is 24 B per
+ * sampled edge on the bus (samples, cols, edge_index as i64; rows is an arange, src/algo/neighbor_sampling.rs:210-218).
+ * tchgeo_pack_transport (DEVICE, asynchronous) writes the used prefixes of `count` padded batches back to back as
+ *   samples32 [sum n_b] i32, eidx32 [sum e_b] i32, counts [sum n_b] u8 = edges drawn for node j of the batch, i.e. the
+ *   run length of j in the batch's (non-decreasing) cols vector,
+ * and the packed offsets n_off / e_off (DEVICE [count + 1]); counts_bytes = size of `counts` (zeroed here).  An id that
+ * does not fit i32 raises TCHGEO_ERR_INDEX in *err_word, a run longer than 255 or a cols vector that is not
+ * non-decreasing TCHGEO_ERR_CAPACITY: the caller then uses tchgeo_pack_ragged.
+ * tchgeo_host_unpack_transport (HOST memory only, synchronous, num_threads worker threads, non-temporal stores) rebuilds
+ * samples / cols / edge_index [same packed offsets] as i64 -- byte for byte what tchgeo_pack_ragged + a D2H copy land.
+ * eidx32 (and, on the host side, edge_index) may be NULL in both calls: edge_index then travels as i64 through
+ * tchgeo_pack_ragged -- 13 B per edge on the bus and a third less for the host threads to write, the better balance
+ * on a host with few cores. */
+TCHGEO_API tchgeo_status tchgeo_pack_transport(const int64_t* samples /*DEVICE [B, samples_stride]*/, int64_t samples_stride,
+                                               const int64_t* cols /*DEVICE [B, edges_stride]*/,
+                                               const int64_t* edge_index /*DEVICE [B, edges_stride]*/, int64_t edges_stride,
+                                               const int64_t* n_lens /*DEVICE [count]*/, const int64_t* e_lens /*DEVICE [count]*/,
+                                               int64_t count, int64_t max_n, int64_t max_e, int32_t* samples32 /*DEVICE*/,
+                                               int32_t* eidx32 /*DEVICE*/, uint8_t* counts /*DEVICE*/, int64_t counts_bytes,
+                                               int64_t* n_off /*DEVICE [count+1]*/, int64_t* e_off /*DEVICE [count+1]*/,
+                                               int32_t* err_word /*DEVICE*/, tchgeo_stream stream);
+TCHGEO_API tchgeo_status tchgeo_host_unpack_transport(const int32_t* samples32 /*HOST*/, const int32_t* eidx32 /*HOST*/,
+                                                      const uint8_t* counts /*HOST*/, const int64_t* n_off /*HOST [count+1]*/,
+                                                      const int64_t* e_off /*HOST [count+1]*/, int64_t count,
+                                                      int64_t* samples /*HOST*/, int64_t* cols /*HOST*/,
+                                                      int64_t* edge_index /*HOST*/, int32_t num_threads);
+
 /* -------------------------------------------------------------------------------------------- */
 /* Dedup + insertion-order relabel of one sampled tree (additive stage).                          */
 /*   nodes      = seeds (duplicates kept) ++ every other id at first appearance                    */

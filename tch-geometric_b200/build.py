@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "tch_geometric", "libtchgeo_cuda.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu", "partitioned.cu", "partitioned_fixed.cu", "random_walk.cu", "relabel.cu"]
+SOURCES = ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu", "partitioned.cu", "partitioned_fixed.cu", "random_walk.cu", "relabel.cu", "transport.cu", "host_unpack.cpp"]
 DEPS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "graph.cuh"), os.path.join(HERE, "..", "include", "tchgeo_cuda.h")]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -34,21 +34,24 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(OBJ, src.replace(".cu", ".o"))
+        o = os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
         objs.append(o)
         if force or _stale(o, [s] + DEPS):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
+            if src.endswith(".cpp"):   # host-only code: the host compiler directly
+                cmd = ["/usr/bin/g++", "-O3", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-c", s, "-o", o]
+            else:
+                cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o]
             procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- nvcc {src} ---\n{out}\n")
+            sys.stderr.write(f"--- compiler output, {src} ---\n{out}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-Xlinker", "--exclude-libs,ALL"]
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-Xlinker", "--exclude-libs,ALL", "-lpthread"]
         subprocess.check_call(cmd)
     return OUT
 

@@ -9,7 +9,7 @@ fn main() {
     let nvcc = env::var("NVCC").unwrap_or_else(|_| "/usr/local/cuda/bin/nvcc".into());
     let mut objs = vec![];
     for src in ["capi.cu", "csx_build.cu", "csx_transform.cu", "gather.cu", "negative_sampling.cu", "neighbor_sampling.cu",
-                "partitioned.cu", "partitioned_fixed.cu", "random_walk.cu", "relabel.cu"] {
+                "partitioned.cu", "partitioned_fixed.cu", "random_walk.cu", "relabel.cu", "transport.cu"] {
         let obj = out.join(src.replace(".cu", ".o"));
         let ok = Command::new(&nvcc)
             .args(["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -20,6 +20,11 @@ fn main() {
         println!("cargo:rerun-if-changed={}", csrc.join(src).display());
         objs.push(obj);
     }
+    // host half of the compact transport: plain C++ (AVX-512 paths are selected at run time)
+    let hu = out.join("host_unpack.o");
+    assert!(Command::new("g++").args(["-std=c++17", "-O3", "-fPIC", "-c"]).arg(csrc.join("host_unpack.cpp")).arg("-o").arg(&hu)
+        .status().unwrap().success());
+    objs.push(hu);
     let lib = out.join("libtchgeo_cuda.a");
     assert!(Command::new("ar").arg("crs").arg(&lib).args(&objs).status().unwrap().success());
     println!("cargo:rustc-link-search=native={}", out.display());

@@ -170,6 +170,12 @@ extern "C" {
                               scratch: *mut i32, stream: tchgeo_stream) -> tchgeo_status;
     pub fn tchgeo_pack_ragged(src: *const i64, stride: i64, lens: *const i64, lens_stride: i64, num_batches: i64, max_len: i64,
                               dst: *mut i64, offsets: *mut i64, stream: tchgeo_stream) -> tchgeo_status;
+    pub fn tchgeo_pack_transport(samples: *const i64, samples_stride: i64, cols: *const i64, edge_index: *const i64,
+        edges_stride: i64, n_lens: *const i64, e_lens: *const i64, count: i64, max_n: i64, max_e: i64, samples32: *mut i32,
+        eidx32: *mut i32, counts: *mut u8, counts_bytes: i64, n_off: *mut i64, e_off: *mut i64, err_word: *mut i32,
+        stream: tchgeo_stream) -> tchgeo_status;
+    pub fn tchgeo_host_unpack_transport(samples32: *const i32, eidx32: *const i32, counts: *const u8, n_off: *const i64,
+        e_off: *const i64, count: i64, samples: *mut i64, cols: *mut i64, edge_index: *mut i64, num_threads: i32) -> tchgeo_status;
     pub fn tchgeo_unique_relabel_batched_workspace_bytes(num_batches: i64, n_max: i64, id_bound: i64) -> usize;
     pub fn tchgeo_unique_relabel_batched(samples: *const i64, stride: i64, lens: *const i64, num_batches: i64, num_seeds: i64,
         n_max: i64, id_bound: i64, nodes: *mut i64, local: *mut i64, nodes_len: *mut i64, workspace: *mut c_void,

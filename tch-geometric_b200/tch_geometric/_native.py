@@ -108,6 +108,11 @@ def _load():
     lib.tchgeo_unique_relabel_batched.restype = c_i32
     lib.tchgeo_unique_relabel_batched.argtypes = [c_vp, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz,
                                                   c_vp, c_vp]
+    lib.tchgeo_pack_transport.restype = c_i32
+    lib.tchgeo_pack_transport.argtypes = [c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp,
+                                          c_i64, c_vp, c_vp, c_vp, c_vp]
+    lib.tchgeo_host_unpack_transport.restype = c_i32
+    lib.tchgeo_host_unpack_transport.argtypes = [c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i32]
     lib.tchgeo_neighbor_sampling_capacity.restype = c_i32
     lib.tchgeo_neighbor_sampling_capacity.argtypes = [P, c_vp, c_vp]
     lib.tchgeo_neighbor_sampling_workspace_bytes.restype = c_sz
@@ -201,6 +206,7 @@ EXPORTS = [
     "tchgeo_plan_create", "tchgeo_plan_enqueue", "tchgeo_plan_enqueue_timed", "tchgeo_plan_collect", "tchgeo_plan_results",
     "tchgeo_plan_num_launches", "tchgeo_plan_destroy", "tchgeo_random_walk_graph", "tchgeo_pack_ragged",
     "tchgeo_partf_workspace_bytes", "tchgeo_partf_scatter", "tchgeo_partf_serve", "tchgeo_partf_finish",
+    "tchgeo_pack_transport", "tchgeo_host_unpack_transport",
 ]
 
 

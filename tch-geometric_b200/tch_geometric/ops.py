@@ -305,6 +305,7 @@ class _Call:
         T, R, H, B = len(seeds), len(rel_src), num_hops, num_batches
         self.T, self.R, self.H, self.B, self.device = T, R, H, B, device
         self.plan = None
+        self.max_fanout = int(np.max(np.asarray(fanouts, dtype=np.int64), initial=0))
         # the reference slices weights / timestamps with the column's range and panics when they are short
         # (EdgeAttr::get, src/data/graph.rs:103-120); the kernels check every column against nnz as well
         for r in range(R):
@@ -514,7 +515,7 @@ class SampledBatches:
         call = self._call
         return packed_to_host(self.samples, self.cols, self.edge_index, self.samples_len, self.edges_len,
                               int(call.cap_n[0]), int(call.cap_e[0]), call.device, host, first,
-                              call.B - first if count is None else int(count))
+                              call.B - first if count is None else int(count), max_fanout=call.max_fanout)
 
     def relabeled(self, b):
         """-> (nodes, local) of batch b: nodes = seeds ++ every other id of samples at its first appearance,
@@ -540,59 +541,128 @@ def host_arange(n: int) -> Tensor:
 
 
 class HostBatches:
-    """Pinned host landing zone (+ its device staging buffers) for `SampledBatches.to_host`: the used prefixes of
-    `samples`, `cols` and `edge_index` of a group of batches arrive packed back to back, one D2H copy per tensor.
-    `fill` = fraction of the worst-case capacity to provide (sampled trees typically use about 0.65 of it)."""
+    """Host landing zone (+ its device staging buffers) for `SampledBatches.to_host`: the used prefixes of `samples`,
+    `cols` and `edge_index` of a group of batches arrive packed back to back as int64 vectors.
+    `fill` = fraction of the worst-case capacity to provide (sampled trees typically use about 0.65 of it).
 
-    def __init__(self, num_batches: int, cap_samples: int, cap_edges: int, num_seeds: int, device, fill: float = 0.8):
-        self.B, self.S, self.device = int(num_batches), int(num_seeds), device
+    transport="plain": three D2H copies of the packed i64 vectors into pinned memory (24 B per edge on the bus).
+    transport="compact": the group travels as i32 samples / edge positions and one u8 edge count per node (9 B per edge;
+    tchgeo_pack_transport) into pinned staging buffers, and a worker thread rebuilds the i64 vectors in host memory with
+    `threads` threads (tchgeo_host_unpack_transport) once the copies have arrived -- `wait()` (also called by `batch`)
+    blocks until they are there.  Same bytes in the end; needs ids < 2^31 and fanouts <= 255.
+    transport="hybrid": as compact, but `edge_index` travels as i64 straight into its pinned vector (13 B per edge on
+    the bus, a third less for the host threads to write): the better balance when the host threads are the limit."""
+
+    def __init__(self, num_batches: int, cap_samples: int, cap_edges: int, num_seeds: int, device, fill: float = 0.8,
+                 transport: str = "plain", threads: Optional[int] = None):
+        if transport not in ("plain", "compact", "hybrid"):
+            raise ValueError("transport must be 'plain', 'compact' or 'hybrid'")
+        self.B, self.S, self.device, self.transport = int(num_batches), int(num_seeds), device, transport
         self.cap_n = int(num_batches * cap_samples * fill) + 1
         self.cap_e = int(num_batches * cap_edges * fill) + 1
-        host = lambda n: torch.empty(n, dtype=torch.int64).pin_memory()
-        devb = lambda n: torch.empty(n, dtype=torch.int64, device=device)
-        self.samples, self.cols, self.edge_index = host(self.cap_n), host(self.cap_e), host(self.cap_e)
-        self._d_samples, self._d_cols, self._d_eidx = devb(self.cap_n), devb(self.cap_e), devb(self.cap_e)
+        host = lambda n, dt=torch.int64: torch.empty(n, dtype=dt).pin_memory()
+        devb = lambda n, dt=torch.int64: torch.empty(n, dtype=dt, device=device)
         self._d_lens = devb(2 * self.B)
         self._d_off = devb(2 * (self.B + 1))
         self._h_lens = host(2 * self.B)
         self.n_off = self.e_off = None       # host offsets [count + 1] of the last to_host
         self.nbytes = 0
+        self._pending = None
+        if transport == "plain":
+            self.samples, self.cols, self.edge_index = host(self.cap_n), host(self.cap_e), host(self.cap_e)
+            self._d_samples, self._d_cols, self._d_eidx = devb(self.cap_n), devb(self.cap_e), devb(self.cap_e)
+            return
+        import concurrent.futures
+        import os
+        self.threads = int(threads) if threads else max(1, min(16, (os.cpu_count() or 2) // 2))
+        self.samples = torch.empty(self.cap_n, dtype=torch.int64)
+        self.cols = torch.empty(self.cap_e, dtype=torch.int64)
+        self._h_s32, self._h_cnt = host(self.cap_n, torch.int32), host(self.cap_n, torch.uint8)
+        self._d_s32, self._d_cnt = devb(self.cap_n, torch.int32), devb(self.cap_n, torch.uint8)
+        if transport == "hybrid":
+            self.edge_index, self._d_eidx = host(self.cap_e), devb(self.cap_e)
+            self._h_e32 = self._d_e32 = None
+        else:
+            self.edge_index = torch.empty(self.cap_e, dtype=torch.int64)
+            self._h_e32, self._d_e32 = host(self.cap_e, torch.int32), devb(self.cap_e, torch.int32)
+        self._d_err, self._h_err = devb(1, torch.int32), host(1, torch.int32)
+        self._event = torch.cuda.Event()
+        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+
+    def wait(self):
+        """compact transport: block until the worker has rebuilt the last group's vectors (no-op otherwise)"""
+        fut, self._pending = self._pending, None
+        if fut is not None:
+            fut.result()
+
+    def _unpack(self, n_off, e_off, count):
+        self._event.synchronize()
+        N.check(N.lib.tchgeo_status_from_error_word(int(self._h_err[0]) & 0xFFFFFFFF))
+        hybrid = self._h_e32 is None
+        N.check(N.lib.tchgeo_host_unpack_transport(_ptr(self._h_s32), None if hybrid else _ptr(self._h_e32), _ptr(self._h_cnt),
+                                                   n_off.ctypes.data, e_off.ctypes.data, count, _ptr(self.samples),
+                                                   _ptr(self.cols), None if hybrid else _ptr(self.edge_index), self.threads))
 
     def batch(self, i):
-        """(samples, rows, cols, edge_index) of the i-th batch of the last transfer, as host views (valid once the
-        stream the transfer went to has been synchronised)"""
+        """(samples, rows, cols, edge_index) of the i-th batch of the last transfer, as host views (plain transport:
+        valid once the stream the transfer went to has been synchronised)"""
+        self.wait()
         n0, n1, e0, e1 = int(self.n_off[i]), int(self.n_off[i + 1]), int(self.e_off[i]), int(self.e_off[i + 1])
         rows = host_arange(self.S + (e1 - e0))[self.S:self.S + (e1 - e0)]
         return self.samples[n0:n1], rows, self.cols[e0:e1], self.edge_index[e0:e1]
 
 
 def packed_to_host(samples, cols, edge_index, samples_len, edges_len, cap_n, cap_e, device, host: "HostBatches",
-                   first: int, count: int) -> int:
+                   first: int, count: int, max_fanout: Optional[int] = None) -> int:
     """Shared by SampledBatches.to_host and the partitioned plans' results (same padded [B, capacity] layout)."""
     if count > host.B:
         raise ValueError("HostBatches is smaller than the group of batches")
+    compact, hybrid = host.transport in ("compact", "hybrid"), host.transport == "hybrid"
+    if compact and max_fanout is not None and max_fanout > 255:
+        raise ValueError("transport='compact' carries one u8 edge count per node: fanouts above 255 need transport='plain'")
+    host.wait()                              # the staging buffers of the previous group are free again
     ns, ne = samples_len[first:first + count], edges_len[first:first + count]
-    n_off = np.concatenate([[0], np.cumsum(ns)])
-    e_off = np.concatenate([[0], np.cumsum(ne)])
+    n_off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(ns)]), dtype=np.int64)
+    e_off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(ne)]), dtype=np.int64)
     if n_off[-1] > host.cap_n or e_off[-1] > host.cap_e:
         raise MemoryError("HostBatches too small for this group: create it with a larger `fill`")
     h = host._h_lens
     h[:count].copy_(torch.from_numpy(np.ascontiguousarray(ns)))
     h[host.B:host.B + count].copy_(torch.from_numpy(np.ascontiguousarray(ne)))
+    nt, et = int(n_off[-1]), int(e_off[-1])
     with torch.cuda.device(device):
         stream = _stream(device)
         host._d_lens.copy_(h, non_blocking=True)
-        for src, lens_at, dst, off_at, cap in ((samples, 0, host._d_samples, 0, cap_n),
-                                               (cols, host.B, host._d_cols, host.B + 1, cap_e),
-                                               (edge_index, host.B, host._d_eidx, host.B + 1, cap_e)):
-            N.check(N.lib.tchgeo_pack_ragged(_ptr(src[first]), src.shape[1], _ptr(host._d_lens[lens_at:]), 1, count,
-                                             int(cap), _ptr(dst), _ptr(host._d_off[off_at:]), stream))
-        nt, et = int(n_off[-1]), int(e_off[-1])
-        host.samples[:nt].copy_(host._d_samples[:nt], non_blocking=True)
-        host.cols[:et].copy_(host._d_cols[:et], non_blocking=True)
-        host.edge_index[:et].copy_(host._d_eidx[:et], non_blocking=True)
+        if compact:
+            host._d_err.zero_()
+            N.check(N.lib.tchgeo_pack_transport(_ptr(samples[first]), samples.shape[1], _ptr(cols[first]),
+                                                _ptr(edge_index[first]), cols.shape[1], _ptr(host._d_lens),
+                                                _ptr(host._d_lens[host.B:]), count, int(cap_n), int(cap_e), _ptr(host._d_s32),
+                                                None if hybrid else _ptr(host._d_e32), _ptr(host._d_cnt), nt, _ptr(host._d_off),
+                                                _ptr(host._d_off[host.B + 1:]), _ptr(host._d_err), stream))
+            host._h_s32[:nt].copy_(host._d_s32[:nt], non_blocking=True)
+            host._h_cnt[:nt].copy_(host._d_cnt[:nt], non_blocking=True)
+            if hybrid:
+                N.check(N.lib.tchgeo_pack_ragged(_ptr(edge_index[first]), edge_index.shape[1], _ptr(host._d_lens[host.B:]), 1,
+                                                 count, int(cap_e), _ptr(host._d_eidx), _ptr(host._d_off[host.B + 1:]), stream))
+                host.edge_index[:et].copy_(host._d_eidx[:et], non_blocking=True)
+            else:
+                host._h_e32[:et].copy_(host._d_e32[:et], non_blocking=True)
+            host._h_err.copy_(host._d_err, non_blocking=True)
+            host._event.record(torch.cuda.current_stream(device))
+            host._pending = host._pool.submit(host._unpack, n_off, e_off, count)
+            host.nbytes = 5 * nt + (8 if hybrid else 4) * et + 4
+        else:
+            for src, lens_at, dst, off_at, cap in ((samples, 0, host._d_samples, 0, cap_n),
+                                                   (cols, host.B, host._d_cols, host.B + 1, cap_e),
+                                                   (edge_index, host.B, host._d_eidx, host.B + 1, cap_e)):
+                N.check(N.lib.tchgeo_pack_ragged(_ptr(src[first]), src.shape[1], _ptr(host._d_lens[lens_at:]), 1, count,
+                                                 int(cap), _ptr(dst), _ptr(host._d_off[off_at:]), stream))
+            host.samples[:nt].copy_(host._d_samples[:nt], non_blocking=True)
+            host.cols[:et].copy_(host._d_cols[:et], non_blocking=True)
+            host.edge_index[:et].copy_(host._d_eidx[:et], non_blocking=True)
+            host.nbytes = 8 * (nt + 2 * et)
     host.n_off, host.e_off = n_off, e_off
-    host.nbytes = 8 * (nt + 2 * et)
     return host.nbytes
 
 

@@ -27,7 +27,7 @@ def declared_symbols():
 
 def test_header_declares_the_expected_entry_points():
     syms = declared_symbols()
-    assert len(syms) == 55
+    assert len(syms) == 57
     for s in ("tchgeo_coo_to_csx", "tchgeo_neighbor_sampling", "tchgeo_neighbor_sampling_homogenous",
               "tchgeo_random_walk", "tchgeo_unique_relabel", "tchgeo_ind2ptr", "tchgeo_last_error"):
         assert s in syms

@@ -77,3 +77,48 @@ def test_packed_host_transfer_of_sampled_batches(thg):
             got = host.batch(i)
             for g, w in zip(got, want[:4]):
                 assert torch.equal(g, w.cpu())
+
+
+@pytest.mark.parametrize("transport,threads", [("compact", 1), ("compact", 3), ("hybrid", 2)])
+def test_compact_host_transport_lands_the_same_vectors(thg, transport, threads):
+    """transport="compact": i32 ids + u8 per-node edge counts on the bus, i64 vectors rebuilt by host threads
+    (tchgeo_pack_transport / tchgeo_host_unpack_transport) -- identical to the plain packed copy, batch by batch,
+    including batches whose nodes draw no edge and a temporal filter that thins the runs."""
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "fakedataset.npz"))
+    ei, n = torch.as_tensor(d["edge_index"]).cuda(), int(d["num_nodes"])
+    ptrs, idx, _ = thg.to_csc(ei, n)
+    B, S = 9, 40
+    seeds = torch.randint(0, n, (B, S), device="cuda")
+    ts = torch.randint(0, 100, (idx.numel(),), device="cuda")
+    flt = thg.TemporalEdgeFilter((0, 30), ts, True, thg.TEMPORAL_SAMPLE_STATIC)
+    for plan, kw in ((thg.HomogenousSampler(ptrs, idx, B, S, [7, 5, 3]), {}),
+                     (thg.HomogenousSampler(ptrs, idx, B, S, [7, 5], filter=flt),
+                      {"inputs_state": torch.zeros((B, S), dtype=torch.int64, device="cuda")})):
+        res = plan.sample(seeds, seed=5, **kw)
+        call = plan._call
+        host = thg.HostBatches(5, int(call.cap_n[0]), int(call.cap_e[0]), S, seeds.device, fill=1.0, transport=transport,
+                               threads=threads)
+        for first, count in ((0, 5), (5, 4), (2, 1)):
+            nbytes = res.to_host(host, first, count)
+            ns, ne = int(res.samples_len[first:first + count].sum()), int(res.edges_len[first:first + count].sum())
+            assert nbytes == 5 * ns + (8 if transport == "hybrid" else 4) * ne + 4
+            for i in range(count):
+                want = res.batch(first + i)
+                got = host.batch(i)
+                for g, w in zip(got, want[:4]):
+                    assert g.dtype == torch.int64 and torch.equal(g, w.cpu())
+
+
+def test_compact_host_transport_refuses_what_it_cannot_carry(thg):
+    import os
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "fakedataset.npz"))
+    ei, n = torch.as_tensor(d["edge_index"]).cuda(), int(d["num_nodes"])
+    ptrs, idx, _ = thg.to_csc(ei, n)
+    seeds = torch.randint(0, n, (2, 8), device="cuda")
+    plan = thg.HomogenousSampler(ptrs, idx, 2, 8, [300])
+    res = plan.sample(seeds, seed=1)
+    host = thg.HostBatches(2, int(plan._call.cap_n[0]), int(plan._call.cap_e[0]), 8, seeds.device, fill=1.0,
+                           transport="compact")
+    with pytest.raises(ValueError):
+        res.to_host(host)

@@ -205,3 +205,39 @@ def test_handles_and_partitioned_entries_validate_on_the_host():
     assert lib.tchgeo_partf_finish(None, None, 8, 5, None, 1, None, None, 1, 1, None, None, None, None, None, 0, None, None,
                                    None, 0, None, None, 0, None) == N.ERR_BAD_ARG
     assert lib.tchgeo_pack_ragged(None, 4, None, 1, 70000, 4, None, None, None) == N.ERR_BAD_ARG
+
+
+def test_host_unpack_transport_rebuilds_the_reference_vectors():
+    """tchgeo_host_unpack_transport is a pure host function: i32 -> i64 widening and run-length expansion of `cols`,
+    any thread count, unaligned destinations, empty batches; inconsistent counts are an error, not garbage."""
+    import ctypes
+    from tch_geometric import _native as N
+    rng = np.random.default_rng(0)
+    B = 23
+    nn = rng.integers(0, 3000, B)
+    nn[3] = 0
+    counts = [rng.integers(0, 16, n).astype(np.uint8) for n in nn]
+    ne = np.array([int(c.sum()) for c in counts])
+    n_off = np.concatenate([[0], np.cumsum(nn)]).astype(np.int64)
+    e_off = np.concatenate([[0], np.cumsum(ne)]).astype(np.int64)
+    s32 = rng.integers(0, 2**31 - 1, n_off[-1]).astype(np.int32)
+    e32 = rng.integers(0, 2**31 - 1, e_off[-1]).astype(np.int32)
+    cnt = np.concatenate(counts).astype(np.uint8)
+    want_cols = np.concatenate([np.repeat(np.arange(n), c) for n, c in zip(nn, counts)])
+    import os
+    for shift, simd in ((0, ""), (1, ""), (1, "sse2"), (3, "sse2")):   # aligned / merely 8-byte aligned destinations
+        os.environ["TCHGEO_HOST_SIMD"] = simd                          # "sse2": the path of CPUs without AVX-512
+        samples = np.zeros(n_off[-1] + 4, np.int64)[shift:shift + n_off[-1]]
+        cols = np.zeros(e_off[-1] + 4, np.int64)[shift:shift + e_off[-1]]
+        eidx = np.zeros(e_off[-1] + 4, np.int64)[shift:shift + e_off[-1]]
+        for threads in (1, 4, 64):
+            st = N.lib.tchgeo_host_unpack_transport(s32.ctypes.data, e32.ctypes.data, cnt.ctypes.data, n_off.ctypes.data,
+                                                    e_off.ctypes.data, B, samples.ctypes.data, cols.ctypes.data,
+                                                    eidx.ctypes.data, threads)
+            assert st == 0, N.last_error()
+            assert (samples == s32).all() and (eidx == e32).all() and (cols == want_cols).all()
+    os.environ.pop("TCHGEO_HOST_SIMD", None)
+    cnt[n_off[5]] += 1
+    st = N.lib.tchgeo_host_unpack_transport(s32.ctypes.data, e32.ctypes.data, cnt.ctypes.data, n_off.ctypes.data,
+                                            e_off.ctypes.data, B, samples.ctypes.data, cols.ctypes.data, eidx.ctypes.data, 2)
+    assert st == N.ERR_INTERNAL
