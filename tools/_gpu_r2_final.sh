@@ -5,10 +5,10 @@ O=gpurun_out/r2final; mkdir -p $O
 python -m pytest tests -m gpu -q > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -4 $O/gpu_tests.log
 python __graft_entry__.py smoke > $O/smoke.log 2>&1; tail -1 $O/smoke.log
 python bench.py --impl reference --steps 2 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
-python bench.py > $O/bench_default_1gpu.json 2> $O/bench_default_1gpu.err; echo "bench rc=$?"; cut -c1-200 $O/bench_default_1gpu.json
+T0=$(date +%s); python bench.py > $O/bench_default_1gpu.json 2> $O/bench_default_1gpu.err; echo "bench rc=$? wall $(( $(date +%s) - T0 )) s"; cut -c1-200 $O/bench_default_1gpu.json
 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/launch_list.csv python bench.py --steps 2 --warmup 1 --no-e2e --no-cpu > $O/ncu_launch.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:hop_kernel -s 2 -c 1 -o $O/r2_hop3 python bench.py --steps 1 --warmup 1 --no-e2e --no-cpu --headline-only > $O/ncu_hop3.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:bk_ -s 6 -c 6 -o $O/r2_relabel_bucketed python bench.py --workload relabel --steps 1 --warmup 1 > $O/ncu_relabel.log 2>&1
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:bk_ -s 7 -c 7 -o $O/r2_relabel_bucketed python bench.py --workload relabel --steps 1 --warmup 1 > $O/ncu_relabel.log 2>&1
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:pf_ -s 16 -c 4 -o $O/r2_partitioned_hop3 python bench.py --workload partitioned --steps 1 --warmup 2 --no-cpu --no-e2e > $O/ncu_part.log 2>&1
 python bench.py --workload walk --steps 5 --warmup 3 > $O/bench_walk.json 2> /dev/null
 python bench.py --workload hetero --steps 10 --warmup 3 > $O/bench_hetero.json 2> /dev/null
