@@ -483,7 +483,8 @@ def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, ca
     except AttributeError:
         ncpu = os.cpu_count() or 2
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-    threads = int(os.environ.get("TCHGEO_BENCH_THREADS", max(2, min(16, ncpu // (2 * max(local_world, 1))))))
+    # one group is rebuilt at a time (a single worker per process) with the rank's share of the host cores
+    threads = int(os.environ.get("TCHGEO_BENCH_THREADS", max(2, min(32, ncpu // max(local_world, 1)))))
     try:
         hosts = [[thg.HostBatches(HB, cap_n, cap_e, S, device, fill=0.8, transport=transport, threads=threads)
                   for _ in range(ring)] for _ in plans]

@@ -540,6 +540,18 @@ def host_arange(n: int) -> Tensor:
     return t
 
 
+_unpack_pool_cache = {}
+
+
+def _unpack_pool():
+    """ONE worker for every HostBatches of the process: groups are rebuilt one at a time, in arrival order, each with
+    all of the caller's threads (several groups at once would only share the same cores and memory channels)."""
+    import concurrent.futures
+    if "pool" not in _unpack_pool_cache:
+        _unpack_pool_cache["pool"] = concurrent.futures.ThreadPoolExecutor(max_workers=1, thread_name_prefix="tchgeo-unpack")
+    return _unpack_pool_cache["pool"]
+
+
 class HostBatches:
     """Host landing zone (+ its device staging buffers) for `SampledBatches.to_host`: the used prefixes of `samples`,
     `cols` and `edge_index` of a group of batches arrive packed back to back as int64 vectors.
@@ -572,9 +584,8 @@ class HostBatches:
             self.samples, self.cols, self.edge_index = host(self.cap_n), host(self.cap_e), host(self.cap_e)
             self._d_samples, self._d_cols, self._d_eidx = devb(self.cap_n), devb(self.cap_e), devb(self.cap_e)
             return
-        import concurrent.futures
         import os
-        self.threads = int(threads) if threads else max(1, min(16, (os.cpu_count() or 2) // 2))
+        self.threads = int(threads) if threads else max(1, min(32, (os.cpu_count() or 2) - 1))
         self.samples = torch.empty(self.cap_n, dtype=torch.int64)
         self.cols = torch.empty(self.cap_e, dtype=torch.int64)
         self._h_s32, self._h_cnt = host(self.cap_n, torch.int32), host(self.cap_n, torch.uint8)
@@ -587,7 +598,7 @@ class HostBatches:
             self._h_e32, self._d_e32 = host(self.cap_e, torch.int32), devb(self.cap_e, torch.int32)
         self._d_err, self._h_err = devb(1, torch.int32), host(1, torch.int32)
         self._event = torch.cuda.Event()
-        self._pool = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+        self._pool = _unpack_pool()
 
     def wait(self):
         """compact transport: block until the worker has rebuilt the last group's vectors (no-op otherwise)"""

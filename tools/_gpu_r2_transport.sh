@@ -1,7 +1,6 @@
 # gpurun (1 GPU): compact host transport -- parity tests, e2e with both transports
 O=gpurun_out/r2t; mkdir -p $O
 nproc > $O/host.txt; lscpu | grep -E "Model name|Socket|NUMA node|^CPU\(s\)|Thread" >> $O/host.txt; free -g | head -2 >> $O/host.txt; cat $O/host.txt
-python tools/host_unpack_bench.py > $O/host_unpack_bench.json; cat $O/host_unpack_bench.json
 python -m pytest tests -m gpu -x -q -k "gather or transport" > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -6 $O/gpu_tests.log
 timeout 600 python bench.py --headline-only --no-cpu --steps 10 --warmup 3 > $O/bench.json 2> $O/bench.err; tail -3 $O/bench.err
 python - <<'PY'
