@@ -16,6 +16,8 @@
 //   3. per relation: stable compaction of its accepted slots -> rows = i, cols = local id.
 // HBM-bound integer work (random row_ptrs / col_indices probes); no tensor cores.
 #include <cub/device/device_scan.cuh>
+#include <cub/iterator/counting_input_iterator.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
 
 #include <vector>
 
@@ -26,12 +28,12 @@
 
 namespace tchgeo {
 // csrc/relabel.cu: the batched dedup + relabel stage (device-side lengths, asynchronous)
-size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound);
+size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound, bool prefer_waves);
 bool relabel_is_bucketed(int64_t num_trees, int64_t n_max, int64_t id_bound);
 tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
                               int64_t num_seeds, int64_t n_max, int64_t id_bound, int64_t* nodes, int64_t* local,
                               int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool prefer_waves);
 namespace {
 
 constexpr int NEG_THREADS = 256;
@@ -102,34 +104,35 @@ __global__ void __launch_bounds__(NEG_THREADS) neg_draw_kernel(const NegDrawPara
   p.crel[g] = rel.rel;
 }
 
-// flags[g] = slot g was accepted and belongs to dst type `t` (by_type) / relation `t` (!by_type)
-__global__ void __launch_bounds__(NEG_THREADS) neg_flag_kernel(const int64_t* __restrict__ cand,
-                                                              const int32_t* __restrict__ crel,
-                                                              const int32_t* __restrict__ rel_dst, int64_t G, int t,
-                                                              int by_type, int* __restrict__ flags) {
-  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  const int r = crel[g];
-  flags[g] = (cand[g] >= 0 && (by_type ? rel_dst[r] : r) == t) ? 1 : 0;
-}
+// flag(g) = slot g was accepted and belongs to dst type `t` (by_type) / relation `t` (!by_type).  The scan reads it through
+// a transform iterator and the scatter kernels recompute it: no flag array, no flag kernel.
+struct NegFlag {
+  const int64_t* cand;
+  const int32_t* crel;
+  const int32_t* rel_dst;
+  int t, by_type;
+  __host__ __device__ __forceinline__ int operator()(int64_t g) const {
+    const int r = crel[g];
+    return (cand[g] >= 0 && (by_type ? rel_dst[r] : r) == t) ? 1 : 0;
+  }
+};
 
-__global__ void __launch_bounds__(NEG_THREADS) neg_scatter_type_kernel(const int64_t* __restrict__ cand,
-                                                                      const int* __restrict__ flags,
+__global__ void __launch_bounds__(NEG_THREADS) neg_scatter_type_kernel(const int64_t* __restrict__ cand, NegFlag flag,
                                                                       const int* __restrict__ ranks, int64_t G,
                                                                       int64_t* __restrict__ seq_tail,
                                                                       int* __restrict__ tpos, int64_t* total) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
-  if (flags[g]) {
+  const int f = flag(g);
+  if (f) {
     seq_tail[ranks[g]] = cand[g];
     tpos[g] = ranks[g];
   }
-  if (g == G - 1) *total = (int64_t)ranks[g] + flags[g];
+  if (g == G - 1) *total = (int64_t)ranks[g] + f;
 }
 
 // rows[e] = index of the input inside its type's inputs, cols[e] = local id of the accepted candidate
-__global__ void __launch_bounds__(NEG_THREADS) neg_scatter_rel_kernel(const int* __restrict__ flags,
-                                                                     const int* __restrict__ ranks,
+__global__ void __launch_bounds__(NEG_THREADS) neg_scatter_rel_kernel(NegFlag flag, const int* __restrict__ ranks,
                                                                      const int* __restrict__ tpos, int64_t g0,
                                                                      int64_t g1, int64_t G, int64_t num_neg,
                                                                      const int64_t* __restrict__ local_tail,
@@ -137,13 +140,17 @@ __global__ void __launch_bounds__(NEG_THREADS) neg_scatter_rel_kernel(const int*
                                                                      int64_t* __restrict__ cols, int64_t* total) {
   const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
-  if (flags[g] && g >= g0 && g < g1) {
+  const int f = flag(g);
+  if (f && g >= g0 && g < g1) {
     const int e = ranks[g];
     rows[e] = (g - g0) / num_neg;
     cols[e] = local_tail[tpos[g]];
   }
-  if (g == G - 1) *total = (int64_t)ranks[g] + flags[g];
+  if (g == G - 1) *total = (int64_t)ranks[g] + f;
 }
+
+using FlagIterator = cub::TransformInputIterator<int, NegFlag, cub::CountingInputIterator<int64_t>>;
+inline FlagIterator flag_iterator(const NegFlag& f) { return FlagIterator(cub::CountingInputIterator<int64_t>(0), f); }
 
 // len_out = num_seeds + accepted (accepted == NULL: nothing can be appended)
 __global__ void neg_len_kernel(const int64_t* accepted, int64_t num_seeds, int64_t* len_out) {
@@ -162,6 +169,7 @@ struct NegPlan {
   int64_t seq_total = 0, max_seq = 0;
   size_t cub_bytes = 0, rl_bytes = 0;
   std::vector<int64_t> id_bound;    // [T] what the relabel stage may assume about the type's ids (0: any i64)
+  bool prefer_waves = true;
   size_t off_cnts = 0;              // device counters: accepted[T] | seq_len[T] | nodes_len[T] | edges_len[R]
   size_t off_hdr, off_rels, off_rel_dst, off_cand, off_crel, off_tpos, off_flags, off_ranks, off_seq, off_local, off_cub,
       off_rl, total;
@@ -183,15 +191,17 @@ tchgeo_status neg_plan(const tchgeo_negative_args* a, NegPlan& P, bool layout = 
     TCHGEO_REQUIRE(a->node_count[r] >= 0 && a->node_count[r] < ((int64_t)1 << 32), "relation %d: size out of range", r);
   }
   // ids of type t: its inputs (checked against num_rows by the draw kernel when the type is the source of a relation)
-  // and the candidates drawn from [0, node_count) of the relations it is the destination of.  With a bound the relabel
-  // stage can use its direct-address buckets -- but that form is built for hundreds of trees per call: for the ONE tree
-  // of millions of ids here it measured 1.04 ms per call against 0.80 ms for the 64-bit wave form, which stays the
-  // default (TCHGEO_NEG_RELABEL=direct selects the buckets).
+  // and the candidates drawn from [0, node_count) of the relations it is the destination of.  With such a bound the
+  // relabel stage can use 32-bit keys; a type whose inputs nothing checks keeps 64-bit keys.  The call relabels ONE tree
+  // of millions of ids per node type, for which the wave form is the fast one (1 Mi inputs x 5 negatives: waves with
+  // 64-bit keys 1.12 ms per call, with 32-bit keys 0.96 ms, direct-address buckets -- built for hundreds of trees --
+  // 1.3 x the wave time).  TCHGEO_NEG_RELABEL=direct | waves64 select the other two.
   P.id_bound.assign(T, 0);
   {
     const char* f = getenv("TCHGEO_NEG_RELABEL");
-    const bool waves = !(f && strcmp(f, "direct") == 0);
-    for (int t = 0; t < T && !waves; ++t) {
+    P.prefer_waves = !(f && strcmp(f, "direct") == 0);
+    const bool waves64 = f && strcmp(f, "waves64") == 0;
+    for (int t = 0; t < T && !waves64; ++t) {
       int64_t bound = 0;
       bool is_src = false;
       for (int r = 0; r < R; ++r) {
@@ -228,14 +238,13 @@ tchgeo_status neg_plan(const tchgeo_negative_args* a, NegPlan& P, bool layout = 
   TCHGEO_REQUIRE(P.max_seq < ((int64_t)1 << 30), "sample list too long for one call");
   if (!layout) return TCHGEO_OK;  // capacities only: pure host arithmetic (the CUB size queries need a device)
   size_t cub = 0;
-  TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, cub, (const int*)nullptr, (int*)nullptr,
-                                                  (int64_t)(G > 0 ? G : 1)));
+  TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(nullptr, cub, flag_iterator(NegFlag{nullptr, nullptr, nullptr, 0, 0}),
+                                                  (int*)nullptr, (int64_t)(G > 0 ? G : 1)));
   P.cub_bytes = cub;
   P.rl_bytes = 0;
   for (int t = 0; t < T; ++t) {
-    // (one tree of millions of ids: only the bucketed form beats the 64-bit wave form here)
-    if (!relabel_is_bucketed(1, std::max<int64_t>(P.seq_cap[t], 1), P.id_bound[t])) P.id_bound[t] = 0;
-    const size_t need = relabel_workspace_bytes(1, std::max<int64_t>(P.seq_cap[t], 1), P.id_bound[t]);
+    if (!P.prefer_waves && !relabel_is_bucketed(1, std::max<int64_t>(P.seq_cap[t], 1), P.id_bound[t])) P.id_bound[t] = 0;
+    const size_t need = relabel_workspace_bytes(1, std::max<int64_t>(P.seq_cap[t], 1), P.id_bound[t], P.prefer_waves);
     TCHGEO_REQUIRE(need != 0, "relabel workspace query failed");
     P.rl_bytes = std::max(P.rl_bytes, need);
   }
@@ -295,7 +304,6 @@ extern "C" tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* a)
   int64_t* cand = (int64_t*)(ws + P.off_cand);
   int32_t* crel = (int32_t*)(ws + P.off_crel);
   int* tpos = (int*)(ws + P.off_tpos);
-  int* flags = (int*)(ws + P.off_flags);
   int* ranks = (int*)(ws + P.off_ranks);
   int64_t* seq = (int64_t*)(ws + P.off_seq);
   int64_t* local = (int64_t*)(ws + P.off_local);
@@ -366,11 +374,10 @@ extern "C" tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* a)
       TCHGEO_CUDA_CHECK(cudaMemcpyAsync(seq_t, a->inputs[t], (size_t)P.S[t] * 8, cudaMemcpyDeviceToDevice, stream));
     const bool grows = G > 0 && P.seq_cap[t] > P.S[t];
     if (grows) {
-      neg_flag_kernel<<<ggrid, NEG_THREADS, 0, stream>>>(cand, crel, d_rel_dst, G, t, 1, flags);
-      TCHGEO_CUDA_CHECK(cudaGetLastError());
+      const NegFlag flag{cand, crel, d_rel_dst, t, 1};
       size_t cub = P.cub_bytes;
-      TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws + P.off_cub, cub, (const int*)flags, ranks, G, stream));
-      neg_scatter_type_kernel<<<ggrid, NEG_THREADS, 0, stream>>>(cand, flags, ranks, G, seq_t + P.S[t], tpos, d_acc + t);
+      TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws + P.off_cub, cub, flag_iterator(flag), ranks, G, stream));
+      neg_scatter_type_kernel<<<ggrid, NEG_THREADS, 0, stream>>>(cand, flag, ranks, G, seq_t + P.S[t], tpos, d_acc + t);
       TCHGEO_CUDA_CHECK(cudaGetLastError());
     }
     neg_len_kernel<<<1, 1, 0, stream>>>(grows ? d_acc + t : nullptr, P.S[t], d_len + t);
@@ -378,7 +385,7 @@ extern "C" tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* a)
     if (P.seq_cap[t] == 0) continue;
     TCHGEO_REQUIRE(a->samples[t], "samples[%d] is NULL", t);
     st = relabel_enqueue(seq_t, P.seq_cap[t], d_len + t, 1, P.S[t], P.seq_cap[t], P.id_bound[t], a->samples[t], local_t, d_nodes + t,
-                         ws + P.off_rl, P.rl_bytes, d_err, stream);
+                         ws + P.off_rl, P.rl_bytes, d_err, stream, P.prefer_waves);
     if (st != TCHGEO_OK) return st;
   }
   // ---- 3. per relation: edges in generation order ----------------------------------------------------
@@ -386,11 +393,10 @@ extern "C" tchgeo_status tchgeo_negative_sampling(const tchgeo_negative_args* a)
     const int s = a->rel_src[r], t = a->rel_dst[r];
     if (P.S[s] == 0 || a->num_neg == 0) continue;
     TCHGEO_REQUIRE(a->rows[r] && a->cols[r], "rows/cols[%d] is NULL", r);
-    neg_flag_kernel<<<ggrid, NEG_THREADS, 0, stream>>>(cand, crel, d_rel_dst, G, r, 0, flags);
-    TCHGEO_CUDA_CHECK(cudaGetLastError());
+    const NegFlag flag{cand, crel, d_rel_dst, r, 0};
     size_t cub = P.cub_bytes;
-    TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws + P.off_cub, cub, (const int*)flags, ranks, G, stream));
-    neg_scatter_rel_kernel<<<ggrid, NEG_THREADS, 0, stream>>>(flags, ranks, tpos, P.slot_base[s],
+    TCHGEO_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(ws + P.off_cub, cub, flag_iterator(flag), ranks, G, stream));
+    neg_scatter_rel_kernel<<<ggrid, NEG_THREADS, 0, stream>>>(flag, ranks, tpos, P.slot_base[s],
                                                              P.slot_base[s] + P.S[s] * a->num_neg, G, a->num_neg,
                                                              local + P.seq_off[t] + P.S[t], a->rows[r], a->cols[r],
                                                              d_elen + r);

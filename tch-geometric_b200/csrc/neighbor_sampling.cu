@@ -1123,12 +1123,12 @@ extern "C" void tchgeo_graph_destroy(tchgeo_graph_t* g) {
 // ---- host-side plan: which launches, which version rows of the length table ------------------
 namespace tchgeo {
 // csrc/relabel.cu
-size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound);
+size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound, bool prefer_waves = false);
 int relabel_launches(int64_t num_trees, int64_t n_max, int64_t id_bound);
 tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
                               int64_t num_seeds, int64_t n_max, int64_t id_bound, int64_t* nodes, int64_t* local,
                               int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
-                              cudaStream_t stream);
+                              cudaStream_t stream, bool prefer_waves = false);
 namespace {
 
 struct Launch {

@@ -1549,9 +1549,9 @@ tchgeo_status rl_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
 //   selects the persistent global-table form instead (also the fallback for trees beyond ~6 M ids),
 //   TCHGEO_RELABEL_WAVES=1 the wave form.
 enum { FORM_WAVES = 0, FORM_PERSISTENT = 1, FORM_BUCKETED = 2 };
-static int relabel_form(int64_t num_trees, int64_t n_max, int64_t id_bound) {
+static int relabel_form(int64_t num_trees, int64_t n_max, int64_t id_bound, bool prefer_waves = false) {
   const char* w = getenv("TCHGEO_RELABEL_WAVES");
-  if (id_bound <= 0 || (w && atoi(w) != 0)) return FORM_WAVES;
+  if (id_bound <= 0 || prefer_waves || (w && atoi(w) != 0)) return FORM_WAVES;
   const char* pe = getenv("TCHGEO_RELABEL_PERSISTENT");
   BkLayout B;
   if (!(pe && atoi(pe) != 0) && bk_layout(num_trees, n_max, id_bound, B)) return FORM_BUCKETED;
@@ -1561,12 +1561,13 @@ static int relabel_form(int64_t num_trees, int64_t n_max, int64_t id_bound) {
 bool relabel_is_bucketed(int64_t num_trees, int64_t n_max, int64_t id_bound) {
   return id_bound > 0 && id_bound <= 0xFFFFFFFFll && relabel_form(num_trees, n_max, id_bound) == FORM_BUCKETED;
 }
-size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound) {
+// prefer_waves: the caller has ONE big tree (negative sampling): the wave form, with 8-byte slots when id_bound != 0
+size_t relabel_workspace_bytes(int64_t num_trees, int64_t n_max, int64_t id_bound, bool prefer_waves) {
   if (id_bound < 0 || id_bound > 0xFFFFFFFFll) return 0;
   const bool k32 = id_bound != 0;
   RlLayout L;
   if (!rl_layout(num_trees, n_max, k32, L)) return 0;
-  const int form = relabel_form(num_trees, n_max, id_bound);
+  const int form = relabel_form(num_trees, n_max, id_bound, prefer_waves);
   if (form == FORM_BUCKETED) {
     BkLayout B;
     bk_layout(num_trees, n_max, id_bound, B);
@@ -1589,14 +1590,15 @@ int relabel_launches(int64_t num_trees, int64_t n_max, int64_t id_bound) {
 tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int64_t* lens, int64_t num_trees,
                               int64_t num_seeds, int64_t n_max, int64_t id_bound, int64_t* nodes, int64_t* local,
                               int64_t* nodes_len, void* workspace, size_t workspace_bytes, uint32_t* err,
-                              cudaStream_t stream) {
+                              cudaStream_t stream, bool prefer_waves) {
   TCHGEO_REQUIRE(id_bound >= 0 && id_bound <= 0xFFFFFFFFll, "relabel: id_bound must be 0 (any i64) or at most 2^32-1");
   const bool k32 = id_bound != 0;
   RlLayout L;
   TCHGEO_REQUIRE(rl_layout(num_trees, n_max, k32, L), "relabel: tree too large");
-  TCHGEO_REQUIRE(workspace && workspace_bytes >= relabel_workspace_bytes(num_trees, n_max, id_bound),
-                 "relabel: workspace too small (need %zu bytes)", relabel_workspace_bytes(num_trees, n_max, id_bound));
-  const int form = relabel_form(num_trees, n_max, id_bound);
+  TCHGEO_REQUIRE(workspace && workspace_bytes >= relabel_workspace_bytes(num_trees, n_max, id_bound, prefer_waves),
+                 "relabel: workspace too small (need %zu bytes)",
+                 relabel_workspace_bytes(num_trees, n_max, id_bound, prefer_waves));
+  const int form = relabel_form(num_trees, n_max, id_bound, prefer_waves);
   if (form == FORM_BUCKETED) {
     BkLayout B;
     bk_layout(num_trees, n_max, id_bound, B);
@@ -1621,7 +1623,7 @@ tchgeo_status relabel_enqueue(const int64_t* samples, int64_t stride, const int6
 using namespace tchgeo;
 
 extern "C" size_t tchgeo_unique_relabel_batched_workspace_bytes(int64_t num_batches, int64_t n_max, int64_t id_bound) {
-  return relabel_workspace_bytes(num_batches, n_max, id_bound);
+  return relabel_workspace_bytes(num_batches, n_max, id_bound, false);
 }
 
 extern "C" tchgeo_status tchgeo_unique_relabel_batched(const int64_t* samples, int64_t stride, const int64_t* lens,
@@ -1634,12 +1636,12 @@ extern "C" tchgeo_status tchgeo_unique_relabel_batched(const int64_t* samples, i
   if (num_batches == 0) return TCHGEO_OK;
   TCHGEO_REQUIRE(samples && lens && nodes && local && nodes_len && err_word, "NULL pointer");
   return relabel_enqueue(samples, stride, lens, num_batches, num_seeds, n_max, id_bound, nodes, local, nodes_len, workspace,
-                         workspace_bytes, (uint32_t*)err_word, (cudaStream_t)stream_);
+                         workspace_bytes, (uint32_t*)err_word, (cudaStream_t)stream_, false);
 }
 
 extern "C" size_t tchgeo_unique_relabel_workspace_bytes(int64_t n) {
   if (n < 0 || n >= ((int64_t)1 << 30)) return 0;
-  return relabel_workspace_bytes(1, n, 0);
+  return relabel_workspace_bytes(1, n, 0, false);
 }
 
 // One tree (the B = 1 case of the batched stage, any i64 ids), synchronous: returns the number of nodes.
