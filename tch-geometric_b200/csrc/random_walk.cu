@@ -20,6 +20,9 @@
 // the optional int32 replica (100 ms -> 63 ms for 24.5 M walkers x 80 steps).
 #include <cstdlib>
 
+#include <cstdlib>
+#include <cstring>
+
 #include "common.cuh"
 #include "graph.cuh"
 
@@ -262,6 +265,159 @@ __global__ void __launch_bounds__(TEMPO_THREADS) tempo_walk_kernel(const TempoPa
   }
 }
 
+
+// ---- thread-per-walker form (the default) ------------------------------------------------------------------------------
+// The warp-per-walker kernel above issues ~200 warp instructions per step for a 25-neighbour node (one Philox evaluation
+// per 32-neighbour chunk, ballots, a warp max): 12.7 G warp instructions, 59 % issue utilisation, 1.3 TB/s of DRAM for the
+// products-shaped graph -- instruction-bound.  Here every THREAD owns a walker and walks its current node's adjacency
+// serially: the reservoir becomes "overwrite on a hit" (the last hit wins by construction), one Philox evaluation serves
+// four consecutive passing positions, and an instruction serves 32 walkers.  A walker standing on a node with more than
+// TEMPO_LIGHT neighbours is handed to the whole warp (the chunked scan of the kernel above), one such walker at a time.
+// Same draws, same results, bit for bit.
+constexpr int TEMPO_LIGHT = 96;
+
+struct TempoPick {
+  int64_t node, ts;
+  uint32_t npass;
+};
+
+// the warp scans [b, e) for the walker of lane `src` (all its parameters are broadcast from that lane)
+__device__ __noinline__ TempoPick tempo_scan_warp(const TempoParams& p, int lane, int64_t b, int64_t e, int64_t i_ts,
+                                                     int64_t lo_w, int64_t hi_w, uint32_t wlo, uint32_t whi, uint32_t l,
+                                                     bool& bad) {
+  uint32_t npass = 0, best = 0;
+  bool has_first = false;
+  int64_t best_node = -1, best_ts = -1, first_node = -1, first_ts = -1;
+  for (int64_t base = b; base < e; base += 32) {
+    const int64_t ep = base + lane;
+    bool pass = false;
+    int64_t node = -1, ts = -1;
+    if (ep < e) {
+      node = __ldg(p.col_indices + ep);
+      ts = __ldg(p.edge_ts + ep);
+      if (ts == -1) {
+        if (node < 0 || node >= p.num_node_ts) bad = true;
+        else ts = __ldg(p.node_ts + node);
+      }
+      pass = ts == -1 || i_ts == -1 || (lo_w <= ts && ts < hi_w);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, pass);
+    if (pass) {
+      const uint32_t pos = npass + (uint32_t)__popc(m & ((1u << lane) - 1u));
+      if (pos == 0) {
+        has_first = true; first_node = node; first_ts = ts;
+      } else {
+        const Philox4 r = philox4x32_10(wlo, whi, l, TAG_TEMPO | ((pos >> 2) << 8), p.key0, p.key1);
+        if (__umulhi(pick4(r, pos & 3u), pos) == 0u) { best = pos; best_node = node; best_ts = ts; }
+      }
+    }
+    npass += (uint32_t)__popc(m);
+  }
+  TempoPick out{-1, -1, npass};
+  if (npass > 0) {
+    uint32_t top = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) top = max(top, __shfl_xor_sync(0xffffffffu, top, o));
+    const uint32_t om = __ballot_sync(0xffffffffu, top ? (best == top) : has_first);
+    const int from = __ffs(om) - 1;
+    out.node = __shfl_sync(0xffffffffu, top ? best_node : first_node, from);
+    out.ts = __shfl_sync(0xffffffffu, top ? best_ts : first_ts, from);
+  }
+  return out;
+}
+
+__global__ void __launch_bounds__(TEMPO_THREADS, 4) tempo_walk_thread_kernel(const TempoParams p) {
+  const int lane = threadIdx.x & 31;
+  const int64_t i = (int64_t)blockIdx.x * TEMPO_THREADS + threadIdx.x;
+  const bool mine = i < p.num_walks;            // (idle lanes of the last warp still help with the hubs)
+  const uint64_t walker = (uint64_t)(p.walker_base + (mine ? i : 0));
+  const uint32_t wlo = (uint32_t)walker, whi = (uint32_t)(walker >> 32);
+  int64_t* row = p.walks + (mine ? i : 0) * p.L;
+  int64_t* row_ts = p.walks_ts + (mine ? i : 0) * p.L;
+  int64_t cur = mine ? p.start[i] : -1;
+  const int64_t i_ts = mine ? p.start_ts[i] : 0;
+  const int64_t lo_w = i_ts + p.w0, hi_w = i_ts + p.w1;  // Range: lo_w <= t < hi_w
+  if (mine) { row[0] = cur; row_ts[0] = i_ts; }
+  bool dead = !mine, bad = false;
+  for (int64_t l = 0; l + 1 < p.L; ++l) {
+    int64_t next = -1, next_ts = -1, b = 0, e = 0;
+    uint32_t npass = 0;
+    if (!dead && (cur < 0 || cur >= p.num_rows)) {  // neighbors_range(cur) out of bounds: the reference panics
+      bad = true;
+      dead = true;
+    }
+    if (!dead) {
+      b = __ldg(p.row_ptrs + cur);
+      e = __ldg(p.row_ptrs + cur + 1);
+    }
+    const bool heavy = !dead && e - b > TEMPO_LIGHT;
+    if (!dead && !heavy) {
+      Philox4 r{0u, 0u, 0u, 0u};
+      uint32_t rblk = 0xFFFFFFFFu;
+      // four neighbours' ids and timestamps are loaded before the first is looked at: the loop is otherwise one DRAM
+      // latency per neighbour and thread
+      for (int64_t ep0 = b; ep0 < e; ep0 += 4) {
+        int64_t nd[4], tt[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool in = ep0 + u < e;
+          nd[u] = in ? __ldg(p.col_indices + ep0 + u) : -1;
+          tt[u] = in ? __ldg(p.edge_ts + ep0 + u) : 0;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          if (ep0 + u >= e) break;
+          const int64_t node = nd[u];
+          int64_t ts = tt[u];
+          if (ts == -1) {  // NAN_TIMESTAMP: fall back to the neighbour's own timestamp, :118-122
+            if (node < 0 || node >= p.num_node_ts) bad = true;
+            else ts = __ldg(p.node_ts + node);
+          }
+          if (!(ts == -1 || i_ts == -1 || (lo_w <= ts && ts < hi_w))) continue;
+          const uint32_t pos = npass++;
+          if (pos == 0) {
+            next = node; next_ts = ts;
+          } else {
+            if ((pos >> 2) != rblk) {
+              rblk = pos >> 2;
+              r = philox4x32_10(wlo, whi, (uint32_t)l, TAG_TEMPO | (rblk << 8), p.key0, p.key1);
+            }
+            if (__umulhi(pick4(r, pos & 3u), pos) == 0u) { next = node; next_ts = ts; }   // a later hit replaces the pick
+          }
+        }
+      }
+    }
+    // hubs: the warp scans them together, one walker at a time
+    uint32_t hm = __ballot_sync(0xffffffffu, heavy);
+    while (hm) {
+      const int src = __ffs(hm) - 1;
+      hm &= hm - 1;
+      bool wbad = false;
+      const TempoPick pk = tempo_scan_warp(p, lane, __shfl_sync(0xffffffffu, b, src), __shfl_sync(0xffffffffu, e, src),
+                                           __shfl_sync(0xffffffffu, i_ts, src), __shfl_sync(0xffffffffu, lo_w, src),
+                                           __shfl_sync(0xffffffffu, hi_w, src), __shfl_sync(0xffffffffu, wlo, src),
+                                           __shfl_sync(0xffffffffu, whi, src), (uint32_t)l, wbad);
+      bad |= wbad;
+      if (lane == src) { next = pk.node; next_ts = pk.ts; npass = pk.npass; }
+    }
+    if (!dead) {
+      if (npass >= (1u << 24)) {
+        bad = true;
+        dead = true;
+      } else if (npass == 0) {
+        // restart: a uniformly drawn earlier position of this walk (the thread re-reads what it wrote), :140-144
+        const Philox4 r = philox4x32_10(wlo, whi, (uint32_t)l, TAG_TEMPO_RESTART, p.key0, p.key1);
+        const int64_t ri = (int64_t)__umulhi(r.x, (uint32_t)(l + 1));
+        next = row[ri]; next_ts = row_ts[ri];
+      }
+    }
+    if (dead) { next = -1; next_ts = -1; }
+    cur = next;
+    if (mine) { row[l + 1] = cur; row_ts[l + 1] = next_ts; }
+  }
+  if (bad) atomicOr(p.err, DEV_ERR_INDEX);
+}
+
 }  // namespace
 }  // namespace tchgeo
 
@@ -375,9 +531,16 @@ extern "C" tchgeo_status tchgeo_tempo_random_walk(const int64_t* row_ptrs, int64
   tp.key0 = (uint32_t)seed; tp.key1 = (uint32_t)(seed >> 32);
   cudaStream_t stream = (cudaStream_t)stream_;
   TCHGEO_CUDA_CHECK(cudaMemsetAsync(scratch, 0, 4, stream));
-  const int64_t grid = (num_walks * 32 + TEMPO_THREADS - 1) / TEMPO_THREADS;
-  TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many walkers for one launch");
-  tempo_walk_kernel<<<(unsigned)grid, TEMPO_THREADS, 0, stream>>>(tp);
+  const char* form = getenv("TCHGEO_TEMPO_WALK");   // "warp": the warp-per-walker kernel (kept for comparison)
+  if (form && strcmp(form, "warp") == 0) {
+    const int64_t grid = (num_walks * 32 + TEMPO_THREADS - 1) / TEMPO_THREADS;
+    TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many walkers for one launch");
+    tempo_walk_kernel<<<(unsigned)grid, TEMPO_THREADS, 0, stream>>>(tp);
+  } else {
+    const int64_t grid = (num_walks + TEMPO_THREADS - 1) / TEMPO_THREADS;
+    TCHGEO_REQUIRE(grid < ((int64_t)1 << 31), "too many walkers for one launch");
+    tempo_walk_thread_kernel<<<(unsigned)grid, TEMPO_THREADS, 0, stream>>>(tp);
+  }
   TCHGEO_CUDA_CHECK(cudaGetLastError());
   uint32_t h = 0;
   TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&h, scratch, 4, cudaMemcpyDeviceToHost, stream));

@@ -58,6 +58,25 @@ def test_fakedataset_heavy_rows_and_sharding(thg, fakedataset):
     assert (np.concatenate([p[1] for p in parts]) == full[1]).all()
 
 
+def test_warp_per_walker_form_gives_the_same_walks(thg, fakedataset, monkeypatch):
+    """The default kernel walks one walker per thread (hubs go to the whole warp); TCHGEO_TEMPO_WALK=warp selects the
+    warp-per-walker kernel.  Same draws, same walks -- including walkers on a 300-neighbour hub and on isolated nodes."""
+    ei, n = fakedataset
+    rng = np.random.default_rng(8)
+    hub = np.stack([np.full(300, 3, dtype=np.int64), rng.choice(n, 300, replace=False)])
+    rp, ci, perm = O.to_csr(np.concatenate([ei, hub], axis=1), n + 2)     # nodes n, n+1 have no neighbours
+    ets = rng.integers(-1, 40, ci.size)
+    nts = rng.integers(-1, 40, n + 2)
+    start = np.concatenate([np.full(70, 3, dtype=np.int64), np.arange(n + 2)])
+    sts = rng.integers(-1, 40, start.size)
+    a = run(thg, rp, ci, nts, ets, start, sts, 11, (0, 15), seed=5)
+    monkeypatch.setenv("TCHGEO_TEMPO_WALK", "warp")
+    b = run(thg, rp, ci, nts, ets, start, sts, 11, (0, 15), seed=5)
+    want = O.tempo_random_walk(rp, ci, nts, ets, start, sts, 11, (0, 15), seed=5)
+    for x, y, w in zip(a, b, want):
+        assert (x == y).all() and (x == w).all()
+
+
 def test_distribution_vs_sequential_oracle(thg, karate):
     rp, ci, nts, ets, n = karate_temporal(karate, seed=2)
     start = np.tile(np.arange(n), 300)

@@ -1,9 +1,10 @@
-# gpurun (1 GPU): negative sampling after the flag kernel went into the scan's input iterator; 32-bit wave tables by default
+# gpurun (1 GPU): tempo_random_walk, thread-per-walker kernel vs warp-per-walker kernel
 O=gpurun_out/r2misc; mkdir -p $O
-python -m pytest tests -m gpu -x -q -k "negative or relabel or smoke" > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -4 $O/gpu_tests.log
-for cfg in "default: " "waves64:TCHGEO_NEG_RELABEL=waves64"; do
-  name=${cfg%%:*}; envs=${cfg#*:}
-  env $envs python bench.py --workload negative --steps 10 --warmup 3 > $O/bench_negative_$name.json 2> $O/bench_negative_$name.err
-  python -c "
-import json; d=json.load(open('$O/bench_negative_$name.json')); print('$name: %.3f ms/call, %.2f G negatives/s, frac %.3f' % (d['ms_per_step'], d['value']/1e9, d['roofline']['frac']))"
+python -m pytest tests -m gpu -x -q -k "tempo" > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -4 $O/gpu_tests.log
+for form in thread warp; do
+TCHGEO_TEMPO_WALK=$form python bench.py --workload tempo_walk --steps 5 --warmup 3 --no-cpu > $O/bench_tempo_walk_$form.json 2> $O/bench_tempo_walk_$form.err
+python -c "
+import json; d=json.load(open('$O/bench_tempo_walk_$form.json')); print('$form: %.3f ms/step, %.3f G/s, frac %.3f' % (d['ms_per_step'], d['value']/1e9, d['roofline']['frac']))"
 done
+timeout 300 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,sm__warps_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct,l1tex__t_sector_hit_rate.pct --clock-control none -k regex:tempo_walk -s 1 -c 1 --csv --log-file $O/tempo_walk_thread_ncu.csv python bench.py --workload tempo_walk --steps 1 --warmup 1 --no-cpu > $O/ncu.log 2>&1
+grep -E "tempo_walk" $O/tempo_walk_thread_ncu.csv | awk -F'","' '{print $13, $14, $15}' | tail -8
