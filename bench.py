@@ -590,8 +590,9 @@ def run_relabel(thg, ptrs, idx, dev_seeds, sampler, B, S, K, W, world, rank, dev
            "hops_ms_per_step": float(ms[:-1].sum()) / K, "relabel_ms_per_step": rl_ms / K,
            "ids_per_step": n_samples / K, "distinct_nodes_per_step": n_nodes / K,
            "what": "sum of the per-launch CUDA-event intervals of one plan (hop kernels + relabel stage)",
-           "roofline": {"bound": "hbm", "kernel": "relabel stage (csrc/relabel.cu, bucketed form): bk_count / bk_offsets / "
-                        "bk_scatter / bk_resolve_direct / bk_compact / bk_lookup over all batches of the step", "achieved": alg / (rl_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+           "roofline": {"bound": "hbm", "kernel": "relabel stage (csrc/relabel.cu, bucketed form, direct-address tables): bk_count / "
+                        "bk_tilescan / bk_offsets / bk_scatter_staged / bk_resolve_direct / bk_compact / bk_lookup over all "
+                        "batches of the step", "achieved": alg / (rl_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                         "frac": alg / (rl_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                         "algorithmic_bytes_per_step": alg / K,
                         "byte_model": "16 B per id (8 read + 8 local written) + 8 B per distinct node"},
