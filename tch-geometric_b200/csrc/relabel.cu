@@ -797,7 +797,9 @@ struct BkParams {
   uint32_t* counts;    // [trees, nb] ids per bucket
   uint32_t* offs;      // [trees, nb] exclusive offsets inside the tree's pair region
   uint32_t* tile_hist; // [trees, tiles_per_tree, nb] ids of tile t in bucket j, then (bk_tilescan_kernel) the ids of the
-                       // bucket in earlier tiles: the scatter needs no atomic cursor
+                       // bucket in earlier tiles OF THE SAME SEGMENT of tiles: the scatter needs no atomic cursor
+  uint32_t* seg_tot;   // [trees, segs, nb] ids of the bucket in the segment, then (bk_offsets_kernel) in earlier segments
+  int32_t segs, tiles_per_seg;   // the tile scan runs per segment of tiles_per_seg tiles (parallelism for few, long trees)
   void* pairs;         // [trees, n_max] uint2 (id, position) or packed uint32, grouped by bucket
   uint32_t* win;       // [trees, n_max] position the map entry of samples[i] points at (BK_NONE: id out of range)
   uint64_t* status;    // [trees, ctiles] look-back words of the compact kernel (zero)
@@ -847,17 +849,18 @@ __global__ void __launch_bounds__(BK_THREADS) bk_count_kernel(const BkParams p) 
   for (int j = tid; j < p.nb; j += BK_THREADS) row[j] = s_hist[j];
 }
 
-// ---- tile scan: per (tree, bucket) the exclusive prefix over the tree's tiles, and the bucket's total ------------------
+// ---- tile scan: per (tree, segment of tiles, bucket) the exclusive prefix over the segment's tiles and its total ---------
 __global__ void __launch_bounds__(256) bk_tilescan_kernel(const BkParams p) {
-  const int b = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
+  const int b = blockIdx.z, sg = blockIdx.y, j = blockIdx.x * 256 + threadIdx.x;
   if (j >= p.nb) return;
   const int64_t n = bk_len(p, b);
   const int nt = (int)((n + BK_TILE - 1) / BK_TILE);
+  int t = sg * p.tiles_per_seg;
+  const int t1 = min(t + p.tiles_per_seg, nt);
   uint32_t* col = p.tile_hist + (size_t)b * p.tiles_per_tree * p.nb + j;
   uint32_t run = 0u;
-  int t = 0;
   constexpr int V = 8;
-  for (; t + V <= nt; t += V) {
+  for (; t + V <= t1; t += V) {
     uint32_t c[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) c[v] = __ldcg(col + (size_t)(t + v) * p.nb);
@@ -867,15 +870,15 @@ __global__ void __launch_bounds__(256) bk_tilescan_kernel(const BkParams p) {
       run += c[v];
     }
   }
-  for (; t < nt; ++t) {
+  for (; t < t1; ++t) {
     const uint32_t c = __ldcg(col + (size_t)t * p.nb);
     col[(size_t)t * p.nb] = run;
     run += c;
   }
-  p.counts[(size_t)b * p.nb + j] = run;
+  p.seg_tot[((size_t)b * p.segs + sg) * p.nb + j] = run;
 }
 
-// ---- offsets: exclusive scan of every tree's bucket counts (one CTA per tree; nb <= 4096) ----------------------------
+// ---- offsets: bucket counts from the segment totals, then their exclusive scan (one CTA per tree; nb <= 4096) ----------
 __global__ void __launch_bounds__(256) bk_offsets_kernel(const BkParams p) {
   __shared__ uint32_t s_wtot[8];
   __shared__ uint32_t s_carry;
@@ -884,7 +887,16 @@ __global__ void __launch_bounds__(256) bk_offsets_kernel(const BkParams p) {
   __syncthreads();
   for (int j0 = 0; j0 < p.nb; j0 += 256) {
     const int j = j0 + tid;
-    const uint32_t v = j < p.nb ? p.counts[(size_t)b * p.nb + j] : 0u;
+    uint32_t v = 0u;
+    if (j < p.nb) {      // segment totals -> ids of the bucket in earlier segments; their sum is the bucket's count
+      uint32_t* sg = p.seg_tot + (size_t)b * p.segs * p.nb + j;
+      for (int q = 0; q < p.segs; ++q) {
+        const uint32_t c = sg[(size_t)q * p.nb];
+        sg[(size_t)q * p.nb] = v;
+        v += c;
+      }
+      p.counts[(size_t)b * p.nb + j] = v;
+    }
     uint32_t incl = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -941,7 +953,9 @@ __global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p
   }
   __syncthreads();
   const uint32_t* row = p.tile_hist + ((size_t)b * p.tiles_per_tree + blockIdx.x) * p.nb;
-  for (int j = tid; j < p.nb; j += BK_THREADS) s_hist[j] = p.offs[(size_t)b * p.nb + j] + row[j];
+  const uint32_t* seg = p.seg_tot + ((size_t)b * p.segs + blockIdx.x / p.tiles_per_seg) * p.nb;
+  for (int j = tid; j < p.nb; j += BK_THREADS)
+    s_hist[j] = p.offs[(size_t)b * p.nb + j] + (p.segs > 1 ? seg[j] : 0u) + row[j];
   __syncthreads();
 #pragma unroll
   for (int u = 0; u < BK_ITEMS; ++u) {
@@ -971,10 +985,12 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter_staged_kernel(const 
   const int64_t i0 = (int64_t)blockIdx.x * BK_TILE;
   if (i0 >= n) return;
   const uint32_t* row = p.tile_hist + ((size_t)b * p.tiles_per_tree + blockIdx.x) * p.nb;
+  const uint32_t* seg = p.seg_tot + ((size_t)b * p.segs + blockIdx.x / p.tiles_per_seg) * p.nb;
   const uint32_t* offs = p.offs + (size_t)b * p.nb;
   for (int j = tid; j < p.nb; j += BK_THREADS) {
     s_start[j] = 0u;
     asm volatile("prefetch.global.L2 [%0];" ::"l"(row + j));   // wanted after the scan, two barriers from here
+    if (p.segs > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(seg + j));
     asm volatile("prefetch.global.L2 [%0];" ::"l"(offs + j));
   }
   if (tid < 32) s_wsum[tid] = 0u;
@@ -1040,7 +1056,7 @@ __global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter_staged_kernel(const 
     if (j >= p.nb) break;
     const uint32_t c = s_start[j];
     s_start[j] = excl;
-    s_base[j] = __ldcg(offs + j) + __ldcg(row + j) - excl;
+    s_base[j] = __ldcg(offs + j) + (p.segs > 1 ? __ldcg(seg + j) : 0u) + __ldcg(row + j) - excl;
     excl += c;
   }
   __syncthreads();
@@ -1338,10 +1354,10 @@ __global__ void __launch_bounds__(RL_THREADS) bk_lookup_kernel(const BkParams p)
 
 struct BkLayout {
   int nb, log2_nb, tiles_per_tree, ctiles;
-  int mode, pos_bits, slots;
+  int mode, pos_bits, slots, segs, tiles_per_seg;
   uint32_t id_bound;
   size_t off_zero, zero_bytes;   // status | ticket: one memset
-  size_t off_counts, off_status, off_ticket, off_offs, off_tile_hist, off_pairs, off_win, total;
+  size_t off_counts, off_status, off_ticket, off_offs, off_tile_hist, off_seg_tot, off_pairs, off_win, total;
 };
 
 inline int bk_bits(uint64_t n) {   // bits needed for values in [0, n)
@@ -1390,6 +1406,14 @@ bool bk_layout(int64_t num_trees, int64_t n_max, int64_t id_bound, BkLayout& L) 
   L.off_counts = o; o += rl_align(tb);
   L.off_offs = o; o += rl_align(tb);
   L.off_tile_hist = o; o += rl_align((size_t)num_trees * L.tiles_per_tree * (size_t)nb * 4);   // depends on the bound
+  // segments of the tile scan: only for few, long trees (one tree of 6 M ids: 16 CTAs walking 1500 tiles each took longer
+  // than the rest of the stage).  With hundreds of trees one segment is best: 8 segments measured 0.29 ms against 0.22 ms
+  // (more rows of the histogram matrix open at once), plus the extra pass over the segment totals.
+  const int64_t ctas = (int64_t)((nb + 255) / 256) * num_trees;
+  L.segs = ctas >= 1024 ? 1 : (int)std::min<int64_t>((2048 + ctas - 1) / ctas, std::min<int64_t>(64, L.tiles_per_tree));
+  L.tiles_per_seg = (L.tiles_per_tree + L.segs - 1) / L.segs;
+  L.segs = (L.tiles_per_tree + L.tiles_per_seg - 1) / L.tiles_per_seg;
+  L.off_seg_tot = o; o += rl_align((size_t)num_trees * L.segs * (size_t)nb * 4);
   L.off_pairs = o; o += rl_align(nn * 8);
   L.off_win = o; o += rl_align(nn * 4);
   L.total = o + 256;
@@ -1405,6 +1429,7 @@ tchgeo_status bk_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
   p.nb = L.nb; p.log2_nb = L.log2_nb; p.tiles_per_tree = L.tiles_per_tree; p.ctiles = L.ctiles;
   p.id_bound = L.id_bound; p.pos_bits = L.pos_bits; p.slots = L.slots;
   p.counts = (uint32_t*)(ws + L.off_counts); p.tile_hist = (uint32_t*)(ws + L.off_tile_hist);
+  p.seg_tot = (uint32_t*)(ws + L.off_seg_tot); p.segs = L.segs; p.tiles_per_seg = L.tiles_per_seg;
   p.offs = (uint32_t*)(ws + L.off_offs); p.pairs = (void*)(ws + L.off_pairs);
   p.win = (uint32_t*)(ws + L.off_win);
   p.status = (uint64_t*)(ws + L.off_status); p.ticket = (uint32_t*)(ws + L.off_ticket);
@@ -1417,7 +1442,7 @@ tchgeo_status bk_enqueue(const int64_t* samples, int64_t stride, const int64_t* 
     default: bk_count_kernel<BK_HASHED><<<tiles, BK_THREADS, 0, stream>>>(p); break;
   }
   TCHGEO_CUDA_CHECK(cudaGetLastError());
-  bk_tilescan_kernel<<<dim3((unsigned)((L.nb + 255) / 256), (unsigned)num_trees), 256, 0, stream>>>(p);
+  bk_tilescan_kernel<<<dim3((unsigned)((L.nb + 255) / 256), (unsigned)L.segs, (unsigned)num_trees), 256, 0, stream>>>(p);
   TCHGEO_CUDA_CHECK(cudaGetLastError());
   bk_offsets_kernel<<<(unsigned)num_trees, 256, 0, stream>>>(p);
   TCHGEO_CUDA_CHECK(cudaGetLastError());

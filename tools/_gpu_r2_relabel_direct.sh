@@ -15,3 +15,8 @@ hdr=rows[0]; i={h:k for k,h in enumerate(hdr)}
 for r in rows[1:]:
     print(r[i['Kernel Name']][:48], r[i['Metric Name']], r[i['Metric Value']], r[i['Metric Unit']])
 PY
+for form in direct waves; do
+  TCHGEO_NEG_RELABEL=$form python bench.py --workload negative --steps 10 --warmup 3 > $O/bench_negative_$form.json 2> $O/bench_negative_$form.err
+  python -c "
+import json; d=json.load(open('$O/bench_negative_$form.json')); print('negative, relabel $form: %.3f ms/call, %.2f G negatives/s' % (d['ms_per_step'], d['value']/1e9))"
+done
