@@ -407,6 +407,7 @@ def run_ours(args):
         # every transport of SampledBatches.to_host is timed; the line's e2e is the fastest one on this box, the others
         # are kept beside it (which wins depends on the host: PCIe rate against the rate its cores write memory at)
         runs = {}
+        # ("mixed" -- 3 compact groups : 1 plain -- measured between compact and hybrid on the 1-GPU box; on request only)
         for tr in (["plain", "compact", "hybrid"] if args.e2e_transport == "all" else [args.e2e_transport]):
             try:
                 runs[tr] = run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, cap_n, cap_e, barrier,
@@ -485,9 +486,12 @@ def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, ca
     local_world = int(os.environ.get("LOCAL_WORLD_SIZE", world))
     # one group is rebuilt at a time (a single worker per process) with the rank's share of the host cores
     threads = int(os.environ.get("TCHGEO_BENCH_THREADS", max(2, min(32, ncpu // max(local_world, 1)))))
+    # "mixed": three of four groups compact, one plain -- the bus carries what the cores cannot write in time
+    kinds = ["compact", "compact", "compact", "plain"] if transport == "mixed" else [transport] * ring
+    ring = len(kinds)
     try:
-        hosts = [[thg.HostBatches(HB, cap_n, cap_e, S, device, fill=0.8, transport=transport, threads=threads)
-                  for _ in range(ring)] for _ in plans]
+        hosts = [[thg.HostBatches(HB, cap_n, cap_e, S, device, fill=0.8, transport=k, threads=threads)
+                  for k in kinds] for _ in plans]
     except RuntimeError as e:
         log(f"[bench] could not pin host output buffers: {e}")
         return None
@@ -550,6 +554,9 @@ def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, ca
         path += (f"transport=compact: tchgeo_pack_transport packs i32 samples / edge positions and one u8 edge count per "
                  f"node, three D2H copies into pinned staging, then tchgeo_host_unpack_transport rebuilds the reference's "
                  f"i64 samples / cols / edge_index in host memory with {threads} threads (inside the timed region)")
+    elif transport == "mixed":
+        path += (f"transport=mixed: three of every four groups travel compact (i32 ids + u8 edge counts, rebuilt by {threads} "
+                 f"host threads inside the timed region), the fourth as packed i64 vectors straight into pinned memory")
     elif transport == "hybrid":
         path += (f"transport=hybrid: edge_index travels as packed i64 straight into its pinned vector; samples travel as "
                  f"i32 and cols as one u8 edge count per node (tchgeo_pack_transport) and tchgeo_host_unpack_transport "
@@ -1287,7 +1294,7 @@ def main():
                     help="partitioned workload, fixed protocol: segment size as a multiple of the mean per-pair load")
     ap.add_argument("--walkers", type=int, default=0, help="walk workload: number of walkers (0 = 10 per node)")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--e2e-transport", choices=["all", "plain", "compact", "hybrid"], default="all",
+    ap.add_argument("--e2e-transport", choices=["all", "plain", "compact", "hybrid", "mixed"], default="all",
                     help="SampledBatches.to_host transport(s) to time for the e2e number")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
