@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(TEMPO_THREADS, 4) tempo_walk_thread_kernel(con
   const int64_t lo_w = i_ts + p.w0, hi_w = i_ts + p.w1;  // Range: lo_w <= t < hi_w
   if (mine) { row[0] = cur; row_ts[0] = i_ts; }
   bool dead = !mine, bad = false;
+  const bool vec_ok = ((reinterpret_cast<uintptr_t>(p.col_indices) | reinterpret_cast<uintptr_t>(p.edge_ts)) & 31u) == 0;
   for (int64_t l = 0; l + 1 < p.L; ++l) {
     int64_t next = -1, next_ts = -1, b = 0, e = 0;
     uint32_t npass = 0;
@@ -354,19 +355,29 @@ __global__ void __launch_bounds__(TEMPO_THREADS, 4) tempo_walk_thread_kernel(con
     if (!dead && !heavy) {
       Philox4 r{0u, 0u, 0u, 0u};
       uint32_t rblk = 0xFFFFFFFFu;
-      // four neighbours' ids and timestamps are loaded before the first is looked at: the loop is otherwise one DRAM
-      // latency per neighbour and thread
-      for (int64_t ep0 = b; ep0 < e; ep0 += 4) {
+      // The adjacency is read in ALIGNED groups of four neighbours (one 32-byte sector of ids, one of timestamps), all
+      // of a group's loads issued before its first neighbour is looked at: every sector is fetched by one pair of
+      // 16-byte loads instead of surviving four loop iterations in an L1 that a thousand such streams overflow.
+      for (int64_t g = b & ~(int64_t)3; g < e; g += 4) {
         int64_t nd[4], tt[4];
+        if (vec_ok && g >= b && g + 4 <= e) {
+          const longlong2 c0 = __ldg(reinterpret_cast<const longlong2*>(p.col_indices + g));
+          const longlong2 c1 = __ldg(reinterpret_cast<const longlong2*>(p.col_indices + g) + 1);
+          const longlong2 t0 = __ldg(reinterpret_cast<const longlong2*>(p.edge_ts + g));
+          const longlong2 t1 = __ldg(reinterpret_cast<const longlong2*>(p.edge_ts + g) + 1);
+          nd[0] = c0.x; nd[1] = c0.y; nd[2] = c1.x; nd[3] = c1.y;
+          tt[0] = t0.x; tt[1] = t0.y; tt[2] = t1.x; tt[3] = t1.y;
+        } else {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const bool in = ep0 + u < e;
-          nd[u] = in ? __ldg(p.col_indices + ep0 + u) : -1;
-          tt[u] = in ? __ldg(p.edge_ts + ep0 + u) : 0;
+          for (int u = 0; u < 4; ++u) {
+            const bool in = g + u >= b && g + u < e;
+            nd[u] = in ? __ldg(p.col_indices + g + u) : -1;
+            tt[u] = in ? __ldg(p.edge_ts + g + u) : 0;
+          }
         }
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          if (ep0 + u >= e) break;
+          if (g + u < b || g + u >= e) continue;
           const int64_t node = nd[u];
           int64_t ts = tt[u];
           if (ts == -1) {  // NAN_TIMESTAMP: fall back to the neighbour's own timestamp, :118-122

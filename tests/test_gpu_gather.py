@@ -92,7 +92,10 @@ def test_compact_host_transport_lands_the_same_vectors(thg, transport, threads):
     seeds = torch.randint(0, n, (B, S), device="cuda")
     ts = torch.randint(0, 100, (idx.numel(),), device="cuda")
     flt = thg.TemporalEdgeFilter((0, 30), ts, True, thg.TEMPORAL_SAMPLE_STATIC)
+    w = torch.rand(idx.numel(), dtype=torch.float64, device="cuda") + 0.1
     for plan, kw in ((thg.HomogenousSampler(ptrs, idx, B, S, [7, 5, 3]), {}),
+                     (thg.HomogenousSampler(ptrs, idx, B, S, [4, 9], sampler=thg.UniformEdgeSampler(True)), {}),
+                     (thg.HomogenousSampler(ptrs, idx, B, S, [6, 4], sampler=thg.WeightedEdgeSampler(w)), {}),
                      (thg.HomogenousSampler(ptrs, idx, B, S, [7, 5], filter=flt),
                       {"inputs_state": torch.zeros((B, S), dtype=torch.int64, device="cuda")})):
         res = plan.sample(seeds, seed=5, **kw)

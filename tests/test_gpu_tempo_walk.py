@@ -75,6 +75,11 @@ def test_warp_per_walker_form_gives_the_same_walks(thg, fakedataset, monkeypatch
     want = O.tempo_random_walk(rp, ci, nts, ets, start, sts, 11, (0, 15), seed=5)
     for x, y, w in zip(a, b, want):
         assert (x == y).all() and (x == w).all()
+    # adjacency arrays that are only 8-byte aligned: the thread-per-walker kernel then reads them element by element
+    monkeypatch.delenv("TCHGEO_TEMPO_WALK")
+    pad = lambda v: torch.cat([torch.zeros(1, dtype=torch.int64, device="cuda"), dev(v)])[1:]
+    w2, t2 = thg.tempo_random_walk(dev(rp), pad(ci), dev(nts), pad(ets), dev(start), dev(sts), 11, (0, 15), seed=5)
+    assert (w2.cpu().numpy() == want[0]).all() and (t2.cpu().numpy() == want[1]).all()
 
 
 def test_distribution_vs_sequential_oracle(thg, karate):
