@@ -186,6 +186,46 @@ int main(int argc, char** argv) {
       fprintf(stderr, "sampling / relabel mismatch in repetition %d\n", rep);
       return 20;
     }
+    // compact host transport: i32 ids + one u8 edge count per node on the bus, the i64 vectors rebuilt on the host
+    // (fan-out > 255 cannot travel this way; karate's 17 and fakedataset's maximum degree can)
+    if (maxdeg <= 255) {
+      int64_t n_tot = 0, e_tot = 0;
+      for (int64_t b = 0; b < B; ++b) { n_tot += slen[b]; e_tot += elen[b]; }
+      int64_t *d_nl = dmalloc<int64_t>(B), *d_el = dmalloc<int64_t>(B), *d_noff = dmalloc<int64_t>(B + 1), *d_eoff = dmalloc<int64_t>(B + 1);
+      int32_t *d_s32 = dmalloc<int32_t>(n_tot + 1), *d_e32 = dmalloc<int32_t>(e_tot + 1), *d_terr = dmalloc<int32_t>(1);
+      uint8_t* d_cnt = dmalloc<uint8_t>(n_tot + 1);
+      CK(cudaMemcpyAsync(d_nl, slen, B * 8, cudaMemcpyHostToDevice, stream));
+      CK(cudaMemcpyAsync(d_el, elen, B * 8, cudaMemcpyHostToDevice, stream));
+      CK(cudaMemsetAsync(d_terr, 0, 4, stream));
+      TG(tchgeo_pack_transport(d_samples, cap_n, d_cols, d_eidx, cap_e, d_nl, d_el, B, cap_n, cap_e, d_s32, d_e32, d_cnt, n_tot,
+                               d_noff, d_eoff, d_terr, stream));
+      std::vector<int32_t> h32(n_tot + 1), he32(e_tot + 1);
+      std::vector<uint8_t> hcnt(n_tot + 1);
+      std::vector<int64_t> noff(B + 1), eoff(B + 1);
+      int32_t terr = -1;
+      CK(cudaMemcpyAsync(h32.data(), d_s32, n_tot * 4, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(he32.data(), d_e32, e_tot * 4, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(hcnt.data(), d_cnt, n_tot, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(noff.data(), d_noff, (B + 1) * 8, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(eoff.data(), d_eoff, (B + 1) * 8, cudaMemcpyDeviceToHost, stream));
+      CK(cudaMemcpyAsync(&terr, d_terr, 4, cudaMemcpyDeviceToHost, stream));
+      CK(cudaStreamSynchronize(stream));
+      if (tchgeo_status_from_error_word((uint32_t)terr) != TCHGEO_OK || noff[B] != n_tot || eoff[B] != e_tot) return 22;
+      std::vector<int64_t> us(n_tot + 1), uc(e_tot + 1), ue(e_tot + 1);
+      TG(tchgeo_host_unpack_transport(h32.data(), he32.data(), hcnt.data(), noff.data(), eoff.data(), B, us.data(), uc.data(),
+                                      ue.data(), 2));
+      for (int64_t b = 0; b < B; ++b) {
+        for (int64_t i = 0; i < slen[b]; ++i) bad += us[noff[b] + i] != hs[b * cap_n + i];
+        for (int64_t i = 0; i < elen[b]; ++i)
+          bad += (uc[eoff[b] + i] != hc[b * cap_e + i]) + (ue[eoff[b] + i] != he[b * cap_e + i]);
+      }
+      if (bad) {
+        fprintf(stderr, "compact transport mismatch in repetition %d\n", rep);
+        return 23;
+      }
+      cudaFree(d_nl); cudaFree(d_el); cudaFree(d_noff); cudaFree(d_eoff); cudaFree(d_s32); cudaFree(d_e32); cudaFree(d_terr);
+      cudaFree(d_cnt);
+    }
   }
   // error path: an out-of-range seed is reported by collect, and the plan stays usable
   const int64_t bad_seeds[B * S] = {0, 1, 4, 5, 33, 33, 2, 33, 9, 11, 12, N + 5};
@@ -194,7 +234,7 @@ int main(int argc, char** argv) {
   if (tchgeo_plan_collect(plan) != TCHGEO_ERR_INDEX) return 21;
   tchgeo_plan_destroy(plan);
   tchgeo_graph_destroy(graph);
-  printf("abi_harness ok: to_csc, graph handle, plan handle (enqueue/collect x2), 2-hop full-neighbourhood sampling and "
-         "relabel of %lld batches match the host restatement\n", (long long)B);
+  printf("abi_harness ok: to_csc, graph handle, plan handle (enqueue/collect x2), 2-hop full-neighbourhood sampling, "
+         "relabel and the compact host transport of %lld batches match the host restatement\n", (long long)B);
   return 0;
 }
