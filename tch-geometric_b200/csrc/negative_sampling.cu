@@ -171,7 +171,7 @@ struct NegPlan {
   std::vector<int64_t> id_bound;    // [T] what the relabel stage may assume about the type's ids (0: any i64)
   bool prefer_waves = true;
   size_t off_cnts = 0;              // device counters: accepted[T] | seq_len[T] | nodes_len[T] | edges_len[R]
-  size_t off_hdr, off_rels, off_rel_dst, off_cand, off_crel, off_tpos, off_flags, off_ranks, off_seq, off_local, off_cub,
+  size_t off_hdr, off_rels, off_rel_dst, off_cand, off_crel, off_tpos, off_ranks, off_seq, off_local, off_cub,
       off_rl, total;
 };
 
@@ -257,7 +257,6 @@ tchgeo_status neg_plan(const tchgeo_negative_args* a, NegPlan& P, bool layout = 
   P.off_cand = o; o += up(g * 8);
   P.off_crel = o; o += up(g * 4);
   P.off_tpos = o; o += up(g * 4);
-  P.off_flags = o; o += up(g * 4);
   P.off_ranks = o; o += up(g * 4);
   P.off_seq = o; o += up(sq * 8);
   P.off_local = o; o += up(sq * 8);
