@@ -51,7 +51,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-Xlinker", "--exclude-libs,ALL", "-lpthread"]
+        cmd = [NVCC, "-shared", "-Wno-deprecated-gpu-targets", "-o", OUT] + objs + ["-ccbin", "/usr/bin/g++", "-Xlinker", "--exclude-libs,ALL", "-lpthread"]
         subprocess.check_call(cmd)
     return OUT
 
