@@ -8,7 +8,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtchgeo_cuda.so")
+# TCHGEO_LIB: another build of the same ABI (A/B measurements of two kernel versions on one box)
+LIB_PATH = os.environ.get("TCHGEO_LIB") or os.path.join(_HERE, "libtchgeo_cuda.so")
 
 OK, ERR_BAD_ARG, ERR_CUDA, ERR_CAPACITY, ERR_INDEX, ERR_REFERENCE_PANIC, ERR_INTERNAL = range(7)
 SAMPLER_UNIFORM, SAMPLER_UNIFORM_REPLACE, SAMPLER_WEIGHTED = 0, 1, 2
