@@ -1,4 +1,5 @@
-# gpurun (1 GPU): the three things the driver runs at round end -- GPU tests, smoke(), the default bench line
+# gpurun (1 GPU): the three things the driver runs at round end -- GPU tests, smoke(), the default bench line -- and the
+# temporal-filter lines after the last kernel change
 O=gpurun_out/r2check; mkdir -p $O
 python -m pytest tests -m gpu -q > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -4 $O/gpu_tests.log
 python __graft_entry__.py smoke > $O/smoke.log 2>&1; tail -1 $O/smoke.log
@@ -12,3 +13,7 @@ print('value %.2f G, %.3f ms, frac %.3f | e2e %s %.3f G (%.1f ms) others %s | re
   [(o['transport'], round(o['value']/1e9,3)) for o in e.get('other_transports',[])], d['with_relabel']['relabel_ms_per_step'],
   d['walk_steps_per_sec']/1e9, d['hetero_edges_per_sec']/1e9, d['cpu_baseline']['value']/1e6))
 PY
+for f in static relative dynamic; do python bench.py --workload temporal --filter $f --steps 5 --warmup 3 > $O/bench_temporal_$f.json 2> /dev/null
+python -c "
+import json; d=json.load(open('$O/bench_temporal_$f.json')); print('temporal $f: %.3f ms/step, %.2f G edges/s, frac %.3f, cpu %.1f M' % (d['ms_per_step'], d['value']/1e9, d['roofline']['frac'], d['cpu_baseline']['value']/1e6))"
+done
