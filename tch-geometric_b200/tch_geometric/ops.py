@@ -576,7 +576,13 @@ class HostBatches:
         devb = lambda n, dt=torch.int64: torch.empty(n, dtype=dt, device=device)
         self._d_lens = devb(2 * self.B)
         self._d_off = devb(2 * (self.B + 1))
-        self._h_lens = host(2 * self.B)
+        # the lengths of a group reach the device by an asynchronous copy out of pinned memory: the source must stay
+        # untouched until the copy has RUN, so consecutive transfers rotate through four small buffers, each guarded
+        # by an event (one buffer would be overwritten by the next group while its copy still waits behind the
+        # previous group's transfers)
+        self._h_lens_ring = [host(2 * self.B) for _ in range(4)]
+        self._h_lens_events = [None] * 4
+        self._h_lens_next = 0
         self.n_off = self.e_off = None       # host offsets [count + 1] of the last to_host
         self.nbytes = 0
         self._pending = None
@@ -637,13 +643,20 @@ def packed_to_host(samples, cols, edge_index, samples_len, edges_len, cap_n, cap
     e_off = np.ascontiguousarray(np.concatenate([[0], np.cumsum(ne)]), dtype=np.int64)
     if n_off[-1] > host.cap_n or e_off[-1] > host.cap_e:
         raise MemoryError("HostBatches too small for this group: create it with a larger `fill`")
-    h = host._h_lens
+    slot = host._h_lens_next
+    host._h_lens_next = (slot + 1) % len(host._h_lens_ring)
+    if host._h_lens_events[slot] is not None:
+        host._h_lens_events[slot].synchronize()      # four transfers ago: long done
+    h = host._h_lens_ring[slot]
     h[:count].copy_(torch.from_numpy(np.ascontiguousarray(ns)))
     h[host.B:host.B + count].copy_(torch.from_numpy(np.ascontiguousarray(ne)))
     nt, et = int(n_off[-1]), int(e_off[-1])
     with torch.cuda.device(device):
         stream = _stream(device)
         host._d_lens.copy_(h, non_blocking=True)
+        if host._h_lens_events[slot] is None:
+            host._h_lens_events[slot] = torch.cuda.Event()
+        host._h_lens_events[slot].record(torch.cuda.current_stream(device))
         if compact:
             host._d_err.zero_()
             N.check(N.lib.tchgeo_pack_transport(_ptr(samples[first]), samples.shape[1], _ptr(cols[first]),
