@@ -539,13 +539,21 @@ def run_e2e(thg, plans, streams, host_seeds, B, S, K, W, world, rank, device, ca
     torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t0) * 1e3
     ms = max(start.elapsed_time(stop), wall_ms)
-    # spot check of the landing zone: the last group of the last drained plan equals the device result
+    # check of the landing zones: every group of the last drained step that is still resident (the last `ring` groups)
+    # equals the device result -- first and last batch of the group, all three vectors
     last = plans[(K - 1) & 1]._call
-    got = hosts[(K - 1) & 1][((B - 1) // HB) % ring].batch(0)
-    b = (B - 1) // HB * HB
-    ne = int(last.edges_len[b, 0])
-    ok = bool(torch.equal(got[0], last.samples[0][b, :int(last.samples_len[b, 0])].cpu())
-              and torch.equal(got[2], last.cols[0][b, :ne].cpu()) and torch.equal(got[3], last.eidx[0][b, :ne].cpu()))
+    groups = list(range(0, B, HB))
+    ok = True
+    for gi in range(max(0, len(groups) - ring), len(groups)):
+        hz = hosts[(K - 1) & 1][gi % ring]
+        cnt = min(HB, B - groups[gi])
+        for i in (0, cnt - 1):
+            b = groups[gi] + i
+            got = hz.batch(i)
+            ne = int(last.edges_len[b, 0])
+            ok = ok and bool(torch.equal(got[0], last.samples[0][b, :int(last.samples_len[b, 0])].cpu())
+                             and torch.equal(got[2], last.cols[0][b, :ne].cpu())
+                             and torch.equal(got[3], last.eidx[0][b, :ne].cpu()))
     ms, edges_all = reduce_job(ms, float(edges), device)
     path = ("HomogenousSampler.sample_async(pinned host seeds) on two plans / two streams + SampledBatches.to_host per "
             "group of 64 batches; rows = arange(S, S+E) is served from a cached host arange (neighbor_sampling.rs:210-218) "

@@ -1,5 +1,6 @@
-# gpurun (1 GPU): e2e with every host transport
+# gpurun (1 GPU): host-transfer tests and the e2e number with every transport
 O=gpurun_out/r2t; mkdir -p $O
+python -m pytest tests -m gpu -x -q -k "gather or transport or harness or partitioned" > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -4 $O/gpu_tests.log
 timeout 600 python bench.py --headline-only --no-cpu --steps 10 --warmup 3 > $O/bench.json 2> $O/bench.err; tail -3 $O/bench.err
 python - <<'PY'
 import json
