@@ -770,7 +770,7 @@ cudaError_t rp_enqueue(const int64_t* samples, int64_t stride, const int64_t* le
 // TCHGEO_RELABEL_PERSISTENT=1 selects the global-table form.
 // =================================================================================================
 constexpr int BK_THREADS = 512;
-constexpr int BK_ITEMS = 8;
+constexpr int BK_ITEMS = 16;
 constexpr int BK_TILE = BK_THREADS * BK_ITEMS;    // ids per CTA in the count / scatter kernels
 constexpr int BK_RTHREADS = 128;                  // resolve: threads per bucket (many short CTAs in flight)
 constexpr int BK_MAX_BUCKETS = 4096;              // shared-memory histogram
@@ -918,52 +918,46 @@ __global__ void __launch_bounds__(256) bk_offsets_kernel(const BkParams p) {
 }
 
 // ---- scatter: (id, position) pairs grouped by bucket ---------------------------------------------------------------
+// (the form for unpacked pairs: hashed buckets, or direct ones whose slot and position do not fit one word.)  The tile
+// scan left in tile_hist the number of ids every bucket received from earlier tiles, so the tile's cursors start at
+// their final places and a shared-memory atomicAdd hands out the slots; the order inside a bucket is whatever the
+// atomics make it, which the resolve kernel (a minimum per id) does not see.
 template <int MODE>
 __global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p) {
-  __shared__ uint32_t s_hist[BK_MAX_BUCKETS];   // rank counters of the tile, then the tile's base in every bucket
+  __shared__ uint32_t s_cur[BK_MAX_BUCKETS];
   const int b = blockIdx.y, tid = threadIdx.x;
   const int64_t n = bk_len(p, b);
   const int64_t i0 = (int64_t)blockIdx.x * BK_TILE;
   if (i0 >= n) return;
-  for (int j = tid; j < p.nb; j += BK_THREADS) s_hist[j] = 0u;
-  __syncthreads();
-  const int64_t* src = p.samples + (int64_t)b * p.stride;
-  uint32_t key[BK_ITEMS], rnk[BK_ITEMS];
-  bool ok[BK_ITEMS];
-  int64_t k64[BK_ITEMS];
-#pragma unroll
-  for (int u = 0; u < BK_ITEMS; ++u) {
-    const int64_t i = i0 + u * BK_THREADS + tid;
-    k64[u] = i < n ? __ldg(src + i) : 0;
-  }
-#pragma unroll
-  for (int u = 0; u < BK_ITEMS; ++u) {
-    const int64_t i = i0 + u * BK_THREADS + tid;
-    ok[u] = false;
-    key[u] = 0u; rnk[u] = 0u;
-    if (i >= n) continue;
-    if ((uint64_t)k64[u] >= (uint64_t)p.id_bound) {
-      p.win[(size_t)b * p.n_max + i] = BK_NONE;   // reported by the count kernel
-      continue;
-    }
-    p.win[(size_t)b * p.n_max + i] = (uint32_t)i;  // "its own winner" until bk_resolve says otherwise (coalesced here,
-    ok[u] = true;                                  // so that the resolve kernel scatters the exceptions only)
-    key[u] = (uint32_t)k64[u];
-    rnk[u] = atomicAdd(&s_hist[bk_bucket<MODE>(key[u], p.log2_nb)], 1u);   // rank inside the tile's share of the bucket
-  }
-  __syncthreads();
   const uint32_t* row = p.tile_hist + ((size_t)b * p.tiles_per_tree + blockIdx.x) * p.nb;
   const uint32_t* seg = p.seg_tot + ((size_t)b * p.segs + blockIdx.x / p.tiles_per_seg) * p.nb;
   for (int j = tid; j < p.nb; j += BK_THREADS)
-    s_hist[j] = p.offs[(size_t)b * p.nb + j] + (p.segs > 1 ? seg[j] : 0u) + row[j];
+    s_cur[j] = p.offs[(size_t)b * p.nb + j] + (p.segs > 1 ? seg[j] : 0u) + row[j];
   __syncthreads();
+  const int64_t* src = p.samples + (int64_t)b * p.stride;
+  uint2* dst = reinterpret_cast<uint2*>(p.pairs) + (size_t)b * p.n_max;
+  constexpr int G = 8;                               // ids requested before the first is placed
+#pragma unroll 1
+  for (int u0 = 0; u0 < BK_ITEMS; u0 += G) {
+    int64_t k64[G];
 #pragma unroll
-  for (int u = 0; u < BK_ITEMS; ++u) {
-    if (!ok[u]) continue;
-    const uint32_t i = (uint32_t)(i0 + u * BK_THREADS + tid);
-    const size_t at = (size_t)b * p.n_max + s_hist[bk_bucket<MODE>(key[u], p.log2_nb)] + rnk[u];
-    if (MODE == BK_PACKED) reinterpret_cast<uint32_t*>(p.pairs)[at] = ((key[u] >> p.log2_nb) << p.pos_bits) | i;
-    else reinterpret_cast<uint2*>(p.pairs)[at] = make_uint2(key[u], i);
+    for (int u = 0; u < G; ++u) {
+      const int64_t i = i0 + (int64_t)(u0 + u) * BK_THREADS + tid;
+      k64[u] = i < n ? __ldg(src + i) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < G; ++u) {
+      const int64_t i = i0 + (int64_t)(u0 + u) * BK_THREADS + tid;
+      if (i >= n) continue;
+      if ((uint64_t)k64[u] >= (uint64_t)p.id_bound) {
+        p.win[(size_t)b * p.n_max + i] = BK_NONE;    // reported by the count kernel
+        continue;
+      }
+      p.win[(size_t)b * p.n_max + i] = (uint32_t)i;  // "its own winner" until bk_resolve says otherwise (coalesced here,
+      const uint32_t key = (uint32_t)k64[u];         // so that the resolve kernel scatters the exceptions only)
+      const uint32_t at = atomicAdd(&s_cur[bk_bucket<MODE>(key, p.log2_nb)], 1u);
+      dst[at] = make_uint2(key, (uint32_t)i);
+    }
   }
 }
 
@@ -972,7 +966,7 @@ __global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p
 // phases (ids, ranks, scan, staging, stores) separated by barriers, so what matters is how many CTAs an SM holds to
 // overlap them: 512 threads and <= 40 registers give three (the first version, 1024 threads x 61 registers, ran ONE CTA
 // per SM and was no faster than the unstaged scatter).
-__global__ void __launch_bounds__(BK_THREADS, 3) bk_scatter_staged_kernel(const BkParams p) {
+__global__ void __launch_bounds__(BK_THREADS, 2) bk_scatter_staged_kernel(const BkParams p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   uint32_t* s_start = s_mem;                       // [nb] rank counters, then the bucket's first slot in the staged tile
   uint32_t* s_base = s_mem + p.nb;                 // [nb] bucket's global base minus its first staged slot

@@ -1,10 +1,9 @@
-# gpurun (1 GPU): A/B of two builds (tools/micro/libtchgeo_a.so, _b.so) on the relabel stage, same box
+# gpurun (1 GPU): relabel tests + the stage's time with direct and hashed buckets
 O=gpurun_out/r2misc; mkdir -p $O
-for rep in 1 2; do
-for v in a b; do
-  TCHGEO_LIB=$PWD/tools/micro/libtchgeo_$v.so python bench.py --workload relabel --steps 5 --warmup 3 > $O/ab.json 2> $O/ab.err
-  python -c "
-import json; d=json.load(open('$O/ab.json')); print('$v: relabel %.3f ms' % d['relabel_ms_per_step'])"
-done
-done
-TCHGEO_LIB=$PWD/tools/micro/libtchgeo_b.so python -m pytest tests -m gpu -x -q -k "relabel" > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -3 $O/gpu_tests.log
+python -m pytest tests -m gpu -x -q -k "relabel or negative or harness or fullsize" > $O/gpu_tests.log 2>&1; echo "rc=$?" >> $O/gpu_tests.log; tail -3 $O/gpu_tests.log
+python bench.py --workload relabel --steps 10 --warmup 3 > $O/bench_relabel.json 2> $O/ab.err
+python -c "
+import json; d=json.load(open('$O/bench_relabel.json')); print('direct: relabel %.3f ms, frac %.3f' % (d['relabel_ms_per_step'], d['roofline']['frac']))"
+TCHGEO_RELABEL_DIRECT=0 python bench.py --workload relabel --steps 10 --warmup 3 > $O/bench_relabel_hashed.json 2> $O/ab.err
+python -c "
+import json; d=json.load(open('$O/bench_relabel_hashed.json')); print('hashed: relabel %.3f ms' % d['relabel_ms_per_step'])"
