@@ -45,8 +45,7 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # no-op unless the library is missing or older than its source
         _lib = ctypes.CDLL(_SO)
     return _lib
 
@@ -76,6 +75,27 @@ def philox4x32_10(ctr, key):
     o = (ctypes.c_uint32 * 4)()
     lib().orc_philox4x32_10(c, k, o)
     return [int(x) for x in o]
+
+
+def kat_xoshiro(state, n):
+    st = (ctypes.c_uint64 * 4)(*state)
+    out = (ctypes.c_uint64 * n)()
+    lib().orc_kat_xoshiro(st, ctypes.c_int64(n), out)
+    return [int(x) for x in out]
+
+
+def kat_seed_from_u64(seed):
+    out = (ctypes.c_uint64 * 4)()
+    lib().orc_kat_seed_from_u64(ctypes.c_uint64(seed), out)
+    return [int(x) for x in out]
+
+
+def kat_reduce(seed, kind, n, range_=1, high=1.0):
+    """kind 0: gen_range(0..range_) values; 1: f32 bits of gen_range(0.0..1.0); 2: f64 bits of gen_range(0.0..high)"""
+    out = (ctypes.c_uint64 * n)()
+    lib().orc_kat_reduce(ctypes.c_uint64(seed), ctypes.c_int(kind), ctypes.c_uint64(range_), ctypes.c_double(high),
+                         ctypes.c_int64(n), out)
+    return [int(x) for x in out]
 
 
 def ind2ptr(ind, m):

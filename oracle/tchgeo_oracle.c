@@ -19,8 +19,10 @@
  *     points seed from entropy (src/utils/random.rs:10).  The deterministic regime (fanout >=
  *     degree) is pinned exactly; the stochastic regime is "parity unpinned" at the RNG-stream
  *     level: rand 0.8.5 (SmallRng = xoshiro256++) is an un-vendored dependency (Cargo.lock:619),
- *     restated here from its published algorithm (ORC_RNG_XOSHIRO) without a way to cross-check the
- *     stream.  Distributional parity (the reference's *biased* reservoirs, quirks Q1/Q2) is what
+ *     restated here from its published algorithm (ORC_RNG_XOSHIRO).  The engine and its SplitMix64
+ *     seeding are pinned to their published known-answer vectors (tests/test_oracle.py); what stays
+ *     unpinned is the sequence of draws a whole reference call makes, for which no reference output
+ *     exists to compare with.  Distributional parity (the reference's *biased* reservoirs, quirks Q1/Q2) is what
  *     the tests assert.
  *
  * Two RNG modes
@@ -156,6 +158,31 @@ static inline double xoshiro_gen_f64(orc_rng* r, double high) {
     memcpy(&v12, &bits, 8);
     double res = (v12 - 1.0) * high + 0.0;
     if (res < high) return res;
+  }
+}
+
+/* Known-answer hooks for tests/test_oracle.py: the engine against the vector published with the reference C
+ * implementation of xoshiro256++ (state {1,2,3,4}; the same vector rand 0.8.5 carries as its own unit test), the
+ * SplitMix64 seeding against SplitMix64's published outputs, and the range / float reductions on a given state so
+ * that a test can restate them independently in Python integers. */
+void orc_kat_xoshiro(const uint64_t state[4], int64_t n, uint64_t* out) {
+  orc_rng r;
+  memcpy(r.s, state, sizeof r.s);
+  for (int64_t i = 0; i < n; ++i) out[i] = xoshiro_next_u64(&r);
+}
+void orc_kat_seed_from_u64(uint64_t seed, uint64_t out[4]) {
+  orc_rng r;
+  xoshiro_seed_from_u64(&r, seed);
+  memcpy(out, r.s, sizeof r.s);
+}
+/* kind 0: gen_range(0..range) as u64; 1: gen_range(0.0..1.0) f32 (bits); 2: gen_range(0.0..high) f64 (bits) */
+void orc_kat_reduce(uint64_t seed, int kind, uint64_t range, double high, int64_t n, uint64_t* out) {
+  orc_rng r;
+  xoshiro_seed_from_u64(&r, seed);
+  for (int64_t i = 0; i < n; ++i) {
+    if (kind == 0) out[i] = xoshiro_gen_range_u64(&r, range);
+    else if (kind == 1) { float f = xoshiro_gen_f32(&r); uint32_t b; memcpy(&b, &f, 4); out[i] = b; }
+    else { double d = xoshiro_gen_f64(&r, high); memcpy(&out[i], &d, 8); }
   }
 }
 

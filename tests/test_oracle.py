@@ -22,6 +22,72 @@ def test_philox_known_answers():
         0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
 
 
+def test_xoshiro256pp_known_answers():
+    # the vector published with the reference C implementation (xoshiro256plusplus.c, state {1,2,3,4}); rand 0.8.5's
+    # SmallRng carries the same vector as its own unit test (rand is un-vendored here: Cargo.lock:619)
+    assert O.kat_xoshiro([1, 2, 3, 4], 10) == [
+        41943041, 58720359, 3588806011781223, 3591011842654386, 9228616714210784205, 9973669472204895162,
+        14011001112246962877, 12406186145184390807, 15849039046786891736, 10450023813501588000]
+
+
+def test_seed_from_u64_is_splitmix64():
+    # SplitMix64's published outputs: seed 0 starts 0xE220A8397B1DCDAF; seed 1234567 is the vector of the reference C file
+    assert O.kat_seed_from_u64(0)[:2] == [0xE220A8397B1DCDAF, 0x6E789E6AA1B965F4]
+    assert O.kat_seed_from_u64(1234567) == [6457827717110365317, 3203168211198807973, 9817491932198370423,
+                                            4593380528125082431]
+
+
+class _PyXoshiro:
+    """independent restatement in Python integers of rand 0.8.5's reductions"""
+    M = (1 << 64) - 1
+
+    def __init__(self, seed):
+        self.s = O.kat_seed_from_u64(seed)
+
+    def next_u64(self):
+        s, M = self.s, self.M
+        rotl = lambda x, k: ((x << k) | (x >> (64 - k))) & M
+        out = (rotl((s[0] + s[3]) & M, 23) + s[0]) & M
+        t = (s[1] << 17) & M
+        s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45)
+        return out
+
+    def gen_range(self, rng):       # UniformInt::sample_single: widening multiply, rejection zone
+        zone = ((rng << (64 - rng.bit_length())) & self.M) - 1
+        while True:
+            m = self.next_u64() * rng
+            if (m & self.M) <= zone:
+                return m >> 64
+
+    def gen_f32(self):              # upper 32 bits, 23 mantissa bits
+        while True:
+            v = np.uint32((self.next_u64() >> 32 >> 9) | 0x3F800000).view(np.float32)
+            r = np.float32(v - np.float32(1.0))
+            if r < 1.0:
+                return int(r.view(np.uint32))
+
+    def gen_f64(self, high):        # 52 mantissa bits
+        while True:
+            v = np.uint64((self.next_u64() >> 12) | 0x3FF0000000000000).view(np.float64)
+            r = (v - 1.0) * high
+            if r < high:
+                return int(np.float64(r).view(np.uint64))
+
+
+@pytest.mark.parametrize("rng", [1, 2, 3, 5, 17, 1000, (1 << 33) + 7, (1 << 63) + 12345, 3 << 62])
+def test_gen_range_restatement(rng):
+    py = _PyXoshiro(7)
+    got = O.kat_reduce(7, 0, 200, range_=rng)
+    assert got == [py.gen_range(rng) for _ in range(200)] and max(got) < rng
+
+
+def test_gen_float_restatement():
+    py = _PyXoshiro(9)
+    assert O.kat_reduce(9, 1, 200) == [py.gen_f32() for _ in range(200)]
+    py = _PyXoshiro(11)
+    assert O.kat_reduce(11, 2, 200, high=3.75) == [py.gen_f64(3.75) for _ in range(200)]
+
+
 # ---------------------------------------------------------------------------------------------
 # CSC/CSR build: reference KATs (src/data/storage.rs:153-184) and fixtures
 # ---------------------------------------------------------------------------------------------
