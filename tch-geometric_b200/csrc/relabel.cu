@@ -964,8 +964,9 @@ __global__ void __launch_bounds__(BK_THREADS) bk_scatter_kernel(const BkParams p
 // ---- scatter, packed pairs: the tile is first grouped by bucket in shared memory, then written out in that order --------
 // A warp's store then covers a few runs of consecutive words instead of 32 different sectors.  The kernel is a chain of
 // phases (ids, ranks, scan, staging, stores) separated by barriers, so what matters is how many CTAs an SM holds to
-// overlap them: 512 threads and <= 40 registers give three (the first version, 1024 threads x 61 registers, ran ONE CTA
-// per SM and was no faster than the unstaged scatter).
+// overlap them: 512 threads x 16 ids (a 50 KB staged tile, <= 64 registers) give two, with half as many tiles and tile
+// histogram rows as the 8-id form that held three (3.24 -> 3.16 ms for the whole stage); the first version, 1024 threads
+// x 61 registers, ran ONE CTA per SM and was no faster than the unstaged scatter.
 __global__ void __launch_bounds__(BK_THREADS, 2) bk_scatter_staged_kernel(const BkParams p) {
   extern __shared__ __align__(16) uint32_t s_mem[];
   uint32_t* s_start = s_mem;                       // [nb] rank counters, then the bucket's first slot in the staged tile
