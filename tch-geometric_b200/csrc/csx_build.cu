@@ -8,7 +8,21 @@
 // decoded from the sorted keys, so no random row[perm] / col[perm] gathers are needed.
 // The device-wide radix sort itself is CUB's DeviceRadixSort (library code, like cuBLAS for a plain
 // GEMM); key build, decode and ind2ptr are the kernels below.
+//
+// Second form ("partition form", the default where it applies; TCHGEO_CSX_SORT=cub selects the radix form): no
+// device-wide sort.  The edges are split ONCE into
+// buckets of 2^low_bits consecutive major ids (a few thousand edges each: tile histograms, a scan over tiles, a
+// scatter of packed 8-byte (key, edge id) pairs), and one CTA per bucket finishes its bucket in shared memory:
+// counting sort by major id, then every column's few dozen minor ids are sorted by a warp (bitonic network in
+// registers for <= 32 entries, in shared memory above).  Global traffic is three passes over the edges instead
+// of the radix sort's fourteen.  It applies when the buckets fit (see pt_plan / PT_CAP) and falls back to the
+// radix form otherwise.
+#include <cub/block/block_reduce.cuh>
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
+
+#include <cstdlib>
+#include <cstring>
 
 #include "common.cuh"
 
@@ -16,6 +30,7 @@ namespace tchgeo {
 namespace {
 
 constexpr int CSX_THREADS = 256;
+constexpr bool PT_DEFAULT_ON = true;    // partition form where it applies; TCHGEO_CSX_SORT=cub | partition overrides
 
 __host__ __device__ inline int bits_for(int64_t n) {  // bits needed for values in [0, n)
   int b = 0;
@@ -114,6 +129,423 @@ inline unsigned grid_for(int64_t n) {
   return (unsigned)g;
 }
 
+
+// =================================================================================================
+// Partition form
+// =================================================================================================
+constexpr int PT_THREADS = 1024;                 // count / scatter kernels
+constexpr int PT_ITEMS = 32;
+constexpr int PT_TILE = PT_THREADS * PT_ITEMS;   // edges per CTA of the count / scatter kernels
+constexpr int PT_GROUP = 8;                      // edges requested before the first is used
+constexpr int PT_NB_MAX = 16384;                 // buckets (shared histogram of the count / scatter kernels: 64 KB)
+constexpr int PT_CAP = 12288;                    // edges one bucket may hold (96 KB of 8-byte pairs, two CTAs per SM)
+constexpr int PT_MAX_LOW_BITS = 10;              // <= 1024 major ids per bucket
+constexpr int PT_BTHREADS = 512;                 // bucket kernel
+constexpr int PT_SEGS = 64;                      // the scan over tiles runs per segment of tiles
+constexpr int PT_WARP_MAX = 1024;                // longer columns are sorted by the whole CTA
+constexpr int PT_HEAVY_MAX = 16;                 // > PT_CAP / PT_WARP_MAX
+
+struct PtParams {
+  const int64_t* major;
+  const int64_t* minor;
+  int64_t E, n_major, n_minor;
+  int low_bits, minor_bits, nb, tiles, tiles_per_seg, segs;
+  uint32_t* tile_hist;  // [tiles][nb] edges of the tile per bucket, then (seg prefix) those of earlier tiles of the segment
+  uint32_t* seg_tot;    // [segs][nb] edges of the segment per bucket, then those of earlier segments
+  uint32_t* tot;        // [nb] edges per bucket
+  uint32_t* base;       // [nb] first slot of the bucket
+  uint32_t* stats;      // [0] DEV_ERR_* bits, [1] largest bucket
+  uint2* pairs;         // [E] (major low bits << minor_bits | minor, edge id), grouped by bucket
+  int64_t* ptrs;
+  int64_t* indices;
+  int64_t* perm;
+};
+
+// ---- tile histograms ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(PT_THREADS) pt_count_kernel(const PtParams p) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_hist = s_dyn;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < p.nb; j += PT_THREADS) s_hist[j] = 0u;
+  __syncthreads();
+  const int64_t i0 = (int64_t)blockIdx.x * PT_TILE;
+  bool bad = false;
+#pragma unroll 1
+  for (int u0 = 0; u0 < PT_ITEMS; u0 += PT_GROUP) {
+    int64_t a[PT_GROUP];
+#pragma unroll
+    for (int u = 0; u < PT_GROUP; ++u) {
+      const int64_t i = i0 + (int64_t)(u0 + u) * PT_THREADS + tid;
+      a[u] = i < p.E ? __ldg(p.major + i) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < PT_GROUP; ++u) {
+      const int64_t i = i0 + (int64_t)(u0 + u) * PT_THREADS + tid;
+      if (i >= p.E) continue;
+      if ((uint64_t)a[u] >= (uint64_t)p.n_major) bad = true;   // no slot for it: the scatter kernel skips it as well
+      else atomicAdd(&s_hist[(uint32_t)(a[u] >> p.low_bits)], 1u);
+    }
+  }
+  if (bad) atomicOr(p.stats, DEV_ERR_INDEX);
+  __syncthreads();
+  uint32_t* row = p.tile_hist + (size_t)blockIdx.x * p.nb;
+  for (int j = tid; j < p.nb; j += PT_THREADS) row[j] = s_hist[j];
+}
+
+// ---- scan over tiles, per bucket: inside every segment of tiles, then over the segments, then over the buckets -------
+__global__ void __launch_bounds__(256) pt_seg_prefix_kernel(const PtParams p) {
+  const int j = blockIdx.x * 256 + threadIdx.x, seg = blockIdx.y;
+  if (j >= p.nb) return;
+  const int t0 = seg * p.tiles_per_seg;
+  const int t1 = min(t0 + p.tiles_per_seg, p.tiles);
+  uint32_t run = 0u;
+  int t = t0;
+  for (; t + 4 <= t1; t += 4) {   // four independent loads in flight
+    uint32_t* c = p.tile_hist + (size_t)t * p.nb + j;
+    const uint32_t v0 = c[0], v1 = c[(size_t)p.nb], v2 = c[2 * (size_t)p.nb], v3 = c[3 * (size_t)p.nb];
+    c[0] = run; run += v0;
+    c[(size_t)p.nb] = run; run += v1;
+    c[2 * (size_t)p.nb] = run; run += v2;
+    c[3 * (size_t)p.nb] = run; run += v3;
+  }
+  for (; t < t1; ++t) {
+    uint32_t* c = p.tile_hist + (size_t)t * p.nb + j;
+    const uint32_t v = *c;
+    *c = run;
+    run += v;
+  }
+  p.seg_tot[(size_t)seg * p.nb + j] = run;
+}
+
+__global__ void __launch_bounds__(256) pt_bucket_tot_kernel(const PtParams p) {
+  const int j = blockIdx.x * 256 + threadIdx.x;
+  if (j >= p.nb) return;
+  uint32_t run = 0u;
+  for (int s = 0; s < p.segs; ++s) {
+    uint32_t* c = p.seg_tot + (size_t)s * p.nb + j;
+    const uint32_t v = *c;
+    *c = run;
+    run += v;
+  }
+  p.tot[j] = run;
+}
+
+struct PtMax {
+  __device__ __forceinline__ uint32_t operator()(uint32_t a, uint32_t b) const { return a > b ? a : b; }
+};
+
+__global__ void __launch_bounds__(1024) pt_bucket_scan_kernel(const PtParams p) {   // one CTA
+  typedef cub::BlockScan<uint32_t, 1024> Scan;
+  typedef cub::BlockReduce<uint32_t, 1024> Reduce;
+  __shared__ typename Scan::TempStorage s_scan;
+  __shared__ typename Reduce::TempStorage s_red;
+  const int per = (p.nb + 1023) / 1024;
+  const int j0 = threadIdx.x * per;
+  uint32_t sum = 0u, mx = 0u;
+  for (int k = 0; k < per; ++k)
+    if (j0 + k < p.nb) {
+      const uint32_t v = p.tot[j0 + k];
+      sum += v;
+      mx = v > mx ? v : mx;
+    }
+  uint32_t excl = 0u;
+  Scan(s_scan).ExclusiveSum(sum, excl);
+  for (int k = 0; k < per; ++k)
+    if (j0 + k < p.nb) {
+      p.base[j0 + k] = excl;
+      excl += p.tot[j0 + k];
+    }
+  const uint32_t m = Reduce(s_red).Reduce(mx, PtMax());
+  if (threadIdx.x == 0) p.stats[1] = m;
+}
+
+// ---- scatter: packed pairs grouped by bucket (any order inside a bucket; the bucket kernel sorts) --------------------
+__global__ void __launch_bounds__(PT_THREADS) pt_scatter_kernel(const PtParams p) {
+  extern __shared__ uint32_t s_dyn[];
+  uint32_t* s_cur = s_dyn;
+  const int tid = threadIdx.x;
+  const int tile = blockIdx.x, seg = tile / p.tiles_per_seg;
+  const uint32_t* row = p.tile_hist + (size_t)tile * p.nb;
+  const uint32_t* sg = p.seg_tot + (size_t)seg * p.nb;
+  for (int j = tid; j < p.nb; j += PT_THREADS) s_cur[j] = p.base[j] + sg[j] + row[j];
+  __syncthreads();
+  const int64_t i0 = (int64_t)tile * PT_TILE;
+  const uint32_t low_mask = (1u << p.low_bits) - 1u;
+  const uint32_t minor_mask = (1u << p.minor_bits) - 1u;   // minor_bits <= 31
+  bool bad = false;
+#pragma unroll 1
+  for (int u0 = 0; u0 < PT_ITEMS; u0 += PT_GROUP) {
+    int64_t a[PT_GROUP], b[PT_GROUP];
+#pragma unroll
+    for (int u = 0; u < PT_GROUP; ++u) {
+      const int64_t i = i0 + (int64_t)(u0 + u) * PT_THREADS + tid;
+      a[u] = i < p.E ? __ldg(p.major + i) : 0;
+      b[u] = i < p.E ? __ldg(p.minor + i) : 0;
+    }
+#pragma unroll
+    for (int u = 0; u < PT_GROUP; ++u) {
+      const int64_t i = i0 + (int64_t)(u0 + u) * PT_THREADS + tid;
+      if (i >= p.E) continue;
+      if ((uint64_t)a[u] >= (uint64_t)p.n_major) continue;            // flagged and left out by the count kernel
+      if ((uint64_t)b[u] >= (uint64_t)p.n_minor) bad = true;          // keeps its (masked) slot, the call fails
+      const uint32_t key = (((uint32_t)a[u] & low_mask) << p.minor_bits) | ((uint32_t)b[u] & minor_mask);
+      const uint32_t at = atomicAdd(&s_cur[(uint32_t)(a[u] >> p.low_bits)], 1u);
+      p.pairs[at] = make_uint2(key, (uint32_t)i);
+    }
+  }
+  if (bad) atomicOr(p.stats, DEV_ERR_INDEX);
+}
+
+// ---- bitonic network on a shared-memory array of any length (every comparator puts the larger value at the higher
+// index, so the missing tail of the power-of-two network behaves like +infinity and its comparators are skipped) -----
+template <bool BLOCK>
+__device__ __forceinline__ void pt_bitonic_shared(uint64_t* a, uint32_t len, int tid, int nthreads) {
+  int lp = 0;                                      // log2 of the network's size
+  while ((1u << lp) < len) ++lp;
+  const uint32_t half = (1u << lp) >> 1;           // comparators per step
+  for (int lk = 1; lk <= lp; ++lk) {
+    const uint32_t hk = 1u << (lk - 1);
+    for (uint32_t t = tid; t < half; t += nthreads) {   // mirror step: r-th of a 2^lk block against its r-th from the end
+      const uint32_t first = (t >> (lk - 1)) << lk, r = t & (hk - 1u);
+      const uint32_t lo = first + r, hi = first + (2u * hk - 1u - r);
+      if (hi < len) {
+        const uint64_t x = a[lo], y = a[hi];
+        if (x > y) { a[lo] = y; a[hi] = x; }
+      }
+    }
+    if (BLOCK) __syncthreads(); else __syncwarp();
+    for (int ld = lk - 2; ld >= 0; --ld) {         // half-cleaners at distance 2^ld
+      const uint32_t d = 1u << ld;
+      for (uint32_t t = tid; t < half; t += nthreads) {
+        const uint32_t lo = ((t >> ld) << (ld + 1)) + (t & (d - 1u)), hi = lo + d;
+        if (hi < len) {
+          const uint64_t x = a[lo], y = a[hi];
+          if (x > y) { a[lo] = y; a[hi] = x; }
+        }
+      }
+      if (BLOCK) __syncthreads(); else __syncwarp();
+    }
+  }
+}
+
+// ---- one CTA per bucket: counting sort by major id in shared memory, then every column sorted by minor id ------------
+__global__ void __launch_bounds__(PT_BTHREADS, 2) pt_bucket_kernel(const PtParams p) {
+  extern __shared__ __align__(16) unsigned char s_raw[];
+  typedef cub::BlockScan<uint32_t, PT_BTHREADS> Scan;
+  __shared__ typename Scan::TempStorage s_scan;
+  __shared__ int s_heavy[PT_HEAVY_MAX];
+  __shared__ int s_nheavy;
+  const int ncol = 1 << p.low_bits;
+  uint64_t* s_pair = reinterpret_cast<uint64_t*>(s_raw);        // [PT_CAP] minor << 32 | edge id, grouped by column
+  uint32_t* s_cnt = reinterpret_cast<uint32_t*>(s_pair + PT_CAP);   // [ncol] entries of the column
+  uint32_t* s_off = s_cnt + ncol;                               // [ncol] first slot of the column inside the bucket
+  uint32_t* s_cur = s_off + ncol;                               // [ncol] cursor of the grouping pass
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bkt = blockIdx.x;
+  const uint32_t n = p.tot[bkt], start = p.base[bkt];
+  for (int c = tid; c < ncol; c += PT_BTHREADS) s_cnt[c] = 0u;
+  if (tid == 0) s_nheavy = 0;
+  __syncthreads();
+  const uint2* src = p.pairs + start;
+  for (uint32_t i = tid; i < n; i += 4 * PT_BTHREADS) {        // four keys in flight per thread (first read: DRAM)
+    uint32_t k[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) k[u] = i + u * PT_BTHREADS < n ? src[i + u * PT_BTHREADS].x : 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * PT_BTHREADS < n) atomicAdd(&s_cnt[k[u] >> p.minor_bits], 1u);
+  }
+  __syncthreads();
+  {
+    const int per = (ncol + PT_BTHREADS - 1) / PT_BTHREADS;    // 1 or 2 columns per thread
+    const int c0 = tid * per;
+    uint32_t v[2] = {0u, 0u};
+    for (int k = 0; k < per; ++k)
+      if (c0 + k < ncol) v[k] = s_cnt[c0 + k];
+    uint32_t excl = 0u;
+    Scan(s_scan).ExclusiveSum(v[0] + v[1], excl);
+    for (int k = 0; k < per; ++k) {
+      const int c = c0 + k;
+      if (c >= ncol) break;
+      s_off[c] = excl;
+      s_cur[c] = excl;
+      const int64_t col = ((int64_t)bkt << p.low_bits) + c;
+      if (col < p.n_major) p.ptrs[col] = (int64_t)start + excl;           // ind2ptr (storage.rs:67-101)
+      if (v[k] > (uint32_t)PT_WARP_MAX) s_heavy[atomicAdd(&s_nheavy, 1)] = c;
+      excl += v[k];
+    }
+    if (bkt == p.nb - 1 && tid == 0) p.ptrs[p.n_major] = p.E;
+  }
+  __syncthreads();
+  const uint32_t minor_mask = (1u << p.minor_bits) - 1u;
+  for (uint32_t i = tid; i < n; i += 4 * PT_BTHREADS) {        // second read of the bucket: served by the L2
+    uint2 kv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) kv[u] = i + u * PT_BTHREADS < n ? src[i + u * PT_BTHREADS] : make_uint2(0u, 0u);
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i + u * PT_BTHREADS < n) {
+        const uint32_t at = atomicAdd(&s_cur[kv[u].x >> p.minor_bits], 1u);
+        s_pair[at] = ((uint64_t)(kv[u].x & minor_mask) << 32) | kv[u].y;
+      }
+  }
+  __syncthreads();
+  int64_t* out_i = p.indices + start;
+  int64_t* out_p = p.perm + start;
+  for (int c = warp; c < ncol; c += PT_BTHREADS / 32) {
+    const uint32_t len = s_cnt[c], off = s_off[c];
+    if (len == 0u || len > (uint32_t)PT_WARP_MAX) continue;
+    if (len <= 32u) {   // the column in registers, one entry per lane
+      uint64_t v = (uint32_t)lane < len ? s_pair[off + lane] : ~0ull;
+      uint32_t pw = 1u;
+      while (pw < len) pw <<= 1;
+      for (uint32_t k = 2u; k <= pw; k <<= 1) {
+        {
+          const uint32_t partner = (uint32_t)lane ^ (k - 1u);
+          const uint64_t o = __shfl_sync(0xffffffffu, v, partner);
+          v = ((uint32_t)lane < partner) ? (v < o ? v : o) : (v > o ? v : o);
+        }
+        for (uint32_t d = k >> 2; d >= 1u; d >>= 1) {
+          const uint32_t partner = (uint32_t)lane ^ d;
+          const uint64_t o = __shfl_sync(0xffffffffu, v, partner);
+          v = ((uint32_t)lane < partner) ? (v < o ? v : o) : (v > o ? v : o);
+        }
+      }
+      if ((uint32_t)lane < len) {
+        out_i[off + lane] = (int64_t)(v >> 32);
+        out_p[off + lane] = (int64_t)(v & 0xffffffffull);
+      }
+    } else {
+      pt_bitonic_shared<false>(s_pair + off, len, lane, 32);
+      for (uint32_t i = lane; i < len; i += 32) {
+        const uint64_t v = s_pair[off + i];
+        out_i[off + i] = (int64_t)(v >> 32);
+        out_p[off + i] = (int64_t)(v & 0xffffffffull);
+      }
+    }
+  }
+  __syncthreads();
+  const int nheavy = s_nheavy;
+  for (int h = 0; h < nheavy; ++h) {   // the few columns above PT_WARP_MAX entries: the whole CTA sorts each
+    const int c = s_heavy[h];
+    const uint32_t len = s_cnt[c], off = s_off[c];
+    pt_bitonic_shared<true>(s_pair + off, len, tid, PT_BTHREADS);
+    for (uint32_t i = tid; i < len; i += PT_BTHREADS) {
+      const uint64_t v = s_pair[off + i];
+      out_i[off + i] = (int64_t)(v >> 32);
+      out_p[off + i] = (int64_t)(v & 0xffffffffull);
+    }
+  }
+}
+
+struct PtLayout {
+  int low_bits, nb, tiles, tiles_per_seg, segs;
+  size_t off_stats, off_pairs, off_tile_hist, off_seg_tot, off_tot, off_base, total;
+};
+
+// bytes the partition form can need for E edges, whatever the shape (the workspace query does not know which side is major)
+inline size_t pt_workspace_bound(int64_t E) {
+  const size_t n = (size_t)(E > 0 ? E : 1);
+  return 256 + align_up(n * 8) + align_up(n * 4 + (size_t)PT_NB_MAX * 4) + align_up((size_t)PT_SEGS * PT_NB_MAX * 4) +
+         2 * align_up((size_t)PT_NB_MAX * 4) + 256;
+}
+
+// Whether the partition form applies, and its geometry: buckets of 2^low_bits major ids that hold about half of PT_CAP on
+// average (the largest bucket is checked on the device before the scatter), key = low bits + minor id in 32 bits, the
+// histogram matrix no larger than 4 bytes per edge.
+inline bool pt_plan(int64_t E, int64_t n_major, int minor_bits, PtLayout& L) {
+  if (E <= 0 || n_major <= 0 || minor_bits > 31) return false;
+  const double avg = (double)E / (double)n_major;
+  int low_bits = 0;
+  while (low_bits < PT_MAX_LOW_BITS && low_bits + 1 + minor_bits <= 32 && avg * (double)(2ll << low_bits) <= 0.6 * PT_CAP)
+    ++low_bits;
+  if (avg * (double)(1ll << low_bits) > 0.6 * PT_CAP) return false;   // one major id alone is a bucket's worth
+  const int64_t nb = (n_major + ((int64_t)1 << low_bits) - 1) >> low_bits;
+  if (nb > PT_NB_MAX) return false;
+  const int64_t tiles = (E + PT_TILE - 1) / PT_TILE;
+  if ((size_t)tiles * (size_t)nb > (size_t)E + (size_t)PT_NB_MAX) return false;
+  L.low_bits = low_bits;
+  L.nb = (int)nb;
+  L.tiles = (int)tiles;
+  L.tiles_per_seg = (int)((tiles + PT_SEGS - 1) / PT_SEGS);
+  L.segs = (int)((tiles + L.tiles_per_seg - 1) / L.tiles_per_seg);
+  L.off_stats = 0;
+  L.off_pairs = 256;
+  L.off_tile_hist = L.off_pairs + align_up((size_t)E * 8);
+  L.off_seg_tot = L.off_tile_hist + align_up((size_t)tiles * nb * 4);
+  L.off_tot = L.off_seg_tot + align_up((size_t)L.segs * nb * 4);
+  L.off_base = L.off_tot + align_up((size_t)nb * 4);
+  L.total = L.off_base + align_up((size_t)nb * 4) + 256;
+  return true;
+}
+
+inline bool pt_wanted() {   // TCHGEO_CSX_SORT=partition | cub
+  const char* v = getenv("TCHGEO_CSX_SORT");
+  if (v == nullptr || *v == 0) return PT_DEFAULT_ON;
+  return strcmp(v, "partition") == 0;
+}
+
+// -> TCHGEO_OK with *done = true when the outputs are written, *done = false when the radix form has to run instead
+tchgeo_status csx_partition_form(const int64_t* major, const int64_t* minor, int64_t E, int64_t n_major, int64_t n_minor,
+                                 int minor_bits, int64_t* ptrs, int64_t* indices, int64_t* perm, void* workspace,
+                                 size_t workspace_bytes, cudaStream_t stream, bool* done) {
+  *done = false;
+  PtLayout L;
+  if (!pt_plan(E, n_major, minor_bits, L) || workspace_bytes < L.total) return TCHGEO_OK;
+  const int ncol = 1 << L.low_bits;
+  const size_t hist_smem = (size_t)L.nb * 4;
+  const size_t bucket_smem = (size_t)PT_CAP * 8 + (size_t)ncol * 12;
+  static bool configured[64] = {};   // per device; benign race: the attributes are idempotent
+  int dev = 0;
+  TCHGEO_CUDA_CHECK(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64 || !configured[dev]) {
+    TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(pt_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_NB_MAX * 4));
+    TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(pt_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PT_NB_MAX * 4));
+    TCHGEO_CUDA_CHECK(cudaFuncSetAttribute(pt_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           PT_CAP * 8 + (1 << PT_MAX_LOW_BITS) * 12));
+    if (dev >= 0 && dev < 64) configured[dev] = true;
+  }
+  char* ws = (char*)workspace;
+  PtParams p;
+  p.major = major; p.minor = minor; p.E = E; p.n_major = n_major; p.n_minor = n_minor;
+  p.low_bits = L.low_bits; p.minor_bits = minor_bits; p.nb = L.nb;
+  p.tiles = L.tiles; p.tiles_per_seg = L.tiles_per_seg; p.segs = L.segs;
+  p.stats = (uint32_t*)(ws + L.off_stats);
+  p.pairs = (uint2*)(ws + L.off_pairs);
+  p.tile_hist = (uint32_t*)(ws + L.off_tile_hist);
+  p.seg_tot = (uint32_t*)(ws + L.off_seg_tot);
+  p.tot = (uint32_t*)(ws + L.off_tot);
+  p.base = (uint32_t*)(ws + L.off_base);
+  p.ptrs = ptrs; p.indices = indices; p.perm = perm;
+  TCHGEO_CUDA_CHECK(cudaMemsetAsync(p.stats, 0, 256, stream));
+  pt_count_kernel<<<(unsigned)L.tiles, PT_THREADS, hist_smem, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  const unsigned gb = (unsigned)((L.nb + 255) / 256);
+  pt_seg_prefix_kernel<<<dim3(gb, (unsigned)L.segs), 256, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  pt_bucket_tot_kernel<<<gb, 256, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  pt_bucket_scan_kernel<<<1, 1024, 0, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  uint32_t hstats[2] = {0u, 0u};
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(hstats, p.stats, 8, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  if (hstats[0] != 0u) {
+    *done = true;
+    return status_from_dev_err(hstats[0]);
+  }
+  if (hstats[1] > (uint32_t)PT_CAP) return TCHGEO_OK;   // a bucket does not fit one CTA's shared memory: radix form
+  pt_scatter_kernel<<<(unsigned)L.tiles, PT_THREADS, hist_smem, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  pt_bucket_kernel<<<(unsigned)L.nb, PT_BTHREADS, bucket_smem, stream>>>(p);
+  TCHGEO_CUDA_CHECK(cudaGetLastError());
+  uint32_t herr = 0u;
+  TCHGEO_CUDA_CHECK(cudaMemcpyAsync(&herr, p.stats, 4, cudaMemcpyDeviceToHost, stream));
+  TCHGEO_CUDA_CHECK(cudaStreamSynchronize(stream));
+  *done = true;
+  return status_from_dev_err(herr);
+}
+
 }  // namespace
 }  // namespace tchgeo
 
@@ -132,7 +564,8 @@ extern "C" size_t tchgeo_coo_to_csx_workspace_bytes(int64_t num_edges, int64_t n
   if (num_edges < 0 || n_rows < 0 || n_cols < 0) return 0;
   CsxLayout L;
   if (csx_layout(num_edges, 64, L) != cudaSuccess) return 0;
-  return L.total;
+  const size_t pt = pt_workspace_bound(num_edges);
+  return L.total > pt ? L.total : pt;
 }
 
 extern "C" tchgeo_status tchgeo_coo_to_csx(const int64_t* row, const int64_t* col, int64_t E, int64_t n_rows,
@@ -154,6 +587,13 @@ extern "C" tchgeo_status tchgeo_coo_to_csx(const int64_t* row, const int64_t* co
   const int minor_bits = bits_for(n_minor), major_bits = bits_for(n_major);
   TCHGEO_REQUIRE(minor_bits + major_bits <= 64, "graph too large: (row, col) key needs more than 64 bits");
   const int end_bit = minor_bits + major_bits;
+  TCHGEO_REQUIRE(workspace != nullptr, "workspace is NULL");
+  if (pt_wanted()) {
+    bool done = false;
+    const tchgeo_status st = csx_partition_form(major, minor, E, n_major, n_minor, minor_bits, ptrs, indices, perm,
+                                                workspace, workspace_bytes, stream, &done);
+    if (st != TCHGEO_OK || done) return st;
+  }
   CsxLayout L;
   TCHGEO_CUDA_CHECK(csx_layout(E, end_bit, L));
   TCHGEO_REQUIRE(workspace != nullptr, "workspace is NULL");

@@ -57,6 +57,31 @@ def test_fixtures_bit_exact(thg, karate, fakedataset, fakehetero, csc):
             assert (g.cpu().numpy() == w).all(), (name, size)
 
 
+@pytest.mark.parametrize("csc", [True, False])
+def test_partition_form_equals_radix_form(thg, monkeypatch, csc):
+    """tchgeo_coo_to_csx has two forms (csx_build.cu): buckets of major ids finished in shared memory, and a device-wide
+    radix sort.  Same ptrs / indices / perm, also where the first hands over to the second (a column too long for a
+    bucket) and where a whole CTA sorts one column (> 1024 entries)."""
+    rng = np.random.default_rng(5)
+    fn = thg.to_csc if csc else thg.to_csr
+    flip = (lambda a: a) if csc else (lambda a: a[::-1])
+    hub = np.stack([rng.integers(0, 50_000, 40_000), np.zeros(40_000, dtype=np.int64)])
+    hub[1, :3000] = rng.integers(0, 1000, 3000)                                  # one column of 37 000: radix form takes over
+    heavy = np.stack([rng.integers(0, 50_000, 60_000), rng.integers(0, 6, 60_000) * 100])   # six columns of ~10 000
+    dup = np.stack([rng.integers(0, 40, 200_000), rng.integers(0, 3000, 200_000)])          # many duplicate edges (Q9)
+    skew = np.stack([rng.integers(0, 1_000_000, 300_000), (rng.pareto(1.2, 300_000) * 50).astype(np.int64) % 400_000])
+    for ei, size in ((hub, (50_000, 1000)), (heavy, (50_000, 600)), (dup, (40, 3000)), (skew, (1_000_000, 400_000))):
+        ei, size = np.ascontiguousarray(flip(ei)), flip(size)
+        monkeypatch.setenv("TCHGEO_CSX_SORT", "cub")
+        want = fn(dev(ei), size)
+        monkeypatch.setenv("TCHGEO_CSX_SORT", "partition")
+        got = fn(dev(ei), size)
+        for name, g, w in zip(("ptrs", "indices", "perm"), got, want):
+            assert torch.equal(g, w), (name, size)
+        o = (O.to_csc if csc else O.to_csr)(ei, size)
+        assert all((g.cpu().numpy() == w).all() for g, w in zip(got, o))
+
+
 def test_karate_anchor(thg, karate):
     ei, n = karate
     ptrs, idx, perm = thg.to_csc(dev(ei), n)
