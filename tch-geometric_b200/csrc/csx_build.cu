@@ -328,6 +328,67 @@ __device__ __forceinline__ void pt_bitonic_shared(uint64_t* a, uint32_t len, int
   }
 }
 
+// ---- the same network for a column of up to 32 R entries held in registers: entry r * 32 + lane lives in v[r] of the
+// lane.  Distances below 32 are shuffles inside a register, distances of 32 and more pair two registers of the same
+// lane (no shuffle), and the mirror step of a block wider than a warp pairs register r with r ^ (block / 32 - 1) of lane
+// ^ 31.  Every loop bound is a compile-time constant, so v[] stays in registers. -------------------------------------------
+__device__ __forceinline__ void pt_keep(uint64_t& v, uint64_t o, bool keep_min) {
+  v = keep_min ? (v < o ? v : o) : (v > o ? v : o);
+}
+
+template <int R, int LP>   // a network of 2^LP entries: LP = 5 + log2 R, or fewer stages for a column of <= 2^LP <= 32
+__device__ __forceinline__ void pt_bitonic_regs(uint64_t (&v)[R], int lane) {
+#pragma unroll
+  for (int lk = 1; lk <= LP; ++lk) {
+    if (lk <= 5) {
+      const int m = (1 << lk) - 1;
+      const bool low_side = (lane & (1 << (lk - 1))) == 0;
+#pragma unroll
+      for (int r = 0; r < R; ++r) pt_keep(v[r], __shfl_xor_sync(0xffffffffu, v[r], m), low_side);
+    } else {
+      const int mr = (1 << (lk - 5)) - 1, top = 1 << (lk - 6);
+      uint64_t o[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) o[r] = __shfl_xor_sync(0xffffffffu, v[(r ^ mr) & (R - 1)], 31);
+#pragma unroll
+      for (int r = 0; r < R; ++r) pt_keep(v[r], o[r], (r & top) == 0);
+    }
+#pragma unroll
+    for (int ld = lk - 2; ld >= 0; --ld) {
+      if (ld >= 5) {
+        const int dr = 1 << (ld - 5);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+          if ((r & dr) == 0) {
+            const uint64_t a = v[r], b = v[(r ^ dr) & (R - 1)];
+            v[r] = a < b ? a : b;
+            v[(r ^ dr) & (R - 1)] = a < b ? b : a;
+          }
+      } else {
+        const int m = 1 << ld;
+        const bool low_side = (lane & m) == 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) pt_keep(v[r], __shfl_xor_sync(0xffffffffu, v[r], m), low_side);
+      }
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void pt_sort_column_regs(const uint64_t* col, uint32_t len, int lane, int64_t* out_i,
+                                                    int64_t* out_p) {
+  uint64_t v[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) v[r] = (uint32_t)(r * 32 + lane) < len ? col[r * 32 + lane] : ~0ull;
+  pt_bitonic_regs<R, 5 + (R == 2 ? 1 : R == 4 ? 2 : 3)>(v, lane);
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+    if ((uint32_t)(r * 32 + lane) < len) {
+      out_i[r * 32 + lane] = (int64_t)(v[r] >> 32);
+      out_p[r * 32 + lane] = (int64_t)(v[r] & 0xffffffffull);
+    }
+}
+
 // ---- one CTA per bucket: counting sort by major id in shared memory, then every column sorted by minor id ------------
 __global__ void __launch_bounds__(PT_BTHREADS, 2) pt_bucket_kernel(const PtParams p) {
   extern __shared__ __align__(16) unsigned char s_raw[];
@@ -395,26 +456,21 @@ __global__ void __launch_bounds__(PT_BTHREADS, 2) pt_bucket_kernel(const PtParam
   for (int c = warp; c < ncol; c += PT_BTHREADS / 32) {
     const uint32_t len = s_cnt[c], off = s_off[c];
     if (len == 0u || len > (uint32_t)PT_WARP_MAX) continue;
-    if (len <= 32u) {   // the column in registers, one entry per lane
-      uint64_t v = (uint32_t)lane < len ? s_pair[off + lane] : ~0ull;
-      uint32_t pw = 1u;
-      while (pw < len) pw <<= 1;
-      for (uint32_t k = 2u; k <= pw; k <<= 1) {
-        {
-          const uint32_t partner = (uint32_t)lane ^ (k - 1u);
-          const uint64_t o = __shfl_sync(0xffffffffu, v, partner);
-          v = ((uint32_t)lane < partner) ? (v < o ? v : o) : (v > o ? v : o);
-        }
-        for (uint32_t d = k >> 2; d >= 1u; d >>= 1) {
-          const uint32_t partner = (uint32_t)lane ^ d;
-          const uint64_t o = __shfl_sync(0xffffffffu, v, partner);
-          v = ((uint32_t)lane < partner) ? (v < o ? v : o) : (v > o ? v : o);
-        }
-      }
+    if (len <= 32u) {   // the column in registers, one entry per lane; the network no wider than the column needs
+      uint64_t v[1] = {(uint32_t)lane < len ? s_pair[off + lane] : ~0ull};
+      if (len > 16u) pt_bitonic_regs<1, 5>(v, lane);
+      else if (len > 8u) pt_bitonic_regs<1, 4>(v, lane);
+      else if (len > 4u) pt_bitonic_regs<1, 3>(v, lane);
+      else if (len > 2u) pt_bitonic_regs<1, 2>(v, lane);
+      else if (len > 1u) pt_bitonic_regs<1, 1>(v, lane);
       if ((uint32_t)lane < len) {
-        out_i[off + lane] = (int64_t)(v >> 32);
-        out_p[off + lane] = (int64_t)(v & 0xffffffffull);
+        out_i[off + lane] = (int64_t)(v[0] >> 32);
+        out_p[off + lane] = (int64_t)(v[0] & 0xffffffffull);
       }
+    } else if (len <= 64u) {   // two entries per lane.  (Four and eight per lane, for columns of up to 128 and 256 entries,
+                               // measured SLOWER than the shared-memory network below: 2.06 -> 2.47 ms for this kernel on the
+                               // lognormal products-shaped graph, whose columns of 65..256 entries hold 29 % of the edges.)
+      pt_sort_column_regs<2>(s_pair + off, len, lane, out_i + off, out_p + off);
     } else {
       pt_bitonic_shared<false>(s_pair + off, len, lane, 32);
       for (uint32_t i = lane; i < len; i += 32) {

@@ -59,6 +59,15 @@ def main():
         fn, e_, size = cases[name]
         out["ms"][name] = {f: timed(f, fn, e_, size) for f in ("cub", "partition")}
     out["all_equal"] = all(out["equal"].values())
+    # per-kernel times of one partition-form call (CUPTI through torch.profiler, no replay)
+    from torch.profiler import ProfilerActivity, profile
+    os.environ["TCHGEO_CSX_SORT"] = "partition"
+    fn, e_, size = cases["products_csc"]
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        fn(e_, size)
+        torch.cuda.synchronize()
+    evs = sorted((e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA), key=lambda e: e.time_range.start)
+    out["partition_timeline_us"] = [[e.name.split("(")[0].split("::")[-1][:40], round(e.time_range.end - e.time_range.start, 1)] for e in evs]
     print(json.dumps(out))
 
 
