@@ -90,6 +90,10 @@ TCHGEO_API tchgeo_status tchgeo_ind2ptr(const int64_t* ind /*DEVICE [numel]*/, i
 /* COO -> CSC (csc != 0) or CSR (csc == 0).  perm = argsort(major*size_minor + minor) (stable),   */
 /* ptrs = ind2ptr(major[perm]), indices = minor[perm].  n_rows = size.0, n_cols = size.1.          */
 /* replaces src/data/storage.rs:103-127                                                          */
+/* Two forms give the same three arrays: buckets of consecutive major ids finished in shared       */
+/* memory (the default where the buckets fit), and a device-wide radix sort of (major, minor) keys  */
+/* (everything else; the environment variable TCHGEO_CSX_SORT=cub | partition forces one).  The     */
+/* call synchronises `stream` before it returns (status of the ids it read).                        */
 /* -------------------------------------------------------------------------------------------- */
 TCHGEO_API size_t tchgeo_coo_to_csx_workspace_bytes(int64_t num_edges, int64_t n_rows, int64_t n_cols);
 TCHGEO_API tchgeo_status tchgeo_coo_to_csx(const int64_t* row /*DEVICE [E]*/, const int64_t* col /*DEVICE [E]*/,
