@@ -27,8 +27,10 @@
  *
  * Two RNG modes
  *   ORC_RNG_XOSHIRO : sequential xoshiro256++ consumed in exactly the reference's order
- *                     (faithful restatement; used for the CPU baseline timing and as the
- *                     distributional reference).
+ *                     (restated from rand 0.8.5's published algorithm -- the crate is not under
+ *                     /root/reference; engine, seeding and range reductions are pinned by
+ *                     known-answer tests, the call-level draw sequence cannot be; used for the
+ *                     CPU baseline timing and as the distributional reference).
  *   ORC_RNG_COUNTER : the same serial algorithms, but every draw comes from Philox4x32-10 keyed by
  *                     (seed) and indexed by (frontier position, draw index, batch, relation/tag),
  *                     i.e. the counter layout documented in DESIGN.md "RNG contract".  The CUDA
