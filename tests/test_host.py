@@ -207,6 +207,25 @@ def test_handles_and_partitioned_entries_validate_on_the_host():
     assert lib.tchgeo_pack_ragged(None, 4, None, 1, 70000, 4, None, None, None) == N.ERR_BAD_ARG
 
 
+def test_csx_build_validates_on_the_host():
+    """tchgeo_coo_to_csx / tchgeo_ind2ptr refuse bad sizes and NULL pointers before any CUDA call (no GPU needed)."""
+    lib = N.lib
+    one = ctypes.c_void_p(8)   # never dereferenced: the checks below fail first
+    assert lib.tchgeo_coo_to_csx(one, one, -1, 4, 4, 1, one, one, one, one, 1 << 20, None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_coo_to_csx(one, one, 10, -4, 4, 1, one, one, one, one, 1 << 20, None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_coo_to_csx(one, one, 1 << 32, 4, 4, 1, one, one, one, one, 1 << 20, None) == N.ERR_BAD_ARG
+    assert b"2^32" in lib.tchgeo_last_error()
+    assert lib.tchgeo_coo_to_csx(one, one, 10, 4, 4, 1, None, one, one, one, 1 << 20, None) == N.ERR_BAD_ARG     # ptrs
+    assert lib.tchgeo_coo_to_csx(None, one, 10, 4, 4, 1, one, one, one, one, 1 << 20, None) == N.ERR_BAD_ARG     # row
+    assert lib.tchgeo_coo_to_csx(one, one, 10, 4, 4, 1, one, one, one, None, 0, None) == N.ERR_BAD_ARG           # workspace
+    assert b"workspace" in lib.tchgeo_last_error()
+    assert lib.tchgeo_coo_to_csx(one, one, 10, 1 << 40, 1 << 40, 1, one, one, one, one, 1 << 20, None) == N.ERR_BAD_ARG
+    assert b"64 bits" in lib.tchgeo_last_error()
+    assert lib.tchgeo_coo_to_csx_workspace_bytes(-1, 4, 4) == 0
+    assert lib.tchgeo_ind2ptr(None, 5, 4, one, None) == N.ERR_BAD_ARG
+    assert lib.tchgeo_ind2ptr(one, 5, -1, one, None) == N.ERR_BAD_ARG
+
+
 def test_host_unpack_transport_rebuilds_the_reference_vectors():
     """tchgeo_host_unpack_transport is a pure host function: i32 -> i64 widening and run-length expansion of `cols`,
     any thread count, unaligned destinations, empty batches; inconsistent counts are an error, not garbage."""
